@@ -1,0 +1,140 @@
+/*
+ * sicelore_gpu.h — C ABI of libsicelore_gpu.so, the B200 (sm_100a) drop-in for the barcode / UMI
+ * edit-distance hot path of SiCeLoRe 2.1's NanoporeBC_UMI_finder (scanfastq pass 2, assignumis).
+ *
+ * The reference has no FFI for this path (pure in-process Java); each entry point below replaces one
+ * loop body of the reference and is what a JNI `native` method of a `com.rw.gpu.Native` class binds
+ * (see INTEGRATION.md).  Citations: F! = Jar/NanoporeBC_UMI_finder-2.1.jar, (File.java:Lnnn) = original
+ * source lines recovered from the class files' LineNumberTable.
+ *
+ * Conventions: plain pointers and sizes; the caller owns every buffer; nothing is retained after a call
+ * returns except objects behind the opaque handles; every function returns 0 on success or a negative
+ * SLR_E_* code, with a thread-local message available from slr_last_error().  There is NO CPU fallback:
+ * without a usable CUDA device every compute call fails with SLR_E_NODEVICE.
+ * Thread safety: all entry points may be called concurrently; calls that share one context are
+ * serialised internally per stream slot (see slr_ctx_create `n_streams`).
+ */
+#ifndef SICELORE_GPU_H
+#define SICELORE_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLR_ABI_VERSION 1
+
+enum {
+    SLR_OK = 0,
+    SLR_E_INVALID = -1,      /* bad argument */
+    SLR_E_NODEVICE = -2,     /* no CUDA device / driver: the library never falls back to the CPU */
+    SLR_E_CUDA = -3,         /* a CUDA runtime call failed (message has the detail) */
+    SLR_E_NOMEM = -4,
+    SLR_E_UNSUPPORTED = -5   /* e.g. --bcEditDistance > 2, barcode length != 16 */
+};
+
+typedef struct slr_ctx slr_ctx;           /* one per (process, device) */
+typedef struct slr_bc_table slr_bc_table; /* device-resident search set (whitelist or used-barcode list) */
+
+/* ---- per-read result of Parser.assignBarcode (F!…/analyzers/Parser.class, Parser.java:L244-L311) ------ */
+#define SLR_F_ASSIGNED  1u   /* BC_FOUND: best.ED <= bcEditDistance && (no second || best.ED < second.ED)  (L251-L252) */
+#define SLR_F_EXCEPTION 2u   /* the Java would have thrown for this read (slice too short / non-IUPAC char) */
+#define SLR_F_TIE_UNPIN 4u   /* >= 11 same-hash OneMatch entries: JDK HashMap treeified its bin, tie order not emulated */
+
+typedef struct {
+    uint64_t bc;          /* OneMatch.matchingBC of the best match (2-bit packed, A=0 G=1 C=2 T=3, first base most significant); 0 if unassigned */
+    int32_t  ed;          /* best edit distance over all offsets; -1 = nothing matched */
+    int32_t  ed_second;   /* best ED of a DIFFERENT barcode (read-name field ed_sec=), INT32_MAX = none (L288-L289) */
+    int8_t   offset;      /* OneMatch.offsetFromPredicted of the best match (L275-L276) */
+    int8_t   n_ins;       /* OneMatch.insertions  \  getOffsetForReadEnd() = n_ins - n_del  (BarcodeMatchTester.java:L533) */
+    int8_t   n_del;       /* OneMatch.deletions   /  bcEnd = bcStart -/+ 15 -/+ (n_ins - n_del)  (Parser.java:L278-L279) */
+    int8_t   n_sub;
+    int32_t  rank;        /* CountsRank.rank of bc (L267-L269); -1 if unassigned */
+    uint32_t flags;       /* SLR_F_* */
+} slr_bc_result;          /* 32 bytes */
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+
+/* Replaces nothing in the reference (there is no device there); the JNI shim calls it once from
+ * WorkerReadscanner's constructor (F!…/WorkerReadscanner.class, WorkerReadscanner.java:L186-L190), where the
+ * reference creates its two work-stealing pools.  device < 0 selects the current device.  n_streams = how
+ * many host threads may have a batch in flight at once (the reference's nCPU Parser workers). */
+int  slr_ctx_create(int device, int n_streams, slr_ctx **out);
+void slr_ctx_destroy(slr_ctx *ctx);
+int  slr_ctx_device(const slr_ctx *ctx);
+
+/* ---- search set ------------------------------------------------------------------------------------- */
+
+/* Replaces BarcodesMapForBCfinding (the Long2ObjectOpenHashMap<CountsRank> built at WorkerReadscanner.java:L264-L269
+ * or by getMapFromCellRangerData for --cellRangerBCs) whose keySet() is the searchSet of every
+ * BarcodeMatchTester (Parser.java:L228).  barcodes2bit[i] is the reference's 2-bit `long`; rank[i] may be NULL.
+ * Duplicates keep the first index.  bc_len must be 16 (config.xml:189 cell_bc_length). */
+int  slr_bc_table_create(slr_ctx *ctx, const uint64_t *barcodes2bit, const int32_t *rank, int64_t n, int bc_len,
+                         slr_bc_table **out);
+void slr_bc_table_destroy(slr_bc_table *t);
+int64_t slr_bc_table_size(const slr_bc_table *t);
+
+/* ---- S1: barcode assignment ------------------------------------------------------------------------- */
+
+/* Replaces the body of Parser.assignBarcode from window extraction to the best / second-best decision
+ * (Parser.java:L198-L252) for a whole ReadChunk at once, i.e. 2*plusminus+1 BarcodeMatchTester.doJob runs
+ * per read (BarcodeMatchTester.java:L198-L244) plus the Matches merge.
+ *   ed_max      --bcEditDistance / assignCellBCwithEditDistance (0, 1 or 2)
+ *   plusminus   config.xml:35 testPlusMinusPos (0..4; reference default 2)
+ *   three_prime scantype == THREEP_BARCODE (Parser.java:L205)
+ *   slices      n * stride bytes, ASCII, a piece of getStrandedSeq() per read
+ *   slice_len   valid bytes per slice (<= stride); lens (nullable) overrides it per read
+ *   anchor[i]   0-based index inside slice i of the first base of the offset-0 window:
+ *               3': (adapterpos - 16) - 1 - slice_start,  5': adapterpos - slice_start   (1-based adapterpos, L206-L210)
+ *               needed span: 3' [anchor-plusminus-4, anchor+plusminus+16)   5' [anchor-plusminus, anchor+plusminus+21)
+ *   out         n records, positional
+ * Host pointers; H2D / D2H copies are part of the call. */
+int  slr_bc_assign(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime,
+                   const uint8_t *slices, int stride, int slice_len, const int32_t *lens, const int32_t *anchor,
+                   int64_t n, slr_bc_result *out);
+
+/* Same, all pointers are DEVICE pointers on ctx's device, asynchronous on `stream` (a cudaStream_t cast to
+ * void*, NULL = default stream).  For callers that already keep reads in HBM (bench `value`, multi-batch pipelines). */
+int  slr_bc_assign_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime,
+                       const uint8_t *d_slices, int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor,
+                       int64_t n, slr_bc_result *d_out, void *stream);
+
+/* Replaces the assignedBarcodes2ndPass ConcurrentHashMap<Long, BarcodeCounts> updates (Parser.java:L305-L311,
+ * BarcodeCounts.addCountForEd) that feed BarcodesAssigned.tsv: the table accumulates, on the device, one
+ * counter per (barcode index, ED 0..2) for every assigned read of every slr_bc_assign* call.
+ * counts_out: n_barcodes * 3 int64 (host).  slr_bc_counts_device returns the device buffer itself so that
+ * a multi-GPU driver can all-reduce it (NCCL) before reading it back. */
+int  slr_bc_counts_read(slr_ctx *ctx, const slr_bc_table *t, int64_t *counts_out);
+int  slr_bc_counts_reset(slr_ctx *ctx, slr_bc_table *t);
+int  slr_bc_counts_device(const slr_bc_table *t, int64_t **d_counts, int64_t *n_elems);
+
+/* ---- S2: UMI distance matrices ---------------------------------------------------------------------- */
+
+/* Replaces ClusteringEditDistanceBase.generateDistanceMatrix (F!com/rw/clustering/ClusteringEditDistanceBase.class,
+ * ClusteringEditDistanceBase.java:L168-L259) for ALL (cell, region) jobs of one BAM chunk
+ * (UmiClustering.cluster, UmiClustering.java:L131-L146): per read pair the 3x3 shifted thresholded
+ * Levenshtein distances (calcEditDistances, L297-L350; limitedCompare threshold 4, -1 -> 5) reduced to the
+ * packed BestEditDistance int (L67-L80, L425-L428).
+ *   umis        m * stride bytes; per read umi_len+2 4-bit codes (A=1 G=2 C=4 T=8 N=15 ...,
+ *               NucleicAcidByteCodeBase.java:L45-L78) = getSubSequence(bcEnd, umi_len+2) of the strand-corrected
+ *               X= mini sequence, i.e. the predicted UMI window widened by one base on each side
+ *   umi_len     config.xml:264 umi_length (<= 30)
+ *   job_offsets n_jobs+1 CSR offsets into the reads
+ *   out_offsets n_jobs+1 offsets into `out`; job j writes an n_j x n_j row-major int32 matrix at out_offsets[j]
+ *               (diagonal = the reference's equalityEditDistance, lower triangle = transposed copy) */
+int  slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets,
+                  int64_t n_jobs, int32_t *out, const int64_t *out_offsets);
+int  slr_umi_dist_dev(slr_ctx *ctx, const uint8_t *d_umis, int stride, int umi_len, const int64_t *d_job_offsets,
+                      int64_t n_jobs, int64_t n_reads, int32_t *d_out, const int64_t *d_out_offsets,
+                      int64_t n_out, void *stream);
+
+/* ---- misc ------------------------------------------------------------------------------------------- */
+const char *slr_last_error(void);
+int  slr_abi_version(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+int64_t slr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,137 @@
+"""ctypes binding of the CPU oracle (liborc.so).  TEST INFRASTRUCTURE ONLY — see slr_oracle.h.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+BC_RESULT = np.dtype([("bc", "<u8"), ("ed", "<i4"), ("ed_second", "<i4"), ("offset", "i1"), ("n_ins", "i1"),
+                      ("n_del", "i1"), ("n_sub", "i1"), ("rank", "<i4"), ("flags", "<u4")], align=True)
+assert BC_RESULT.itemsize == 24 or BC_RESULT.itemsize == 32
+
+F_ASSIGNED, F_EXCEPTION, F_TIE_UNPIN = 1, 2, 4
+INT_MAX = 2147483647
+
+
+class Match(C.Structure):
+    _fields_ = [("read_seq", C.c_uint64), ("bc", C.c_uint64), ("ed", C.c_int32), ("offset", C.c_int32),
+                ("n_sub", C.c_int32), ("n_ins", C.c_int32), ("n_del", C.c_int32)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborc.so")
+    src = [os.path.join(_HERE, f) for f in ("slr_oracle.c", "slr_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liborc.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_pack2bit.restype = C.c_uint64
+        L.orc_pack2bit.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        L.orc_revcomp2bit.restype = C.c_uint64
+        L.orc_revcomp2bit.argtypes = [C.c_uint64, C.c_int]
+        L.orc_replace_deg.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+        L.orc_insert_deg.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+        L.orc_delete_byte.restype = C.c_uint64
+        L.orc_delete_byte.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int]
+        L.orc_set_new.restype = C.c_void_p
+        L.orc_set_new.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_set_free.argtypes = [C.c_void_p]
+        L.orc_set_find.restype = C.c_int64
+        L.orc_set_find.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_match_tester.restype = C.c_int
+        L.orc_match_tester.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_int, C.POINTER(Match), C.POINTER(C.c_int64)]
+        L.orc_assign_barcode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
+        L.orc_assign_barcode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                               C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.POINTER(C.c_int64), C.c_int]
+        L.orc_limited_compare.restype = C.c_int
+        L.orc_limited_compare.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int]
+        L.orc_umi_best9.restype = C.c_int32
+        L.orc_umi_best9.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.orc_umi_transpose.restype = C.c_int32
+        L.orc_umi_transpose.argtypes = [C.c_int32]
+        L.orc_umi_equality.restype = C.c_int32
+        L.orc_umi_matrix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+        L.orc_umi_matrix_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_int]
+        _LIB = L
+    return _LIB
+
+
+class BarcodeSet:
+    """Search set (whitelist / used-barcode list) + ranks."""
+
+    def __init__(self, keys, rank=None):
+        self.keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        self.rank = None if rank is None else np.ascontiguousarray(rank, dtype=np.int32)
+        self.h = lib().orc_set_new(self.keys.ctypes.data, len(self.keys))
+
+    def __del__(self):
+        try:
+            lib().orc_set_free(self.h)
+        except Exception:
+            pass
+
+    def find(self, key):
+        return lib().orc_set_find(self.h, int(key))
+
+
+def match_tester(bset, seq, length, ed, skip_full=False, allow_indels=True, post4=None, do_next=True, offset=0):
+    out = (Match * 16)()
+    probes = C.c_int64(0)
+    if post4 is None:
+        pp, pl = None, -1
+    else:
+        arr = np.ascontiguousarray(post4, dtype=np.uint8)
+        pp, pl = arr.ctypes.data, len(arr)
+    n = lib().orc_match_tester(bset.h, int(seq), length, ed, int(skip_full), int(allow_indels), pp, pl, int(do_next),
+                               offset, out, C.byref(probes))
+    if n < 0:
+        return None, probes.value
+    return [dict(read_seq=m.read_seq, bc=m.bc, ed=m.ed, offset=m.offset, n_sub=m.n_sub, n_ins=m.n_ins, n_del=m.n_del)
+            for m in out[:n]], probes.value
+
+
+def assign_barcode_batch(bset, slices, anchor, ed_max, plusminus=2, three_prime=True, bc_len=16, slice_len=None,
+                         n_threads=0):
+    """slices: uint8 [n, stride]; anchor: int32 [n].  Returns (results[BC_RESULT], total_probes)."""
+    slices = np.ascontiguousarray(slices, dtype=np.uint8)
+    anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+    n, stride = slices.shape
+    if slice_len is None:
+        slice_len = stride
+    out = np.zeros(n, dtype=BC_RESULT)
+    assert out.itemsize == 32
+    probes = C.c_int64(0)
+    lib().orc_assign_barcode_batch(bset.h, None if bset.rank is None else bset.rank.ctypes.data, ed_max, plusminus,
+                                   int(three_prime), bc_len, slices.ctypes.data, stride, slice_len, anchor.ctypes.data,
+                                   n, out.ctypes.data, C.byref(probes), n_threads)
+    return out, probes.value
+
+
+def umi_matrix_batch(umis, job_offsets, umi_len=12, n_threads=0):
+    """umis: uint8 [m, umi_len+2] 4-bit codes; job_offsets: int64 [n_jobs+1].  Returns (flat int32, out_offsets)."""
+    umis = np.ascontiguousarray(umis, dtype=np.uint8)
+    job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+    sizes = np.diff(job_offsets)
+    out_offsets = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(sizes * sizes, out=out_offsets[1:])
+    out = np.zeros(int(out_offsets[-1]), dtype=np.int32)
+    lib().orc_umi_matrix_batch(umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(sizes),
+                               out.ctypes.data, out_offsets.ctypes.data, n_threads)
+    return out, out_offsets

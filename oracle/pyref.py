@@ -1,0 +1,420 @@
+"""Second, independent restatement of the reference path (pure Python, object-for-object like the Java).
+
+TEST INFRASTRUCTURE ONLY.  It exists so that the C oracle (slr_oracle.c) is checked by a differently
+structured implementation of the same bytecode: Java objects become Python objects, `long` becomes a
+masked int, java.util.HashMap is modelled with real bucket lists and a real resize().  Slow: use on small
+lists / few windows.  Citations as in slr_oracle.c (F!/T! jars, original .java line numbers).
+"""
+from collections import deque
+
+M64 = (1 << 64) - 1
+
+
+def _shl(x, n):
+    return (x << (n & 63)) & M64
+
+
+def _ushr(x, n):
+    return (x & M64) >> (n & 63)
+
+
+def _sext8(b):
+    return b & M64 if b >= 0 else (b + (1 << 64)) & M64
+
+
+# ---- T!com/rw/nuc/encoding/TwoBit/NucleicAcidTwoBitPerBase ------------------------------------------
+BASE_TO_TWOBIT = [-2] * 254                                   # java:L78-L79
+for ch, v in (("A", 0), ("a", 0), ("G", 1), ("g", 1), ("C", 2), ("c", 2), ("T", 3), ("t", 3)):
+    BASE_TO_TWOBIT[ord(ch)] = v                               # java:L80-L87
+REVERSE_COMP = [3, 2, 1, 0]                                   # java:L72-L76
+CLEAR_BITS = []                                               # java:L89-L100
+_l = (-4) & M64
+for _i in range(32):
+    CLEAR_BITS.append(_l)
+    _l = ((_l << 2) | 3) & M64
+SET_BITS = [[0, 1, 3, 2]]                                     # java:L105-L112
+for _i in range(31):
+    SET_BITS.append([(v << 2) & M64 for v in SET_BITS[-1]])
+
+# ---- T!com/rw/nuc/encoding/NucleicAcidByteCodeBase --------------------------------------------------
+ENCODE = [-1] * 254                                           # java:L45-L46
+for chs, v in (("-", 0), ("Aa", 1), ("Gg", 2), ("Cc", 4), ("Tt", 8), ("Nn", 15), ("Hh", 13), ("Rr", 3), ("Yy", 12),
+               ("Mm", 5), ("Kk", 10), ("Ss", 6), ("Ww", 9), ("Bb", 14), ("Vv", 7), ("Dd", 11)):
+    for ch in chs:
+        ENCODE[ord(ch)] = v                                   # java:L48-L78
+ONEBYTE_RC = [-1] * 16                                        # java:L100-L133
+for a, b in (("-", "-"), ("A", "T"), ("G", "C"), ("C", "G"), ("T", "A"), ("N", "N"), ("H", "D"), ("R", "Y"), ("Y", "R"),
+             ("M", "K"), ("K", "M"), ("S", "S"), ("W", "W"), ("B", "V"), ("V", "B"), ("D", "H")):
+    ONEBYTE_RC[ENCODE[ord(a)]] = ENCODE[ord(b)]
+BYTE_TO_2BITLONG_0 = [0] * 16                                 # java:L92-L98, row 0
+for ch in "AGCT":
+    BYTE_TO_2BITLONG_0[ENCODE[ord(ch)]] = BASE_TO_TWOBIT[ord(ch)]
+
+
+class JavaException(Exception):
+    pass
+
+
+def pack(s):                                                  # getLongHashForSeq java:L183-L187
+    r = 0
+    for ch in s:
+        c = ord(ch) if isinstance(ch, str) else ch
+        if c >= 254:
+            raise JavaException("AIOOBE BASE_TO_TWOBIT_ARRAY")
+        r = (_shl(r, 2) | _sext8(BASE_TO_TWOBIT[c])) & M64
+    return r
+
+
+def revcomp2(seq, L):                                         # java:L477-L484
+    t = 0
+    for _ in range(L):
+        t = _shl(t, 2)
+        t |= REVERSE_COMP[seq & 3]
+        seq = _ushr(seq, 2)
+    return t
+
+
+def replace_deg(seq, pos, L):                                 # java:L228-L234
+    seq &= CLEAR_BITS[L - pos - 1]
+    shift = (L - (pos + 1)) << 1
+    return [seq | _shl(b, shift) for b in range(4)]
+
+
+def insert_deg(h, pos, L):                                    # java:L300-L310
+    shift = (L - pos - 1) << 1
+    upper = _shl(_ushr(h, shift), shift)
+    shift = 64 - shift
+    h = _shl(h, shift)
+    h = _ushr(h, shift + 2)
+    row = SET_BITS[L - (pos + 1) - 1]
+    return [upper | h | row[b] for b in (0, 1, 3, 2)]
+
+
+def delete_byte(h, code4, pos, L):                            # java:L321-L327
+    shift = (L - pos) << 1
+    upper = _shl(_ushr(h, shift), shift)
+    shift = 64 - shift
+    h = _shl(h, shift + 2)
+    h = _ushr(h, shift)
+    if not 0 <= code4 < 16:
+        raise JavaException("AIOOBE BYTE_TO_2BITLONG_ARRAY")
+    return upper | h | BYTE_TO_2BITLONG_0[code4]
+
+
+# ---- F!com/rw/nuc/encoding/TwoBit/LongSeqMutated ------------------------------------------------------
+class LongSeqMutated:
+    __slots__ = ("seq", "L", "unmut", "nSub", "nIns", "nDel", "offset", "posPrev", "posCur", "level")
+
+    def __init__(self, seq, L, offset):                       # java:L61 -> L44-L50
+        self.seq, self.L, self.offset = seq, L, offset
+        self.unmut = None
+        self.nSub = self.nIns = self.nDel = 0
+        self.posPrev = self.posCur = -1
+        self.level = 0
+
+    def copy(self):                                           # java:L68-L77
+        c = LongSeqMutated(self.seq, self.L, self.offset)
+        c.unmut = self.unmut
+        c.nSub, c.nIns, c.nDel = self.nSub, self.nIns, self.nDel
+        c.posPrev, c.posCur, c.level = self.posPrev, self.posCur, self.level
+        return c
+
+
+class OneMatch:                                               # BarcodeMatchTester$Matches$OneMatch
+    def __init__(self, readSeq, ed, offset, bc, L, nSub, nIns, nDel):
+        self.readSeq, self.ed, self.offset, self.bc = readSeq, ed, offset, bc
+        self.L, self.nSub, self.nIns, self.nDel = L, nSub, nIns, nDel
+
+    def jhash(self):                                          # java:L443
+        h = (self.readSeq ^ (self.readSeq >> 32)) & 0xFFFFFFFF
+        return h
+
+    def jequals(self, o):                                     # java:L433-L436
+        return o.readSeq == self.readSeq and o.ed == self.ed and o.offset == self.offset
+
+    def key(self):                                            # compareTo java:L449-L461 is a weak order on this key
+        return (self.ed, 0 if self.offset == 0 else 1)
+
+
+class JHashSet:
+    """java.util.HashSet / HashMap semantics that influence iteration order."""
+
+    def __init__(self):
+        self.table = None
+        self.size = 0
+        self.threshold = 0
+        self.treeified = False
+
+    def _resize(self):
+        if self.table is None:
+            self.table = [[] for _ in range(16)]
+            self.threshold = 12
+            return
+        old = self.table
+        ncap = len(old) * 2
+        self.threshold *= 2
+        self.table = [[] for _ in range(ncap)]
+        for j, chain in enumerate(old):
+            for (h, e) in chain:                              # split keeps relative order
+                self.table[h & (ncap - 1)].append((h, e))
+
+    def add(self, e):
+        hc = e.jhash()
+        h = (hc ^ (hc >> 16)) & 0xFFFFFFFF
+        if self.table is None:
+            self._resize()
+        chain = self.table[h & (len(self.table) - 1)]
+        for (h2, e2) in chain:
+            if h2 == h and e2.jequals(e):
+                return False
+        chain.append((h, e))
+        if len(chain) >= 9:                                   # binCount >= TREEIFY_THRESHOLD - 1
+            if len(self.table) < 64:
+                self._resize()
+            else:
+                self.treeified = True
+        self.size += 1
+        if self.size > self.threshold:
+            self._resize()
+        return True
+
+    def __iter__(self):
+        if self.table is None:
+            return
+        for chain in self.table:
+            for (_, e) in chain:
+                yield e
+
+
+# ---- F!com/rw/nanoporereadscanner/analyzers/BarcodeMatchTester ---------------------------------------
+class BarcodeMatchTester:
+    def __init__(self, seq, L, ed, skipFullMatches, allowIndels, searchSet, offset, post, doNext):
+        self.seq, self.L, self.ed = seq, L, ed
+        self.skipFull, self.allowIndels, self.set = skipFullMatches, allowIndels, searchSet
+        self.offset, self.post, self.doNext = offset, post, doNext
+        self.deque = deque()
+        self.matches = JHashSet()
+        self.probes = 0
+        # NucTwoBitPerBaseEDtesterBase ctor java:L82-L95
+        if ed >= 2:
+            self.tested = set()
+            self.use64 = L >= 14 and L > 16
+        else:
+            self.tested = None
+
+    def _key(self, s):
+        return s if self.use64 else (s & 0xFFFFFFFF)
+
+    def already(self, s):                                     # java:L120
+        return self.tested is not None and self._key(s) in self.tested
+
+    def mark(self, s):                                        # java:L105-L112
+        if self.tested is not None:
+            self.tested.add(self._key(s))
+
+    def check(self, n):                                       # java:L367-L374
+        if self.skipFull and n.unmut == n.seq:
+            return None
+        self.probes += 1
+        if n.seq in self.set:
+            return OneMatch(n.unmut, n.level, n.offset, n.seq, self.L, n.nSub, n.nIns, n.nDel)
+        return None
+
+    def goNext(self, n):                                      # NucTwoBitPerBaseEDtesterBase java:L133-L144
+        if self.ed > n.level:
+            c = n.copy()
+            c.posPrev = n.posCur
+            c.posCur = -1
+            c.level = n.level + 1
+            self.deque.append(c)
+
+    def doJob(self):                                          # java:L198-L244
+        parent = LongSeqMutated(self.seq, self.L, self.offset)
+        parent.unmut = self.seq
+        r = self.check(parent)
+        if r is not None:
+            self.matches.add(r)
+        if self.ed == 0:
+            return self.matches
+        parent.level = 1
+        self.deque.append(parent)
+        Lm1 = self.L - 1
+        while self.deque:
+            cur = self.deque.pop()                            # pollLast
+            cur.posCur += 1
+            if cur.posCur < Lm1:
+                self.deque.append(cur.copy())
+            if cur.posPrev == cur.posCur:
+                continue
+            # substitutions java:L257-L273
+            for s in replace_deg(cur.seq, cur.posCur, self.L):
+                if s != cur.seq and not self.already(s):
+                    n = cur.copy()
+                    n.nSub += 1
+                    n.seq = s
+                    r = self.check(n)
+                    if r is not None:
+                        self.matches.add(r)
+                    if r is not None or self.doNext:
+                        self.goNext(n)
+            if self.allowIndels and cur.posCur < Lm1:
+                # insertions java:L284-L300
+                for s in insert_deg(cur.seq, cur.posCur, self.L):
+                    if not self.already(s):
+                        n = cur.copy()
+                        n.seq = s
+                        n.nDel += 1
+                        r = self.check(n)
+                        if r is not None:
+                            self.matches.add(r)
+                        if r is None or self.doNext:
+                            self.goNext(n)
+                # deletions java:L313-L357
+                if not (self.post is not None and cur.nDel + 1 > len(self.post)):
+                    last = self.post[cur.nDel] if self.post is not None else 0
+                    m = delete_byte(cur.seq, last, cur.posCur, self.L)
+                    cands = [m] if self.post is not None else [m, m | 1, m | 2, m | 3]
+                    for s in cands:
+                        if not self.already(s):
+                            n = cur.copy()
+                            n.seq = s
+                            n.nIns += 1
+                            r = self.check(n)
+                            if r is not None:
+                                self.matches.add(r)
+                            if r is None or self.doNext:
+                                self.goNext(n)
+            self.mark(cur.seq)
+        return self.matches
+
+
+# ---- F!com/rw/nanoporereadscanner/analyzers/Parser.assignBarcode (java:L195-L315) ---------------------
+def assign_barcode(read, adapterpos, search, ranks, ed_max, plusminus=2, three_prime=True, L=16):
+    """`read` = stranded read string, `adapterpos` as the Java (1-based adapter end).  Returns a dict
+    (assigned False => only ed / ed_second are meaningful) or raises JavaException."""
+    def substring(b, e):
+        if b < 0 or e > len(read) or b > e:
+            raise JavaException("StringIndexOutOfBounds")
+        return read[b:e]
+
+    matches = JHashSet()
+    probes = 0
+    for off in sorted(range(-plusminus, plusminus + 1), key=abs):          # L198-L200 (stable)
+        if three_prime:
+            bcStart = adapterpos - L + off                                  # L206
+            bcEnd = adapterpos - 1 + off                                    # L207
+        else:
+            bcStart = adapterpos + 1 + off                                  # L209
+            bcEnd = adapterpos + L + off                                    # L210
+        bc = pack(substring(bcStart - 1, bcEnd))                            # L214
+        if three_prime:
+            codes = []
+            for ch in substring(bcStart - 5, bcStart):                      # L218
+                c = ENCODE[ord(ch)] if ord(ch) < 254 else None
+                if c is None:
+                    raise JavaException("AIOOBE ENCODE_MATRIX")
+                codes.append(c & 0xFF)
+            post = []
+            for c in reversed(codes):                                       # reverseComplement()
+                if c > 15:
+                    raise JavaException("AIOOBE ONEBYTE_REVERSECOMP_MATRIX")
+                post.append(ONEBYTE_RC[c])
+            bc = revcomp2(bc, L)                                            # L221
+        else:
+            post = []
+            for ch in substring(bcEnd, bcEnd + 5):                          # L219
+                if ord(ch) >= 254:
+                    raise JavaException("AIOOBE ENCODE_MATRIX")
+                c = ENCODE[ord(ch)]
+                post.append(c if c >= 0 else 255)
+        t = BarcodeMatchTester(bc, L, ed_max, False, True, search, off, post, True)   # L223-L238
+        m = t.doJob()
+        probes += t.probes
+        for e in m:                                                         # addAll (L240)
+            matches.add(e)
+    res = dict(assigned=False, bc=0, ed=-1, ed_second=2147483647, offset=0, n_ins=0, n_del=0, n_sub=0, rank=-1,
+               probes=probes, tie_unpinned=matches.treeified)
+    lst = list(matches)
+    if not lst:                                                             # L244
+        return res
+    lst.sort(key=OneMatch.key)                                              # stable (L247)
+    best = lst[0]
+    second = None
+    for e in lst[1:]:
+        if e.bc != best.bc:                                                 # distinctByKey(matchingBC)
+            second = e
+            break
+    res["ed"] = best.ed
+    res["ed_second"] = second.ed if second is not None else 2147483647
+    if best.ed <= ed_max and (second is None or best.ed < second.ed):      # L251-L252
+        res.update(assigned=True, bc=best.bc, offset=best.offset, n_ins=best.nIns, n_del=best.nDel, n_sub=best.nSub,
+                   rank=ranks.get(best.bc, -1) if ranks is not None else -1)
+        # L273-L280
+        if three_prime:
+            start = adapterpos - 1 + best.offset
+            end = start - (L - 1) - (best.nIns - best.nDel)
+        else:
+            start = adapterpos + 1 + best.offset
+            end = start + (L - 1) + (best.nIns - best.nDel)
+        res["bcStart"], res["bcEnd"] = start, end
+    return res
+
+
+# ---- UMI: apachemod/LevenshteinDistance.limitedCompare (java:L220-L283) --------------------------------
+IMAX = 2147483647
+
+
+def _i32(x):
+    x &= 0xFFFFFFFF
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
+def limited_compare(left, right, threshold):
+    n, m = len(left), len(right)
+    p = [0] * (n + 1)
+    d = [0] * (n + 1)
+    boundary = threshold + 1
+    for i in range(boundary):
+        p[i] = i
+    for i in range(boundary, n + 1):
+        p[i] = IMAX
+    for i in range(n + 1):
+        d[i] = IMAX
+    for j in range(1, m + 1):
+        rj = right[j - 1]
+        d[0] = j
+        mn = max(1, j - threshold)
+        mx = n if j > IMAX - threshold else min(n, j + threshold)
+        if mn > 1:
+            d[mn - 1] = IMAX
+        lower = IMAX
+        for i in range(mn, mx + 1):
+            if left[i - 1] == rj:
+                d[i] = p[i - 1]
+            else:
+                d[i] = _i32(1 + min(min(d[i - 1], p[i]), p[i - 1]))
+            lower = min(lower, d[i])
+        if lower > threshold:
+            return -1
+        p, d = d, p
+    return p[n] if p[n] <= threshold else -1
+
+
+def umi_best9(a, b, umi_len=12):
+    """ClusteringEditDistanceBase.calcEditDistances + calcBestEditDistance (java:L297-L350, L67-L80)."""
+    eds = [[0] * 3 for _ in range(3)]
+    for i in (-1, 0, 1):
+        s1 = list(a[1 + i:1 + i + umi_len])
+        for j in (-1, 0, 1):
+            s2 = list(b[1 + j:1 + j + umi_len])
+            if s1 == s2:
+                eds[i + 1][j + 1] = 0
+            else:
+                dd = limited_compare(s1, s2, 4)
+                eds[i + 1][j + 1] = 5 if dd == -1 else dd
+    best = (127, 0, 0)
+    for i in (1, 2, 0):                                       # EnumSet order ZERO, PLUSONE, MINUSONE (getValue 1,2,0)
+        for v in (1, 2, 0):
+            if eds[i][v] < best[0]:
+                best = (eds[i][v], i, v)
+    return _i32((best[0] & 0xFFFFFF) | (0x08000000 << best[1]) | (0x01000000 << best[2]))

@@ -1,0 +1,96 @@
+/*
+ * slr_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the SiCeLoRe 2.1 barcode / UMI edit-distance hot path, written from the
+ * shipped bytecode (no Java source exists in the reference tree).  Citations use the survey's
+ * notation:  F! = Jar/NanoporeBC_UMI_finder-2.1.jar,  T! = Jar/lib/TwoFourBitNucAcidLibraryMaven-1.0.jar,
+ * (Foo.java:Lnnn) = original source line recovered from the LineNumberTable (tools/jdis.py).
+ *
+ * PARITY STATUS: "parity unpinned".  The reference ships no tests / golden vectors for this path and
+ * cannot be executed in the build container (no JVM).  The oracle is pinned only by (i) the two
+ * read-name examples of /root/reference/README.md:400,452, (ii) an independent second restatement
+ * (oracle/pyref.py) and (iii) brute-force property checks (tests/).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may link
+ * or call this file.  The product (libsicelore_gpu.so) never does.
+ */
+#ifndef SLR_ORACLE_H
+#define SLR_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_ED 8
+
+/* ---------- 2-bit primitives (T!com/rw/nuc/encoding/TwoBit/NucleicAcidTwoBitPerBase) ---------- */
+uint64_t orc_pack2bit(const uint8_t *chars, int len, int *bad_char);          /* java:L183-L187 */
+uint64_t orc_revcomp2bit(uint64_t seq, int len);                              /* java:L477-L484 */
+void     orc_replace_deg(uint64_t seq, uint64_t out[4], int pos, int len);    /* java:L228-L234 */
+void     orc_insert_deg(uint64_t seq, uint64_t out[4], int pos, int len);     /* java:L300-L310 */
+uint64_t orc_delete_byte(uint64_t seq, int code4, int pos, int len);          /* java:L321-L327 */
+int      orc_encode4bit(uint8_t c);   /* NucleicAcidByteCodeBase.ENCODE_MATRIX, 0xFF = unknown (java:L45-L78) */
+int      orc_revcomp4bit(int code);   /* ONEBYTE_REVERSECOMP_MATRIX (java:L100-L133) */
+
+/* ---------- barcode search set (stands in for fastutil LongSet.contains: membership only) ------ */
+typedef struct orc_set orc_set;
+orc_set *orc_set_new(const uint64_t *keys, int64_t n);
+void     orc_set_free(orc_set *s);
+int64_t  orc_set_find(const orc_set *s, uint64_t key);   /* index into keys[] or -1 */
+int64_t  orc_set_size(const orc_set *s);
+
+/* ---------- BarcodeMatchTester.doJob (F!...BarcodeMatchTester.java:L198-L244) ------------------ */
+typedef struct {
+    uint64_t read_seq;      /* OneMatch.readSeq = unmutated window */
+    uint64_t bc;            /* OneMatch.matchingBC */
+    int32_t  ed;            /* OneMatch.editDistance = DFS level of the hit */
+    int32_t  offset;        /* OneMatch.offsetFromPredicted */
+    int32_t  n_sub, n_ins, n_del;   /* counters exactly as the Java names them (INS op bumps nDel) */
+} orc_match;
+
+/* Returns number of matches (0..ed+1) in DISCOVERY order (= HashSet chain order, all share one hash),
+ * or -1 if the Java would have thrown (invalid post code reached).  post4 = 4-bit codes, post_len<0 => null. */
+int orc_match_tester(const orc_set *set, uint64_t seq, int len, int ed, int skip_full_matches,
+                     int allow_indels, const uint8_t *post4, int post_len, int do_next_level_if_match,
+                     int offset, orc_match *out, int64_t *n_probes);
+
+/* ---------- Parser.assignBarcode (F!...Parser.java:L195-L315) ---------------------------------- */
+#define ORC_F_ASSIGNED   1u   /* BC_FOUND */
+#define ORC_F_EXCEPTION  2u   /* the Java would have thrown (index out of range / unknown char) */
+#define ORC_F_TIE_UNPIN  4u   /* HashMap bin got treeified: iteration order not emulated */
+
+typedef struct {
+    uint64_t bc;            /* best.matchingBC if assigned else 0 */
+    int32_t  ed;            /* best ED; -1 = no match at any offset */
+    int32_t  ed_second;     /* second-best ED (distinct barcode), INT32_MAX = none */
+    int8_t   offset;        /* best.offsetFromPredicted (assigned only) */
+    int8_t   n_ins;         /* OneMatch.insertions */
+    int8_t   n_del;         /* OneMatch.deletions */
+    int8_t   n_sub;
+    int32_t  rank;          /* CountsRank.rank of bc, -1 if unassigned */
+    uint32_t flags;
+} orc_bc_result;            /* 32 bytes, same layout as slr_bc_result */
+
+void orc_assign_barcode(const orc_set *set, const int32_t *rank, int ed_max, int plusminus, int three_prime,
+                        int bc_len, const uint8_t *slice, int slice_len, int anchor,
+                        orc_bc_result *out, int64_t *n_probes);
+
+/* batch, OpenMP over reads (used as the CPU baseline).  slices: n * stride bytes */
+void orc_assign_barcode_batch(const orc_set *set, const int32_t *rank, int ed_max, int plusminus, int three_prime,
+                              int bc_len, const uint8_t *slices, int stride, int slice_len, const int32_t *anchor,
+                              int64_t n, orc_bc_result *out, int64_t *n_probes_total, int n_threads);
+
+/* ---------- UMI distances (F!com/rw/clustering/ClusteringEditDistanceBase.java:L297-L350) ------ */
+int     orc_limited_compare(const uint8_t *left, int n, const uint8_t *right, int m, int threshold); /* apachemod/LevenshteinDistance.java:L220-L283 */
+int32_t orc_umi_best9(const uint8_t *a, const uint8_t *b, int umi_len);    /* a,b: umi_len+2 4-bit codes (window -1..+1) */
+int32_t orc_umi_transpose(int32_t packed);                                  /* BestEditDistance.getTransposedCopy L458 */
+int32_t orc_umi_equality(void);                                             /* EQUALITYMATRIX result (L90-L92) */
+/* generateDistanceMatrix for one (cell, region) job: n reads, out = n*n row-major packed ints */
+void    orc_umi_matrix(const uint8_t *umis, int stride, int umi_len, int64_t n, int32_t *out);
+void    orc_umi_matrix_batch(const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
+                             int32_t *out, const int64_t *out_offsets, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
