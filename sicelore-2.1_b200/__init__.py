@@ -1,0 +1,371 @@
+"""sicelore-2.1_b200 — host-side mirror (Python, ctypes) of the reference interface for the barcode / UMI
+edit-distance hot path, on top of the C ABI of libsicelore_gpu.so (include/sicelore_gpu.h).
+
+The directory name is not a Python identifier; `__graft_entry__.load_package()` imports it as `sicelore_b200`.
+
+Names follow the reference (F! = Jar/NanoporeBC_UMI_finder-2.1.jar):
+  BarcodesMapForBCfinding    F!com/rw/nanoporereadscanner/WorkerReadscanner$BarcodesMapForBCfinding  (search set + ranks)
+  Parser.assign_barcodes     F!com/rw/nanoporereadscanner/analyzers/Parser.assignBarcode (Parser.java:L195-L315)
+  generate_distance_matrices F!com/rw/clustering/ClusteringEditDistanceBase.generateDistanceMatrix (…java:L168-L259)
+  BestEditDistance           F!com/rw/clustering/ClusteringEditDistanceBase$BestEditDistance (L382-L449)
+  read_name_suffix           F!com/rw/nanoporereadscanner/readerwriter/FastqRecordExt (bc= ed= ed_sec= bcStart= bcEnd= rk=)
+
+There is NO CPU fallback here: every compute call goes to the CUDA library and raises when the library or a device
+is missing.  (The CPU oracle lives in oracle/ and is test infrastructure only.)
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_GPU = os.path.join(_HERE, "libsicelore_gpu.so")
+LIB_SYNTH = os.path.join(_HERE, "libslr_synth.so")
+NVCC = os.environ.get("SLR_NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = "/usr/bin/g++"            # $CXX in this image points at a gcc without libgomp
+
+SLR_OK, SLR_E_INVALID, SLR_E_NODEVICE, SLR_E_CUDA, SLR_E_NOMEM, SLR_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+F_ASSIGNED, F_EXCEPTION, F_TIE_UNPIN = 1, 2, 4
+INT_MAX = 2147483647
+
+BC_RESULT = np.dtype([("bc", "<u8"), ("ed", "<i4"), ("ed_second", "<i4"), ("offset", "i1"), ("n_ins", "i1"),
+                      ("n_del", "i1"), ("n_sub", "i1"), ("rank", "<i4"), ("flags", "<u4")], align=True)
+assert BC_RESULT.itemsize == 32
+
+EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
+           "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
+           "slr_bc_counts_device", "slr_umi_dist", "slr_umi_dist_dev", "slr_last_error", "slr_abi_version",
+           "slr_launch_count"]
+
+
+class SiceloreGpuError(RuntimeError):
+    """A libsicelore_gpu call failed (code = SLR_E_*).  The Java shim maps this to log + System.exit(1)."""
+
+    def __init__(self, code, msg):
+        super().__init__("libsicelore_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SiceloreGpuMissing(RuntimeError):
+    """The CUDA library has not been built: there is no other implementation to fall back to."""
+
+
+# ---------------------------------------------------------------------------------------------- build
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    """Compile libsicelore_gpu.so (nvcc, sm_100a only) and libslr_synth.so (g++) in-tree."""
+    srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
+    inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
+    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "umi_dist.cu")]
+    if force or _stale(LIB_GPU, srcs + [inc]):
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+               "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    syn = os.path.join(_CSRC, "synth.cpp")
+    if force or _stale(LIB_SYNTH, [syn]):
+        subprocess.check_call([CXX, "-O3", "-fPIC", "-shared", "-fopenmp", "-std=c++17", "-o", LIB_SYNTH, syn])
+    return LIB_GPU, LIB_SYNTH
+
+
+# ---------------------------------------------------------------------------------------------- library handles
+_gpu = None
+_syn = None
+
+
+def gpu_lib():
+    """The CUDA library.  Fails loudly when it has not been built."""
+    global _gpu
+    if _gpu is None:
+        if not os.path.exists(LIB_GPU):
+            raise SiceloreGpuMissing("libsicelore_gpu.so is missing: run __graft_entry__.build() (needs nvcc); "
+                                     "there is no CPU fallback")
+        L = C.CDLL(LIB_GPU)
+        vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+        L.slr_ctx_create.argtypes = [i32, i32, C.POINTER(vp)]
+        L.slr_ctx_destroy.argtypes = [vp]
+        L.slr_ctx_destroy.restype = None
+        L.slr_ctx_device.argtypes = [vp]
+        L.slr_bc_table_create.argtypes = [vp, vp, vp, i64, i32, C.POINTER(vp)]
+        L.slr_bc_table_destroy.argtypes = [vp]
+        L.slr_bc_table_destroy.restype = None
+        L.slr_bc_table_size.argtypes = [vp]
+        L.slr_bc_table_size.restype = i64
+        L.slr_bc_assign.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, i64, vp]
+        L.slr_bc_assign_dev.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, i64, vp, vp]
+        L.slr_bc_counts_read.argtypes = [vp, vp, vp]
+        L.slr_bc_counts_reset.argtypes = [vp, vp]
+        L.slr_bc_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+        L.slr_umi_dist.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
+        L.slr_umi_dist_dev.argtypes = [vp, vp, i32, i32, vp, i64, i64, vp, vp, i64, vp]
+        L.slr_last_error.restype = C.c_char_p
+        L.slr_abi_version.restype = i32
+        L.slr_launch_count.restype = i64
+        _gpu = L
+    return _gpu
+
+
+def _check(rc):
+    if rc != 0:
+        raise SiceloreGpuError(rc, gpu_lib().slr_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(gpu_lib().slr_launch_count())
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("p_sub", C.c_double), ("p_ins", C.c_double), ("p_del", C.c_double), ("p_random", C.c_double),
+                ("p_n", C.c_double), ("jitter", C.c_double * 5), ("n_cells", C.c_int64), ("three_prime", C.c_int)]
+
+
+def synth_lib():
+    global _syn
+    if _syn is None:
+        if not os.path.exists(LIB_SYNTH):
+            build()
+        L = C.CDLL(LIB_SYNTH)
+        L.slr_synth_whitelist.argtypes = [C.c_void_p, C.c_int64, C.c_uint64]
+        L.slr_synth_whitelist.restype = None
+        L.slr_synth_default_params.argtypes = [C.POINTER(SynthParams)]
+        L.slr_synth_default_params.restype = None
+        L.slr_synth_reads.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.POINTER(SynthParams),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.slr_synth_reads.restype = None
+        L.slr_synth_umi_jobs.argtypes = [C.c_int64, C.c_double, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_int,
+                                         C.c_void_p, C.c_void_p]
+        L.slr_synth_umi_jobs.restype = None
+        _syn = L
+    return _syn
+
+
+# ---------------------------------------------------------------------------------------------- synthetic workloads
+def synth_whitelist(n, seed):
+    """n distinct pseudo-random 16-mers, 2-bit packed (stand-in for 737K-august-2016 / 3M-february-2018)."""
+    out = np.empty(n, dtype=np.uint64)
+    synth_lib().slr_synth_whitelist(out.ctypes.data, n, seed)
+    return out
+
+
+def synth_reads(whitelist, n, seed, first=0, three_prime=True, n_cells=0, p_sub=0.02, p_ins=0.01, p_del=0.02,
+                p_random=0.10, p_n=0.01, out=None):
+    """Boundary buffers for reads [first, first+n) of a synthetic run: (slices[n,32] u8, anchor[n] i32, truth[n] i64)."""
+    prm = SynthParams()
+    synth_lib().slr_synth_default_params(C.byref(prm))
+    prm.p_sub, prm.p_ins, prm.p_del, prm.p_random, prm.p_n = p_sub, p_ins, p_del, p_random, p_n
+    prm.n_cells, prm.three_prime = n_cells, int(three_prime)
+    wl = np.ascontiguousarray(whitelist, dtype=np.uint64)
+    if out is None:
+        slices = np.empty((n, 32), dtype=np.uint8)
+        anchor = np.empty(n, dtype=np.int32)
+    else:
+        slices, anchor = out
+    truth = np.empty(n, dtype=np.int64)
+    synth_lib().slr_synth_reads(wl.ctypes.data, len(wl), first, n, seed, C.byref(prm), slices.ctypes.data,
+                                anchor.ctypes.data, truth.ctypes.data, None)
+    return slices, anchor, truth
+
+
+def synth_umi_jobs(n_jobs, mean=4.0, cap=2000, seed=4, p_err=0.05, p_shift=0.05, umi_len=12):
+    """(umis[m,16] u8 4-bit codes, job_offsets[n_jobs+1] i64) for n_jobs (cell, region) groups."""
+    offs = np.zeros(n_jobs + 1, dtype=np.int64)
+    synth_lib().slr_synth_umi_jobs(n_jobs, mean, cap, seed, p_err, p_shift, umi_len, offs.ctypes.data, None)
+    umis = np.zeros((int(offs[-1]), 16), dtype=np.uint8)
+    synth_lib().slr_synth_umi_jobs(n_jobs, mean, cap, seed, p_err, p_shift, umi_len, offs.ctypes.data, umis.ctypes.data)
+    return umis, offs
+
+
+# ---------------------------------------------------------------------------------------------- 2-bit helpers
+_B2 = "AGCT"            # NucleicAcidTwoBitPerBase: A=0 G=1 C=2 T=3 (T!…NucleicAcidTwoBitPerBase.java:L80-L87)
+
+
+def pack_barcode(s):
+    h = 0
+    for ch in s:
+        h = (h << 2) | _B2.index(ch.upper())
+    return h
+
+
+def unpack_barcode(h, length=16):
+    return "".join(_B2[(int(h) >> (2 * (length - 1 - i))) & 3] for i in range(length))
+
+
+def read_whitelist(path):
+    """NanoporeReadScannerMain.readBarcodesFile: one barcode per line, optional '-1' suffix, .gz ok."""
+    import gzip
+    op = gzip.open if path.endswith(".gz") else open
+    keys = []
+    with op(path, "rt") as f:
+        for line in f:
+            s = line.strip().split("-")[0].split()[0] if line.strip() else ""
+            if s:
+                keys.append(pack_barcode(s))
+    return np.array(keys, dtype=np.uint64)
+
+
+# ---------------------------------------------------------------------------------------------- context / table
+class Context:
+    """One per (process, device): streams and staging buffers of the CUDA library."""
+
+    def __init__(self, device=-1, n_streams=2):
+        h = C.c_void_p()
+        _check(gpu_lib().slr_ctx_create(device, n_streams, C.byref(h)))
+        self.h = h
+
+    @property
+    def device(self):
+        return gpu_lib().slr_ctx_device(self.h)
+
+    def close(self):
+        if self.h:
+            gpu_lib().slr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BarcodesMapForBCfinding:
+    """Device-resident search set: barcode (2-bit long) -> CountsRank.rank, plus the per-barcode ED counters."""
+
+    def __init__(self, ctx, barcodes2bit, rank=None, bc_len=16):
+        self.ctx = ctx
+        self.keys = np.ascontiguousarray(barcodes2bit, dtype=np.uint64)
+        self.rank = None if rank is None else np.ascontiguousarray(rank, dtype=np.int32)
+        h = C.c_void_p()
+        _check(gpu_lib().slr_bc_table_create(ctx.h, self.keys.ctypes.data, None if self.rank is None else self.rank.ctypes.data,
+                                             len(self.keys), bc_len, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def getMapFromCellRangerData(cls, ctx, barcodes2bit):
+        """--cellRangerBCs flow: every barcode of the list gets a rank (1-based list order here)."""
+        return cls(ctx, barcodes2bit, np.arange(1, len(barcodes2bit) + 1, dtype=np.int32))
+
+    def size(self):
+        return int(gpu_lib().slr_bc_table_size(self.h))
+
+    def counts(self):
+        """assignedBarcodes2ndPass as an [n, 3] array (reads assigned to barcode i at ED 0/1/2) -> BarcodesAssigned.tsv"""
+        out = np.zeros((len(self.keys), 3), dtype=np.int64)
+        _check(gpu_lib().slr_bc_counts_read(self.ctx.h, self.h, out.ctypes.data))
+        return out
+
+    def reset_counts(self):
+        _check(gpu_lib().slr_bc_counts_reset(self.ctx.h, self.h))
+
+    def counts_device_ptr(self):
+        p, n = C.c_void_p(), C.c_int64()
+        _check(gpu_lib().slr_bc_counts_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            gpu_lib().slr_bc_table_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Parser:
+    """Mirror of the second-pass Parser for the part that moved to the GPU (assignBarcode, Parser.java:L195-L315)."""
+
+    def __init__(self, ctx, hashMapForBCfinding, bcEditDistance=1, testPlusMinusPos=2, three_prime=True):
+        self.ctx, self.map = ctx, hashMapForBCfinding
+        self.ed, self.pm, self.three_prime = int(bcEditDistance), int(testPlusMinusPos), bool(three_prime)
+
+    def assign_barcodes(self, slices, anchor, lens=None, out=None):
+        """slices u8 [n, stride] (host), anchor i32 [n] -> structured array BC_RESULT [n]."""
+        slices = np.ascontiguousarray(slices, dtype=np.uint8)
+        anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+        n, stride = slices.shape
+        if out is None:
+            out = np.empty(n, dtype=BC_RESULT)
+        lp = None
+        if lens is not None:
+            lens = np.ascontiguousarray(lens, dtype=np.int32)
+            lp = lens.ctypes.data
+        _check(gpu_lib().slr_bc_assign(self.ctx.h, self.map.h, self.ed, self.pm, int(self.three_prime), slices.ctypes.data,
+                                       stride, min(stride, 32), lp, anchor.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def assign_barcodes_dev(self, d_slices, stride, d_anchor, n, d_out, stream=0, d_lens=0, slice_len=32):
+        """Device-pointer variant (ints = raw CUDA pointers, e.g. torch tensor.data_ptr()); asynchronous on `stream`."""
+        _check(gpu_lib().slr_bc_assign_dev(self.ctx.h, self.map.h, self.ed, self.pm, int(self.three_prime), d_slices, stride,
+                                           slice_len, d_lens or None, d_anchor, n, d_out, stream or None))
+
+    @staticmethod
+    def barcode_positions(res, adapterpos, three_prime=True, bc_len=16):
+        """BarcodeResult.start / end as the Java sets them (Parser.java:L273-L280); adapterpos = 1-based adapter end."""
+        off = res["offset"].astype(np.int64)
+        d = res["n_ins"].astype(np.int64) - res["n_del"].astype(np.int64)      # OneMatch.getOffsetForReadEnd
+        if three_prime:
+            start = adapterpos - 1 + off
+            end = start - (bc_len - 1) - d
+        else:
+            start = adapterpos + 1 + off
+            end = start + (bc_len - 1) + d
+        return start, end
+
+
+def read_name_suffix(res_i, bc_start, bc_end):
+    """The barcode part of FastqRecordExt's read-name suffix (README.md:400): bc= ed= ed_sec= bcStart= bcEnd= rk="""
+    return "bc=%s_ed=%d_ed_sec=%d_bcStart=%d_bcEnd=%d_rk=%d" % (unpack_barcode(res_i["bc"]), res_i["ed"], res_i["ed_second"],
+                                                              bc_start, bc_end, res_i["rank"])
+
+
+# ---------------------------------------------------------------------------------------------- UMI distances
+class BestEditDistance:
+    """Decoder of the packed int (ClusteringEditDistanceBase$BestEditDistance, java:L382-L416)."""
+    MINUSONE, ZERO, PLUSONE = 0, 1, 2
+
+    @staticmethod
+    def getED(packed):
+        return np.asarray(packed) & 0xFFFFFF
+
+    @staticmethod
+    def getPos1(packed):
+        p = (np.asarray(packed).astype(np.int64) >> 27) & 7
+        return np.where(p & 1, 0, np.where(p & 2, 1, 2))
+
+    @staticmethod
+    def getPos2(packed):
+        p = (np.asarray(packed).astype(np.int64) >> 24) & 7
+        return np.where(p & 1, 0, np.where(p & 2, 1, 2))
+
+
+def out_offsets_for(job_offsets):
+    sizes = np.diff(np.asarray(job_offsets, dtype=np.int64))
+    oo = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(sizes * sizes, out=oo[1:])
+    return oo
+
+
+def generate_distance_matrices(ctx, umis, job_offsets, umi_len=12, out=None, out_offsets=None):
+    """ClusteringEditDistanceBase.generateDistanceMatrix for all jobs at once.
+    umis u8 [m, stride] (umi_len+2 4-bit codes per read), job_offsets i64 [n_jobs+1] -> (flat int32, out_offsets)."""
+    umis = np.ascontiguousarray(umis, dtype=np.uint8)
+    job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+    if out_offsets is None:
+        out_offsets = out_offsets_for(job_offsets)
+    out_offsets = np.ascontiguousarray(out_offsets, dtype=np.int64)
+    if out is None:
+        out = np.empty(int(out_offsets[-1]), dtype=np.int32)
+    _check(gpu_lib().slr_umi_dist(ctx.h, umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(job_offsets) - 1,
+                                  out.ctypes.data, out_offsets.ctypes.data))
+    return out, out_offsets

@@ -1,0 +1,336 @@
+// bc_core.cuh — per-lane logic of the barcode-assignment kernel, __host__ __device__ so that
+// tests/host_sim replays exactly the same code on the CPU (the warp orchestration lives in bc_assign.cu).
+//
+// Reference behaviour restated here (F! = Jar/NanoporeBC_UMI_finder-2.1.jar, T! = Jar/lib/TwoFourBitNucAcidLibraryMaven-1.0.jar):
+//   BarcodeMatchTester.doJob / substitutions / insertions / deletions   F!…/analyzers/BarcodeMatchTester.class (BarcodeMatchTester.java:L198-L357)
+//   NucTwoBitPerBaseEDtesterBase visited set                            F!…/TwoBit/ed/NucTwoBitPerBaseEDtesterBase.class (…java:L82-L120)
+//   NucleicAcidTwoBitPerBase replace/insert/delete                      T!…/TwoBit/NucleicAcidTwoBitPerBase.class (…java:L228-L327)
+//   Parser.assignBarcode merge + decision                               F!…/analyzers/Parser.class (Parser.java:L240-L311)
+#pragma once
+#include "slr_table.cuh"
+#include "../../include/sicelore_gpu.h"
+
+constexpr int SLR_MAX_OFFSETS = 9;             // plusminus <= 4
+constexpr uint32_t SLR_NONE32 = 0xFFFFFFFFu;
+constexpr unsigned long long SLR_VH_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr int SLR_VH_SIZE = 256;
+
+// matches of one read: one slot per (offset index, ED level) — Matches is a HashSet whose equals() is
+// (readSeq, ED, offset) (BarcodeMatchTester.java:L433-L436), i.e. first hit per ED level per offset wins.
+struct SlrMatchStore {
+    uint32_t m_w[SLR_MAX_OFFSETS];             // window = OneMatch.readSeq
+    uint32_t m_bc[SLR_MAX_OFFSETS][3];         // OneMatch.matchingBC
+    uint8_t m_cnt[SLR_MAX_OFFSETS][3];         // nSub | nIns << 2 | nDel << 4
+    uint8_t m_valid[SLR_MAX_OFFSETS];          // bit ED set = that level has a match
+};
+
+SLR_HD int slr_offset_of(int k) { return (k == 0) ? 0 : ((k & 1) ? -((k + 1) / 2) : (k / 2)); }   // 0,-1,1,-2,2 (Parser.java:L198-L200)
+
+// ---- visited-hash lookup (value -> earliest processing time); insertion is done by the orchestration ----
+SLR_HD uint32_t slr_vh_slot(uint32_t v) { return (v * 0x9E3779B1u) >> 24; }
+SLR_HD uint32_t slr_vh_tmin(const unsigned long long *tab, uint32_t v)
+{
+    uint32_t slot = slr_vh_slot(v);
+    while (true) {
+        const unsigned long long cur = tab[slot];
+        if (cur == SLR_VH_EMPTY) return SLR_NONE32;
+        if ((uint32_t)(cur >> 32) == v) return (uint32_t)cur;
+        slot = (slot + 1) & (SLR_VH_SIZE - 1);
+    }
+}
+
+// ---- level-1 mutant of window w: root position p, creation index j (0-3 SUB A,G,C,T; 4-7 INS; 8 DEL) ----
+// low 32 bits of getLongHashReplaceByteDeg / InsertByteDeg / deleteByte (java:L228-L234, L300-L310, L321-L327).
+// dead = the Java value carries garbage in bits 62-63 (insert at p = L-2 shifts by 64 == 0): never matches,
+// but its (int) value still enters the visited set.
+SLR_HD uint32_t slr_gen_mutant(uint32_t w, int p, int j, uint32_t cbase, bool &valid, bool &dead)
+{
+    const int sh = 2 * (15 - p);
+    dead = false;
+    if (j < 4) {
+        valid = ((w >> sh) & 3u) != (uint32_t)j;               // s != cur.seq (L260)
+        return (w & ~(3u << sh)) | ((uint32_t)j << sh);
+    }
+    valid = p < 15;                                            // indels only for posCur < L-1 (L234)
+    if (!valid) return 0;
+    if (j < 8) {
+        const uint32_t below = slr_lowmask(sh);                // digits p+1..15
+        dead = (p == 14) && ((w & 3u) != 0u);
+        return (w & ~below) | ((w & below) >> 2) | ((uint32_t)(j - 4) << (sh - 2));
+    }
+    const uint32_t below = slr_lowmask(sh + 2);                // digits p..15
+    return (w & ~below) | ((w << 2) & below) | cbase;
+}
+
+// remove digit i (0 = most significant) of a 4-digit (8-bit) pattern -> 6 bits
+SLR_HD uint32_t slr_rm_digit(uint32_t P, int i)
+{
+    switch (i) {
+    case 0: return P & 0x3Fu;
+    case 1: return ((P >> 2) & 0x30u) | (P & 0x0Fu);
+    case 2: return ((P >> 2) & 0x3Cu) | (P & 0x03u);
+    default: return P >> 2;
+    }
+}
+
+// Context of one node expansion (= all positions of one LongSeqMutated popped from the deque)
+struct SlrExpand {
+    uint32_t cs;        // node sequence
+    uint32_t w;         // unmutated window
+    int pskip;          // posTreatedInPreviousLevel (must not be mutated again, L227), -1 for the root
+    uint32_t cbase;     // base appended by a deletion: post[nDel+1] (L329)
+    uint32_t tproc;     // processing time of this node (level 2 only)
+    int level;          // 1 = root expansion (hits are ED 1), 2 = level-1 node expansion (hits are ED 2)
+    bool use_visited;   // ed >= 2 (NucTwoBitPerBaseEDtesterBase.java:L82-L95)
+};
+
+// Would the reference have skipped mutant s, created at position q of this node, as "already tested"?
+// visited (java:L105-L120) holds the (int) seq of every node that finished at least one position:
+//   level 1: {w, once the root did position 0} U {level-1 mutants of earlier root positions}
+//   level 2: {w} U {level-1 nodes processed before this node} U {this node, after its first position}
+SLR_HD bool slr_is_visited(const SlrExpand &e, const unsigned long long *vh, uint32_t s, int q)
+{
+    if (!e.use_visited) return false;
+    if (e.level == 1) {
+        if (q >= 1 && s == e.w) return true;
+        const uint32_t t = slr_vh_tmin(vh, s);
+        return t != SLR_NONE32 && (int)(t >> 4) < q;
+    }
+    if (s == e.w) return true;
+    const uint32_t t = slr_vh_tmin(vh, s);
+    if (t == SLR_NONE32) return false;
+    if (t < e.tproc) return true;
+    const int firstpos = (e.pskip == 0) ? 1 : 0;
+    return t == e.tproc && q > firstpos;
+}
+
+// Test slot pattern P of table g against the op-mutants (0 SUB, 1 INS, 2 DEL) of node e that fall into digit
+// group g.  Returns the smallest traversal rank q*9 + idx (idx: 0-3 SUB base, 4-7 INS base, 8 DEL) of a
+// generating, non-visited mutant, or SLR_NONE32.  s = the full candidate barcode.
+SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *vh, int g, int op, uint32_t P, uint32_t s)
+{
+    const uint32_t csg = (e.cs >> (24 - 8 * g)) & 0xFFu;
+    if (op == 0) {                                             // substitutions (L257-L273)
+        const uint32_t x = P ^ csg;
+        const uint32_t d = (x | (x >> 1)) & 0x55u;
+        if (d == 0u || (d & (d - 1u)) != 0u) return SLR_NONE32;   // exactly one digit differs
+        const int il = 3 - ((slr_ffs(d) - 1) >> 1);
+        const int q = 4 * g + il;
+        if (q == e.pskip) return SLR_NONE32;
+        if (slr_is_visited(e, vh, s, q)) return SLR_NONE32;
+        return (uint32_t)(q * 9) + ((P >> (2 * (3 - il))) & 3u);
+    }
+    if (op == 1) {                                             // insertions (L284-L300): new digit at j = q+1
+        const uint32_t c012 = csg >> 2;
+        for (int jl = 0; jl < 4; jl++) {
+            const int j = 4 * g + jl, q = j - 1;
+            if (j < 1 || q == e.pskip) continue;
+            if (j == 15 && (e.cs & 3u) != 0u) continue;        // the `>>> 64` value: garbage in bits 62-63
+            if (slr_rm_digit(P, jl) != c012) continue;
+            if (slr_is_visited(e, vh, s, q)) continue;
+            return (uint32_t)(q * 9) + 4u + ((P >> (2 * (3 - jl))) & 3u);
+        }
+        return SLR_NONE32;
+    }
+    // deletions (L313-L357): digit q removed, tail shifted left, cbase appended
+    const uint32_t n0 = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;
+    if ((P & 3u) != n0) return SLR_NONE32;
+    const uint32_t P012 = P >> 2;
+    for (int ql = 0; ql < 4; ql++) {
+        const int q = 4 * g + ql;
+        if (q > 14 || q == e.pskip) continue;
+        if (slr_rm_digit(csg, ql) != P012) continue;
+        if (slr_is_visited(e, vh, s, q)) continue;
+        return (uint32_t)(q * 9) + 8u;
+    }
+    return SLR_NONE32;
+}
+
+// All op-mutants of node e whose edit falls into digit group g: ONE bucket load.
+// Returns the best (smallest) traversal rank and the matching barcode.
+SLR_HD uint32_t slr_expand_group(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
+                                 uint32_t &bc_out)
+{
+    const int lo_bits = 24 - 8 * g;
+    const uint32_t hi = g == 0 ? 0u : (e.cs >> (32 - 8 * g));
+    uint32_t lo;
+    if (op == 0) lo = e.cs;
+    else if (op == 1) lo = e.cs >> 2;
+    else lo = (e.cs << 2) | e.cbase;
+    lo &= slr_lowmask(lo_bits);
+    const uint32_t rest = (hi << lo_bits) | lo;
+    const uint32_t m = slr_mix24(rest);
+    const int tb = 24 - t.bbits;
+    const uint32_t bucket = m >> tb, tag = m & ((1u << tb) - 1u);
+    const SlrBucket k = slr_load_bucket(t, g, bucket);
+    uint32_t match = slr_tag_match(k, tag);
+    uint32_t best = SLR_NONE32;
+    while (match) {
+        const int i = slr_ffs(match) - 1;
+        match &= match - 1u;
+        const uint32_t P = k.slot(i) & 0xFFu;
+        const uint32_t s = slr_key_join(rest, P, g);
+        const uint32_t r = slr_check_pattern(e, vh, g, op, P, s);
+        if (r < best) { best = r; bc_out = s; }
+    }
+    if (t.st_n[g] > 0 && slr_bucket_full(k)) {                 // overflowed bucket: rare
+        const uint32_t want_hi = 0x80u | tag;
+        for (int i = slr_stash_lower(t, g, bucket); i < t.st_n[g] && slr_ldg(t.st_bucket[g] + i) == bucket; i++) {
+            const uint32_t sl = slr_ldg(t.st_slot[g] + i);
+            if ((sl >> 8) != want_hi) continue;
+            const uint32_t P = sl & 0xFFu;
+            const uint32_t s = slr_key_join(rest, P, g);
+            const uint32_t r = slr_check_pattern(e, vh, g, op, P, s);
+            if (r < best) { best = r; bc_out = s; }
+        }
+    }
+    return best;
+}
+
+// counters the Java attaches to a mutant created by idx (0-3 SUB -> nSubstitutions, 4-7 INS -> nDeletions (L290),
+// 8 DEL -> nInsertions (L346)); packed nSub | nIns << 2 | nDel << 4
+SLR_HD uint32_t slr_cnt_of(uint32_t idx) { return idx < 4 ? 1u : (idx < 8 ? (1u << 4) : (1u << 2)); }
+
+// ---- character classes -----------------------------------------------------------------------------------
+// BASE_TO_TWOBIT_ARRAY (T!…NucleicAcidTwoBitPerBase.java:L78-L87): returns 0..3 or 4 for "not ACGT"
+SLR_HD uint32_t slr_code2(uint32_t c)
+{
+    switch (c) {
+    case 'A': case 'a': return 0; case 'G': case 'g': return 1; case 'C': case 'c': return 2; case 'T': case 't': return 3;
+    default: return 4;
+    }
+}
+// is c in NucleicAcidByteCodeBase.ENCODE_MATRIX (T!…NucleicAcidByteCodeBase.java:L45-L78)?
+SLR_HD bool slr_in_encode_matrix(uint32_t c)
+{
+    if (c == '-') return true;
+    switch (c | 0x20u) {
+    case 'a': case 'g': case 'c': case 't': case 'n': case 'h': case 'r': case 'y': case 'm': case 'k': case 's':
+    case 'w': case 'b': case 'v': case 'd':
+        return true;                         // only letters fold onto 'a'..'z' under |0x20
+    default: return false;
+    }
+}
+
+// reverse the order of the 16 base-4 digits of x
+SLR_HD uint32_t slr_rev_digits(uint32_t x)
+{
+    x = slr_brev(x);
+    return ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+}
+// spread the low 16 bits of x to the even bit positions
+SLR_HD uint32_t slr_spread16(uint32_t x)
+{
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// Per-slice bit planes: bit i describes char i of the slice (on the GPU these are warp ballots).
+struct SlrSliceBits {
+    uint32_t bit0, bit1;      // 2-bit code planes
+    uint32_t nonacgt;         // char is not ACGTacgt
+    uint32_t unknown;         // char is not in ENCODE_MATRIX
+    uint32_t over253;         // char >= 254 (indexing past the 254-entry tables -> AIOOBE)
+};
+
+// Window + post bases of offset o.  Returns false if the Java would have thrown (Parser.java:L214-L219).
+// w = OneMatch.readSeq; dead = window can never match (5' window with a non-ACGT char: bits >= 32 set).
+SLR_HD bool slr_window(const SlrSliceBits &b, int len, int anc, int o, int three_prime, int ed_max, uint32_t &w, uint32_t &p1,
+                       uint32_t &p2, bool &dead)
+{
+    const int ws = anc + o;
+    dead = false;
+    if (ws < 0 || ws + 16 > len) return false;                              // substring(bcStart-1, bcEnd)
+    if (three_prime) {
+        if (ws - 4 < 0) return false;                                       // substring(bcStart-5, bcStart)
+        if ((b.unknown >> (ws - 4)) & 0x1Fu) return false;                  // reverseComplement(): ONEBYTE_REVERSECOMP_MATRIX[-1]
+        // post[1] = comp(read[ws]), post[2] = comp(read[ws-1]); codes other than A,G,C,T append A (BYTE_TO_2BITLONG_ARRAY)
+        const uint32_t a1 = ((b.bit1 >> ws) & 1u) * 2u + ((b.bit0 >> ws) & 1u);
+        const uint32_t a2 = ((b.bit1 >> (ws - 1)) & 1u) * 2u + ((b.bit0 >> (ws - 1)) & 1u);
+        p1 = ((b.nonacgt >> ws) & 1u) ? 0u : 3u - a1;
+        p2 = ((b.nonacgt >> (ws - 1)) & 1u) ? 0u : 3u - a2;
+    } else {
+        if (ws + 21 > len) return false;                                    // substring(bcEnd, bcEnd+5)
+        if ((b.over253 >> (ws + 16)) & 0x1Fu) return false;                 // ENCODE_MATRIX[c], 254 entries
+        // a code of -1 only throws when a deletion fetches it: post[1] at ED >= 1, post[2] at ED >= 2
+        if (ed_max >= 1 && ((b.unknown >> (ws + 16)) & 1u)) return false;
+        if (ed_max >= 2 && ((b.unknown >> (ws + 17)) & 1u)) return false;
+        p1 = ((b.nonacgt >> (ws + 16)) & 1u) ? 0u : ((b.bit1 >> (ws + 16)) & 1u) * 2u + ((b.bit0 >> (ws + 16)) & 1u);
+        p2 = ((b.nonacgt >> (ws + 17)) & 1u) ? 0u : ((b.bit1 >> (ws + 17)) & 1u) * 2u + ((b.bit0 >> (ws + 17)) & 1u);
+    }
+    if ((b.over253 >> ws) & 0xFFFFu) return false;                          // BASE_TO_TWOBIT_ARRAY[c], 254 entries
+    // getLongHashForSeq (java:L183-L187): a non-ACGT char ORs a sign-extended (byte)-2 into the hash: every
+    // earlier digit becomes 3, that digit 2, bits >= 32 garbage.  wbits holds char ws+i at digit i from the LSB.
+    uint32_t wbits = slr_spread16(b.bit0 >> ws) | (slr_spread16(b.bit1 >> ws) << 1);
+    const uint32_t badw = (b.nonacgt >> ws) & 0xFFFFu;
+    if (badw) {
+        const int jlast = 31 - slr_clz(badw);
+        wbits |= slr_lowmask(2 * jlast);
+        wbits = (wbits & ~(3u << (2 * jlast))) | (2u << (2 * jlast));
+        dead = !three_prime;
+    }
+    // 3': reverseComplement (java:L477-L484) reads only the low 32 bits; wbits is already reversed, complement = ~
+    w = three_prime ? ~wbits : slr_rev_digits(wbits);
+    return true;
+}
+
+// ---- merge + decision (Parser.java:L240-L311) -----------------------------------------------------------
+// Emulates the iteration order of the merged java.util.HashSet<OneMatch> (hashCode = (int)(readSeq ^ readSeq>>>32),
+// BarcodeMatchTester.java:L443; JDK HashMap: capacity 16, resize above 12/24/48 entries, a chain reaching 9 nodes
+// resizes while capacity < 64), then the stable sort by OneMatch.compareTo (L449-L461), distinctByKey(matchingBC).
+// Fills everything but rank (needs the index map) and returns the best barcode's ED level, or -1.
+SLR_HD int slr_decide(const SlrMatchStore &S, int noff, int ed_max, slr_bc_result &res)
+{
+    int cap = 16, thr = 12, cnt = 0;
+    bool treeified = false;
+    for (int k = 0; k < noff; k++) {
+        const uint32_t sp = S.m_w[k] ^ (S.m_w[k] >> 16);
+        for (int lv = 0; lv < 3; lv++) {
+            if (!((S.m_valid[k] >> lv) & 1)) continue;
+            int chain = 0;
+            for (int k2 = 0; k2 <= k; k2++) {
+                const uint32_t sp2 = S.m_w[k2] ^ (S.m_w[k2] >> 16);
+                if ((sp2 & (uint32_t)(cap - 1)) != (sp & (uint32_t)(cap - 1))) continue;
+                for (int l2 = 0; l2 < 3; l2++)
+                    if (((S.m_valid[k2] >> l2) & 1) && (k2 < k || l2 < lv)) chain++;
+            }
+            cnt++;
+            if (chain >= 8) { if (cap < 64) { cap <<= 1; thr <<= 1; } else treeified = true; }
+            if (cnt > thr) { cap <<= 1; thr <<= 1; }
+        }
+    }
+    if (cnt == 0) return -1;
+    if (treeified) res.flags |= SLR_F_TIE_UNPIN;
+    uint32_t bestkey = SLR_NONE32;
+    int bk = 0, blv = 0;
+    for (int k = 0; k < noff; k++) {
+        const uint32_t sp = S.m_w[k] ^ (S.m_w[k] >> 16);
+        for (int lv = 0; lv < 3; lv++) {
+            if (!((S.m_valid[k] >> lv) & 1)) continue;
+            const uint32_t key = ((uint32_t)lv << 20) | ((k != 0 ? 1u : 0u) << 16) | ((sp & (uint32_t)(cap - 1)) << 8) | (uint32_t)(k * 3 + lv);
+            if (key < bestkey) { bestkey = key; bk = k; blv = lv; }
+        }
+    }
+    const uint32_t bbc = S.m_bc[bk][blv];
+    int second = 0x7FFFFFFF;
+    for (int k = 0; k < noff; k++)
+        for (int lv = 0; lv < 3; lv++)
+            if (((S.m_valid[k] >> lv) & 1) && S.m_bc[k][lv] != bbc && lv < second) second = lv;
+    res.ed = blv;
+    res.ed_second = second;
+    if (blv <= ed_max && blv < second) {                                    // L251-L252
+        res.flags |= SLR_F_ASSIGNED;
+        res.bc = bbc;
+        res.offset = (int8_t)slr_offset_of(bk);
+        const uint32_t c = S.m_cnt[bk][blv];
+        res.n_sub = (int8_t)(c & 3u);
+        res.n_ins = (int8_t)((c >> 2) & 3u);
+        res.n_del = (int8_t)((c >> 4) & 3u);
+        return blv;
+    }
+    return -1;
+}

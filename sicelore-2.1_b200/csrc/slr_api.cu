@@ -1,0 +1,389 @@
+// slr_api.cu — the C ABI of libsicelore_gpu.so (include/sicelore_gpu.h): context, device tables, batching.
+// Host-side runtime only; the kernels are in bc_assign.cu / umi_dist.cu.  No CPU fallback anywhere: without a
+// CUDA device every entry point fails with SLR_E_NODEVICE.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "slr_kernels.h"
+#include "slr_table_build.h"
+#include "umi_core.cuh"
+#include "bc_core.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess) return fail(SLR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr long long BC_CHUNK = 1 << 20;        // reads per pipelined chunk of the host-pointer path
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return SLR_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(SLR_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return SLR_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// one slot = what one host thread needs to have a batch in flight: two streams + ping-pong device buffers
+struct Slot {
+    std::mutex mtx;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    DevBuf slices[2], anchor[2], lens[2], out[2];
+    DevBuf umi, joff, ooff, uout;
+};
+
+}  // namespace
+
+struct slr_ctx {
+    int device = 0;
+    int n_slots = 1;
+    std::vector<Slot *> slots;
+    std::atomic<unsigned> next{0};
+};
+
+struct slr_bc_table {
+    slr_ctx *ctx = nullptr;
+    SlrTableDev dev;
+    void *d_buckets = nullptr;                 // 4 tables, contiguous
+    void *d_stash_b[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *d_stash_s[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *d_ix_keys = nullptr, *d_ix_vals = nullptr, *d_rank = nullptr, *d_counts = nullptr;
+    long long n = 0, n_distinct = 0;
+};
+
+extern "C" {
+
+const char *slr_last_error(void) { return g_err.c_str(); }
+int slr_abi_version(void) { return SLR_ABI_VERSION; }
+int64_t slr_launch_count(void) { return g_launches.load(); }
+
+int slr_ctx_create(int device, int n_streams, slr_ctx **out)
+{
+    if (!out) return fail(SLR_E_INVALID, "slr_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(SLR_E_NODEVICE, "no CUDA device available (%s); libsicelore_gpu has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) return fail(SLR_E_INVALID, "device %d out of range (have %d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SLR_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    slr_ctx *c = new slr_ctx();
+    c->device = device;
+    c->n_slots = n_streams < 1 ? 1 : (n_streams > 64 ? 64 : n_streams);
+    for (int i = 0; i < c->n_slots; i++) {
+        Slot *s = new Slot();
+        for (int k = 0; k < 2; k++) {
+            e = cudaStreamCreateWithFlags(&s->stream[k], cudaStreamNonBlocking);
+            if (e != cudaSuccess) { delete s; slr_ctx_destroy(c); return fail(SLR_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        }
+        c->slots.push_back(s);
+    }
+    *out = c;
+    return SLR_OK;
+}
+
+void slr_ctx_destroy(slr_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (Slot *s : c->slots) {
+        for (int k = 0; k < 2; k++) {
+            if (s->stream[k]) { cudaStreamSynchronize(s->stream[k]); cudaStreamDestroy(s->stream[k]); }
+            s->slices[k].release(); s->anchor[k].release(); s->lens[k].release(); s->out[k].release();
+        }
+        s->umi.release(); s->joff.release(); s->ooff.release(); s->uout.release();
+        delete s;
+    }
+    delete c;
+}
+
+int slr_ctx_device(const slr_ctx *c) { return c ? c->device : -1; }
+
+// ---------------------------------------------------------------------------------------------------------
+int slr_bc_table_create(slr_ctx *ctx, const uint64_t *barcodes2bit, const int32_t *rank, int64_t n, int bc_len, slr_bc_table **out)
+{
+    if (!ctx || !out || (!barcodes2bit && n > 0) || n < 0) return fail(SLR_E_INVALID, "slr_bc_table_create: bad argument");
+    *out = nullptr;
+    if (bc_len != 16) return fail(SLR_E_UNSUPPORTED, "cell_bc_length %d not supported (only 16)", bc_len);
+    if (n > 0x7FFFFFFFLL) return fail(SLR_E_UNSUPPORTED, "more than 2^31 barcodes");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlrTableHost H;
+    slr_build_table(barcodes2bit, rank, n, H);
+    slr_bc_table *t = new slr_bc_table();
+    t->ctx = ctx; t->n = n; t->n_distinct = H.n_distinct;
+    memset(&t->dev, 0, sizeof(t->dev));
+    const size_t tbytes = ((size_t)16 << H.bbits) * sizeof(uint16_t);
+#define TRY_OR_FREE(expr)                                                                                       \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess) { slr_bc_table_destroy(t); return fail(SLR_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } \
+    } while (0)
+    TRY_OR_FREE(cudaMalloc(&t->d_buckets, 4 * tbytes));
+    for (int g = 0; g < 4; g++) {
+        char *base = (char *)t->d_buckets + g * tbytes;
+        TRY_OR_FREE(cudaMemcpy(base, H.slots[g].data(), tbytes, cudaMemcpyHostToDevice));
+        t->dev.bk[g] = reinterpret_cast<const uint4 *>(base);
+        const size_t sn = H.st_bucket[g].size();
+        t->dev.st_n[g] = (int)sn;
+        if (sn) {
+            TRY_OR_FREE(cudaMalloc(&t->d_stash_b[g], sn * 4));
+            TRY_OR_FREE(cudaMalloc(&t->d_stash_s[g], sn * 2));
+            TRY_OR_FREE(cudaMemcpy(t->d_stash_b[g], H.st_bucket[g].data(), sn * 4, cudaMemcpyHostToDevice));
+            TRY_OR_FREE(cudaMemcpy(t->d_stash_s[g], H.st_slot[g].data(), sn * 2, cudaMemcpyHostToDevice));
+        }
+        t->dev.st_bucket[g] = (const uint32_t *)t->d_stash_b[g];
+        t->dev.st_slot[g] = (const uint16_t *)t->d_stash_s[g];
+    }
+    t->dev.bbits = H.bbits;
+    const size_t ixn = (size_t)H.ix_mask + 1;
+    TRY_OR_FREE(cudaMalloc(&t->d_ix_keys, ixn * 4));
+    TRY_OR_FREE(cudaMalloc(&t->d_ix_vals, ixn * 4));
+    TRY_OR_FREE(cudaMemcpy(t->d_ix_keys, H.ix_keys.data(), ixn * 4, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(t->d_ix_vals, H.ix_vals.data(), ixn * 4, cudaMemcpyHostToDevice));
+    t->dev.ix_keys = (const uint32_t *)t->d_ix_keys;
+    t->dev.ix_vals = (const int32_t *)t->d_ix_vals;
+    t->dev.ix_mask = H.ix_mask;
+    if (rank && n > 0) {
+        TRY_OR_FREE(cudaMalloc(&t->d_rank, (size_t)n * 4));
+        TRY_OR_FREE(cudaMemcpy(t->d_rank, rank, (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    t->dev.rank = (const int32_t *)t->d_rank;
+    const size_t cbytes = (size_t)(n > 0 ? n : 1) * 3 * sizeof(unsigned long long);
+    TRY_OR_FREE(cudaMalloc(&t->d_counts, cbytes));
+    TRY_OR_FREE(cudaMemset(t->d_counts, 0, cbytes));
+    t->dev.counts = (unsigned long long *)t->d_counts;
+    t->dev.n = n;
+#undef TRY_OR_FREE
+    *out = t;
+    return SLR_OK;
+}
+
+void slr_bc_table_destroy(slr_bc_table *t)
+{
+    if (!t) return;
+    if (t->ctx) cudaSetDevice(t->ctx->device);
+    cudaFree(t->d_buckets);
+    for (int g = 0; g < 4; g++) { cudaFree(t->d_stash_b[g]); cudaFree(t->d_stash_s[g]); }
+    cudaFree(t->d_ix_keys); cudaFree(t->d_ix_vals); cudaFree(t->d_rank); cudaFree(t->d_counts);
+    delete t;
+}
+
+int64_t slr_bc_table_size(const slr_bc_table *t) { return t ? t->n_distinct : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+static int check_bc_args(const slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int stride, int slice_len, int64_t n)
+{
+    if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_assign: ctx / table is NULL");
+    if (ed_max < 0) return fail(SLR_E_INVALID, "bcEditDistance %d < 0", ed_max);
+    if (ed_max > 2) return fail(SLR_E_UNSUPPORTED, "bcEditDistance %d not supported by the GPU path (0, 1 or 2)", ed_max);
+    if (plusminus < 0 || 2 * plusminus + 1 > SLR_MAX_OFFSETS) return fail(SLR_E_UNSUPPORTED, "testPlusMinusPos %d not supported (0..4)", plusminus);
+    if (slice_len < 1 || slice_len > 32 || stride < slice_len) return fail(SLR_E_INVALID, "slice_len %d / stride %d invalid (1 <= slice_len <= 32 <= stride)", slice_len, stride);
+    if (n < 0) return fail(SLR_E_INVALID, "n < 0");
+    return SLR_OK;
+}
+
+int slr_bc_assign_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, const uint8_t *d_slices,
+                      int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, int64_t n, slr_bc_result *d_out,
+                      void *stream)
+{
+    int rc = check_bc_args(ctx, t, ed_max, plusminus, stride, slice_len, n);
+    if (rc) return rc;
+    if (n == 0) return SLR_OK;
+    if (!d_slices || !d_anchor || !d_out) return fail(SLR_E_INVALID, "slr_bc_assign_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (int64_t off = 0; off < n; off += (1LL << 30)) {           // grid.x limit: 2^31-1 blocks of 8 reads
+        const int64_t m = (n - off) < (1LL << 30) ? (n - off) : (1LL << 30);
+        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, d_slices + off * stride, stride, slice_len,
+                                      d_lens ? d_lens + off : nullptr, d_anchor + off, m, d_out + off, (cudaStream_t)stream));
+        g_launches++;
+    }
+    return SLR_OK;
+}
+
+int slr_bc_assign(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, const uint8_t *slices, int stride,
+                  int slice_len, const int32_t *lens, const int32_t *anchor, int64_t n, slr_bc_result *out)
+{
+    int rc = check_bc_args(ctx, t, ed_max, plusminus, stride, slice_len, n);
+    if (rc) return rc;
+    if (n == 0) return SLR_OK;
+    if (!slices || !anchor || !out) return fail(SLR_E_INVALID, "slr_bc_assign: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(s->mtx);
+    // chunked ping-pong pipeline: H2D of chunk c+1 (stream B) overlaps the kernel of chunk c (stream A)
+    int c = 0;
+    for (int64_t off = 0; off < n; off += BC_CHUNK, c++) {
+        const int64_t m = (n - off) < BC_CHUNK ? (n - off) : BC_CHUNK;
+        const int b = c & 1;
+        cudaStream_t st = s->stream[b];
+        CUDA_TRY(cudaStreamSynchronize(st));                       // buffers of this parity are free again
+        if ((rc = s->slices[b].reserve((size_t)m * stride))) return rc;
+        if ((rc = s->anchor[b].reserve((size_t)m * 4))) return rc;
+        if ((rc = s->out[b].reserve((size_t)m * sizeof(slr_bc_result)))) return rc;
+        if (lens && (rc = s->lens[b].reserve((size_t)m * 4))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s->slices[b].p, slices + off * stride, (size_t)m * stride, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s->anchor[b].p, anchor + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        if (lens) CUDA_TRY(cudaMemcpyAsync(s->lens[b].p, lens + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, (const uint8_t *)s->slices[b].p, stride, slice_len,
+                                      lens ? (const int32_t *)s->lens[b].p : nullptr, (const int32_t *)s->anchor[b].p, m,
+                                      (slr_bc_result *)s->out[b].p, st));
+        g_launches++;
+        CUDA_TRY(cudaMemcpyAsync(out + off, s->out[b].p, (size_t)m * sizeof(slr_bc_result), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(s->stream[1]));
+    return SLR_OK;
+}
+
+int slr_bc_counts_read(slr_ctx *ctx, const slr_bc_table *t, int64_t *counts_out)
+{
+    if (!ctx || !t || !counts_out) return fail(SLR_E_INVALID, "slr_bc_counts_read: NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(counts_out, t->d_counts, (size_t)t->n * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return SLR_OK;
+}
+
+int slr_bc_counts_reset(slr_ctx *ctx, slr_bc_table *t)
+{
+    if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_counts_reset: NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemset(t->d_counts, 0, (size_t)(t->n > 0 ? t->n : 1) * 3 * sizeof(int64_t)));
+    return SLR_OK;
+}
+
+int slr_bc_counts_device(const slr_bc_table *t, int64_t **d_counts, int64_t *n_elems)
+{
+    if (!t || !d_counts || !n_elems) return fail(SLR_E_INVALID, "slr_bc_counts_device: NULL argument");
+    *d_counts = (int64_t *)t->d_counts;
+    *n_elems = t->n * 3;
+    return SLR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int check_umi_args(const slr_ctx *ctx, int stride, int umi_len, int64_t n_jobs)
+{
+    if (!ctx) return fail(SLR_E_INVALID, "slr_umi_dist: ctx is NULL");
+    if (umi_len < 1 || umi_len > SLR_UMI_MAX_LEN) return fail(SLR_E_UNSUPPORTED, "umi_length %d not supported (1..%d)", umi_len, SLR_UMI_MAX_LEN);
+    if (stride < umi_len + 2) return fail(SLR_E_INVALID, "stride %d < umi_len + 2", stride);
+    if (n_jobs < 0) return fail(SLR_E_INVALID, "n_jobs < 0");
+    return SLR_OK;
+}
+
+int slr_umi_dist_dev(slr_ctx *ctx, const uint8_t *d_umis, int stride, int umi_len, const int64_t *d_job_offsets, int64_t n_jobs,
+                     int64_t n_reads, int32_t *d_out, const int64_t *d_out_offsets, int64_t n_out, void *stream)
+{
+    int rc = check_umi_args(ctx, stride, umi_len, n_jobs);
+    if (rc) return rc;
+    (void)n_out;
+    if (n_jobs == 0 || n_reads == 0) return SLR_OK;
+    if (!d_umis || !d_job_offsets || !d_out || !d_out_offsets) return fail(SLR_E_INVALID, "slr_umi_dist_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(slr_launch_umi_dist(d_umis, stride, umi_len, (const long long *)d_job_offsets, n_jobs, n_reads, d_out,
+                                 (const long long *)d_out_offsets, (cudaStream_t)stream));
+    g_launches++;
+    return SLR_OK;
+}
+
+int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs, int32_t *out,
+                 const int64_t *out_offsets)
+{
+    int rc = check_umi_args(ctx, stride, umi_len, n_jobs);
+    if (rc) return rc;
+    if (n_jobs == 0) return SLR_OK;
+    if (!umis || !job_offsets || !out || !out_offsets) return fail(SLR_E_INVALID, "slr_umi_dist: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(s->mtx);
+    cudaStream_t st = s->stream[0];
+    // job ranges of at most ~2^28 output cells per launch (a single larger job still goes in one launch)
+    const int64_t CELL_LIMIT = 1LL << 28;
+    std::vector<long long> joff, ooff;
+    int64_t j = 0;
+    while (j < n_jobs) {
+        int64_t j1 = j, cells = 0;
+        joff.clear(); ooff.clear();
+        const int64_t r0 = job_offsets[j];
+        while (j1 < n_jobs) {
+            const int64_t nj = job_offsets[j1 + 1] - job_offsets[j1];
+            if (nj < 0) return fail(SLR_E_INVALID, "job_offsets not monotone at %lld", (long long)j1);
+            if (j1 > j && cells + nj * nj > CELL_LIMIT) break;
+            joff.push_back(job_offsets[j1] - r0);
+            ooff.push_back(cells);
+            cells += nj * nj;
+            j1++;
+        }
+        joff.push_back(job_offsets[j1] - r0);
+        ooff.push_back(cells);
+        const int64_t nr = job_offsets[j1] - r0, nj_range = j1 - j;
+        if (nr > 0) {
+            if ((rc = s->umi.reserve((size_t)nr * stride))) return rc;
+            if ((rc = s->joff.reserve(joff.size() * 8))) return rc;
+            if ((rc = s->ooff.reserve(ooff.size() * 8))) return rc;
+            if ((rc = s->uout.reserve((size_t)cells * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s->umi.p, umis + r0 * stride, (size_t)nr * stride, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s->joff.p, joff.data(), joff.size() * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s->ooff.p, ooff.data(), ooff.size() * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(slr_launch_umi_dist((const uint8_t *)s->umi.p, stride, umi_len, (const long long *)s->joff.p, nj_range, nr,
+                                         (int32_t *)s->uout.p, (const long long *)s->ooff.p, st));
+            g_launches++;
+            // jobs may sit anywhere in the caller's `out`: copy back per contiguous run
+            int64_t a = j;
+            while (a < j1) {
+                int64_t b = a;
+                while (b + 1 < j1) {
+                    const int64_t nb = job_offsets[b + 1] - job_offsets[b];
+                    if (out_offsets[b + 1] != out_offsets[b] + nb * nb) break;
+                    b++;
+                }
+                const int64_t nb = job_offsets[b + 1] - job_offsets[b];
+                const int64_t ncell = ooff[b - j] + nb * nb - ooff[a - j];
+                if (ncell > 0)
+                    CUDA_TRY(cudaMemcpyAsync(out + out_offsets[a], (int32_t *)s->uout.p + ooff[a - j], (size_t)ncell * 4,
+                                             cudaMemcpyDeviceToHost, st));
+                a = b + 1;
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        j = j1;
+    }
+    return SLR_OK;
+}
+
+}  // extern "C"

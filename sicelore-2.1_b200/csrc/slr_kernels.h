@@ -1,0 +1,13 @@
+// slr_kernels.h — launchers of the CUDA kernels (internal to libsicelore_gpu.so)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "slr_table.cuh"
+#include "../../include/sicelore_gpu.h"
+
+cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, const uint8_t *d_slices,
+                                 int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, long long n,
+                                 slr_bc_result *d_out, cudaStream_t stream);
+
+cudaError_t slr_launch_umi_dist(const uint8_t *d_umis, int stride, int umi_len, const long long *d_job_offsets, long long n_jobs,
+                                long long n_reads, int32_t *d_out, const long long *d_out_offsets, cudaStream_t stream);

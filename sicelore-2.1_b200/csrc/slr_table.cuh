@@ -1,0 +1,219 @@
+// slr_table.cuh — device-resident barcode search set ("digit-group bucket tables").
+//
+// What it replaces: java.util.Set<Long>.contains on the fastutil key set of BarcodesMapForBCfinding,
+// probed once per mutant by BarcodeMatchTester.checkMatchWithTestSets
+// (F!com/rw/nanoporereadscanner/analyzers/BarcodeMatchTester.class, BarcodeMatchTester.java:L367-L374).
+//
+// Layout (B200: everything is sized to stay L2-resident, 4 x 16 MB for a 3 M list):
+//   a 16-nt barcode is 16 base-4 digits d0..d15 (d0 most significant, A=0 G=1 C=2 T=3).  Table g (g=0..3)
+//   "ignores" digit group g = digits 4g..4g+3: a key is split into  pat = those 8 bits  and  rest = the other
+//   24 bits.  rest goes through a 24-bit bijection; its top `bbits` bits select a 32-byte bucket (one L2
+//   sector), the remaining 24-bbits bits are a tag.  A bucket holds 16 uint16 slots
+//   slot = 0x8000 | tag << 8 | pat   (exact: (bucket, tag, pat) <-> key is a bijection), 0 = empty.
+//   => all single-edit neighbours of a node whose edit falls into digit group g share ONE bucket of table g,
+//   so one 32-byte load tests up to 16 mutants of the reference's enumeration at once.
+//   Buckets that overflow spill into a small sorted stash (checked only when a bucket is completely full).
+//
+// Everything here is __host__ __device__ so that tests/host_sim can run the same logic on the CPU.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+struct SlrTableDev {
+    const uint4 *bk[4];            // 2 x uint4 per bucket
+    const uint32_t *st_bucket[4];  // stash: sorted bucket ids
+    const uint16_t *st_slot[4];    //        and their slots
+    int st_n[4];
+    int bbits;                     // log2(#buckets), 17..22  (tag bits = 24 - bbits <= 7)
+    const uint32_t *ix_keys;       // key -> index map (open addressing, linear probing)
+    const int32_t *ix_vals;        //   -1 = empty
+    uint32_t ix_mask;
+    const int32_t *rank;           // CountsRank.rank per index (may be null)
+    unsigned long long *counts;    // n x 3 assigned-read counters by ED (BarcodeCounts.addCountForEd)
+    long long n;
+};
+
+#define SLR_HD __host__ __device__ __forceinline__
+
+// ---- intrinsics with host equivalents ----------------------------------------------------------------
+SLR_HD int slr_ffs(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x);
+#else
+    return x ? __builtin_ctz(x) + 1 : 0;
+#endif
+}
+SLR_HD int slr_popc(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+SLR_HD int slr_clz(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+SLR_HD uint32_t slr_brev(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+SLR_HD uint32_t slr_byte_perm(uint32_t a, uint32_t b, uint32_t s)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, s);
+#else
+    const uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((pool >> (8 * ((s >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+template <typename T> SLR_HD T slr_ldg(const T *p)
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+SLR_HD uint32_t slr_lowmask(int nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
+
+// 24-bit bijection (odd multipliers mod 2^24, xorshifts)
+SLR_HD uint32_t slr_mix24(uint32_t id)
+{
+    uint32_t m = (id * 0x9E3779u) & 0xFFFFFFu;
+    m ^= m >> 12;
+    m = (m * 0x85EBCBu) & 0xFFFFFFu;
+    m ^= m >> 11;
+    return m;
+}
+
+// split a 32-bit key for table g
+SLR_HD uint32_t slr_key_pat(uint32_t key, int g) { return (key >> (24 - 8 * g)) & 0xFFu; }
+SLR_HD uint32_t slr_key_rest(uint32_t key, int g)
+{
+    const int lo_bits = 24 - 8 * g;
+    const uint32_t hi = g == 0 ? 0u : (key >> (32 - 8 * g));
+    return (hi << lo_bits) | (key & slr_lowmask(lo_bits));
+}
+SLR_HD uint32_t slr_key_join(uint32_t rest, uint32_t pat, int g)
+{
+    const int lo_bits = 24 - 8 * g;
+    const uint32_t hi = rest >> lo_bits;
+    return (g == 0 ? 0u : (hi << (32 - 8 * g))) | (pat << lo_bits) | (rest & slr_lowmask(lo_bits));
+}
+SLR_HD uint32_t slr_ix_hash(uint32_t key) { return (key * 0x9E3779B1u) ^ (key >> 15); }
+
+// One bucket = 16 slots in two uint4.
+struct SlrBucket {
+    uint4 a, b;
+    SLR_HD uint32_t word(int i) const
+    {
+        switch (i) {
+        case 0: return a.x; case 1: return a.y; case 2: return a.z; case 3: return a.w;
+        case 4: return b.x; case 5: return b.y; case 6: return b.z; default: return b.w;
+        }
+    }
+    SLR_HD uint32_t slot(int i) const { const uint32_t w = word(i >> 1); return (i & 1) ? (w >> 16) : (w & 0xFFFFu); }
+};
+
+SLR_HD SlrBucket slr_load_bucket(const SlrTableDev &t, int g, uint32_t bucket)
+{
+    const uint4 *p = t.bk[g] + 2 * (size_t)bucket;
+    SlrBucket r;
+    r.a = slr_ldg(p);
+    r.b = slr_ldg(p + 1);
+    return r;
+}
+
+// Bit i of the result (i = 0..15) set  <=>  slot i is valid and carries `tag`.
+// The high bytes of the 16 slots are gathered with PRMT (selector 0x7531: byte1/byte3 of each word) and
+// compared bytewise with an exact zero-byte test.
+SLR_HD uint32_t slr_tag_match(const SlrBucket &k, uint32_t tag)
+{
+    const uint32_t want = (0x80u | tag) * 0x01010101u;
+    uint32_t h0 = slr_byte_perm(k.a.x, k.a.y, 0x7531) ^ want;   // slots 0..3
+    uint32_t h1 = slr_byte_perm(k.a.z, k.a.w, 0x7531) ^ want;   // slots 4..7
+    uint32_t h2 = slr_byte_perm(k.b.x, k.b.y, 0x7531) ^ want;   // slots 8..11
+    uint32_t h3 = slr_byte_perm(k.b.z, k.b.w, 0x7531) ^ want;   // slots 12..15
+    h0 = (((h0 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h0);              // bit 7 of each byte = byte != 0
+    h1 = (((h1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h1);
+    h2 = (((h2 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h2);
+    h3 = (((h3 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h3);
+    if (((h0 & h1 & h2 & h3) & 0x80808080u) == 0x80808080u) return 0u;     // fast path: nothing matches
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        m |= ((~h0 >> (7 + 8 * i)) & 1u) << i;
+        m |= ((~h1 >> (7 + 8 * i)) & 1u) << (4 + i);
+        m |= ((~h2 >> (7 + 8 * i)) & 1u) << (8 + i);
+        m |= ((~h3 >> (7 + 8 * i)) & 1u) << (12 + i);
+    }
+    return m;
+}
+
+SLR_HD bool slr_bucket_full(const SlrBucket &k)
+{
+    return ((k.a.x & k.a.y & k.a.z & k.a.w & k.b.x & k.b.y & k.b.z & k.b.w) & 0x80008000u) == 0x80008000u;
+}
+
+// first stash entry of `bucket` (lower bound); its entries end where st_bucket != bucket
+SLR_HD int slr_stash_lower(const SlrTableDev &t, int g, uint32_t bucket)
+{
+    int lo = 0, hi = t.st_n[g];
+    const uint32_t *b = t.st_bucket[g];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (slr_ldg(b + mid) < bucket) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// exact membership of one key (the ED-0 probe, BarcodeMatchTester.java:L204)
+SLR_HD bool slr_contains(const SlrTableDev &t, uint32_t key)
+{
+    const uint32_t m = slr_mix24(slr_key_rest(key, 0));
+    const int tb = 24 - t.bbits;
+    const uint32_t bucket = m >> tb, tag = m & ((1u << tb) - 1u);
+    const uint32_t want = 0x8000u | (tag << 8) | slr_key_pat(key, 0);
+    const SlrBucket k = slr_load_bucket(t, 0, bucket);
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t w = k.word(i);
+        hit |= ((w & 0xFFFFu) == want) | ((w >> 16) == want);
+    }
+    if (!hit && t.st_n[0] > 0 && slr_bucket_full(k)) {
+        for (int i = slr_stash_lower(t, 0, bucket); i < t.st_n[0] && slr_ldg(t.st_bucket[0] + i) == bucket; i++)
+            hit |= (uint32_t)slr_ldg(t.st_slot[0] + i) == want;
+    }
+    return hit;
+}
+
+// key -> index in the caller's barcode array (for rank / counters); -1 if absent
+SLR_HD int slr_index_of(const SlrTableDev &t, uint32_t key)
+{
+    uint32_t h = slr_ix_hash(key) & t.ix_mask;
+    while (true) {
+        const int v = slr_ldg(t.ix_vals + h);
+        if (v < 0) return -1;
+        if (slr_ldg(t.ix_keys + h) == key) return v;
+        h = (h + 1) & t.ix_mask;
+    }
+}

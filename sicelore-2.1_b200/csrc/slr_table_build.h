@@ -1,0 +1,101 @@
+// slr_table_build.h — host-side construction of the digit-group bucket tables (see slr_table.cuh).
+// Pure C++ (no CUDA calls): used by the C ABI (uploads the arrays) and by tests/host_sim (uses them in place).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "slr_table.cuh"
+
+struct SlrTableHost {
+    int bbits = 17;
+    std::vector<uint16_t> slots[4];            // (1 << bbits) * 16 per table
+    std::vector<uint32_t> st_bucket[4];        // sorted stash
+    std::vector<uint16_t> st_slot[4];
+    std::vector<uint32_t> ix_keys;
+    std::vector<int32_t> ix_vals;
+    uint32_t ix_mask = 0;
+    std::vector<int32_t> rank;                 // empty = none
+    long long n = 0;                           // number of input barcodes (index space of rank / counts)
+    long long n_distinct = 0;
+    long long n_ignored = 0;                   // entries with bits >= 32 set (can never equal a clean 16-nt window)
+};
+
+// bucket bits: ~6 keys per 16-slot bucket, clamped so that the tag fits 7 bits
+inline int slr_choose_bbits(long long n)
+{
+    int b = 17;
+    while (b < 22 && (6LL << b) < n) b++;
+    return b;
+}
+
+inline void slr_build_table(const uint64_t *keys, const int32_t *rank, long long n, SlrTableHost &T, int force_bbits = 0)
+{
+    T.n = n;
+    // ---- key -> first index map (duplicates keep the first index, like Map.put on a fresh map ignoring later puts) ----
+    uint32_t cap = 16;
+    while ((long long)cap < 2 * n + 2) cap <<= 1;
+    T.ix_mask = cap - 1;
+    T.ix_keys.assign(cap, 0);
+    T.ix_vals.assign(cap, -1);
+    std::vector<uint32_t> distinct;
+    distinct.reserve((size_t)n);
+    T.n_ignored = 0;
+    for (long long i = 0; i < n; i++) {
+        if (keys[i] >> 32) { T.n_ignored++; continue; }
+        const uint32_t k = (uint32_t)keys[i];
+        uint32_t h = slr_ix_hash(k) & T.ix_mask;
+        bool dup = false;
+        while (T.ix_vals[h] >= 0) {
+            if (T.ix_keys[h] == k) { dup = true; break; }
+            h = (h + 1) & T.ix_mask;
+        }
+        if (dup) continue;
+        T.ix_keys[h] = k;
+        T.ix_vals[h] = (int32_t)i;
+        distinct.push_back(k);
+    }
+    T.n_distinct = (long long)distinct.size();
+    if (rank) T.rank.assign(rank, rank + n); else T.rank.clear();
+
+    T.bbits = force_bbits ? force_bbits : slr_choose_bbits(T.n_distinct);
+    const int tb = 24 - T.bbits;
+    const size_t nb = (size_t)1 << T.bbits;
+    for (int g = 0; g < 4; g++) {
+        T.slots[g].assign(nb * 16, 0);
+        std::vector<uint8_t> fill(nb, 0);
+        std::vector<std::pair<uint32_t, uint16_t>> stash;
+        for (uint32_t k : distinct) {
+            const uint32_t m = slr_mix24(slr_key_rest(k, g));
+            const uint32_t bucket = m >> tb, tag = m & ((1u << tb) - 1u);
+            const uint16_t slot = (uint16_t)(0x8000u | (tag << 8) | slr_key_pat(k, g));
+            if (fill[bucket] < 16) T.slots[g][(size_t)bucket * 16 + fill[bucket]++] = slot;
+            else stash.emplace_back(bucket, slot);
+        }
+        std::sort(stash.begin(), stash.end());
+        T.st_bucket[g].clear();
+        T.st_slot[g].clear();
+        for (auto &e : stash) { T.st_bucket[g].push_back(e.first); T.st_slot[g].push_back(e.second); }
+    }
+}
+
+// view of host arrays as the device struct (for the CPU simulation)
+inline SlrTableDev slr_table_host_view(const SlrTableHost &T, unsigned long long *counts)
+{
+    SlrTableDev d;
+    memset(&d, 0, sizeof(d));
+    for (int g = 0; g < 4; g++) {
+        d.bk[g] = reinterpret_cast<const uint4 *>(T.slots[g].data());
+        d.st_bucket[g] = T.st_bucket[g].data();
+        d.st_slot[g] = T.st_slot[g].data();
+        d.st_n[g] = (int)T.st_bucket[g].size();
+    }
+    d.bbits = T.bbits;
+    d.ix_keys = T.ix_keys.data();
+    d.ix_vals = T.ix_vals.data();
+    d.ix_mask = T.ix_mask;
+    d.rank = T.rank.empty() ? nullptr : T.rank.data();
+    d.counts = counts;
+    d.n = T.n;
+    return d;
+}

@@ -1,0 +1,40 @@
+"""Freezes known-answer vectors from the CPU oracle into tests/golden/*.npz.
+
+The reference ships no tests or golden outputs for this path and cannot run here (JVM bytecode, no JDK), so these
+vectors pin the ORACLE against drift; they were produced by oracle/slr_oracle.c at the commit that added them and
+cross-checked against the independent restatement oracle/pyref.py.  Re-run only when a reference-reading bug is
+fixed:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import orc  # noqa: E402
+import workloads  # noqa: E402
+
+
+def main():
+    for name, seed, tp, ed, skew, dense in [("bc_3p_ed1", 101, True, 1, False, False), ("bc_3p_ed2", 102, True, 2, False, False),
+                                            ("bc_3p_ed2_skew", 103, True, 2, True, False), ("bc_5p_ed2", 104, False, 2, False, False),
+                                            ("bc_3p_ed2_dense", 105, True, 2, True, True), ("bc_5p_ed1_dense", 106, False, 1, False, True),
+                                            ("bc_3p_ed0", 107, True, 0, False, False)]:
+        _, slices, anchors, wl = workloads.adversarial(seed, tp, 160, skew=skew, dense=dense)
+        rank = np.arange(1, len(wl) + 1, dtype=np.int32)
+        res, probes = orc.assign_barcode_batch(orc.BarcodeSet(wl, rank), slices, anchors, ed, 2, tp)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), slices=slices, anchor=anchors, whitelist=wl, rank=rank,
+                            ed=np.int32(ed), three_prime=np.int32(tp), result=res, probes=np.int64(probes))
+        print(name, len(wl), int((res["flags"] & 1).sum()), probes)
+    for umi_len in (12, 10):
+        umis, offs = workloads.umi_jobs(200 + umi_len, umi_len, n_jobs=30, max_n=24)
+        m, oo = orc.umi_matrix_batch(umis, offs, umi_len)
+        np.savez_compressed(os.path.join(HERE, "umi_len%d.npz" % umi_len), umis=umis, job_offsets=offs, umi_len=np.int32(umi_len),
+                            matrix=m, out_offsets=oo)
+        print("umi", umi_len, len(m))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+// bc_sim.cu — TEST INFRASTRUCTURE: replays the warp orchestration of bc_assign.cu sequentially on the CPU,
+// using the very same __host__ __device__ per-lane code (bc_core.cuh, slr_table.cuh) and the same table
+// builder.  Lets the algorithm (digit-group buckets, traversal ranks, visited-time logic, HashSet order) be
+// checked against the oracle in the GPU-less build container.  Never part of the product library.
+#include <cstdio>
+#include <vector>
+#include "../../sicelore-2.1_b200/csrc/bc_core.cuh"
+#include "../../sicelore-2.1_b200/csrc/slr_table_build.h"
+
+static void vh_insert_host(unsigned long long *tab, uint32_t v, uint32_t t)
+{
+    uint32_t slot = slr_vh_slot(v);
+    const unsigned long long val = ((unsigned long long)v << 32) | t;
+    while (true) {
+        unsigned long long cur = tab[slot];
+        if (cur == SLR_VH_EMPTY) { tab[slot] = val; return; }
+        if ((uint32_t)(cur >> 32) == v) { if (val < cur) tab[slot] = val; return; }
+        slot = (slot + 1) & (SLR_VH_SIZE - 1);
+    }
+}
+
+static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, const uint8_t *slice, int len, int anc,
+                     slr_bc_result *out, long long *n_loads)
+{
+    SlrSliceBits sb = {0, 0, 0, 0, 0};
+    for (int lane = 0; lane < 32; lane++) {
+        const uint32_t ch = lane < len ? slice[lane] : 0u;
+        const uint32_t c2 = slr_code2(ch);
+        sb.bit0 |= (c2 & 1u) << lane;
+        sb.bit1 |= ((c2 >> 1) & 1u) << lane;
+        sb.nonacgt |= (uint32_t)(c2 == 4u) << lane;
+        sb.unknown |= (uint32_t)(!slr_in_encode_matrix(ch)) << lane;
+        sb.over253 |= (uint32_t)(ch >= 254u) << lane;
+    }
+    static thread_local unsigned long long vh[SLR_VH_SIZE];
+    uint8_t live[160];
+    SlrMatchStore ms;
+    memset(&ms, 0, sizeof(ms));
+    uint32_t flags = 0;
+    const int noff = 2 * plusminus + 1;
+    for (int k = 0; k < noff; k++) {
+        uint32_t w, p1, p2;
+        bool dead_window;
+        if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window)) { flags |= SLR_F_EXCEPTION; break; }
+        ms.m_w[k] = w;
+        if (dead_window) continue;
+        uint32_t valid_levels = slr_contains(tab, w) ? 1u : 0u;
+        (*n_loads)++;
+        if (valid_levels) { ms.m_bc[k][0] = w; ms.m_cnt[k][0] = 0; }
+        if (ed_max >= 1) {
+            const bool use_vis = ed_max >= 2;
+            if (use_vis) {
+                for (int i = 0; i < SLR_VH_SIZE; i++) vh[i] = SLR_VH_EMPTY;
+                for (int sl = 0; sl < 144; sl++) {
+                    const int p = sl / 9, j = 8 - (sl - p * 9);
+                    bool v, d;
+                    const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
+                    if (v) vh_insert_host(vh, mval, (uint32_t)(p * 16 + (8 - j)));
+                }
+            }
+            SlrExpand e;
+            e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.level = 1; e.use_visited = use_vis;
+            uint32_t rmin = SLR_NONE32, bc1 = 0;
+            for (int lane = 0; lane < 16; lane++) {
+                const int g = (lane >> 2) & 3, op = lane & 3;
+                if (op == 3) continue;
+                uint32_t b = 0;
+                const uint32_t r = slr_expand_group(tab, e, vh, g, op, b);
+                (*n_loads)++;
+                if (r < rmin) { rmin = r; bc1 = b; }
+            }
+            if (rmin != SLR_NONE32) { valid_levels |= 2u; ms.m_bc[k][1] = bc1; ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin % 9u); }
+            if (use_vis) {
+                int nlive = 0;
+                for (int sl = 0; sl < 144; sl++) {
+                    const int p = sl / 9, j = 8 - (sl - p * 9);
+                    bool v, d;
+                    const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
+                    if (v && !d && !slr_is_visited(e, vh, mval, p)) live[nlive++] = (uint8_t)sl;
+                }
+                for (int it = 0; it * 2 < nlive; it++) {
+                    uint32_t m2 = SLR_NONE32, bc2 = 0, c1w = 0;
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int g = (lane >> 2) & 3, op = lane & 3, h = lane >> 4;
+                        const int idx = it * 2 + h;
+                        if (!(idx < nlive && op < 3)) continue;
+                        const int sl = live[idx];
+                        const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
+                        bool v, d;
+                        SlrExpand e2;
+                        e2.cs = slr_gen_mutant(w, p, j, p1, v, d);
+                        e2.w = w; e2.pskip = p; e2.level = 2; e2.use_visited = true;
+                        e2.cbase = (j >= 4 && j < 8) ? p2 : p1;
+                        e2.tproc = (uint32_t)(p * 16 + jj);
+                        uint32_t b = 0;
+                        uint32_t r2 = slr_expand_group(tab, e2, vh, g, op, b);
+                        (*n_loads)++;
+                        if (r2 != SLR_NONE32) r2 |= (uint32_t)h << 16;
+                        if (r2 < m2) { m2 = r2; bc2 = b; c1w = slr_cnt_of((uint32_t)j); }
+                    }
+                    if (m2 != SLR_NONE32) {
+                        valid_levels |= 4u;
+                        ms.m_bc[k][2] = bc2;
+                        ms.m_cnt[k][2] = (uint8_t)(c1w + slr_cnt_of((m2 & 0xFFFFu) % 9u));
+                        break;
+                    }
+                }
+            }
+        }
+        ms.m_valid[k] = (uint8_t)valid_levels;
+    }
+    slr_bc_result res;
+    memset(&res, 0, sizeof(res));
+    res.ed = -1; res.ed_second = 0x7FFFFFFF; res.rank = -1; res.flags = flags;
+    if (!(flags & SLR_F_EXCEPTION)) {
+        const int lv = slr_decide(ms, noff, ed_max, res);
+        if (lv >= 0) {
+            const int ix = slr_index_of(tab, (uint32_t)res.bc);
+            res.rank = (ix >= 0 && tab.rank) ? tab.rank[ix] : ix;
+            if (ix >= 0 && tab.counts) tab.counts[(size_t)ix * 3 + lv]++;
+        }
+    }
+    *out = res;
+}
+
+extern "C" int sim_bc_assign(const uint64_t *keys, const int32_t *rank, int64_t n_keys, int force_bbits, int ed_max, int plusminus,
+                             int three_prime, const uint8_t *slices, int stride, int slice_len, const int32_t *lens,
+                             const int32_t *anchor, int64_t n, slr_bc_result *out, unsigned long long *counts, long long *n_loads,
+                             long long *stash_sizes)
+{
+    SlrTableHost T;
+    slr_build_table(keys, rank, n_keys, T, force_bbits);
+    SlrTableDev tab = slr_table_host_view(T, counts);
+    long long loads = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int len = lens ? (lens[i] < slice_len ? lens[i] : slice_len) : slice_len;
+        sim_read(tab, ed_max, plusminus, three_prime, slices + i * stride, len, anchor[i], &out[i], &loads);
+    }
+    if (n_loads) *n_loads = loads;
+    if (stash_sizes) for (int g = 0; g < 4; g++) stash_sizes[g] = (long long)T.st_bucket[g].size();
+    return 0;
+}
+
+// ---- UMI distance: same per-pair code as umi_dist.cu, rows walked sequentially ---------------------------
+#include "../../sicelore-2.1_b200/csrc/umi_core.cuh"
+extern "C" int sim_umi_dist(const uint8_t *umis, int stride, int umi_len, const long long *job_offsets, long long n_jobs, int32_t *out,
+                            const long long *out_offsets)
+{
+    for (long long j = 0; j < n_jobs; j++) {
+        const long long j0 = job_offsets[j], n = job_offsets[j + 1] - j0;
+        int32_t *mat = out + out_offsets[j];
+        for (long long i = 0; i < n; i++) {
+            const unsigned long long rowp = slr_umi_pack(umis + (j0 + i) * stride, umi_len + 2);
+            uint32_t peq[48];
+            for (int e = 0; e < 48; e++) peq[e] = slr_umi_peq_entry(rowp, umi_len, e >> 4, (uint32_t)(e & 15));
+            for (long long v = i; v < n; v++) {
+                if (v == i) { mat[i * n + i] = slr_umi_equality(); continue; }
+                const unsigned long long colp = slr_umi_pack(umis + (j0 + v) * stride, umi_len + 2);
+                const int32_t e = slr_umi_best9(peq, umi_len, colp);
+                mat[i * n + v] = e;
+                mat[v * n + i] = slr_umi_transpose(e);
+            }
+        }
+    }
+    return 0;
+}
