@@ -20,7 +20,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_GPU = os.path.join(_HERE, "libsicelore_gpu.so")
+LIB_GPU = os.environ.get("SLR_LIB_GPU") or os.path.join(_HERE, "libsicelore_gpu.so")   # override: kernel experiments only
 LIB_SYNTH = os.path.join(_HERE, "libslr_synth.so")
 NVCC = os.environ.get("SLR_NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++"            # $CXX in this image points at a gcc without libgomp

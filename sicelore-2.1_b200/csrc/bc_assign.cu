@@ -26,180 +26,228 @@ namespace {
 
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr unsigned FULL = 0xFFFFFFFFu;
+#ifndef SLR_BC_MINB_ED2
+#define SLR_BC_MINB_ED2 3                      // resident CTAs per SM the ED-2 kernel is compiled for (register cap 80)
+#endif
 
-struct WarpShared {
+struct alignas(16) WarpShared {
     unsigned long long vh[SLR_VH_SIZE];        // visited hash: (value << 32) | processing time
-    uint8_t live[160];                         // level-1 nodes to expand, in processing order
+    uint2 node[144];                           // level-1 nodes to expand, in processing order: (sequence, slr_node_meta)
     SlrMatchStore ms;
 };
 
-__device__ __forceinline__ void vh_insert(unsigned long long *tab, uint32_t v, uint32_t t)
+// first insertion wins: the caller inserts in increasing processing time (rounds in order, duplicates inside a
+// round removed with __match_any_sync), so an existing key always carries the smaller time.
+__device__ __forceinline__ void vh_insert_first(unsigned long long *tab, uint32_t v, uint32_t t)
 {
     uint32_t slot = slr_vh_slot(v);
     const unsigned long long val = ((unsigned long long)v << 32) | t;
     while (true) {
         unsigned long long cur = *((volatile unsigned long long *)&tab[slot]);
         if (cur == SLR_VH_EMPTY) {
-            const unsigned long long old = atomicCAS(&tab[slot], SLR_VH_EMPTY, val);
-            if (old == SLR_VH_EMPTY) return;
-            cur = old;
+            cur = atomicCAS(&tab[slot], SLR_VH_EMPTY, val);
+            if (cur == SLR_VH_EMPTY) return;
         }
-        if ((uint32_t)(cur >> 32) == v) { atomicMin(&tab[slot], val); return; }
+        if ((uint32_t)(cur >> 32) == v) return;
         slot = (slot + 1) & (SLR_VH_SIZE - 1);
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-bc_assign_kernel(SlrTableDev tab, int ed_max, int plusminus, int three_prime, const uint8_t *__restrict__ slices,
-                 int stride, int slice_len, const int32_t *__restrict__ lens, const int32_t *__restrict__ anchor,
-                 long long n, slr_bc_result *__restrict__ out)
+// Persistent warps: warp i of the grid takes reads i, i + #warps, ... (reads are i.i.d., a static stride balances).
+template <int EDMAX>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EDMAX >= 2 ? SLR_BC_MINB_ED2 : 4)
+bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t *__restrict__ slices, int stride, int slice_len,
+                 const int32_t *__restrict__ lens, const int32_t *__restrict__ anchor, long long n, slr_bc_result *__restrict__ out)
 {
     __shared__ WarpShared smem[WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const long long read = (long long)blockIdx.x * WARPS_PER_BLOCK + wib;
-    if (read >= n) return;
     WarpShared &S = smem[wib];
-
-    // ---- the slice: lane i owns char i; bit planes by ballot ------------------------------------------------
-    const int len = lens ? min(lens[read], slice_len) : slice_len;
-    const uint32_t ch = (lane < len) ? (uint32_t)slices[read * (long long)stride + lane] : 0u;
-    const int anc = anchor[read];
-    const uint32_t c2 = slr_code2(ch);
-    SlrSliceBits sb;
-    sb.bit0 = __ballot_sync(FULL, c2 & 1u);
-    sb.bit1 = __ballot_sync(FULL, (c2 >> 1) & 1u);
-    sb.nonacgt = __ballot_sync(FULL, c2 == 4u);
-    sb.unknown = __ballot_sync(FULL, !slr_in_encode_matrix(ch));
-    sb.over253 = __ballot_sync(FULL, ch >= 254u);
-
-    uint32_t flags = 0;
+    const long long nwarps = (long long)gridDim.x * WARPS_PER_BLOCK;
     const int noff = 2 * plusminus + 1;
-    if (lane < SLR_MAX_OFFSETS) S.ms.m_valid[lane] = 0;
-    __syncwarp();
+    // root expansion: lanes 0..11 = (digit group, op); lane 0's bucket (table 0, rest of w) also answers the ED-0 probe
+    const int g1 = (lane * 11) >> 5, op1 = lane - 3 * g1;
 
-    const int g = (lane >> 2) & 3, op = lane & 3, h = lane >> 4;
+    for (long long read = (long long)blockIdx.x * WARPS_PER_BLOCK + wib; read < n; read += nwarps) {
+        // ---- the slice: lane i owns char i; bit planes by ballot --------------------------------------------
+        const int len = lens ? min(lens[read], slice_len) : slice_len;
+        const uint32_t ch = (lane < len) ? (uint32_t)slices[read * (long long)stride + lane] : 0u;
+        const int anc = anchor[read];
+        const uint32_t c2 = slr_code2(ch);
+        SlrSliceBits sb;
+        sb.bit0 = __ballot_sync(FULL, c2 & 1u);
+        sb.bit1 = __ballot_sync(FULL, (c2 >> 1) & 1u);
+        sb.nonacgt = __ballot_sync(FULL, c2 == 4u);
+        sb.unknown = __ballot_sync(FULL, !slr_in_encode_matrix(ch));
+        sb.over253 = __ballot_sync(FULL, ch >= 254u);
 
-    for (int k = 0; k < noff; k++) {
-        uint32_t w, p1, p2;
-        bool dead_window;
-        if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window)) {
-            flags |= SLR_F_EXCEPTION;
-            break;
-        }
-        if (lane == 0) S.ms.m_w[k] = w;
-        if (dead_window) continue;
+        uint32_t flags = 0;
+        if (lane < SLR_MAX_OFFSETS) S.ms.m_valid[lane] = 0;
+        __syncwarp();
 
-        // ======== BarcodeMatchTester.doJob for this window ====================================================
-        uint32_t valid_levels = 0;
-        if (lane == 3) valid_levels = slr_contains(tab, w) ? 1u : 0u;             // ED 0 (L204-L206)
-        valid_levels = __shfl_sync(FULL, valid_levels, 3);
-        if (valid_levels && lane == 0) { S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; }
-
-        if (ed_max >= 1) {
-            const bool use_vis = ed_max >= 2;
-            if (use_vis) {
-                // visited hash over the 139 level-1 mutants; processing time t = p*16 + (8-j): the nodes of one
-                // root position are popped in reverse creation order (ArrayDeque add / pollLast, L212-L218)
-                for (int i = lane; i < SLR_VH_SIZE; i += 32) S.vh[i] = SLR_VH_EMPTY;
-                __syncwarp();
-                for (int r = 0; r < 5; r++) {
-                    const int sl = r * 32 + lane;
-                    if (sl < 144) {
-                        const int p = sl / 9, j = 8 - (sl - p * 9);
-                        bool v, d;
-                        const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
-                        if (v) vh_insert(S.vh, mval, (uint32_t)(p * 16 + (8 - j)));
-                    }
-                }
-                __syncwarp();
+        for (int k = 0; k < noff; k++) {
+            uint32_t w, p1, p2;
+            bool dead_window;
+            if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, EDMAX, w, p1, p2, dead_window)) {
+                flags |= SLR_F_EXCEPTION;
+                break;
             }
+            if (lane == 0) S.ms.m_w[k] = w;
+            if (dead_window) continue;
+
+            // ======== BarcodeMatchTester.doJob for this window ================================================
+            // issue the root's bucket loads first: their latency overlaps the visited-hash construction
             SlrExpand e;
-            e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.level = 1; e.use_visited = use_vis;
-            uint32_t r1 = SLR_NONE32, bc1 = 0;
-            if (lane < 16 && op < 3) r1 = slr_expand_group(tab, e, S.vh, g, op, bc1);
-            const uint32_t rmin = __reduce_min_sync(FULL, r1);
-            if (rmin != SLR_NONE32) {                                             // first ED-1 hit in creation order
-                const int src = __ffs((int)__ballot_sync(FULL, r1 == rmin)) - 1;
-                bc1 = __shfl_sync(FULL, bc1, src);
-                valid_levels |= 2u;
-                if (lane == 0) { S.ms.m_bc[k][1] = bc1; S.ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin % 9u); }
+            e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.use_visited = EDMAX >= 2;
+            SlrProbe pr1;
+            SlrBucket bk1;
+            const bool root_lane = EDMAX >= 1 ? lane < 12 : lane == 0;
+            if (root_lane) {
+                pr1 = slr_probe_addr(tab, w, p1, g1, op1);
+                bk1 = slr_load_bucket(tab, g1, pr1.bucket);
             }
-            if (use_vis) {
-                // ---- level-1 nodes the reference expands, in processing order ------------------------------
-                int nlive = 0;
+
+            uint32_t mv[5];
+            uint32_t mflags = 0;                                    // bit r: valid, bit 8 + r: expandable (valid, not dead)
+            if (EDMAX >= 2) {
+                // visited hash over the 139 level-1 mutants; processing time t = p*16 + (8-j)
+                ulonglong2 *vh2 = reinterpret_cast<ulonglong2 *>(S.vh);
+#pragma unroll
+                for (int i = 0; i < SLR_VH_SIZE / 64; i++) vh2[i * 32 + lane] = make_ulonglong2(SLR_VH_EMPTY, SLR_VH_EMPTY);
+                __syncwarp();
+#pragma unroll
                 for (int r = 0; r < 5; r++) {
                     const int sl = r * 32 + lane;
-                    bool livenode = false;
-                    if (sl < 144) {
-                        const int p = sl / 9, j = 8 - (sl - p * 9);
-                        bool v, d;
-                        const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
-                        livenode = v && !d && !slr_is_visited(e, S.vh, mval, p);
+                    const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
+                    bool v, d;
+                    mv[r] = slr_gen_mutant(w, p & 15, j, p1, v, d);
+                    v = v && sl < 144;
+                    const uint32_t vmask = __ballot_sync(FULL, v);
+                    const uint32_t peers = __match_any_sync(FULL, mv[r]);
+                    if (v) {
+                        mflags |= 1u << r;
+                        if (!d) mflags |= 0x100u << r;
+                        if ((peers & vmask & ((1u << lane) - 1u)) == 0u) vh_insert_first(S.vh, mv[r], (uint32_t)(p * 16 + jj));
                     }
+                    __syncwarp();
+                }
+            }
+
+            // ---- ED 0 (L204-L206) and ED 1: first hit in creation order = warp minimum of the traversal ranks --
+            uint32_t r1 = SLR_NONE32, bc1 = 0;
+            bool hit0 = false;
+            if (root_lane) {
+                if (lane == 0) hit0 = slr_contains_in(tab, bk1, pr1.bucket, pr1.tag, w >> 24);
+                if (EDMAX >= 1) r1 = slr_probe_eval<1>(tab, e, S.vh, g1, op1, pr1, bk1, bc1);
+            }
+            uint32_t valid_levels = __shfl_sync(FULL, hit0 ? 1u : 0u, 0);
+            if (valid_levels && lane == 0) { S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; }
+            if (EDMAX >= 1) {
+                const uint32_t rmin = __reduce_min_sync(FULL, r1);
+                if (rmin != SLR_NONE32) {
+                    const int src = __ffs((int)__ballot_sync(FULL, r1 == rmin)) - 1;
+                    bc1 = __shfl_sync(FULL, bc1, src);
+                    valid_levels |= 2u;
+                    if (lane == 0) { S.ms.m_bc[k][1] = bc1; S.ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
+                }
+            }
+            if (EDMAX >= 2) {
+                // ---- level-1 nodes the reference expands, in processing order ----------------------------------
+                int nlive = 0;
+#pragma unroll
+                for (int r = 0; r < 5; r++) {
+                    const int sl = r * 32 + lane;
+                    const int p = sl / 9, j = 8 - (sl - p * 9);
+                    const bool livenode = ((mflags >> (8 + r)) & 1u) && !slr_is_visited<1>(e, S.vh, mv[r], p);
                     const uint32_t bal = __ballot_sync(FULL, livenode);
-                    if (livenode) S.live[nlive + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)sl;
+                    if (livenode) S.node[nlive + __popc(bal & ((1u << lane) - 1u))] = make_uint2(mv[r], slr_node_meta(p, j, p1, p2));
                     nlive += __popc(bal);
                 }
                 __syncwarp();
-                // ---- level 2: two nodes per warp step; stop at the first step with a valid hit -------------
-                for (int it = 0; it * 2 < nlive; it++) {
-                    const int idx = it * 2 + h;
+                // ---- level 2: probe pi = node * 12 + (group, op); 32 probes per warp step.  The search for the ED-2
+                // slot stops once a hit is known and every probe of its node has been evaluated (later nodes only
+                // have larger ranks; the reference keeps enumerating but HashSet.add is then a no-op).
+                const int nprobe = nlive * 12;
+                uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
+                for (int base = 0; base < nprobe; base += 32) {
+                    const int pi = base + lane;
                     uint32_t r2 = SLR_NONE32, bc2 = 0, c1 = 0;
-                    if (idx < nlive && op < 3) {
-                        const int sl = S.live[idx];
-                        const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
-                        bool v, d;
-                        SlrExpand e2;
-                        e2.cs = slr_gen_mutant(w, p, j, p1, v, d);
-                        e2.w = w; e2.pskip = p; e2.level = 2; e2.use_visited = true;
-                        e2.cbase = (j >= 4 && j < 8) ? p2 : p1;                   // post[nDel+1]; nDel = 1 below an INS node
-                        e2.tproc = (uint32_t)(p * 16 + jj);
-                        c1 = slr_cnt_of((uint32_t)j);
-                        r2 = slr_expand_group(tab, e2, S.vh, g, op, bc2);
-                        if (r2 != SLR_NONE32) r2 |= (uint32_t)h << 16;
+                    if (pi < nprobe) {
+                        const int nd = pi / 12, rem = pi - nd * 12;
+                        const int g = (rem * 11) >> 5, op = rem - 3 * g;
+                        const uint2 nrec = S.node[nd];
+                        const SlrExpand e2 = slr_node_expand(nrec.x, nrec.y, w);
+                        c1 = nrec.y >> 10;
+                        r2 = slr_expand_group<2>(tab, e2, S.vh, g, op, bc2);
+                        if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
                     }
                     const uint32_t m2 = __reduce_min_sync(FULL, r2);
-                    if (m2 != SLR_NONE32) {
+                    if (m2 < best) {
                         const int src = __ffs((int)__ballot_sync(FULL, r2 == m2)) - 1;
-                        bc2 = __shfl_sync(FULL, bc2, src);
-                        c1 = __shfl_sync(FULL, c1, src);
-                        valid_levels |= 4u;
-                        if (lane == 0) {
-                            S.ms.m_bc[k][2] = bc2;
-                            S.ms.m_cnt[k][2] = (uint8_t)(c1 + slr_cnt_of((m2 & 0xFFFFu) % 9u));
-                        }
-                        break;
+                        bcb = __shfl_sync(FULL, bc2, src);
+                        cntb = __shfl_sync(FULL, c1, src);
+                        best = m2;
                     }
+                    if (best != SLR_NONE32 && (int)(best >> 8) * 12 + 12 <= base + 32) break;
+                }
+                if (best != SLR_NONE32) {
+                    valid_levels |= 4u;
+                    if (lane == 0) { S.ms.m_bc[k][2] = bcb; S.ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u)); }
                 }
             }
+            if (lane == 0) S.ms.m_valid[k] = (uint8_t)valid_levels;
+            __syncwarp();
         }
-        if (lane == 0) S.ms.m_valid[k] = (uint8_t)valid_levels;
+        __syncwarp();
+
+        // ======== merge + decision (Parser.java:L240-L311); uniform across the warp, lane 0 writes ============
+        slr_bc_result res;
+        res.bc = 0; res.ed = -1; res.ed_second = 0x7FFFFFFF; res.offset = 0; res.n_ins = 0; res.n_del = 0; res.n_sub = 0;
+        res.rank = -1; res.flags = flags;
+        if (!(flags & SLR_F_EXCEPTION)) {
+            const int lv = slr_decide(S.ms, noff, EDMAX, res);
+            if (lv >= 0 && lane == 0) {
+                const int ix = slr_index_of(tab, (uint32_t)res.bc);
+                res.rank = (ix >= 0 && tab.rank) ? tab.rank[ix] : ix;                  // CountsRank.rank (L267-L269)
+                if (ix >= 0 && tab.counts) atomicAdd(&tab.counts[(size_t)ix * 3 + lv], 1ull);   // BarcodeCounts.addCountForEd (L305-L311)
+            }
+        }
+        if (lane == 0) {
+            uint4 *o = reinterpret_cast<uint4 *>(out + read);
+            uint4 v0, v1;
+            v0.x = (uint32_t)res.bc; v0.y = (uint32_t)(res.bc >> 32); v0.z = (uint32_t)res.ed; v0.w = (uint32_t)res.ed_second;
+            v1.x = (uint32_t)(uint8_t)res.offset | ((uint32_t)(uint8_t)res.n_ins << 8) | ((uint32_t)(uint8_t)res.n_del << 16) |
+                   ((uint32_t)(uint8_t)res.n_sub << 24);
+            v1.y = (uint32_t)res.rank; v1.z = res.flags; v1.w = 0;
+            o[0] = v0; o[1] = v1;
+        }
         __syncwarp();
     }
-    __syncwarp();
+}
 
-    // ======== merge + decision (Parser.java:L240-L311); uniform across the warp, lane 0 writes ================
-    slr_bc_result res;
-    res.bc = 0; res.ed = -1; res.ed_second = 0x7FFFFFFF; res.offset = 0; res.n_ins = 0; res.n_del = 0; res.n_sub = 0;
-    res.rank = -1; res.flags = flags;
-    if (!(flags & SLR_F_EXCEPTION)) {
-        const int lv = slr_decide(S.ms, noff, ed_max, res);
-        if (lv >= 0 && lane == 0) {
-            const int ix = slr_index_of(tab, (uint32_t)res.bc);
-            res.rank = (ix >= 0 && tab.rank) ? tab.rank[ix] : ix;                  // CountsRank.rank (L267-L269)
-            if (ix >= 0 && tab.counts) atomicAdd(&tab.counts[(size_t)ix * 3 + lv], 1ull);   // BarcodeCounts.addCountForEd (L305-L311)
-        }
+template <int EDMAX>
+cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, const uint8_t *d_slices, int stride, int slice_len,
+                     const int32_t *d_lens, const int32_t *d_anchor, long long n, slr_bc_result *d_out, cudaStream_t stream)
+{
+    static int resident_ctas[64];                                // per device: #SMs x resident CTAs per SM
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (resident_ctas[dev] == 0) {
+        int bps = 0, sms = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_assign_kernel<EDMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bc_assign_kernel<EDMAX>, WARPS_PER_BLOCK * 32, 0);
+        if (e != cudaSuccess) return e;
+        resident_ctas[dev] = sms * (bps > 0 ? bps : 1);
     }
-    if (lane == 0) {
-        uint4 *o = reinterpret_cast<uint4 *>(out + read);
-        uint4 v0, v1;
-        v0.x = (uint32_t)res.bc; v0.y = (uint32_t)(res.bc >> 32); v0.z = (uint32_t)res.ed; v0.w = (uint32_t)res.ed_second;
-        v1.x = (uint32_t)(uint8_t)res.offset | ((uint32_t)(uint8_t)res.n_ins << 8) | ((uint32_t)(uint8_t)res.n_del << 16) |
-               ((uint32_t)(uint8_t)res.n_sub << 24);
-        v1.y = (uint32_t)res.rank; v1.z = res.flags; v1.w = 0;
-        o[0] = v0; o[1] = v1;
-    }
+    const long long need = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const long long resident = resident_ctas[dev];               // one wave of persistent CTAs: a multiple of the SM count
+    const unsigned blocks = (unsigned)(need < resident ? need : resident);
+    bc_assign_kernel<EDMAX><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens,
+                                                                        d_anchor, n, d_out);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -209,8 +257,10 @@ cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusmin
                                  slr_bc_result *d_out, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
-    const long long blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    bc_assign_kernel<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(tab, ed_max, plusminus, three_prime, d_slices, stride,
-                                                                           slice_len, d_lens, d_anchor, n, d_out);
-    return cudaGetLastError();
+    switch (ed_max) {
+    case 0: return launch_t<0>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+    case 1: return launch_t<1>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+    case 2: return launch_t<2>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+    default: return cudaErrorInvalidValue;
+    }
 }

@@ -42,35 +42,20 @@ SLR_HD uint32_t slr_vh_tmin(const unsigned long long *tab, uint32_t v)
 // ---- level-1 mutant of window w: root position p, creation index j (0-3 SUB A,G,C,T; 4-7 INS; 8 DEL) ----
 // low 32 bits of getLongHashReplaceByteDeg / InsertByteDeg / deleteByte (java:L228-L234, L300-L310, L321-L327).
 // dead = the Java value carries garbage in bits 62-63 (insert at p = L-2 shifts by 64 == 0): never matches,
-// but its (int) value still enters the visited set.
+// but its (int) value still enters the visited set.  Straight-line (lanes of one warp mix all three kinds).
 SLR_HD uint32_t slr_gen_mutant(uint32_t w, int p, int j, uint32_t cbase, bool &valid, bool &dead)
 {
     const int sh = 2 * (15 - p);
-    dead = false;
-    if (j < 4) {
-        valid = ((w >> sh) & 3u) != (uint32_t)j;               // s != cur.seq (L260)
-        return (w & ~(3u << sh)) | ((uint32_t)j << sh);
-    }
-    valid = p < 15;                                            // indels only for posCur < L-1 (L234)
-    if (!valid) return 0;
-    if (j < 8) {
-        const uint32_t below = slr_lowmask(sh);                // digits p+1..15
-        dead = (p == 14) && ((w & 3u) != 0u);
-        return (w & ~below) | ((w & below) >> 2) | ((uint32_t)(j - 4) << (sh - 2));
-    }
-    const uint32_t below = slr_lowmask(sh + 2);                // digits p..15
-    return (w & ~below) | ((w << 2) & below) | cbase;
-}
-
-// remove digit i (0 = most significant) of a 4-digit (8-bit) pattern -> 6 bits
-SLR_HD uint32_t slr_rm_digit(uint32_t P, int i)
-{
-    switch (i) {
-    case 0: return P & 0x3Fu;
-    case 1: return ((P >> 2) & 0x30u) | (P & 0x0Fu);
-    case 2: return ((P >> 2) & 0x3Cu) | (P & 0x03u);
-    default: return P >> 2;
-    }
+    const uint32_t below = slr_lowmask(sh);                    // digits p+1..15
+    const uint32_t below2 = (below << 2) | 3u;                 // digits p..15
+    const uint32_t sub = (w & ~(3u << sh)) | ((uint32_t)(j & 3) << sh);
+    const uint32_t ins = (w & ~below) | ((w & below) >> 2) | (((uint32_t)(j & 3) << sh) >> 2);
+    const uint32_t del = (w & ~below2) | ((w << 2) & below2) | cbase;
+    const bool is_sub = j < 4;
+    valid = is_sub ? (((w >> sh) & 3u) != (uint32_t)j)          // s != cur.seq (L260)
+                   : (p < 15);                                  // indels only for posCur < L-1 (L234)
+    dead = (!is_sub) && (j < 8) && (p == 14) && ((w & 3u) != 0u);
+    return is_sub ? sub : (j < 8 ? ins : del);
 }
 
 // Context of one node expansion (= all positions of one LongSeqMutated popped from the deque)
@@ -80,7 +65,6 @@ struct SlrExpand {
     int pskip;          // posTreatedInPreviousLevel (must not be mutated again, L227), -1 for the root
     uint32_t cbase;     // base appended by a deletion: post[nDel+1] (L329)
     uint32_t tproc;     // processing time of this node (level 2 only)
-    int level;          // 1 = root expansion (hits are ED 1), 2 = level-1 node expansion (hits are ED 2)
     bool use_visited;   // ed >= 2 (NucTwoBitPerBaseEDtesterBase.java:L82-L95)
 };
 
@@ -88,10 +72,11 @@ struct SlrExpand {
 // visited (java:L105-L120) holds the (int) seq of every node that finished at least one position:
 //   level 1: {w, once the root did position 0} U {level-1 mutants of earlier root positions}
 //   level 2: {w} U {level-1 nodes processed before this node} U {this node, after its first position}
-SLR_HD bool slr_is_visited(const SlrExpand &e, const unsigned long long *vh, uint32_t s, int q)
+// Monotone in q: visited at q implies visited at every later position of the same node.
+template <int LEVEL> SLR_HD bool slr_is_visited(const SlrExpand &e, const unsigned long long *vh, uint32_t s, int q)
 {
-    if (!e.use_visited) return false;
-    if (e.level == 1) {
+    if (LEVEL == 1) {
+        if (!e.use_visited) return false;
         if (q >= 1 && s == e.w) return true;
         const uint32_t t = slr_vh_tmin(vh, s);
         return t != SLR_NONE32 && (int)(t >> 4) < q;
@@ -105,91 +90,123 @@ SLR_HD bool slr_is_visited(const SlrExpand &e, const unsigned long long *vh, uin
 }
 
 // Test slot pattern P of table g against the op-mutants (0 SUB, 1 INS, 2 DEL) of node e that fall into digit
-// group g.  Returns the smallest traversal rank q*9 + idx (idx: 0-3 SUB base, 4-7 INS base, 8 DEL) of a
+// group g.  Returns the smallest traversal rank q*16 + idx (idx: 0-3 SUB base, 4-7 INS base, 8 DEL) of a
 // generating, non-visited mutant, or SLR_NONE32.  s = the full candidate barcode.
-SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *vh, int g, int op, uint32_t P, uint32_t s)
+// INS / DEL: "a 4-digit string is a 3-digit string plus one digit": with lpre = common leading digits and
+// lsuf = common trailing digits the generating positions are exactly the interval [3 - lsuf, lpre].
+template <int LEVEL> SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *vh, int g, int op, uint32_t P, uint32_t s)
 {
     const uint32_t csg = (e.cs >> (24 - 8 * g)) & 0xFFu;
+    int q;
+    uint32_t idx;
     if (op == 0) {                                             // substitutions (L257-L273)
         const uint32_t x = P ^ csg;
         const uint32_t d = (x | (x >> 1)) & 0x55u;
         if (d == 0u || (d & (d - 1u)) != 0u) return SLR_NONE32;   // exactly one digit differs
         const int il = 3 - ((slr_ffs(d) - 1) >> 1);
-        const int q = 4 * g + il;
+        q = 4 * g + il;
         if (q == e.pskip) return SLR_NONE32;
-        if (slr_is_visited(e, vh, s, q)) return SLR_NONE32;
-        return (uint32_t)(q * 9) + ((P >> (2 * (3 - il))) & 3u);
-    }
-    if (op == 1) {                                             // insertions (L284-L300): new digit at j = q+1
-        const uint32_t c012 = csg >> 2;
-        for (int jl = 0; jl < 4; jl++) {
-            const int j = 4 * g + jl, q = j - 1;
-            if (j < 1 || q == e.pskip) continue;
-            if (j == 15 && (e.cs & 3u) != 0u) continue;        // the `>>> 64` value: garbage in bits 62-63
-            if (slr_rm_digit(P, jl) != c012) continue;
-            if (slr_is_visited(e, vh, s, q)) continue;
-            return (uint32_t)(q * 9) + 4u + ((P >> (2 * (3 - jl))) & 3u);
+        idx = (P >> (2 * (3 - il))) & 3u;
+    } else {
+        uint32_t long4, short3;
+        if (op == 1) {                                         // insertions (L284-L300): new digit at j = q+1
+            long4 = P; short3 = csg >> 2;
+        } else {                                               // deletions (L313-L357): digit q removed, cbase appended
+            const uint32_t n0 = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;
+            if ((P & 3u) != n0) return SLR_NONE32;
+            long4 = csg; short3 = P >> 2;
         }
-        return SLR_NONE32;
+        const uint32_t xh = (long4 >> 2) ^ short3, xl = (long4 & 0x3Fu) ^ short3;
+        const int hi = (slr_clz(xh) - 26) >> 1;                // common leading digits, 0..3
+        int x = 3 - ((slr_ffs(xl | 0x40u) - 1) >> 1);          // 3 - common trailing digits
+        q = -2;
+        for (; x <= hi; x++) {                                 // almost always a single candidate
+            const int qq = (op == 1) ? 4 * g + x - 1 : 4 * g + x;
+            if (qq < 0 || qq > 14 || qq == e.pskip) continue;
+            if (op == 1 && qq == 14 && (e.cs & 3u) != 0u) continue;   // the `>>> 64` value: garbage in bits 62-63
+            q = qq;
+            break;
+        }
+        if (q < 0) return SLR_NONE32;
+        idx = (op == 1) ? 4u + ((P >> (2 * (3 - x))) & 3u) : 8u;
     }
-    // deletions (L313-L357): digit q removed, tail shifted left, cbase appended
-    const uint32_t n0 = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;
-    if ((P & 3u) != n0) return SLR_NONE32;
-    const uint32_t P012 = P >> 2;
-    for (int ql = 0; ql < 4; ql++) {
-        const int q = 4 * g + ql;
-        if (q > 14 || q == e.pskip) continue;
-        if (slr_rm_digit(csg, ql) != P012) continue;
-        if (slr_is_visited(e, vh, s, q)) continue;
-        return (uint32_t)(q * 9) + 8u;
-    }
-    return SLR_NONE32;
+    if (slr_is_visited<LEVEL>(e, vh, s, q)) return SLR_NONE32;
+    return (uint32_t)(q * 16) + idx;
 }
 
-// All op-mutants of node e whose edit falls into digit group g: ONE bucket load.
-// Returns the best (smallest) traversal rank and the matching barcode.
-SLR_HD uint32_t slr_expand_group(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
-                                 uint32_t &bc_out)
+// Address part of one probe = all op-mutants of node e whose edit falls into digit group g: ONE bucket.
+struct SlrProbe {
+    uint32_t rest, bucket, tag;
+};
+SLR_HD SlrProbe slr_probe_addr(const SlrTableDev &t, uint32_t cs, uint32_t cbase, int g, int op)
 {
     const int lo_bits = 24 - 8 * g;
-    const uint32_t hi = g == 0 ? 0u : (e.cs >> (32 - 8 * g));
-    uint32_t lo;
-    if (op == 0) lo = e.cs;
-    else if (op == 1) lo = e.cs >> 2;
-    else lo = (e.cs << 2) | e.cbase;
-    lo &= slr_lowmask(lo_bits);
-    const uint32_t rest = (hi << lo_bits) | lo;
-    const uint32_t m = slr_mix24(rest);
+    const uint32_t himask = ~slr_lowmask(lo_bits + 8);         // digit groups above g (g = 0: none)
+    const uint32_t lo = (op == 0) ? cs : ((op == 1) ? (cs >> 2) : ((cs << 2) | cbase));
+    SlrProbe pr;
+    pr.rest = ((cs & himask) >> 8) | (lo & slr_lowmask(lo_bits));
+    const uint32_t m = slr_mix24(pr.rest);
     const int tb = 24 - t.bbits;
-    const uint32_t bucket = m >> tb, tag = m & ((1u << tb) - 1u);
-    const SlrBucket k = slr_load_bucket(t, g, bucket);
-    uint32_t match = slr_tag_match(k, tag);
+    pr.bucket = m >> tb;
+    pr.tag = m & ((1u << tb) - 1u);
+    return pr;
+}
+
+// Evaluate a loaded bucket: best (smallest) traversal rank and the matching barcode.
+template <int LEVEL> SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
+                                                   const SlrProbe &pr, const SlrBucket &k, uint32_t &bc_out)
+{
+    uint32_t match = slr_tag_match(k, pr.tag);
     uint32_t best = SLR_NONE32;
     while (match) {
         const int i = slr_ffs(match) - 1;
         match &= match - 1u;
-        const uint32_t P = k.slot(i) & 0xFFu;
-        const uint32_t s = slr_key_join(rest, P, g);
-        const uint32_t r = slr_check_pattern(e, vh, g, op, P, s);
+        const uint32_t P = slr_bucket_pat(k, i);
+        const uint32_t s = slr_key_join(pr.rest, P, g);
+        const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, P, s);
         if (r < best) { best = r; bc_out = s; }
     }
-    if (t.st_n[g] > 0 && slr_bucket_full(k)) {                 // overflowed bucket: rare
-        const uint32_t want_hi = 0x80u | tag;
-        for (int i = slr_stash_lower(t, g, bucket); i < t.st_n[g] && slr_ldg(t.st_bucket[g] + i) == bucket; i++) {
+    if (t.st_total > 0 && slr_bucket_full(k)) {                // overflowed bucket: rare
+        const uint32_t want_hi = 0x80u | pr.tag;
+        for (int i = slr_stash_lower(t, g, pr.bucket); i < t.st_n[g] && slr_ldg(t.st_bucket[g] + i) == pr.bucket; i++) {
             const uint32_t sl = slr_ldg(t.st_slot[g] + i);
             if ((sl >> 8) != want_hi) continue;
             const uint32_t P = sl & 0xFFu;
-            const uint32_t s = slr_key_join(rest, P, g);
-            const uint32_t r = slr_check_pattern(e, vh, g, op, P, s);
+            const uint32_t s = slr_key_join(pr.rest, P, g);
+            const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, P, s);
             if (r < best) { best = r; bc_out = s; }
         }
     }
     return best;
 }
 
+template <int LEVEL> SLR_HD uint32_t slr_expand_group(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
+                                                     uint32_t &bc_out)
+{
+    const SlrProbe pr = slr_probe_addr(t, e.cs, e.cbase, g, op);
+    const SlrBucket k = slr_load_bucket(t, g, pr.bucket);
+    return slr_probe_eval<LEVEL>(t, e, vh, g, op, pr, k, bc_out);
+}
+
 // counters the Java attaches to a mutant created by idx (0-3 SUB -> nSubstitutions, 4-7 INS -> nDeletions (L290),
 // 8 DEL -> nInsertions (L346)); packed nSub | nIns << 2 | nDel << 4
 SLR_HD uint32_t slr_cnt_of(uint32_t idx) { return idx < 4 ? 1u : (idx < 8 ? (1u << 4) : (1u << 2)); }
+
+// A level-1 node the reference expands: packed for the level-2 loop.
+//   meta bits 0-7 = processing time p*16 + jj (jj = 8 - j: nodes of one root position are popped in reverse
+//   creation order, ArrayDeque add / pollLast, L212-L218), bits 8-9 = cbase of the node's deletions
+//   (post[nDel+1]; nDel = 1 below an INS node), bits 10-15 = counters of the level-1 edit (slr_cnt_of).
+SLR_HD uint32_t slr_node_meta(int p, int j, uint32_t p1, uint32_t p2)
+{
+    const uint32_t cb = (j >= 4 && j < 8) ? p2 : p1;
+    return (uint32_t)(p * 16 + (8 - j)) | (cb << 8) | (slr_cnt_of((uint32_t)j) << 10);
+}
+SLR_HD SlrExpand slr_node_expand(uint32_t cs, uint32_t meta, uint32_t w)
+{
+    SlrExpand e;
+    e.cs = cs; e.w = w; e.pskip = (int)((meta >> 4) & 15u); e.cbase = (meta >> 8) & 3u; e.tproc = meta & 0xFFu; e.use_visited = true;
+    return e;
+}
 
 // ---- character classes -----------------------------------------------------------------------------------
 // BASE_TO_TWOBIT_ARRAY (T!…NucleicAcidTwoBitPerBase.java:L78-L87): returns 0..3 or 4 for "not ACGT"

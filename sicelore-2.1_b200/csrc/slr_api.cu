@@ -147,7 +147,7 @@ int slr_bc_table_create(slr_ctx *ctx, const uint64_t *barcodes2bit, const int32_
     slr_bc_table *t = new slr_bc_table();
     t->ctx = ctx; t->n = n; t->n_distinct = H.n_distinct;
     memset(&t->dev, 0, sizeof(t->dev));
-    const size_t tbytes = ((size_t)16 << H.bbits) * sizeof(uint16_t);
+    const size_t tbytes = (size_t)32 << H.bbits;        // 32-byte buckets
 #define TRY_OR_FREE(expr)                                                                                       \
     do {                                                                                                        \
         cudaError_t e_ = (expr);                                                                                \
@@ -160,6 +160,7 @@ int slr_bc_table_create(slr_ctx *ctx, const uint64_t *barcodes2bit, const int32_
         t->dev.bk[g] = reinterpret_cast<const uint4 *>(base);
         const size_t sn = H.st_bucket[g].size();
         t->dev.st_n[g] = (int)sn;
+        t->dev.st_total += (int)sn;
         if (sn) {
             TRY_OR_FREE(cudaMalloc(&t->d_stash_b[g], sn * 4));
             TRY_OR_FREE(cudaMalloc(&t->d_stash_s[g], sn * 2));

@@ -8,8 +8,8 @@
 //   a 16-nt barcode is 16 base-4 digits d0..d15 (d0 most significant, A=0 G=1 C=2 T=3).  Table g (g=0..3)
 //   "ignores" digit group g = digits 4g..4g+3: a key is split into  pat = those 8 bits  and  rest = the other
 //   24 bits.  rest goes through a 24-bit bijection; its top `bbits` bits select a 32-byte bucket (one L2
-//   sector), the remaining 24-bbits bits are a tag.  A bucket holds 16 uint16 slots
-//   slot = 0x8000 | tag << 8 | pat   (exact: (bucket, tag, pat) <-> key is a bijection), 0 = empty.
+//   sector), the remaining 24-bbits bits are a tag.  A bucket holds 16 slots: bytes 0..15 = 0x80 | tag of
+//   slot i (0 = empty), bytes 16..31 = pat of slot i   (exact: (bucket, tag, pat) <-> key is a bijection).
 //   => all single-edit neighbours of a node whose edit falls into digit group g share ONE bucket of table g,
 //   so one 32-byte load tests up to 16 mutants of the reference's enumeration at once.
 //   Buckets that overflow spill into a small sorted stash (checked only when a bucket is completely full).
@@ -24,6 +24,7 @@ struct SlrTableDev {
     const uint32_t *st_bucket[4];  // stash: sorted bucket ids
     const uint16_t *st_slot[4];    //        and their slots
     int st_n[4];
+    int st_total;                  // sum of st_n (0 for almost every list: the stash code is then skipped)
     int bbits;                     // log2(#buckets), 17..22  (tag bits = 24 - bbits <= 7)
     const uint32_t *ix_keys;       // key -> index map (open addressing, linear probing)
     const int32_t *ix_vals;        //   -1 = empty
@@ -120,17 +121,10 @@ SLR_HD uint32_t slr_key_join(uint32_t rest, uint32_t pat, int g)
 }
 SLR_HD uint32_t slr_ix_hash(uint32_t key) { return (key * 0x9E3779B1u) ^ (key >> 15); }
 
-// One bucket = 16 slots in two uint4.
+// One bucket = 16 slots in two uint4: a = the 16 tag bytes (0x80 | tag, 0 = empty slot), b = the 16 pattern bytes.
+// (Tags and patterns sit in separate halves so that the tag filter is four word-wide byte compares.)
 struct SlrBucket {
     uint4 a, b;
-    SLR_HD uint32_t word(int i) const
-    {
-        switch (i) {
-        case 0: return a.x; case 1: return a.y; case 2: return a.z; case 3: return a.w;
-        case 4: return b.x; case 5: return b.y; case 6: return b.z; default: return b.w;
-        }
-    }
-    SLR_HD uint32_t slot(int i) const { const uint32_t w = word(i >> 1); return (i & 1) ? (w >> 16) : (w & 0xFFFFu); }
 };
 
 SLR_HD SlrBucket slr_load_bucket(const SlrTableDev &t, int g, uint32_t bucket)
@@ -142,36 +136,33 @@ SLR_HD SlrBucket slr_load_bucket(const SlrTableDev &t, int g, uint32_t bucket)
     return r;
 }
 
+// bit 7 of every byte of the result set <=> that byte of x equals the byte replicated in `want` (exact, carry-free)
+SLR_HD uint32_t slr_eq_bytes(uint32_t x, uint32_t want)
+{
+    const uint32_t h = x ^ want;
+    return ~(((h & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h) & 0x80808080u;
+}
+// gather bit 7 of the four bytes into a nibble (bits 31..28 of the product are 0, no carries: see DESIGN.md §3)
+SLR_HD uint32_t slr_nibble_of(uint32_t eq) { return ((eq >> 7) * 0x01020408u) >> 24; }
+
 // Bit i of the result (i = 0..15) set  <=>  slot i is valid and carries `tag`.
-// The high bytes of the 16 slots are gathered with PRMT (selector 0x7531: byte1/byte3 of each word) and
-// compared bytewise with an exact zero-byte test.
 SLR_HD uint32_t slr_tag_match(const SlrBucket &k, uint32_t tag)
 {
     const uint32_t want = (0x80u | tag) * 0x01010101u;
-    uint32_t h0 = slr_byte_perm(k.a.x, k.a.y, 0x7531) ^ want;   // slots 0..3
-    uint32_t h1 = slr_byte_perm(k.a.z, k.a.w, 0x7531) ^ want;   // slots 4..7
-    uint32_t h2 = slr_byte_perm(k.b.x, k.b.y, 0x7531) ^ want;   // slots 8..11
-    uint32_t h3 = slr_byte_perm(k.b.z, k.b.w, 0x7531) ^ want;   // slots 12..15
-    h0 = (((h0 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h0);              // bit 7 of each byte = byte != 0
-    h1 = (((h1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h1);
-    h2 = (((h2 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h2);
-    h3 = (((h3 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h3);
-    if (((h0 & h1 & h2 & h3) & 0x80808080u) == 0x80808080u) return 0u;     // fast path: nothing matches
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        m |= ((~h0 >> (7 + 8 * i)) & 1u) << i;
-        m |= ((~h1 >> (7 + 8 * i)) & 1u) << (4 + i);
-        m |= ((~h2 >> (7 + 8 * i)) & 1u) << (8 + i);
-        m |= ((~h3 >> (7 + 8 * i)) & 1u) << (12 + i);
-    }
-    return m;
+    const uint32_t e0 = slr_eq_bytes(k.a.x, want), e1 = slr_eq_bytes(k.a.y, want);
+    const uint32_t e2 = slr_eq_bytes(k.a.z, want), e3 = slr_eq_bytes(k.a.w, want);
+    if ((e0 | e1 | e2 | e3) == 0u) return 0u;                              // fast path: nothing matches
+    return slr_nibble_of(e0) | (slr_nibble_of(e1) << 4) | (slr_nibble_of(e2) << 8) | (slr_nibble_of(e3) << 12);
 }
 
-SLR_HD bool slr_bucket_full(const SlrBucket &k)
+// pattern byte of slot i
+SLR_HD uint32_t slr_bucket_pat(const SlrBucket &k, int i)
 {
-    return ((k.a.x & k.a.y & k.a.z & k.a.w & k.b.x & k.b.y & k.b.z & k.b.w) & 0x80008000u) == 0x80008000u;
+    const bool lo = i < 8;
+    return slr_byte_perm(lo ? k.b.x : k.b.z, lo ? k.b.y : k.b.w, (uint32_t)(i & 7)) & 0xFFu;
 }
+
+SLR_HD bool slr_bucket_full(const SlrBucket &k) { return ((k.a.x & k.a.y & k.a.z & k.a.w) & 0x80808080u) == 0x80808080u; }
 
 // first stash entry of `bucket` (lower bound); its entries end where st_bucket != bucket
 SLR_HD int slr_stash_lower(const SlrTableDev &t, int g, uint32_t bucket)
@@ -186,24 +177,28 @@ SLR_HD int slr_stash_lower(const SlrTableDev &t, int g, uint32_t bucket)
 }
 
 // exact membership of one key (the ED-0 probe, BarcodeMatchTester.java:L204)
+SLR_HD bool slr_contains_in(const SlrTableDev &t, const SlrBucket &k, uint32_t bucket, uint32_t tag, uint32_t pat)
+{
+    const uint32_t pw = pat * 0x01010101u;
+    const uint32_t want = (0x80u | tag) * 0x01010101u;
+    uint32_t hit = slr_eq_bytes(k.a.x, want) & slr_eq_bytes(k.b.x, pw);
+    hit |= slr_eq_bytes(k.a.y, want) & slr_eq_bytes(k.b.y, pw);
+    hit |= slr_eq_bytes(k.a.z, want) & slr_eq_bytes(k.b.z, pw);
+    hit |= slr_eq_bytes(k.a.w, want) & slr_eq_bytes(k.b.w, pw);
+    if (hit) return true;
+    if (t.st_total > 0 && slr_bucket_full(k)) {
+        const uint32_t sw = 0x8000u | (tag << 8) | pat;
+        for (int i = slr_stash_lower(t, 0, bucket); i < t.st_n[0] && slr_ldg(t.st_bucket[0] + i) == bucket; i++)
+            if ((uint32_t)slr_ldg(t.st_slot[0] + i) == sw) return true;
+    }
+    return false;
+}
 SLR_HD bool slr_contains(const SlrTableDev &t, uint32_t key)
 {
     const uint32_t m = slr_mix24(slr_key_rest(key, 0));
     const int tb = 24 - t.bbits;
     const uint32_t bucket = m >> tb, tag = m & ((1u << tb) - 1u);
-    const uint32_t want = 0x8000u | (tag << 8) | slr_key_pat(key, 0);
-    const SlrBucket k = slr_load_bucket(t, 0, bucket);
-    bool hit = false;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint32_t w = k.word(i);
-        hit |= ((w & 0xFFFFu) == want) | ((w >> 16) == want);
-    }
-    if (!hit && t.st_n[0] > 0 && slr_bucket_full(k)) {
-        for (int i = slr_stash_lower(t, 0, bucket); i < t.st_n[0] && slr_ldg(t.st_bucket[0] + i) == bucket; i++)
-            hit |= (uint32_t)slr_ldg(t.st_slot[0] + i) == want;
-    }
-    return hit;
+    return slr_contains_in(t, slr_load_bucket(t, 0, bucket), bucket, tag, slr_key_pat(key, 0));
 }
 
 // key -> index in the caller's barcode array (for rank / counters); -1 if absent

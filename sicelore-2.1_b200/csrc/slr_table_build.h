@@ -9,7 +9,7 @@
 
 struct SlrTableHost {
     int bbits = 17;
-    std::vector<uint16_t> slots[4];            // (1 << bbits) * 16 per table
+    std::vector<uint8_t> slots[4];             // (1 << bbits) buckets of 32 bytes per table: 16 tag bytes, 16 pattern bytes
     std::vector<uint32_t> st_bucket[4];        // sorted stash
     std::vector<uint16_t> st_slot[4];
     std::vector<uint32_t> ix_keys;
@@ -62,15 +62,19 @@ inline void slr_build_table(const uint64_t *keys, const int32_t *rank, long long
     const int tb = 24 - T.bbits;
     const size_t nb = (size_t)1 << T.bbits;
     for (int g = 0; g < 4; g++) {
-        T.slots[g].assign(nb * 16, 0);
+        T.slots[g].assign(nb * 32, 0);
         std::vector<uint8_t> fill(nb, 0);
         std::vector<std::pair<uint32_t, uint16_t>> stash;
         for (uint32_t k : distinct) {
             const uint32_t m = slr_mix24(slr_key_rest(k, g));
             const uint32_t bucket = m >> tb, tag = m & ((1u << tb) - 1u);
             const uint16_t slot = (uint16_t)(0x8000u | (tag << 8) | slr_key_pat(k, g));
-            if (fill[bucket] < 16) T.slots[g][(size_t)bucket * 16 + fill[bucket]++] = slot;
-            else stash.emplace_back(bucket, slot);
+            if (fill[bucket] < 16) {
+                uint8_t *b = &T.slots[g][(size_t)bucket * 32];
+                b[fill[bucket]] = (uint8_t)(slot >> 8);
+                b[16 + fill[bucket]] = (uint8_t)(slot & 0xFFu);
+                fill[bucket]++;
+            } else stash.emplace_back(bucket, slot);
         }
         std::sort(stash.begin(), stash.end());
         T.st_bucket[g].clear();
@@ -89,6 +93,7 @@ inline SlrTableDev slr_table_host_view(const SlrTableHost &T, unsigned long long
         d.st_bucket[g] = T.st_bucket[g].data();
         d.st_slot[g] = T.st_slot[g].data();
         d.st_n[g] = (int)T.st_bucket[g].size();
+        d.st_total += d.st_n[g];
     }
     d.bbits = T.bbits;
     d.ix_keys = T.ix_keys.data();

@@ -7,6 +7,7 @@
 #include "../../sicelore-2.1_b200/csrc/bc_core.cuh"
 #include "../../sicelore-2.1_b200/csrc/slr_table_build.h"
 
+// first insertion wins; the caller inserts in increasing processing time (like the kernel's rounds)
 static void vh_insert_host(unsigned long long *tab, uint32_t v, uint32_t t)
 {
     uint32_t slot = slr_vh_slot(v);
@@ -14,7 +15,7 @@ static void vh_insert_host(unsigned long long *tab, uint32_t v, uint32_t t)
     while (true) {
         unsigned long long cur = tab[slot];
         if (cur == SLR_VH_EMPTY) { tab[slot] = val; return; }
-        if ((uint32_t)(cur >> 32) == v) { if (val < cur) tab[slot] = val; return; }
+        if ((uint32_t)(cur >> 32) == v) return;
         slot = (slot + 1) & (SLR_VH_SIZE - 1);
     }
 }
@@ -33,7 +34,7 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
         sb.over253 |= (uint32_t)(ch >= 254u) << lane;
     }
     static thread_local unsigned long long vh[SLR_VH_SIZE];
-    uint8_t live[160];
+    uint32_t node_cs[144], node_meta[144];
     SlrMatchStore ms;
     memset(&ms, 0, sizeof(ms));
     uint32_t flags = 0;
@@ -44,67 +45,66 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
         if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window)) { flags |= SLR_F_EXCEPTION; break; }
         ms.m_w[k] = w;
         if (dead_window) continue;
-        uint32_t valid_levels = slr_contains(tab, w) ? 1u : 0u;
-        (*n_loads)++;
-        if (valid_levels) { ms.m_bc[k][0] = w; ms.m_cnt[k][0] = 0; }
-        if (ed_max >= 1) {
-            const bool use_vis = ed_max >= 2;
-            if (use_vis) {
-                for (int i = 0; i < SLR_VH_SIZE; i++) vh[i] = SLR_VH_EMPTY;
-                for (int sl = 0; sl < 144; sl++) {
-                    const int p = sl / 9, j = 8 - (sl - p * 9);
-                    bool v, d;
-                    const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
-                    if (v) vh_insert_host(vh, mval, (uint32_t)(p * 16 + (8 - j)));
-                }
+        SlrExpand e;
+        e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.use_visited = ed_max >= 2;
+        if (ed_max >= 2) {
+            for (int i = 0; i < SLR_VH_SIZE; i++) vh[i] = SLR_VH_EMPTY;
+            for (int sl = 0; sl < 144; sl++) {
+                const int p = sl / 9, j = 8 - (sl - p * 9);
+                bool v, d;
+                const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
+                if (v) vh_insert_host(vh, mval, (uint32_t)(p * 16 + (8 - j)));
             }
-            SlrExpand e;
-            e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.level = 1; e.use_visited = use_vis;
-            uint32_t rmin = SLR_NONE32, bc1 = 0;
-            for (int lane = 0; lane < 16; lane++) {
-                const int g = (lane >> 2) & 3, op = lane & 3;
-                if (op == 3) continue;
+        }
+        // lane 0's bucket (table 0, rest of w) answers the ED-0 probe
+        uint32_t valid_levels = 0;
+        uint32_t rmin = SLR_NONE32, bc1 = 0;
+        for (int lane = 0; lane < (ed_max >= 1 ? 12 : 1); lane++) {
+            const int g = (lane * 11) >> 5, op = lane - 3 * g;
+            const SlrProbe pr = slr_probe_addr(tab, w, p1, g, op);
+            const SlrBucket bk = slr_load_bucket(tab, g, pr.bucket);
+            (*n_loads)++;
+            if (lane == 0 && slr_contains_in(tab, bk, pr.bucket, pr.tag, w >> 24)) valid_levels = 1u;
+            if (ed_max >= 1) {
                 uint32_t b = 0;
-                const uint32_t r = slr_expand_group(tab, e, vh, g, op, b);
-                (*n_loads)++;
+                const uint32_t r = slr_probe_eval<1>(tab, e, vh, g, op, pr, bk, b);
                 if (r < rmin) { rmin = r; bc1 = b; }
             }
-            if (rmin != SLR_NONE32) { valid_levels |= 2u; ms.m_bc[k][1] = bc1; ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin % 9u); }
-            if (use_vis) {
-                int nlive = 0;
-                for (int sl = 0; sl < 144; sl++) {
-                    const int p = sl / 9, j = 8 - (sl - p * 9);
-                    bool v, d;
-                    const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
-                    if (v && !d && !slr_is_visited(e, vh, mval, p)) live[nlive++] = (uint8_t)sl;
+        }
+        if (valid_levels) { ms.m_bc[k][0] = w; ms.m_cnt[k][0] = 0; }
+        if (rmin != SLR_NONE32) { valid_levels |= 2u; ms.m_bc[k][1] = bc1; ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
+        if (ed_max >= 2) {
+            int nlive = 0;
+            for (int sl = 0; sl < 144; sl++) {
+                const int p = sl / 9, j = 8 - (sl - p * 9);
+                bool v, d;
+                const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
+                if (v && !d && !slr_is_visited<1>(e, vh, mval, p)) {
+                    node_cs[nlive] = mval;
+                    node_meta[nlive++] = slr_node_meta(p, j, p1, p2);
                 }
-                for (int it = 0; it * 2 < nlive; it++) {
-                    uint32_t m2 = SLR_NONE32, bc2 = 0, c1w = 0;
-                    for (int lane = 0; lane < 32; lane++) {
-                        const int g = (lane >> 2) & 3, op = lane & 3, h = lane >> 4;
-                        const int idx = it * 2 + h;
-                        if (!(idx < nlive && op < 3)) continue;
-                        const int sl = live[idx];
-                        const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
-                        bool v, d;
-                        SlrExpand e2;
-                        e2.cs = slr_gen_mutant(w, p, j, p1, v, d);
-                        e2.w = w; e2.pskip = p; e2.level = 2; e2.use_visited = true;
-                        e2.cbase = (j >= 4 && j < 8) ? p2 : p1;
-                        e2.tproc = (uint32_t)(p * 16 + jj);
-                        uint32_t b = 0;
-                        uint32_t r2 = slr_expand_group(tab, e2, vh, g, op, b);
-                        (*n_loads)++;
-                        if (r2 != SLR_NONE32) r2 |= (uint32_t)h << 16;
-                        if (r2 < m2) { m2 = r2; bc2 = b; c1w = slr_cnt_of((uint32_t)j); }
-                    }
-                    if (m2 != SLR_NONE32) {
-                        valid_levels |= 4u;
-                        ms.m_bc[k][2] = bc2;
-                        ms.m_cnt[k][2] = (uint8_t)(c1w + slr_cnt_of((m2 & 0xFFFFu) % 9u));
-                        break;
-                    }
+            }
+            const int nprobe = nlive * 12;
+            uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
+            for (int base = 0; base < nprobe; base += 32) {
+                for (int lane = 0; lane < 32; lane++) {
+                    const int pi = base + lane;
+                    if (pi >= nprobe) break;
+                    const int nd = pi / 12, rem = pi - nd * 12;
+                    const int g = (rem * 11) >> 5, op = rem - 3 * g;
+                    const SlrExpand e2 = slr_node_expand(node_cs[nd], node_meta[nd], w);
+                    uint32_t b = 0;
+                    uint32_t r2 = slr_expand_group<2>(tab, e2, vh, g, op, b);
+                    (*n_loads)++;
+                    if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
+                    if (r2 < best) { best = r2; bcb = b; cntb = node_meta[nd] >> 10; }
                 }
+                if (best != SLR_NONE32 && (int)(best >> 8) * 12 + 12 <= base + 32) break;
+            }
+            if (best != SLR_NONE32) {
+                valid_levels |= 4u;
+                ms.m_bc[k][2] = bcb;
+                ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u));
             }
         }
         ms.m_valid[k] = (uint8_t)valid_levels;
