@@ -36,9 +36,10 @@ struct alignas(16) WarpShared {
     SlrMatchStore ms;
 };
 
-// first insertion wins: the caller inserts in increasing processing time (rounds in order, duplicates inside a
-// round removed with __match_any_sync), so an existing key always carries the smaller time.
-__device__ __forceinline__ void vh_insert_first(unsigned long long *tab, uint32_t v, uint32_t t)
+// First insertion wins: the caller inserts in increasing processing time (rounds in order, duplicates inside a
+// round removed with __match_any_sync), so an existing key always carries the smaller time.  Returns the time
+// stored for v.
+__device__ __forceinline__ uint32_t vh_insert_first(unsigned long long *tab, uint32_t v, uint32_t t)
 {
     uint32_t slot = slr_vh_slot(v);
     const unsigned long long val = ((unsigned long long)v << 32) | t;
@@ -46,9 +47,9 @@ __device__ __forceinline__ void vh_insert_first(unsigned long long *tab, uint32_
         unsigned long long cur = *((volatile unsigned long long *)&tab[slot]);
         if (cur == SLR_VH_EMPTY) {
             cur = atomicCAS(&tab[slot], SLR_VH_EMPTY, val);
-            if (cur == SLR_VH_EMPTY) return;
+            if (cur == SLR_VH_EMPTY) return t;
         }
-        if ((uint32_t)(cur >> 32) == v) return;
+        if ((uint32_t)(cur >> 32) == v) return (uint32_t)cur;
         slot = (slot + 1) & (SLR_VH_SIZE - 1);
     }
 }
@@ -107,10 +108,12 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
                 bk1 = slr_load_bucket(tab, g1, pr1.bucket);
             }
 
-            uint32_t mv[5];
-            uint32_t mflags = 0;                                    // bit r: valid, bit 8 + r: expandable (valid, not dead)
+            int nlive = 0;
             if (EDMAX >= 2) {
-                // visited hash over the 139 level-1 mutants; processing time t = p*16 + (8-j)
+                // One pass over the 144 level-1 slots in processing order (5 rounds of 32): build the visited hash
+                // value -> earliest processing time t = p*16 + (8-j), and keep the nodes the reference expands
+                // (valid, no 62-63 garbage, not "already tested" when created: slr_is_visited<1> with the time just
+                // found) as compact (sequence, meta) records.
                 ulonglong2 *vh2 = reinterpret_cast<ulonglong2 *>(S.vh);
 #pragma unroll
                 for (int i = 0; i < SLR_VH_SIZE / 64; i++) vh2[i * 32 + lane] = make_ulonglong2(SLR_VH_EMPTY, SLR_VH_EMPTY);
@@ -120,17 +123,20 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
                     const int sl = r * 32 + lane;
                     const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
                     bool v, d;
-                    mv[r] = slr_gen_mutant(w, p & 15, j, p1, v, d);
+                    const uint32_t mv = slr_gen_mutant(w, p & 15, j, p1, v, d);
                     v = v && sl < 144;
                     const uint32_t vmask = __ballot_sync(FULL, v);
-                    const uint32_t peers = __match_any_sync(FULL, mv[r]);
-                    if (v) {
-                        mflags |= 1u << r;
-                        if (!d) mflags |= 0x100u << r;
-                        if ((peers & vmask & ((1u << lane) - 1u)) == 0u) vh_insert_first(S.vh, mv[r], (uint32_t)(p * 16 + jj));
-                    }
+                    const uint32_t lowpeers = __match_any_sync(FULL, mv) & vmask & ((1u << lane) - 1u);
+                    uint32_t tfirst = (uint32_t)(p * 16 + jj);
+                    if (v && lowpeers == 0u) tfirst = vh_insert_first(S.vh, mv, tfirst);
                     __syncwarp();
+                    tfirst = __shfl_sync(FULL, tfirst, (v && lowpeers != 0u) ? __ffs((int)lowpeers) - 1 : lane);
+                    const bool livenode = v && !d && !((p >= 1 && mv == w) || (int)(tfirst >> 4) < p);
+                    const uint32_t bal = __ballot_sync(FULL, livenode);
+                    if (livenode) S.node[nlive + __popc(bal & ((1u << lane) - 1u))] = make_uint2(mv, slr_node_meta(p, j, p1, p2));
+                    nlive += __popc(bal);
                 }
+                __syncwarp();
             }
 
             // ---- ED 0 (L204-L206) and ED 1: first hit in creation order = warp minimum of the traversal ranks --
@@ -152,18 +158,6 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
                 }
             }
             if (EDMAX >= 2) {
-                // ---- level-1 nodes the reference expands, in processing order ----------------------------------
-                int nlive = 0;
-#pragma unroll
-                for (int r = 0; r < 5; r++) {
-                    const int sl = r * 32 + lane;
-                    const int p = sl / 9, j = 8 - (sl - p * 9);
-                    const bool livenode = ((mflags >> (8 + r)) & 1u) && !slr_is_visited<1>(e, S.vh, mv[r], p);
-                    const uint32_t bal = __ballot_sync(FULL, livenode);
-                    if (livenode) S.node[nlive + __popc(bal & ((1u << lane) - 1u))] = make_uint2(mv[r], slr_node_meta(p, j, p1, p2));
-                    nlive += __popc(bal);
-                }
-                __syncwarp();
                 // ---- level 2: probe pi = node * 12 + (group, op); 32 probes per warp step.  The search for the ED-2
                 // slot stops once a hit is known and every probe of its node has been evaluated (later nodes only
                 // have larger ranks; the reference keeps enumerating but HashSet.add is then a no-op).

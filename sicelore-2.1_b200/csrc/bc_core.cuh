@@ -91,46 +91,49 @@ template <int LEVEL> SLR_HD bool slr_is_visited(const SlrExpand &e, const unsign
 
 // Test slot pattern P of table g against the op-mutants (0 SUB, 1 INS, 2 DEL) of node e that fall into digit
 // group g.  Returns the smallest traversal rank q*16 + idx (idx: 0-3 SUB base, 4-7 INS base, 8 DEL) of a
-// generating, non-visited mutant, or SLR_NONE32.  s = the full candidate barcode.
+// generating, non-visited mutant, or SLR_NONE32.  rest = the probe's rest (s = slr_key_join(rest, P, g) is the
+// full candidate barcode).
 // INS / DEL: "a 4-digit string is a 3-digit string plus one digit": with lpre = common leading digits and
 // lsuf = common trailing digits the generating positions are exactly the interval [3 - lsuf, lpre].
-template <int LEVEL> SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *vh, int g, int op, uint32_t P, uint32_t s)
+// The first half is a straight-line filter (a slot with the right tag is a list barcode that agrees with the node
+// outside the digit group, but only ~5 % of those are one edit away); the rest runs for real candidates only.
+template <int LEVEL> SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *vh, int g, int op, uint32_t P,
+                                                      uint32_t rest, uint32_t &s_out)
 {
     const uint32_t csg = (e.cs >> (24 - 8 * g)) & 0xFFu;
+    const uint32_t x = P ^ csg;
+    const uint32_t d = (x | (x >> 1)) & 0x55u;
+    const bool sub_ok = d != 0u && (d & (d - 1u)) == 0u;        // exactly one digit differs
+    const uint32_t long4 = (op == 1) ? P : csg, short3 = (op == 1) ? (csg >> 2) : (P >> 2);
+    const uint32_t xh = (long4 >> 2) ^ short3, xl = (long4 & 0x3Fu) ^ short3;
+    const int hi = (slr_clz(xh) - 26) >> 1;                    // common leading digits, 0..3
+    int xx = 3 - ((slr_ffs(xl | 0x40u) - 1) >> 1);             // 3 - common trailing digits
+    const uint32_t n0 = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;   // digit that follows the group after a deletion
+    const bool indel_ok = xx <= hi && (op == 1 || (P & 3u) == n0);
+    if (!(op == 0 ? sub_ok : indel_ok)) return SLR_NONE32;
+
     int q;
     uint32_t idx;
     if (op == 0) {                                             // substitutions (L257-L273)
-        const uint32_t x = P ^ csg;
-        const uint32_t d = (x | (x >> 1)) & 0x55u;
-        if (d == 0u || (d & (d - 1u)) != 0u) return SLR_NONE32;   // exactly one digit differs
         const int il = 3 - ((slr_ffs(d) - 1) >> 1);
         q = 4 * g + il;
         if (q == e.pskip) return SLR_NONE32;
         idx = (P >> (2 * (3 - il))) & 3u;
-    } else {
-        uint32_t long4, short3;
-        if (op == 1) {                                         // insertions (L284-L300): new digit at j = q+1
-            long4 = P; short3 = csg >> 2;
-        } else {                                               // deletions (L313-L357): digit q removed, cbase appended
-            const uint32_t n0 = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;
-            if ((P & 3u) != n0) return SLR_NONE32;
-            long4 = csg; short3 = P >> 2;
-        }
-        const uint32_t xh = (long4 >> 2) ^ short3, xl = (long4 & 0x3Fu) ^ short3;
-        const int hi = (slr_clz(xh) - 26) >> 1;                // common leading digits, 0..3
-        int x = 3 - ((slr_ffs(xl | 0x40u) - 1) >> 1);          // 3 - common trailing digits
+    } else {                                                   // insertions (L284-L300): new digit at j = q+1; deletions (L313-L357)
         q = -2;
-        for (; x <= hi; x++) {                                 // almost always a single candidate
-            const int qq = (op == 1) ? 4 * g + x - 1 : 4 * g + x;
+        for (; xx <= hi; xx++) {                               // almost always a single candidate
+            const int qq = (op == 1) ? 4 * g + xx - 1 : 4 * g + xx;
             if (qq < 0 || qq > 14 || qq == e.pskip) continue;
             if (op == 1 && qq == 14 && (e.cs & 3u) != 0u) continue;   // the `>>> 64` value: garbage in bits 62-63
             q = qq;
             break;
         }
         if (q < 0) return SLR_NONE32;
-        idx = (op == 1) ? 4u + ((P >> (2 * (3 - x))) & 3u) : 8u;
+        idx = (op == 1) ? 4u + ((P >> (2 * (3 - xx))) & 3u) : 8u;
     }
+    const uint32_t s = slr_key_join(rest, P, g);
     if (slr_is_visited<LEVEL>(e, vh, s, q)) return SLR_NONE32;
+    s_out = s;
     return (uint32_t)(q * 16) + idx;
 }
 
@@ -140,11 +143,11 @@ struct SlrProbe {
 };
 SLR_HD SlrProbe slr_probe_addr(const SlrTableDev &t, uint32_t cs, uint32_t cbase, int g, int op)
 {
-    const int lo_bits = 24 - 8 * g;
-    const uint32_t himask = ~slr_lowmask(lo_bits + 8);         // digit groups above g (g = 0: none)
+    const uint32_t lomask = 0x00FFFFFFu >> (8 * g);            // digit groups below g
+    const uint32_t himask = ~(0xFFFFFFFFu >> (8 * g));         // digit groups above g (g = 0: none)
     const uint32_t lo = (op == 0) ? cs : ((op == 1) ? (cs >> 2) : ((cs << 2) | cbase));
     SlrProbe pr;
-    pr.rest = ((cs & himask) >> 8) | (lo & slr_lowmask(lo_bits));
+    pr.rest = ((cs & himask) >> 8) | (lo & lomask);
     const uint32_t m = slr_mix24(pr.rest);
     const int tb = 24 - t.bbits;
     pr.bucket = m >> tb;
@@ -156,14 +159,14 @@ SLR_HD SlrProbe slr_probe_addr(const SlrTableDev &t, uint32_t cs, uint32_t cbase
 template <int LEVEL> SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
                                                    const SlrProbe &pr, const SlrBucket &k, uint32_t &bc_out)
 {
-    uint32_t match = slr_tag_match(k, pr.tag);
+    uint32_t match = slr_tag_match(k, pr.tag);                 // bit 8*byte + word: slot 4*word + byte carries the tag
     uint32_t best = SLR_NONE32;
     while (match) {
-        const int i = slr_ffs(match) - 1;
+        const int b = slr_ffs(match) - 1;
         match &= match - 1u;
-        const uint32_t P = slr_bucket_pat(k, i);
-        const uint32_t s = slr_key_join(pr.rest, P, g);
-        const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, P, s);
+        const uint32_t P = slr_bucket_pat(k, b);
+        uint32_t s = 0;
+        const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, P, pr.rest, s);
         if (r < best) { best = r; bc_out = s; }
     }
     if (t.st_total > 0 && slr_bucket_full(k)) {                // overflowed bucket: rare
@@ -171,9 +174,8 @@ template <int LEVEL> SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const 
         for (int i = slr_stash_lower(t, g, pr.bucket); i < t.st_n[g] && slr_ldg(t.st_bucket[g] + i) == pr.bucket; i++) {
             const uint32_t sl = slr_ldg(t.st_slot[g] + i);
             if ((sl >> 8) != want_hi) continue;
-            const uint32_t P = sl & 0xFFu;
-            const uint32_t s = slr_key_join(pr.rest, P, g);
-            const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, P, s);
+            uint32_t s = 0;
+            const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, sl & 0xFFu, pr.rest, s);
             if (r < best) { best = r; bc_out = s; }
         }
     }

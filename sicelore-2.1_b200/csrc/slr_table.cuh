@@ -142,24 +142,21 @@ SLR_HD uint32_t slr_eq_bytes(uint32_t x, uint32_t want)
     const uint32_t h = x ^ want;
     return ~(((h & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h) & 0x80808080u;
 }
-// gather bit 7 of the four bytes into a nibble (bits 31..28 of the product are 0, no carries: see DESIGN.md §3)
-SLR_HD uint32_t slr_nibble_of(uint32_t eq) { return ((eq >> 7) * 0x01020408u) >> 24; }
-
-// Bit i of the result (i = 0..15) set  <=>  slot i is valid and carries `tag`.
+// Bit 8*byte + word of the result set  <=>  slot 4*word + byte (byte `byte` of tag word `word`) is valid and
+// carries `tag` (the four per-word byte masks are interleaved with four shifts; the order of the set bits is
+// irrelevant to the callers, which take a minimum over all matches).
 SLR_HD uint32_t slr_tag_match(const SlrBucket &k, uint32_t tag)
 {
     const uint32_t want = (0x80u | tag) * 0x01010101u;
-    const uint32_t e0 = slr_eq_bytes(k.a.x, want), e1 = slr_eq_bytes(k.a.y, want);
-    const uint32_t e2 = slr_eq_bytes(k.a.z, want), e3 = slr_eq_bytes(k.a.w, want);
-    if ((e0 | e1 | e2 | e3) == 0u) return 0u;                              // fast path: nothing matches
-    return slr_nibble_of(e0) | (slr_nibble_of(e1) << 4) | (slr_nibble_of(e2) << 8) | (slr_nibble_of(e3) << 12);
+    return (slr_eq_bytes(k.a.x, want) >> 7) | (slr_eq_bytes(k.a.y, want) >> 6) | (slr_eq_bytes(k.a.z, want) >> 5) |
+           (slr_eq_bytes(k.a.w, want) >> 4);
 }
 
-// pattern byte of slot i
-SLR_HD uint32_t slr_bucket_pat(const SlrBucket &k, int i)
+// pattern byte of the slot named by bit b of slr_tag_match
+SLR_HD uint32_t slr_bucket_pat(const SlrBucket &k, int b)
 {
-    const bool lo = i < 8;
-    return slr_byte_perm(lo ? k.b.x : k.b.z, lo ? k.b.y : k.b.w, (uint32_t)(i & 7)) & 0xFFu;
+    const uint32_t w = (b & 2) ? ((b & 1) ? k.b.w : k.b.z) : ((b & 1) ? k.b.y : k.b.x);
+    return (w >> (b & 24)) & 0xFFu;
 }
 
 SLR_HD bool slr_bucket_full(const SlrBucket &k) { return ((k.a.x & k.a.y & k.a.z & k.a.w) & 0x80808080u) == 0x80808080u; }
