@@ -27,7 +27,7 @@ namespace {
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 #ifndef SLR_BC_MINB_ED2
-#define SLR_BC_MINB_ED2 3                      // resident CTAs per SM the ED-2 kernel is compiled for (register cap 80)
+#define SLR_BC_MINB_ED2 4                      // resident CTAs per SM the ED-2 kernel is compiled for (register cap 64)
 #endif
 
 struct alignas(16) WarpShared {
@@ -66,8 +66,6 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
     WarpShared &S = smem[wib];
     const long long nwarps = (long long)gridDim.x * WARPS_PER_BLOCK;
     const int noff = 2 * plusminus + 1;
-    // root expansion: lanes 0..11 = (digit group, op); lane 0's bucket (table 0, rest of w) also answers the ED-0 probe
-    const int g1 = (lane * 11) >> 5, op1 = lane - 3 * g1;
 
     for (long long read = (long long)blockIdx.x * WARPS_PER_BLOCK + wib; read < n; read += nwarps) {
         // ---- the slice: lane i owns char i; bit planes by ballot --------------------------------------------
@@ -97,28 +95,17 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
             if (dead_window) continue;
 
             // ======== BarcodeMatchTester.doJob for this window ================================================
-            // issue the root's bucket loads first: their latency overlaps the visited-hash construction
-            SlrExpand e;
-            e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.use_visited = EDMAX >= 2;
-            SlrProbe pr1;
-            SlrBucket bk1;
-            const bool root_lane = EDMAX >= 1 ? lane < 12 : lane == 0;
-            if (root_lane) {
-                pr1 = slr_probe_addr(tab, w, p1, g1, op1);
-                bk1 = slr_load_bucket(tab, g1, pr1.bucket);
-            }
-
             int nlive = 0;
             if (EDMAX >= 2) {
                 // One pass over the 144 level-1 slots in processing order (5 rounds of 32): build the visited hash
                 // value -> earliest processing time t = p*16 + (8-j), and keep the nodes the reference expands
-                // (valid, no 62-63 garbage, not "already tested" when created: slr_is_visited<1> with the time just
-                // found) as compact (sequence, meta) records.
+                // (valid, no 62-63 garbage, not "already tested" when created: slr_is_visited at level 1 with the
+                // time just found) as compact (sequence, meta) records.
                 ulonglong2 *vh2 = reinterpret_cast<ulonglong2 *>(S.vh);
 #pragma unroll
                 for (int i = 0; i < SLR_VH_SIZE / 64; i++) vh2[i * 32 + lane] = make_ulonglong2(SLR_VH_EMPTY, SLR_VH_EMPTY);
                 __syncwarp();
-#pragma unroll
+#pragma unroll 1
                 for (int r = 0; r < 5; r++) {
                     const int sl = r * 32 + lane;
                     const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
@@ -139,42 +126,56 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
                 __syncwarp();
             }
 
-            // ---- ED 0 (L204-L206) and ED 1: first hit in creation order = warp minimum of the traversal ranks --
-            uint32_t r1 = SLR_NONE32, bc1 = 0;
-            bool hit0 = false;
-            if (root_lane) {
-                if (lane == 0) hit0 = slr_contains_in(tab, bk1, pr1.bucket, pr1.tag, w >> 24);
-                if (EDMAX >= 1) r1 = slr_probe_eval<1>(tab, e, S.vh, g1, op1, pr1, bk1, bc1);
-            }
-            uint32_t valid_levels = __shfl_sync(FULL, hit0 ? 1u : 0u, 0);
-            if (valid_levels && lane == 0) { S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; }
-            if (EDMAX >= 1) {
-                const uint32_t rmin = __reduce_min_sync(FULL, r1);
-                if (rmin != SLR_NONE32) {
-                    const int src = __ffs((int)__ballot_sync(FULL, r1 == rmin)) - 1;
-                    bc1 = __shfl_sync(FULL, bc1, src);
-                    valid_levels |= 2u;
-                    if (lane == 0) { S.ms.m_bc[k][1] = bc1; S.ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
-                }
-            }
-            if (EDMAX >= 2) {
-                // ---- level 2: probe pi = node * 12 + (group, op); 32 probes per warp step.  The search for the ED-2
-                // slot stops once a hit is known and every probe of its node has been evaluated (later nodes only
-                // have larger ranks; the reference keeps enumerating but HashSet.add is then a no-op).
-                const int nprobe = nlive * 12;
-                uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
-                for (int base = 0; base < nprobe; base += 32) {
-                    const int pi = base + lane;
-                    uint32_t r2 = SLR_NONE32, bc2 = 0, c1 = 0;
-                    if (pi < nprobe) {
-                        const int nd = pi / 12, rem = pi - nd * 12;
-                        const int g = (rem * 11) >> 5, op = rem - 3 * g;
-                        const uint2 nrec = S.node[nd];
-                        const SlrExpand e2 = slr_node_expand(nrec.x, nrec.y, w);
+            // ---- one probe loop for all levels: probe pi = node * 12 + (digit group, op), node 0 = the root (its hits are
+            // ED 1; probe 0's bucket = table 0 / rest of w also answers the ED-0 lookup, L204-L206), node n >= 1 = the
+            // n-th live level-1 node (hits are ED 2).  32 probes per warp step; "first hit wins" = warp minimum of
+            // (node, traversal rank).  The ED-2 search stops once a hit is known and every probe of its node has been
+            // evaluated (later nodes only have larger ranks; the reference keeps enumerating but HashSet.add is then
+            // a no-op).
+            uint32_t valid_levels = 0;
+            const int nprobe = EDMAX >= 1 ? 12 + nlive * 12 : 1;
+            uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
+#pragma unroll 1
+            for (int base = 0; base < nprobe; base += 32) {
+                const int pi = base + lane;
+                uint32_t r2 = SLR_NONE32, bc2 = 0, c1 = 0;
+                bool hit0 = false;
+                if (pi < nprobe) {
+                    const int nd = pi / 12, rem = pi - nd * 12;
+                    const int g = (rem * 11) >> 5, op = rem - 3 * g;
+                    SlrExpand e2;
+                    if (nd == 0) e2 = slr_root_expand(w, p1, EDMAX >= 2);
+                    else {
+                        const uint2 nrec = S.node[nd - 1];
+                        e2 = slr_node_expand(nrec.x, nrec.y, w);
                         c1 = nrec.y >> 10;
-                        r2 = slr_expand_group<2>(tab, e2, S.vh, g, op, bc2);
+                    }
+                    const SlrProbe pr = slr_probe_addr(tab, e2.cs, e2.cbase, g, op);
+                    const SlrBucket bk = slr_load_bucket(tab, g, pr.bucket);
+                    if (pi == 0) hit0 = slr_contains_in(tab, bk, pr.bucket, pr.tag, w >> 24);
+                    if (EDMAX >= 1) {
+                        r2 = slr_probe_eval(tab, e2, S.vh, g, op, pr, bk, bc2);
                         if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
                     }
+                }
+                if (base == 0) {
+                    if (__shfl_sync(FULL, hit0 ? 1u : 0u, 0)) {
+                        valid_levels |= 1u;
+                        if (lane == 0) { S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; }
+                    }
+                    if (EDMAX >= 1) {                                             // first ED-1 hit in creation order
+                        const uint32_t r1 = r2 < 256u ? r2 : SLR_NONE32;
+                        const uint32_t rmin = __reduce_min_sync(FULL, r1);
+                        if (rmin != SLR_NONE32) {
+                            const int src = __ffs((int)__ballot_sync(FULL, r1 == rmin)) - 1;
+                            const uint32_t bc1 = __shfl_sync(FULL, bc2, src);
+                            valid_levels |= 2u;
+                            if (lane == 0) { S.ms.m_bc[k][1] = bc1; S.ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
+                        }
+                        if (r2 < 256u) r2 = SLR_NONE32;
+                    }
+                }
+                if (EDMAX >= 2) {
                     const uint32_t m2 = __reduce_min_sync(FULL, r2);
                     if (m2 < best) {
                         const int src = __ffs((int)__ballot_sync(FULL, r2 == m2)) - 1;
@@ -184,10 +185,10 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
                     }
                     if (best != SLR_NONE32 && (int)(best >> 8) * 12 + 12 <= base + 32) break;
                 }
-                if (best != SLR_NONE32) {
-                    valid_levels |= 4u;
-                    if (lane == 0) { S.ms.m_bc[k][2] = bcb; S.ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u)); }
-                }
+            }
+            if (EDMAX >= 2 && best != SLR_NONE32) {
+                valid_levels |= 4u;
+                if (lane == 0) { S.ms.m_bc[k][2] = bcb; S.ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u)); }
             }
             if (lane == 0) S.ms.m_valid[k] = (uint8_t)valid_levels;
             __syncwarp();

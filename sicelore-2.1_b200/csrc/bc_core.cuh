@@ -65,6 +65,7 @@ struct SlrExpand {
     int pskip;          // posTreatedInPreviousLevel (must not be mutated again, L227), -1 for the root
     uint32_t cbase;     // base appended by a deletion: post[nDel+1] (L329)
     uint32_t tproc;     // processing time of this node (level 2 only)
+    int level;          // 1 = root expansion (hits are ED 1), 2 = level-1 node expansion (hits are ED 2)
     bool use_visited;   // ed >= 2 (NucTwoBitPerBaseEDtesterBase.java:L82-L95)
 };
 
@@ -73,9 +74,9 @@ struct SlrExpand {
 //   level 1: {w, once the root did position 0} U {level-1 mutants of earlier root positions}
 //   level 2: {w} U {level-1 nodes processed before this node} U {this node, after its first position}
 // Monotone in q: visited at q implies visited at every later position of the same node.
-template <int LEVEL> SLR_HD bool slr_is_visited(const SlrExpand &e, const unsigned long long *vh, uint32_t s, int q)
+SLR_HD bool slr_is_visited(const SlrExpand &e, const unsigned long long *vh, uint32_t s, int q)
 {
-    if (LEVEL == 1) {
+    if (e.level == 1) {
         if (!e.use_visited) return false;
         if (q >= 1 && s == e.w) return true;
         const uint32_t t = slr_vh_tmin(vh, s);
@@ -97,7 +98,7 @@ template <int LEVEL> SLR_HD bool slr_is_visited(const SlrExpand &e, const unsign
 // lsuf = common trailing digits the generating positions are exactly the interval [3 - lsuf, lpre].
 // The first half is a straight-line filter (a slot with the right tag is a list barcode that agrees with the node
 // outside the digit group, but only ~5 % of those are one edit away); the rest runs for real candidates only.
-template <int LEVEL> SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *vh, int g, int op, uint32_t P,
+SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *vh, int g, int op, uint32_t P,
                                                       uint32_t rest, uint32_t &s_out)
 {
     const uint32_t csg = (e.cs >> (24 - 8 * g)) & 0xFFu;
@@ -132,7 +133,7 @@ template <int LEVEL> SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const
         idx = (op == 1) ? 4u + ((P >> (2 * (3 - xx))) & 3u) : 8u;
     }
     const uint32_t s = slr_key_join(rest, P, g);
-    if (slr_is_visited<LEVEL>(e, vh, s, q)) return SLR_NONE32;
+    if (slr_is_visited(e, vh, s, q)) return SLR_NONE32;
     s_out = s;
     return (uint32_t)(q * 16) + idx;
 }
@@ -155,8 +156,24 @@ SLR_HD SlrProbe slr_probe_addr(const SlrTableDev &t, uint32_t cs, uint32_t cbase
     return pr;
 }
 
+// Overflow stash of a full bucket (cold: P(bucket overflows) ~ 1e-4 for random lists).
+#define SLR_COLD static __host__ __device__ __noinline__
+SLR_COLD uint32_t slr_probe_stash(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
+                                                     const SlrProbe &pr, uint32_t best, uint32_t &bc_out)
+{
+    const uint32_t want_hi = 0x80u | pr.tag;
+    for (int i = slr_stash_lower(t, g, pr.bucket); i < t.st_n[g] && slr_ldg(t.st_bucket[g] + i) == pr.bucket; i++) {
+        const uint32_t sl = slr_ldg(t.st_slot[g] + i);
+        if ((sl >> 8) != want_hi) continue;
+        uint32_t s = 0;
+        const uint32_t r = slr_check_pattern(e, vh, g, op, sl & 0xFFu, pr.rest, s);
+        if (r < best) { best = r; bc_out = s; }
+    }
+    return best;
+}
+
 // Evaluate a loaded bucket: best (smallest) traversal rank and the matching barcode.
-template <int LEVEL> SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
+SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
                                                    const SlrProbe &pr, const SlrBucket &k, uint32_t &bc_out)
 {
     uint32_t match = slr_tag_match(k, pr.tag);                 // bit 8*byte + word: slot 4*word + byte carries the tag
@@ -166,28 +183,20 @@ template <int LEVEL> SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const 
         match &= match - 1u;
         const uint32_t P = slr_bucket_pat(k, b);
         uint32_t s = 0;
-        const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, P, pr.rest, s);
+        const uint32_t r = slr_check_pattern(e, vh, g, op, P, pr.rest, s);
         if (r < best) { best = r; bc_out = s; }
     }
-    if (t.st_total > 0 && slr_bucket_full(k)) {                // overflowed bucket: rare
-        const uint32_t want_hi = 0x80u | pr.tag;
-        for (int i = slr_stash_lower(t, g, pr.bucket); i < t.st_n[g] && slr_ldg(t.st_bucket[g] + i) == pr.bucket; i++) {
-            const uint32_t sl = slr_ldg(t.st_slot[g] + i);
-            if ((sl >> 8) != want_hi) continue;
-            uint32_t s = 0;
-            const uint32_t r = slr_check_pattern<LEVEL>(e, vh, g, op, sl & 0xFFu, pr.rest, s);
-            if (r < best) { best = r; bc_out = s; }
-        }
-    }
+    if (t.st_total > 0 && slr_bucket_full(k))                  // overflowed bucket: rare, kept out of line
+        best = slr_probe_stash(t, e, vh, g, op, pr, best, bc_out);
     return best;
 }
 
-template <int LEVEL> SLR_HD uint32_t slr_expand_group(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
+SLR_HD uint32_t slr_expand_group(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
                                                      uint32_t &bc_out)
 {
     const SlrProbe pr = slr_probe_addr(t, e.cs, e.cbase, g, op);
     const SlrBucket k = slr_load_bucket(t, g, pr.bucket);
-    return slr_probe_eval<LEVEL>(t, e, vh, g, op, pr, k, bc_out);
+    return slr_probe_eval(t, e, vh, g, op, pr, k, bc_out);
 }
 
 // counters the Java attaches to a mutant created by idx (0-3 SUB -> nSubstitutions, 4-7 INS -> nDeletions (L290),
@@ -203,10 +212,16 @@ SLR_HD uint32_t slr_node_meta(int p, int j, uint32_t p1, uint32_t p2)
     const uint32_t cb = (j >= 4 && j < 8) ? p2 : p1;
     return (uint32_t)(p * 16 + (8 - j)) | (cb << 8) | (slr_cnt_of((uint32_t)j) << 10);
 }
+SLR_HD SlrExpand slr_root_expand(uint32_t w, uint32_t p1, bool use_visited)
+{
+    SlrExpand e;
+    e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.level = 1; e.use_visited = use_visited;
+    return e;
+}
 SLR_HD SlrExpand slr_node_expand(uint32_t cs, uint32_t meta, uint32_t w)
 {
     SlrExpand e;
-    e.cs = cs; e.w = w; e.pskip = (int)((meta >> 4) & 15u); e.cbase = (meta >> 8) & 3u; e.tproc = meta & 0xFFu; e.use_visited = true;
+    e.cs = cs; e.w = w; e.pskip = (int)((meta >> 4) & 15u); e.cbase = (meta >> 8) & 3u; e.tproc = meta & 0xFFu; e.level = 2; e.use_visited = true;
     return e;
 }
 
@@ -302,32 +317,47 @@ SLR_HD bool slr_window(const SlrSliceBits &b, int len, int anc, int o, int three
 // BarcodeMatchTester.java:L443; JDK HashMap: capacity 16, resize above 12/24/48 entries, a chain reaching 9 nodes
 // resizes while capacity < 64), then the stable sort by OneMatch.compareTo (L449-L461), distinctByKey(matchingBC).
 // Fills everything but rank (needs the index map) and returns the best barcode's ED level, or -1.
-SLR_HD int slr_decide(const SlrMatchStore &S, int noff, int ed_max, slr_bc_result &res)
+// Capacity of the merged HashMap after all insertions (cold: only reached with >= 9 entries, see slr_decide).
+SLR_COLD int slr_decide_cap(const SlrMatchStore &S, int noff, bool &treeified)
 {
     int cap = 16, thr = 12, cnt = 0;
-    bool treeified = false;
+    treeified = false;
+#pragma unroll 1
     for (int k = 0; k < noff; k++) {
         const uint32_t sp = S.m_w[k] ^ (S.m_w[k] >> 16);
+#pragma unroll 1
         for (int lv = 0; lv < 3; lv++) {
             if (!((S.m_valid[k] >> lv) & 1)) continue;
-            int chain = 0;
-            for (int k2 = 0; k2 <= k; k2++) {
+            int chain = slr_popc(S.m_valid[k] & ((1u << lv) - 1u));
+#pragma unroll 1
+            for (int k2 = 0; k2 < k; k2++) {
                 const uint32_t sp2 = S.m_w[k2] ^ (S.m_w[k2] >> 16);
-                if ((sp2 & (uint32_t)(cap - 1)) != (sp & (uint32_t)(cap - 1))) continue;
-                for (int l2 = 0; l2 < 3; l2++)
-                    if (((S.m_valid[k2] >> l2) & 1) && (k2 < k || l2 < lv)) chain++;
+                if (((sp2 ^ sp) & (uint32_t)(cap - 1)) == 0u) chain += slr_popc(S.m_valid[k2] & 7u);
             }
             cnt++;
             if (chain >= 8) { if (cap < 64) { cap <<= 1; thr <<= 1; } else treeified = true; }
             if (cnt > thr) { cap <<= 1; thr <<= 1; }
         }
     }
+    return cap;
+}
+
+SLR_HD int slr_decide(const SlrMatchStore &S, int noff, int ed_max, slr_bc_result &res)
+{
+    int cnt = 0;
+#pragma unroll 1
+    for (int k = 0; k < noff; k++) cnt += slr_popc(S.m_valid[k] & 7u);
+    int cap = 16;                                  // <= 8 entries: no bin reaches 9 nodes, no resize above 12
+    bool treeified = false;
+    if (cnt > 8) cap = slr_decide_cap(S, noff, treeified);
     if (cnt == 0) return -1;
     if (treeified) res.flags |= SLR_F_TIE_UNPIN;
     uint32_t bestkey = SLR_NONE32;
     int bk = 0, blv = 0;
+#pragma unroll 1
     for (int k = 0; k < noff; k++) {
         const uint32_t sp = S.m_w[k] ^ (S.m_w[k] >> 16);
+#pragma unroll
         for (int lv = 0; lv < 3; lv++) {
             if (!((S.m_valid[k] >> lv) & 1)) continue;
             const uint32_t key = ((uint32_t)lv << 20) | ((k != 0 ? 1u : 0u) << 16) | ((sp & (uint32_t)(cap - 1)) << 8) | (uint32_t)(k * 3 + lv);
@@ -336,7 +366,9 @@ SLR_HD int slr_decide(const SlrMatchStore &S, int noff, int ed_max, slr_bc_resul
     }
     const uint32_t bbc = S.m_bc[bk][blv];
     int second = 0x7FFFFFFF;
+#pragma unroll 1
     for (int k = 0; k < noff; k++)
+#pragma unroll
         for (int lv = 0; lv < 3; lv++)
             if (((S.m_valid[k] >> lv) & 1) && S.m_bc[k][lv] != bbc && lv < second) second = lv;
     res.ed = blv;

@@ -45,8 +45,7 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
         if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window)) { flags |= SLR_F_EXCEPTION; break; }
         ms.m_w[k] = w;
         if (dead_window) continue;
-        SlrExpand e;
-        e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.use_visited = ed_max >= 2;
+        const SlrExpand e = slr_root_expand(w, p1, ed_max >= 2);
         if (ed_max >= 2) {
             for (int i = 0; i < SLR_VH_SIZE; i++) vh[i] = SLR_VH_EMPTY;
             for (int sl = 0; sl < 144; sl++) {
@@ -67,7 +66,7 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
             if (lane == 0 && slr_contains_in(tab, bk, pr.bucket, pr.tag, w >> 24)) valid_levels = 1u;
             if (ed_max >= 1) {
                 uint32_t b = 0;
-                const uint32_t r = slr_probe_eval<1>(tab, e, vh, g, op, pr, bk, b);
+                const uint32_t r = slr_probe_eval(tab, e, vh, g, op, pr, bk, b);
                 if (r < rmin) { rmin = r; bc1 = b; }
             }
         }
@@ -79,7 +78,7 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
                 const int p = sl / 9, j = 8 - (sl - p * 9);
                 bool v, d;
                 const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
-                if (v && !d && !slr_is_visited<1>(e, vh, mval, p)) {
+                if (v && !d && !slr_is_visited(e, vh, mval, p)) {
                     node_cs[nlive] = mval;
                     node_meta[nlive++] = slr_node_meta(p, j, p1, p2);
                 }
@@ -94,7 +93,7 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
                     const int g = (rem * 11) >> 5, op = rem - 3 * g;
                     const SlrExpand e2 = slr_node_expand(node_cs[nd], node_meta[nd], w);
                     uint32_t b = 0;
-                    uint32_t r2 = slr_expand_group<2>(tab, e2, vh, g, op, b);
+                    uint32_t r2 = slr_expand_group(tab, e2, vh, g, op, b);
                     (*n_loads)++;
                     if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
                     if (r2 < best) { best = r2; bcb = b; cntb = node_meta[nd] >> 10; }

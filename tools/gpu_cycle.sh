@@ -4,5 +4,6 @@ tag=${1:-x}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_tests.log 2>&1; tail -3 gpurun_out/${tag}_tests.log
 python tools/perf_bc.py 3000000 3000000 2 2000000 5
+for v in sicelore-2.1_b200/libslr_var_*.so; do [ -f "$v" ] && SLR_LIB_GPU=$PWD/$v python tools/perf_bc.py 3000000 3000000 2 2000000 5; done
 python tools/perf_bc.py 737280 737 1 10000000 5
 ncu --set full --clock-control none --import-source on -k regex:bc_assign -c 1 -o gpurun_out/${tag}_bc_full python tools/prof_bc.py 3000000 3000000 2 1000000 1 > gpurun_out/${tag}_ncu.log 2>&1; tail -1 gpurun_out/${tag}_ncu.log
