@@ -34,6 +34,7 @@ struct alignas(16) WarpShared {
     unsigned long long vh[SLR_VH_SIZE];        // visited hash: (value << 32) | processing time
     uint2 node[144];                           // level-1 nodes to expand, in processing order: (sequence, slr_node_meta)
     SlrMatchStore ms;
+    uint32_t win[SLR_MAX_OFFSETS];             // per window: p1 | p2 << 2 | dead << 4   (the window itself is ms.m_w)
 };
 
 // First insertion wins: the caller inserts in increasing processing time (rounds in order, duplicates inside a
@@ -55,6 +56,15 @@ __device__ __forceinline__ uint32_t vh_insert_first(unsigned long long *tab, uin
 }
 
 // Persistent warps: warp i of the grid takes reads i, i + #warps, ... (reads are i.i.d., a static stride balances).
+// Per read:
+//   1. the 2*plusminus+1 windows (bit-field extracts of the ballot planes);
+//   2. levels 0 and 1 of ALL windows: 12 bucket probes per window (4 digit groups x SUB/INS/DEL), two windows per warp
+//      step (16 lanes each); "first hit wins" = minimum traversal rank over the 16 lanes of a window;
+//   3. slr_level2_plan: which ED-2 searches can still change the record (most reads: none, or just enough to settle
+//      ed_second) - the reference runs all of them, but its HashSet.add / distinctByKey make the rest dead work;
+//   4. per remaining window: visited hash + live level-1 nodes, then 32 probes per warp step over the nodes in the
+//      reference's LIFO processing order, stopping at the first step whose hit cannot be beaten;
+//   5. merge + decision (slr_decide), rank lookup, counter, one 32-byte record.
 template <int EDMAX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EDMAX >= 2 ? SLR_BC_MINB_ED2 : 4)
 bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t *__restrict__ slices, int stride, int slice_len,
@@ -80,122 +90,141 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
         sb.unknown = __ballot_sync(FULL, !slr_in_encode_matrix(ch));
         sb.over253 = __ballot_sync(FULL, ch >= 254u);
 
+        // ---- 1. windows: lane k computes window k (Parser.java:L205-L221) ---------------------------------------
         uint32_t flags = 0;
-        if (lane < SLR_MAX_OFFSETS) S.ms.m_valid[lane] = 0;
-        __syncwarp();
-
-        for (int k = 0; k < noff; k++) {
-            uint32_t w, p1, p2;
-            bool dead_window;
-            if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, EDMAX, w, p1, p2, dead_window)) {
-                flags |= SLR_F_EXCEPTION;
-                break;
+        {
+            uint32_t w = 0, p1 = 0, p2 = 0;
+            bool dead_window = false, ok = true;
+            if (lane < noff) ok = slr_window(sb, len, anc, slr_offset_of(lane), three_prime, EDMAX, w, p1, p2, dead_window);
+            if (lane < noff) {
+                S.ms.m_w[lane] = w;
+                S.ms.m_valid[lane] = 0;
+                S.win[lane] = p1 | (p2 << 2) | ((dead_window ? 1u : 0u) << 4);
             }
-            if (lane == 0) S.ms.m_w[k] = w;
-            if (dead_window) continue;
-
-            // ======== BarcodeMatchTester.doJob for this window ================================================
-            int nlive = 0;
-            if (EDMAX >= 2) {
-                // One pass over the 144 level-1 slots in processing order (5 rounds of 32): build the visited hash
-                // value -> earliest processing time t = p*16 + (8-j), and keep the nodes the reference expands
-                // (valid, no 62-63 garbage, not "already tested" when created: slr_is_visited at level 1 with the
-                // time just found) as compact (sequence, meta) records.
-                ulonglong2 *vh2 = reinterpret_cast<ulonglong2 *>(S.vh);
-#pragma unroll
-                for (int i = 0; i < SLR_VH_SIZE / 64; i++) vh2[i * 32 + lane] = make_ulonglong2(SLR_VH_EMPTY, SLR_VH_EMPTY);
-                __syncwarp();
-#pragma unroll 1
-                for (int r = 0; r < 5; r++) {
-                    const int sl = r * 32 + lane;
-                    const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
-                    bool v, d;
-                    const uint32_t mv = slr_gen_mutant(w, p & 15, j, p1, v, d);
-                    v = v && sl < 144;
-                    const uint32_t vmask = __ballot_sync(FULL, v);
-                    const uint32_t lowpeers = __match_any_sync(FULL, mv) & vmask & ((1u << lane) - 1u);
-                    uint32_t tfirst = (uint32_t)(p * 16 + jj);
-                    if (v && lowpeers == 0u) tfirst = vh_insert_first(S.vh, mv, tfirst);
-                    __syncwarp();
-                    tfirst = __shfl_sync(FULL, tfirst, (v && lowpeers != 0u) ? __ffs((int)lowpeers) - 1 : lane);
-                    const bool livenode = v && !d && !((p >= 1 && mv == w) || (int)(tfirst >> 4) < p);
-                    const uint32_t bal = __ballot_sync(FULL, livenode);
-                    if (livenode) S.node[nlive + __popc(bal & ((1u << lane) - 1u))] = make_uint2(mv, slr_node_meta(p, j, p1, p2));
-                    nlive += __popc(bal);
-                }
-                __syncwarp();
-            }
-
-            // ---- one probe loop for all levels: probe pi = node * 12 + (digit group, op), node 0 = the root (its hits are
-            // ED 1; probe 0's bucket = table 0 / rest of w also answers the ED-0 lookup, L204-L206), node n >= 1 = the
-            // n-th live level-1 node (hits are ED 2).  32 probes per warp step; "first hit wins" = warp minimum of
-            // (node, traversal rank).  The ED-2 search stops once a hit is known and every probe of its node has been
-            // evaluated (later nodes only have larger ranks; the reference keeps enumerating but HashSet.add is then
-            // a no-op).
-            uint32_t valid_levels = 0;
-            const int nprobe = EDMAX >= 1 ? 12 + nlive * 12 : 1;
-            uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
-#pragma unroll 1
-            for (int base = 0; base < nprobe; base += 32) {
-                const int pi = base + lane;
-                uint32_t r2 = SLR_NONE32, bc2 = 0, c1 = 0;
-                bool hit0 = false;
-                if (pi < nprobe) {
-                    const int nd = pi / 12, rem = pi - nd * 12;
-                    const int g = (rem * 11) >> 5, op = rem - 3 * g;
-                    SlrExpand e2;
-                    if (nd == 0) e2 = slr_root_expand(w, p1, EDMAX >= 2);
-                    else {
-                        const uint2 nrec = S.node[nd - 1];
-                        e2 = slr_node_expand(nrec.x, nrec.y, w);
-                        c1 = nrec.y >> 10;
-                    }
-                    const SlrProbe pr = slr_probe_addr(tab, e2.cs, e2.cbase, g, op);
-                    const SlrBucket bk = slr_load_bucket(tab, g, pr.bucket);
-                    if (pi == 0) hit0 = slr_contains_in(tab, bk, pr.bucket, pr.tag, w >> 24);
-                    if (EDMAX >= 1) {
-                        r2 = slr_probe_eval(tab, e2, S.vh, g, op, pr, bk, bc2);
-                        if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
-                    }
-                }
-                if (base == 0) {
-                    if (__shfl_sync(FULL, hit0 ? 1u : 0u, 0)) {
-                        valid_levels |= 1u;
-                        if (lane == 0) { S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; }
-                    }
-                    if (EDMAX >= 1) {                                             // first ED-1 hit in creation order
-                        const uint32_t r1 = r2 < 256u ? r2 : SLR_NONE32;
-                        const uint32_t rmin = __reduce_min_sync(FULL, r1);
-                        if (rmin != SLR_NONE32) {
-                            const int src = __ffs((int)__ballot_sync(FULL, r1 == rmin)) - 1;
-                            const uint32_t bc1 = __shfl_sync(FULL, bc2, src);
-                            valid_levels |= 2u;
-                            if (lane == 0) { S.ms.m_bc[k][1] = bc1; S.ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
-                        }
-                        if (r2 < 256u) r2 = SLR_NONE32;
-                    }
-                }
-                if (EDMAX >= 2) {
-                    const uint32_t m2 = __reduce_min_sync(FULL, r2);
-                    if (m2 < best) {
-                        const int src = __ffs((int)__ballot_sync(FULL, r2 == m2)) - 1;
-                        bcb = __shfl_sync(FULL, bc2, src);
-                        cntb = __shfl_sync(FULL, c1, src);
-                        best = m2;
-                    }
-                    if (best != SLR_NONE32 && (int)(best >> 8) * 12 + 12 <= base + 32) break;
-                }
-            }
-            if (EDMAX >= 2 && best != SLR_NONE32) {
-                valid_levels |= 4u;
-                if (lane == 0) { S.ms.m_bc[k][2] = bcb; S.ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u)); }
-            }
-            if (lane == 0) S.ms.m_valid[k] = (uint8_t)valid_levels;
-            __syncwarp();
+            if (__ballot_sync(FULL, !ok)) flags |= SLR_F_EXCEPTION;        // the Java throws at the first bad window: no record
         }
         __syncwarp();
 
-        // ======== merge + decision (Parser.java:L240-L311); uniform across the warp, lane 0 writes ============
+        if (!(flags & SLR_F_EXCEPTION)) {
+            // ---- 2. levels 0 and 1 of every window (BarcodeMatchTester.java:L204-L206 + the root's expansion) ----
+            // lanes 16h .. 16h+11 = the 12 probes of window kb + h; probe 0's bucket (table 0, rest of w) also answers
+            // the ED-0 lookup.
+#pragma unroll 1
+            for (int kb = 0; kb < noff; kb += 2) {
+                const int k = kb + (lane >> 4), rem = lane & 15;
+                uint32_t r2 = SLR_NONE32, bc2 = 0;
+                bool hit0 = false;
+                uint32_t w = 0;
+                if (k < noff && rem < (EDMAX >= 1 ? 12 : 1)) {
+                    w = S.ms.m_w[k];
+                    const uint32_t wi = S.win[k];
+                    if (!(wi & 16u)) {
+                        const int g = (rem * 11) >> 5, op = rem - 3 * g;
+                        const SlrExpand e1 = slr_root_expand(w, wi & 3u, EDMAX >= 2);
+                        const SlrProbe pr = slr_probe_addr(tab, w, wi & 3u, g, op);
+                        const SlrBucket bk = slr_load_bucket(tab, g, pr.bucket);
+                        if (rem == 0) hit0 = slr_contains_in(tab, bk, pr.bucket, pr.tag, w >> 24);
+                        if (EDMAX >= 1) r2 = slr_probe_eval(tab, e1, S.vh, g, op, pr, bk, bc2);
+                    }
+                }
+                uint32_t rmin = r2;                                              // minimum over the 16 lanes of the window
+                if (EDMAX >= 1) {
+#pragma unroll
+                    for (int d = 8; d >= 1; d >>= 1) rmin = min(rmin, __shfl_xor_sync(FULL, rmin, d));
+                }
+                const uint32_t winners = __ballot_sync(FULL, r2 == rmin && r2 != SLR_NONE32) & (0xFFFFu << (lane & 16));
+                const uint32_t bc1 = __shfl_sync(FULL, bc2, winners ? __ffs((int)winners) - 1 : lane);
+                if (rem == 0 && k < noff) {
+                    uint32_t lv = 0;
+                    if (hit0) { lv |= 1u; S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; }
+                    if (rmin != SLR_NONE32) { lv |= 2u; S.ms.m_bc[k][1] = bc1; S.ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
+                    S.ms.m_valid[k] = (uint8_t)lv;
+                }
+            }
+            __syncwarp();
+
+            if (EDMAX >= 2) {
+                // ---- 3. which ED-2 searches matter? ----------------------------------------------------------------
+                uint32_t bcA = 0;
+                const int plan = slr_level2_plan(S.ms, noff, bcA);
+                // ---- 4. ED-2 searches ---------------------------------------------------------------------------------
+#pragma unroll 1
+                for (int k = 0; k < noff && plan != SLR_L2_NONE; k++) {
+                    const uint32_t wi = S.win[k];
+                    if (wi & 16u) continue;
+                    const uint32_t w = S.ms.m_w[k], p1 = wi & 3u, p2 = (wi >> 2) & 3u;
+                    // One pass over the 144 level-1 slots in processing order (5 rounds of 32): build the visited hash
+                    // value -> earliest processing time t = p*16 + (8-j), and keep the nodes the reference expands
+                    // (valid, no 62-63 garbage, not "already tested" when created) as compact (sequence, meta) records.
+                    int nlive = 0;
+                    ulonglong2 *vh2 = reinterpret_cast<ulonglong2 *>(S.vh);
+#pragma unroll
+                    for (int i = 0; i < SLR_VH_SIZE / 64; i++) vh2[i * 32 + lane] = make_ulonglong2(SLR_VH_EMPTY, SLR_VH_EMPTY);
+                    __syncwarp();
+#pragma unroll 1
+                    for (int r = 0; r < 5; r++) {
+                        const int sl = r * 32 + lane;
+                        const int p = sl / 9, jj = sl - p * 9, j = 8 - jj;
+                        bool v, d;
+                        const uint32_t mv = slr_gen_mutant(w, p & 15, j, p1, v, d);
+                        v = v && sl < 144;
+                        const uint32_t vmask = __ballot_sync(FULL, v);
+                        const uint32_t lowpeers = __match_any_sync(FULL, mv) & vmask & ((1u << lane) - 1u);
+                        uint32_t tfirst = (uint32_t)(p * 16 + jj);
+                        if (v && lowpeers == 0u) tfirst = vh_insert_first(S.vh, mv, tfirst);
+                        __syncwarp();
+                        tfirst = __shfl_sync(FULL, tfirst, (v && lowpeers != 0u) ? __ffs((int)lowpeers) - 1 : lane);
+                        const bool livenode = v && !d && !((p >= 1 && mv == w) || (int)(tfirst >> 4) < p);
+                        const uint32_t bal = __ballot_sync(FULL, livenode);
+                        if (livenode) S.node[nlive + __popc(bal & ((1u << lane) - 1u))] = make_uint2(mv, slr_node_meta(p, j, p1, p2));
+                        nlive += __popc(bal);
+                    }
+                    __syncwarp();
+
+                    // probe pi = node * 12 + (digit group, op) over the live nodes; 32 probes per warp step; first hit wins =
+                    // warp minimum of (node, traversal rank).  The search stops once a hit is known and every probe of its
+                    // node has been evaluated (later nodes only have larger ranks).
+                    const int nprobe = nlive * 12;
+                    uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
+#pragma unroll 1
+                    for (int base = 0; base < nprobe; base += 32) {
+                        const int pi = base + lane;
+                        uint32_t r2 = SLR_NONE32, bc2 = 0, c1 = 0;
+                        if (pi < nprobe) {
+                            const int nd = pi / 12, rem = pi - nd * 12;
+                            const int g = (rem * 11) >> 5, op = rem - 3 * g;
+                            const uint2 nrec = S.node[nd];
+                            const SlrExpand e2 = slr_node_expand(nrec.x, nrec.y, w);
+                            c1 = nrec.y >> 10;
+                            const SlrProbe pr = slr_probe_addr(tab, e2.cs, e2.cbase, g, op);
+                            const SlrBucket bk = slr_load_bucket(tab, g, pr.bucket);
+                            r2 = slr_probe_eval(tab, e2, S.vh, g, op, pr, bk, bc2);
+                            if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
+                        }
+                        const uint32_t m2 = __reduce_min_sync(FULL, r2);
+                        if (m2 < best) {
+                            const int src = __ffs((int)__ballot_sync(FULL, r2 == m2)) - 1;
+                            bcb = __shfl_sync(FULL, bc2, src);
+                            cntb = __shfl_sync(FULL, c1, src);
+                            best = m2;
+                        }
+                        if (best != SLR_NONE32 && (int)(best >> 8) * 12 + 12 <= base + 32) break;
+                    }
+                    if (best != SLR_NONE32) {
+                        if (lane == 0) {
+                            S.ms.m_bc[k][2] = bcb;
+                            S.ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u));
+                            S.ms.m_valid[k] |= 4u;
+                        }
+                        if (plan == SLR_L2_UNTIL && bcb != bcA) break;               // ed_second is settled
+                    }
+                    __syncwarp();
+                }
+                __syncwarp();
+            }
+        }
+
+        // ======== 5. merge + decision (Parser.java:L240-L311); uniform across the warp, lane 0 writes ============
         slr_bc_result res;
         res.bc = 0; res.ed = -1; res.ed_second = 0x7FFFFFFF; res.offset = 0; res.n_ins = 0; res.n_del = 0; res.n_sub = 0;
         res.rank = -1; res.flags = flags;

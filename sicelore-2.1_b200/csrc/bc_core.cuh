@@ -74,13 +74,16 @@ struct SlrExpand {
 //   level 1: {w, once the root did position 0} U {level-1 mutants of earlier root positions}
 //   level 2: {w} U {level-1 nodes processed before this node} U {this node, after its first position}
 // Monotone in q: visited at q implies visited at every later position of the same node.
+// Level 1 needs no table: only the FIRST hit of the root expansion is kept and the earliest creation of a value is
+// never "already tested", so a later duplicate can only matter when every earlier creation was a dead one (the
+// INS at p = L-2 whose Java value carries garbage in bits 62-63: it never matches, but its (int) value
+// (w & ~3) | b is marked).  The only later creations of those values are the substitutions at the last position.
 SLR_HD bool slr_is_visited(const SlrExpand &e, const unsigned long long *vh, uint32_t s, int q)
 {
     if (e.level == 1) {
         if (!e.use_visited) return false;
         if (q >= 1 && s == e.w) return true;
-        const uint32_t t = slr_vh_tmin(vh, s);
-        return t != SLR_NONE32 && (int)(t >> 4) < q;
+        return q == 15 && (e.w & 3u) != 0u && ((s ^ e.w) & ~3u) == 0u;
     }
     if (s == e.w) return true;
     const uint32_t t = slr_vh_tmin(vh, s);
@@ -156,27 +159,48 @@ SLR_HD SlrProbe slr_probe_addr(const SlrTableDev &t, uint32_t cs, uint32_t cbase
     return pr;
 }
 
-// Overflow stash of a full bucket (cold: P(bucket overflows) ~ 1e-4 for random lists).
+// Overflow stash of a full bucket (cold: P(bucket overflows) ~ 1e-4 for random lists).  Out of line and called with
+// scalars only: a struct handed over by reference would have to live in local memory in the hot loop as well.
+// Returns best << 32 | barcode.
 #define SLR_COLD static __host__ __device__ __noinline__
-SLR_COLD uint32_t slr_probe_stash(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
-                                                     const SlrProbe &pr, uint32_t best, uint32_t &bc_out)
+SLR_COLD unsigned long long slr_probe_stash(const uint32_t *st_bucket, const uint16_t *st_slot, int st_total,
+                                            const unsigned long long *vh, uint32_t cs, uint32_t w, uint32_t epack, uint32_t gop,
+                                            uint32_t rest, uint32_t bucket, uint32_t tag, uint32_t best, uint32_t bc)
 {
-    const uint32_t want_hi = 0x80u | pr.tag;
-    for (int i = slr_stash_lower(t, g, pr.bucket); i < t.st_n[g] && slr_ldg(t.st_bucket[g] + i) == pr.bucket; i++) {
-        const uint32_t sl = slr_ldg(t.st_slot[g] + i);
+    SlrExpand e;
+    e.cs = cs; e.w = w; e.pskip = (int)(epack & 31u) - 1; e.cbase = (epack >> 5) & 3u; e.tproc = (epack >> 8) & 0xFFu;
+    e.level = (int)((epack >> 16) & 3u); e.use_visited = (epack >> 18) & 1u;
+    const int g = (int)(gop >> 2), op = (int)(gop & 3u);
+    const uint32_t want_hi = 0x80u | tag, gb = ((uint32_t)g << 24) | bucket;
+    for (int i = slr_stash_lower(st_bucket, st_total, gb); i < st_total && slr_ldg(st_bucket + i) == gb; i++) {
+        const uint32_t sl = slr_ldg(st_slot + i);
         if ((sl >> 8) != want_hi) continue;
         uint32_t s = 0;
-        const uint32_t r = slr_check_pattern(e, vh, g, op, sl & 0xFFu, pr.rest, s);
-        if (r < best) { best = r; bc_out = s; }
+        const uint32_t r = slr_check_pattern(e, vh, g, op, sl & 0xFFu, rest, s);
+        if (r < best) { best = r; bc = s; }
     }
-    return best;
+    return ((unsigned long long)best << 32) | bc;
 }
 
 // Evaluate a loaded bucket: best (smallest) traversal rank and the matching barcode.
 SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const unsigned long long *vh, int g, int op,
                                                    const SlrProbe &pr, const SlrBucket &k, uint32_t &bc_out)
 {
-    uint32_t match = slr_tag_match(k, pr.tag);                 // bit 8*byte + word: slot 4*word + byte carries the tag
+    // Tag filter AND a byte-parallel necessary condition on the pattern, the same straight-line code for all three ops
+    // (lanes of one warp mix them): a one-edit pattern agrees with the node's digit group either in the two leading
+    // digits or in two trailing digits (SUB: the other half; INS: digits 2,3 = the node's 1,2; DEL: digits 1,2 = the
+    // node's 2,3 and digit 3 = the digit that follows the group).  1/8 (DEL 1/32) of the unrelated slots survive.
+    const uint32_t csg0 = (e.cs >> (24 - 8 * g)) & 0xFFu;
+    const uint32_t nx = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;
+    const uint32_t mA = (op == 2) ? 0xF3u : 0xF0u, vA = (csg0 & 0xF0u) | ((op == 2) ? nx : 0u);
+    const uint32_t mB = (op == 2) ? 0x3Fu : 0x0Fu;
+    const uint32_t vB = (op == 0) ? (csg0 & 0x0Fu) : ((op == 1) ? ((csg0 >> 2) & 0x0Fu) : (((csg0 & 0x0Fu) << 2) | nx));
+    const uint32_t mA4 = mA * 0x01010101u, vA4 = vA * 0x01010101u, mB4 = mB * 0x01010101u, vB4 = vB * 0x01010101u;
+    const uint32_t want = (0x80u | pr.tag) * 0x01010101u;
+    uint32_t match = ((slr_eq_bytes(k.a.x, want) & (slr_eq_bytes(k.b.x & mA4, vA4) | slr_eq_bytes(k.b.x & mB4, vB4))) >> 7) |
+                     ((slr_eq_bytes(k.a.y, want) & (slr_eq_bytes(k.b.y & mA4, vA4) | slr_eq_bytes(k.b.y & mB4, vB4))) >> 6) |
+                     ((slr_eq_bytes(k.a.z, want) & (slr_eq_bytes(k.b.z & mA4, vA4) | slr_eq_bytes(k.b.z & mB4, vB4))) >> 5) |
+                     ((slr_eq_bytes(k.a.w, want) & (slr_eq_bytes(k.b.w & mA4, vA4) | slr_eq_bytes(k.b.w & mB4, vB4))) >> 4);
     uint32_t best = SLR_NONE32;
     while (match) {
         const int b = slr_ffs(match) - 1;
@@ -186,8 +210,14 @@ SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const u
         const uint32_t r = slr_check_pattern(e, vh, g, op, P, pr.rest, s);
         if (r < best) { best = r; bc_out = s; }
     }
-    if (t.st_total > 0 && slr_bucket_full(k))                  // overflowed bucket: rare, kept out of line
-        best = slr_probe_stash(t, e, vh, g, op, pr, best, bc_out);
+    if (t.st_total > 0 && slr_bucket_full(k)) {                // overflowed bucket: rare, kept out of line
+        const uint32_t epack = (uint32_t)(e.pskip + 1) | (e.cbase << 5) | (e.tproc << 8) | ((uint32_t)e.level << 16) |
+                               ((e.use_visited ? 1u : 0u) << 18);
+        const unsigned long long r = slr_probe_stash(t.st_bucket, t.st_slot, t.st_total, vh, e.cs, e.w, epack, (uint32_t)(g * 4 + op),
+                                                     pr.rest, pr.bucket, pr.tag, best, bc_out);
+        best = (uint32_t)(r >> 32);
+        bc_out = (uint32_t)r;
+    }
     return best;
 }
 
@@ -340,6 +370,43 @@ SLR_COLD int slr_decide_cap(const SlrMatchStore &S, int noff, bool &treeified)
         }
     }
     return cap;
+}
+
+// Which ED-2 searches can still change the record once levels 0 and 1 of every window are known?  (The reference runs
+// all of them; the kernel skips the ones whose result provably cannot reach the output.)
+//   SLR_L2_ALL   every window (nothing matched yet, or too many entries to pin the HashSet capacity)
+//   SLR_L2_NONE  none: the best match has ED <= 1 and another barcode already sits at ED <= 1, so neither best nor
+//                ed_second can move
+//   SLR_L2_UNTIL windows in order until one yields an ED-2 hit on a barcode other than bcA: every ED <= 1 entry
+//                carries bcA, so best is fixed and ed_second is 2 if such a hit exists, else none
+// With n01 + noff <= 8 entries in total the merged HashMap stays at capacity 16 whatever the ED-2 searches add (no
+// resize above 12, no bin of 9), so the tie order among the ED <= 1 entries - and with it the best match - is final.
+enum { SLR_L2_NONE = 0, SLR_L2_ALL = 1, SLR_L2_UNTIL = 2 };
+SLR_HD int slr_level2_plan(const SlrMatchStore &S, int noff, uint32_t &bcA)
+{
+    int n01 = 0;
+#pragma unroll 1
+    for (int k = 0; k < noff; k++) n01 += slr_popc(S.m_valid[k] & 3u);
+    bcA = 0;
+    if (n01 == 0 || n01 + noff > 8) return SLR_L2_ALL;
+    uint32_t bestkey = SLR_NONE32;
+#pragma unroll 1
+    for (int k = 0; k < noff; k++) {
+        const uint32_t sp = S.m_w[k] ^ (S.m_w[k] >> 16);
+#pragma unroll
+        for (int lv = 0; lv < 2; lv++) {
+            if (!((S.m_valid[k] >> lv) & 1)) continue;
+            const uint32_t key = ((uint32_t)lv << 20) | ((k != 0 ? 1u : 0u) << 16) | ((sp & 15u) << 8) | (uint32_t)(k * 3 + lv);
+            if (key < bestkey) { bestkey = key; bcA = S.m_bc[k][lv]; }
+        }
+    }
+    bool other = false;
+#pragma unroll 1
+    for (int k = 0; k < noff; k++)
+#pragma unroll
+        for (int lv = 0; lv < 2; lv++)
+            if (((S.m_valid[k] >> lv) & 1) && S.m_bc[k][lv] != bcA) other = true;
+    return other ? SLR_L2_NONE : SLR_L2_UNTIL;
 }
 
 SLR_HD int slr_decide(const SlrMatchStore &S, int noff, int ed_max, slr_bc_result &res)

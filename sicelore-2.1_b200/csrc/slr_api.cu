@@ -74,8 +74,7 @@ struct slr_bc_table {
     slr_ctx *ctx = nullptr;
     SlrTableDev dev;
     void *d_buckets = nullptr;                 // 4 tables, contiguous
-    void *d_stash_b[4] = {nullptr, nullptr, nullptr, nullptr};
-    void *d_stash_s[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *d_stash_b = nullptr, *d_stash_s = nullptr;
     void *d_ix_keys = nullptr, *d_ix_vals = nullptr, *d_rank = nullptr, *d_counts = nullptr;
     long long n = 0, n_distinct = 0;
 };
@@ -154,22 +153,18 @@ int slr_bc_table_create(slr_ctx *ctx, const uint64_t *barcodes2bit, const int32_
         if (e_ != cudaSuccess) { slr_bc_table_destroy(t); return fail(SLR_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } \
     } while (0)
     TRY_OR_FREE(cudaMalloc(&t->d_buckets, 4 * tbytes));
-    for (int g = 0; g < 4; g++) {
-        char *base = (char *)t->d_buckets + g * tbytes;
-        TRY_OR_FREE(cudaMemcpy(base, H.slots[g].data(), tbytes, cudaMemcpyHostToDevice));
-        t->dev.bk[g] = reinterpret_cast<const uint4 *>(base);
-        const size_t sn = H.st_bucket[g].size();
-        t->dev.st_n[g] = (int)sn;
-        t->dev.st_total += (int)sn;
-        if (sn) {
-            TRY_OR_FREE(cudaMalloc(&t->d_stash_b[g], sn * 4));
-            TRY_OR_FREE(cudaMalloc(&t->d_stash_s[g], sn * 2));
-            TRY_OR_FREE(cudaMemcpy(t->d_stash_b[g], H.st_bucket[g].data(), sn * 4, cudaMemcpyHostToDevice));
-            TRY_OR_FREE(cudaMemcpy(t->d_stash_s[g], H.st_slot[g].data(), sn * 2, cudaMemcpyHostToDevice));
-        }
-        t->dev.st_bucket[g] = (const uint32_t *)t->d_stash_b[g];
-        t->dev.st_slot[g] = (const uint16_t *)t->d_stash_s[g];
+    TRY_OR_FREE(cudaMemcpy(t->d_buckets, H.slots.data(), 4 * tbytes, cudaMemcpyHostToDevice));
+    t->dev.bk = reinterpret_cast<const uint4 *>(t->d_buckets);
+    const size_t sn = H.st_bucket.size();
+    t->dev.st_total = (int)sn;
+    if (sn) {
+        TRY_OR_FREE(cudaMalloc(&t->d_stash_b, sn * 4));
+        TRY_OR_FREE(cudaMalloc(&t->d_stash_s, sn * 2));
+        TRY_OR_FREE(cudaMemcpy(t->d_stash_b, H.st_bucket.data(), sn * 4, cudaMemcpyHostToDevice));
+        TRY_OR_FREE(cudaMemcpy(t->d_stash_s, H.st_slot.data(), sn * 2, cudaMemcpyHostToDevice));
     }
+    t->dev.st_bucket = (const uint32_t *)t->d_stash_b;
+    t->dev.st_slot = (const uint16_t *)t->d_stash_s;
     t->dev.bbits = H.bbits;
     const size_t ixn = (size_t)H.ix_mask + 1;
     TRY_OR_FREE(cudaMalloc(&t->d_ix_keys, ixn * 4));
@@ -199,7 +194,7 @@ void slr_bc_table_destroy(slr_bc_table *t)
     if (!t) return;
     if (t->ctx) cudaSetDevice(t->ctx->device);
     cudaFree(t->d_buckets);
-    for (int g = 0; g < 4; g++) { cudaFree(t->d_stash_b[g]); cudaFree(t->d_stash_s[g]); }
+    cudaFree(t->d_stash_b); cudaFree(t->d_stash_s);
     cudaFree(t->d_ix_keys); cudaFree(t->d_ix_vals); cudaFree(t->d_rank); cudaFree(t->d_counts);
     delete t;
 }

@@ -20,12 +20,11 @@
 #include <cuda_runtime.h>
 
 struct SlrTableDev {
-    const uint4 *bk[4];            // 2 x uint4 per bucket
-    const uint32_t *st_bucket[4];  // stash: sorted bucket ids
-    const uint16_t *st_slot[4];    //        and their slots
-    int st_n[4];
-    int st_total;                  // sum of st_n (0 for almost every list: the stash code is then skipped)
-    int bbits;                     // log2(#buckets), 17..22  (tag bits = 24 - bbits <= 7)
+    const uint4 *bk;               // the four tables back to back: table g starts at bucket g << bbits; 2 x uint4 per bucket
+    const uint32_t *st_bucket;     // stash of all four tables: sorted (g << 24 | bucket) ids
+    const uint16_t *st_slot;       //        and their slots
+    int st_total;                  // stash entries (0 for almost every list: the stash code is then skipped)
+    int bbits;                     // log2(#buckets per table), 17..22  (tag bits = 24 - bbits <= 7)
     const uint32_t *ix_keys;       // key -> index map (open addressing, linear probing)
     const int32_t *ix_vals;        //   -1 = empty
     uint32_t ix_mask;
@@ -127,12 +126,20 @@ struct SlrBucket {
     uint4 a, b;
 };
 
+// (no dynamically indexed member in SlrTableDev: a kernel parameter indexed at run time is copied to local memory)
 SLR_HD SlrBucket slr_load_bucket(const SlrTableDev &t, int g, uint32_t bucket)
 {
-    const uint4 *p = t.bk[g] + 2 * (size_t)bucket;
+    const uint4 *p = t.bk + 2 * (((size_t)g << t.bbits) + bucket);
     SlrBucket r;
-    r.a = slr_ldg(p);
-    r.b = slr_ldg(p + 1);
+#ifdef __CUDA_ARCH__
+    // one 256-bit read-only load = one 32-byte L2 sector per lane (sm_100: LDG.E.256.CONSTANT)
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+        : "l"(p));
+#else
+    r.a = p[0];
+    r.b = p[1];
+#endif
     return r;
 }
 
@@ -161,14 +168,13 @@ SLR_HD uint32_t slr_bucket_pat(const SlrBucket &k, int b)
 
 SLR_HD bool slr_bucket_full(const SlrBucket &k) { return ((k.a.x & k.a.y & k.a.z & k.a.w) & 0x80808080u) == 0x80808080u; }
 
-// first stash entry of `bucket` (lower bound); its entries end where st_bucket != bucket
-SLR_HD int slr_stash_lower(const SlrTableDev &t, int g, uint32_t bucket)
+// first stash entry of bucket id `gb` = g << 24 | bucket (lower bound); its entries end where st_bucket != gb
+SLR_HD int slr_stash_lower(const uint32_t *st_bucket, int st_total, uint32_t gb)
 {
-    int lo = 0, hi = t.st_n[g];
-    const uint32_t *b = t.st_bucket[g];
+    int lo = 0, hi = st_total;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (slr_ldg(b + mid) < bucket) lo = mid + 1; else hi = mid;
+        if (slr_ldg(st_bucket + mid) < gb) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -185,8 +191,8 @@ SLR_HD bool slr_contains_in(const SlrTableDev &t, const SlrBucket &k, uint32_t b
     if (hit) return true;
     if (t.st_total > 0 && slr_bucket_full(k)) {
         const uint32_t sw = 0x8000u | (tag << 8) | pat;
-        for (int i = slr_stash_lower(t, 0, bucket); i < t.st_n[0] && slr_ldg(t.st_bucket[0] + i) == bucket; i++)
-            if ((uint32_t)slr_ldg(t.st_slot[0] + i) == sw) return true;
+        for (int i = slr_stash_lower(t.st_bucket, t.st_total, bucket); i < t.st_total && slr_ldg(t.st_bucket + i) == bucket; i++)
+            if ((uint32_t)slr_ldg(t.st_slot + i) == sw) return true;
     }
     return false;
 }

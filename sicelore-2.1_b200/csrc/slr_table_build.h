@@ -9,9 +9,10 @@
 
 struct SlrTableHost {
     int bbits = 17;
-    std::vector<uint8_t> slots[4];             // (1 << bbits) buckets of 32 bytes per table: 16 tag bytes, 16 pattern bytes
-    std::vector<uint32_t> st_bucket[4];        // sorted stash
-    std::vector<uint16_t> st_slot[4];
+    std::vector<uint8_t> slots;                // 4 tables back to back, (1 << bbits) buckets of 32 bytes each: 16 tag bytes, 16 pattern bytes
+    std::vector<uint32_t> st_bucket;           // stash of all tables, sorted by (g << 24 | bucket)
+    std::vector<uint16_t> st_slot;
+    long long st_n[4] = {0, 0, 0, 0};          // stash entries per table (statistics)
     std::vector<uint32_t> ix_keys;
     std::vector<int32_t> ix_vals;
     uint32_t ix_mask = 0;
@@ -61,8 +62,10 @@ inline void slr_build_table(const uint64_t *keys, const int32_t *rank, long long
     T.bbits = force_bbits ? force_bbits : slr_choose_bbits(T.n_distinct);
     const int tb = 24 - T.bbits;
     const size_t nb = (size_t)1 << T.bbits;
+    T.slots.assign(4 * nb * 32, 0);
+    T.st_bucket.clear();
+    T.st_slot.clear();
     for (int g = 0; g < 4; g++) {
-        T.slots[g].assign(nb * 32, 0);
         std::vector<uint8_t> fill(nb, 0);
         std::vector<std::pair<uint32_t, uint16_t>> stash;
         for (uint32_t k : distinct) {
@@ -70,16 +73,15 @@ inline void slr_build_table(const uint64_t *keys, const int32_t *rank, long long
             const uint32_t bucket = m >> tb, tag = m & ((1u << tb) - 1u);
             const uint16_t slot = (uint16_t)(0x8000u | (tag << 8) | slr_key_pat(k, g));
             if (fill[bucket] < 16) {
-                uint8_t *b = &T.slots[g][(size_t)bucket * 32];
+                uint8_t *b = &T.slots[((size_t)g * nb + bucket) * 32];
                 b[fill[bucket]] = (uint8_t)(slot >> 8);
                 b[16 + fill[bucket]] = (uint8_t)(slot & 0xFFu);
                 fill[bucket]++;
-            } else stash.emplace_back(bucket, slot);
+            } else stash.emplace_back(((uint32_t)g << 24) | bucket, slot);
         }
         std::sort(stash.begin(), stash.end());
-        T.st_bucket[g].clear();
-        T.st_slot[g].clear();
-        for (auto &e : stash) { T.st_bucket[g].push_back(e.first); T.st_slot[g].push_back(e.second); }
+        T.st_n[g] = (long long)stash.size();
+        for (auto &e : stash) { T.st_bucket.push_back(e.first); T.st_slot.push_back(e.second); }
     }
 }
 
@@ -88,13 +90,10 @@ inline SlrTableDev slr_table_host_view(const SlrTableHost &T, unsigned long long
 {
     SlrTableDev d;
     memset(&d, 0, sizeof(d));
-    for (int g = 0; g < 4; g++) {
-        d.bk[g] = reinterpret_cast<const uint4 *>(T.slots[g].data());
-        d.st_bucket[g] = T.st_bucket[g].data();
-        d.st_slot[g] = T.st_slot[g].data();
-        d.st_n[g] = (int)T.st_bucket[g].size();
-        d.st_total += d.st_n[g];
-    }
+    d.bk = reinterpret_cast<const uint4 *>(T.slots.data());
+    d.st_bucket = T.st_bucket.data();
+    d.st_slot = T.st_slot.data();
+    d.st_total = (int)T.st_bucket.size();
     d.bbits = T.bbits;
     d.ix_keys = T.ix_keys.data();
     d.ix_vals = T.ix_vals.data();

@@ -20,6 +20,9 @@ static void vh_insert_host(unsigned long long *tab, uint32_t v, uint32_t t)
     }
 }
 
+static int force_all_l2 = 0;   // sim_set_force_all_l2(1): run every ED-2 search like the reference (checks that skipping is exact)
+extern "C" void sim_set_force_all_l2(int v) { force_all_l2 = v; }
+
 static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, const uint8_t *slice, int len, int anc,
                      slr_bc_result *out, long long *n_loads)
 {
@@ -39,23 +42,20 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
     memset(&ms, 0, sizeof(ms));
     uint32_t flags = 0;
     const int noff = 2 * plusminus + 1;
+    uint32_t win_p1[SLR_MAX_OFFSETS], win_p2[SLR_MAX_OFFSETS];
+    bool win_dead[SLR_MAX_OFFSETS];
+    // 1. windows
     for (int k = 0; k < noff; k++) {
-        uint32_t w, p1, p2;
-        bool dead_window;
-        if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window)) { flags |= SLR_F_EXCEPTION; break; }
-        ms.m_w[k] = w;
-        if (dead_window) continue;
+        uint32_t w = 0, p1 = 0, p2 = 0;
+        bool dead_window = false;
+        if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window)) flags |= SLR_F_EXCEPTION;
+        ms.m_w[k] = w; win_p1[k] = p1; win_p2[k] = p2; win_dead[k] = dead_window;
+    }
+    // 2. levels 0 and 1 of every window
+    for (int k = 0; k < noff && !(flags & SLR_F_EXCEPTION); k++) {
+        if (win_dead[k]) continue;
+        const uint32_t w = ms.m_w[k], p1 = win_p1[k];
         const SlrExpand e = slr_root_expand(w, p1, ed_max >= 2);
-        if (ed_max >= 2) {
-            for (int i = 0; i < SLR_VH_SIZE; i++) vh[i] = SLR_VH_EMPTY;
-            for (int sl = 0; sl < 144; sl++) {
-                const int p = sl / 9, j = 8 - (sl - p * 9);
-                bool v, d;
-                const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
-                if (v) vh_insert_host(vh, mval, (uint32_t)(p * 16 + (8 - j)));
-            }
-        }
-        // lane 0's bucket (table 0, rest of w) answers the ED-0 probe
         uint32_t valid_levels = 0;
         uint32_t rmin = SLR_NONE32, bc1 = 0;
         for (int lane = 0; lane < (ed_max >= 1 ? 12 : 1); lane++) {
@@ -72,41 +72,55 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
         }
         if (valid_levels) { ms.m_bc[k][0] = w; ms.m_cnt[k][0] = 0; }
         if (rmin != SLR_NONE32) { valid_levels |= 2u; ms.m_bc[k][1] = bc1; ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
-        if (ed_max >= 2) {
-            int nlive = 0;
-            for (int sl = 0; sl < 144; sl++) {
-                const int p = sl / 9, j = 8 - (sl - p * 9);
-                bool v, d;
-                const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
-                if (v && !d && !slr_is_visited(e, vh, mval, p)) {
-                    node_cs[nlive] = mval;
-                    node_meta[nlive++] = slr_node_meta(p, j, p1, p2);
-                }
-            }
-            const int nprobe = nlive * 12;
-            uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
-            for (int base = 0; base < nprobe; base += 32) {
-                for (int lane = 0; lane < 32; lane++) {
-                    const int pi = base + lane;
-                    if (pi >= nprobe) break;
-                    const int nd = pi / 12, rem = pi - nd * 12;
-                    const int g = (rem * 11) >> 5, op = rem - 3 * g;
-                    const SlrExpand e2 = slr_node_expand(node_cs[nd], node_meta[nd], w);
-                    uint32_t b = 0;
-                    uint32_t r2 = slr_expand_group(tab, e2, vh, g, op, b);
-                    (*n_loads)++;
-                    if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
-                    if (r2 < best) { best = r2; bcb = b; cntb = node_meta[nd] >> 10; }
-                }
-                if (best != SLR_NONE32 && (int)(best >> 8) * 12 + 12 <= base + 32) break;
-            }
-            if (best != SLR_NONE32) {
-                valid_levels |= 4u;
-                ms.m_bc[k][2] = bcb;
-                ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u));
+        ms.m_valid[k] = (uint8_t)valid_levels;
+    }
+    // 3. + 4. the ED-2 searches that can still change the record
+    uint32_t bcA = 0;
+    const int plan = (ed_max >= 2 && !(flags & SLR_F_EXCEPTION)) ? (force_all_l2 ? (int)SLR_L2_ALL : slr_level2_plan(ms, noff, bcA)) : (int)SLR_L2_NONE;
+    for (int k = 0; k < noff && plan != SLR_L2_NONE; k++) {
+        if (win_dead[k]) continue;
+        const uint32_t w = ms.m_w[k], p1 = win_p1[k], p2 = win_p2[k];
+        for (int i = 0; i < SLR_VH_SIZE; i++) vh[i] = SLR_VH_EMPTY;
+        for (int sl = 0; sl < 144; sl++) {
+            const int p = sl / 9, j = 8 - (sl - p * 9);
+            bool v, d;
+            const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
+            if (v) vh_insert_host(vh, mval, (uint32_t)(p * 16 + (8 - j)));
+        }
+        int nlive = 0;
+        for (int sl = 0; sl < 144; sl++) {
+            const int p = sl / 9, j = 8 - (sl - p * 9);
+            bool v, d;
+            const uint32_t mval = slr_gen_mutant(w, p, j, p1, v, d);
+            const uint32_t tfirst = v ? slr_vh_tmin(vh, mval) : 0u;
+            if (v && !d && !((p >= 1 && mval == w) || (int)(tfirst >> 4) < p)) {
+                node_cs[nlive] = mval;
+                node_meta[nlive++] = slr_node_meta(p, j, p1, p2);
             }
         }
-        ms.m_valid[k] = (uint8_t)valid_levels;
+        const int nprobe = nlive * 12;
+        uint32_t best = SLR_NONE32, bcb = 0, cntb = 0;
+        for (int base = 0; base < nprobe; base += 32) {
+            for (int lane = 0; lane < 32; lane++) {
+                const int pi = base + lane;
+                if (pi >= nprobe) break;
+                const int nd = pi / 12, rem = pi - nd * 12;
+                const int g = (rem * 11) >> 5, op = rem - 3 * g;
+                const SlrExpand e2 = slr_node_expand(node_cs[nd], node_meta[nd], w);
+                uint32_t b = 0;
+                uint32_t r2 = slr_expand_group(tab, e2, vh, g, op, b);
+                (*n_loads)++;
+                if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
+                if (r2 < best) { best = r2; bcb = b; cntb = node_meta[nd] >> 10; }
+            }
+            if (best != SLR_NONE32 && (int)(best >> 8) * 12 + 12 <= base + 32) break;
+        }
+        if (best != SLR_NONE32) {
+            ms.m_valid[k] |= 4u;
+            ms.m_bc[k][2] = bcb;
+            ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u));
+            if (plan == SLR_L2_UNTIL && bcb != bcA) break;
+        }
     }
     slr_bc_result res;
     memset(&res, 0, sizeof(res));
@@ -136,7 +150,7 @@ extern "C" int sim_bc_assign(const uint64_t *keys, const int32_t *rank, int64_t 
         sim_read(tab, ed_max, plusminus, three_prime, slices + i * stride, len, anchor[i], &out[i], &loads);
     }
     if (n_loads) *n_loads = loads;
-    if (stash_sizes) for (int g = 0; g < 4; g++) stash_sizes[g] = (long long)T.st_bucket[g].size();
+    if (stash_sizes) for (int g = 0; g < 4; g++) stash_sizes[g] = T.st_n[g];
     return 0;
 }
 

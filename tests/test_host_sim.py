@@ -88,6 +88,28 @@ def test_sim_synthetic_737k(sim, orc, pkg):
     assert (exp["bc"][ok][hit] == wl[truth[ok][hit]]).mean() > 0.9       # README.md:100,180: ED 2 trades accuracy for yield
 
 
+def test_sim_lazy_level2_is_exact(sim, orc, pkg):
+    """slr_level2_plan skips ED-2 searches that cannot reach the record: same bytes as running all of them (what the
+    reference does), on adversarial inputs (many planted ED <= 1 / ED 2 neighbours, HashSet ties) and on synthetic
+    reads, with fewer bucket loads on the latter."""
+    sim.sim_set_force_all_l2.argtypes = [C.c_int]
+    cases = [workloads.adversarial(4100 + i, tp, 300, skew=bool(i & 1))[1:] for i, tp in enumerate((True, False, True, False))]
+    wl = pkg.synth_whitelist(200000, 9)
+    sl, an, _ = pkg.synth_reads(wl, 3000, seed=3)
+    cases.append((sl, an, wl))
+    for i, (slices, anchors, wl) in enumerate(cases):
+        exp, _ = orc.assign_barcode_batch(orc.BarcodeSet(wl), slices, anchors, 2, 2, i % 2 == 0)
+        try:
+            sim.sim_set_force_all_l2(1)
+            full, _, loads_full, _ = run_sim(sim, orc, wl, None, slices, anchors, 2, 2, i % 2 == 0)
+        finally:
+            sim.sim_set_force_all_l2(0)
+        lazy, _, loads_lazy, _ = run_sim(sim, orc, wl, None, slices, anchors, 2, 2, i % 2 == 0)
+        assert (full == exp).all() and (lazy == exp).all()
+        assert loads_lazy <= loads_full
+    assert loads_lazy * 1.1 < loads_full          # sparse list: fewer early exits than on the 3 M list (there: 2.2x)
+
+
 def test_sim_golden(sim, orc):
     for f in sorted(glob.glob(os.path.join(GOLDEN, "bc_*.npz"))):
         g = np.load(f)
