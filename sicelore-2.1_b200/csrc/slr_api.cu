@@ -58,7 +58,8 @@ struct Slot {
     std::mutex mtx;
     cudaStream_t stream[2] = {nullptr, nullptr};
     DevBuf slices[2], anchor[2], lens[2], out[2];
-    DevBuf umi, joff, ooff, uout;
+    DevBuf umi, joff, ooff, uout, uscr;
+    cudaEvent_t uscr_free = nullptr;           // recorded after the last launch that uses uscr (it may run on a caller's stream)
 };
 
 }  // namespace
@@ -110,6 +111,8 @@ int slr_ctx_create(int device, int n_streams, slr_ctx **out)
             e = cudaStreamCreateWithFlags(&s->stream[k], cudaStreamNonBlocking);
             if (e != cudaSuccess) { delete s; slr_ctx_destroy(c); return fail(SLR_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         }
+        e = cudaEventCreateWithFlags(&s->uscr_free, cudaEventDisableTiming);
+        if (e != cudaSuccess) { delete s; slr_ctx_destroy(c); return fail(SLR_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
         c->slots.push_back(s);
     }
     *out = c;
@@ -125,7 +128,8 @@ void slr_ctx_destroy(slr_ctx *c)
             if (s->stream[k]) { cudaStreamSynchronize(s->stream[k]); cudaStreamDestroy(s->stream[k]); }
             s->slices[k].release(); s->anchor[k].release(); s->lens[k].release(); s->out[k].release();
         }
-        s->umi.release(); s->joff.release(); s->ooff.release(); s->uout.release();
+        s->umi.release(); s->joff.release(); s->ooff.release(); s->uout.release(); s->uscr.release();
+        if (s->uscr_free) cudaEventDestroy(s->uscr_free);
         delete s;
     }
     delete c;
@@ -311,9 +315,15 @@ int slr_umi_dist_dev(slr_ctx *ctx, const uint8_t *d_umis, int stride, int umi_le
     if (n_jobs == 0 || n_reads == 0) return SLR_OK;
     if (!d_umis || !d_job_offsets || !d_out || !d_out_offsets) return fail(SLR_E_INVALID, "slr_umi_dist_dev: NULL buffer");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    // the kernels need a per-read scratch area: take a slot's, ordered behind its previous user with an event
+    Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(s->mtx);
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->uscr_free, 0));
+    if ((rc = s->uscr.reserve(slr_umi_scratch_bytes(n_reads)))) return rc;
     CUDA_TRY(slr_launch_umi_dist(d_umis, stride, umi_len, (const long long *)d_job_offsets, n_jobs, n_reads, d_out,
-                                 (const long long *)d_out_offsets, (cudaStream_t)stream));
-    g_launches++;
+                                 (const long long *)d_out_offsets, s->uscr.p, (cudaStream_t)stream));
+    CUDA_TRY(cudaEventRecord(s->uscr_free, (cudaStream_t)stream));
+    g_launches += SLR_UMI_LAUNCHES;
     return SLR_OK;
 }
 
@@ -353,12 +363,15 @@ int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, con
             if ((rc = s->joff.reserve(joff.size() * 8))) return rc;
             if ((rc = s->ooff.reserve(ooff.size() * 8))) return rc;
             if ((rc = s->uout.reserve((size_t)cells * 4))) return rc;
+            CUDA_TRY(cudaStreamWaitEvent(st, s->uscr_free, 0));
+            if ((rc = s->uscr.reserve(slr_umi_scratch_bytes(nr)))) return rc;
             CUDA_TRY(cudaMemcpyAsync(s->umi.p, umis + r0 * stride, (size_t)nr * stride, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(s->joff.p, joff.data(), joff.size() * 8, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(s->ooff.p, ooff.data(), ooff.size() * 8, cudaMemcpyHostToDevice, st));
             CUDA_TRY(slr_launch_umi_dist((const uint8_t *)s->umi.p, stride, umi_len, (const long long *)s->joff.p, nj_range, nr,
-                                         (int32_t *)s->uout.p, (const long long *)s->ooff.p, st));
-            g_launches++;
+                                         (int32_t *)s->uout.p, (const long long *)s->ooff.p, s->uscr.p, st));
+            CUDA_TRY(cudaEventRecord(s->uscr_free, st));
+            g_launches += SLR_UMI_LAUNCHES;
             // jobs may sit anywhere in the caller's `out`: copy back per contiguous run
             int64_t a = j;
             while (a < j1) {

@@ -9,5 +9,9 @@ cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusmin
                                  int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, long long n,
                                  slr_bc_result *d_out, cudaStream_t stream);
 
+// d_scratch: slr_umi_scratch_bytes(n_reads) bytes of device memory (8-byte aligned) that stay untouched until the launch
+// has finished on `stream`; three kernels are enqueued (SLR_UMI_LAUNCHES)
+constexpr int SLR_UMI_LAUNCHES = 3;
+size_t slr_umi_scratch_bytes(long long n_reads);
 cudaError_t slr_launch_umi_dist(const uint8_t *d_umis, int stride, int umi_len, const long long *d_job_offsets, long long n_jobs,
-                                long long n_reads, int32_t *d_out, const long long *d_out_offsets, cudaStream_t stream);
+                                long long n_reads, int32_t *d_out, const long long *d_out_offsets, void *d_scratch, cudaStream_t stream);

@@ -154,25 +154,42 @@ extern "C" int sim_bc_assign(const uint64_t *keys, const int32_t *rank, int64_t 
     return 0;
 }
 
-// ---- UMI distance: same per-pair code as umi_dist.cu, rows walked sequentially ---------------------------
+// ---- UMI distance: same per-pair code as umi_dist.cu (bit planes of the row read, register-only Myers), pairs walked
+// sequentially ----------------------------------------------------------------------------------------------------
 #include "../../sicelore-2.1_b200/csrc/umi_core.cuh"
+template <int L> static void sim_umi_job(const uint8_t *umis, int stride, long long n, int32_t *mat)
+{
+    for (long long i = 0; i < n; i++) {
+        uint8_t rb[16] = {0};
+        memcpy(rb, umis + i * stride, L + 2);
+        uint32_t rw[4], pl[4];
+        memcpy(rw, rb, 16);
+        slr_umi_planes(rw, pl);
+        const unsigned long long rp = slr_umi_planes_pack(pl);
+        mat[i * n + i] = slr_umi_equality();
+        for (long long v = i + 1; v < n; v++) {
+            uint8_t cb[16] = {0};
+            memcpy(cb, umis + v * stride, L + 2);
+            uint32_t cw[4];
+            memcpy(cw, cb, 16);
+            const int32_t e = slr_umi_best9_planes<L>(rp, cw);
+            mat[i * n + v] = e;
+            mat[v * n + i] = slr_umi_transpose(e);
+        }
+    }
+}
 extern "C" int sim_umi_dist(const uint8_t *umis, int stride, int umi_len, const long long *job_offsets, long long n_jobs, int32_t *out,
                             const long long *out_offsets)
 {
     for (long long j = 0; j < n_jobs; j++) {
         const long long j0 = job_offsets[j], n = job_offsets[j + 1] - j0;
         int32_t *mat = out + out_offsets[j];
-        for (long long i = 0; i < n; i++) {
-            const unsigned long long rowp = slr_umi_pack(umis + (j0 + i) * stride, umi_len + 2);
-            uint32_t peq[48];
-            for (int e = 0; e < 48; e++) peq[e] = slr_umi_peq_entry(rowp, umi_len, e >> 4, (uint32_t)(e & 15));
-            for (long long v = i; v < n; v++) {
-                if (v == i) { mat[i * n + i] = slr_umi_equality(); continue; }
-                const unsigned long long colp = slr_umi_pack(umis + (j0 + v) * stride, umi_len + 2);
-                const int32_t e = slr_umi_best9(peq, umi_len, colp);
-                mat[i * n + v] = e;
-                mat[v * n + i] = slr_umi_transpose(e);
-            }
+        const uint8_t *u = umis + j0 * stride;
+        switch (umi_len) {
+#define C(LL) case LL: sim_umi_job<LL>(u, stride, n, mat); break;
+            C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14)
+#undef C
+        default: return -1;
         }
     }
     return 0;
