@@ -199,10 +199,17 @@ def main():
         if world > 1:
             dist.all_reduce(d_counts)                     # cross-shard merge of the BarcodesAssigned counters (sum, int64)
 
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=2)
+    np_res = h_res.numpy().view(pkg.BC_RESULT).reshape(-1)
+
     def step_e2e():
-        parser.assign_barcodes(h_slices.numpy(), h_anchor.numpy(), out=h_res.numpy().view(pkg.BC_RESULT).reshape(-1))
+        # the two seams are independent calls of two host threads (the reference's worker pools are concurrent too); each
+        # call copies its inputs H2D, runs its kernels and copies its results D2H before it returns
+        f = pool.submit(parser.assign_barcodes, h_slices.numpy(), h_anchor.numpy(), None, np_res)
         if use_umi:
             pkg.generate_distance_matrices(ctx, h_umis.numpy(), h_offs.numpy(), 12, out=h_mat.numpy(), out_offsets=h_oo.numpy())
+        f.result()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -286,9 +293,10 @@ def main():
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                            "kernel": "bc_assign_kernel", "kernel_ms_per_launch": bc_ms, "units_per_launch": R,
                            "algorithmic_bytes_per_read": bytes_per_read,
-                           "note": "algorithmic bytes are the REFERENCE algorithm's (probes x 8 B); the kernel answers the same queries "
-                                   "with ~1.1 k 32-byte L2-resident bucket loads per read and stops each ED-2 search at the first "
-                                   "valid hit, so frac > 1 does not mean HBM saturation (DRAM traffic is ~70 B/read, see DESIGN.md)"}
+                           "note": "algorithmic bytes are the REFERENCE algorithm's (SURVEY.md 8d: hash probes x 8 B + boundary in/out); "
+                                   "the kernel answers the same queries with ~0.5 k 32-byte L2-resident bucket loads per read (one load "
+                                   "tests every mutant of a digit group, ED-2 searches that cannot reach the record are skipped), so "
+                                   "frac > 1 is not HBM saturation: the kernel is issue-bound (ncu: profiles/), see DESIGN.md 4.1"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

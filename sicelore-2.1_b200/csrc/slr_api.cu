@@ -58,8 +58,8 @@ struct Slot {
     std::mutex mtx;
     cudaStream_t stream[2] = {nullptr, nullptr};
     DevBuf slices[2], anchor[2], lens[2], out[2];
-    DevBuf umi, joff, ooff, uout, uscr;
-    cudaEvent_t uscr_free = nullptr;           // recorded after the last launch that uses uscr (it may run on a caller's stream)
+    DevBuf umi[2], joff[2], ooff[2], uout[2], uscr[2];
+    cudaEvent_t uscr_free = nullptr;           // recorded after the last launch that uses uscr[0] on a caller's stream (slr_umi_dist_dev)
 };
 
 }  // namespace
@@ -128,7 +128,7 @@ void slr_ctx_destroy(slr_ctx *c)
             if (s->stream[k]) { cudaStreamSynchronize(s->stream[k]); cudaStreamDestroy(s->stream[k]); }
             s->slices[k].release(); s->anchor[k].release(); s->lens[k].release(); s->out[k].release();
         }
-        s->umi.release(); s->joff.release(); s->ooff.release(); s->uout.release(); s->uscr.release();
+        for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); }
         if (s->uscr_free) cudaEventDestroy(s->uscr_free);
         delete s;
     }
@@ -319,9 +319,9 @@ int slr_umi_dist_dev(slr_ctx *ctx, const uint8_t *d_umis, int stride, int umi_le
     Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
     std::lock_guard<std::mutex> lock(s->mtx);
     CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->uscr_free, 0));
-    if ((rc = s->uscr.reserve(slr_umi_scratch_bytes(n_reads)))) return rc;
+    if ((rc = s->uscr[0].reserve(slr_umi_scratch_bytes(n_reads)))) return rc;
     CUDA_TRY(slr_launch_umi_dist(d_umis, stride, umi_len, (const long long *)d_job_offsets, n_jobs, n_reads, d_out,
-                                 (const long long *)d_out_offsets, s->uscr.p, (cudaStream_t)stream));
+                                 (const long long *)d_out_offsets, s->uscr[0].p, (cudaStream_t)stream));
     CUDA_TRY(cudaEventRecord(s->uscr_free, (cudaStream_t)stream));
     g_launches += SLR_UMI_LAUNCHES;
     return SLR_OK;
@@ -337,61 +337,64 @@ int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, con
     CUDA_TRY(cudaSetDevice(ctx->device));
     Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
     std::lock_guard<std::mutex> lock(s->mtx);
-    cudaStream_t st = s->stream[0];
-    // job ranges of at most ~2^28 output cells per launch (a single larger job still goes in one launch)
-    const int64_t CELL_LIMIT = 1LL << 28;
-    std::vector<long long> joff, ooff;
+    // job ranges of at most ~2^23 output cells (a single larger job still goes in one launch), ping-pong on the slot's two
+    // streams: H2D of range c+1 and D2H of range c-1 overlap the kernels of range c
+    const int64_t CELL_LIMIT = 1LL << 23;
+    std::vector<long long> joff[2], ooff[2];
+    CUDA_TRY(cudaStreamWaitEvent(s->stream[0], s->uscr_free, 0));         // uscr[0] may still serve a slr_umi_dist_dev launch
     int64_t j = 0;
-    while (j < n_jobs) {
+    for (int c = 0; j < n_jobs; c++) {
+        const int b = c & 1;
+        cudaStream_t st = s->stream[b];
+        CUDA_TRY(cudaStreamSynchronize(st));                               // buffers (and host vectors) of this parity are free again
         int64_t j1 = j, cells = 0;
-        joff.clear(); ooff.clear();
+        joff[b].clear(); ooff[b].clear();
         const int64_t r0 = job_offsets[j];
         while (j1 < n_jobs) {
             const int64_t nj = job_offsets[j1 + 1] - job_offsets[j1];
             if (nj < 0) return fail(SLR_E_INVALID, "job_offsets not monotone at %lld", (long long)j1);
             if (j1 > j && cells + nj * nj > CELL_LIMIT) break;
-            joff.push_back(job_offsets[j1] - r0);
-            ooff.push_back(cells);
+            joff[b].push_back(job_offsets[j1] - r0);
+            ooff[b].push_back(cells);
             cells += nj * nj;
             j1++;
         }
-        joff.push_back(job_offsets[j1] - r0);
-        ooff.push_back(cells);
+        joff[b].push_back(job_offsets[j1] - r0);
+        ooff[b].push_back(cells);
         const int64_t nr = job_offsets[j1] - r0, nj_range = j1 - j;
         if (nr > 0) {
-            if ((rc = s->umi.reserve((size_t)nr * stride))) return rc;
-            if ((rc = s->joff.reserve(joff.size() * 8))) return rc;
-            if ((rc = s->ooff.reserve(ooff.size() * 8))) return rc;
-            if ((rc = s->uout.reserve((size_t)cells * 4))) return rc;
-            CUDA_TRY(cudaStreamWaitEvent(st, s->uscr_free, 0));
-            if ((rc = s->uscr.reserve(slr_umi_scratch_bytes(nr)))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(s->umi.p, umis + r0 * stride, (size_t)nr * stride, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(s->joff.p, joff.data(), joff.size() * 8, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(s->ooff.p, ooff.data(), ooff.size() * 8, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(slr_launch_umi_dist((const uint8_t *)s->umi.p, stride, umi_len, (const long long *)s->joff.p, nj_range, nr,
-                                         (int32_t *)s->uout.p, (const long long *)s->ooff.p, s->uscr.p, st));
-            CUDA_TRY(cudaEventRecord(s->uscr_free, st));
+            if ((rc = s->umi[b].reserve((size_t)nr * stride))) return rc;
+            if ((rc = s->joff[b].reserve(joff[b].size() * 8))) return rc;
+            if ((rc = s->ooff[b].reserve(ooff[b].size() * 8))) return rc;
+            if ((rc = s->uout[b].reserve((size_t)cells * 4))) return rc;
+            if ((rc = s->uscr[b].reserve(slr_umi_scratch_bytes(nr)))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s->umi[b].p, umis + r0 * stride, (size_t)nr * stride, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s->joff[b].p, joff[b].data(), joff[b].size() * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s->ooff[b].p, ooff[b].data(), ooff[b].size() * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(slr_launch_umi_dist((const uint8_t *)s->umi[b].p, stride, umi_len, (const long long *)s->joff[b].p, nj_range, nr,
+                                         (int32_t *)s->uout[b].p, (const long long *)s->ooff[b].p, s->uscr[b].p, st));
             g_launches += SLR_UMI_LAUNCHES;
             // jobs may sit anywhere in the caller's `out`: copy back per contiguous run
             int64_t a = j;
             while (a < j1) {
-                int64_t b = a;
-                while (b + 1 < j1) {
-                    const int64_t nb = job_offsets[b + 1] - job_offsets[b];
-                    if (out_offsets[b + 1] != out_offsets[b] + nb * nb) break;
-                    b++;
+                int64_t e = a;
+                while (e + 1 < j1) {
+                    const int64_t ne = job_offsets[e + 1] - job_offsets[e];
+                    if (out_offsets[e + 1] != out_offsets[e] + ne * ne) break;
+                    e++;
                 }
-                const int64_t nb = job_offsets[b + 1] - job_offsets[b];
-                const int64_t ncell = ooff[b - j] + nb * nb - ooff[a - j];
+                const int64_t ne = job_offsets[e + 1] - job_offsets[e];
+                const int64_t ncell = ooff[b][e - j] + ne * ne - ooff[b][a - j];
                 if (ncell > 0)
-                    CUDA_TRY(cudaMemcpyAsync(out + out_offsets[a], (int32_t *)s->uout.p + ooff[a - j], (size_t)ncell * 4,
+                    CUDA_TRY(cudaMemcpyAsync(out + out_offsets[a], (int32_t *)s->uout[b].p + ooff[b][a - j], (size_t)ncell * 4,
                                              cudaMemcpyDeviceToHost, st));
-                a = b + 1;
+                a = e + 1;
             }
-            CUDA_TRY(cudaStreamSynchronize(st));
         }
         j = j1;
     }
+    CUDA_TRY(cudaStreamSynchronize(s->stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(s->stream[1]));
     return SLR_OK;
 }
 
