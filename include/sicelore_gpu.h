@@ -108,6 +108,30 @@ int  slr_bc_counts_read(slr_ctx *ctx, const slr_bc_table *t, int64_t *counts_out
 int  slr_bc_counts_reset(slr_ctx *ctx, slr_bc_table *t);
 int  slr_bc_counts_device(const slr_bc_table *t, int64_t **d_counts, int64_t *n_elems);
 
+/* ---- S3: pass-1 collision test of the used-barcode list ------------------------------------------------- */
+
+/* Matches of one BarcodeMatchTester run of the collision tester: at most one OneMatch per ED level
+ * (BarcodeMatchTester$Matches is a HashSet whose equals() is (readSeq, ED, offset), BarcodeMatchTester.java:L433-L436). */
+typedef struct {
+    uint64_t bc[2];      /* OneMatch.matchingBC of the ED-1 / ED-2 entry */
+    uint8_t  valid;      /* bit 0: ED-1 entry present, bit 1: ED-2 entry present */
+    uint8_t  n_sub[2], n_ins[2], n_del[2];   /* OneMatch counters as the Java names them */
+    uint8_t  pad;
+} slr_collide_result;    /* 24 bytes */
+
+/* Replaces the BarcodeDatasetColissionTester.submitSeq loop (F!com/rw/nanoporereadscanner/analyzers/
+ * BarcodeDatasetColissionTester.class, BarcodeDatasetColissionTester.java:L212-L229): for every barcode of the
+ * used-barcode list one BarcodeMatchTester(seq, editDistance, skipFullMatches=true, allowIndels=true,
+ * searchSet = the list's keySet(), offset 0, cell_bc_length, postSeq=null, doNextLevelIfMatchFound=false).call()
+ * (L215-L222), whose Matches feed getUnfilteredColissionData / generateColissionMergedBCmap (L126-L203, host Java).
+ *   t          the search set = barcodes_b4filtering.keySet()  (slr_bc_table_create of the same list)
+ *   ed_max     mergeBCsED (config.xml:25; null = --bcEditDistance): 0, 1 or 2
+ *   barcodes   n queries (2-bit longs), normally the list itself; out: n records, positional */
+int  slr_bc_collide(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint64_t *barcodes, int64_t n,
+                    slr_collide_result *out);
+int  slr_bc_collide_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint64_t *d_barcodes, int64_t n,
+                        slr_collide_result *d_out, void *stream);
+
 /* ---- S2: UMI distance matrices ---------------------------------------------------------------------- */
 
 /* Replaces ClusteringEditDistanceBase.generateDistanceMatrix (F!com/rw/clustering/ClusteringEditDistanceBase.class,

@@ -14,6 +14,10 @@ BC_RESULT = np.dtype([("bc", "<u8"), ("ed", "<i4"), ("ed_second", "<i4"), ("offs
                       ("n_del", "i1"), ("n_sub", "i1"), ("rank", "<i4"), ("flags", "<u4")], align=True)
 assert BC_RESULT.itemsize == 24 or BC_RESULT.itemsize == 32
 
+COLLIDE_RESULT = np.dtype([("bc", "<u8", (2,)), ("valid", "u1"), ("n_sub", "u1", (2,)), ("n_ins", "u1", (2,)), ("n_del", "u1", (2,)),
+                           ("pad", "u1")], align=True)
+assert COLLIDE_RESULT.itemsize == 24
+
 F_ASSIGNED, F_EXCEPTION, F_TIE_UNPIN = 1, 2, 4
 INT_MAX = 2147483647
 
@@ -59,6 +63,7 @@ def lib():
         L.orc_assign_barcode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                                C.POINTER(C.c_int64), C.c_int]
+        L.orc_collide_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_int]
         L.orc_limited_compare.restype = C.c_int
         L.orc_limited_compare.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int]
         L.orc_umi_best9.restype = C.c_int32
@@ -121,6 +126,15 @@ def assign_barcode_batch(bset, slices, anchor, ed_max, plusminus=2, three_prime=
     lib().orc_assign_barcode_batch(bset.h, None if bset.rank is None else bset.rank.ctypes.data, ed_max, plusminus,
                                    int(three_prime), bc_len, slices.ctypes.data, stride, slice_len, anchor.ctypes.data,
                                    n, out.ctypes.data, C.byref(probes), n_threads)
+    return out, probes.value
+
+
+def collide_batch(bset, queries, ed, bc_len=16, n_threads=0):
+    """BarcodeDatasetColissionTester: Matches of every query barcode against bset.  Returns (COLLIDE_RESULT[n], probes)."""
+    q = np.ascontiguousarray(queries, dtype=np.uint64)
+    out = np.zeros(len(q), dtype=COLLIDE_RESULT)
+    probes = C.c_int64(0)
+    lib().orc_collide_batch(bset.h, ed, bc_len, q.ctypes.data, len(q), out.ctypes.data, C.byref(probes), n_threads)
     return out, probes.value
 
 

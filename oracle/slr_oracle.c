@@ -550,6 +550,39 @@ void orc_assign_barcode_batch(const orc_set *set, const int32_t *rank, int ed_ma
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * BarcodeDatasetColissionTester.submitSeq (F!com/rw/nanoporereadscanner/analyzers/BarcodeDatasetColissionTester.class,
+ * BarcodeDatasetColissionTester.java:L212-L229): every used barcode is run through the same engine against the used
+ * list itself with skipFullMatches = true, allowIndels = true, offset 0, postSeq = null, doNext = false (L215-L222).
+ * Matches keeps the first hit of every ED level (HashSet.equals on (readSeq, ED, offset)).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_collide_batch(const orc_set *set, int ed, int bc_len, const uint64_t *queries, int64_t n, orc_collide_result *out,
+                       int64_t *n_probes_total, int n_threads)
+{
+    int64_t total = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : total)
+#endif
+    for (int64_t i = 0; i < n; i++) {
+        orc_match m[ORC_MAX_ED + 2];
+        int64_t probes = 0;
+        orc_collide_result r;
+        memset(&r, 0, sizeof(r));
+        int k = orc_match_tester(set, queries[i], bc_len, ed, 1, 1, NULL, -1, 0, 0, m, &probes);
+        for (int a = 0; a < k; a++) {
+            if (m[a].ed < 1 || m[a].ed > 2) continue;
+            int lv = m[a].ed - 1;
+            r.valid |= (uint8_t)(1u << lv);
+            r.bc[lv] = m[a].bc;
+            r.n_sub[lv] = (uint8_t)m[a].n_sub; r.n_ins[lv] = (uint8_t)m[a].n_ins; r.n_del[lv] = (uint8_t)m[a].n_del;
+        }
+        out[i] = r;
+        total += probes;
+    }
+    if (n_probes_total) *n_probes_total += total;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * UMI pair distance
  * ---------------------------------------------------------------------------------------------- */
 

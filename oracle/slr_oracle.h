@@ -80,6 +80,19 @@ void orc_assign_barcode_batch(const orc_set *set, const int32_t *rank, int ed_ma
                               int bc_len, const uint8_t *slices, int stride, int slice_len, const int32_t *anchor,
                               int64_t n, orc_bc_result *out, int64_t *n_probes_total, int n_threads);
 
+/* ---------- pass-1 collision tester (F!...BarcodeDatasetColissionTester.java:L212-L229) ---------- */
+typedef struct {
+    uint64_t bc[2];         /* matchingBC of the ED-1 / ED-2 OneMatch */
+    uint8_t  valid;         /* bit 0: ED-1 entry, bit 1: ED-2 entry */
+    uint8_t  n_sub[2], n_ins[2], n_del[2];
+    uint8_t  pad;
+} orc_collide_result;       /* 24 bytes, same layout as slr_collide_result */
+
+/* one BarcodeMatchTester(seq, ed, skipFullMatches=true, allowIndels=true, set, offset 0, len, postSeq=null,
+ * doNextLevelIfMatchFound=false).call() per query (L215-L222); OpenMP over queries */
+void orc_collide_batch(const orc_set *set, int ed, int bc_len, const uint64_t *queries, int64_t n, orc_collide_result *out,
+                       int64_t *n_probes_total, int n_threads);
+
 /* ---------- UMI distances (F!com/rw/clustering/ClusteringEditDistanceBase.java:L297-L350) ------ */
 int     orc_limited_compare(const uint8_t *left, int n, const uint8_t *right, int m, int threshold); /* apachemod/LevenshteinDistance.java:L220-L283 */
 int32_t orc_umi_best9(const uint8_t *a, const uint8_t *b, int umi_len);    /* a,b: umi_len+2 4-bit codes (window -1..+1) */

@@ -32,10 +32,13 @@ INT_MAX = 2147483647
 BC_RESULT = np.dtype([("bc", "<u8"), ("ed", "<i4"), ("ed_second", "<i4"), ("offset", "i1"), ("n_ins", "i1"),
                       ("n_del", "i1"), ("n_sub", "i1"), ("rank", "<i4"), ("flags", "<u4")], align=True)
 assert BC_RESULT.itemsize == 32
+COLLIDE_RESULT = np.dtype([("bc", "<u8", (2,)), ("valid", "u1"), ("n_sub", "u1", (2,)), ("n_ins", "u1", (2,)), ("n_del", "u1", (2,)),
+                           ("pad", "u1")], align=True)
+assert COLLIDE_RESULT.itemsize == 24
 
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
-           "slr_bc_counts_device", "slr_umi_dist", "slr_umi_dist_dev", "slr_last_error", "slr_abi_version",
+           "slr_bc_counts_device", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_last_error", "slr_abi_version",
            "slr_launch_count"]
 
 
@@ -63,7 +66,7 @@ def build(force=False, verbose=False):
     """Compile libsicelore_gpu.so (nvcc, sm_100a only) and libslr_synth.so (g++) in-tree."""
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
-    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "umi_dist.cu")]
+    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -104,6 +107,8 @@ def gpu_lib():
         L.slr_bc_counts_read.argtypes = [vp, vp, vp]
         L.slr_bc_counts_reset.argtypes = [vp, vp]
         L.slr_bc_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+        L.slr_bc_collide.argtypes = [vp, vp, i32, vp, i64, vp]
+        L.slr_bc_collide_dev.argtypes = [vp, vp, i32, vp, i64, vp, vp]
         L.slr_umi_dist.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
         L.slr_umi_dist_dev.argtypes = [vp, vp, i32, i32, vp, i64, i64, vp, vp, i64, vp]
         L.slr_last_error.restype = C.c_char_p
@@ -321,6 +326,22 @@ class Parser:
             start = adapterpos + 1 + off
             end = start + (bc_len - 1) + d
         return start, end
+
+
+class BarcodeDatasetColissionTester:
+    """Mirror of the pass-1 collision tester for the part that moved to the GPU: one BarcodeMatchTester run per used barcode
+    against the list itself (BarcodeDatasetColissionTester.submitSeq, BarcodeDatasetColissionTester.java:L212-L229)."""
+
+    def __init__(self, ctx, barcodes_b4filtering, editDistance):
+        self.ctx, self.map, self.ed = ctx, barcodes_b4filtering, int(editDistance)
+
+    def colissionsFromScan(self, barcodes=None, out=None):
+        """Matches per barcode as a COLLIDE_RESULT array (default: every key of the map, in key order of the input)."""
+        q = np.ascontiguousarray(self.map.keys if barcodes is None else barcodes, dtype=np.uint64)
+        if out is None:
+            out = np.empty(len(q), dtype=COLLIDE_RESULT)
+        _check(gpu_lib().slr_bc_collide(self.ctx.h, self.map.h, self.ed, q.ctypes.data, len(q), out.ctypes.data))
+        return out
 
 
 def read_name_suffix(res_i, bc_start, bc_end):

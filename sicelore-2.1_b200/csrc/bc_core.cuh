@@ -58,6 +58,13 @@ SLR_HD uint32_t slr_gen_mutant(uint32_t w, int p, int j, uint32_t cbase, bool &v
     return is_sub ? sub : (j < 8 ? ins : del);
 }
 
+// postSeq == null variant (BarcodeDatasetColissionTester): 12 creations per position, j = 8 + b is the deletion that
+// appends base b (deleteByte with code 0, then | 1, 2, 3: BarcodeMatchTester.java:L330-L340)
+SLR_HD uint32_t slr_gen_mutant12(uint32_t w, int p, int j, bool &valid, bool &dead)
+{
+    return slr_gen_mutant(w, p, j < 8 ? j : 8, j < 8 ? 0u : (uint32_t)(j - 8), valid, dead);
+}
+
 // Context of one node expansion (= all positions of one LongSeqMutated popped from the deque)
 struct SlrExpand {
     uint32_t cs;        // node sequence
@@ -67,6 +74,8 @@ struct SlrExpand {
     uint32_t tproc;     // processing time of this node (level 2 only)
     int level;          // 1 = root expansion (hits are ED 1), 2 = level-1 node expansion (hits are ED 2)
     bool use_visited;   // ed >= 2 (NucTwoBitPerBaseEDtesterBase.java:L82-L95)
+    bool nopost;        // postSeq == null (pass-1 collision tester): a deletion appends all four bases (L336-L340), creation
+                        // index 8 + base; cbase then names the appended base of THIS probe (digit groups 0-2)
 };
 
 // Would the reference have skipped mutant s, created at position q of this node, as "already tested"?
@@ -113,7 +122,7 @@ SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *
     const int hi = (slr_clz(xh) - 26) >> 1;                    // common leading digits, 0..3
     int xx = 3 - ((slr_ffs(xl | 0x40u) - 1) >> 1);             // 3 - common trailing digits
     const uint32_t n0 = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;   // digit that follows the group after a deletion
-    const bool indel_ok = xx <= hi && (op == 1 || (P & 3u) == n0);
+    const bool indel_ok = xx <= hi && (op == 1 || (P & 3u) == n0 || (e.nopost && g == 3));
     if (!(op == 0 ? sub_ok : indel_ok)) return SLR_NONE32;
 
     int q;
@@ -133,7 +142,7 @@ SLR_HD uint32_t slr_check_pattern(const SlrExpand &e, const unsigned long long *
             break;
         }
         if (q < 0) return SLR_NONE32;
-        idx = (op == 1) ? 4u + ((P >> (2 * (3 - xx))) & 3u) : 8u;
+        idx = (op == 1) ? 4u + ((P >> (2 * (3 - xx))) & 3u) : (e.nopost ? 8u + (g == 3 ? (P & 3u) : e.cbase) : 8u);
     }
     const uint32_t s = slr_key_join(rest, P, g);
     if (slr_is_visited(e, vh, s, q)) return SLR_NONE32;
@@ -169,7 +178,7 @@ SLR_COLD unsigned long long slr_probe_stash(const uint32_t *st_bucket, const uin
 {
     SlrExpand e;
     e.cs = cs; e.w = w; e.pskip = (int)(epack & 31u) - 1; e.cbase = (epack >> 5) & 3u; e.tproc = (epack >> 8) & 0xFFu;
-    e.level = (int)((epack >> 16) & 3u); e.use_visited = (epack >> 18) & 1u;
+    e.level = (int)((epack >> 16) & 3u); e.use_visited = (epack >> 18) & 1u; e.nopost = (epack >> 19) & 1u;
     const int g = (int)(gop >> 2), op = (int)(gop & 3u);
     const uint32_t want_hi = 0x80u | tag, gb = ((uint32_t)g << 24) | bucket;
     for (int i = slr_stash_lower(st_bucket, st_total, gb); i < st_total && slr_ldg(st_bucket + i) == gb; i++) {
@@ -192,9 +201,10 @@ SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const u
     // node's 2,3 and digit 3 = the digit that follows the group).  1/8 (DEL 1/32) of the unrelated slots survive.
     const uint32_t csg0 = (e.cs >> (24 - 8 * g)) & 0xFFu;
     const uint32_t nx = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;
-    const uint32_t mA = (op == 2) ? 0xF3u : 0xF0u, vA = (csg0 & 0xF0u) | ((op == 2) ? nx : 0u);
-    const uint32_t mB = (op == 2) ? 0x3Fu : 0x0Fu;
-    const uint32_t vB = (op == 0) ? (csg0 & 0x0Fu) : ((op == 1) ? ((csg0 >> 2) & 0x0Fu) : (((csg0 & 0x0Fu) << 2) | nx));
+    const bool fix3 = op == 2 && !(e.nopost && g == 3);          // a deletion pins digit 3 (unless every appended base is tried)
+    const uint32_t mA = fix3 ? 0xF3u : 0xF0u, vA = (csg0 & 0xF0u) | (fix3 ? nx : 0u);
+    const uint32_t mB = (op == 2) ? (fix3 ? 0x3Fu : 0x3Cu) : 0x0Fu;
+    const uint32_t vB = (op == 0) ? (csg0 & 0x0Fu) : ((op == 1) ? ((csg0 >> 2) & 0x0Fu) : (((csg0 & 0x0Fu) << 2) | (fix3 ? nx : 0u)));
     const uint32_t mA4 = mA * 0x01010101u, vA4 = vA * 0x01010101u, mB4 = mB * 0x01010101u, vB4 = vB * 0x01010101u;
     const uint32_t want = (0x80u | pr.tag) * 0x01010101u;
     uint32_t match = ((slr_eq_bytes(k.a.x, want) & (slr_eq_bytes(k.b.x & mA4, vA4) | slr_eq_bytes(k.b.x & mB4, vB4))) >> 7) |
@@ -212,7 +222,7 @@ SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const u
     }
     if (t.st_total > 0 && slr_bucket_full(k)) {                // overflowed bucket: rare, kept out of line
         const uint32_t epack = (uint32_t)(e.pskip + 1) | (e.cbase << 5) | (e.tproc << 8) | ((uint32_t)e.level << 16) |
-                               ((e.use_visited ? 1u : 0u) << 18);
+                               ((e.use_visited ? 1u : 0u) << 18) | ((e.nopost ? 1u : 0u) << 19);
         const unsigned long long r = slr_probe_stash(t.st_bucket, t.st_slot, t.st_total, vh, e.cs, e.w, epack, (uint32_t)(g * 4 + op),
                                                      pr.rest, pr.bucket, pr.tag, best, bc_out);
         best = (uint32_t)(r >> 32);
@@ -245,13 +255,13 @@ SLR_HD uint32_t slr_node_meta(int p, int j, uint32_t p1, uint32_t p2)
 SLR_HD SlrExpand slr_root_expand(uint32_t w, uint32_t p1, bool use_visited)
 {
     SlrExpand e;
-    e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.level = 1; e.use_visited = use_visited;
+    e.cs = w; e.w = w; e.pskip = -1; e.cbase = p1; e.tproc = 0; e.level = 1; e.use_visited = use_visited; e.nopost = false;
     return e;
 }
 SLR_HD SlrExpand slr_node_expand(uint32_t cs, uint32_t meta, uint32_t w)
 {
     SlrExpand e;
-    e.cs = cs; e.w = w; e.pskip = (int)((meta >> 4) & 15u); e.cbase = (meta >> 8) & 3u; e.tproc = meta & 0xFFu; e.level = 2; e.use_visited = true;
+    e.cs = cs; e.w = w; e.pskip = (int)((meta >> 4) & 15u); e.cbase = (meta >> 8) & 3u; e.tproc = meta & 0xFFu; e.level = 2; e.use_visited = true; e.nopost = false;
     return e;
 }
 

@@ -297,6 +297,44 @@ int slr_bc_counts_device(const slr_bc_table *t, int64_t **d_counts, int64_t *n_e
 }
 
 // ---------------------------------------------------------------------------------------------------------
+int slr_bc_collide_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint64_t *d_barcodes, int64_t n, slr_collide_result *d_out,
+                       void *stream)
+{
+    if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_collide: ctx / table is NULL");
+    if (ed_max < 0 || n < 0) return fail(SLR_E_INVALID, "slr_bc_collide: mergeBCsED %d / n %lld invalid", ed_max, (long long)n);
+    if (ed_max > 2) return fail(SLR_E_UNSUPPORTED, "mergeBCsED %d not supported by the GPU path (0, 1 or 2)", ed_max);
+    if (n == 0) return SLR_OK;
+    if (!d_barcodes || !d_out) return fail(SLR_E_INVALID, "slr_bc_collide_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(slr_launch_bc_collide(t->dev, ed_max, (const unsigned long long *)d_barcodes, n, d_out, (cudaStream_t)stream));
+    g_launches++;
+    return SLR_OK;
+}
+
+int slr_bc_collide(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint64_t *barcodes, int64_t n, slr_collide_result *out)
+{
+    if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_collide: ctx / table is NULL");
+    if (n > 0 && (!barcodes || !out)) return fail(SLR_E_INVALID, "slr_bc_collide: NULL buffer");
+    if (ed_max < 0 || n < 0) return fail(SLR_E_INVALID, "slr_bc_collide: mergeBCsED %d / n %lld invalid", ed_max, (long long)n);
+    if (ed_max > 2) return fail(SLR_E_UNSUPPORTED, "mergeBCsED %d not supported by the GPU path (0, 1 or 2)", ed_max);
+    if (n == 0) return SLR_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(s->mtx);
+    cudaStream_t st = s->stream[0];
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int rc;
+    if ((rc = s->slices[0].reserve((size_t)n * 8))) return rc;             // the slot's staging buffers double as query / result space
+    if ((rc = s->out[0].reserve((size_t)n * sizeof(slr_collide_result)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->slices[0].p, barcodes, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(slr_launch_bc_collide(t->dev, ed_max, (const unsigned long long *)s->slices[0].p, n, (slr_collide_result *)s->out[0].p, st));
+    g_launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, s->out[0].p, (size_t)n * sizeof(slr_collide_result), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SLR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 static int check_umi_args(const slr_ctx *ctx, int stride, int umi_len, int64_t n_jobs)
 {
     if (!ctx) return fail(SLR_E_INVALID, "slr_umi_dist: ctx is NULL");

@@ -15,3 +15,6 @@ constexpr int SLR_UMI_LAUNCHES = 3;
 size_t slr_umi_scratch_bytes(long long n_reads);
 cudaError_t slr_launch_umi_dist(const uint8_t *d_umis, int stride, int umi_len, const long long *d_job_offsets, long long n_jobs,
                                 long long n_reads, int32_t *d_out, const long long *d_out_offsets, void *d_scratch, cudaStream_t stream);
+
+cudaError_t slr_launch_bc_collide(const SlrTableDev &tab, int ed_max, const unsigned long long *d_queries, long long n,
+                                  slr_collide_result *d_out, cudaStream_t stream);

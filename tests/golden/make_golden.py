@@ -28,6 +28,11 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), slices=slices, anchor=anchors, whitelist=wl, rank=rank,
                             ed=np.int32(ed), three_prime=np.int32(tp), result=res, probes=np.int64(probes))
         print(name, len(wl), int((res["flags"] & 1).sum()), probes)
+    for name, seed, ed, skew in [("collide_ed1", 301, 1, False), ("collide_ed2", 302, 2, False), ("collide_ed2_skew", 303, 2, True)]:
+        wl = workloads.used_list(seed, 150, skew)
+        res, probes = orc.collide_batch(orc.BarcodeSet(wl), wl, ed)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), whitelist=wl, ed=np.int32(ed), result=res, probes=np.int64(probes))
+        print(name, len(wl), int((res["valid"] & 1).sum()), int(((res["valid"] >> 1) & 1).sum()), probes)
     for umi_len in (12, 10):
         umis, offs = workloads.umi_jobs(200 + umi_len, umi_len, n_jobs=30, max_n=24)
         m, oo = orc.umi_matrix_batch(umis, offs, umi_len)

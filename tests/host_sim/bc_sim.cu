@@ -154,6 +154,84 @@ extern "C" int sim_bc_assign(const uint64_t *keys, const int32_t *rank, int64_t 
     return 0;
 }
 
+// ---- pass-1 collision tester: the orchestration of bc_collide.cu, lane by lane -----------------------------------
+extern "C" int sim_bc_collide(const uint64_t *keys, int64_t n_keys, int force_bbits, int ed_max, const uint64_t *queries, int64_t n,
+                              slr_collide_result *out, long long *n_loads)
+{
+    SlrTableHost T;
+    slr_build_table(keys, nullptr, n_keys, T, force_bbits);
+    SlrTableDev tab = slr_table_host_view(T, nullptr);
+    static thread_local unsigned long long vh[SLR_VH_SIZE];
+    long long loads = 0;
+    for (int64_t qi = 0; qi < n; qi++) {
+        slr_collide_result res;
+        memset(&res, 0, sizeof(res));
+        uint32_t best1 = SLR_NONE32, bc1 = 0, best2 = SLR_NONE32, bc2 = 0, cnt2 = 0;
+        if (!(queries[qi] >> 32) && ed_max >= 1) {
+            const uint32_t w = (uint32_t)queries[qi];
+            uint32_t node_cs[192], node_meta[192];
+            int nlive = 0;
+            for (int i = 0; i < SLR_VH_SIZE; i++) vh[i] = SLR_VH_EMPTY;
+            for (int sl = 0; sl < 192; sl++) {                       // processing order; the kernel does 32 slots per round:
+                const int p = sl / 12, jj = sl - p * 12, j = 11 - jj;  // insertions of a round are visible to its own lookups, and a
+                bool v, d;                                           // later slot never has a smaller time, so slot order is equivalent
+                const uint32_t mv = slr_gen_mutant12(w, p, j, v, d);
+                loads += (v && !d && mv != w) ? 1 : 0;
+                const bool member = v && !d && mv != w && slr_contains(tab, mv);
+                const bool pushtype = v && ((j < 4) == member);
+                bool blocked = false;
+                if (ed_max >= 2) {
+                    // the kernel inserts the whole round first: an insertion of a LATER slot of the same round has a larger time
+                    // and the same or a later position, so it cannot block this slot either
+                    if (pushtype) vh_insert_host(vh, mv, (uint32_t)(p * 16 + jj));
+                    const uint32_t t = v ? slr_vh_tmin(vh, mv) : SLR_NONE32;
+                    blocked = (p >= 1 && mv == w) || (t != SLR_NONE32 && (int)(t >> 4) < p);
+                }
+                const bool created = v && !blocked;
+                if (created && member && (uint32_t)(p * 16 + j) < best1) { best1 = (uint32_t)(p * 16 + j); bc1 = mv; }
+                if (ed_max >= 2 && created && pushtype && !d) {
+                    node_cs[nlive] = mv;
+                    node_meta[nlive++] = (uint32_t)(p * 16 + jj) | (slr_cnt_of((uint32_t)j) << 10);
+                }
+            }
+            if (ed_max >= 2) {
+                const int nprobe = nlive * 21;
+                for (int base = 0; base < nprobe; base += 32) {
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int pi = base + lane;
+                        if (pi >= nprobe) break;
+                        const int nd = pi / 21, rem = pi - nd * 21;
+                        const int g = rem < 8 ? (rem >> 1) : (rem < 20 ? ((rem - 8) >> 2) : 3);
+                        const int op = rem < 8 ? (rem & 1) : 2;
+                        SlrExpand e2 = slr_node_expand(node_cs[nd], node_meta[nd], w);
+                        e2.nopost = true;
+                        e2.cbase = (rem >= 8 && rem < 20) ? (uint32_t)((rem - 8) & 3) : 0u;
+                        uint32_t b = 0;
+                        uint32_t r2 = slr_expand_group(tab, e2, vh, g, op, b);
+                        loads++;
+                        if (r2 != SLR_NONE32) r2 |= (uint32_t)nd << 8;
+                        if (r2 < best2) { best2 = r2; bc2 = b; cnt2 = node_meta[nd] >> 10; }
+                    }
+                    if (best2 != SLR_NONE32 && (int)(best2 >> 8) * 21 + 21 <= base + 32) break;
+                }
+            }
+        }
+        if (best1 != SLR_NONE32) {
+            const uint32_t c = slr_cnt_of(best1 & 15u);
+            res.valid |= 1u; res.bc[0] = bc1;
+            res.n_sub[0] = (uint8_t)(c & 3u); res.n_ins[0] = (uint8_t)((c >> 2) & 3u); res.n_del[0] = (uint8_t)((c >> 4) & 3u);
+        }
+        if (best2 != SLR_NONE32) {
+            const uint32_t c = cnt2 + slr_cnt_of(best2 & 15u);
+            res.valid |= 2u; res.bc[1] = bc2;
+            res.n_sub[1] = (uint8_t)(c & 3u); res.n_ins[1] = (uint8_t)((c >> 2) & 3u); res.n_del[1] = (uint8_t)((c >> 4) & 3u);
+        }
+        out[qi] = res;
+    }
+    if (n_loads) *n_loads = loads;
+    return 0;
+}
+
 // ---- UMI distance: same per-pair code as umi_dist.cu (bit planes of the row read, register-only Myers), pairs walked
 // sequentially ----------------------------------------------------------------------------------------------------
 #include "../../sicelore-2.1_b200/csrc/umi_core.cuh"

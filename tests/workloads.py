@@ -96,3 +96,20 @@ def umi_jobs(seed, umi_len=12, n_jobs=60, max_n=40):
     umis[:, :umi_len + 2] = np.array(rows)
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     return umis, offs
+
+
+def used_list(seed, n_cells, skew=False, n_children=6):
+    """A pass-1 style used-barcode list: `n_cells` random barcodes plus 0..n_children-1 variants of each at 1-3 edits
+    (sequencing-error children that the collision tester is there to find); `skew` = homopolymer-rich (duplicate mutants)."""
+    rng = random.Random(seed)
+    alpha = "AAAAACGT" if skew else "ACGT"
+    wl = set()
+    for _ in range(n_cells):
+        s = "".join(rng.choice(alpha) for _ in range(16))
+        wl.add(pyref.pack(s))
+        for _ in range(rng.randrange(0, n_children)):
+            m = (mutate(s, rng.randrange(1, 4), rng) + "".join(rng.choice("ACGT") for _ in range(3)))[:16]
+            wl.add(pyref.pack(m))
+    wl = sorted(wl)
+    rng.shuffle(wl)
+    return np.array(wl, dtype=np.uint64)
