@@ -108,6 +108,19 @@ int  slr_bc_counts_read(slr_ctx *ctx, const slr_bc_table *t, int64_t *counts_out
 int  slr_bc_counts_reset(slr_ctx *ctx, slr_bc_table *t);
 int  slr_bc_counts_device(const slr_bc_table *t, int64_t **d_counts, int64_t *n_elems);
 
+/* ---- pass 1: exact lookup of the offset-0 window (used-barcode counting) ---------------------------------- */
+
+/* Replaces the per-read body of UsedCellBCListGenerator$Worker.call (F!com/rw/nanoporereadscanner/analyzers/
+ * UsedCellBCListGenerator$Worker.class, UsedCellBCListGenerator.java:L206-L232): the window at the predicted position
+ * (3': read[adapterpos-16 .. adapterpos-1] reverse-complemented, 5': read[adapterpos+1 .. adapterpos+16]) is looked up
+ * in the 10x whitelist and counted.  Same buffers as slr_bc_assign (anchor = window start in the slice); no post
+ * sequence is taken, so no flank is needed.  out[i].flags & SLR_F_ASSIGNED = in the list (bc, rank set, ed = 0); the
+ * per-barcode counts (unfilteredUsedBarcodeMap) accumulate in the table's ED-0 counters (slr_bc_counts_read). */
+int  slr_bc_exact(slr_ctx *ctx, const slr_bc_table *t, int three_prime, const uint8_t *slices, int stride, int slice_len,
+                  const int32_t *lens, const int32_t *anchor, int64_t n, slr_bc_result *out);
+int  slr_bc_exact_dev(slr_ctx *ctx, const slr_bc_table *t, int three_prime, const uint8_t *d_slices, int stride, int slice_len,
+                      const int32_t *d_lens, const int32_t *d_anchor, int64_t n, slr_bc_result *d_out, void *stream);
+
 /* ---- S3: pass-1 collision test of the used-barcode list ------------------------------------------------- */
 
 /* Matches of one BarcodeMatchTester run of the collision tester: at most one OneMatch per ED level

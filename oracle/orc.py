@@ -63,6 +63,8 @@ def lib():
         L.orc_assign_barcode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                                C.POINTER(C.c_int64), C.c_int]
+        L.orc_exact_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int64, C.c_void_p]
         L.orc_collide_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_int]
         L.orc_limited_compare.restype = C.c_int
         L.orc_limited_compare.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int]
@@ -127,6 +129,19 @@ def assign_barcode_batch(bset, slices, anchor, ed_max, plusminus=2, three_prime=
                                    int(three_prime), bc_len, slices.ctypes.data, stride, slice_len, anchor.ctypes.data,
                                    n, out.ctypes.data, C.byref(probes), n_threads)
     return out, probes.value
+
+
+def exact_lookup_batch(bset, slices, anchor, three_prime=True, bc_len=16, lens=None):
+    """UsedCellBCListGenerator$Worker: exact lookup of the offset-0 window.  Returns BC_RESULT[n]."""
+    slices = np.ascontiguousarray(slices, dtype=np.uint8)
+    anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+    n, stride = slices.shape
+    out = np.zeros(n, dtype=BC_RESULT)
+    lp = None if lens is None else np.ascontiguousarray(lens, dtype=np.int32)
+    lib().orc_exact_lookup_batch(bset.h, None if bset.rank is None else bset.rank.ctypes.data, int(three_prime), bc_len,
+                                 slices.ctypes.data, stride, min(stride, 32), None if lp is None else lp.ctypes.data,
+                                 anchor.ctypes.data, n, out.ctypes.data)
+    return out
 
 
 def collide_batch(bset, queries, ed, bc_len=16, n_threads=0):

@@ -550,6 +550,33 @@ void orc_assign_barcode_batch(const orc_set *set, const int32_t *rank, int ed_ma
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * UsedCellBCListGenerator$Worker.call, per read (F!com/rw/nanoporereadscanner/analyzers/UsedCellBCListGenerator$Worker.class,
+ * UsedCellBCListGenerator.java:L206-L232): bcStart/bcEnd from the adapter end (L210-L215), bc0 = 2-bit pack of
+ * read.substring(bcStart-1, bcEnd) (L218-L219), reverse complement for 3' (L220-L221), then containsKey on the used map /
+ * the whitelist predicate (L222-L229).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_exact_lookup_batch(const orc_set *set, const int32_t *rank, int three_prime, int bc_len, const uint8_t *slices, int stride,
+                            int slice_len, const int32_t *lens, const int32_t *anchor, int64_t n, orc_bc_result *out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        orc_bc_result *r = &out[i];
+        memset(r, 0, sizeof(*r));
+        r->ed = -1; r->ed_second = INT32_MAX; r->rank = -1;
+        int len = lens ? (lens[i] < slice_len ? lens[i] : slice_len) : slice_len;
+        int ws = anchor[i];
+        if (ws < 0 || ws + bc_len > len) { r->flags |= ORC_F_EXCEPTION; continue; }      /* substring throws */
+        int bad = 0;
+        uint64_t bc = orc_pack2bit(slices + i * (int64_t)stride + ws, bc_len, &bad);
+        if (bad) { r->flags |= ORC_F_EXCEPTION; continue; }                              /* BASE_TO_TWOBIT_ARRAY[c >= 254] */
+        if (three_prime) bc = orc_revcomp2bit(bc, bc_len);
+        int64_t idx = orc_set_find(set, bc);
+        if (idx < 0) continue;
+        r->flags |= ORC_F_ASSIGNED; r->bc = bc; r->ed = 0;
+        r->rank = rank ? rank[idx] : (int32_t)idx;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * BarcodeDatasetColissionTester.submitSeq (F!com/rw/nanoporereadscanner/analyzers/BarcodeDatasetColissionTester.class,
  * BarcodeDatasetColissionTester.java:L212-L229): every used barcode is run through the same engine against the used
  * list itself with skipFullMatches = true, allowIndels = true, offset 0, postSeq = null, doNext = false (L215-L222).

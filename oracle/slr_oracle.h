@@ -80,6 +80,11 @@ void orc_assign_barcode_batch(const orc_set *set, const int32_t *rank, int ed_ma
                               int bc_len, const uint8_t *slices, int stride, int slice_len, const int32_t *anchor,
                               int64_t n, orc_bc_result *out, int64_t *n_probes_total, int n_threads);
 
+/* ---------- pass-1 exact lookup (F!...UsedCellBCListGenerator$Worker, UsedCellBCListGenerator.java:L206-L232) ---------- */
+/* window at the predicted position only, no post sequence; found => flags = ASSIGNED, bc, ed = 0, rank */
+void orc_exact_lookup_batch(const orc_set *set, const int32_t *rank, int three_prime, int bc_len, const uint8_t *slices, int stride,
+                            int slice_len, const int32_t *lens, const int32_t *anchor, int64_t n, orc_bc_result *out);
+
 /* ---------- pass-1 collision tester (F!...BarcodeDatasetColissionTester.java:L212-L229) ---------- */
 typedef struct {
     uint64_t bc[2];         /* matchingBC of the ED-1 / ED-2 OneMatch */

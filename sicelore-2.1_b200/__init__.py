@@ -38,7 +38,7 @@ assert COLLIDE_RESULT.itemsize == 24
 
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
-           "slr_bc_counts_device", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_last_error", "slr_abi_version",
+           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_last_error", "slr_abi_version",
            "slr_launch_count"]
 
 
@@ -107,6 +107,8 @@ def gpu_lib():
         L.slr_bc_counts_read.argtypes = [vp, vp, vp]
         L.slr_bc_counts_reset.argtypes = [vp, vp]
         L.slr_bc_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+        L.slr_bc_exact.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, i64, vp]
+        L.slr_bc_exact_dev.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, i64, vp, vp]
         L.slr_bc_collide.argtypes = [vp, vp, i32, vp, i64, vp]
         L.slr_bc_collide_dev.argtypes = [vp, vp, i32, vp, i64, vp, vp]
         L.slr_umi_dist.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
@@ -326,6 +328,34 @@ class Parser:
             start = adapterpos + 1 + off
             end = start + (bc_len - 1) + d
         return start, end
+
+
+class UsedCellBCListGenerator:
+    """Mirror of the pass-1 used-barcode counting (UsedCellBCListGenerator$Worker.call, UsedCellBCListGenerator.java:L206-L232):
+    exact lookup of the offset-0 window in the 10x whitelist; counts accumulate in the table (unfilteredUsedBarcodeMap)."""
+
+    def __init__(self, ctx, whitelist_table, three_prime=True):
+        self.ctx, self.map, self.three_prime = ctx, whitelist_table, bool(three_prime)
+
+    def addFastqs(self, slices, anchor, lens=None, out=None):
+        slices = np.ascontiguousarray(slices, dtype=np.uint8)
+        anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+        n, stride = slices.shape
+        if out is None:
+            out = np.empty(n, dtype=BC_RESULT)
+        lp = None
+        if lens is not None:
+            lens = np.ascontiguousarray(lens, dtype=np.int32)
+            lp = lens.ctypes.data
+        _check(gpu_lib().slr_bc_exact(self.ctx.h, self.map.h, int(self.three_prime), slices.ctypes.data, stride, min(stride, 32), lp,
+                                      anchor.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def unfilteredUsedBarcodeMap(self):
+        """barcode -> read count for every whitelist barcode seen at least once (key order of the whitelist)"""
+        c = self.map.counts()[:, 0]
+        sel = np.nonzero(c)[0]
+        return self.map.keys[sel], c[sel]
 
 
 class BarcodeDatasetColissionTester:

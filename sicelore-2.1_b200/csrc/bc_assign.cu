@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t vh_insert_first(unsigned long long *tab, uin
 //   5. merge + decision (slr_decide), rank lookup, counter, one 32-byte record.
 template <int EDMAX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EDMAX >= 2 ? SLR_BC_MINB_ED2 : 4)
-bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t *__restrict__ slices, int stride, int slice_len,
+bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post, const uint8_t *__restrict__ slices, int stride, int slice_len,
                  const int32_t *__restrict__ lens, const int32_t *__restrict__ anchor, long long n, slr_bc_result *__restrict__ out)
 {
     __shared__ WarpShared smem[WARPS_PER_BLOCK];
@@ -95,7 +95,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
         {
             uint32_t w = 0, p1 = 0, p2 = 0;
             bool dead_window = false, ok = true;
-            if (lane < noff) ok = slr_window(sb, len, anc, slr_offset_of(lane), three_prime, EDMAX, w, p1, p2, dead_window);
+            if (lane < noff) ok = slr_window(sb, len, anc, slr_offset_of(lane), three_prime, EDMAX, w, p1, p2, dead_window, need_post != 0);
             if (lane < noff) {
                 S.ms.m_w[lane] = w;
                 S.ms.m_valid[lane] = 0;
@@ -250,7 +250,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, const uint8_t 
 }
 
 template <int EDMAX>
-cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, const uint8_t *d_slices, int stride, int slice_len,
+cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, int need_post, const uint8_t *d_slices, int stride, int slice_len,
                      const int32_t *d_lens, const int32_t *d_anchor, long long n, slr_bc_result *d_out, cudaStream_t stream)
 {
     static int resident_ctas[64];                                // per device: #SMs x resident CTAs per SM
@@ -269,22 +269,22 @@ cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, con
     const long long need = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const long long resident = resident_ctas[dev];               // one wave of persistent CTAs: a multiple of the SM count
     const unsigned blocks = (unsigned)(need < resident ? need : resident);
-    bc_assign_kernel<EDMAX><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens,
+    bc_assign_kernel<EDMAX><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens,
                                                                         d_anchor, n, d_out);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, const uint8_t *d_slices,
+cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, int need_post, const uint8_t *d_slices,
                                  int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, long long n,
                                  slr_bc_result *d_out, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
     switch (ed_max) {
-    case 0: return launch_t<0>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
-    case 1: return launch_t<1>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
-    case 2: return launch_t<2>(tab, plusminus, three_prime, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+    case 0: return launch_t<0>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+    case 1: return launch_t<1>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+    case 2: return launch_t<2>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
     default: return cudaErrorInvalidValue;
     }
 }

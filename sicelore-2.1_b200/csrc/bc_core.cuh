@@ -313,13 +313,17 @@ struct SlrSliceBits {
 
 // Window + post bases of offset o.  Returns false if the Java would have thrown (Parser.java:L214-L219).
 // w = OneMatch.readSeq; dead = window can never match (5' window with a non-ACGT char: bits >= 32 set).
+// need_post = false: the pass-1 exact lookup (UsedCellBCListGenerator$Worker, UsedCellBCListGenerator.java:L210-L221) takes
+// the window only, no post sequence.
 SLR_HD bool slr_window(const SlrSliceBits &b, int len, int anc, int o, int three_prime, int ed_max, uint32_t &w, uint32_t &p1,
-                       uint32_t &p2, bool &dead)
+                       uint32_t &p2, bool &dead, bool need_post = true)
 {
     const int ws = anc + o;
     dead = false;
+    p1 = p2 = 0;
     if (ws < 0 || ws + 16 > len) return false;                              // substring(bcStart-1, bcEnd)
-    if (three_prime) {
+    if (!need_post) {
+    } else if (three_prime) {
         if (ws - 4 < 0) return false;                                       // substring(bcStart-5, bcStart)
         if ((b.unknown >> (ws - 4)) & 0x1Fu) return false;                  // reverseComplement(): ONEBYTE_REVERSECOMP_MATRIX[-1]
         // post[1] = comp(read[ws]), post[2] = comp(read[ws-1]); codes other than A,G,C,T append A (BYTE_TO_2BITLONG_ARRAY)

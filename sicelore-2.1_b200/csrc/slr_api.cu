@@ -217,9 +217,9 @@ static int check_bc_args(const slr_ctx *ctx, const slr_bc_table *t, int ed_max, 
     return SLR_OK;
 }
 
-int slr_bc_assign_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, const uint8_t *d_slices,
-                      int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, int64_t n, slr_bc_result *d_out,
-                      void *stream)
+static int bc_assign_dev_impl(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, int need_post,
+                              const uint8_t *d_slices, int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, int64_t n,
+                              slr_bc_result *d_out, void *stream)
 {
     int rc = check_bc_args(ctx, t, ed_max, plusminus, stride, slice_len, n);
     if (rc) return rc;
@@ -228,15 +228,29 @@ int slr_bc_assign_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusm
     CUDA_TRY(cudaSetDevice(ctx->device));
     for (int64_t off = 0; off < n; off += (1LL << 30)) {           // grid.x limit: 2^31-1 blocks of 8 reads
         const int64_t m = (n - off) < (1LL << 30) ? (n - off) : (1LL << 30);
-        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, d_slices + off * stride, stride, slice_len,
+        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, d_slices + off * stride, stride, slice_len,
                                       d_lens ? d_lens + off : nullptr, d_anchor + off, m, d_out + off, (cudaStream_t)stream));
         g_launches++;
     }
     return SLR_OK;
 }
 
-int slr_bc_assign(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, const uint8_t *slices, int stride,
-                  int slice_len, const int32_t *lens, const int32_t *anchor, int64_t n, slr_bc_result *out)
+int slr_bc_assign_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, const uint8_t *d_slices,
+                      int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, int64_t n, slr_bc_result *d_out,
+                      void *stream)
+{
+    return bc_assign_dev_impl(ctx, t, ed_max, plusminus, three_prime, 1, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+}
+
+int slr_bc_exact_dev(slr_ctx *ctx, const slr_bc_table *t, int three_prime, const uint8_t *d_slices, int stride, int slice_len,
+                     const int32_t *d_lens, const int32_t *d_anchor, int64_t n, slr_bc_result *d_out, void *stream)
+{
+    return bc_assign_dev_impl(ctx, t, 0, 0, three_prime, 0, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+}
+
+static int bc_assign_host_impl(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, int need_post,
+                               const uint8_t *slices, int stride, int slice_len, const int32_t *lens, const int32_t *anchor, int64_t n,
+                               slr_bc_result *out)
 {
     int rc = check_bc_args(ctx, t, ed_max, plusminus, stride, slice_len, n);
     if (rc) return rc;
@@ -259,7 +273,7 @@ int slr_bc_assign(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus
         CUDA_TRY(cudaMemcpyAsync(s->slices[b].p, slices + off * stride, (size_t)m * stride, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(s->anchor[b].p, anchor + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
         if (lens) CUDA_TRY(cudaMemcpyAsync(s->lens[b].p, lens + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, (const uint8_t *)s->slices[b].p, stride, slice_len,
+        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, (const uint8_t *)s->slices[b].p, stride, slice_len,
                                       lens ? (const int32_t *)s->lens[b].p : nullptr, (const int32_t *)s->anchor[b].p, m,
                                       (slr_bc_result *)s->out[b].p, st));
         g_launches++;
@@ -268,6 +282,18 @@ int slr_bc_assign(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus
     CUDA_TRY(cudaStreamSynchronize(s->stream[0]));
     CUDA_TRY(cudaStreamSynchronize(s->stream[1]));
     return SLR_OK;
+}
+
+int slr_bc_assign(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int three_prime, const uint8_t *slices, int stride,
+                  int slice_len, const int32_t *lens, const int32_t *anchor, int64_t n, slr_bc_result *out)
+{
+    return bc_assign_host_impl(ctx, t, ed_max, plusminus, three_prime, 1, slices, stride, slice_len, lens, anchor, n, out);
+}
+
+int slr_bc_exact(slr_ctx *ctx, const slr_bc_table *t, int three_prime, const uint8_t *slices, int stride, int slice_len,
+                 const int32_t *lens, const int32_t *anchor, int64_t n, slr_bc_result *out)
+{
+    return bc_assign_host_impl(ctx, t, 0, 0, three_prime, 0, slices, stride, slice_len, lens, anchor, n, out);
 }
 
 int slr_bc_counts_read(slr_ctx *ctx, const slr_bc_table *t, int64_t *counts_out)

@@ -5,7 +5,8 @@
 #include "slr_table.cuh"
 #include "../../include/sicelore_gpu.h"
 
-cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, const uint8_t *d_slices,
+// need_post = 0: exact lookup of the window only (pass-1 used-barcode counting), no post sequence is taken
+cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, int need_post, const uint8_t *d_slices,
                                  int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, long long n,
                                  slr_bc_result *d_out, cudaStream_t stream);
 

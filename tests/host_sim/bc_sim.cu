@@ -20,6 +20,8 @@ static void vh_insert_host(unsigned long long *tab, uint32_t v, uint32_t t)
     }
 }
 
+static int sim_need_post = 1;  // sim_set_need_post(0): the pass-1 exact lookup (window only)
+extern "C" void sim_set_need_post(int v) { sim_need_post = v; }
 static int force_all_l2 = 0;   // sim_set_force_all_l2(1): run every ED-2 search like the reference (checks that skipping is exact)
 extern "C" void sim_set_force_all_l2(int v) { force_all_l2 = v; }
 
@@ -48,7 +50,7 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
     for (int k = 0; k < noff; k++) {
         uint32_t w = 0, p1 = 0, p2 = 0;
         bool dead_window = false;
-        if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window)) flags |= SLR_F_EXCEPTION;
+        if (!slr_window(sb, len, anc, slr_offset_of(k), three_prime, ed_max, w, p1, p2, dead_window, sim_need_post != 0)) flags |= SLR_F_EXCEPTION;
         ms.m_w[k] = w; win_p1[k] = p1; win_p2[k] = p2; win_dead[k] = dead_window;
     }
     // 2. levels 0 and 1 of every window

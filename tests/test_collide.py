@@ -111,6 +111,69 @@ def test_golden(sim, orc):
         assert (got == g["result"]).all(), f
 
 
+# ---- pass-1 exact lookup (UsedCellBCListGenerator$Worker, UsedCellBCListGenerator.java:L206-L232) -------------------
+def exact_case(seed, three_prime):
+    """adversarial slices whose offset-0 windows are partly planted in the list; anchors near both slice ends (no flank)"""
+    _, slices, anchors, wl = workloads.adversarial(seed, three_prime, 400, nrand=100)
+    rng = np.random.default_rng(seed)
+    anchors = rng.integers(-1, 18, size=len(slices)).astype(np.int32)
+    keys = set(int(x) for x in wl)
+    for i in range(0, len(slices), 2):                          # plant every other read's own window
+        a = int(anchors[i])
+        if 0 <= a <= 16:
+            s = bytes(slices[i, a:a + 16]).decode("latin1")
+            if all(c in "ACGTacgt" for c in s):
+                keys.add(pyref.pack(workloads.rcs(s.upper()) if three_prime else s.upper()))
+    wl = np.array(sorted(keys), dtype=np.uint64)
+    return slices, anchors, wl
+
+
+@pytest.mark.parametrize("three_prime", [True, False])
+def test_exact_lookup_sim_vs_oracle(sim, orc, three_prime):
+    slices, anchors, wl = exact_case(11 + three_prime, three_prime)
+    rank = np.arange(1, len(wl) + 1, dtype=np.int32)
+    exp = orc.exact_lookup_batch(orc.BarcodeSet(wl, rank), slices, anchors, three_prime)
+    assert (exp["flags"] & 1).sum() > 100 and (exp["flags"] & 2).sum() > 5
+    sim.sim_set_need_post.argtypes = [C.c_int]
+    got = np.zeros(len(slices), dtype=orc.BC_RESULT)
+    counts = np.zeros(len(wl) * 3, dtype=np.uint64)
+    loads = C.c_longlong(0)
+    st = np.zeros(4, dtype=np.int64)
+    try:
+        sim.sim_set_need_post(0)
+        sim.sim_bc_assign(wl.ctypes.data, rank.ctypes.data, len(wl), 0, 0, 0, int(three_prime), slices.ctypes.data, 32, 32, None,
+                          anchors.ctypes.data, len(slices), got.ctypes.data, counts.ctypes.data, C.byref(loads), st.ctypes.data)
+    finally:
+        sim.sim_set_need_post(1)
+    assert (got == exp).all(), np.nonzero(got != exp)[0][:10]
+    assert counts.reshape(-1, 3)[:, 0].sum() == (exp["flags"] & 1).sum()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("three_prime", [True, False])
+def test_exact_lookup_gpu(pkg, orc, ctx, three_prime):
+    slices, anchors, wl = exact_case(21 + three_prime, three_prime)
+    rank = np.arange(1, len(wl) + 1, dtype=np.int32)
+    exp = orc.exact_lookup_batch(orc.BarcodeSet(wl, rank), slices, anchors, three_prime)
+    table = pkg.BarcodesMapForBCfinding(ctx, wl, rank)
+    gen = pkg.UsedCellBCListGenerator(ctx, table, three_prime)
+    got = gen.addFastqs(slices, anchors)
+    assert (got == exp).all(), np.nonzero(got != exp)[0][:10]
+    keys, cnt = gen.unfilteredUsedBarcodeMap()
+    ok = (exp["flags"] & 1) == 1
+    ek, ec = np.unique(exp["bc"][ok], return_counts=True)
+    order = np.argsort(keys)
+    assert (keys[order] == ek).all() and (cnt[order] == ec).all()
+    # synthetic reads of configs[1]: the pass-1 list = barcodes seen without error at the predicted position
+    wl = pkg.synth_whitelist(737280, 737)
+    sl, an, truth = pkg.synth_reads(wl, 200000, seed=1, three_prime=three_prime)
+    table = pkg.BarcodesMapForBCfinding(ctx, wl)
+    got = pkg.UsedCellBCListGenerator(ctx, table, three_prime).addFastqs(sl, an)
+    exp = orc.exact_lookup_batch(orc.BarcodeSet(wl), sl, an, three_prime)
+    assert (got == exp).all()
+    assert 0.2 < ((got["flags"] & 1) == 1).mean() < 0.6
+
+
 # ---- the CUDA kernel through the C ABI ------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("skew", [False, True])
