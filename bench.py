@@ -8,7 +8,8 @@
 One step = one pass of the hot path over one batch per GPU (weak scaling: every rank gets its own shard of the run):
   S1  slr_bc_assign    R reads x 5 window offsets vs the 3 M-barcode list at --bcEditDistance 2   (BASELINE.json configs[2])
   S2  slr_umi_dist     the same R reads grouped into (cell, region) jobs (geometric, mean 4) -> packed 3x3 distance matrices
-  (N > 1) all-reduce of the per-barcode x ED counters (BarcodesAssigned.tsv) over NCCL — the only cross-shard exchange.
+  (N > 1) two cross-shard exchanges over NCCL: the (cell, region) group cut by every shard boundary is merged onto the lower rank
+          (all_gather of the boundary reads, UmiShardMerger) and the per-barcode x ED counters (BarcodesAssigned.tsv) are all-reduced.
 `value`  : reads/s with all inputs already resident in HBM, timed with CUDA events on the launching stream.
 `e2e`    : the same step through the host-pointer C ABI (slr_bc_assign / slr_umi_dist) from pinned host buffers, H2D and
            D2H copies inside the timed region.
@@ -121,7 +122,7 @@ def main():
     config = {"workload": "%s: %d synthetic 3' reads/GPU/step vs %d-barcode synthetic whitelist, bcEditDistance %d, "
                           "testPlusMinusPos 2%s" % (a.workload, a.reads, n_wl, ed, "" if a.no_umi else
                                                     " + UMI distance matrices of the same reads in (cell,region) jobs (mean 4)"),
-              "reads_per_gpu_per_step": a.reads, "whitelist": n_wl, "bc_edit_distance": ed, "sharding": "reads sharded, list replicated",
+              "reads_per_gpu_per_step": a.reads, "whitelist": n_wl, "bc_edit_distance": ed, "sharding": "reads sharded, list replicated; N>1: boundary UMI groups merged (all_gather) + counters all-reduced over NCCL",
               "l2_policy": "inputs larger than L2 (320 MB of slices per step) + table random access"}
 
     # ------------------------------------------------------------------------------------------ reference arm
@@ -179,9 +180,21 @@ def main():
         n_cells = int(oo_np[-1])
         h_umis, h_offs, h_oo = pin(torch.from_numpy(umis_np)), pin(torch.from_numpy(offs_np)), pin(torch.from_numpy(oo_np))
         h_mat = pin(torch.empty(n_cells, dtype=torch.int32))
-        d_umis, d_offs, d_oo = h_umis.to(dev), h_offs.to(dev), h_oo.to(dev)
-        d_mat = torch.empty(n_cells, dtype=torch.int32, device=dev)
-        n_jobs = len(offs_np) - 1
+        MERGE_CAP = 4096
+        d_umis_all = torch.zeros((R + MERGE_CAP, 16), dtype=torch.uint8, device=dev)
+        d_umis_all[:R] = h_umis.to(dev)
+        d_umis, d_offs, d_oo = d_umis_all, h_offs.to(dev), h_oo.to(dev)
+        n_jobs, n_umi_rows, dev_cells = len(offs_np) - 1, R, n_cells
+        merger = None
+        if world > 1:
+            # cross-shard UMI merge: the (cell, region) group cut by every shard boundary is clustered as ONE job on the
+            # lower rank (the last job of rank r and the first job of rank r+1 carry the same key)
+            merger = pkg.UmiShardMerger(cap=MERGE_CAP)
+            row0, n_umi_rows, moffs = merger.merge(d_umis_all, R, offs_np, (rank << 32, 0), ((rank + 1) << 32, 0))
+            moo = pkg.out_offsets_for(moffs)
+            d_umis, d_offs, d_oo = d_umis_all[row0:], torch.from_numpy(moffs).to(dev), torch.from_numpy(moo).to(dev)
+            n_jobs, dev_cells = len(moffs) - 1, int(moo[-1])
+        d_mat = torch.empty(dev_cells, dtype=torch.int32, device=dev)
     cptr, cn = table.counts_device_ptr()
     d_counts = torch.as_tensor(CudaArrayView(cptr, cn), device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -194,8 +207,10 @@ def main():
         if ev:
             ev[1].record()
         if use_umi:
-            pkg._check(lib.slr_umi_dist_dev(ctx.h, d_umis.data_ptr(), 16, 12, d_offs.data_ptr(), n_jobs, R, d_mat.data_ptr(),
-                                            d_oo.data_ptr(), n_cells, stream))
+            if merger is not None:
+                merger.exchange(d_umis_all, R)            # NCCL all_gather of the boundary groups' reads
+            pkg._check(lib.slr_umi_dist_dev(ctx.h, d_umis.data_ptr(), 16, 12, d_offs.data_ptr(), n_jobs, n_umi_rows, d_mat.data_ptr(),
+                                            d_oo.data_ptr(), dev_cells, stream))
         if world > 1:
             dist.all_reduce(d_counts)                     # cross-shard merge of the BarcodesAssigned counters (sum, int64)
 

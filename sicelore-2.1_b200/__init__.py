@@ -420,3 +420,104 @@ def generate_distance_matrices(ctx, umis, job_offsets, umi_len=12, out=None, out
     _check(gpu_lib().slr_umi_dist(ctx.h, umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(job_offsets) - 1,
                                   out.ctypes.data, out_offsets.ctypes.data))
     return out, out_offsets
+
+
+# ---------------------------------------------------------------------------------------------- cross-shard UMI merge
+class UmiShardMerger:
+    """Cross-shard merge of the UMI clustering jobs when the (cell, region)-sorted read stream is sharded by read index
+    over the ranks: a (cell, region) group (UmiClustering.groupDataByCellAndRegion, UmiClustering.java:L97-L118) that
+    straddles a shard boundary must be clustered as ONE job.  The rank that holds the group's first reads absorbs the
+    leading reads of the following rank(s); those ranks drop them.  One all_gather of a few int64 per rank + one
+    all_gather of the (padded) leading group of every rank — torch.distributed, NCCL on device tensors, gloo on the CPU.
+
+    Keys are (cell barcode, region id) pairs; every rank passes the key of its first and last job."""
+
+    META = 6          # first_cell, first_region, first_count, last_cell, last_region, n_jobs
+
+    def __init__(self, cap=4096, group=None):
+        self.cap, self.group = int(cap), group
+
+    @staticmethod
+    def plan(meta_all, rank, cap):
+        """Pure part: meta_all [world, 6] (host ints).  Returns (give, takes) where give = number of leading reads this
+        rank hands to a lower rank (its whole first job) and takes = [(source rank, count), ...] appended to its last job."""
+        world = len(meta_all)
+        fk = lambda r: (int(meta_all[r][0]), int(meta_all[r][1]))
+        lk = lambda r: (int(meta_all[r][3]), int(meta_all[r][4]))
+        nj = lambda r: int(meta_all[r][5])
+
+        def gives(r):      # rank r's first job continues the previous non-empty rank's last job
+            if r == 0 or nj(r) == 0:
+                return False
+            q = r - 1
+            while q >= 0 and nj(q) == 0:
+                q -= 1
+            return q >= 0 and lk(q) == fk(r)
+        give = int(meta_all[rank][2]) if gives(rank) else 0
+        takes = []
+        # a rank whose only job is handed away has nothing left to absorb into
+        if nj(rank) > 0 and not (gives(rank) and nj(rank) == 1):
+            r = rank + 1
+            while r < world:
+                if nj(r) == 0:
+                    r += 1
+                    continue
+                if not (gives(r) and fk(r) == lk(rank)):
+                    break
+                takes.append((r, int(meta_all[r][2])))
+                if nj(r) > 1:
+                    break
+                r += 1
+        total = sum(c for _, c in takes)
+        if total > cap or give > cap:
+            raise SiceloreGpuError(SLR_E_UNSUPPORTED, "a (cell, region) group crossing a shard boundary has more than %d reads" % cap)
+        return give, takes
+
+    def exchange(self, umis, n_reads):
+        """The data movement of the last planned merge alone (the plan is static while the sharding is): all_gather of every
+        rank's leading group, the absorbed reads land behind this rank's own reads.  Returns the number of rows appended."""
+        import torch
+        import torch.distributed as dist
+        first_count, give, takes = self.last_plan
+        world = dist.get_world_size(self.group)
+        stride = umis.shape[1]
+        lead = torch.zeros((self.cap, stride), dtype=torch.uint8, device=umis.device)
+        k = min(first_count, self.cap)
+        if k:
+            lead[:k] = umis[:k]
+        lead_all = torch.empty(world * self.cap * stride, dtype=torch.uint8, device=umis.device)
+        dist.all_gather_into_tensor(lead_all, lead.reshape(-1), group=self.group)
+        lead_all = lead_all.reshape(world, self.cap, stride)
+        extra = 0
+        for src, cnt in takes:
+            umis[n_reads + extra:n_reads + extra + cnt] = lead_all[src, :cnt]
+            extra += cnt
+        return extra
+
+    def merge(self, umis, n_reads, job_offsets, first_key, last_key):
+        """umis: torch uint8 [n_reads + cap, stride] (device or CPU; rows >= n_reads are free space), job_offsets: host int64
+        [n_jobs + 1].  Returns (row0, n_rows, offsets): the jobs of this rank after the merge are `offsets` (host int64,
+        relative to row0) over umis[row0 : row0 + n_rows]."""
+        import torch
+        import torch.distributed as dist
+        job_offsets = np.asarray(job_offsets, dtype=np.int64)
+        n_jobs = len(job_offsets) - 1
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        first_count = int(job_offsets[1] - job_offsets[0]) if n_jobs > 0 else 0
+        meta = torch.tensor([first_key[0], first_key[1], first_count, last_key[0], last_key[1], n_jobs], dtype=torch.int64,
+                            device=umis.device)
+        meta_all = torch.empty(world * self.META, dtype=torch.int64, device=umis.device)
+        dist.all_gather_into_tensor(meta_all, meta, group=self.group)
+        meta_all = meta_all.cpu().numpy().reshape(world, self.META)
+        give, takes = self.plan(meta_all, rank, self.cap)
+        self.last_plan = (first_count, give, takes)
+        extra = self.exchange(umis, n_reads)
+        offs = job_offsets - job_offsets[0]
+        row0 = 0
+        if give:
+            row0 = give
+            offs = offs[1:] - give
+        if extra:
+            offs = offs.copy()
+            offs[-1] += extra
+        return row0, n_reads - row0 + extra, np.ascontiguousarray(offs, dtype=np.int64)
