@@ -147,6 +147,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
                 // ---- 3. which ED-2 searches matter? ----------------------------------------------------------------
                 uint32_t bcA = 0;
                 const int plan = slr_level2_plan(S.ms, noff, bcA);
+                bool have_first = false;                                         // SLR_L2_TWO: an ED-2 hit has been seen (its barcode: bcA)
                 // ---- 4. ED-2 searches ---------------------------------------------------------------------------------
 #pragma unroll 1
                 for (int k = 0; k < noff && plan != SLR_L2_NONE; k++) {
@@ -217,6 +218,10 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
                             S.ms.m_valid[k] |= 4u;
                         }
                         if (plan == SLR_L2_UNTIL && bcb != bcA) break;               // ed_second is settled
+                        if (plan == SLR_L2_TWO) {
+                            if (have_first && bcb != bcA) break;                     // two barcodes at ED 2: unassigned, ed = ed_second = 2
+                            if (!have_first) { have_first = true; bcA = bcb; }
+                        }
                     }
                     __syncwarp();
                 }

@@ -388,21 +388,25 @@ SLR_COLD int slr_decide_cap(const SlrMatchStore &S, int noff, bool &treeified)
 
 // Which ED-2 searches can still change the record once levels 0 and 1 of every window are known?  (The reference runs
 // all of them; the kernel skips the ones whose result provably cannot reach the output.)
-//   SLR_L2_ALL   every window (nothing matched yet, or too many entries to pin the HashSet capacity)
+//   SLR_L2_ALL   every window (too many entries to pin the HashSet capacity)
+//   SLR_L2_TWO   nothing matched at ED <= 1: windows in order until two DIFFERENT barcodes have been hit at ED 2 - the best
+//                match then has ED 2 and so has the second best, i.e. the read is unassigned with ed = ed_second = 2
+//                whatever the remaining windows add (an unassigned record carries nothing else)
 //   SLR_L2_NONE  none: the best match has ED <= 1 and another barcode already sits at ED <= 1, so neither best nor
 //                ed_second can move
 //   SLR_L2_UNTIL windows in order until one yields an ED-2 hit on a barcode other than bcA: every ED <= 1 entry
 //                carries bcA, so best is fixed and ed_second is 2 if such a hit exists, else none
 // With n01 + noff <= 8 entries in total the merged HashMap stays at capacity 16 whatever the ED-2 searches add (no
 // resize above 12, no bin of 9), so the tie order among the ED <= 1 entries - and with it the best match - is final.
-enum { SLR_L2_NONE = 0, SLR_L2_ALL = 1, SLR_L2_UNTIL = 2 };
+enum { SLR_L2_NONE = 0, SLR_L2_ALL = 1, SLR_L2_UNTIL = 2, SLR_L2_TWO = 3 };
 SLR_HD int slr_level2_plan(const SlrMatchStore &S, int noff, uint32_t &bcA)
 {
     int n01 = 0;
 #pragma unroll 1
     for (int k = 0; k < noff; k++) n01 += slr_popc(S.m_valid[k] & 3u);
     bcA = 0;
-    if (n01 == 0 || n01 + noff > 8) return SLR_L2_ALL;
+    if (n01 + noff > 8) return SLR_L2_ALL;
+    if (n01 == 0) return SLR_L2_TWO;
     uint32_t bestkey = SLR_NONE32;
 #pragma unroll 1
     for (int k = 0; k < noff; k++) {

@@ -78,6 +78,7 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
     }
     // 3. + 4. the ED-2 searches that can still change the record
     uint32_t bcA = 0;
+    bool have_first = false;
     const int plan = (ed_max >= 2 && !(flags & SLR_F_EXCEPTION)) ? (force_all_l2 ? (int)SLR_L2_ALL : slr_level2_plan(ms, noff, bcA)) : (int)SLR_L2_NONE;
     for (int k = 0; k < noff && plan != SLR_L2_NONE; k++) {
         if (win_dead[k]) continue;
@@ -122,6 +123,10 @@ static void sim_read(const SlrTableDev &tab, int ed_max, int plusminus, int thre
             ms.m_bc[k][2] = bcb;
             ms.m_cnt[k][2] = (uint8_t)(cntb + slr_cnt_of(best & 15u));
             if (plan == SLR_L2_UNTIL && bcb != bcA) break;
+            if (plan == SLR_L2_TWO) {
+                if (have_first && bcb != bcA) break;
+                if (!have_first) { have_first = true; bcA = bcb; }
+            }
         }
     }
     slr_bc_result res;
