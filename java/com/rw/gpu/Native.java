@@ -1,0 +1,37 @@
+package com.rw.gpu;
+
+import java.nio.ByteBuffer;
+
+/**
+ * JNI binding of libsicelore_gpu.so (include/sicelore_gpu.h) for NanoporeBC_UMI_finder-2.1.jar.
+ * Not compiled in the build image (no JDK there); the glue is java/sicelore_gpu_jni.c, compile-checked against a stub jni.h by
+ * tests/test_abi.py.  All buffers are DIRECT ByteBuffers in native byte order; records are documented in INTEGRATION.md.
+ * Every int-returning method returns 0 or a negative SLR_E_* code; lastError() has the message.  There is no CPU fallback.
+ */
+public final class Native {
+    static { System.loadLibrary("sicelore_gpu_jni"); }
+    private Native() {}
+
+    public static native long ctxCreate(int device, int nStreams);                         // slr_ctx_create  (0 = failed)
+    public static native void ctxDestroy(long ctx);                                        // slr_ctx_destroy
+    /** barcodes2bit = key set of the Long2ObjectOpenHashMap (WorkerReadscanner.java:L264-L269), rank = CountsRank.rank or null */
+    public static native long bcTableCreate(long ctx, long[] barcodes2bit, int[] rank);    // slr_bc_table_create (0 = failed)
+    public static native void bcTableDestroy(long table);
+    public static native long bcTableSize(long table);
+    /** Parser.assignBarcode for a whole ReadChunk (Parser.java:L198-L252); lens may be null */
+    public static native int bcAssign(long ctx, long table, int edMax, int plusMinus, boolean threePrime, ByteBuffer slices, int stride,
+                                      int sliceLen, ByteBuffer lens, ByteBuffer anchor, long n, ByteBuffer out);
+    /** UsedCellBCListGenerator$Worker exact lookup (UsedCellBCListGenerator.java:L206-L232) */
+    public static native int bcExact(long ctx, long table, boolean threePrime, ByteBuffer slices, int stride, int sliceLen,
+                                     ByteBuffer lens, ByteBuffer anchor, long n, ByteBuffer out);
+    /** assignedBarcodes2ndPass / unfilteredUsedBarcodeMap counters: countsOut.length = 3 * number of barcodes */
+    public static native int bcCountsRead(long ctx, long table, long[] countsOut);
+    public static native int bcCountsReset(long ctx, long table);
+    /** BarcodeDatasetColissionTester.submitSeq loop (BarcodeDatasetColissionTester.java:L212-L229); out: n * 24 bytes */
+    public static native int bcCollide(long ctx, long table, int edMax, long[] barcodes, ByteBuffer out);
+    /** ClusteringEditDistanceBase.generateDistanceMatrix for all jobs of a BAM chunk (…java:L168-L259) */
+    public static native int umiDist(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, ByteBuffer out,
+                                     ByteBuffer outOffsets);
+    public static native String lastError();
+    public static native int abiVersion();
+}

@@ -1,0 +1,112 @@
+/* JNI glue between com.rw.gpu.Native (java/com/rw/gpu/Native.java) and the C ABI of libsicelore_gpu.so (include/sicelore_gpu.h).
+ * Build where a JDK exists:  gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude java/sicelore_gpu_jni.c \
+ *                                -Lsicelore-2.1_b200 -lsicelore_gpu -o libsicelore_gpu_jni.so
+ * Pure pointer forwarding: direct ByteBuffers are passed by address, Java arrays are pinned for the duration of the call. */
+#include <jni.h>
+#include <stddef.h>
+#include "sicelore_gpu.h"
+
+#define BUF(b) ((b) ? (*env)->GetDirectBufferAddress(env, (b)) : NULL)
+
+JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_ctxCreate(JNIEnv *env, jclass cls, jint device, jint nStreams)
+{
+    (void)env; (void)cls;
+    slr_ctx *c = NULL;
+    return slr_ctx_create(device, nStreams, &c) == SLR_OK ? (jlong)(size_t)c : 0;
+}
+
+JNIEXPORT void JNICALL Java_com_rw_gpu_Native_ctxDestroy(JNIEnv *env, jclass cls, jlong ctx)
+{
+    (void)env; (void)cls;
+    slr_ctx_destroy((slr_ctx *)(size_t)ctx);
+}
+
+JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_bcTableCreate(JNIEnv *env, jclass cls, jlong ctx, jlongArray barcodes, jintArray rank)
+{
+    (void)cls;
+    const jsize n = (*env)->GetArrayLength(env, barcodes);
+    jlong *b = (*env)->GetLongArrayElements(env, barcodes, NULL);
+    jint *r = rank ? (*env)->GetIntArrayElements(env, rank, NULL) : NULL;
+    slr_bc_table *t = NULL;
+    const int rc = slr_bc_table_create((slr_ctx *)(size_t)ctx, (const uint64_t *)b, (const int32_t *)r, (int64_t)n, 16, &t);
+    (*env)->ReleaseLongArrayElements(env, barcodes, b, JNI_ABORT);
+    if (r) (*env)->ReleaseIntArrayElements(env, rank, r, JNI_ABORT);
+    return rc == SLR_OK ? (jlong)(size_t)t : 0;
+}
+
+JNIEXPORT void JNICALL Java_com_rw_gpu_Native_bcTableDestroy(JNIEnv *env, jclass cls, jlong table)
+{
+    (void)env; (void)cls;
+    slr_bc_table_destroy((slr_bc_table *)(size_t)table);
+}
+
+JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_bcTableSize(JNIEnv *env, jclass cls, jlong table)
+{
+    (void)env; (void)cls;
+    return (jlong)slr_bc_table_size((const slr_bc_table *)(size_t)table);
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_bcAssign(JNIEnv *env, jclass cls, jlong ctx, jlong table, jint edMax, jint plusMinus,
+                                                       jboolean threePrime, jobject slices, jint stride, jint sliceLen, jobject lens,
+                                                       jobject anchor, jlong n, jobject out)
+{
+    (void)cls;
+    return slr_bc_assign((slr_ctx *)(size_t)ctx, (const slr_bc_table *)(size_t)table, edMax, plusMinus, threePrime ? 1 : 0,
+                         (const uint8_t *)BUF(slices), stride, sliceLen, (const int32_t *)BUF(lens), (const int32_t *)BUF(anchor),
+                         (int64_t)n, (slr_bc_result *)BUF(out));
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_bcExact(JNIEnv *env, jclass cls, jlong ctx, jlong table, jboolean threePrime, jobject slices,
+                                                      jint stride, jint sliceLen, jobject lens, jobject anchor, jlong n, jobject out)
+{
+    (void)cls;
+    return slr_bc_exact((slr_ctx *)(size_t)ctx, (const slr_bc_table *)(size_t)table, threePrime ? 1 : 0, (const uint8_t *)BUF(slices),
+                        stride, sliceLen, (const int32_t *)BUF(lens), (const int32_t *)BUF(anchor), (int64_t)n, (slr_bc_result *)BUF(out));
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_bcCountsRead(JNIEnv *env, jclass cls, jlong ctx, jlong table, jlongArray countsOut)
+{
+    (void)cls;
+    jlong *c = (*env)->GetLongArrayElements(env, countsOut, NULL);
+    const int rc = slr_bc_counts_read((slr_ctx *)(size_t)ctx, (const slr_bc_table *)(size_t)table, (int64_t *)c);
+    (*env)->ReleaseLongArrayElements(env, countsOut, c, 0);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_bcCountsReset(JNIEnv *env, jclass cls, jlong ctx, jlong table)
+{
+    (void)env; (void)cls;
+    return slr_bc_counts_reset((slr_ctx *)(size_t)ctx, (slr_bc_table *)(size_t)table);
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_bcCollide(JNIEnv *env, jclass cls, jlong ctx, jlong table, jint edMax, jlongArray barcodes,
+                                                        jobject out)
+{
+    (void)cls;
+    const jsize n = (*env)->GetArrayLength(env, barcodes);
+    jlong *b = (*env)->GetLongArrayElements(env, barcodes, NULL);
+    const int rc = slr_bc_collide((slr_ctx *)(size_t)ctx, (const slr_bc_table *)(size_t)table, edMax, (const uint64_t *)b, (int64_t)n,
+                                  (slr_collide_result *)BUF(out));
+    (*env)->ReleaseLongArrayElements(env, barcodes, b, JNI_ABORT);
+    return rc;
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_umiDist(JNIEnv *env, jclass cls, jlong ctx, jobject umis, jint stride, jint umiLen,
+                                                      jobject jobOffsets, jlong nJobs, jobject out, jobject outOffsets)
+{
+    (void)cls;
+    return slr_umi_dist((slr_ctx *)(size_t)ctx, (const uint8_t *)BUF(umis), stride, umiLen, (const int64_t *)BUF(jobOffsets), (int64_t)nJobs,
+                        (int32_t *)BUF(out), (const int64_t *)BUF(outOffsets));
+}
+
+JNIEXPORT jstring JNICALL Java_com_rw_gpu_Native_lastError(JNIEnv *env, jclass cls)
+{
+    (void)cls;
+    return (*env)->NewStringUTF(env, slr_last_error());
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_abiVersion(JNIEnv *env, jclass cls)
+{
+    (void)env; (void)cls;
+    return slr_abi_version();
+}

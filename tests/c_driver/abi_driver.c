@@ -1,0 +1,81 @@
+/* TEST INFRASTRUCTURE: a plain-C caller of libsicelore_gpu.so (no Python, no torch) that replays recorded boundary buffers
+ * through the C ABI and compares the records byte for byte with the recorded reference results — what the JNI glue does
+ * from Java (java/sicelore_gpu_jni.c), minus the JVM.
+ *   abi_driver <file>      file = "SLRB" | u32 kind (1 bc_assign, 2 umi_dist, 3 bc_collide, 4 bc_exact) | kind-specific payload
+ * exit code 0 = identical, 1 = mismatch, 2 = bad file, 3 = no CUDA device (the library has no CPU fallback). */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "sicelore_gpu.h"
+
+static void *rd(FILE *f, size_t bytes)
+{
+    void *p = malloc(bytes ? bytes : 1);
+    if (!p || fread(p, 1, bytes, f) != bytes) { fprintf(stderr, "short read\n"); exit(2); }
+    return p;
+}
+static int64_t rd64(FILE *f) { int64_t v; if (fread(&v, 8, 1, f) != 1) { fprintf(stderr, "short read\n"); exit(2); } return v; }
+
+#define CHECK(call)                                                                    \
+    do {                                                                               \
+        int rc_ = (call);                                                              \
+        if (rc_ != SLR_OK) {                                                           \
+            fprintf(stderr, "%s -> %d: %s\n", #call, rc_, slr_last_error());           \
+            return rc_ == SLR_E_NODEVICE ? 3 : 1;                                      \
+        }                                                                              \
+    } while (0)
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) { fprintf(stderr, "usage: abi_driver <file>\n"); return 2; }
+    FILE *f = fopen(argv[1], "rb");
+    char magic[4];
+    uint32_t kind;
+    if (!f || fread(magic, 1, 4, f) != 4 || memcmp(magic, "SLRB", 4) || fread(&kind, 4, 1, f) != 1) { fprintf(stderr, "bad file\n"); return 2; }
+    if (slr_abi_version() != SLR_ABI_VERSION) { fprintf(stderr, "ABI version mismatch\n"); return 1; }
+    slr_ctx *ctx = NULL;
+    CHECK(slr_ctx_create(0, 2, &ctx));
+    int bad = 0;
+    if (kind == 1 || kind == 3 || kind == 4) {
+        const int64_t n_keys = rd64(f), has_rank = rd64(f);
+        uint64_t *keys = rd(f, (size_t)n_keys * 8);
+        int32_t *rank = has_rank ? rd(f, (size_t)n_keys * 4) : NULL;
+        slr_bc_table *t = NULL;
+        CHECK(slr_bc_table_create(ctx, keys, rank, n_keys, 16, &t));
+        if (kind == 3) {
+            const int64_t ed = rd64(f), n = rd64(f);
+            uint64_t *q = rd(f, (size_t)n * 8);
+            slr_collide_result *exp = rd(f, (size_t)n * sizeof(slr_collide_result)), *got = malloc((size_t)n * sizeof(slr_collide_result) + 1);
+            CHECK(slr_bc_collide(ctx, t, (int)ed, q, n, got));
+            bad = memcmp(got, exp, (size_t)n * sizeof(slr_collide_result)) != 0;
+            printf("bc_collide: %lld barcodes, ED %lld: %s\n", (long long)n, (long long)ed, bad ? "MISMATCH" : "OK");
+        } else {
+            const int64_t ed = rd64(f), pm = rd64(f), tp = rd64(f), n = rd64(f);
+            uint8_t *slices = rd(f, (size_t)n * 32);
+            int32_t *anchor = rd(f, (size_t)n * 4);
+            slr_bc_result *exp = rd(f, (size_t)n * sizeof(slr_bc_result)), *got = malloc((size_t)n * sizeof(slr_bc_result) + 1);
+            if (kind == 1) CHECK(slr_bc_assign(ctx, t, (int)ed, (int)pm, (int)tp, slices, 32, 32, NULL, anchor, n, got));
+            else CHECK(slr_bc_exact(ctx, t, (int)tp, slices, 32, 32, NULL, anchor, n, got));
+            bad = memcmp(got, exp, (size_t)n * sizeof(slr_bc_result)) != 0;
+            int64_t *counts = malloc((size_t)n_keys * 24 + 8), total = 0, assigned = 0;
+            CHECK(slr_bc_counts_read(ctx, t, counts));
+            for (int64_t i = 0; i < n_keys * 3; i++) total += counts[i];
+            for (int64_t i = 0; i < n; i++) assigned += exp[i].flags & SLR_F_ASSIGNED;
+            bad |= total != assigned;
+            printf("%s: %lld reads, ED %lld, %lld assigned, counters %lld: %s\n", kind == 1 ? "bc_assign" : "bc_exact", (long long)n,
+                   (long long)ed, (long long)assigned, (long long)total, bad ? "MISMATCH" : "OK");
+        }
+        slr_bc_table_destroy(t);
+    } else if (kind == 2) {
+        const int64_t umi_len = rd64(f), n_jobs = rd64(f), m = rd64(f), cells = rd64(f);
+        uint8_t *umis = rd(f, (size_t)m * 16);
+        int64_t *joff = rd(f, (size_t)(n_jobs + 1) * 8), *ooff = rd(f, (size_t)(n_jobs + 1) * 8);
+        int32_t *exp = rd(f, (size_t)cells * 4), *got = malloc((size_t)cells * 4 + 4);
+        CHECK(slr_umi_dist(ctx, umis, 16, (int)umi_len, joff, n_jobs, got, ooff));
+        bad = memcmp(got, exp, (size_t)cells * 4) != 0;
+        printf("umi_dist: %lld jobs, %lld reads, %lld cells: %s\n", (long long)n_jobs, (long long)m, (long long)cells, bad ? "MISMATCH" : "OK");
+    } else { fprintf(stderr, "unknown kind %u\n", kind); return 2; }
+    slr_ctx_destroy(ctx);
+    return bad ? 1 : 0;
+}

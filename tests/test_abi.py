@@ -64,3 +64,73 @@ def test_synth_is_deterministic_and_shardable(pkg):
     u, o = pkg.synth_umi_jobs(50, mean=4.0, cap=30, seed=2)
     u2, o2 = pkg.synth_umi_jobs(50, mean=4.0, cap=30, seed=2)
     assert (u == u2).all() and (o == o2).all() and o[-1] == len(u) and (np.diff(o) >= 1).all()
+
+
+# ---- callers other than Python: the JNI glue (compile / link check against a stub jni.h) and a plain-C driver ---------------
+def build_c(out, src, extra):
+    import subprocess
+    lib_dir = os.path.join(ROOT, "sicelore-2.1_b200")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include")] + extra +
+                          [src, "-L" + lib_dir, "-lsicelore_gpu", "-Wl,-rpath," + lib_dir, "-o", out])
+    return out
+
+
+def test_jni_glue_compiles_and_links(pkg, tmp_path):
+    """java/sicelore_gpu_jni.c forwards every native method of java/com/rw/gpu/Native.java to the C ABI"""
+    import subprocess
+    so = build_c(str(tmp_path / "libsicelore_gpu_jni.so"), os.path.join(ROOT, "java", "sicelore_gpu_jni.c"),
+                 ["-shared", "-fPIC", "-I" + os.path.join(ROOT, "tests", "jni_stub")])
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"Java_com_rw_gpu_Native_(\w+)", syms))
+    java = open(os.path.join(ROOT, "java", "com", "rw", "gpu", "Native.java")).read()
+    natives = set(re.findall(r"public static native [\w\[\]]+ (\w+)\(", java))
+    assert natives and exported == natives, (sorted(natives - exported), sorted(exported - natives))
+
+
+def write_driver_file(path, kind, arrays):
+    import numpy as np
+    with open(path, "wb") as f:
+        f.write(b"SLRB" + np.uint32(kind).tobytes())
+        for a in arrays:
+            f.write(np.int64(a).tobytes() if np.isscalar(a) or isinstance(a, (int, np.integer)) else np.ascontiguousarray(a).tobytes())
+
+
+def driver_inputs(tmp_path, orc):
+    import numpy as np
+    gold = os.path.join(ROOT, "tests", "golden")
+    files = []
+    g = np.load(os.path.join(gold, "bc_3p_ed2.npz"))
+    n = len(g["slices"])
+    files.append(write_driver_file(tmp_path / "bc.bin", 1, [len(g["whitelist"]), 1, g["whitelist"], g["rank"], int(g["ed"]), 2, int(g["three_prime"]),
+                                                          n, g["slices"], g["anchor"], g["result"]]) or tmp_path / "bc.bin")
+    ex = orc.exact_lookup_batch(orc.BarcodeSet(g["whitelist"], g["rank"]), g["slices"], g["anchor"], True)
+    files.append(write_driver_file(tmp_path / "exact.bin", 4, [len(g["whitelist"]), 1, g["whitelist"], g["rank"], 0, 0, 1, n, g["slices"],
+                                                             g["anchor"], ex]) or tmp_path / "exact.bin")
+    c = np.load(os.path.join(gold, "collide_ed2_skew.npz"))
+    files.append(write_driver_file(tmp_path / "collide.bin", 3, [len(c["whitelist"]), 0, c["whitelist"], int(c["ed"]), len(c["whitelist"]),
+                                                               c["whitelist"], c["result"]]) or tmp_path / "collide.bin")
+    u = np.load(os.path.join(gold, "umi_len12.npz"))
+    files.append(write_driver_file(tmp_path / "umi.bin", 2, [int(u["umi_len"]), len(u["job_offsets"]) - 1, len(u["umis"]), len(u["matrix"]),
+                                                           u["umis"], u["job_offsets"], u["out_offsets"], u["matrix"]]) or tmp_path / "umi.bin")
+    return files
+
+
+def test_c_driver_fails_loudly_without_gpu(pkg, orc, tmp_path):
+    import subprocess
+    import torch
+    exe = build_c(str(tmp_path / "abi_driver"), os.path.join(ROOT, "tests", "c_driver", "abi_driver.c"), [])
+    files = driver_inputs(tmp_path, orc)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([exe, str(files[0])], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_driver_replays_golden_buffers(pkg, orc, tmp_path):
+    """a C program (no Python, no torch in the process) gets bit-identical records through the C ABI"""
+    import subprocess
+    exe = build_c(str(tmp_path / "abi_driver"), os.path.join(ROOT, "tests", "c_driver", "abi_driver.c"), [])
+    for f in driver_inputs(tmp_path, orc):
+        r = subprocess.run([exe, str(f)], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (f, r.stdout, r.stderr)
