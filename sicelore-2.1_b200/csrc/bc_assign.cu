@@ -55,6 +55,64 @@ __device__ __forceinline__ uint32_t vh_insert_first(unsigned long long *tab, uin
     }
 }
 
+// Warp-parallel forms of slr_level2_plan / slr_decide (bc_core.cuh, the serial forms the CPU replay uses): lane e = 3 k + lv
+// owns entry (window k, ED level lv) of the match store.  With at most 8 entries the merged HashMap stays at capacity 16,
+// the sort key of an entry is (ED, offset != 0, bucket, insertion order) and everything is a warp min-reduction; more
+// entries (HashMap resizes, possible treeified bin) take the serial path.
+struct WarpEntry {
+    uint32_t key;       // sort key at capacity 16, SLR_NONE32 = no entry
+    uint32_t bc;
+    int lv;
+};
+__device__ __forceinline__ WarpEntry warp_entry(const SlrMatchStore &M, int noff, int lane, int max_lv)
+{
+    WarpEntry e;
+    e.key = SLR_NONE32; e.bc = 0;
+    const int k = lane / 3;
+    e.lv = lane - 3 * k;
+    if (k < noff && e.lv <= max_lv && ((M.m_valid[k] >> e.lv) & 1)) {
+        const uint32_t w = M.m_w[k], sp = w ^ (w >> 16);
+        e.key = ((uint32_t)e.lv << 20) | ((k != 0 ? 1u : 0u) << 16) | ((sp & 15u) << 8) | (uint32_t)lane;
+        e.bc = M.m_bc[k][e.lv];
+    }
+    return e;
+}
+__device__ __forceinline__ int warp_level2_plan(const SlrMatchStore &M, int noff, int lane, uint32_t &bcA)
+{
+    const WarpEntry e = warp_entry(M, noff, lane, 1);
+    const int n01 = __popc(__ballot_sync(FULL, e.key != SLR_NONE32));
+    bcA = 0;
+    if (n01 + noff > 8) return SLR_L2_ALL;
+    if (n01 == 0) return SLR_L2_TWO;
+    const uint32_t best = __reduce_min_sync(FULL, e.key);
+    bcA = __shfl_sync(FULL, e.bc, (int)(best & 0xFFu));
+    return __ballot_sync(FULL, e.key != SLR_NONE32 && e.bc != bcA) ? SLR_L2_NONE : SLR_L2_UNTIL;
+}
+__device__ __forceinline__ int warp_decide(const SlrMatchStore &M, int noff, int ed_max, int lane, slr_bc_result &res)
+{
+    const WarpEntry e = warp_entry(M, noff, lane, 2);
+    const int cnt = __popc(__ballot_sync(FULL, e.key != SLR_NONE32));
+    if (cnt > 8) return slr_decide(M, noff, ed_max, res);
+    if (cnt == 0) return -1;
+    const uint32_t best = __reduce_min_sync(FULL, e.key);
+    const int be = (int)(best & 0xFFu), bk = be / 3, blv = (int)(best >> 20);
+    const uint32_t bbc = __shfl_sync(FULL, e.bc, be);
+    const uint32_t second = __reduce_min_sync(FULL, (e.key != SLR_NONE32 && e.bc != bbc) ? (uint32_t)e.lv : 0x7FFFFFFFu);
+    res.ed = blv;
+    res.ed_second = (int32_t)second;
+    if (blv <= ed_max && blv < (int)second) {                                   // L251-L252
+        res.flags |= SLR_F_ASSIGNED;
+        res.bc = bbc;
+        res.offset = (int8_t)slr_offset_of(bk);
+        const uint32_t c = M.m_cnt[bk][blv];
+        res.n_sub = (int8_t)(c & 3u);
+        res.n_ins = (int8_t)((c >> 2) & 3u);
+        res.n_del = (int8_t)((c >> 4) & 3u);
+        return blv;
+    }
+    return -1;
+}
+
 // Persistent warps: warp i of the grid takes reads i, i + #warps, ... (reads are i.i.d., a static stride balances).
 // Per read:
 //   1. the 2*plusminus+1 windows (bit-field extracts of the ballot planes);
@@ -146,7 +204,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
             if (EDMAX >= 2) {
                 // ---- 3. which ED-2 searches matter? ----------------------------------------------------------------
                 uint32_t bcA = 0;
-                const int plan = slr_level2_plan(S.ms, noff, bcA);
+                const int plan = warp_level2_plan(S.ms, noff, lane, bcA);
                 bool have_first = false;                                         // SLR_L2_TWO: an ED-2 hit has been seen (its barcode: bcA)
                 // ---- 4. ED-2 searches ---------------------------------------------------------------------------------
 #pragma unroll 1
@@ -234,7 +292,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
         res.bc = 0; res.ed = -1; res.ed_second = 0x7FFFFFFF; res.offset = 0; res.n_ins = 0; res.n_del = 0; res.n_sub = 0;
         res.rank = -1; res.flags = flags;
         if (!(flags & SLR_F_EXCEPTION)) {
-            const int lv = slr_decide(S.ms, noff, EDMAX, res);
+            const int lv = warp_decide(S.ms, noff, EDMAX, lane, res);
             if (lv >= 0 && lane == 0) {
                 const int ix = slr_index_of(tab, (uint32_t)res.bc);
                 res.rank = (ix >= 0 && tab.rank) ? tab.rank[ix] : ix;                  // CountsRank.rank (L267-L269)
