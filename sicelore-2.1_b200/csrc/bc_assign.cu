@@ -35,6 +35,7 @@ struct alignas(16) WarpShared {
     uint2 node[144];                           // level-1 nodes to expand, in processing order: (sequence, slr_node_meta)
     SlrMatchStore ms;
     uint32_t win[SLR_MAX_OFFSETS];             // per window: p1 | p2 << 2 | dead << 4   (the window itself is ms.m_w)
+    uint32_t r1[SLR_MAX_OFFSETS];              // per window: traversal rank of the ED-1 hit kept so far
 };
 
 // First insertion wins: the caller inserts in increasing processing time (rounds in order, duplicates inside a
@@ -116,8 +117,8 @@ __device__ __forceinline__ int warp_decide(const SlrMatchStore &M, int noff, int
 // Persistent warps: warp i of the grid takes reads i, i + #warps, ... (reads are i.i.d., a static stride balances).
 // Per read:
 //   1. the 2*plusminus+1 windows (bit-field extracts of the ballot planes);
-//   2. levels 0 and 1 of ALL windows: 12 bucket probes per window (4 digit groups x SUB/INS/DEL), two windows per warp
-//      step (16 lanes each); "first hit wins" = minimum traversal rank over the 16 lanes of a window;
+//   2. levels 0 and 1 of ALL windows: 12 bucket probes per window (4 digit groups x SUB/INS/DEL), 32 probes per warp step;
+//      "first hit wins" = minimum traversal rank over the probes of a window;
 //   3. slr_level2_plan: which ED-2 searches can still change the record (most reads: none, or just enough to settle
 //      ed_second) - the reference runs all of them, but its HashSet.add / distinctByKey make the rest dead work;
 //   4. per remaining window: visited hash + live level-1 nodes, then 32 probes per warp step over the nodes in the
@@ -158,6 +159,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
                 S.ms.m_w[lane] = w;
                 S.ms.m_valid[lane] = 0;
                 S.win[lane] = p1 | (p2 << 2) | ((dead_window ? 1u : 0u) << 4);
+                S.r1[lane] = SLR_NONE32;
             }
             if (__ballot_sync(FULL, !ok)) flags |= SLR_F_EXCEPTION;        // the Java throws at the first bad window: no record
         }
@@ -165,40 +167,45 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
 
         if (!(flags & SLR_F_EXCEPTION)) {
             // ---- 2. levels 0 and 1 of every window (BarcodeMatchTester.java:L204-L206 + the root's expansion) ----
-            // lanes 16h .. 16h+11 = the 12 probes of window kb + h; probe 0's bucket (table 0, rest of w) also answers
-            // the ED-0 lookup.
+            // probe pi = 12 k + (digit group, op) of window k, 32 probes per warp step (5 windows: 2 steps); probe 0 of a window
+            // (table 0, rest of w) also answers the ED-0 lookup.  First hit per window = minimum traversal rank over its probes,
+            // kept across steps in S.r1.
+            constexpr int PER = EDMAX >= 1 ? 12 : 1;
+            const int nprobe1 = noff * PER;
 #pragma unroll 1
-            for (int kb = 0; kb < noff; kb += 2) {
-                const int k = kb + (lane >> 4), rem = lane & 15;
+            for (int base = 0; base < nprobe1; base += 32) {
+                const int pi = base + lane;
+                const int k = pi / PER, rem = pi - k * PER;
                 uint32_t r2 = SLR_NONE32, bc2 = 0;
-                bool hit0 = false;
-                uint32_t w = 0;
-                if (k < noff && rem < (EDMAX >= 1 ? 12 : 1)) {
-                    w = S.ms.m_w[k];
-                    const uint32_t wi = S.win[k];
+                if (pi < nprobe1) {
+                    const uint32_t w = S.ms.m_w[k], wi = S.win[k];
                     if (!(wi & 16u)) {
                         const int g = (rem * 11) >> 5, op = rem - 3 * g;
                         const SlrExpand e1 = slr_root_expand(w, wi & 3u, EDMAX >= 2);
                         const SlrProbe pr = slr_probe_addr(tab, w, wi & 3u, g, op);
                         const SlrBucket bk = slr_load_bucket(tab, g, pr.bucket);
-                        if (rem == 0) hit0 = slr_contains_in(tab, bk, pr.bucket, pr.tag, w >> 24);
+                        if (rem == 0 && slr_contains_in(tab, bk, pr.bucket, pr.tag, w >> 24)) {
+                            S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; S.ms.m_valid[k] = 1;
+                        }
                         if (EDMAX >= 1) r2 = slr_probe_eval(tab, e1, S.vh, g, op, pr, bk, bc2);
                     }
                 }
-                uint32_t rmin = r2;                                              // minimum over the 16 lanes of the window
                 if (EDMAX >= 1) {
-#pragma unroll
-                    for (int d = 8; d >= 1; d >>= 1) rmin = min(rmin, __shfl_xor_sync(FULL, rmin, d));
-                }
-                const uint32_t winners = __ballot_sync(FULL, r2 == rmin && r2 != SLR_NONE32) & (0xFFFFu << (lane & 16));
-                const uint32_t bc1 = __shfl_sync(FULL, bc2, winners ? __ffs((int)winners) - 1 : lane);
-                if (rem == 0 && k < noff) {
-                    uint32_t lv = 0;
-                    if (hit0) { lv |= 1u; S.ms.m_bc[k][0] = w; S.ms.m_cnt[k][0] = 0; }
-                    if (rmin != SLR_NONE32) { lv |= 2u; S.ms.m_bc[k][1] = bc1; S.ms.m_cnt[k][1] = (uint8_t)slr_cnt_of(rmin & 15u); }
-                    S.ms.m_valid[k] = (uint8_t)lv;
+                    const int k_hi = min(noff - 1, (base + 31) / PER);
+#pragma unroll 1
+                    for (int kk = base / PER; kk <= k_hi; kk++) {
+                        const uint32_t mine = (k == kk) ? r2 : SLR_NONE32;
+                        const uint32_t m = __reduce_min_sync(FULL, mine);
+                        if (m != SLR_NONE32) {
+                            const int src = __ffs((int)__ballot_sync(FULL, mine == m)) - 1;
+                            const uint32_t b1 = __shfl_sync(FULL, bc2, src);
+                            if (lane == 0 && m < S.r1[kk]) { S.r1[kk] = m; S.ms.m_bc[kk][1] = b1; S.ms.m_cnt[kk][1] = (uint8_t)slr_cnt_of(m & 15u); }
+                        }
+                    }
                 }
             }
+            __syncwarp();
+            if (EDMAX >= 1 && lane < noff && S.r1[lane] != SLR_NONE32) S.ms.m_valid[lane] |= 2u;
             __syncwarp();
 
             if (EDMAX >= 2) {
