@@ -246,8 +246,23 @@ def main():
     e1.record()
     sync_all()
     launches = pkg.launch_count() - l0
+    clocks = sampler.summary()                             # stop sampling here: nvidia-smi takes driver locks that stall the
+    sampler.join(timeout=10)                               # host-side submission of the end-to-end leg below
     ms_total = e0.elapsed_time(e1)
     bc_ms = sum(x.elapsed_time(y) for x, y in bc_ev) / a.steps
+    # host <-> device link of this box (pinned, 256 MB each way): explains e2e on a slow PCIe slot / remote NUMA node
+    link = {}
+    pb, db = pin(torch.empty(256 << 20, dtype=torch.uint8)), torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for name, dst, src in (("h2d_gbs", db, pb), ("d2h_gbs", pb, db)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        link[name] = (256 << 20) / (c0.elapsed_time(c1) / 1e3) / 1e9
+    del pb, db
     # end to end through the host-pointer ABI
     step_e2e()
     sync_all()
@@ -256,7 +271,6 @@ def main():
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / a.steps
-    clocks = sampler.summary()
     t = torch.tensor([ms_total / a.steps, e2e_s * 1e3, bc_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,7 +285,7 @@ def main():
         h2d = R * 36 + (int(h_umis.numel()) + 8 * (len(offs_np) + len(oo_np)) if use_umi else 0)
         d2h = R * 32 + (n_cells * 4 if use_umi else 0)
         out["e2e"] = {"value": world * R / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                      "ms_per_step": e2e_ms}
+                      "ms_per_step": e2e_ms, "link": link}
         # ---- CPU baseline (bounded sample, all host threads) + the reference's algorithmic bytes per read -------------
         probes_per_read = 55091.0 if ed >= 2 else 620.0       # App. A.5 of SURVEY.md; re-measured on the sample below
         if not a.no_cpu_baseline:

@@ -25,6 +25,7 @@
 namespace {
 
 constexpr int WARPS_PER_BLOCK = 8;
+constexpr int READ_BATCH = 4;                  // reads a warp takes per visit to the work counter
 constexpr unsigned FULL = 0xFFFFFFFFu;
 #ifndef SLR_BC_MINB_ED2
 #define SLR_BC_MINB_ED2 4                      // resident CTAs per SM the ED-2 kernel is compiled for (register cap 64)
@@ -127,7 +128,8 @@ __device__ __forceinline__ int warp_decide(const SlrMatchStore &M, int noff, int
 template <int EDMAX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EDMAX >= 2 ? SLR_BC_MINB_ED2 : 4)
 bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post, const uint8_t *__restrict__ slices, int stride, int slice_len,
-                 const int32_t *__restrict__ lens, const int32_t *__restrict__ anchor, long long n, slr_bc_result *__restrict__ out)
+                 const int32_t *__restrict__ lens, const int32_t *__restrict__ anchor, long long n, slr_bc_result *__restrict__ out,
+                 unsigned long long *__restrict__ work)
 {
     __shared__ WarpShared smem[WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31;
@@ -136,7 +138,13 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
     const long long nwarps = (long long)gridDim.x * WARPS_PER_BLOCK;
     const int noff = 2 * plusminus + 1;
 
-    for (long long read = (long long)blockIdx.x * WARPS_PER_BLOCK + wib; read < n; read += nwarps) {
+    // Work distribution: the cost of a read varies by an order of magnitude (none / one / all ED-2 searches), so a static stride
+    // leaves a long tail; warps take batches of READ_BATCH reads from a device counter instead (first batch: static).
+    long long batch0 = ((long long)blockIdx.x * WARPS_PER_BLOCK + wib) * READ_BATCH;
+    for (;;) {
+    if (batch0 >= n) break;
+    const long long batch1 = batch0 + READ_BATCH < n ? batch0 + READ_BATCH : n;
+    for (long long read = batch0; read < batch1; read++) {
         // ---- the slice: lane i owns char i; bit planes by ballot --------------------------------------------
         const int len = lens ? min(lens[read], slice_len) : slice_len;
         const uint32_t ch = (lane < len) ? (uint32_t)slices[read * (long long)stride + lane] : 0u;
@@ -317,11 +325,16 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
         }
         __syncwarp();
     }
+    unsigned long long nb = 0;
+    if (lane == 0) nb = atomicAdd(work, (unsigned long long)READ_BATCH);
+    batch0 = (long long)__shfl_sync(FULL, nb, 0) + nwarps * READ_BATCH;
+    }
 }
 
 template <int EDMAX>
 cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, int need_post, const uint8_t *d_slices, int stride, int slice_len,
-                     const int32_t *d_lens, const int32_t *d_anchor, long long n, slr_bc_result *d_out, cudaStream_t stream)
+                     const int32_t *d_lens, const int32_t *d_anchor, long long n, slr_bc_result *d_out, unsigned long long *d_work,
+                     cudaStream_t stream)
 {
     static int resident_ctas[64];                                // per device: #SMs x resident CTAs per SM
     int dev = 0;
@@ -336,11 +349,11 @@ cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, int
         if (e != cudaSuccess) return e;
         resident_ctas[dev] = sms * (bps > 0 ? bps : 1);
     }
-    const long long need = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const long long need = (n + WARPS_PER_BLOCK * READ_BATCH - 1) / (WARPS_PER_BLOCK * READ_BATCH);
     const long long resident = resident_ctas[dev];               // one wave of persistent CTAs: a multiple of the SM count
     const unsigned blocks = (unsigned)(need < resident ? need : resident);
     bc_assign_kernel<EDMAX><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens,
-                                                                        d_anchor, n, d_out);
+                                                                        d_anchor, n, d_out, d_work);
     return cudaGetLastError();
 }
 
@@ -348,13 +361,15 @@ cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, int
 
 cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, int need_post, const uint8_t *d_slices,
                                  int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, long long n,
-                                 slr_bc_result *d_out, cudaStream_t stream)
+                                 slr_bc_result *d_out, unsigned long long *d_work, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
+    cudaError_t e0 = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);      // the work counter of this launch
+    if (e0 != cudaSuccess) return e0;
     switch (ed_max) {
-    case 0: return launch_t<0>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
-    case 1: return launch_t<1>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
-    case 2: return launch_t<2>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, stream);
+    case 0: return launch_t<0>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, d_work, stream);
+    case 1: return launch_t<1>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, d_work, stream);
+    case 2: return launch_t<2>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor, n, d_out, d_work, stream);
     default: return cudaErrorInvalidValue;
     }
 }

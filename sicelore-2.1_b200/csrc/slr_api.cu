@@ -64,7 +64,12 @@ struct Slot {
 
 }  // namespace
 
+constexpr unsigned WORK_COUNTERS = 4096;       // one 8-byte work counter per kernel launch in flight, handed out round-robin
+
 struct slr_ctx {
+    unsigned long long *d_work = nullptr;
+    std::atomic<unsigned> next_work{0};
+    unsigned long long *work_counter() { return d_work + next_work.fetch_add(1) % WORK_COUNTERS; }
     int device = 0;
     int n_slots = 1;
     std::vector<Slot *> slots;
@@ -104,6 +109,8 @@ int slr_ctx_create(int device, int n_streams, slr_ctx **out)
         return fail(SLR_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     slr_ctx *c = new slr_ctx();
     c->device = device;
+    e = cudaMalloc((void **)&c->d_work, WORK_COUNTERS * sizeof(unsigned long long));
+    if (e != cudaSuccess) { delete c; return fail(SLR_E_NOMEM, "cudaMalloc(work counters): %s", cudaGetErrorString(e)); }
     c->n_slots = n_streams < 1 ? 1 : (n_streams > 64 ? 64 : n_streams);
     for (int i = 0; i < c->n_slots; i++) {
         Slot *s = new Slot();
@@ -132,6 +139,7 @@ void slr_ctx_destroy(slr_ctx *c)
         if (s->uscr_free) cudaEventDestroy(s->uscr_free);
         delete s;
     }
+    cudaFree(c->d_work);
     delete c;
 }
 
@@ -229,7 +237,7 @@ static int bc_assign_dev_impl(slr_ctx *ctx, const slr_bc_table *t, int ed_max, i
     for (int64_t off = 0; off < n; off += (1LL << 30)) {           // grid.x limit: 2^31-1 blocks of 8 reads
         const int64_t m = (n - off) < (1LL << 30) ? (n - off) : (1LL << 30);
         CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, d_slices + off * stride, stride, slice_len,
-                                      d_lens ? d_lens + off : nullptr, d_anchor + off, m, d_out + off, (cudaStream_t)stream));
+                                      d_lens ? d_lens + off : nullptr, d_anchor + off, m, d_out + off, ctx->work_counter(), (cudaStream_t)stream));
         g_launches++;
     }
     return SLR_OK;
@@ -275,7 +283,7 @@ static int bc_assign_host_impl(slr_ctx *ctx, const slr_bc_table *t, int ed_max, 
         if (lens) CUDA_TRY(cudaMemcpyAsync(s->lens[b].p, lens + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, (const uint8_t *)s->slices[b].p, stride, slice_len,
                                       lens ? (const int32_t *)s->lens[b].p : nullptr, (const int32_t *)s->anchor[b].p, m,
-                                      (slr_bc_result *)s->out[b].p, st));
+                                      (slr_bc_result *)s->out[b].p, ctx->work_counter(), st));
         g_launches++;
         CUDA_TRY(cudaMemcpyAsync(out + off, s->out[b].p, (size_t)m * sizeof(slr_bc_result), cudaMemcpyDeviceToHost, st));
     }

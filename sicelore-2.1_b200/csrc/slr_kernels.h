@@ -8,7 +8,7 @@
 // need_post = 0: exact lookup of the window only (pass-1 used-barcode counting), no post sequence is taken
 cudaError_t slr_launch_bc_assign(const SlrTableDev &tab, int ed_max, int plusminus, int three_prime, int need_post, const uint8_t *d_slices,
                                  int stride, int slice_len, const int32_t *d_lens, const int32_t *d_anchor, long long n,
-                                 slr_bc_result *d_out, cudaStream_t stream);
+                                 slr_bc_result *d_out, unsigned long long *d_work, cudaStream_t stream);   // d_work: 8 bytes, this launch's own
 
 // d_scratch: slr_umi_scratch_bytes(n_reads) bytes of device memory (8-byte aligned) that stay untouched until the launch
 // has finished on `stream`; three kernels are enqueued (SLR_UMI_LAUNCHES)
