@@ -165,6 +165,74 @@ int  slr_umi_dist_dev(slr_ctx *ctx, const uint8_t *d_umis, int stride, int umi_l
                       int64_t n_jobs, int64_t n_reads, int32_t *d_out, const int64_t *d_out_offsets,
                       int64_t n_out, void *stream);
 
+/* ---- S4: Illumina-guided barcode / UMI search ------------------------------------------------- */
+
+/* Replaces, for a batch of reads, the offset loop of IlluminaUMIanalyzer.findUMI (F!com/rw/umifinder/analyzers/
+ * IlluminaUMIanalyzer.class, IlluminaUMIanalyzer.java:L89-L136) or of IlluminaBarcodeAnalyzer.testBarcodes (F!…/
+ * IlluminaBarcodeAnalyzer.class, IlluminaBarcodeAnalyzer.java:L272-L304) — one BCUMIEDtesterBase.matchesSeqEditDistance run
+ * per offset (F!com/rw/nuc/encoding/TwoBit/ed/BCUMIEDtesterBase.class, BCUMIEDtesterBase.java:L82-L203) with the
+ * checkMatchWithTestSets of UMInucTwoBitPerBaseEDtester (…java:L52-L67) or BCnucTwoBitPerBaseEDtester (…java:L72-L92) — and
+ * the sorted().distinct() reduction of the collected list (IlluminaBarcodeUMIAnalyzerBase.getBestAndSecondBCorUMI,
+ * …java:L52-L60; testBarcodes L336-L339).  The host keeps the Needleman alignment of the two survivors and all flags. */
+typedef struct slr_guided_sets slr_guided_sets;    /* device-resident candidate sets */
+
+#define SLR_G_W_GENE  1u   /* entry (or an ancestor node) was found in the per-gene list: BARCODE_FOUND_FOR_GENE_OR_GENOMIC_REGION */
+#define SLR_G_W_ALL   2u   /* BC_ONLY_FOUND_IN_ALL_PASSED_10xBCs */
+#define SLR_G_W_EMPTY 4u   /* BC_IN_EMPTY_DROPS */
+#define SLR_G_EXCEPTION 1u /* the Java would have thrown for this read (N in a window, non-IUPAC char, slice too short) */
+
+typedef struct {
+    uint64_t seq[2];       /* sequences of the first two entries of the sorted, distinct match list (2-bit packed) */
+    int8_t   n_sub[2], n_ins[2], n_del[2], offset[2];   /* nSubstitutions / nInsertions / nDeletions / startOffsetFromPredicted */
+    uint8_t  where[2];     /* SLR_G_W_* bits of findingErrorFlag (0 in the UMI flavour) */
+    uint8_t  n_distinct;   /* min(size of the distinct list, 2): 0 = UMI_NOT_FOUND / no hit, 2 = a second-best match exists */
+    uint8_t  flags;        /* SLR_G_EXCEPTION */
+    int32_t  n_raw;        /* size of the raw list (matchLList.size()) */
+    int32_t  min_err_gene; /* min getNErrors() over entries with the GENE bit (testBarcodes L312-L313), INT32_MAX = none */
+    int32_t  pad;
+} slr_guided_result;       /* 40 bytes */
+
+typedef struct {
+    uint64_t seq;
+    int8_t   n_sub, n_ins, n_del, offset;
+    uint8_t  where;        /* SLR_G_W_* */
+    uint8_t  level;        /* currentlevel of the probed node */
+    uint16_t pad;
+} slr_guided_hit;          /* 16 bytes: one entry of the raw list, in list order */
+
+/* Candidate sets.  group_keys / group_offsets: CSR of the groups (UMI flavour: the UMIs of one (gene, cell) =
+ * IlluminaOneGeneOneCellData; BC flavour: the cell barcodes of one gene or genomic region = BarcodesMap), 2-bit packed.
+ * BC flavour only: all_keys = All10xselectedCells searched while currentlevel <= all_ed (maxEDtoCheckBCAll10xBCs), NULL when
+ * checkAllassignedBarcodes is false; empty_keys = EmptyDropBarcodes searched while currentlevel <= empty_ed
+ * (maxEDtoCheckBCEmptyDrops), NULL when checkEmptyDrops is false.  seq_len = umi_length or cell_bc_length (<= 16). */
+int  slr_guided_sets_create(slr_ctx *ctx, const uint64_t *group_keys, const int64_t *group_offsets, int64_t n_groups,
+                            const uint64_t *all_keys, int64_t n_all, int all_ed, const uint64_t *empty_keys, int64_t n_empty,
+                            int empty_ed, int bc_flavour, int seq_len, slr_guided_sets **out);
+void slr_guided_sets_destroy(slr_guided_sets *s);
+
+/*   plusminus  umi_posplusminus / bc_posplusminus: offsets 0,-1,+1,… in that order
+ *   post_len   bases handed to the tester as postUMIseq / postBCseq (UMI: ed + posplusminus + 2, the caller pads a short read
+ *              with 'A' like findUMI L118-L124; BC: 10), ed + 1 <= post_len, seq_len + post_len <= 32
+ *   bailout    umi_bailout_afterED / cell_BC_bailout_after_ED, < 0 = null
+ *   slices     n * stride bytes, ASCII, STRANDED orientation (getSeqRevComp for 3' reads); window of offset i =
+ *              slice[anchor+i, +seq_len), its post sequence the post_len bases that follow; slice_len <= 32
+ *   group_id   candidate group of read i (out of range = no group: BC flavour searches only the global lists)
+ *   ed         per read: maxEDdyn (slr_dyn_max_ed) or the fixed edit distance, 0..4
+ *   raw_out    optional (NULL): the first raw_cap entries of every read's raw list, n * raw_cap records */
+int  slr_guided_match(slr_ctx *ctx, const slr_guided_sets *s, int plusminus, int post_len, int bailout, const uint8_t *slices,
+                      int stride, int slice_len, const int32_t *anchor, const int32_t *group_id, const int32_t *ed, int64_t n,
+                      slr_guided_result *out, slr_guided_hit *raw_out, int raw_cap);
+int  slr_guided_match_dev(slr_ctx *ctx, const slr_guided_sets *s, int plusminus, int post_len, int bailout,
+                          const uint8_t *d_slices, int stride, int slice_len, const int32_t *d_anchor, const int32_t *d_group_id,
+                          const int32_t *d_ed, int max_ed, int64_t n, slr_guided_result *d_out, slr_guided_hit *d_raw_out,
+                          int raw_cap, void *stream);
+
+/* DynamicEditDistances.getmaxED (F!com/rw/parameters/DynamicEditDistances.class, DynamicEditDistances.java:L93-L98): the largest
+ * edit distance e whose max_candidates[e] >= count * (2 * plusminus + 1), capped at `cap` (< 0 = null).  max_candidates = one
+ * <errorpercent> column of bcMaxEditDistances.xml / umiMaxEditDistances.xml.  Returns -1 when no entry qualifies (the Java
+ * throws NoSuchElementException).  Pure host arithmetic. */
+int  slr_dyn_max_ed(const int64_t *max_candidates, int n_ed, int count, int plusminus, int cap);
+
 /* ---- misc ------------------------------------------------------------------------------------------- */
 const char *slr_last_error(void);
 int  slr_abi_version(void);

@@ -164,3 +164,41 @@ def umi_matrix_batch(umis, job_offsets, umi_len=12, n_threads=0):
     lib().orc_umi_matrix_batch(umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(sizes),
                                out.ctypes.data, out_offsets.ctypes.data, n_threads)
     return out, out_offsets
+
+
+# ---- Illumina-guided search -------------------------------------------------------------------------
+GUIDED_HIT = np.dtype([("seq", "<u8"), ("n_sub", "i1"), ("n_ins", "i1"), ("n_del", "i1"), ("offset", "i1"), ("where", "u1"),
+                       ("level", "u1"), ("pad", "<u2")], align=True)
+assert GUIDED_HIT.itemsize == 16
+GUIDED_RESULT = np.dtype([("seq", "<u8", (2,)), ("n_sub", "i1", (2,)), ("n_ins", "i1", (2,)), ("n_del", "i1", (2,)),
+                          ("offset", "i1", (2,)), ("where", "u1", (2,)), ("n_distinct", "u1"), ("flags", "u1"), ("n_raw", "<i4"),
+                          ("min_err_gene", "<i4"), ("pad", "<i4")], align=True)
+assert GUIDED_RESULT.itemsize == 40
+W_GENE, W_ALL, W_EMPTY, G_EXCEPTION = 1, 2, 4, 1
+
+
+def guided_batch(group_keys, group_offsets, slices, anchor, group_id, ed, length, plusminus, post_len, bailout=-1,
+                 bc_flavour=False, all_keys=None, all_ed=0, empty_keys=None, empty_ed=0, slice_len=None, raw_cap=0, n_threads=0):
+    """orc_guided_batch.  Returns (GUIDED_RESULT[n], raw GUIDED_HIT[n, raw_cap] or None, probes)."""
+    L = lib()
+    L.orc_guided_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int]
+    gk = np.ascontiguousarray(group_keys, dtype=np.uint64)
+    go = np.ascontiguousarray(group_offsets, dtype=np.int64)
+    slices = np.ascontiguousarray(slices, dtype=np.uint8)
+    anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+    gid = np.ascontiguousarray(group_id, dtype=np.int32)
+    n, stride = slices.shape
+    edv = np.ascontiguousarray(np.broadcast_to(np.asarray(ed, dtype=np.int32), (n,)))
+    ak = None if all_keys is None else np.ascontiguousarray(all_keys, dtype=np.uint64)
+    ek = None if empty_keys is None else np.ascontiguousarray(empty_keys, dtype=np.uint64)
+    out = np.zeros(n, dtype=GUIDED_RESULT)
+    raw = np.zeros((n, raw_cap), dtype=GUIDED_HIT) if raw_cap else None
+    probes = C.c_int64(0)
+    L.orc_guided_batch(gk.ctypes.data, go.ctypes.data, len(go) - 1, None if ak is None else ak.ctypes.data, 0 if ak is None else len(ak),
+                       all_ed, None if ek is None else ek.ctypes.data, 0 if ek is None else len(ek), empty_ed, int(bc_flavour), length,
+                       plusminus, bailout, post_len, slices.ctypes.data, stride, stride if slice_len is None else slice_len,
+                       anchor.ctypes.data, gid.ctypes.data, edv.ctypes.data, n, out.ctypes.data,
+                       None if raw is None else raw.ctypes.data, raw_cap, C.byref(probes), n_threads)
+    return out, raw, probes.value

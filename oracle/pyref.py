@@ -418,3 +418,195 @@ def umi_best9(a, b, umi_len=12):
             if eds[i][v] < best[0]:
                 best = (eds[i][v], i, v)
     return _i32((best[0] & 0xFFFFFF) | (0x08000000 << best[1]) | (0x01000000 << best[2]))
+
+
+# =====================================================================================================
+# Illumina-guided search: BCUMIEDtesterBase + UMInuc/BCnuc testers + the consumers' reduction.
+# Written object-for-object: one Python object per Java object, the matchingList holds the very objects the Java
+# list holds (so the aliasing of the root node and the flag inheritance through the copy constructor are real).
+# =====================================================================================================
+FLAG_GENE, FLAG_ALL, FLAG_EMPTY = 1, 2, 4        # stand-ins for the BarcodeFindingFlag bits the tester sets
+FOURBIT_TO_TWOBIT = [0] * 15                     # NucleicAcidInmutableOneBytePerBase.java:L29-L37
+for _ch in "AGCT":
+    FOURBIT_TO_TWOBIT[ENCODE[ord(_ch)]] = BASE_TO_TWOBIT[ord(_ch)]
+
+
+class GuidedNode:
+    """LongSeqMutated incl. the NucTwoBitPerBaseWithErrors fields the guided mode uses (findingErrorFlag)."""
+    __slots__ = ("seq", "L", "nSub", "nIns", "nDel", "offset", "posPrev", "posCur", "level", "flag")
+
+    def __init__(self, seq, L, level, offset):                # LongSeqMutated.java:L61 (nDeletions 0, pos -1/-1)
+        self.seq, self.L, self.offset, self.level = seq, L, offset, level
+        self.nSub = self.nIns = self.nDel = 0
+        self.posPrev = self.posCur = -1
+        self.flag = 0
+
+    def copy(self):                                           # LongSeqMutated.java:L68-L77 + NucTwoBitPerBaseWithErrors.java:L46-L56
+        c = GuidedNode(self.seq, self.L, self.level, self.offset)
+        c.nSub, c.nIns, c.nDel = self.nSub, self.nIns, self.nDel
+        c.posPrev, c.posCur = self.posPrev, self.posCur
+        c.flag = self.flag                                    # L55: findingErrorFlag is copied
+        return c
+
+    def n_errors(self):                                       # getNErrors java:L100
+        return self.nDel + self.nIns + self.nSub
+
+
+class GuidedTester:
+    """BCUMIEDtesterBase with either checkMatchWithTestSets flavour.
+    umis: set (UMI flavour) — or gene/all/empty sets (BC flavour, gene may be None)."""
+
+    def __init__(self, ed, L, post4, bailout=None, umis=None, gene=None, all_bcs=None, all_ed=0, empty=None, empty_ed=0,
+                 bc_flavour=False, allow_indels=True):
+        self.ed, self.L, self.post4, self.bailout, self.allow_indels = ed, L, post4, bailout, allow_indels
+        self.umis, self.gene, self.all_bcs, self.all_ed, self.empty, self.empty_ed = umis, gene, all_bcs, all_ed, empty, empty_ed
+        self.bc_flavour = bc_flavour
+        self.matching = []                                    # BCUMIEDtesterBase.java:L53
+        self.deque = deque()                                  # NucTwoBitPerBaseEDtesterBase.java:L62
+        # ctor L82-L95: Optional<Boolean> use64bitHash
+        if L >= 14 and ed >= 2:
+            self.use64 = L > 16
+        elif L < 14 and ed >= 2:
+            self.use64 = False
+        else:
+            self.use64 = None
+        self.tested = set()
+        self.probes = 0
+
+    def add_tested(self, seq):                                # L105-L112
+        if self.use64 is not None:
+            self.tested.add(seq if self.use64 else seq & 0xFFFFFFFF)
+
+    def already_tested(self, seq):                            # L120
+        if self.use64 is None:
+            return False
+        return (seq if self.use64 else seq & 0xFFFFFFFF) in self.tested
+
+    def check(self, node):
+        if not self.bc_flavour:                               # UMInucTwoBitPerBaseEDtester.java:L60-L62
+            self.probes += 1
+            return node if node.seq in self.umis else None
+        # BCnucTwoBitPerBaseEDtester.java:L72-L92
+        if self.gene is not None:
+            self.probes += 1
+            if node.seq in self.gene:
+                node.flag |= FLAG_GENE                        # L76: on the node itself
+                return node
+        if self.all_bcs is not None and node.level <= self.all_ed:
+            self.probes += 1
+            if node.seq in self.all_bcs:
+                es = node.copy()                              # L80: new NucTwoBitPerBaseWithErrors(seq)
+                es.flag |= FLAG_ALL
+                return es
+        if self.empty is not None and node.level <= self.empty_ed:
+            self.probes += 1
+            if node.seq in self.empty:
+                es = node.copy()
+                es.flag |= FLAG_EMPTY
+                return es
+        return None
+
+    def go_next(self, node):                                  # NucTwoBitPerBaseEDtesterBase.java:L133-L144
+        if self.ed > node.level:
+            if self.bailout is None or node.level < self.bailout or not self.matching:
+                d = node.copy()
+                d.posPrev = node.posCur
+                d.posCur = -1
+                d.level = node.level + 1
+                self.deque.append(d)
+
+    def run(self, seq, offset):                               # matchesSeqEditDistance BCUMIEDtesterBase.java:L82-L124
+        L = self.L
+        parent = GuidedNode(seq, L, 1, offset)                # L82: (seq, nDeletions 0, currentlevel 1, offset)
+        r = self.check(parent)
+        if r is not None:
+            self.matching.append(r)
+        if self.ed == 0:
+            return self.matching
+        self.deque.append(parent)
+        while self.deque:
+            cur = self.deque.pop()                            # pollLast
+            cur.posCur += 1
+            if cur.posCur < L - 1:
+                self.deque.append(cur.copy())
+            if cur.posPrev == cur.posCur:
+                continue
+            for s in replace_deg(cur.seq, cur.posCur, L):     # substitutions L136-L151
+                if s != cur.seq and not self.already_tested(s):
+                    m = cur.copy()
+                    m.nSub += 1
+                    m.seq = s
+                    r = self.check(m)
+                    if r is not None:
+                        self.matching.append(r)
+                    self.go_next(m)
+            if self.allow_indels:
+                if cur.posCur < L - 1:                        # insertions L161-L175
+                    for s in insert_deg(cur.seq, cur.posCur, L):
+                        if not self.already_tested(s):
+                            m = cur.copy()
+                            m.seq = s
+                            m.nDel += 1
+                            r = self.check(m)
+                            if r is not None:
+                                self.matching.append(r)
+                            self.go_next(m)
+                if cur.nDel + 1 <= len(self.post4):           # deletions L187-L203
+                    code = self.post4[cur.nDel]               # getByteAt(nDeletions+1)
+                    s = delete_byte(cur.seq, code, cur.posCur, L)
+                    if not self.already_tested(s):
+                        m = cur.copy()
+                        m.seq = s
+                        m.nIns += 1
+                        r = self.check(m)
+                        if r is not None:
+                            self.matching.append(r)
+                        self.go_next(m)
+            self.add_tested(cur.seq)
+        return self.matching
+
+
+def score_where_found(flag):                                  # BarcodeFindingFlag.java:L119-L131
+    if flag & FLAG_GENE:
+        return 3
+    if flag & FLAG_ALL:
+        return 2
+    if flag & FLAG_EMPTY:
+        return 1
+    return 0
+
+
+def guided_query(slice_ascii, anchor, L, ed, plusminus, post_len, bailout=None, bc_flavour=False, **sets):
+    """Offset loop of findUMI / testBarcodes + sorted().distinct() of getBestAndSecondBCorUMI.
+    Returns (raw list of dicts, sorted distinct list of dicts).  Raises JavaException like the Java would."""
+    raw = []
+    for i in sorted(range(-plusminus, plusminus + 1), key=abs):          # stable: 0,-1,1,-2,2
+        ws = anchor + i
+        if ws < 0 or ws + L + post_len > len(slice_ascii):
+            raise JavaException("getSubSequence out of range")
+        codes = []
+        for ch in slice_ascii[ws:ws + L + post_len]:
+            c = ENCODE[ch] if ch < 254 else -1
+            if c < 0:
+                raise JavaException("unknown base")
+            codes.append(c)
+        w = 0
+        for c in codes[:L]:                                              # getLongHashForBytes T!...java:L197-L201
+            if c >= 15:
+                raise JavaException("AIOOBE FOURBIT_TO_TWOBIT_MATRIX")
+            w = (_shl(w, 2) | FOURBIT_TO_TWOBIT[c]) & M64
+        t = GuidedTester(ed, L, codes[L:], bailout=bailout, bc_flavour=bc_flavour, **sets)
+        raw.extend(t.run(w, i))
+    as_dict = lambda n: dict(seq=n.seq, n_sub=n.nSub, n_ins=n.nIns, n_del=n.nDel, offset=n.offset, where=n.flag, level=n.level)
+    lst = raw
+    if len(raw) > 1:
+        if bc_flavour:
+            key = lambda n: (n.n_errors(), score_where_found(n.flag), abs(n.offset))
+        else:
+            key = lambda n: (n.n_errors(), abs(n.offset))
+        lst, seen = [], set()
+        for n in sorted(raw, key=key):                                   # list.sort / Stream.sorted are stable, like Python's
+            if n.seq not in seen:
+                seen.add(n.seq)
+                lst.append(n)
+    return [as_dict(n) for n in raw], [as_dict(n) for n in lst]

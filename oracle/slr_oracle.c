@@ -714,3 +714,268 @@ void orc_umi_matrix_batch(const uint8_t *umis, int stride, int umi_len, const in
         orc_umi_matrix(umis + s * stride, stride, umi_len, n, out + out_offsets[j]);
     }
 }
+
+/* ================================================================================================
+ * Illumina-guided search engine
+ * F!com/rw/nuc/encoding/TwoBit/ed/BCUMIEDtesterBase (BCUMIEDtesterBase.java:L82-L203) on top of
+ * NucTwoBitPerBaseEDtesterBase (visited set L82-L120, goNextEDlevel with bailout L133-L144).
+ * Differences from BarcodeMatchTester.doJob that matter: the root is created with currentlevel 1 (L82,
+ * LongSeqMutated.java:L61), every hit is appended to an ArrayList (no first-wins collapse, L88-L89, L145-L146),
+ * goNextEDlevel is always called (L148, L172, L201), deletions also run at the last position (L113-L119) and
+ * need a non-null post sequence (L187-L190).
+ * ============================================================================================== */
+typedef struct {
+    uint64_t seq;
+    int16_t pos_prev, pos_cur, level;
+    int8_t  n_sub, n_ins, n_del;
+    uint8_t inh;             /* findingErrorFlag of the node: GENE bit, copied by the copy constructor (NucTwoBitPerBaseWithErrors.java:L55) */
+} gnode;
+
+typedef struct {
+    const orc_guided_sets *sets;
+    int len, ed, allow_indels, bailout, offset;
+    const uint8_t *post4; int post_len;
+    vset visited;
+    gnode *stack; int sp, scap;
+    orc_guided_hit *out; int64_t cap, n_out;
+    int64_t probes;
+    int exception;
+} gtester;
+
+static void gpush(gtester *t, const gnode *n)
+{
+    if (t->sp == t->scap) {
+        t->scap = t->scap ? t->scap * 2 : 64;
+        t->stack = (gnode *)realloc(t->stack, (size_t)t->scap * sizeof(gnode));
+    }
+    t->stack[t->sp++] = *n;
+}
+
+static void glist_add(gtester *t, const gnode *n, unsigned where)
+{
+    if (t->n_out < t->cap) {
+        orc_guided_hit *h = &t->out[t->n_out];
+        memset(h, 0, sizeof(*h));
+        h->seq = n->seq; h->n_sub = n->n_sub; h->n_ins = n->n_ins; h->n_del = n->n_del;
+        h->offset = (int8_t)t->offset; h->where = (uint8_t)where; h->level = (uint8_t)n->level;
+    }
+    t->n_out++;
+}
+
+/* checkMatchWithTestSets + matchingList.add.  UMI flavour (UMInucTwoBitPerBaseEDtester.java:L52-L67, useShortenedUMI is
+ * false at the only call site, IlluminaUMIanalyzer.java:L126): umis.contains(seq).  BC flavour
+ * (BCnucTwoBitPerBaseEDtester.java:L72-L92): gene set at any level -> the NODE ITSELF gets the GENE bit (L76, inherited by
+ * every descendant); else all-passed list while currentlevel <= allPassed10xBCsED (L79-L83); else empty drops while
+ * currentlevel <= outOfCellsBarcodesED (L85-L89); the two latter return a COPY (flag stays off the node). */
+static void gcheck(gtester *t, gnode *n)
+{
+    const orc_guided_sets *s = t->sets;
+    if (s->group) {
+        t->probes++;
+        if (orc_set_find(s->group, n->seq) >= 0) {
+            if (s->bc_flavour) n->inh = 1;                             /* L76: seq.findingErrorFlag |= GENE */
+            glist_add(t, n, n->inh ? ORC_W_GENE : 0u);
+            return;
+        }
+    }
+    if (s->all && n->level <= s->all_ed) {
+        t->probes++;
+        if (orc_set_find(s->all, n->seq) >= 0) { glist_add(t, n, (n->inh ? ORC_W_GENE : 0u) | ORC_W_ALL); return; }
+    }
+    if (s->empty && n->level <= s->empty_ed) {
+        t->probes++;
+        if (orc_set_find(s->empty, n->seq) >= 0) { glist_add(t, n, (n->inh ? ORC_W_GENE : 0u) | ORC_W_EMPTY); return; }
+    }
+}
+
+/* goNextEDlevel (NucTwoBitPerBaseEDtesterBase.java:L133-L144): no push once level >= bailout and the list is non-empty */
+static void ggo_next(gtester *t, const gnode *n)
+{
+    if (t->ed > n->level) {
+        if (t->bailout < 0 || n->level < t->bailout || t->n_out == 0) {
+            gnode c = *n;
+            c.pos_prev = n->pos_cur;
+            c.pos_cur = -1;
+            c.level = (int16_t)(n->level + 1);
+            gpush(t, &c);
+        }
+    }
+}
+
+int64_t orc_guided_tester(const orc_guided_sets *sets, uint64_t seq, int len, int ed, int allow_indels, const uint8_t *post4,
+                          int post_len, int bailout, int offset, orc_guided_hit *out, int64_t cap, int64_t *n_probes)
+{
+    gtester t;
+    memset(&t, 0, sizeof(t));
+    t.sets = sets; t.len = len; t.ed = ed; t.allow_indels = allow_indels; t.bailout = bailout; t.offset = offset;
+    t.post4 = post4; t.post_len = post_len; t.out = out; t.cap = cap;
+    vset_init(&t.visited, ed, len);        /* ctor L82-L95: active iff ed >= 2; int keys for len <= 16 */
+
+    gnode parent;
+    memset(&parent, 0, sizeof(parent));
+    parent.seq = seq; parent.pos_prev = -1; parent.pos_cur = -1; parent.level = 1;     /* L82 */
+    gcheck(&t, &parent);                                                                /* L86-L89 */
+    if (ed != 0) {                                                                      /* L91-L92 */
+        gpush(&t, &parent);                                                             /* L94 */
+        const int len_m1 = len - 1;                                                     /* L96 */
+        uint64_t mut[4];
+        while (t.sp > 0 && !t.exception) {
+            gnode cur = t.stack[--t.sp];                                                /* pollLast (L100) */
+            cur.pos_cur++;                                                              /* L104 */
+            if (cur.pos_cur < len_m1) gpush(&t, &cur);                                  /* L105-L106 */
+            if (cur.pos_prev == cur.pos_cur) continue;                                  /* L109-L110 */
+            /* substitutions (L136-L151) */
+            orc_replace_deg(cur.seq, mut, cur.pos_cur, len);
+            for (int i = 0; i < 4; i++) {
+                if (mut[i] != cur.seq && !vset_contains(&t.visited, mut[i])) {          /* L138-L139 */
+                    gnode n = cur; n.n_sub++; n.seq = mut[i];
+                    gcheck(&t, &n);
+                    ggo_next(&t, &n);                                                   /* L148 */
+                }
+            }
+            if (allow_indels) {                                                         /* L113 */
+                if (cur.pos_cur < len_m1) {                                             /* L115: insertions only */
+                    orc_insert_deg(cur.seq, mut, cur.pos_cur, len);
+                    for (int i = 0; i < 4; i++) {
+                        if (!vset_contains(&t.visited, mut[i])) {                       /* L163 */
+                            gnode n = cur; n.seq = mut[i]; n.n_del++;                   /* L165-L166 */
+                            gcheck(&t, &n);
+                            ggo_next(&t, &n);                                           /* L172 */
+                        }
+                    }
+                }
+                /* deletions (L187-L203), also at the last position */
+                if (cur.n_del + 1 <= post_len) {                                        /* L187-L188 */
+                    int code = post4[cur.n_del];                                        /* getByteAt(nDeletions + 1), 1-based (L190) */
+                    if (code > 15) { t.exception = 1; break; }                          /* BYTE_TO_2BITLONG_ARRAY[0][-1] -> AIOOBE */
+                    uint64_t m = orc_delete_byte(cur.seq, code, cur.pos_cur, len);
+                    if (!vset_contains(&t.visited, m)) {                                /* L192 */
+                        gnode n = cur; n.seq = m; n.n_ins++;                            /* L194-L195 */
+                        gcheck(&t, &n);
+                        ggo_next(&t, &n);                                               /* L201 */
+                    }
+                }
+            }
+            vset_add(&t.visited, cur.seq);                                              /* L122 */
+        }
+    }
+    if (n_probes) *n_probes += t.probes;
+    vset_free(&t.visited);
+    free(t.stack);
+    return t.exception ? -1 : t.n_out;
+}
+
+/* BarcodeFindingFlag.scoreWhereFound (BarcodeFindingFlag.java:L119-L131); GENE_NOT_FOUND_IN_ILLUMINA is never set by the tester */
+static int score_where(unsigned where)
+{
+    if (where & ORC_W_GENE) return 3;
+    if (where & ORC_W_ALL) return 2;
+    if (where & ORC_W_EMPTY) return 1;
+    return 0;
+}
+
+typedef struct { orc_guided_hit h; int64_t idx; int bc; } gsort_item;
+
+/* BCEditDistanceErrorComparator.compare (IlluminaBarcodeUMIAnalyzerBase.java:L106-L110) / EditDistanceErrorComparator
+ * (L143-L144); the original index makes qsort reproduce Stream.sorted's stable order */
+static int gsort_cmp(const void *pa, const void *pb)
+{
+    const gsort_item *a = (const gsort_item *)pa, *b = (const gsort_item *)pb;
+    int r = (a->h.n_del + a->h.n_ins + a->h.n_sub) - (b->h.n_del + b->h.n_ins + b->h.n_sub);
+    if (r == 0 && a->bc) r = score_where(a->h.where) - score_where(b->h.where);
+    if (r == 0) r = abs(a->h.offset) - abs(b->h.offset);
+    if (r == 0) r = a->idx < b->idx ? -1 : a->idx > b->idx ? 1 : 0;
+    return r;
+}
+
+void orc_guided_query(const orc_guided_sets *sets, int bc_flavour, int len, int ed, int plusminus, int bailout, int post_len,
+                      const uint8_t *slice, int slice_len, int anchor, orc_guided_result *out, orc_guided_hit *raw_out,
+                      int64_t raw_cap, int64_t *n_probes)
+{
+    memset(out, 0, sizeof(*out));
+    out->min_err_gene = INT32_MAX;
+    int64_t cap = 256, n = 0;
+    orc_guided_hit *list = (orc_guided_hit *)malloc((size_t)cap * sizeof(*list));
+    /* IntStream.rangeClosed(-pm, pm).boxed().sorted(comparingInt(Math::abs)) (IlluminaUMIanalyzer.java:L89-L91,
+     * IlluminaBarcodeAnalyzer.java:L272-L278): 0,-1,1,-2,2 */
+    for (int k = 0; k <= 2 * plusminus; k++) {
+        const int o = (k == 0) ? 0 : ((k & 1) ? -((k + 1) / 2) : (k / 2));
+        const int ws = anchor + o;
+        if (ws < 0 || ws + len + post_len > slice_len) goto exception;                  /* getSubSequence out of range */
+        uint64_t w = 0;
+        for (int i = 0; i < len; i++) {            /* new NucleicAcidTwoBitPerBase(bytes): getLongHashForBytes (T!...java:L197-L201) */
+            const int c = orc_encode4bit(slice[ws + i]);
+            if (c >= 15) goto exception;           /* unknown char; N = 15 indexes past FOURBIT_TO_TWOBIT_MATRIX[15] (AIOOBE) */
+            w = (w << 2) | (uint64_t)(c == 2 ? 1 : c == 4 ? 2 : c == 8 ? 3 : 0);       /* other IUPAC codes map to 0 */
+        }
+        uint8_t post4[32];
+        for (int i = 0; i < post_len && i < 32; i++) post4[i] = (uint8_t)orc_encode4bit(slice[ws + len + i]);
+        for (;;) {
+            int64_t r = orc_guided_tester(sets, w, len, ed, 1, post4, post_len, bailout, o, list + n, cap - n, n_probes);
+            if (r < 0) goto exception;
+            if (n + r <= cap) { n += r; break; }
+            cap = (n + r) * 2;                      /* list too small: grow and run this window again */
+            list = (orc_guided_hit *)realloc(list, (size_t)cap * sizeof(*list));
+        }
+    }
+    out->n_raw = (int32_t)n;
+    for (int64_t i = 0; i < n && raw_out && i < raw_cap; i++) raw_out[i] = list[i];
+    if (n > 0) {
+        gsort_item *it = (gsort_item *)malloc((size_t)n * sizeof(*it));
+        for (int64_t i = 0; i < n; i++) {
+            it[i].h = list[i]; it[i].idx = i; it[i].bc = bc_flavour;
+            if ((list[i].where & ORC_W_GENE) && list[i].n_sub + list[i].n_ins + list[i].n_del < out->min_err_gene)
+                out->min_err_gene = list[i].n_sub + list[i].n_ins + list[i].n_del;
+        }
+        if (n > 1) qsort(it, (size_t)n, sizeof(*it), gsort_cmp);                        /* L52-L56 (size() > 1 only) */
+        int nd = 0;
+        for (int64_t i = 0; i < n && nd < 2; i++) {                                     /* distinct(): equals = (sequence, seqlength) */
+            if (nd == 1 && it[i].h.seq == out->seq[0]) continue;
+            out->seq[nd] = it[i].h.seq; out->n_sub[nd] = it[i].h.n_sub; out->n_ins[nd] = it[i].h.n_ins;
+            out->n_del[nd] = it[i].h.n_del; out->offset[nd] = it[i].h.offset; out->where[nd] = it[i].h.where;
+            nd++;
+        }
+        out->n_distinct = (uint8_t)nd;
+        free(it);
+    }
+    free(list);
+    return;
+exception:
+    free(list);
+    memset(out, 0, sizeof(*out));
+    out->min_err_gene = INT32_MAX;
+    out->flags = ORC_G_EXCEPTION;
+}
+
+void orc_guided_batch(const uint64_t *group_keys, const int64_t *group_offsets, int64_t n_groups, const uint64_t *all_keys,
+                      int64_t n_all, int all_ed, const uint64_t *empty_keys, int64_t n_empty, int empty_ed, int bc_flavour, int len,
+                      int plusminus, int bailout, int post_len, const uint8_t *slices, int stride, int slice_len,
+                      const int32_t *anchor, const int32_t *group_id, const int32_t *ed, int64_t n, orc_guided_result *out,
+                      orc_guided_hit *raw_out, int64_t raw_cap, int64_t *n_probes_total, int n_threads)
+{
+    orc_set **gs = (orc_set **)calloc((size_t)(n_groups > 0 ? n_groups : 1), sizeof(orc_set *));
+    for (int64_t g = 0; g < n_groups; g++) {
+        const int64_t m = group_offsets[g + 1] - group_offsets[g];
+        if (m > 0) gs[g] = orc_set_new(group_keys + group_offsets[g], m);              /* isEmpty() -> null (L299) */
+    }
+    orc_set *all = all_keys ? orc_set_new(all_keys, n_all) : NULL;
+    orc_set *empty = empty_keys ? orc_set_new(empty_keys, n_empty) : NULL;
+    int64_t probes = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : probes)
+#endif
+    for (int64_t i = 0; i < n; i++) {
+        orc_guided_sets s;
+        s.group = (group_id[i] >= 0 && group_id[i] < n_groups) ? gs[group_id[i]] : NULL;
+        s.all = all; s.all_ed = all_ed; s.empty = empty; s.empty_ed = empty_ed; s.bc_flavour = bc_flavour;
+        int64_t p = 0;
+        orc_guided_query(&s, bc_flavour, len, ed[i], plusminus, bailout, post_len, slices + (size_t)i * stride, slice_len, anchor[i],
+                         &out[i], raw_out ? raw_out + i * raw_cap : NULL, raw_cap, &p);
+        probes += p;
+    }
+    if (n_probes_total) *n_probes_total += probes;
+    for (int64_t g = 0; g < n_groups; g++) orc_set_free(gs[g]);
+    free(gs);
+    orc_set_free(all); orc_set_free(empty);
+}

@@ -98,6 +98,65 @@ typedef struct {
 void orc_collide_batch(const orc_set *set, int ed, int bc_len, const uint64_t *queries, int64_t n, orc_collide_result *out,
                        int64_t *n_probes_total, int n_threads);
 
+/* ---------- Illumina-guided search engine ----------------------------------------------------------
+ * F!com/rw/nuc/encoding/TwoBit/ed/BCUMIEDtesterBase.matchesSeqEditDistance (BCUMIEDtesterBase.java:L82-L124, L136-L203),
+ * checkMatchWithTestSets of UMInucTwoBitPerBaseEDtester (java:L52-L67) and BCnucTwoBitPerBaseEDtester (java:L72-L92),
+ * goNextEDlevel with bailoutIfFoundAfterED (NucTwoBitPerBaseEDtesterBase.java:L133-L144), the offset loops of
+ * IlluminaUMIanalyzer.findUMI (java:L89-L136) / IlluminaBarcodeAnalyzer.testBarcodes (java:L272-L304) and the
+ * sorted().distinct() reduction of IlluminaBarcodeUMIAnalyzerBase.getBestAndSecondBCorUMI (java:L52-L60, comparators L106-L110, L143-L144). */
+#define ORC_W_GENE  1u    /* BarcodeFindingFlag.BARCODE_FOUND_FOR_GENE_OR_GENOMIC_REGION (own or inherited from an ancestor node) */
+#define ORC_W_ALL   2u    /* BC_ONLY_FOUND_IN_ALL_PASSED_10xBCs */
+#define ORC_W_EMPTY 4u    /* BC_IN_EMPTY_DROPS */
+
+typedef struct {
+    const orc_set *group;  /* UMI flavour: umis of the (gene, cell); BC flavour: cellBcsForGene (NULL when empty, java:L299) */
+    const orc_set *all;    /* allPassed10xBCs, NULL = checkAllassignedBarcodes false (UMI flavour: NULL) */
+    int all_ed;            /* maxEDtoCheckBCAll10xBCs */
+    const orc_set *empty;  /* outOfCellsBarcodes, NULL = checkEmptyDrops false or no empty-drop list */
+    int empty_ed;          /* maxEDtoCheckBCEmptyDrops */
+    int bc_flavour;        /* 1 = BCnucTwoBitPerBaseEDtester (a group hit puts the GENE bit on the node), 0 = UMInucTwoBitPerBaseEDtester */
+} orc_guided_sets;
+
+typedef struct {
+    uint64_t seq;                          /* the matching (mutated) sequence */
+    int8_t   n_sub, n_ins, n_del, offset;  /* counters as the Java names them; startOffsetFromPredicted */
+    uint8_t  where;                        /* ORC_W_* bits of findingErrorFlag */
+    uint8_t  level;                        /* currentlevel of the probed node (root: 1 with 0 errors) */
+    uint16_t pad;
+} orc_guided_hit;                          /* 16 bytes */
+
+/* one tester (one window): the matchingList in list order.  Returns its size (the first `cap` entries are stored),
+ * -1 if the Java would have thrown.  bailout < 0 = null.  post4: 4-bit codes (non-NULL in both callers). */
+int64_t orc_guided_tester(const orc_guided_sets *sets, uint64_t seq, int len, int ed, int allow_indels, const uint8_t *post4,
+                          int post_len, int bailout, int offset, orc_guided_hit *out, int64_t cap, int64_t *n_probes);
+
+#define ORC_G_EXCEPTION 1u
+typedef struct {
+    uint64_t seq[2];                       /* first two entries of the sorted, distinct list */
+    int8_t   n_sub[2], n_ins[2], n_del[2], offset[2];
+    uint8_t  where[2];
+    uint8_t  n_distinct;                   /* min(size of the distinct list, 2) */
+    uint8_t  flags;                        /* ORC_G_EXCEPTION */
+    int32_t  n_raw;                        /* size of the raw list over all offsets */
+    int32_t  min_err_gene;                 /* min getNErrors() over entries carrying the GENE bit (testBarcodes L312-L313), INT32_MAX none */
+    int32_t  pad;
+} orc_guided_result;                       /* 40 bytes, same layout as slr_guided_result */
+
+/* one query = one read against one candidate group: offsets 0,-1,+1,... (sorted by |i|, stable), window =
+ * slice[anchor+i, +len), post = slice[anchor+i+len, +post_len) (stranded orientation, ASCII), then the reduction.
+ * bc_flavour selects the comparator with scoreWhereFound.  raw_out (optional): first raw_cap entries of the raw list. */
+void orc_guided_query(const orc_guided_sets *sets, int bc_flavour, int len, int ed, int plusminus, int bailout, int post_len,
+                      const uint8_t *slice, int slice_len, int anchor, orc_guided_result *out, orc_guided_hit *raw_out,
+                      int64_t raw_cap, int64_t *n_probes);
+
+/* batch over queries (OpenMP).  group_keys/group_offsets: CSR of the candidate groups (2-bit packed), query i searches group
+ * group_id[i] at edit distance ed[i]; all_keys / empty_keys: the two global lists of the BC flavour (NULL = unused). */
+void orc_guided_batch(const uint64_t *group_keys, const int64_t *group_offsets, int64_t n_groups, const uint64_t *all_keys,
+                      int64_t n_all, int all_ed, const uint64_t *empty_keys, int64_t n_empty, int empty_ed, int bc_flavour, int len,
+                      int plusminus, int bailout, int post_len, const uint8_t *slices, int stride, int slice_len,
+                      const int32_t *anchor, const int32_t *group_id, const int32_t *ed, int64_t n, orc_guided_result *out,
+                      orc_guided_hit *raw_out, int64_t raw_cap, int64_t *n_probes_total, int n_threads);
+
 /* ---------- UMI distances (F!com/rw/clustering/ClusteringEditDistanceBase.java:L297-L350) ------ */
 int     orc_limited_compare(const uint8_t *left, int n, const uint8_t *right, int m, int threshold); /* apachemod/LevenshteinDistance.java:L220-L283 */
 int32_t orc_umi_best9(const uint8_t *a, const uint8_t *b, int umi_len);    /* a,b: umi_len+2 4-bit codes (window -1..+1) */

@@ -35,11 +35,18 @@ assert BC_RESULT.itemsize == 32
 COLLIDE_RESULT = np.dtype([("bc", "<u8", (2,)), ("valid", "u1"), ("n_sub", "u1", (2,)), ("n_ins", "u1", (2,)), ("n_del", "u1", (2,)),
                            ("pad", "u1")], align=True)
 assert COLLIDE_RESULT.itemsize == 24
+GUIDED_RESULT = np.dtype([("seq", "<u8", (2,)), ("n_sub", "i1", (2,)), ("n_ins", "i1", (2,)), ("n_del", "i1", (2,)),
+                          ("offset", "i1", (2,)), ("where", "u1", (2,)), ("n_distinct", "u1"), ("flags", "u1"), ("n_raw", "<i4"),
+                          ("min_err_gene", "<i4"), ("pad", "<i4")], align=True)
+assert GUIDED_RESULT.itemsize == 40
+GUIDED_HIT = np.dtype([("seq", "<u8"), ("n_sub", "i1"), ("n_ins", "i1"), ("n_del", "i1"), ("offset", "i1"), ("where", "u1"),
+                       ("level", "u1"), ("pad", "<u2")], align=True)
+assert GUIDED_HIT.itemsize == 16
 
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
-           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_last_error", "slr_abi_version",
-           "slr_launch_count"]
+           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
+           "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count"]
 
 
 class SiceloreGpuError(RuntimeError):
@@ -66,7 +73,7 @@ def build(force=False, verbose=False):
     """Compile libsicelore_gpu.so (nvcc, sm_100a only) and libslr_synth.so (g++) in-tree."""
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
-    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu")]
+    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "guided_match.cu")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -113,6 +120,12 @@ def gpu_lib():
         L.slr_bc_collide_dev.argtypes = [vp, vp, i32, vp, i64, vp, vp]
         L.slr_umi_dist.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
         L.slr_umi_dist_dev.argtypes = [vp, vp, i32, i32, vp, i64, i64, vp, vp, i64, vp]
+        L.slr_guided_sets_create.argtypes = [vp, vp, vp, i64, vp, i64, i32, vp, i64, i32, i32, i32, C.POINTER(vp)]
+        L.slr_guided_sets_destroy.argtypes = [vp]
+        L.slr_guided_sets_destroy.restype = None
+        L.slr_guided_match.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, i64, vp, vp, i32]
+        L.slr_guided_match_dev.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, i32, vp]
+        L.slr_dyn_max_ed.argtypes = [vp, i32, i32, i32, i32]
         L.slr_last_error.restype = C.c_char_p
         L.slr_abi_version.restype = i32
         L.slr_launch_count.restype = i64
@@ -192,6 +205,54 @@ def synth_umi_jobs(n_jobs, mean=4.0, cap=2000, seed=4, p_err=0.05, p_shift=0.05,
 
 # ---------------------------------------------------------------------------------------------- 2-bit helpers
 _B2 = "AGCT"            # NucleicAcidTwoBitPerBase: A=0 G=1 C=2 T=3 (T!…NucleicAcidTwoBitPerBase.java:L80-L87)
+
+
+def synth_guided(n, seq_len, seed=9, n_groups=1000, group_size=8, pm=2, post_len=8, bc_flavour=False, n_all=6000, n_empty=100000,
+                 p_sub=0.02, p_ins=0.01, p_del=0.02, p_random=0.1):
+    """Synthetic Illumina-guided batch (numpy, vectorised): n_groups candidate groups of ~group_size random sequences, every read is a
+    candidate of its group pushed through the error model of synth_reads (sub / ins / del per base), placed at anchor = pm + 1 of a
+    32-byte stranded slice with +-1 jitter of the predicted position; p_random of the reads carry a random window.
+    Returns dict(group_keys, group_offsets, all_keys, empty_keys, slices, anchor, group_id)."""
+    rng = np.random.default_rng(seed)
+    L = int(seq_len)
+    sizes = np.maximum(1, rng.poisson(group_size, n_groups)) if group_size > 1 else np.ones(n_groups, dtype=np.int64)
+    go = np.zeros(n_groups + 1, dtype=np.int64)
+    np.cumsum(sizes, out=go[1:])
+    gk = rng.integers(0, 1 << (2 * L), int(go[-1]), dtype=np.uint64)
+    gid = rng.integers(0, n_groups, n).astype(np.int32)
+    pick = go[gid] + (rng.random(n) * sizes[gid]).astype(np.int64)
+    true = gk[pick]
+    rnd = rng.random(n) < p_random
+    true = np.where(rnd, rng.integers(0, 1 << (2 * L), n, dtype=np.uint64), true)
+    bases = np.frombuffer(b"AGCT", dtype=np.uint8)
+    digits = ((true[:, None] >> (2 * (L - 1 - np.arange(L, dtype=np.uint64)))[None, :]) & np.uint64(3)).astype(np.int64)   # [n, L]
+    tail = rng.integers(0, 4, (n, 40))
+    src = np.concatenate([digits, tail], axis=1)                                   # candidate followed by random bases
+    # per-base edits: walk the source with a cursor; del skips a source base, ins emits a random base without advancing
+    out = np.zeros((n, 32), dtype=np.int64)
+    lead = pm + 1 + rng.choice([-1, 0, 0, 0, 1], n) * (pm > 0)
+    pre = rng.integers(0, 4, (n, 8))
+    cur = np.zeros(n, dtype=np.int64)
+    for col in range(32):
+        in_lead = col < lead
+        r = rng.random(n)
+        is_ins = (~in_lead) & (r < p_ins)
+        is_del = (~in_lead) & (r >= p_ins) & (r < p_ins + p_del)
+        cur = cur + is_del
+        b = src[np.arange(n), np.minimum(cur, src.shape[1] - 1)]
+        sub = (~in_lead) & (rng.random(n) < p_sub)
+        b = np.where(sub, (b + rng.integers(1, 4, n)) & 3, b)
+        b = np.where(is_ins, rng.integers(0, 4, n), b)
+        b = np.where(in_lead, pre[:, col % 8], b)
+        out[:, col] = b
+        cur = cur + ((~in_lead) & (~is_ins))
+    slices = bases[out].astype(np.uint8)
+    anchor = np.full(n, pm + 1, dtype=np.int32)
+    ak = ek = None
+    if bc_flavour:
+        ak = np.unique(np.concatenate([gk[rng.integers(0, len(gk), min(n_all, len(gk)))], rng.integers(0, 1 << (2 * L), n_all // 4, dtype=np.uint64)]))
+        ek = np.unique(rng.integers(0, 1 << (2 * L), n_empty, dtype=np.uint64))
+    return dict(group_keys=gk, group_offsets=go, all_keys=ak, empty_keys=ek, slices=np.ascontiguousarray(slices), anchor=anchor, group_id=gid)
 
 
 def pack_barcode(s):
@@ -379,6 +440,81 @@ def read_name_suffix(res_i, bc_start, bc_end):
     return "bc=%s_ed=%d_ed_sec=%d_bcStart=%d_bcEnd=%d_rk=%d" % (unpack_barcode(res_i["bc"]), res_i["ed"], res_i["ed_second"],
                                                               bc_start, bc_end, res_i["rank"])
 
+
+
+# ---------------------------------------------------------------------------------------------- Illumina-guided search
+class DynamicEditDistances:
+    """Mirror of com.rw.parameters.DynamicEditDistances for one (length, errorpercent) column of bcMaxEditDistances.xml /
+    umiMaxEditDistances.xml: max_candidates[e] = <maxBarcodes> of edit distance e (DynamicEditDistances.java:L75, L93-L98)."""
+
+    def __init__(self, max_candidates):
+        self.col = np.ascontiguousarray(max_candidates, dtype=np.int64)
+
+    @classmethod
+    def from_xml(cls, path, length, errorpercent):
+        """Reads the reference's own table file (XMLData -> OneUMILengthColumn -> ErrorPercentColumn -> EditDistanceColumn)."""
+        import xml.etree.ElementTree as ET
+        for lc in ET.parse(path).getroot().iter():
+            if lc.find("umiBCLength") is not None and int(lc.find("umiBCLength").text) == length:
+                for ec in lc.iter():
+                    if ec.find("errorpercent") is not None and int(ec.find("errorpercent").text) == errorpercent:
+                        rows = {int(d.find("editDistance").text): int(d.find("maxBarcodes").text)
+                                for d in ec.iter() if d.find("editDistance") is not None and d.find("maxBarcodes") is not None}
+                        return cls([rows[e] for e in range(len(rows))])
+        raise KeyError("no column for length %d, error %d %% in %s" % (length, errorpercent, path))
+
+    def getmaxED(self, count, pos_plusminus, maxED=None):
+        r = gpu_lib().slr_dyn_max_ed(self.col.ctypes.data, len(self.col), int(count), int(pos_plusminus), -1 if maxED is None else int(maxED))
+        if r < 0:
+            raise LookupError("NoSuchElementException: no edit distance admits %d candidates" % count)
+        return r
+
+
+class GuidedSets:
+    """Device-resident candidate sets of the Illumina-guided search and the batched search itself: the offset loops of
+    IlluminaUMIanalyzer.findUMI (IlluminaUMIanalyzer.java:L89-L136, bc_flavour=False: UMInucTwoBitPerBaseEDtester) and
+    IlluminaBarcodeAnalyzer.testBarcodes (IlluminaBarcodeAnalyzer.java:L272-L304, bc_flavour=True: BCnucTwoBitPerBaseEDtester)
+    plus the sorted().distinct() reduction of getBestAndSecondBCorUMI."""
+    W_GENE, W_ALL, W_EMPTY, EXCEPTION = 1, 2, 4, 1
+
+    def __init__(self, ctx, group_keys, group_offsets, seq_len, bc_flavour=False, all_keys=None, all_ed=0, empty_keys=None, empty_ed=0):
+        self.ctx, self.seq_len = ctx, int(seq_len)
+        gk = np.ascontiguousarray(group_keys, dtype=np.uint64)
+        go = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        ak = None if all_keys is None else np.ascontiguousarray(all_keys, dtype=np.uint64)
+        ek = None if empty_keys is None else np.ascontiguousarray(empty_keys, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(gpu_lib().slr_guided_sets_create(ctx.h, gk.ctypes.data, go.ctypes.data, len(go) - 1, None if ak is None else ak.ctypes.data,
+                                                0 if ak is None else len(ak), int(all_ed), None if ek is None else ek.ctypes.data,
+                                                0 if ek is None else len(ek), int(empty_ed), int(bool(bc_flavour)), self.seq_len, C.byref(h)))
+        self.h = h
+
+    def match(self, slices, anchor, group_id, ed, posplusminus, post_len, bailout=None, slice_len=None, raw_cap=0):
+        """slices uint8 [n, stride] (stranded orientation), anchor / group_id int32 [n], ed scalar or int32 [n].
+        Returns (GUIDED_RESULT[n], GUIDED_HIT[n, raw_cap] or None)."""
+        slices = np.ascontiguousarray(slices, dtype=np.uint8)
+        anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+        gid = np.ascontiguousarray(group_id, dtype=np.int32)
+        n, stride = slices.shape
+        edv = np.ascontiguousarray(np.broadcast_to(np.asarray(ed, dtype=np.int32), (n,)))
+        out = np.empty(n, dtype=GUIDED_RESULT)
+        raw = np.empty((n, raw_cap), dtype=GUIDED_HIT) if raw_cap else None
+        _check(gpu_lib().slr_guided_match(self.ctx.h, self.h, int(posplusminus), int(post_len), -1 if bailout is None else int(bailout),
+                                          slices.ctypes.data, stride, stride if slice_len is None else int(slice_len), anchor.ctypes.data,
+                                          gid.ctypes.data, edv.ctypes.data, n, out.ctypes.data, None if raw is None else raw.ctypes.data,
+                                          int(raw_cap)))
+        return out, raw
+
+    def close(self):
+        if getattr(self, "h", None):
+            gpu_lib().slr_guided_sets_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 # ---------------------------------------------------------------------------------------------- UMI distances
 class BestEditDistance:

@@ -1,0 +1,223 @@
+// guided_core.cuh — per-lane logic of the Illumina-guided search kernel, __host__ __device__ so that
+// tests/host_sim replays the same code on the CPU; the warp orchestration lives in guided_match.cu.
+//
+// Reference behaviour restated here (F! = Jar/NanoporeBC_UMI_finder-2.1.jar, T! = Jar/lib/TwoFourBitNucAcidLibraryMaven-1.0.jar):
+//   BCUMIEDtesterBase.matchesSeqEditDistance / substitutions / insertions / deletions   F!…/TwoBit/ed/BCUMIEDtesterBase.class (BCUMIEDtesterBase.java:L82-L203)
+//   NucTwoBitPerBaseEDtesterBase visited set + goNextEDlevel (bailout)                  F!…/TwoBit/ed/NucTwoBitPerBaseEDtesterBase.class (…java:L82-L144)
+//   checkMatchWithTestSets: UMInucTwoBitPerBaseEDtester (…java:L52-L67), BCnucTwoBitPerBaseEDtester (…java:L72-L92)
+//   reduction of the match list: IlluminaBarcodeUMIAnalyzerBase.getBestAndSecondBCorUMI (…java:L52-L60), comparators (L106-L110, L143-L144)
+//   NucleicAcidTwoBitPerBase replace/insert/delete                                      T!…/TwoBit/NucleicAcidTwoBitPerBase.class (…java:L228-L327)
+//
+// The engine enumerates the <= ed edit neighbourhood of one window depth first.  A deque node is (sequence, counters, previous /
+// current position, level); popping it runs ONE position (<= 9 children: SUB A,G,C,T, INS A,G,C,T, DEL), every child is probed
+// against the candidate sets and, below the last level, pushed.  The kernel keeps that order but runs all positions of a
+// last-level node (whose children are never pushed) as one batch of 9·L children, 32 per warp step.
+#pragma once
+#include <stdint.h>
+#include "../../include/sicelore_gpu.h"
+
+#ifdef __CUDACC__
+#define SLR_GHD static __host__ __device__ __forceinline__
+#else
+#define SLR_GHD static inline
+#endif
+
+constexpr int SLR_G_MAX_ED = 4;                 // IlluminaUMIanalyzer.java:L75 asserts ed < 5
+constexpr int SLR_G_STACK = 48;                 // deque depth: (continuation + 9 children) per level
+constexpr uint32_t SLR_G_EMPTY = 0xFFFFFFFFu;   // empty slot of a candidate table
+
+// ---- candidate sets -------------------------------------------------------------------------------------------------------
+// Every set (one per candidate group + the two global lists of the BC flavour) is an open-addressing table of 32-bit keys
+// (L <= 16 => a clean 2-bit sequence fits 32 bits; values with garbage in bits 62-63 never match, see slr_g_child).
+// meta: bits 0-4 log2(capacity), bit 8 "holds the all-T key 0xFFFFFFFF" (the empty marker), bit 9 "non-empty".
+struct SlrGuidedSetsDev {
+    const uint32_t *slots;
+    const uint2 *groups;            // x = first slot, y = meta
+    int n_groups;
+    uint2 all_set, empty_set;       // BC flavour: allPassed10xBCs / outOfCellsBarcodes (meta 0 = absent)
+    int all_ed, empty_ed;           // maxEDtoCheckBCAll10xBCs / maxEDtoCheckBCEmptyDrops
+    int bc_flavour;
+};
+
+SLR_GHD uint32_t slr_g_hash(uint32_t key) { return key * 0x9E3779B1u; }
+
+SLR_GHD bool slr_g_contains(const uint32_t *slots, uint2 set, uint32_t key)
+{
+    const uint32_t meta = set.y;
+    if (!(meta & 0x200u)) return false;
+    if (key == SLR_G_EMPTY) return (meta & 0x100u) != 0u;
+    const uint32_t lg = meta & 31u, mask = (1u << lg) - 1u;
+    uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;       // lg >= 1
+    const uint32_t *tab = slots + set.x;
+    while (true) {
+#if defined(__CUDA_ARCH__)
+        const uint32_t v = __ldg(tab + slot);
+#else
+        const uint32_t v = tab[slot];
+#endif
+        if (v == key) return true;
+        if (v == SLR_G_EMPTY) return false;
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// ---- visited set: IntHashSet on (int) seq of every node that has run a position (java:L105-L120), active for ed >= 2 ----
+// per-warp table of 64-bit slots (stamp << 32 | key); a slot whose stamp is not the current window's is empty, so the table is
+// never cleared between windows.
+SLR_GHD uint32_t slr_g_vis_log2(int ed) { return ed <= 2 ? 9u : (ed == 3 ? 16u : 22u); }
+
+SLR_GHD bool slr_g_vis_contains(const unsigned long long *tab, uint32_t lg, uint32_t stamp, uint32_t key)
+{
+    const uint32_t mask = (1u << lg) - 1u;
+    uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;
+    while (true) {
+        const unsigned long long v = tab[slot];
+        if ((uint32_t)(v >> 32) != stamp) return false;
+        if ((uint32_t)v == key) return true;
+        slot = (slot + 1u) & mask;
+    }
+}
+
+SLR_GHD void slr_g_vis_insert(unsigned long long *tab, uint32_t lg, uint32_t stamp, uint32_t key)
+{
+    const uint32_t mask = (1u << lg) - 1u;
+    uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;
+    while (true) {
+        const unsigned long long v = tab[slot];
+        if ((uint32_t)(v >> 32) != stamp) { tab[slot] = ((unsigned long long)stamp << 32) | key; return; }
+        if ((uint32_t)v == key) return;
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// ---- deque node (LongSeqMutated, LongSeqMutated.java:L44-L77) packed in 8 bytes ------------------------------------------------
+// meta: bits 0-4 posTreatedInCurrentCycle + 1, 5-9 posTreatedInPreviousLevel + 1, 10-12 currentlevel, 13-15 nSubstitutions,
+//       16-18 nInsertions, 19-21 nDeletions, 22 "dead" (bits 62-63 of the Java long are set), 23 findingErrorFlag GENE bit
+struct SlrGNode { uint32_t seq, meta; };
+SLR_GHD int  slr_g_pos_cur(uint32_t m)  { return (int)(m & 31u) - 1; }
+SLR_GHD int  slr_g_pos_prev(uint32_t m) { return (int)((m >> 5) & 31u) - 1; }
+SLR_GHD int  slr_g_level(uint32_t m)    { return (int)((m >> 10) & 7u); }
+SLR_GHD int  slr_g_nsub(uint32_t m)     { return (int)((m >> 13) & 7u); }
+SLR_GHD int  slr_g_nins(uint32_t m)     { return (int)((m >> 16) & 7u); }
+SLR_GHD int  slr_g_ndel(uint32_t m)     { return (int)((m >> 19) & 7u); }
+SLR_GHD bool slr_g_dead(uint32_t m)     { return (m >> 22) & 1u; }
+SLR_GHD bool slr_g_inh(uint32_t m)      { return (m >> 23) & 1u; }
+SLR_GHD uint32_t slr_g_root_meta()      { return (1u << 10); }                      // pos -1/-1, level 1, no errors (java:L82)
+// goNextEDlevel (java:L137-L140): posPrev = parent's current position, posCur = -1, level + 1
+SLR_GHD uint32_t slr_g_next_level_meta(uint32_t child_meta, int pos)
+{
+    return (child_meta & ~0x3FFu & ~(7u << 10)) | ((uint32_t)(pos + 1) << 5) | ((uint32_t)(slr_g_level(child_meta) + 1) << 10);
+}
+
+// ---- one child of node (seq, meta) at position p: j = 0-3 SUB A,G,C,T, 4-7 INS A,G,C,T, 8 DEL ---------------------------------
+// low 32 bits of getLongHashReplaceByteDeg / InsertByteDeg / deleteByte for a sequence of L bases (digit i at bits 2(L-1-i));
+// post2 holds the 2-bit value appended by a deletion for nDeletions = k at bits 2k (BYTE_TO_2BITLONG_ARRAY[0][getByteAt(k+1)]).
+// valid  = the Java creates and probes this child, apart from the visited-set test;
+// meta_out = the child's counters / flags (level and positions still the parent's: the Java copies the node);
+// throws |= the deletion reads a post base outside ENCODE_MATRIX (postbad bit k = post base k is such a char):
+//           BYTE_TO_2BITLONG_ARRAY[0][-1] -> ArrayIndexOutOfBoundsException, raised only when that base is used.
+SLR_GHD uint32_t slr_g_child(uint32_t seq, uint32_t meta, int L, int p, int j, uint32_t post2, uint32_t postbad, int post_len, bool &valid,
+                            uint32_t &meta_out, bool &throws)
+{
+    const int sh = 2 * (L - 1 - p);
+    const uint32_t below = sh == 0 ? 0u : (0xFFFFFFFFu >> (32 - sh));      // digits p+1..L-1
+    const uint32_t below2 = (below << 2) | 3u;                              // digits p..L-1
+    const uint32_t b = (uint32_t)(j & 3);
+    const int ndel = slr_g_ndel(meta);
+    const uint32_t cbase = (post2 >> (2 * ndel)) & 3u;
+    const uint32_t sub = (seq & ~(3u << sh)) | (b << sh);
+    const uint32_t ins = (seq & ~below) | ((seq & below) >> 2) | ((b << sh) >> 2);
+    const uint32_t del = (seq & ~below2) | ((seq << 2) & below2) | cbase;
+    const bool is_sub = j < 4, is_ins = !is_sub && j < 8;
+    valid = is_sub ? (((seq >> sh) & 3u) != b)            // s != cur.seq (java:L138)
+          : is_ins ? (p < L - 1)                          // insertions only for posCur < L-1 (java:L115)
+                   : (ndel + 1 <= post_len);              // deletions at every position, java:L187
+    if (!is_sub && !is_ins && valid && ((postbad >> ndel) & 1u)) throws = true;
+    // insert at p = L-2: `>>> 64` == `>>> 0` leaves the old last base in bits 62-63 (never matches; (int) value unaffected)
+    const bool dead = slr_g_dead(meta) || (is_ins && p == L - 2 && (seq & 3u) != 0u);
+    meta_out = (meta & ~(1u << 22)) + (is_sub ? (1u << 13) : is_ins ? (1u << 19) : (1u << 16)) | ((uint32_t)dead << 22);
+    return is_sub ? sub : (is_ins ? ins : del);
+}
+
+// ---- checkMatchWithTestSets: 0 = no hit, else SLR_G_W_* bits of the list entry; inh_out = GENE bit now on the node ------
+SLR_GHD uint32_t slr_g_probe(const SlrGuidedSetsDev &S, uint2 group, uint32_t s, uint32_t meta, int level, bool &inh_out)
+{
+    inh_out = slr_g_inh(meta);
+    if (slr_g_dead(meta)) return 0u;
+    if (slr_g_contains(S.slots, group, s)) {
+        if (!S.bc_flavour) return 0x80u;                                    // UMI flavour: a hit without flag bits
+        inh_out = true;                                                     // BCnuc…java:L76: on the node itself
+        return SLR_G_W_GENE;
+    }
+    if (!S.bc_flavour) return 0u;
+    const uint32_t g = inh_out ? SLR_G_W_GENE : 0u;
+    if (level <= S.all_ed && slr_g_contains(S.slots, S.all_set, s)) return g | SLR_G_W_ALL;        // java:L79-L83
+    if (level <= S.empty_ed && slr_g_contains(S.slots, S.empty_set, s)) return g | SLR_G_W_EMPTY;  // java:L85-L89
+    return 0u;
+}
+
+// ---- running "sorted().distinct()" of the match list: the first two entries -------------------------------------------------
+// key = (getNErrors, [scoreWhereFound], |offset|); hits arrive in list order, so an equal key never displaces an earlier hit
+// (Stream.sorted is stable) and distinct() keeps the first entry of each sequence.
+struct SlrGTop2 {
+    uint32_t seq[2], key[2], info[2];
+    int n, n_raw, min_err_gene;
+};
+SLR_GHD void slr_g_top2_init(SlrGTop2 &T) { T.n = 0; T.n_raw = 0; T.min_err_gene = 0x7FFFFFFF; T.seq[0] = T.seq[1] = 0; T.key[0] = T.key[1] = 0xFFFFFFFFu; T.info[0] = T.info[1] = 0; }
+SLR_GHD uint32_t slr_g_score(uint32_t where)                                  // BarcodeFindingFlag.java:L119-L131
+{
+    return (where & SLR_G_W_GENE) ? 3u : (where & SLR_G_W_ALL) ? 2u : (where & SLR_G_W_EMPTY) ? 1u : 0u;
+}
+SLR_GHD void slr_g_top2_add(SlrGTop2 &T, int bc_flavour, uint32_t seq, uint32_t child_meta, int offset, uint32_t where)
+{
+    where &= 7u;
+    const int nerr = slr_g_nsub(child_meta) + slr_g_nins(child_meta) + slr_g_ndel(child_meta);
+    const uint32_t key = ((uint32_t)nerr << 8) | ((bc_flavour ? slr_g_score(where) : 0u) << 4) | (uint32_t)(offset < 0 ? -offset : offset);
+    const uint32_t info = (uint32_t)slr_g_nsub(child_meta) | ((uint32_t)slr_g_nins(child_meta) << 4) | ((uint32_t)slr_g_ndel(child_meta) << 8) |
+                          ((uint32_t)(offset + 8) << 12) | (where << 16);
+    T.n_raw++;
+    if ((where & SLR_G_W_GENE) && nerr < T.min_err_gene) T.min_err_gene = nerr;
+    if (T.n == 0) { T.seq[0] = seq; T.key[0] = key; T.info[0] = info; T.n = 1; return; }
+    if (seq == T.seq[0]) {
+        if (key < T.key[0]) { T.key[0] = key; T.info[0] = info; }
+        return;
+    }
+    if (key < T.key[0]) {
+        T.seq[1] = T.seq[0]; T.key[1] = T.key[0]; T.info[1] = T.info[0];
+        T.seq[0] = seq; T.key[0] = key; T.info[0] = info; T.n = 2;
+        return;
+    }
+    if (T.n == 1 || key < T.key[1]) { T.seq[1] = seq; T.key[1] = key; T.info[1] = info; T.n = 2; }
+}
+SLR_GHD void slr_g_top2_store(const SlrGTop2 &T, uint32_t flags, slr_guided_result &r)
+{
+    for (int i = 0; i < 2; i++) {
+        const bool on = i < T.n && !flags;
+        const uint32_t f = on ? T.info[i] : 0u;
+        r.seq[i] = on ? (uint64_t)T.seq[i] : 0ull;
+        r.n_sub[i] = (int8_t)(f & 15u); r.n_ins[i] = (int8_t)((f >> 4) & 15u); r.n_del[i] = (int8_t)((f >> 8) & 15u);
+        r.offset[i] = on ? (int8_t)((int)((f >> 12) & 15u) - 8) : (int8_t)0;
+        r.where[i] = (uint8_t)((f >> 16) & 7u);
+    }
+    r.n_distinct = flags ? (uint8_t)0 : (uint8_t)T.n;
+    r.flags = (uint8_t)flags;
+    r.n_raw = flags ? 0 : T.n_raw;
+    r.min_err_gene = flags ? 0x7FFFFFFF : T.min_err_gene;
+    r.pad = 0;
+}
+
+// ---- characters ----------------------------------------------------------------------------------------------------------------
+// NucleicAcidByteCodeBase.ENCODE_MATRIX (T!…NucleicAcidByteCodeBase.java:L45-L78): 4-bit code, 0xFF = not in the matrix
+SLR_GHD uint32_t slr_g_code4(uint32_t c)
+{
+    if (c == '-') return 0u;
+    switch (c | 0x20u) {
+    case 'a': return 1u; case 'g': return 2u; case 'c': return 4u; case 't': return 8u; case 'n': return 15u;
+    case 'h': return 13u; case 'r': return 3u; case 'y': return 12u; case 'm': return 5u; case 'k': return 10u;
+    case 's': return 6u; case 'w': return 9u; case 'b': return 14u; case 'v': return 7u; case 'd': return 11u;
+    default: return 0xFFu;
+    }
+}
+// FOURBIT_TO_TWOBIT_MATRIX / BYTE_TO_2BITLONG_ARRAY[0]: G->1, C->2, T->3, every other code (A, IUPAC, N in a post sequence) -> 0
+SLR_GHD uint32_t slr_g_two_of_code4(uint32_t c4) { return c4 == 2u ? 1u : c4 == 4u ? 2u : c4 == 8u ? 3u : 0u; }
+SLR_GHD int slr_g_offset_of(int k) { return (k == 0) ? 0 : ((k & 1) ? -((k + 1) / 2) : (k / 2)); }   // 0,-1,1,-2,2 (java:L89-L91)

@@ -1,0 +1,208 @@
+// guided_match.cu — Illumina-guided barcode / UMI search for sm_100a.
+//
+// One warp per read (query).  For every offset window the warp walks the reference's depth-first enumeration
+// (BCUMIEDtesterBase.matchesSeqEditDistance, F!…/TwoBit/ed/BCUMIEDtesterBase.class, BCUMIEDtesterBase.java:L82-L124) in the
+// reference's own order, because the match list is ordered and the visited set / the bailout depend on what ran before:
+//   * the deque lives in shared memory (per warp, LIFO like ArrayDeque.add / pollLast);
+//   * a node below the last level runs ONE position per pop: its <= 9 children are generated, tested against the visited
+//     set, probed and pushed by 9 lanes (ballot + prefix ranks keep the creation order);
+//   * a node of the last level (the bulk: ~(9L)^(ed-1) of them) runs ALL its positions as one batch of 9·L children, 32 per
+//     warp step — its children are never pushed, and the only change of the visited set in between is the node's own
+//     sequence after its first position (the "self rule" below);
+//   * hits are folded, in list order, into the first two entries of the consumers' sorted().distinct() list.
+// The visited set is a per-warp table in global memory (stamped slots, never cleared between windows); the candidate
+// sets are small open-addressing tables that stay in L1/L2.  Integer work only: no tensor cores.
+#include <cuda_runtime.h>
+#include "guided_core.cuh"
+#include "slr_kernels.h"
+
+namespace {
+
+constexpr int G_WARPS = 8;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct GWarpShared {
+    SlrGNode stack[SLR_G_STACK];
+    uint8_t codes[32];
+};
+
+// list order bookkeeping of one hit (all lanes hold the same state); lane 0 writes the optional raw record
+__device__ __forceinline__ void g_record(SlrGTop2 &T, int bc_flavour, uint32_t seq, uint32_t cmeta, int level, int offset, uint32_t where,
+                                         slr_guided_hit *raw, int raw_cap, int lane)
+{
+    if (raw && T.n_raw < raw_cap && lane == 0) {
+        slr_guided_hit h;
+        h.seq = seq; h.n_sub = (int8_t)slr_g_nsub(cmeta); h.n_ins = (int8_t)slr_g_nins(cmeta); h.n_del = (int8_t)slr_g_ndel(cmeta);
+        h.offset = (int8_t)offset; h.where = (uint8_t)(where & 7u); h.level = (uint8_t)level; h.pad = 0;
+        raw[T.n_raw] = h;
+    }
+    slr_g_top2_add(T, bc_flavour, seq, cmeta, offset, where);
+}
+
+__global__ void __launch_bounds__(G_WARPS * 32)
+guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int bailout, const uint8_t *__restrict__ slices, int stride,
+                    int slice_len, const int32_t *__restrict__ anchor, const int32_t *__restrict__ group_id,
+                    const int32_t *__restrict__ ed_arr, long long n, slr_guided_result *__restrict__ out, slr_guided_hit *raw_out,
+                    int raw_cap, unsigned long long *vis_all, uint32_t vis_lg_alloc, int max_ed, unsigned long long *work)
+{
+    __shared__ GWarpShared sh[G_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    GWarpShared &W = sh[wib];
+    const long long gwarp = (long long)blockIdx.x * G_WARPS + wib;
+    unsigned long long *vis = vis_all + ((size_t)gwarp << vis_lg_alloc);
+    uint32_t stamp = 0;                                    // the table is zeroed before the launch: stamp 0 = never written
+    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    const int nchild = 9 * L;
+
+    while (true) {
+        unsigned long long qq = 0;
+        if (lane == 0) qq = atomicAdd(work, 1ull);
+        const long long q = (long long)__shfl_sync(FULL, qq, 0);
+        if (q >= n) break;
+
+        const int ed = ed_arr[q], gid = group_id[q], anc = anchor[q];
+        const uint2 group = (gid >= 0 && gid < S.n_groups) ? S.groups[gid] : make_uint2(0u, 0u);
+        const uint32_t ch = lane < slice_len ? slices[(size_t)q * stride + lane] : 0u;
+        W.codes[lane] = (uint8_t)slr_g_code4(ch);
+        __syncwarp();
+        slr_guided_hit *raw = raw_out ? raw_out + (size_t)q * raw_cap : nullptr;
+        const uint32_t vlg = slr_g_vis_log2(ed);
+        const bool use_vis = ed >= 2;                      // MINED_TOHASHTESTED_* = 2 (java:L82-L83)
+        SlrGTop2 T;
+        slr_g_top2_init(T);
+        uint32_t flags = (ed < 0 || ed > max_ed) ? SLR_G_EXCEPTION : 0u;      // host entry points refuse such a batch
+
+        for (int k = 0; k <= 2 * plusminus && !flags; k++) {
+            const int o = slr_g_offset_of(k), ws = anc + o;
+            if (ws < 0 || ws + L + post_len > slice_len) { flags = SLR_G_EXCEPTION; break; }           // getSubSequence throws
+            const uint32_t c4 = lane < L + post_len ? W.codes[ws + lane] : 0u;
+            // N (15) or a char outside ENCODE_MATRIX (-1) in the window indexes outside FOURBIT_TO_TWOBIT_MATRIX (AIOOBE)
+            if (__any_sync(FULL, lane < L && c4 >= 15u)) { flags = SLR_G_EXCEPTION; break; }
+            const uint32_t postbad = __ballot_sync(FULL, lane >= L && lane < L + post_len && c4 == 0xFFu) >> L;   // thrown only if used
+            bool throws = false;
+            const uint32_t two = slr_g_two_of_code4(c4);
+            const uint32_t w = __reduce_or_sync(FULL, lane < L ? two << (2 * (L - 1 - lane)) : 0u);     // getLongHashForBytes
+            const uint32_t post2 = __reduce_or_sync(FULL, (lane >= L && lane < L + post_len && lane - L < 16) ? two << (2 * (lane - L)) : 0u);
+            stamp++;
+            int nlist = 0;                                 // matchingList.size() of this tester
+
+            // ---- root: checkMatchWithTestSets(parent) with currentlevel 1 (java:L82-L89) ----
+            uint32_t root_meta = slr_g_root_meta();
+            {
+                bool inh;
+                const uint32_t where = slr_g_probe(S, group, w, root_meta, 1, inh);
+                if (where) { g_record(T, S.bc_flavour, w, root_meta, 1, o, where, raw, raw_cap, lane); nlist++; }
+                if (inh) root_meta |= 1u << 23;
+            }
+            if (ed == 0) continue;                         // java:L91-L92
+            int sp = 0;
+            if (lane == 0) { W.stack[0].seq = w; W.stack[0].meta = root_meta; }
+            sp = 1;
+            __syncwarp();
+
+            while (sp > 0) {
+                const SlrGNode node = W.stack[--sp];       // pollLast (java:L100)
+                __syncwarp();
+                const int level = slr_g_level(node.meta), pos_prev = slr_g_pos_prev(node.meta);
+                if (level == ed) {
+                    // ---- last level: every position of this node, 32 children per step ----
+                    const int p0 = pos_prev == 0 ? 1 : 0;  // first position that runs; node.seq is "tested" after it (java:L122)
+                    for (int c0 = 0; c0 < nchild; c0 += 32) {
+                        const int c = c0 + lane, p = c / 9, j = c - 9 * p;
+                        bool valid = false, inh;
+                        uint32_t cmeta = 0, s = 0, where = 0;
+                        if (c < nchild && p != pos_prev) {                                               // java:L109-L110
+                            s = slr_g_child(node.seq, node.meta, L, p, j, post2, postbad, post_len, valid, cmeta, throws);
+                            if (valid && use_vis && ((s == node.seq && p > p0) || slr_g_vis_contains(vis, vlg, stamp, s))) valid = false;
+                            if (valid) where = slr_g_probe(S, group, s, cmeta, level, inh);
+                        }
+                        uint32_t hits = __ballot_sync(FULL, where != 0u);
+                        while (hits) {
+                            const int src = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            g_record(T, S.bc_flavour, __shfl_sync(FULL, s, src), __shfl_sync(FULL, cmeta, src), level, o,
+                                     __shfl_sync(FULL, where, src), raw, raw_cap, lane);
+                            nlist++;
+                        }
+                    }
+                    if (use_vis) {
+                        if (lane == 0) slr_g_vis_insert(vis, vlg, stamp, node.seq);
+                        __syncwarp();
+                    }
+                    continue;
+                }
+                // ---- inner node: one position (java:L104-L122) ----
+                const int pos = slr_g_pos_cur(node.meta) + 1;
+                const uint32_t meta = (node.meta & ~31u) | (uint32_t)(pos + 1);
+                if (pos < L - 1) {                         // continuation, pushed BEFORE the children (java:L105-L106)
+                    if (lane == 0) { W.stack[sp].seq = node.seq; W.stack[sp].meta = meta; }
+                    sp++;
+                }
+                if (pos_prev == pos) { __syncwarp(); continue; }
+                bool valid = false, inh = false;
+                uint32_t cmeta = 0, s = 0, where = 0;
+                if (lane < 9) {
+                    s = slr_g_child(node.seq, meta, L, pos, lane, post2, postbad, post_len, valid, cmeta, throws);
+                    if (valid && use_vis && slr_g_vis_contains(vis, vlg, stamp, s)) valid = false;
+                    if (valid) where = slr_g_probe(S, group, s, cmeta, level, inh);
+                }
+                uint32_t hits = __ballot_sync(FULL, where != 0u);
+                // goNextEDlevel (java:L134-L142): ed > level holds here; bailout: no push once level >= bailout and the list is non-empty
+                const bool push_ok = valid && (bailout < 0 || level < bailout || nlist + __popc(hits & le_mask) == 0);
+                while (hits) {
+                    const int src = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    g_record(T, S.bc_flavour, __shfl_sync(FULL, s, src), __shfl_sync(FULL, cmeta, src), level, o,
+                             __shfl_sync(FULL, where, src), raw, raw_cap, lane);
+                    nlist++;
+                }
+                const uint32_t pm = __ballot_sync(FULL, push_ok);
+                if (push_ok) {
+                    const int at = sp + __popc(pm & lt_mask);
+                    W.stack[at].seq = s;
+                    W.stack[at].meta = slr_g_next_level_meta((cmeta & ~(1u << 23)) | ((uint32_t)inh << 23), pos);
+                }
+                sp += __popc(pm);
+                if (use_vis && lane == 0) slr_g_vis_insert(vis, vlg, stamp, node.seq);                  // addToTestedSeqs (java:L122)
+                __syncwarp();
+            }
+            if (__any_sync(FULL, throws)) flags = SLR_G_EXCEPTION;     // a deletion used an invalid post base somewhere in this window
+        }
+        if (lane == 0) slr_g_top2_store(T, flags, out[q]);
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+size_t slr_guided_vis_bytes(int max_ed, int *warps_out)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // resident warps: 2 CTAs of 8 warps per SM; the 32 MB tables of ed = 4 get one CTA on every second SM
+    const int ctas = max_ed >= 4 ? (sms / 2 > 0 ? sms / 2 : 1) : 2 * sms;
+    const int warps = ctas * G_WARPS;
+    if (warps_out) *warps_out = warps;
+    return ((size_t)warps << slr_g_vis_log2(max_ed)) * sizeof(unsigned long long);
+}
+
+cudaError_t slr_launch_guided_match(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, int bailout, const uint8_t *d_slices,
+                                    int stride, int slice_len, const int32_t *d_anchor, const int32_t *d_group_id, const int32_t *d_ed,
+                                    int max_ed, long long n, slr_guided_result *d_out, slr_guided_hit *d_raw, int raw_cap, void *d_vis,
+                                    unsigned long long *d_work, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    int warps = 0;
+    const size_t vbytes = slr_guided_vis_bytes(max_ed, &warps);
+    cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_vis, 0, vbytes, stream);
+    if (e != cudaSuccess) return e;
+    const long long need = (n + G_WARPS - 1) / G_WARPS;
+    const long long resident = warps / G_WARPS;
+    const unsigned blocks = (unsigned)(need < resident ? need : resident);
+    guided_match_kernel<<<blocks, G_WARPS * 32, 0, stream>>>(S, L, plusminus, post_len, bailout, d_slices, stride, slice_len, d_anchor,
+                                                            d_group_id, d_ed, n, d_out, d_raw, raw_cap, (unsigned long long *)d_vis,
+                                                            slr_g_vis_log2(max_ed), max_ed, d_work);
+    return cudaGetLastError();
+}

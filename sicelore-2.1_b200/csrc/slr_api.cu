@@ -12,6 +12,7 @@
 #include "slr_table_build.h"
 #include "umi_core.cuh"
 #include "bc_core.cuh"
+#include "guided_build.h"
 
 namespace {
 
@@ -60,6 +61,8 @@ struct Slot {
     DevBuf slices[2], anchor[2], lens[2], out[2];
     DevBuf umi[2], joff[2], ooff[2], uout[2], uscr[2];
     cudaEvent_t uscr_free = nullptr;           // recorded after the last launch that uses uscr[0] on a caller's stream (slr_umi_dist_dev)
+    DevBuf gsl, ganc, ggid, ged, gout, graw, gvis;   // Illumina-guided search: staging buffers + the per-warp visited tables
+    cudaEvent_t gvis_free = nullptr;           // recorded after the last guided launch that uses gvis
 };
 
 }  // namespace
@@ -119,6 +122,7 @@ int slr_ctx_create(int device, int n_streams, slr_ctx **out)
             if (e != cudaSuccess) { delete s; slr_ctx_destroy(c); return fail(SLR_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         }
         e = cudaEventCreateWithFlags(&s->uscr_free, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->gvis_free, cudaEventDisableTiming);
         if (e != cudaSuccess) { delete s; slr_ctx_destroy(c); return fail(SLR_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
         c->slots.push_back(s);
     }
@@ -137,6 +141,8 @@ void slr_ctx_destroy(slr_ctx *c)
         }
         for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); }
         if (s->uscr_free) cudaEventDestroy(s->uscr_free);
+        if (s->gvis_free) cudaEventDestroy(s->gvis_free);
+        s->gsl.release(); s->ganc.release(); s->ggid.release(); s->ged.release(); s->gout.release(); s->graw.release(); s->gvis.release();
         delete s;
     }
     cudaFree(c->d_work);
@@ -468,6 +474,156 @@ int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, con
     CUDA_TRY(cudaStreamSynchronize(s->stream[0]));
     CUDA_TRY(cudaStreamSynchronize(s->stream[1]));
     return SLR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// S4: Illumina-guided search
+}  // extern "C"
+
+struct slr_guided_sets {
+    slr_ctx *ctx = nullptr;
+    SlrGuidedSetsDev dev;
+    void *d_slots = nullptr, *d_groups = nullptr;
+    int seq_len = 0;
+};
+
+extern "C" {
+
+int slr_guided_sets_create(slr_ctx *ctx, const uint64_t *group_keys, const int64_t *group_offsets, int64_t n_groups,
+                           const uint64_t *all_keys, int64_t n_all, int all_ed, const uint64_t *empty_keys, int64_t n_empty,
+                           int empty_ed, int bc_flavour, int seq_len, slr_guided_sets **out)
+{
+    if (!ctx || !out || n_groups < 0 || (n_groups > 0 && !group_offsets) || n_all < 0 || n_empty < 0)
+        return fail(SLR_E_INVALID, "slr_guided_sets_create: bad argument");
+    *out = nullptr;
+    if (seq_len < 2 || seq_len > 16) return fail(SLR_E_UNSUPPORTED, "sequence length %d not supported by the guided search (2..16)", seq_len);
+    if (n_groups > 0x7FFFFFFFLL) return fail(SLR_E_UNSUPPORTED, "more than 2^31 candidate groups");
+    for (int64_t g = 0; g < n_groups; g++)
+        if (group_offsets[g + 1] < group_offsets[g]) return fail(SLR_E_INVALID, "group_offsets not monotone at %lld", (long long)g);
+    if (n_groups > 0 && group_offsets[n_groups] > group_offsets[0] && !group_keys) return fail(SLR_E_INVALID, "group_keys is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlrGuidedSetsHost H;
+    slr_guided_build(group_keys, group_offsets, n_groups, all_keys, n_all, empty_keys, n_empty, seq_len, H);
+    if (H.slots.size() > 0xFFFFFFFFull) return fail(SLR_E_UNSUPPORTED, "candidate tables exceed 2^32 slots");
+    slr_guided_sets *s = new slr_guided_sets();
+    s->ctx = ctx; s->seq_len = seq_len;
+    cudaError_t e = cudaMalloc(&s->d_slots, H.slots.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_groups, (H.groups.size() + 1) * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_slots, H.slots.data(), H.slots.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !H.groups.empty()) e = cudaMemcpy(s->d_groups, H.groups.data(), H.groups.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { slr_guided_sets_destroy(s); return fail(SLR_E_CUDA, "slr_guided_sets_create: %s", cudaGetErrorString(e)); }
+    s->dev.slots = (const uint32_t *)s->d_slots;
+    s->dev.groups = (const uint2 *)s->d_groups;
+    s->dev.n_groups = (int)n_groups;
+    s->dev.all_set = H.all_set; s->dev.empty_set = H.empty_set;
+    s->dev.all_ed = all_ed; s->dev.empty_ed = empty_ed;
+    s->dev.bc_flavour = bc_flavour ? 1 : 0;
+    *out = s;
+    return SLR_OK;
+}
+
+void slr_guided_sets_destroy(slr_guided_sets *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_slots); cudaFree(s->d_groups);
+    delete s;
+}
+
+static int check_guided_args(const slr_ctx *ctx, const slr_guided_sets *s, int plusminus, int post_len, int stride, int slice_len, int64_t n,
+                             int raw_cap, int max_ed)
+{
+    if (!ctx || !s) return fail(SLR_E_INVALID, "slr_guided_match: ctx / sets is NULL");
+    if (s->ctx != ctx) return fail(SLR_E_INVALID, "slr_guided_match: the sets belong to another context");
+    if (n < 0 || raw_cap < 0) return fail(SLR_E_INVALID, "slr_guided_match: n / raw_cap negative");
+    if (plusminus < 0 || plusminus > 4) return fail(SLR_E_UNSUPPORTED, "posplusminus %d not supported (0..4)", plusminus);
+    if (slice_len < 1 || slice_len > 32 || stride < slice_len) return fail(SLR_E_UNSUPPORTED, "slice_len %d / stride %d: slices of at most 32 bytes", slice_len, stride);
+    if (post_len < 1 || s->seq_len + post_len > 32) return fail(SLR_E_UNSUPPORTED, "post_len %d: need 1 <= post_len and seq_len + post_len <= 32", post_len);
+    if (max_ed < 0 || max_ed > SLR_G_MAX_ED) return fail(SLR_E_UNSUPPORTED, "edit distance %d not supported by the guided search (0..%d)", max_ed, SLR_G_MAX_ED);
+    if (max_ed + 1 > post_len) return fail(SLR_E_INVALID, "post_len %d shorter than ed + 1 = %d", post_len, max_ed + 1);
+    return SLR_OK;
+}
+
+int slr_guided_match_dev(slr_ctx *ctx, const slr_guided_sets *s, int plusminus, int post_len, int bailout, const uint8_t *d_slices,
+                         int stride, int slice_len, const int32_t *d_anchor, const int32_t *d_group_id, const int32_t *d_ed, int max_ed,
+                         int64_t n, slr_guided_result *d_out, slr_guided_hit *d_raw_out, int raw_cap, void *stream)
+{
+    int rc = check_guided_args(ctx, s, plusminus, post_len, stride, slice_len, n, raw_cap, max_ed);
+    if (rc) return rc;
+    if (n == 0) return SLR_OK;
+    if (!d_slices || !d_anchor || !d_group_id || !d_ed || !d_out) return fail(SLR_E_INVALID, "slr_guided_match_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Slot *sl = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(sl->mtx);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaStreamWaitEvent(st, sl->gvis_free, 0));                  // the slot's visited tables may still serve an earlier launch
+    if (slr_guided_vis_bytes(max_ed, nullptr) > sl->gvis.cap) CUDA_TRY(cudaEventSynchronize(sl->gvis_free));   // about to be reallocated
+    if ((rc = sl->gvis.reserve(slr_guided_vis_bytes(max_ed, nullptr)))) return rc;
+    CUDA_TRY(slr_launch_guided_match(s->dev, s->seq_len, plusminus, post_len, bailout, d_slices, stride, slice_len, d_anchor, d_group_id, d_ed,
+                                     max_ed, n, d_out, d_raw_out, raw_cap, sl->gvis.p, ctx->work_counter(), st));
+    CUDA_TRY(cudaEventRecord(sl->gvis_free, st));
+    g_launches++;
+    return SLR_OK;
+}
+
+int slr_guided_match(slr_ctx *ctx, const slr_guided_sets *s, int plusminus, int post_len, int bailout, const uint8_t *slices, int stride,
+                     int slice_len, const int32_t *anchor, const int32_t *group_id, const int32_t *ed, int64_t n, slr_guided_result *out,
+                     slr_guided_hit *raw_out, int raw_cap)
+{
+    if (n > 0 && (!slices || !anchor || !group_id || !ed || !out)) return fail(SLR_E_INVALID, "slr_guided_match: NULL buffer");
+    int max_ed = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (ed[i] < 0) return fail(SLR_E_INVALID, "slr_guided_match: ed[%lld] = %d", (long long)i, ed[i]);
+        if (ed[i] > max_ed) max_ed = ed[i];
+    }
+    int rc = check_guided_args(ctx, s, plusminus, post_len, stride, slice_len, n, raw_cap, max_ed);
+    if (rc) return rc;
+    if (n == 0) return SLR_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Slot *sl = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(sl->mtx);
+    cudaStream_t st = sl->stream[0];
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventSynchronize(sl->gvis_free));
+    const int64_t CHUNK = 1 << 20;
+    const size_t m0 = (size_t)(n < CHUNK ? n : CHUNK);
+    if ((rc = sl->gsl.reserve(m0 * stride))) return rc;
+    if ((rc = sl->ganc.reserve(m0 * 4))) return rc;
+    if ((rc = sl->ggid.reserve(m0 * 4))) return rc;
+    if ((rc = sl->ged.reserve(m0 * 4))) return rc;
+    if ((rc = sl->gout.reserve(m0 * sizeof(slr_guided_result)))) return rc;
+    if (raw_out && raw_cap > 0 && (rc = sl->graw.reserve(m0 * raw_cap * sizeof(slr_guided_hit)))) return rc;
+    if ((rc = sl->gvis.reserve(slr_guided_vis_bytes(max_ed, nullptr)))) return rc;
+    for (int64_t off = 0; off < n; off += CHUNK) {
+        const size_t m = (size_t)(n - off < CHUNK ? n - off : CHUNK);
+        CUDA_TRY(cudaMemcpyAsync(sl->gsl.p, slices + off * stride, m * stride, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(sl->ganc.p, anchor + off, m * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(sl->ggid.p, group_id + off, m * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(sl->ged.p, ed + off, m * 4, cudaMemcpyHostToDevice, st));
+        slr_guided_hit *d_raw = (raw_out && raw_cap > 0) ? (slr_guided_hit *)sl->graw.p : nullptr;
+        if (d_raw) CUDA_TRY(cudaMemsetAsync(d_raw, 0, m * raw_cap * sizeof(slr_guided_hit), st));
+        CUDA_TRY(slr_launch_guided_match(s->dev, s->seq_len, plusminus, post_len, bailout, (const uint8_t *)sl->gsl.p, stride, slice_len,
+                                         (const int32_t *)sl->ganc.p, (const int32_t *)sl->ggid.p, (const int32_t *)sl->ged.p, max_ed,
+                                         (long long)m, (slr_guided_result *)sl->gout.p, d_raw, raw_cap, sl->gvis.p, ctx->work_counter(), st));
+        g_launches++;
+        CUDA_TRY(cudaMemcpyAsync(out + off, sl->gout.p, m * sizeof(slr_guided_result), cudaMemcpyDeviceToHost, st));
+        if (d_raw) CUDA_TRY(cudaMemcpyAsync(raw_out + off * raw_cap, d_raw, m * raw_cap * sizeof(slr_guided_hit), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return SLR_OK;
+}
+
+// DynamicEditDistances.getmaxED (DynamicEditDistances.java:L93-L98, lambda L94)
+int slr_dyn_max_ed(const int64_t *max_candidates, int n_ed, int count, int plusminus, int cap)
+{
+    if (!max_candidates || n_ed <= 0) return -1;
+    const int64_t need = (int64_t)(int32_t)((uint32_t)count * (uint32_t)(2 * plusminus + 1));     // int arithmetic, then i2l
+    int best = -1;
+    for (int e = 0; e < n_ed; e++)
+        if (max_candidates[e] >= need) best = e;                                                   // filter + max by key
+    if (best < 0) return -1;
+    if (cap >= 0 && best > cap) best = cap;
+    return best;
 }
 
 }  // extern "C"

@@ -19,3 +19,11 @@ cudaError_t slr_launch_umi_dist(const uint8_t *d_umis, int stride, int umi_len, 
 
 cudaError_t slr_launch_bc_collide(const SlrTableDev &tab, int ed_max, const unsigned long long *d_queries, long long n,
                                   slr_collide_result *d_out, cudaStream_t stream);
+
+// Illumina-guided search (guided_match.cu).  d_vis: slr_guided_vis_bytes(max_ed) bytes, zeroed by the launcher; every ed[i] <= max_ed
+#include "guided_core.cuh"
+size_t slr_guided_vis_bytes(int max_ed, int *warps_out);
+cudaError_t slr_launch_guided_match(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, int bailout, const uint8_t *d_slices,
+                                    int stride, int slice_len, const int32_t *d_anchor, const int32_t *d_group_id, const int32_t *d_ed,
+                                    int max_ed, long long n, slr_guided_result *d_out, slr_guided_hit *d_raw, int raw_cap, void *d_vis,
+                                    unsigned long long *d_work, cudaStream_t stream);

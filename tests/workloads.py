@@ -113,3 +113,77 @@ def used_list(seed, n_cells, skew=False, n_children=6):
     wl = sorted(wl)
     rng.shuffle(wl)
     return np.array(wl, dtype=np.uint64)
+
+
+# ---- Illumina-guided search ---------------------------------------------------------------------------
+G_BASES = "AGCT"                       # 2-bit order of the reference: A=0 G=1 C=2 T=3
+
+
+def g_pack(s):
+    v = 0
+    for ch in s:
+        v = (v << 2) | G_BASES.index(ch)
+    return v
+
+
+def g_unpack(v, L):
+    return "".join(G_BASES[(int(v) >> (2 * (L - 1 - i))) & 3] for i in range(L))
+
+
+def guided(seed, L, nq, max_err, pm, post_len, bc_flavour, group_sizes=(0, 1, 2, 5, 12, 40), skew=False, n_all=30, n_empty=60,
+           special=True):
+    """Synthetic guided-search batch: candidate groups (CSR), optionally the two global lists of the BC flavour, and 32-byte
+    stranded slices whose windows sit 0..max_err edits from a candidate, shifted by up to pm+1 bases, with N / IUPAC /
+    lower-case / invalid characters sprinkled in and homopolymer-rich windows (`skew`: duplicate mutants -> visited set).
+    Returns dict(group_keys, group_offsets, all_keys, empty_keys, slices, anchor, group_id, slice_len)."""
+    rng = random.Random(seed)
+    alpha = "AAAAAGCT" if skew else "AGCT"
+    rseq = lambda n, a=alpha: "".join(rng.choice(a) for _ in range(n))
+    groups = []
+    for m in group_sizes:
+        g = {g_pack(rseq(L)) for _ in range(m)}
+        if special and m >= 5:
+            g.add(g_pack("T" * L))                      # all-T: collides with the empty-slot marker of the device tables when L = 16
+            g.add(g_pack("A" * L))
+        groups.append(sorted(g))
+    allk = emptyk = None
+    if bc_flavour:
+        allk = sorted({k for g in groups for k in g} | {g_pack(rseq(L)) for _ in range(n_all)})
+        emptyk = sorted({g_pack(rseq(L)) for _ in range(n_empty)} | ({g_pack("T" * L)} if special else set()))
+    slice_len = min(32, 2 * pm + L + post_len + 2)
+    slices = np.zeros((nq, 32), dtype=np.uint8)
+    anchor = np.zeros(nq, dtype=np.int32)
+    gid = np.zeros(nq, dtype=np.int32)
+    for q in range(nq):
+        g = rng.randrange(len(groups))
+        gid[q] = g if rng.random() > 0.03 else rng.choice([-1, len(groups) + 3])
+        r = rng.random()
+        if groups[g] and r < 0.7:
+            true = g_unpack(rng.choice(groups[g]), L)
+        elif bc_flavour and r < 0.85:
+            true = g_unpack(rng.choice(allk), L)
+        elif bc_flavour and r < 0.95:
+            true = g_unpack(rng.choice(emptyk), L)
+        else:
+            true = rseq(L)
+        mid = mutate(true, rng.randrange(0, max_err + 2), rng).replace("A", rng.choice("Aa"), 1)
+        a = pm + (1 if 2 * pm + L + post_len + 1 <= 32 else 0)
+        lead = a + rng.choice([-1, 0, 0, 0, 1]) if pm > 0 else a
+        s = (rseq(max(lead, 0), "AGCT") + mid + rseq(32, "AGCT"))[:32]
+        x = rng.random()
+        if x < 0.04:
+            p = rng.randrange(32)
+            s = s[:p] + "N" + s[p + 1:]
+        elif x < 0.07:
+            p = rng.randrange(32)
+            s = s[:p] + rng.choice("RYKMSWBDHV") + s[p + 1:]
+        elif x < 0.08:
+            p = rng.randrange(32)
+            s = s[:p] + rng.choice("X*@") + s[p + 1:]
+        slices[q] = np.frombuffer(s.encode(), dtype=np.uint8)
+        anchor[q] = a if rng.random() > 0.02 else rng.choice([0, 1, 32 - L])      # windows / post leaving the slice -> exception
+    return dict(group_keys=np.array([k for g in groups for k in g], dtype=np.uint64),
+                group_offsets=np.cumsum([0] + [len(g) for g in groups]).astype(np.int64),
+                all_keys=None if allk is None else np.array(allk, dtype=np.uint64),
+                empty_keys=None if emptyk is None else np.array(emptyk, dtype=np.uint64),
+                slices=slices, anchor=anchor, group_id=gid, slice_len=slice_len, groups=groups)
