@@ -180,6 +180,7 @@ typedef struct slr_guided_sets slr_guided_sets;    /* device-resident candidate 
 #define SLR_G_W_ALL   2u   /* BC_ONLY_FOUND_IN_ALL_PASSED_10xBCs */
 #define SLR_G_W_EMPTY 4u   /* BC_IN_EMPTY_DROPS */
 #define SLR_G_EXCEPTION 1u /* the Java would have thrown for this read (N in a window, non-IUPAC char, slice too short) */
+#define SLR_G_TABLE_FULL 2u /* the device's visited table overflowed: the record is invalid (sized 4x above the measured maximum; never observed) */
 
 typedef struct {
     uint64_t seq[2];       /* sequences of the first two entries of the sorted, distinct match list (2-bit packed) */

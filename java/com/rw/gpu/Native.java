@@ -32,6 +32,17 @@ public final class Native {
     /** ClusteringEditDistanceBase.generateDistanceMatrix for all jobs of a BAM chunk (…java:L168-L259) */
     public static native int umiDist(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, ByteBuffer out,
                                      ByteBuffer outOffsets);
+    /** candidate sets of the Illumina-guided search: groupKeys / groupOffsets = CSR of the per-(gene, cell) UMIs (IlluminaOneGeneOneCellData) or of the
+     *  per-gene cell barcodes (BarcodesMap); allKeys = All10xselectedCells, emptyKeys = EmptyDropBarcodes (BC flavour, nullable)  (0 = failed) */
+    public static native long guidedSetsCreate(long ctx, long[] groupKeys, long[] groupOffsets, long[] allKeys, int allEd, long[] emptyKeys,
+                                               int emptyEd, boolean bcFlavour, int seqLen);
+    public static native void guidedSetsDestroy(long sets);
+    /** offset loop of IlluminaUMIanalyzer.findUMI (…java:L89-L136) / IlluminaBarcodeAnalyzer.testBarcodes (…java:L272-L304) + sorted().distinct()
+     *  (IlluminaBarcodeUMIAnalyzerBase.java:L52-L60) for n reads; out: n * 40 bytes (slr_guided_result); rawOut nullable: n * rawCap * 16 bytes */
+    public static native int guidedMatch(long ctx, long sets, int plusMinus, int postLen, int bailout, ByteBuffer slices, int stride, int sliceLen,
+                                         ByteBuffer anchor, ByteBuffer groupId, ByteBuffer ed, long n, ByteBuffer out, ByteBuffer rawOut, int rawCap);
+    /** DynamicEditDistances.getmaxED (DynamicEditDistances.java:L93-L98); cap < 0 = null; -1 = NoSuchElementException */
+    public static native int dynMaxEd(long[] maxCandidates, int count, int plusMinus, int cap);
     public static native String lastError();
     public static native int abiVersion();
 }

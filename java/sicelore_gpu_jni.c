@@ -99,6 +99,53 @@ JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_umiDist(JNIEnv *env, jclass cls, j
                         (int32_t *)BUF(out), (const int64_t *)BUF(outOffsets));
 }
 
+JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_guidedSetsCreate(JNIEnv *env, jclass cls, jlong ctx, jlongArray groupKeys, jlongArray groupOffsets,
+                                                                jlongArray allKeys, jint allEd, jlongArray emptyKeys, jint emptyEd,
+                                                                jboolean bcFlavour, jint seqLen)
+{
+    (void)cls;
+    const jsize ng = (*env)->GetArrayLength(env, groupOffsets) - 1;
+    jlong *gk = (*env)->GetLongArrayElements(env, groupKeys, NULL);
+    jlong *go = (*env)->GetLongArrayElements(env, groupOffsets, NULL);
+    jlong *ak = allKeys ? (*env)->GetLongArrayElements(env, allKeys, NULL) : NULL;
+    jlong *ek = emptyKeys ? (*env)->GetLongArrayElements(env, emptyKeys, NULL) : NULL;
+    slr_guided_sets *s = NULL;
+    const int rc = slr_guided_sets_create((slr_ctx *)(size_t)ctx, (const uint64_t *)gk, (const int64_t *)go, (int64_t)ng, (const uint64_t *)ak,
+                                          ak ? (int64_t)(*env)->GetArrayLength(env, allKeys) : 0, allEd, (const uint64_t *)ek,
+                                          ek ? (int64_t)(*env)->GetArrayLength(env, emptyKeys) : 0, emptyEd, bcFlavour ? 1 : 0, seqLen, &s);
+    (*env)->ReleaseLongArrayElements(env, groupKeys, gk, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, groupOffsets, go, JNI_ABORT);
+    if (ak) (*env)->ReleaseLongArrayElements(env, allKeys, ak, JNI_ABORT);
+    if (ek) (*env)->ReleaseLongArrayElements(env, emptyKeys, ek, JNI_ABORT);
+    return rc == SLR_OK ? (jlong)(size_t)s : 0;
+}
+
+JNIEXPORT void JNICALL Java_com_rw_gpu_Native_guidedSetsDestroy(JNIEnv *env, jclass cls, jlong sets)
+{
+    (void)env; (void)cls;
+    slr_guided_sets_destroy((slr_guided_sets *)(size_t)sets);
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_guidedMatch(JNIEnv *env, jclass cls, jlong ctx, jlong sets, jint plusMinus, jint postLen, jint bailout,
+                                                          jobject slices, jint stride, jint sliceLen, jobject anchor, jobject groupId, jobject ed,
+                                                          jlong n, jobject out, jobject rawOut, jint rawCap)
+{
+    (void)cls;
+    return slr_guided_match((slr_ctx *)(size_t)ctx, (const slr_guided_sets *)(size_t)sets, plusMinus, postLen, bailout, (const uint8_t *)BUF(slices),
+                            stride, sliceLen, (const int32_t *)BUF(anchor), (const int32_t *)BUF(groupId), (const int32_t *)BUF(ed), (int64_t)n,
+                            (slr_guided_result *)BUF(out), rawOut ? (slr_guided_hit *)BUF(rawOut) : NULL, rawCap);
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_dynMaxEd(JNIEnv *env, jclass cls, jlongArray maxCandidates, jint count, jint plusMinus, jint cap)
+{
+    (void)cls;
+    const jsize n = (*env)->GetArrayLength(env, maxCandidates);
+    jlong *m = (*env)->GetLongArrayElements(env, maxCandidates, NULL);
+    const int r = slr_dyn_max_ed((const int64_t *)m, (int)n, count, plusMinus, cap);
+    (*env)->ReleaseLongArrayElements(env, maxCandidates, m, JNI_ABORT);
+    return r;
+}
+
 JNIEXPORT jstring JNICALL Java_com_rw_gpu_Native_lastError(JNIEnv *env, jclass cls)
 {
     (void)cls;

@@ -210,7 +210,9 @@ static void vset_init(vset *v, int ed, int len)
     v->used = (uint8_t *)calloc(cap, 1);
     v->mask = cap - 1;
 }
-static void vset_free(vset *v) { free(v->keys); free(v->used); }
+static uint64_t g_max_visited;                 /* statistics for sizing the GPU tables (not thread safe: single-threaded probes only) */
+uint64_t orc_debug_max_visited(int reset) { uint64_t r = g_max_visited; if (reset) g_max_visited = 0; return r; }
+static void vset_free(vset *v) { if (v->count > g_max_visited) g_max_visited = v->count; free(v->keys); free(v->used); }
 static inline uint64_t vset_key(const vset *v, uint64_t seq) { return v->use64 ? seq : (uint64_t)(uint32_t)seq; } /* l2i */
 static int vset_contains(const vset *v, uint64_t seq)          /* checkWhetherAlreadyTested (L120) */
 {

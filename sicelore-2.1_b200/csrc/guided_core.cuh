@@ -64,30 +64,35 @@ SLR_GHD bool slr_g_contains(const uint32_t *slots, uint2 set, uint32_t key)
 // ---- visited set: IntHashSet on (int) seq of every node that has run a position (java:L105-L120), active for ed >= 2 ----
 // per-warp table of 64-bit slots (stamp << 32 | key); a slot whose stamp is not the current window's is empty, so the table is
 // never cleared between windows.
-SLR_GHD uint32_t slr_g_vis_log2(int ed) { return ed <= 2 ? 9u : (ed == 3 ? 16u : 22u); }
+// Sizes: the set holds the DISTINCT sequences within ed-1 edits of the window that were expanded — measured with the oracle on
+// random and homopolymer-rich 16-mers: <= 145 at ed 2, 4.1 k at ed 3, 17.7 k at ed 4 — tables of 2^9 / 2^15 / 2^17 slots.
+SLR_GHD uint32_t slr_g_vis_log2(int ed) { return ed <= 2 ? 9u : (ed == 3 ? 15u : 17u); }
 
 SLR_GHD bool slr_g_vis_contains(const unsigned long long *tab, uint32_t lg, uint32_t stamp, uint32_t key)
 {
     const uint32_t mask = (1u << lg) - 1u;
     uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;
-    while (true) {
+    for (uint32_t i = 0; i <= mask; i++) {                 // bounded: a full table cannot hang the warp
         const unsigned long long v = tab[slot];
         if ((uint32_t)(v >> 32) != stamp) return false;
         if ((uint32_t)v == key) return true;
         slot = (slot + 1u) & mask;
     }
+    return false;
 }
 
-SLR_GHD void slr_g_vis_insert(unsigned long long *tab, uint32_t lg, uint32_t stamp, uint32_t key)
+// false = the table is full (the read is then flagged SLR_G_TABLE_FULL; never observed)
+SLR_GHD bool slr_g_vis_insert(unsigned long long *tab, uint32_t lg, uint32_t stamp, uint32_t key)
 {
     const uint32_t mask = (1u << lg) - 1u;
     uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;
-    while (true) {
+    for (uint32_t i = 0; i <= mask; i++) {
         const unsigned long long v = tab[slot];
-        if ((uint32_t)(v >> 32) != stamp) { tab[slot] = ((unsigned long long)stamp << 32) | key; return; }
-        if ((uint32_t)v == key) return;
+        if ((uint32_t)(v >> 32) != stamp) { tab[slot] = ((unsigned long long)stamp << 32) | key; return true; }
+        if ((uint32_t)v == key) return true;
         slot = (slot + 1u) & mask;
     }
+    return false;
 }
 
 // ---- deque node (LongSeqMutated, LongSeqMutated.java:L44-L77) packed in 8 bytes ------------------------------------------------

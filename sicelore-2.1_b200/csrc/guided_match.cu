@@ -39,6 +39,8 @@ __device__ __forceinline__ void g_record(SlrGTop2 &T, int bc_flavour, uint32_t s
     slr_g_top2_add(T, bc_flavour, seq, cmeta, offset, where);
 }
 
+// VIS_SMEM: every ed of the batch is <= 2, the visited tables (512 slots per warp) live in shared memory
+template <bool VIS_SMEM>
 __global__ void __launch_bounds__(G_WARPS * 32)
 guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int bailout, const uint8_t *__restrict__ slices, int stride,
                     int slice_len, const int32_t *__restrict__ anchor, const int32_t *__restrict__ group_id,
@@ -46,11 +48,19 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
                     int raw_cap, unsigned long long *vis_all, uint32_t vis_lg_alloc, int max_ed, unsigned long long *work)
 {
     __shared__ GWarpShared sh[G_WARPS];
+    __shared__ unsigned long long svis[VIS_SMEM ? G_WARPS : 1][VIS_SMEM ? 512 : 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     GWarpShared &W = sh[wib];
     const long long gwarp = (long long)blockIdx.x * G_WARPS + wib;
-    unsigned long long *vis = vis_all + ((size_t)gwarp << vis_lg_alloc);
-    uint32_t stamp = 0;                                    // the table is zeroed before the launch: stamp 0 = never written
+    unsigned long long *vis;
+    if (VIS_SMEM) {
+        vis = svis[wib];
+        for (int i = lane; i < 512; i += 32) vis[i] = 0ull;
+        __syncwarp();
+    } else {
+        vis = vis_all + ((size_t)gwarp << vis_lg_alloc);
+    }
+    uint32_t stamp = 0;                                    // the table starts zeroed: stamp 0 = never written
     const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
     const int nchild = 9 * L;
 
@@ -79,7 +89,7 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
             // N (15) or a char outside ENCODE_MATRIX (-1) in the window indexes outside FOURBIT_TO_TWOBIT_MATRIX (AIOOBE)
             if (__any_sync(FULL, lane < L && c4 >= 15u)) { flags = SLR_G_EXCEPTION; break; }
             const uint32_t postbad = __ballot_sync(FULL, lane >= L && lane < L + post_len && c4 == 0xFFu) >> L;   // thrown only if used
-            bool throws = false;
+            bool throws = false, throws_full = false;
             const uint32_t two = slr_g_two_of_code4(c4);
             const uint32_t w = __reduce_or_sync(FULL, lane < L ? two << (2 * (L - 1 - lane)) : 0u);     // getLongHashForBytes
             const uint32_t post2 = __reduce_or_sync(FULL, (lane >= L && lane < L + post_len && lane - L < 16) ? two << (2 * (lane - L)) : 0u);
@@ -126,7 +136,7 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
                         }
                     }
                     if (use_vis) {
-                        if (lane == 0) slr_g_vis_insert(vis, vlg, stamp, node.seq);
+                        if (lane == 0 && !slr_g_vis_insert(vis, vlg, stamp, node.seq)) throws_full = true;
                         __syncwarp();
                     }
                     continue;
@@ -163,10 +173,11 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
                     W.stack[at].meta = slr_g_next_level_meta((cmeta & ~(1u << 23)) | ((uint32_t)inh << 23), pos);
                 }
                 sp += __popc(pm);
-                if (use_vis && lane == 0) slr_g_vis_insert(vis, vlg, stamp, node.seq);                  // addToTestedSeqs (java:L122)
+                if (use_vis && lane == 0 && !slr_g_vis_insert(vis, vlg, stamp, node.seq)) throws_full = true;   // addToTestedSeqs (java:L122)
                 __syncwarp();
             }
             if (__any_sync(FULL, throws)) flags = SLR_G_EXCEPTION;     // a deletion used an invalid post base somewhere in this window
+            if (__any_sync(FULL, throws_full)) flags |= SLR_G_TABLE_FULL;
         }
         if (lane == 0) slr_g_top2_store(T, flags, out[q]);
         __syncwarp();
@@ -175,15 +186,28 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
 
 }  // namespace
 
+// one wave of persistent CTAs: #SMs x resident CTAs per SM (registers / shared memory decide).  Returns the bytes of per-warp
+// visited tables that wave needs in global memory (8 for ed <= 2; 256 KB per warp at ed 3, 1 MB at ed 4).
 size_t slr_guided_vis_bytes(int max_ed, int *warps_out)
 {
-    int dev = 0, sms = 148;
+    static int per_sm[64][2], sms_of[64];
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // resident warps: 2 CTAs of 8 warps per SM; the 32 MB tables of ed = 4 get one CTA on every second SM
-    const int ctas = max_ed >= 4 ? (sms / 2 > 0 ? sms / 2 : 1) : 2 * sms;
+    dev &= 63;
+    const int v = max_ed <= 2 ? 1 : 0;
+    if (per_sm[dev][v] == 0) {
+        int bps = 0, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (v) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, guided_match_kernel<true>, G_WARPS * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, guided_match_kernel<false>, G_WARPS * 32, 0);
+        per_sm[dev][v] = bps > 0 ? bps : 1;
+        sms_of[dev] = sms;
+    }
+    const int sms = sms_of[dev];
+    const int ctas = per_sm[dev][v] * sms;
     const int warps = ctas * G_WARPS;
     if (warps_out) *warps_out = warps;
+    if (max_ed <= 2) return 8;
     return ((size_t)warps << slr_g_vis_log2(max_ed)) * sizeof(unsigned long long);
 }
 
@@ -201,8 +225,13 @@ cudaError_t slr_launch_guided_match(const SlrGuidedSetsDev &S, int L, int plusmi
     const long long need = (n + G_WARPS - 1) / G_WARPS;
     const long long resident = warps / G_WARPS;
     const unsigned blocks = (unsigned)(need < resident ? need : resident);
-    guided_match_kernel<<<blocks, G_WARPS * 32, 0, stream>>>(S, L, plusminus, post_len, bailout, d_slices, stride, slice_len, d_anchor,
-                                                            d_group_id, d_ed, n, d_out, d_raw, raw_cap, (unsigned long long *)d_vis,
-                                                            slr_g_vis_log2(max_ed), max_ed, d_work);
+    if (max_ed <= 2)
+        guided_match_kernel<true><<<blocks, G_WARPS * 32, 0, stream>>>(S, L, plusminus, post_len, bailout, d_slices, stride, slice_len, d_anchor,
+                                                                      d_group_id, d_ed, n, d_out, d_raw, raw_cap, (unsigned long long *)d_vis,
+                                                                      slr_g_vis_log2(max_ed), max_ed, d_work);
+    else
+        guided_match_kernel<false><<<blocks, G_WARPS * 32, 0, stream>>>(S, L, plusminus, post_len, bailout, d_slices, stride, slice_len, d_anchor,
+                                                                       d_group_id, d_ed, n, d_out, d_raw, raw_cap, (unsigned long long *)d_vis,
+                                                                       slr_g_vis_log2(max_ed), max_ed, d_work);
     return cudaGetLastError();
 }

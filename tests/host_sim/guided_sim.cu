@@ -78,7 +78,7 @@ void sim_query(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, in
                     for (int lane = 0; lane < 32; lane++)
                         if (wh_[lane]) { sim_record(T, S.bc_flavour, s_[lane], cm_[lane], level, o, wh_[lane], raw, raw_cap); nlist++; }
                 }
-                if (use_vis) slr_g_vis_insert(vis, vlg, stamp, node.seq);
+                if (use_vis && !slr_g_vis_insert(vis, vlg, stamp, node.seq)) flags |= SLR_G_TABLE_FULL;
                 continue;
             }
             const int pos = slr_g_pos_cur(node.meta) + 1;
@@ -109,7 +109,7 @@ void sim_query(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, in
                     stack[sp].meta = slr_g_next_level_meta((cm_[lane] & ~(1u << 23)) | ((uint32_t)inh_[lane] << 23), pos);
                     sp++;
                 }
-            if (use_vis) slr_g_vis_insert(vis, vlg, stamp, node.seq);
+            if (use_vis && !slr_g_vis_insert(vis, vlg, stamp, node.seq)) flags |= SLR_G_TABLE_FULL;
         }
         if (throws) flags = SLR_G_EXCEPTION;
     }

@@ -104,6 +104,16 @@ def test_sim_vs_oracle(sim, orc, case):
         assert (exp["n_raw"] > 0).sum() > 0 or nq < 10
 
 
+@pytest.mark.parametrize("L,post_len,bc", [(12, 6, False), (16, 10, True)])
+def test_sim_ed4_full_length(sim, orc, L, post_len, bc):
+    """the deepest supported search (IlluminaUMIanalyzer.java:L75: ed < 5) at real UMI / barcode lengths: ~0.5-2 M probes per window"""
+    w = workloads.guided(900 + L, L, 6, 4, 1, post_len, bc)
+    exp, eraw, _ = oracle_run(orc, w, L, 4, 1, post_len, 2 if bc else None, bc)
+    got, graw = sim_run(sim, orc, w, L, 4, 1, post_len, 2 if bc else None, bc)
+    assert_same(got, graw, exp, eraw, "ED 4")
+    assert (exp["n_raw"] > 0).any()
+
+
 def test_sim_mixed_edit_distances(sim, orc):
     """dynamic ED: every read carries its own maxEDdyn; the stamped visited table is shared by windows of different table sizes"""
     w = workloads.guided(77, 12, 120, 2, 2, 6, False)
@@ -253,6 +263,15 @@ def test_gpu_vs_oracle(pkg, ctx, orc, case):
         exp, eraw, _ = oracle_run(orc, w, L, ed, pm, post_len, bailout, bc)
         got, graw = gpu_run(pkg, ctx, w, L, ed, pm, post_len, bailout, bc)
         assert_same(got, graw, exp, eraw, "GPU")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,post_len,bc", [(12, 6, False), (16, 10, True)])
+def test_gpu_ed4_full_length(pkg, ctx, orc, L, post_len, bc):
+    w = workloads.guided(900 + L, L, 64, 4, 1, post_len, bc)
+    exp, eraw, _ = oracle_run(orc, w, L, 4, 1, post_len, 2 if bc else None, bc)
+    got, graw = gpu_run(pkg, ctx, w, L, 4, 1, post_len, 2 if bc else None, bc)
+    assert_same(got, graw, exp, eraw, "GPU ED 4")
 
 
 @pytest.mark.gpu
