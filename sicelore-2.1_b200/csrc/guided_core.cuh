@@ -144,6 +144,66 @@ SLR_GHD uint32_t slr_g_child(uint32_t seq, uint32_t meta, int L, int p, int j, u
     return is_sub ? sub : (is_ins ? ins : del);
 }
 
+// ---- candidate filter of a last-level node --------------------------------------------------------------------------------------
+// Necessary condition for "c is a child of s" (one SUB, INS or DEL of the engine on an L-mer): c and s share a prefix, and the rest of c
+// equals the rest of s either in place (SUB at p: prefix p, suffix L-1-p), shifted towards the end (INS after p: prefix p+1, then
+// c[i] = s[i-1] for i >= p+2) or shifted towards the start (DEL at p: prefix p, c[i] = s[i+1] for p <= i <= L-2; the appended post base is
+// not checked).  A last-level node none of whose candidates passes cannot produce a hit: its batch of 9·L children is skipped (the
+// node still enters the visited set); otherwise only the positions that can hit are run.  Conservative by construction; tests
+// enumerate every child of random nodes.
+SLR_GHD int slr_g_clz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+SLR_GHD int slr_g_ctz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;                // x != 0
+#else
+    return __builtin_ctz(x);
+#endif
+}
+// pmin / pmax: the positions at which a child of s can equal c (SUB: the one differing digit; INS after p: prefix >= p+1 and shifted
+// suffix from p+2; DEL at p: prefix >= p and shifted suffix from p) — the batch only has to run those positions.
+SLR_GHD bool slr_g_may_be_child(uint32_t c, uint32_t s, int L, int &pmin, int &pmax)
+{
+    const uint32_t fm = L >= 16 ? 0xFFFFFFFFu : ((1u << (2 * L)) - 1u);
+    c &= fm;
+    const uint32_t x0 = (c ^ s) & fm;
+    const int lead = x0 ? ((slr_g_clz32(x0) - (32 - 2 * L)) >> 1) : L;         // equal leading digits
+    const int t0 = x0 ? (slr_g_ctz32(x0) >> 1) : L;                            // equal trailing digits
+    const uint32_t x1 = (c ^ (s >> 2)) & fm;
+    const int t1 = x1 ? (slr_g_ctz32(x1) >> 1) : L;                            // trailing digits with c[i] == s[i-1]
+    const uint32_t x2 = ((c ^ (s << 2)) & fm) >> 2;
+    const int t2 = (x2 ? (slr_g_ctz32(x2) >> 1) : L) + 1;                      // trailing digits with c[i] == s[i+1], the last one granted
+    int lo = L, hi = -1;
+    if (x0 && lead + t0 >= L - 1) { lo = lead; hi = lead; }                    // SUB at p = lead (x0 == 0: a substitution never recreates s)
+    const int ilo = L - 2 - t1 > 0 ? L - 2 - t1 : 0, ihi = lead - 1 < L - 2 ? lead - 1 : L - 2;
+    if (ilo <= ihi) { lo = ilo < lo ? ilo : lo; hi = ihi > hi ? ihi : hi; }    // INS after p in [L-2-t1, lead-1]
+    const int dlo = L - t2 > 0 ? L - t2 : 0, dhi = lead < L - 1 ? lead : L - 1;
+    if (dlo <= dhi) { lo = dlo < lo ? dlo : lo; hi = dhi > hi ? dhi : hi; }    // DEL at p in [L-t2, lead]
+    pmin = lo; pmax = hi;
+    return lo <= hi;
+}
+// slot `i` of a small group's table as a filter candidate: valid unless the slot is the empty marker of a group without the all-T key
+SLR_GHD bool slr_g_filter_slot(const uint32_t *slots, uint2 set, uint32_t i, uint32_t &cand)
+{
+    const uint32_t meta = set.y;
+    cand = 0u;
+    if (!(meta & 0x200u) || i >= (1u << (meta & 31u))) return false;
+#if defined(__CUDA_ARCH__)
+    cand = __ldg(slots + set.x + i);
+#else
+    cand = slots[set.x + i];
+#endif
+    return cand != SLR_G_EMPTY || (meta & 0x100u) != 0u;
+}
+SLR_GHD bool slr_g_filter_usable(uint2 set) { return !(set.y & 0x200u) || (set.y & 31u) <= 6u; }    // empty group or <= 64 slots
+
 // ---- checkMatchWithTestSets: 0 = no hit, else SLR_G_W_* bits of the list entry; inh_out = GENE bit now on the node ------
 SLR_GHD uint32_t slr_g_probe(const SlrGuidedSetsDev &S, uint2 group, uint32_t s, uint32_t meta, int level, bool &inh_out)
 {

@@ -41,7 +41,7 @@ __device__ __forceinline__ void g_record(SlrGTop2 &T, int bc_flavour, uint32_t s
 
 // VIS_SMEM: every ed of the batch is <= 2, the visited tables (512 slots per warp) live in shared memory
 template <bool VIS_SMEM>
-__global__ void __launch_bounds__(G_WARPS * 32)
+__global__ void __launch_bounds__(G_WARPS * 32, VIS_SMEM ? 4 : 3)
 guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int bailout, const uint8_t *__restrict__ slices, int stride,
                     int slice_len, const int32_t *__restrict__ anchor, const int32_t *__restrict__ group_id,
                     const int32_t *__restrict__ ed_arr, long long n, slr_guided_result *__restrict__ out, slr_guided_hit *raw_out,
@@ -78,6 +78,12 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
         slr_guided_hit *raw = raw_out ? raw_out + (size_t)q * raw_cap : nullptr;
         const uint32_t vlg = slr_g_vis_log2(ed);
         const bool use_vis = ed >= 2;                      // MINED_TOHASHTESTED_* = 2 (java:L82-L83)
+        // candidate filter of the last level (guided_core.cuh): lane i holds slots i and 32 + i of a small group's table
+        uint32_t cand0, cand1;
+        const bool cok0 = slr_g_filter_slot(S.slots, group, (uint32_t)lane, cand0), cok1 = slr_g_filter_slot(S.slots, group, 32u + lane, cand1);
+        // usable when the group is small and, in the BC flavour, the global lists are not probed at the last level (= ed)
+        const bool filt_leaf = slr_g_filter_usable(group) &&
+                               !(S.bc_flavour && (((S.all_set.y & 0x200u) && ed <= S.all_ed) || ((S.empty_set.y & 0x200u) && ed <= S.empty_ed)));
         SlrGTop2 T;
         slr_g_top2_init(T);
         uint32_t flags = (ed < 0 || ed > max_ed) ? SLR_G_EXCEPTION : 0u;      // host entry points refuse such a batch
@@ -117,11 +123,24 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
                 if (level == ed) {
                     // ---- last level: every position of this node, 32 children per step ----
                     const int p0 = pos_prev == 0 ? 1 : 0;  // first position that runs; node.seq is "tested" after it (java:L122)
-                    for (int c0 = 0; c0 < nchild; c0 += 32) {
+                    // skip the batch when no child can hit: a dead node, or (small group, the global lists out of reach at this level, no
+                    // invalid post base a deletion would trip over) no candidate within one edit of the node; else run only the
+                    // positions at which some candidate can be hit
+                    int c_lo = 0, c_hi = nchild - 1;
+                    bool run = !slr_g_dead(node.meta);
+                    if (run && filt_leaf && postbad == 0u) {
+                        int a0 = L, b0 = -1, a1 = L, b1 = -1;
+                        if (cok0) slr_g_may_be_child(cand0, node.seq, L, a0, b0);
+                        if (cok1) slr_g_may_be_child(cand1, node.seq, L, a1, b1);
+                        const int pmin = __reduce_min_sync(FULL, a0 < a1 ? a0 : a1), pmax = __reduce_max_sync(FULL, b0 > b1 ? b0 : b1);
+                        run = pmin <= pmax;
+                        c_lo = 9 * pmin; c_hi = 9 * pmax + 8;
+                    }
+                    for (int c0 = c_lo; run && c0 <= c_hi; c0 += 32) {
                         const int c = c0 + lane, p = c / 9, j = c - 9 * p;
                         bool valid = false, inh;
                         uint32_t cmeta = 0, s = 0, where = 0;
-                        if (c < nchild && p != pos_prev) {                                               // java:L109-L110
+                        if (c <= c_hi && p != pos_prev) {                                                // java:L109-L110
                             s = slr_g_child(node.seq, node.meta, L, p, j, post2, postbad, post_len, valid, cmeta, throws);
                             if (valid && use_vis && ((s == node.seq && p > p0) || slr_g_vis_contains(vis, vlg, stamp, s))) valid = false;
                             if (valid) where = slr_g_probe(S, group, s, cmeta, level, inh);

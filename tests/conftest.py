@@ -41,6 +41,9 @@ def sim():
     L.sim_guided_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    L.sim_guided_filter_skips.restype = C.c_longlong
+    L.sim_guided_filter_violations.restype = C.c_longlong
+    L.sim_guided_filter_violations.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_ulonglong]
     return L
 
 

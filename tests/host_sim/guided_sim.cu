@@ -7,6 +7,9 @@
 
 namespace {
 
+int sim_no_filter = 0;             // sim_guided_set_filter(0): run every last-level batch (checks that skipping is exact)
+long long sim_filter_skips = 0;
+
 void sim_record(SlrGTop2 &T, int bc_flavour, uint32_t seq, uint32_t cmeta, int level, int offset, uint32_t where, slr_guided_hit *raw, int raw_cap)
 {
     if (raw && T.n_raw < raw_cap) {
@@ -27,6 +30,11 @@ void sim_query(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, in
     const uint32_t vlg = slr_g_vis_log2(ed);
     const bool use_vis = ed >= 2;
     const int nchild = 9 * L;
+    uint32_t cand[64];
+    bool cok[64];
+    for (uint32_t i = 0; i < 64; i++) cok[i] = slr_g_filter_slot(S.slots, group, i, cand[i]);
+    const bool filt_leaf = slr_g_filter_usable(group) &&
+                           !(S.bc_flavour && (((S.all_set.y & 0x200u) && ed <= S.all_ed) || ((S.empty_set.y & 0x200u) && ed <= S.empty_ed)));
     SlrGTop2 T;
     slr_g_top2_init(T);
     uint32_t flags = (ed < 0 || ed > max_ed) ? SLR_G_EXCEPTION : 0u;
@@ -62,13 +70,27 @@ void sim_query(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, in
             const int level = slr_g_level(node.meta), pos_prev = slr_g_pos_prev(node.meta);
             if (level == ed) {
                 const int p0 = pos_prev == 0 ? 1 : 0;
-                for (int c0 = 0; c0 < nchild; c0 += 32) {
+                int c_lo = 0, c_hi = nchild - 1;
+                bool run = !slr_g_dead(node.meta);
+                if (run && filt_leaf && postbad == 0u && !sim_no_filter) {
+                    int pmin = L, pmax = -1;
+                    for (int i = 0; i < 64; i++) {
+                        int a = L, b = -1;
+                        if (cok[i]) slr_g_may_be_child(cand[i], node.seq, L, a, b);
+                        if (a < pmin) pmin = a;
+                        if (b > pmax) pmax = b;
+                    }
+                    run = pmin <= pmax;
+                    c_lo = 9 * pmin; c_hi = 9 * pmax + 8;
+                    sim_filter_skips += !run;
+                }
+                for (int c0 = c_lo; run && c0 <= c_hi; c0 += 32) {
                     uint32_t s_[32], cm_[32], wh_[32];
                     for (int lane = 0; lane < 32; lane++) {          // all lanes of a step see the same visited table
                         const int c = c0 + lane, p = c / 9, j = c - 9 * p;
                         bool valid = false, inh;
                         uint32_t cmeta = 0, s = 0, where = 0;
-                        if (c < nchild && p != pos_prev) {
+                        if (c <= c_hi && p != pos_prev) {
                             s = slr_g_child(node.seq, node.meta, L, p, j, post2, postbad, post_len, valid, cmeta, throws);
                             if (valid && use_vis && ((s == node.seq && p > p0) || slr_g_vis_contains(vis, vlg, stamp, s))) valid = false;
                             if (valid) where = slr_g_probe(S, group, s, cmeta, level, inh);
@@ -138,4 +160,31 @@ extern "C" void sim_guided_batch(const uint64_t *group_keys, const int64_t *grou
     for (int64_t i = 0; i < n; i++)
         sim_query(S, L, plusminus, post_len, bailout, slices + (size_t)i * stride, slice_len, anchor[i], group_id[i], ed[i], max_ed, &out[i],
                   raw_out ? raw_out + (size_t)i * raw_cap : nullptr, raw_cap, vis.data(), stamp);
+}
+
+extern "C" void sim_guided_set_filter(int on) { sim_no_filter = !on; }
+extern "C" long long sim_guided_filter_skips(int reset) { const long long r = sim_filter_skips; if (reset) sim_filter_skips = 0; return r; }
+
+// every child the engine can create from `n` random nodes must pass slr_g_may_be_child: returns the number of violations
+extern "C" long long sim_guided_filter_violations(int L, int post_len, long long n, unsigned long long seed)
+{
+    unsigned long long x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (uint32_t)(x >> 16); };
+    const uint32_t fm = L >= 16 ? 0xFFFFFFFFu : ((1u << (2 * L)) - 1u);
+    long long bad = 0;
+    for (long long i = 0; i < n; i++) {
+        uint32_t s = rnd() & fm;
+        if (i % 3 == 0) s &= rnd() & rnd();                    // homopolymer-rich
+        const uint32_t post2 = rnd();
+        const uint32_t meta = slr_g_root_meta() | ((rnd() % 3u) << 19);     // nDeletions 0..2 picks the appended post base
+        for (int p = 0; p < L; p++)
+            for (int j = 0; j < 9; j++) {
+                bool valid, throws = false;
+                uint32_t cm;
+                const uint32_t c = slr_g_child(s, meta, L, p, j, post2, 0u, post_len, valid, cm, throws);
+                int a = L, b = -1;
+                if (valid && !(slr_g_may_be_child(c, s, L, a, b) && a <= p && p <= b)) bad++;      // passes, and p lies in the reported range
+            }
+    }
+    return bad;
 }

@@ -114,6 +114,26 @@ def test_sim_ed4_full_length(sim, orc, L, post_len, bc):
     assert (exp["n_raw"] > 0).any()
 
 
+def test_candidate_filter_is_conservative(sim, orc):
+    """the last-level batch of a node is skipped when no candidate of a small group can be one of its children: every child the engine
+    can create passes the filter (exhaustive over positions x operations of random nodes), skipping changes no field of any record,
+    and it does skip most batches"""
+    for L, post_len in ((12, 6), (16, 10), (8, 5), (5, 4)):
+        assert sim.sim_guided_filter_violations(L, post_len, 20000, L) == 0
+    w = workloads.guided(55, 12, 200, 2, 2, 6, False, skew=True)
+    sim.sim_guided_filter_skips(1)
+    got, graw = sim_run(sim, orc, w, 12, 2, 2, 6, None, False)
+    skips = sim.sim_guided_filter_skips(1)
+    sim.sim_guided_set_filter(0)
+    try:
+        ref, rraw = sim_run(sim, orc, w, 12, 2, 2, 6, None, False)
+    finally:
+        sim.sim_guided_set_filter(1)
+    assert sim.sim_guided_filter_skips(1) == 0
+    assert_same(got, graw, ref, rraw, "filter on vs off")
+    assert skips > 10000
+
+
 def test_sim_mixed_edit_distances(sim, orc):
     """dynamic ED: every read carries its own maxEDdyn; the stamped visited table is shared by windows of different table sizes"""
     w = workloads.guided(77, 12, 120, 2, 2, 6, False)
