@@ -1,0 +1,88 @@
+"""Formats either side of the hot path.  The read-name tests are pinned by the reference's own published examples
+(/root/reference/README.md:400 and :452, quoted below verbatim)."""
+import os
+
+import numpy as np
+
+import __graft_entry__ as g
+
+README_400 = ("_FWD_PS=566_PE=590_AE=619_bc=TCCGATCGTGCCAAGA_ed=0_ed_sec=2147483647_bcStart=618_bcEnd=603_rk=2987_"
+              "X=AAAAAAAAAAAATGGCGTGTATTGTCTTGGCACGATCGGAAGA_Q=27.1")
+README_452 = ("_REV_PS=1257_PE=1305_AE=1327_T=40_bc=GAGTGAGGTTGGGTAG_ed=1_ed_sec=2147483647_bcStart=1326_bcEnd=1311_rk=3883_"
+              "X=AAAAAAAAAAACAAACCAAGTAACCAACCCAACCTCACTCAGA_Q=15.9")
+
+
+def fmt():
+    pkg = g.load_package()
+    import importlib
+    return importlib.import_module("sicelore_b200.formats")
+
+
+def test_parse_readme_examples():
+    F = fmt()
+    a = F.parse_read_name("b5c7a1f2-read" + README_400)
+    assert a == dict(reversed=False, polya_start=566, polya_end=590, adapter_end=619, ed=0, bc="TCCGATCGTGCCAAGA", ed_second=2147483647,
+                     bc_start=618, bc_end=603, rank=2987, seq="AAAAAAAAAAAATGGCGTGTATTGTCTTGGCACGATCGGAAGA", mean_qv=float(np.float32(27.1)))
+    b = F.parse_read_name("sp2" + README_452)
+    assert b["reversed"] and b["tso_end"] == 40 and b["adapter_end"] == 1327 and b["bc"] == "GAGTGAGGTTGGGTAG" and b["ed"] == 1
+    assert b["bc_start"] == 1326 and b["bc_end"] == 1311 and b["rank"] == 3883 and abs(b["mean_qv"] - 15.9) < 1e-6
+    assert F.parse_read_name("read_without_tags") is None
+    # the assignumis limit on the barcode ED drops the barcode block (FastqRecordExt.java:L450-L459)
+    c = F.parse_read_name("x" + README_452, max_bc_ed=0)
+    assert "bc" not in c and "rank" not in c and c["adapter_end"] == 1327
+
+
+def test_write_reproduces_readme_examples():
+    """rebuild the stranded read around the published X= string and write the extension back: identical up to the published end"""
+    F = fmt()
+    for ex, qv in ((README_400, 27.1), (README_452, 15.9)):
+        p = F.parse_read_name("r" + ex)
+        ae, x = p["adapter_end"], p["seq"]
+        begin = ae - 40 - 1                               # 3' geometry (L253): X = stranded[AE-41, AE+2)
+        stranded = "C" * begin + x + "G" * 50
+        # quality string whose mean formats as the published Q=; getMeanQV(quals, begin, end) skips begin - 1 chars and takes
+        # end - begin + 1: the base before the X= range is averaged in as well (FastqRecordExt.java:L57-L59, L270)
+        q_lo, q_hi, n = int(qv), int(qv) + 1, len(x) + 1
+        n_hi = round((qv - q_lo) * n)
+        quals = "I" * (begin - 1) + chr(33 + q_hi) * n_hi + chr(33 + q_lo) * (n - n_hi) + "I" * 50
+        out = F.read_name_extension(p["reversed"], stranded, quals, adapter_end=ae, polya_start=p["polya_start"], polya_end=p["polya_end"],
+                                    tso_end=p.get("tso_end"), bc=p["bc"], ed=p["ed"], ed_second=p["ed_second"], bc_start=p["bc_start"],
+                                    bc_end=p["bc_end"], rank=p["rank"])
+        assert out.startswith(ex + "_"), (out, ex)
+        assert out.endswith(" cellBC=" + p["bc"])
+        assert F.parse_read_name("r" + out.split(" ")[0]) == p                  # round trip
+
+
+def test_barcode_geometry_of_readme_examples():
+    """bc= is the reverse complement of X[-19:-3] up to `ed` edits; bcStart - bcEnd = 15 (3' reads count down towards the polyA)"""
+    F = fmt()
+    rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    a = F.parse_read_name("r" + README_400)
+    assert rc(a["seq"][-19:-3]) == a["bc"] and a["bc_start"] - a["bc_end"] == 15 and a["bc_start"] == a["adapter_end"] - 1
+    b = F.parse_read_name("r" + README_452)
+    w = rc(b["seq"][-19:-3])
+    assert sum(x != y for x, y in zip(w, b["bc"])) == b["ed"] == 1
+
+
+def test_decimal_format():
+    F = fmt()
+    assert F._dec_format_1(27.1) == "27.1" and F._dec_format_1(27.0) == "27" and F._dec_format_1(9.96) == "10" and F._dec_format_1(0.25) == "0.2"
+
+
+def test_assigned_tsv_round_trip(tmp_path):
+    F = fmt()
+    pkg = g.load_package()
+    keys = np.array([pkg.pack_barcode(s) for s in ("CGGACTGTCTTGTACT", "AGCCTAAAGGGAAACA", "ACCCACTCAGTTCCCT", "TTTTTTTTTTTTTTTT")], dtype=np.uint64)
+    counts = np.array([[118919, 21693, 5], [88046, 36699, 0], [8499, 112448, 0], [0, 0, 0]], dtype=np.int64)
+    path = str(tmp_path / "BarcodesAssigned.tsv")
+    assert F.write_assigned_tsv(path, keys, counts, 1) == 3                     # the unassigned barcode is not listed
+    lines = open(path).read().split("\n")
+    assert lines[0] == "Barcode\tn Reads with ED<=1 match\tED=0\tED=1"
+    # the three rows the comment block of SelectValidCellBarcode.java:44-48 shows, in descending order of reads
+    assert lines[1] == "CGGACTGTCTTGTACT\t140,612\t118,919\t21,693"
+    assert lines[2] == "AGCCTAAAGGGAAACA\t124,745\t88,046\t36,699"
+    assert lines[3] == "ACCCACTCAGTTCCCT\t120,947\t8,499\t112,448"
+    rows = F.read_assigned_tsv(path)
+    assert rows[0] == ("CGGACTGTCTTGTACT", 140612, 118919, 21693) and len(rows) == 3
+    F.write_assigned_tsv(path, keys, counts, 2)
+    assert open(path).readline() == "Barcode\tn Reads with ED<=2 match\tED=0\tED=1\tED=2\n"
