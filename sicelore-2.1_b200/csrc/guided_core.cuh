@@ -95,6 +95,27 @@ SLR_GHD bool slr_g_vis_insert(unsigned long long *tab, uint32_t lg, uint32_t sta
     return false;
 }
 
+#if defined(__CUDACC__)
+// concurrent insert by the lanes of one warp (batched nodes): the slot is claimed with a 64-bit CAS
+static __device__ __forceinline__ bool slr_g_vis_insert_atomic(unsigned long long *tab, uint32_t lg, uint32_t stamp, uint32_t key)
+{
+    const uint32_t mask = (1u << lg) - 1u;
+    uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;
+    const unsigned long long want = ((unsigned long long)stamp << 32) | key;
+    for (uint32_t i = 0; i <= mask;) {
+        const unsigned long long v = *((volatile unsigned long long *)&tab[slot]);
+        if (v == want) return true;
+        if ((uint32_t)(v >> 32) != stamp) {
+            if (atomicCAS(&tab[slot], v, want) == v) return true;
+            continue;                                           // another lane took the slot: look at it again
+        }
+        slot = (slot + 1u) & mask;
+        i++;
+    }
+    return false;
+}
+#endif
+
 // ---- deque node (LongSeqMutated, LongSeqMutated.java:L44-L77) packed in 8 bytes ------------------------------------------------
 // meta: bits 0-4 posTreatedInCurrentCycle + 1, 5-9 posTreatedInPreviousLevel + 1, 10-12 currentlevel, 13-15 nSubstitutions,
 //       16-18 nInsertions, 19-21 nDeletions, 22 "dead" (bits 62-63 of the Java long are set), 23 findingErrorFlag GENE bit
@@ -203,6 +224,62 @@ SLR_GHD bool slr_g_filter_slot(const uint32_t *slots, uint2 set, uint32_t i, uin
     return cand != SLR_G_EMPTY || (meta & 0x100u) != 0u;
 }
 SLR_GHD bool slr_g_filter_usable(uint2 set) { return !(set.y & 0x200u) || (set.y & 31u) <= 6u; }    // empty group or <= 64 slots
+
+// ---- "far node" test of a node one level above the last ------------------------------------------------------------------------
+// One engine operation x -> x' is one Levenshtein edit between prefixes: SUB Lev(x, x') = 1, INS Lev(x[:L-1], x') = 1 (the last base is
+// pushed out), DEL Lev(x, x'[:L-1]) = 1 (an unchecked base is pulled in).  Cutting one more base off either side of such a pair keeps the
+// distance <= 1 for a suitable cut of the other side, so a candidate c reachable from s with <= 2 operations satisfies
+//     Lev(s[:i], c[:j]) <= 2   for some i, j in L-2..L
+// (necessary, not sufficient: the engine's visited set, position skip and dead values only remove paths).  Myers / Hyyro bit-parallel
+// global edit distance, pattern = candidate (its four match masks are per-read constants), text = node: the last-row score and the two top
+// vertical deltas after the columns L-2..L give the nine values.  A node that is far from every candidate cannot produce a hit in its
+// whole subtree.
+struct SlrGPeq { uint32_t eq[4]; };
+SLR_GHD SlrGPeq slr_g_peq(uint32_t c, int L)
+{
+    SlrGPeq P;
+    P.eq[0] = P.eq[1] = P.eq[2] = P.eq[3] = 0u;
+    for (int i = 0; i < L; i++) {
+        const uint32_t d = (c >> (2 * (L - 1 - i))) & 3u;        // pattern position i (0 = first base) -> bit i
+        P.eq[0] |= (uint32_t)(d == 0u) << i; P.eq[1] |= (uint32_t)(d == 1u) << i;
+        P.eq[2] |= (uint32_t)(d == 2u) << i; P.eq[3] |= (uint32_t)(d == 3u) << i;
+    }
+    return P;
+}
+SLR_GHD int slr_g_popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+SLR_GHD bool slr_g_within2(const SlrGPeq &P, uint32_t s, int L)
+{
+    const uint32_t ones = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    uint32_t Pv = ones, Mv = 0u;
+    int score = L, best = 99;                                     // score = D[L][j] = Lev(c, s[:j])
+    for (int j = 0; j < L; j++) {
+        const uint32_t d = (s >> (2 * (L - 1 - j))) & 3u;
+        const uint32_t Eq = d == 0u ? P.eq[0] : d == 1u ? P.eq[1] : d == 2u ? P.eq[2] : P.eq[3];
+        const uint32_t Xv = Eq | Mv;
+        const uint32_t Xh = ((((Eq & Pv) + Pv) ^ Pv) | Eq) & ones;
+        uint32_t Ph = (Mv | ~(Xh | Pv)) & ones;
+        uint32_t Mh = Pv & Xh;
+        score += (int)((Ph >> (L - 1)) & 1u) - (int)((Mh >> (L - 1)) & 1u);
+        Ph = ((Ph << 1) | 1u) & ones;                              // D[0][j] = j
+        Mh = (Mh << 1) & ones;
+        Pv = (Mh | ~(Xv | Ph)) & ones;
+        Mv = Ph & Xv;
+        if (j >= L - 3) {                                          // columns L-2..L: D[L][.], D[L-1][.], D[L-2][.]
+            const int d1 = score - (int)((Pv >> (L - 1)) & 1u) + (int)((Mv >> (L - 1)) & 1u);
+            const int d2 = d1 - (int)((Pv >> (L - 2)) & 1u) + (int)((Mv >> (L - 2)) & 1u);
+            const int m = score < d1 ? (score < d2 ? score : d2) : (d1 < d2 ? d1 : d2);
+            if (m < best) best = m;
+        }
+    }
+    return best <= 2;
+}
 
 // ---- checkMatchWithTestSets: 0 = no hit, else SLR_G_W_* bits of the list entry; inh_out = GENE bit now on the node ------
 SLR_GHD uint32_t slr_g_probe(const SlrGuidedSetsDev &S, uint2 group, uint32_t s, uint32_t meta, int level, bool &inh_out)

@@ -24,6 +24,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct GWarpShared {
     SlrGNode stack[SLR_G_STACK];
     uint8_t codes[32];
+    uint32_t peq[2][4][32];                    // match masks of the lane's two filter candidates (slr_g_peq), per-read constants
 };
 
 // list order bookkeeping of one hit (all lanes hold the same state); lane 0 writes the optional raw record
@@ -84,6 +85,13 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
         // usable when the group is small and, in the BC flavour, the global lists are not probed at the last level (= ed)
         const bool filt_leaf = slr_g_filter_usable(group) &&
                                !(S.bc_flavour && (((S.all_set.y & 0x200u) && ed <= S.all_ed) || ((S.empty_set.y & 0x200u) && ed <= S.empty_ed)));
+        // far-node test one level above the last: usable when the global lists are out of reach at the levels ed-1 and ed
+        const bool filt_inner = ed >= 2 && slr_g_filter_usable(group) &&
+                                !(S.bc_flavour && (((S.all_set.y & 0x200u) && ed - 1 <= S.all_ed) || ((S.empty_set.y & 0x200u) && ed - 1 <= S.empty_ed)));
+        if (filt_inner) {
+            const SlrGPeq p0 = slr_g_peq(cand0, L), p1 = slr_g_peq(cand1, L);
+            for (int b = 0; b < 4; b++) { W.peq[0][b][lane] = p0.eq[b]; W.peq[1][b][lane] = p1.eq[b]; }
+        }
         SlrGTop2 T;
         slr_g_top2_init(T);
         uint32_t flags = (ed < 0 || ed > max_ed) ? SLR_G_EXCEPTION : 0u;      // host entry points refuse such a batch
@@ -159,6 +167,33 @@ guided_match_kernel(SlrGuidedSetsDev S, int L, int plusminus, int post_len, int 
                         __syncwarp();
                     }
                     continue;
+                }
+                // ---- a fresh node one level above the last that is far from every candidate (or dead): nothing in its subtree can hit, all
+                // that remains of it are the visited-set entries of the node and of its children (each child would be popped, run
+                // its — hitless — batch and mark itself) ----
+                if (level == ed - 1 && slr_g_pos_cur(node.meta) < 0 && filt_inner && postbad == 0u) {
+                    bool far = slr_g_dead(node.meta);
+                    if (!far) {
+                        SlrGPeq p0, p1;
+                        for (int b = 0; b < 4; b++) { p0.eq[b] = W.peq[0][b][lane]; p1.eq[b] = W.peq[1][b][lane]; }
+                        far = !__any_sync(FULL, (cok0 && slr_g_within2(p0, node.seq, L)) || (cok1 && slr_g_within2(p1, node.seq, L)));
+                    }
+                    if (far) {
+                        if (bailout < 0 || level < bailout || nlist == 0) {             // else no child is pushed (java:L134-L135)
+                            for (int c0 = 0; c0 < nchild; c0 += 32) {
+                                const int c = c0 + lane, p = c / 9, j = c - 9 * p;
+                                if (c < nchild && p != pos_prev) {
+                                    bool valid = false, thr = false;
+                                    uint32_t cmeta;
+                                    const uint32_t sc = slr_g_child(node.seq, node.meta, L, p, j, post2, 0u, post_len, valid, cmeta, thr);
+                                    if (valid && !slr_g_vis_insert_atomic(vis, vlg, stamp, sc)) throws_full = true;
+                                }
+                            }
+                        }
+                        if (lane == 0 && !slr_g_vis_insert_atomic(vis, vlg, stamp, node.seq)) throws_full = true;
+                        __syncwarp();
+                        continue;
+                    }
                 }
                 // ---- inner node: one position (java:L104-L122) ----
                 const int pos = slr_g_pos_cur(node.meta) + 1;

@@ -42,6 +42,7 @@ def sim():
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
     L.sim_guided_filter_skips.restype = C.c_longlong
+    L.sim_guided_far_nodes.restype = C.c_longlong
     L.sim_guided_filter_violations.restype = C.c_longlong
     L.sim_guided_filter_violations.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_ulonglong]
     return L

@@ -8,7 +8,7 @@
 namespace {
 
 int sim_no_filter = 0;             // sim_guided_set_filter(0): run every last-level batch (checks that skipping is exact)
-long long sim_filter_skips = 0;
+long long sim_filter_skips = 0, sim_far_nodes = 0;
 
 void sim_record(SlrGTop2 &T, int bc_flavour, uint32_t seq, uint32_t cmeta, int level, int offset, uint32_t where, slr_guided_hit *raw, int raw_cap)
 {
@@ -35,6 +35,10 @@ void sim_query(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, in
     for (uint32_t i = 0; i < 64; i++) cok[i] = slr_g_filter_slot(S.slots, group, i, cand[i]);
     const bool filt_leaf = slr_g_filter_usable(group) &&
                            !(S.bc_flavour && (((S.all_set.y & 0x200u) && ed <= S.all_ed) || ((S.empty_set.y & 0x200u) && ed <= S.empty_ed)));
+    const bool filt_inner = ed >= 2 && slr_g_filter_usable(group) &&
+                            !(S.bc_flavour && (((S.all_set.y & 0x200u) && ed - 1 <= S.all_ed) || ((S.empty_set.y & 0x200u) && ed - 1 <= S.empty_ed)));
+    SlrGPeq peq[64];
+    if (filt_inner) for (int i = 0; i < 64; i++) peq[i] = slr_g_peq(cand[i], L);
     SlrGTop2 T;
     slr_g_top2_init(T);
     uint32_t flags = (ed < 0 || ed > max_ed) ? SLR_G_EXCEPTION : 0u;
@@ -103,6 +107,27 @@ void sim_query(const SlrGuidedSetsDev &S, int L, int plusminus, int post_len, in
                 if (use_vis && !slr_g_vis_insert(vis, vlg, stamp, node.seq)) flags |= SLR_G_TABLE_FULL;
                 continue;
             }
+            if (level == ed - 1 && slr_g_pos_cur(node.meta) < 0 && filt_inner && postbad == 0u && !sim_no_filter) {
+                bool far = slr_g_dead(node.meta);
+                if (!far) {
+                    far = true;
+                    for (int i = 0; i < 64; i++) if (cok[i] && slr_g_within2(peq[i], node.seq, L)) far = false;
+                }
+                if (far) {
+                    sim_far_nodes++;
+                    if (bailout < 0 || level < bailout || nlist == 0)
+                        for (int c = 0; c < nchild; c++) {
+                            const int p = c / 9, j = c - 9 * p;
+                            if (p == pos_prev) continue;
+                            bool valid = false, thr = false;
+                            uint32_t cmeta;
+                            const uint32_t sc = slr_g_child(node.seq, node.meta, L, p, j, post2, 0u, post_len, valid, cmeta, thr);
+                            if (valid && !slr_g_vis_insert(vis, vlg, stamp, sc)) flags |= SLR_G_TABLE_FULL;
+                        }
+                    if (!slr_g_vis_insert(vis, vlg, stamp, node.seq)) flags |= SLR_G_TABLE_FULL;
+                    continue;
+                }
+            }
             const int pos = slr_g_pos_cur(node.meta) + 1;
             const uint32_t meta = (node.meta & ~31u) | (uint32_t)(pos + 1);
             if (pos < L - 1) { stack[sp].seq = node.seq; stack[sp].meta = meta; sp++; }
@@ -163,6 +188,7 @@ extern "C" void sim_guided_batch(const uint64_t *group_keys, const int64_t *grou
 }
 
 extern "C" void sim_guided_set_filter(int on) { sim_no_filter = !on; }
+extern "C" long long sim_guided_far_nodes(int reset) { const long long r = sim_far_nodes; if (reset) sim_far_nodes = 0; return r; }
 extern "C" long long sim_guided_filter_skips(int reset) { const long long r = sim_filter_skips; if (reset) sim_filter_skips = 0; return r; }
 
 // every child the engine can create from `n` random nodes must pass slr_g_may_be_child: returns the number of violations

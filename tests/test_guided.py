@@ -132,6 +132,22 @@ def test_candidate_filter_is_conservative(sim, orc):
     assert sim.sim_guided_filter_skips(1) == 0
     assert_same(got, graw, ref, rraw, "filter on vs off")
     assert skips > 10000
+    # far-node batches one level above the last (ED 3: the level-2 nodes; with a bailout; BC flavour at ED 4 where the lists are out of reach)
+    for L, ed, pm, post_len, bailout, bc, nq in ((12, 3, 1, 6, None, False, 24), (12, 3, 1, 6, 2, False, 24), (10, 4, 0, 6, None, False, 6),
+                                                 (16, 4, 0, 10, 2, True, 4), (12, 2, 2, 6, None, False, 150)):
+        w = workloads.guided(60 + ed, L, nq, ed, pm, post_len, bc, skew=True, group_sizes=(0, 1, 2, 5, 12, 25))
+        sim.sim_guided_far_nodes(1)
+        got, graw = sim_run(sim, orc, w, L, ed, pm, post_len, bailout, bc)
+        far = sim.sim_guided_far_nodes(1)
+        sim.sim_guided_set_filter(0)
+        try:
+            ref, rraw = sim_run(sim, orc, w, L, ed, pm, post_len, bailout, bc)
+        finally:
+            sim.sim_guided_set_filter(1)
+        assert_same(got, graw, ref, rraw, "far-node batches on vs off")
+        exp, eraw, _ = oracle_run(orc, w, L, ed, pm, post_len, bailout, bc)
+        assert_same(got, graw, exp, eraw, "far-node batches vs oracle")
+        assert far > 0 or bc, (L, ed, bc)      # BC flavour: the all-passed list (maxEDtoCheckBCAll10xBCs 3) is still probed at level 3
 
 
 def test_sim_mixed_edit_distances(sim, orc):
