@@ -158,6 +158,7 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's banner (NCCL_DEBUG=VERSION/INFO) off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = pkg.Context(local_rank, n_streams=2)

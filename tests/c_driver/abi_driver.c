@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE: a plain-C caller of libsicelore_gpu.so (no Python, no torch) that replays recorded boundary buffers
  * through the C ABI and compares the records byte for byte with the recorded reference results — what the JNI glue does
  * from Java (java/sicelore_gpu_jni.c), minus the JVM.
- *   abi_driver <file>      file = "SLRB" | u32 kind (1 bc_assign, 2 umi_dist, 3 bc_collide, 4 bc_exact) | kind-specific payload
+ *   abi_driver <file>      file = "SLRB" | u32 kind (1 bc_assign, 2 umi_dist, 3 bc_collide, 4 bc_exact, 5 guided_match) | kind-specific payload
  * exit code 0 = identical, 1 = mismatch, 2 = bad file, 3 = no CUDA device (the library has no CPU fallback). */
 #include <stddef.h>
 #include <stdint.h>
@@ -83,6 +83,29 @@ int main(int argc, char **argv)
         CHECK(slr_umi_dist(ctx, umis, 16, (int)umi_len, joff, n_jobs, got, ooff));
         bad = memcmp(got, exp, (size_t)cells * 4) != 0;
         printf("umi_dist: %lld jobs, %lld reads, %lld cells: %s\n", (long long)n_jobs, (long long)m, (long long)cells, bad ? "MISMATCH" : "OK");
+    } else if (kind == 5) {
+        const int64_t L = rd64(f), bc = rd64(f), pm = rd64(f), post_len = rd64(f), bailout = rd64(f), slice_len = rd64(f), raw_cap = rd64(f);
+        const int64_t n_groups = rd64(f), n_keys = rd64(f), n_all = rd64(f), n_empty = rd64(f), n = rd64(f);
+        uint64_t *gk = rd(f, (size_t)n_keys * 8);
+        int64_t *go = rd(f, (size_t)(n_groups + 1) * 8);
+        uint64_t *ak = rd(f, (size_t)n_all * 8), *ek = rd(f, (size_t)n_empty * 8);
+        uint8_t *slices = rd(f, (size_t)n * 32);
+        int32_t *anchor = rd(f, (size_t)n * 4), *gid = rd(f, (size_t)n * 4), *ed = rd(f, (size_t)n * 4);
+        slr_guided_result *exp = rd(f, (size_t)n * sizeof(slr_guided_result)), *got = malloc((size_t)n * sizeof(slr_guided_result) + 1);
+        slr_guided_hit *eraw = rd(f, (size_t)(n * raw_cap) * sizeof(slr_guided_hit)), *graw = malloc((size_t)(n * raw_cap) * sizeof(slr_guided_hit) + 1);
+        slr_guided_sets *gs = NULL;
+        CHECK(slr_guided_sets_create(ctx, gk, go, n_groups, bc ? ak : NULL, n_all, 3, bc ? ek : NULL, n_empty, 2, (int)bc, (int)L, &gs));
+        CHECK(slr_guided_match(ctx, gs, (int)pm, (int)post_len, (int)bailout, slices, 32, (int)slice_len, anchor, gid, ed, n, got, graw, (int)raw_cap));
+        bad = rec_differ(got, exp, n, sizeof(slr_guided_result), offsetof(slr_guided_result, pad));
+        int64_t found = 0;
+        for (int64_t i = 0; i < n; i++) {
+            found += exp[i].n_distinct > 0;
+            if (!exp[i].flags)                      /* the raw records of a read that throws are unspecified */
+                bad |= memcmp(graw + i * raw_cap, eraw + i * raw_cap, (size_t)raw_cap * sizeof(slr_guided_hit)) != 0;
+        }
+        printf("guided_match: %lld reads, L %lld, %s flavour, %lld found: %s\n", (long long)n, (long long)L, bc ? "BC" : "UMI", (long long)found,
+               bad ? "MISMATCH" : "OK");
+        slr_guided_sets_destroy(gs);
     } else { fprintf(stderr, "unknown kind %u\n", kind); return 2; }
     slr_ctx_destroy(ctx);
     return bad ? 1 : 0;

@@ -112,6 +112,14 @@ def driver_inputs(tmp_path, orc):
     u = np.load(os.path.join(gold, "umi_len12.npz"))
     files.append(write_driver_file(tmp_path / "umi.bin", 2, [int(u["umi_len"]), len(u["job_offsets"]) - 1, len(u["umis"]), len(u["matrix"]),
                                                            u["umis"], u["job_offsets"], u["out_offsets"], u["matrix"]]) or tmp_path / "umi.bin")
+    for name in ("guided_umi_ed2", "guided_bc_mixed"):
+        z = np.load(os.path.join(gold, name + ".npz"))
+        raw = z["raw"].view(orc.GUIDED_HIT).reshape(len(z["slices"]), -1)
+        files.append(write_driver_file(tmp_path / (name + ".bin"), 5, [
+            int(z["L"]), int(z["bc"]), int(z["pm"]), int(z["post_len"]), int(z["bailout"]), int(z["slice_len"]), raw.shape[1],
+            len(z["group_offsets"]) - 1, len(z["group_keys"]), len(z["all_keys"]), len(z["empty_keys"]), len(z["slices"]), z["group_keys"],
+            z["group_offsets"], z["all_keys"], z["empty_keys"], z["slices"], z["anchor"], z["group_id"], z["ed"].astype(np.int32), z["result"],
+            raw]) or tmp_path / (name + ".bin"))
     return files
 
 
