@@ -1,0 +1,391 @@
+"""Golden vectors produced BY THE REFERENCE ITSELF: the class files of /root/reference/Jar are executed by oracle/minijvm.py (there is no
+JDK in the image) and the inputs / outputs are frozen in tests/golden/ref_*.npz.  Run in the build container only:
+
+    python oracle/make_ref_vectors.py
+
+What runs is the reference's bytecode, unmodified: NucleicAcidTwoBitPerBase (pack, reverse complement, the three mutation primitives),
+BarcodeMatchTester.doJob (second-pass and collision-tester settings), UMInuc/BCnucTwoBitPerBaseEDtester.matchesSeqEditDistance
+(Illumina-guided engine incl. bailout) and LevenshteinDistance.apply (thresholded UMI distance).  Containers that are not in the two
+jars (java.util, eclipse-collections, fastutil, the Illumina data holders) are Python shims with membership semantics (minijvm.py).
+tests/test_ref_vectors.py checks the C oracle (and the GPU path, through the oracle) against these vectors."""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import minijvm as J  # noqa: E402
+
+REF = "/root/reference/Jar"
+JARS = [REF + "/NanoporeBC_UMI_finder-2.1.jar", REF + "/lib/TwoFourBitNucAcidLibraryMaven-1.0.jar"]
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+T2 = "com/rw/nuc/encoding/TwoBit/NucleicAcidTwoBitPerBase"
+ONEBYTE = "com/rw/nuc/encoding/onebyte/NucleicAcidInmutableOneBytePerBase"
+BMT = "com/rw/nanoporereadscanner/analyzers/BarcodeMatchTester"
+UMIT = "com/rw/nuc/encoding/TwoBit/ed/UMInucTwoBitPerBaseEDtester"
+BCT = "com/rw/nuc/encoding/TwoBit/ed/BCnucTwoBitPerBaseEDtester"
+LEV = "com/rw/nanopore/analyzers/apachemod/LevenshteinDistance"
+M64 = (1 << 64) - 1
+BASES = "AGCT"
+
+
+def carr(s):
+    a = J.JArr("C", len(s), 0)
+    a.a = [ord(c) for c in s]
+    return a
+
+
+def barr(v):
+    a = J.JArr("B", len(v), 0)
+    a.a = [int(x) - 256 if int(x) > 127 else int(x) for x in v]
+    return a
+
+
+def rseq(rng, n, alpha="AGCT"):
+    return "".join(alpha[i] for i in rng.integers(0, len(alpha), n))
+
+
+def primitives(vm, rng):
+    rows, seqs = [], []
+    for L in (12, 16):
+        for t in range(60):
+            s = rseq(rng, L, "AAAAGCT" if t % 3 == 0 else "AGCT")
+            if t % 10 == 9:
+                p = int(rng.integers(L))
+                s = s[:p] + "N" + s[p + 1:]
+            h = vm.call_static(T2, "getLongHashForSeq", "([C)J", carr(s))
+            rc = vm.call_virtual(vm.construct(T2, "(JI)V", J.L(h), L), "reverseComplement", "()Lcom/rw/nuc/encoding/TwoBit/NucleicAcidTwoBitPerBase;").f["sequence"]
+            seqs.append((s, L, int(h) & M64, int(rc) & M64))
+            out = J.JArr("J", 4, J.L(0))
+            for p in range(L):
+                vm.call_static(T2, "getLongHashReplaceByteDeg", "(J[JII)V", J.L(h), out, p, L)
+                rep = [int(x) & M64 for x in out.a]
+                if p < L - 1:
+                    vm.call_static(T2, "getLongHashInsertByteDeg", "(J[JII)V", J.L(h), out, p, L)
+                    ins = [int(x) & M64 for x in out.a]
+                else:
+                    ins = [0, 0, 0, 0]
+                dl = [int(vm.call_static(T2, "getLongHashdeleteByte", "(JBII)J", J.L(h), c4, p, L)) & M64 for c4 in (1, 2, 4, 8, 15)]
+                rows.append([L, int(h) & M64, p, int(rc) & M64] + rep + ins + dl)
+    return np.array(rows, dtype=np.uint64), seqs
+
+
+def onebyte(vm, s):
+    return vm.construct(ONEBYTE, "(Ljava/lang/CharSequence;)V", s)
+
+
+def run_dojob(vm, keys, w, L, ed, skip_full, post, do_next, offset):
+    """new BarcodeMatchTester(ed, skipFullMatches, allowIndels = true, searchSet, offset, L, postSeq, doNext).doJob(seq)"""
+    t = vm.construct(BMT, "(IZZLjava/util/Set;SILcom/rw/nuc/encoding/onebyte/NucleicAcidInmutableOneBytePerBase;Z)V", ed, int(skip_full), 1,
+                     J.PySet(keys), offset, L, None if post is None else onebyte(vm, post), int(do_next))
+    seq = vm.construct(T2, "(JI)V", J.L(w), L)
+    m = vm.call_virtual(t, "doJob", "(Lcom/rw/nuc/encoding/TwoBit/NucleicAcidTwoBitPerBase;)Lcom/rw/nanoporereadscanner/analyzers/BarcodeMatchTester$Matches;", seq)
+    out = []
+    if m is not None:
+        for o in m.native.items():
+            f = o.f
+            out.append((int(f["readSeq"]) & M64, int(f["matchingBC"]) & M64, f["editDistance"], f["substitutions"], f["insertions"], f["deletions"],
+                        f["offsetFromPredicted"]))
+    return out
+
+
+def pack(s):
+    v = 0
+    for ch in s:
+        v = (v << 2) | BASES.index(ch)
+    return v
+
+
+def unpack(v, L):
+    return "".join(BASES[(v >> (2 * (L - 1 - i))) & 3] for i in range(L))
+
+
+def mutate(rng, s, k):
+    s = list(s)
+    for _ in range(k):
+        op, p = int(rng.integers(3)), int(rng.integers(len(s)))
+        if op == 0:
+            s[p] = BASES[int(rng.integers(4))]
+        elif op == 1:
+            s.insert(p, BASES[int(rng.integers(4))])
+        else:
+            del s[p]
+    return "".join(s)
+
+
+def dojob_cases(vm, rng, n_cases, L=16):
+    """windows planted 0..3 edits from list members (so that every ED level and the first-hit-wins order are exercised)"""
+    cases = []
+    for t in range(n_cases):
+        alpha = "AAAAGCT" if t % 4 == 0 else "AGCT"
+        keys = sorted({pack(rseq(rng, L, alpha)) for _ in range(40)})
+        base = unpack(keys[int(rng.integers(len(keys)))], L)
+        wstr = (mutate(rng, base, int(rng.integers(0, 4))) + rseq(rng, 8))[:L]
+        # plant extra neighbours of the window itself: competing hits at ED 1 / 2
+        for _ in range(int(rng.integers(0, 6))):
+            keys.append(pack((mutate(rng, wstr, int(rng.integers(1, 3))) + rseq(rng, 4))[:L]))
+        keys = sorted(set(keys))
+        ed = 1 if t % 5 == 0 else 2
+        mode = t % 3                      # 0/1: second pass (post given, doNext), 2: collision tester (no post, !doNext, skipFullMatches)
+        post = None if mode == 2 else rseq(rng, 5, "AGCTN" if t % 7 == 0 else "AGCT")
+        off = int(rng.integers(-2, 3))
+        if mode == 2:
+            keys = sorted(set(keys) | {pack(wstr)})
+        res = run_dojob(vm, keys, pack(wstr), L, ed, mode == 2, post, mode != 2, off)
+        cases.append(dict(keys=keys, w=pack(wstr), ed=ed, mode=mode, post=post or "", off=off, res=res))
+    return cases
+
+
+def guided_cases(vm, rng, n_cases):
+    """UMInucTwoBitPerBaseEDtester / BCnucTwoBitPerBaseEDtester.matchesSeqEditDistance: the whole ordered ArrayList"""
+    params_cls = vm.load("com/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams")
+    cases = []
+    for t in range(n_cases):
+        bc = t % 3 == 2
+        L = 16 if bc else 12
+        ed = [1, 2, 2, 3][t % 4] if not bc else [1, 2][t % 2]
+        if L == 12 and ed == 3 and t % 8 != 3:
+            ed = 2
+        keys = sorted({pack(rseq(rng, L)) for _ in range(int(rng.integers(1, 9)))})
+        base = unpack(keys[int(rng.integers(len(keys)))], L)
+        wstr = (mutate(rng, base, int(rng.integers(0, ed + 1))) + rseq(rng, 8))[:L]
+        post = rseq(rng, 10 if bc else ed + 3)
+        bail = None if t % 2 == 0 else int(rng.integers(1, 3))
+        off = int(rng.integers(-2, 3))
+        params = vm.new_object(params_cls, init=False)                   # field holder only: the testers read three nested fields
+        if bc:
+            bp = vm.new_object(vm.load("com/rw/parameters/BarcodeParameters"), init=False)
+            allk = sorted(set(keys) | {pack((mutate(rng, wstr, int(rng.integers(0, 3))) + rseq(rng, 4))[:L]) for _ in range(4)})
+            empk = sorted({pack((mutate(rng, wstr, int(rng.integers(1, 3))) + rseq(rng, 4))[:L]) for _ in range(3)})
+            bp.f["cell_BC_bailout_after_ED"] = bail
+            bp.f["maxEDtoCheckBCAll10xBCs"], bp.f["maxEDtoCheckBCEmptyDrops"] = 3, 2
+            bp.f["checkAllassignedBarcodes"], bp.f["checkEmptyDrops"] = 1, 1
+            params.f["barcodes"] = bp
+            tester = vm.construct(BCT, "(Lcom/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams;Lcom/rw/nuc/reads/Illumina/All10xselectedCells;"
+                                       "Lcom/rw/nuc/reads/Illumina/EmptyDropBarcodes;Lcom/rw/nuc/reads/Illumina/BarcodesMap;I"
+                                       "Lcom/rw/nuc/encoding/onebyte/NucleicAcidInmutableOneBytePerBase;I)V",
+                                  params, J.PySet(allk), J.PySet(empk), J.PySet(keys), ed, onebyte(vm, post), L)
+        else:
+            up = vm.new_object(vm.load("com/rw/parameters/UMIparameters"), init=False)
+            up.f["umi_bailout_afterED"] = bail
+            params.f["umis"] = up
+            allk = empk = []
+            tester = vm.construct(UMIT, "(ILcom/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams;"
+                                        "Lcom/rw/nuc/reads/Illumina/byGene/IlluminaOneGeneOneCellData;Z"
+                                        "Lcom/rw/nuc/encoding/onebyte/NucleicAcidInmutableOneBytePerBase;ZI)V",
+                                  ed, params, J.PySet(keys), 1, onebyte(vm, post), 0, L)
+        seq = vm.construct(T2, "(JI)V", J.L(pack(wstr)), L)
+        lst = vm.call_virtual(tester, "matchesSeqEditDistance", "(Lcom/rw/nuc/encoding/TwoBit/NucleicAcidTwoBitPerBase;I)Ljava/util/ArrayList;", seq, off)
+        res = [(int(o.f["sequence"]) & M64, o.f["nSubstitutions"], o.f["nInsertions"], o.f["nDeletions"], o.f["startOffsetFromPredicted"],
+                o.f["findingErrorFlag"]) for o in lst.v]
+        cases.append(dict(bc=bc, L=L, ed=ed, keys=keys, allk=allk, empk=empk, w=pack(wstr), post=post, bail=-1 if bail is None else bail, off=off, res=res))
+    return cases
+
+
+def lev_cases(vm, rng, n):
+    lev = vm.construct(LEV, "(Ljava/lang/Integer;)V", 4)
+    rows = []
+    for t in range(n):
+        a = rng.choice([1, 2, 4, 8, 15], 12, p=[.24, .24, .24, .24, .04]).astype(np.uint8)
+        b = a.copy()
+        for _ in range(int(rng.integers(0, 7))):
+            op, p = int(rng.integers(3)), int(rng.integers(12))
+            if op == 0:
+                b[p] = rng.choice([1, 2, 4, 8])
+            elif op == 1:
+                b = np.concatenate([b[:p], [rng.choice([1, 2, 4, 8])], b[p:]])[:12]
+            else:
+                b = np.concatenate([b[:p], b[p + 1:], [rng.choice([1, 2, 4, 8])]])
+        d = vm.call_virtual(lev, "apply", "([B[B)Ljava/lang/Integer;", barr(a), barr(b))
+        rows.append(np.concatenate([a, b, [np.uint8(d & 0xFF)]]))
+    return np.array(rows, dtype=np.uint8)
+
+
+def best9_cases(vm, rng, n, umi_len=12):
+    """pair of reads -> 3 x 3 thresholded distances (LevenshteinDistance.apply on the reference's bytecode; the window slicing and the
+    equal-bytes shortcut of lambda$static$7, ClusteringEditDistanceBase.java:L316-L343, are done here) -> new ClusteringEditDistanceBase(eds):
+    best-of-9 in the reference's visiting order, BestEditDistance packing and its transposed copy"""
+    CED = "com/rw/clustering/ClusteringEditDistanceBase"
+    lev = vm.construct(LEV, "(Ljava/lang/Integer;)V", 4)
+    rows = []
+    for t in range(n):
+        a = rng.choice([1, 2, 4, 8, 15], umi_len + 2, p=[.245, .245, .245, .245, .02]).astype(np.uint8)
+        b = a.copy() if t % 4 else rng.choice([1, 2, 4, 8], umi_len + 2).astype(np.uint8)
+        for _ in range(int(rng.integers(0, 5))):
+            op, p = int(rng.integers(3)), int(rng.integers(umi_len + 2))
+            if op == 0:
+                b[p] = rng.choice([1, 2, 4, 8])
+            elif op == 1:
+                b = np.concatenate([b[:p], [rng.choice([1, 2, 4, 8])], b[p:]])[:umi_len + 2]
+            else:
+                b = np.concatenate([b[:p], b[p + 1:], [rng.choice([1, 2, 4, 8])]])
+        if t % 9 == 0:
+            b = np.roll(a, 1 if t % 2 else -1)                      # a pure shift: best at a non-central position
+        eds = J.JArr("L", 3, None)
+        for i in range(3):
+            row = J.JArr("B", 3, 0)
+            for j in range(3):
+                s1, s2 = a[i:i + umi_len], b[j:j + umi_len]
+                if (s1 == s2).all():
+                    row.a[j] = 0
+                else:
+                    d = vm.call_virtual(lev, "apply", "([B[B)Ljava/lang/Integer;", barr(s1), barr(s2))
+                    row.a[j] = 5 if d == -1 else d
+            eds.a[i] = row
+        o = vm.construct(CED, "([[B)V", eds)
+        best = o.f["bestEditDistance"]
+        tr = vm.call_virtual(best, "getTransposedCopy", "()Lcom/rw/clustering/ClusteringEditDistanceBase$BestEditDistance;")
+        rows.append(np.concatenate([a, b]).astype(np.int64).tolist() + [best.f["ed"], tr.f["ed"]])
+    eq = vm.load(CED).statics["equalityEditDistance"].f["bestEditDistance"].f["ed"]
+    return np.array(rows, dtype=np.int64), eq
+
+
+PKG = "com/rw/nanoporereadscanner/"
+
+
+def bare(vm, name):
+    return vm.new_object(vm.load(name), init=False)
+
+
+def make_parser(vm, keys, ranks, ed, pm, three_prime, L=16):
+    """a Parser whose fields hold just what assignBarcode reads: parameters (testPlusMinusPos, assignCellBCwithEditDistance, cell_bc_length,
+    scantype), hashMapForBCfinding (the search set + CountsRank.rank) and the assignedBarcodes2ndPass map"""
+    P = bare(vm, PKG + "analyzers/Parser")
+    params, rsp, bp = bare(vm, PKG + "parameters/ParametersReadScannerApp"), bare(vm, "com/rw/parameters/ReadScannerParameters"), bare(vm, "com/rw/parameters/BarcodeParameters")
+    rsp.f["testPlusMinusPos"] = pm
+    rsp.f["assignCellBCwithEditDistance"] = J.JNative("com/google/common/base/Optional", (ed,))
+    bp.f["cell_bc_length"] = L
+    st = vm.load("com/rw/parameters/ParametersMainBase$SCANTYPE")
+    vm.init_class(st)
+    params.f["readScannerParameters"], params.f["barcodes"] = rsp, bp
+    params.f["scantype"] = st.statics["THREEP_BARCODE" if three_prime else [k for k in st.statics if k.startswith("FIVEP")][0]]
+    P.f["parameters"] = params
+    bm = bare(vm, PKG + "WorkerReadscanner$BarcodesMapForBCfinding")
+    bm.native = {}
+    for k, r in zip(keys, ranks):
+        cr = bare(vm, PKG + "WorkerReadscanner$CountsRank")
+        cr.f["rank"] = int(r)
+        bm.native[int(k)] = cr
+    P.f["hashMapForBCfinding"] = bm
+    P.f["assignedBarcodes2ndPass"] = J.JNative("java/util/concurrent/ConcurrentHashMap", {})
+    return P
+
+
+def run_assign(vm, P, read, adapterpos):
+    """Parser.assignBarcode(fq) on the reference's bytecode.  Returns the BarcodeResult fields (None = nothing assigned) or 'EXC:<class>'"""
+    fq = bare(vm, PKG + "readerwriter/FastqRecordExt")
+    fq.f["strandedSequence"] = read
+    sr = vm.new_object(vm.load(PKG + "readerwriter/ReadScanResult"))
+    fq.f["scanResult"] = sr
+    ar = vm.call_virtual(sr, "getAdapterresultCreateIfNull", "()L" + PKG + "readerwriter/ReadScanResult$Adapterresult;")
+    ar.f["end"] = adapterpos
+    try:
+        vm.invoke_exact(PKG + "analyzers/Parser", "assignBarcode", "(L" + PKG + "readerwriter/FastqRecordExt;)V", [P, fq])
+    except J.JavaThrow as ex:
+        return "EXC:" + ex.cls
+    br = [v for k, v in sr.f.items() if isinstance(v, J.JObj) and v.cls.name.endswith("BarcodeResult")]
+    if not br or br[0].f.get("barcodeseq") is None:
+        return None
+    b = br[0].f
+    rank = b.get("rank")
+    rank = rank.v[0] if isinstance(rank, J.JNative) and rank.v else (rank if isinstance(rank, int) else -1)
+    return (int(b["barcodeseq"].f["sequence"]) & M64, b["editDistance"], b["editDistanceSecondBest"], b["start"], b["end"], rank, int(sr.f["flag"]) & M64)
+
+
+def assign_cases(vm, rng, n_cases):
+    """whole reads through Parser.assignBarcode: 3' and 5' geometry, hits planted at several offsets / ED levels (ambiguity across offsets and
+    levels), N in and around the window, windows running off the read"""
+    L = 16
+    comp = str.maketrans("ACGT", "TGCA")
+    cases = []
+    for t in range(n_cases):
+        tp = t % 4 != 3
+        ed = 1 if t % 5 == 0 else 2
+        pm = 2 if t % 6 else 1
+        read = rseq(rng, 60)
+        ap = int(rng.integers(24, 36)) if t % 11 else int(rng.integers(14, 22))        # adapter end, 1-based; small values run off the read (3')
+        if not tp and t % 11 == 0:
+            ap = int(rng.integers(38, 46))
+        keys = {pack(rseq(rng, L)) for _ in range(30)}
+        for _ in range(int(rng.integers(1, 5))):                                        # plant barcodes near windows at random offsets
+            o = int(rng.integers(-pm, pm + 1))
+            if tp:
+                b, e = ap - L - 1 + o, ap - 1 + o
+                w = read[b:e][::-1].translate(comp) if 0 <= b and e <= len(read) else rseq(rng, L)
+            else:
+                b = ap + o
+                w = read[b:b + L] if b + L <= len(read) else rseq(rng, L)
+            if len(w) == L:
+                keys.add(pack((mutate(rng, w, int(rng.integers(0, ed + 1))) + rseq(rng, 4))[:L]))
+        if t % 9 == 0:
+            p = int(rng.integers(max(0, ap - 24), min(60, ap + 22)))
+            read = read[:p] + "N" + read[p + 1:]
+        keys = sorted(keys)
+        ranks = list(range(1, len(keys) + 1))
+        P = make_parser(vm, keys, ranks, ed, pm, tp)
+        res = run_assign(vm, P, read, ap)
+        counts = {int(k): (v.f["counts"].v[0], {int(e): c.v[0] for e, c in v.f["edCounts"].v.items()}) for k, v in P.f["assignedBarcodes2ndPass"].v.items()}
+        cases.append(dict(read=read, ap=ap, tp=tp, ed=ed, pm=pm, keys=keys, res=res, counts=counts))
+    return cases
+
+
+def flat(cases, key):
+    off = np.cumsum([0] + [len(c[key]) for c in cases]).astype(np.int64)
+    return np.array([k for c in cases for k in c[key]], dtype=np.uint64), off
+
+
+def main():
+    vm = J.VM(JARS)
+    rng = np.random.default_rng(20261017)
+    t0 = time.time()
+    prim, seqs = primitives(vm, rng)
+    np.savez_compressed(os.path.join(OUT, "ref_primitives.npz"), rows=prim, seq=np.array([x[0].ljust(16, "-") for x in seqs]),
+                        seq_len=np.array([x[1] for x in seqs], dtype=np.int32), seq_hash=np.array([x[2] for x in seqs], dtype=np.uint64),
+                        seq_revcomp=np.array([x[3] for x in seqs], dtype=np.uint64))
+    print("primitives", prim.shape, "%.1fs" % (time.time() - t0), vm.n_insn, "bytecodes")
+
+    lv = lev_cases(vm, rng, 400)
+    np.savez_compressed(os.path.join(OUT, "ref_levenshtein.npz"), rows=lv)
+    print("levenshtein", lv.shape, "d histogram", np.bincount(lv[:, 24].astype(np.int8).astype(int) + 1))
+
+    b9, eq = best9_cases(vm, np.random.default_rng(99), 300)
+    np.savez_compressed(os.path.join(OUT, "ref_best9.npz"), rows=b9, equality=np.int64(eq))
+    print("best-of-9", b9.shape, "ED histogram", np.bincount(b9[:, 28] & 0xFFFFFF), "equality %#x" % eq)
+
+    dj = dojob_cases(vm, rng, 45)
+    keys, koff = flat(dj, "keys")
+    res = np.array([(i,) + r for i, c in enumerate(dj) for r in c["res"]], dtype=np.int64).reshape(-1, 8)
+    np.savez_compressed(os.path.join(OUT, "ref_dojob.npz"), keys=keys, key_offsets=koff, w=np.array([c["w"] for c in dj], dtype=np.uint64),
+                        ed=np.array([c["ed"] for c in dj], dtype=np.int32), mode=np.array([c["mode"] for c in dj], dtype=np.int32),
+                        post=np.array([c["post"].ljust(5, "-") for c in dj]), off=np.array([c["off"] for c in dj], dtype=np.int32), res=res)
+    print("doJob", len(dj), "cases,", len(res), "matches, %.1fs" % (time.time() - t0), vm.n_insn, "bytecodes")
+
+    ac = assign_cases(vm, np.random.default_rng(777), 40)
+    keys, koff = flat(ac, "keys")
+    status = np.array([2 if isinstance(c["res"], str) else (0 if c["res"] is None else 1) for c in ac], dtype=np.int32)     # 0 unassigned, 1 assigned, 2 exception
+    resrows = np.array([list(c["res"]) if isinstance(c["res"], tuple) else [0] * 7 for c in ac], dtype=np.uint64)
+    cnt = np.array([(i, k, e, n) for i, c in enumerate(ac) for k, (tot, eds) in c["counts"].items() for e, n in eds.items()], dtype=np.int64).reshape(-1, 4)
+    np.savez_compressed(os.path.join(OUT, "ref_assign.npz"), read=np.array([c["read"] for c in ac]), adapterpos=np.array([c["ap"] for c in ac], dtype=np.int32),
+                        three_prime=np.array([c["tp"] for c in ac], dtype=np.int32), ed=np.array([c["ed"] for c in ac], dtype=np.int32),
+                        pm=np.array([c["pm"] for c in ac], dtype=np.int32), keys=keys, key_offsets=koff, status=status, result=resrows, counts=cnt,
+                        exc=np.array([c["res"] if isinstance(c["res"], str) else "" for c in ac]))
+    print("assignBarcode", len(ac), "reads: unassigned/assigned/exception", np.bincount(status, minlength=3), "%.1fs" % (time.time() - t0), vm.n_insn, "bytecodes")
+
+    gc = guided_cases(vm, rng, 36)
+    keys, koff = flat(gc, "keys")
+    ak, aoff = flat(gc, "allk")
+    ek, eoff = flat(gc, "empk")
+    res = np.array([(i,) + r for i, c in enumerate(gc) for r in c["res"]], dtype=np.int64).reshape(-1, 7)
+    np.savez_compressed(os.path.join(OUT, "ref_guided.npz"), keys=keys, key_offsets=koff, all_keys=ak, all_offsets=aoff, empty_keys=ek, empty_offsets=eoff,
+                        w=np.array([c["w"] for c in gc], dtype=np.uint64), L=np.array([c["L"] for c in gc], dtype=np.int32),
+                        ed=np.array([c["ed"] for c in gc], dtype=np.int32), bc=np.array([c["bc"] for c in gc], dtype=np.int32),
+                        bail=np.array([c["bail"] for c in gc], dtype=np.int32), off=np.array([c["off"] for c in gc], dtype=np.int32),
+                        post=np.array([c["post"].ljust(10, "-") for c in gc]), res=res,
+                        flag_gene=np.int64(512), flag_all=np.int64(4), flag_empty=np.int64(8))     # BarcodeFindingFlag.flagValue read from the enum
+    print("guided", len(gc), "cases,", len(res), "list entries, %.1fs" % (time.time() - t0), vm.n_insn, "bytecodes")
+
+
+if __name__ == "__main__":
+    main()

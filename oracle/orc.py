@@ -202,3 +202,22 @@ def guided_batch(group_keys, group_offsets, slices, anchor, group_id, ed, length
                        anchor.ctypes.data, gid.ctypes.data, edv.ctypes.data, n, out.ctypes.data,
                        None if raw is None else raw.ctypes.data, raw_cap, C.byref(probes), n_threads)
     return out, raw, probes.value
+
+
+def guided_tester(group, seq, length, ed, post4, bailout=-1, offset=0, bc_flavour=False, all_set=None, all_ed=0, empty_set=None, empty_ed=0,
+                  cap=4096):
+    """orc_guided_tester: the raw matchingList of one BCUMIEDtesterBase run (one window).  group / all_set / empty_set: BarcodeSet or None."""
+    class Sets(C.Structure):
+        _fields_ = [("group", C.c_void_p), ("all", C.c_void_p), ("all_ed", C.c_int), ("empty", C.c_void_p), ("empty_ed", C.c_int),
+                    ("bc_flavour", C.c_int)]
+    L = lib()
+    L.orc_guided_tester.restype = C.c_int64
+    L.orc_guided_tester.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_int64, C.POINTER(C.c_int64)]
+    s = Sets(None if group is None else group.h, None if all_set is None else all_set.h, all_ed, None if empty_set is None else empty_set.h,
+             empty_ed, int(bc_flavour))
+    out = np.zeros(cap, dtype=GUIDED_HIT)
+    p4 = np.ascontiguousarray(post4, dtype=np.uint8)
+    probes = C.c_int64(0)
+    n = L.orc_guided_tester(C.byref(s), int(seq), length, ed, 1, p4.ctypes.data, len(p4), bailout, offset, out.ctypes.data, cap, C.byref(probes))
+    return (None if n < 0 else out[:min(n, cap)]), n

@@ -1,0 +1,211 @@
+"""The oracle against vectors produced by the REFERENCE'S OWN BYTECODE (tests/golden/ref_*.npz): the class files of
+/root/reference/Jar were executed by oracle/minijvm.py (a JVM-subset interpreter, there is no JDK in the image) with
+oracle/make_ref_vectors.py; inputs and outputs are frozen here, nothing below needs the jars.  These vectors pin the 2-bit primitives,
+BarcodeMatchTester.doJob (second-pass and collision-tester settings), the Illumina-guided engine with both checkMatchWithTestSets
+flavours and the thresholded Levenshtein distance of the UMI matrix."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyref
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+M64 = (1 << 64) - 1
+
+
+def test_primitives_match_reference_bytecode(orc):
+    z = np.load(os.path.join(GOLDEN, "ref_primitives.npz"))
+    L = orc.lib()
+    for s, n, h, rc in zip(z["seq"], z["seq_len"], z["seq_hash"], z["seq_revcomp"]):
+        s = str(s)[:int(n)]
+        bad = C.c_int(0)
+        assert L.orc_pack2bit(s.encode(), int(n), C.byref(bad)) == int(h) == pyref.pack(s)          # getLongHashForSeq incl. the N sign extension
+        assert L.orc_revcomp2bit(int(h), int(n)) == int(rc) == pyref.revcomp2(int(h), int(n))        # reverseComplement()
+    out = (C.c_uint64 * 4)()
+    for row in z["rows"]:
+        n, h, p = int(row[0]), int(row[1]), int(row[2])
+        L.orc_replace_deg(h, out, p, n)
+        assert list(out) == [int(x) for x in row[4:8]] == [x & M64 for x in pyref.replace_deg(h, p, n)]
+        if p < n - 1:
+            L.orc_insert_deg(h, out, p, n)
+            assert list(out) == [int(x) for x in row[8:12]] == [x & M64 for x in pyref.insert_deg(h, p, n)]      # incl. the p = L-2 shift quirk
+        for k, c4 in enumerate((1, 2, 4, 8, 15)):
+            assert L.orc_delete_byte(h, c4, p, n) == int(row[12 + k]) == pyref.delete_byte(h, c4, p, n) & M64
+    assert len(z["rows"]) == 1680
+
+
+def test_limited_compare_matches_reference_bytecode(orc):
+    z = np.load(os.path.join(GOLDEN, "ref_levenshtein.npz"))["rows"]
+    L = orc.lib()
+    seen = set()
+    for row in z:
+        a, b, d = row[:12].tobytes(), row[12:24].tobytes(), int(np.int8(row[24]))
+        assert L.orc_limited_compare(a, 12, b, 12, 4) == d
+        seen.add(d)
+    assert seen == {-1, 0, 1, 2, 3, 4}
+
+
+def test_dojob_matches_reference_bytecode(orc):
+    """BarcodeMatchTester.doJob run by the reference's own class files: every OneMatch (readSeq, matchingBC, ED, counters, offset) in
+    discovery order, for the second-pass settings (post sequence, doNextLevelIfMatchFound) and the collision tester's
+    (skipFullMatches, postSeq = null, !doNext)"""
+    z = np.load(os.path.join(GOLDEN, "ref_dojob.npz"))
+    n_cases, n_match = len(z["w"]), 0
+    for i in range(n_cases):
+        keys = z["keys"][z["key_offsets"][i]:z["key_offsets"][i + 1]]
+        mode, ed, off, w = int(z["mode"][i]), int(z["ed"][i]), int(z["off"][i]), int(z["w"][i])
+        post = None if mode == 2 else [pyref.ENCODE[ord(c)] for c in str(z["post"][i])[:5]]
+        got, _ = orc.match_tester(orc.BarcodeSet(keys), w, 16, ed, skip_full=(mode == 2), allow_indels=True, post4=post, do_next=(mode != 2), offset=off)
+        exp = z["res"][z["res"][:, 0] == i][:, 1:]
+        got_rows = [(m["read_seq"], m["bc"], m["ed"], m["n_sub"], m["n_ins"], m["n_del"], m["offset"]) for m in got]
+        assert got_rows == [tuple(int(x) & M64 if k < 2 else int(x) for k, x in enumerate(r)) for r in exp], (i, mode, ed, got_rows, exp)
+        n_match += len(exp)
+    assert n_cases == 45 and n_match >= 60
+    assert {int(e) for e in z["res"][:, 3]} == {0, 1, 2}                        # hits at every ED level
+
+
+def test_guided_engine_matches_reference_bytecode(orc):
+    """UMInuc / BCnucTwoBitPerBaseEDtester.matchesSeqEditDistance run by the reference's own class files: the whole ArrayList in list order
+    (duplicates, counters, startOffsetFromPredicted, findingErrorFlag incl. the GENE bit inherited by descendants), with and without bailout"""
+    z = np.load(os.path.join(GOLDEN, "ref_guided.npz"))
+    fg, fa, fe = int(z["flag_gene"]), int(z["flag_all"]), int(z["flag_empty"])
+    n_entries = 0
+    flags_seen = set()
+    for i in range(len(z["w"])):
+        sl = lambda k, o: z[k][z[o][i]:z[o][i + 1]]
+        keys, allk, empk = sl("keys", "key_offsets"), sl("all_keys", "all_offsets"), sl("empty_keys", "empty_offsets")
+        bc, L, ed, bail, off, w = bool(z["bc"][i]), int(z["L"][i]), int(z["ed"][i]), int(z["bail"][i]), int(z["off"][i]), int(z["w"][i])
+        post4 = [pyref.ENCODE[ord(c)] for c in str(z["post"][i]).rstrip("-")]
+        got, n = orc.guided_tester(orc.BarcodeSet(keys), w, L, ed, post4, bailout=bail, offset=off, bc_flavour=bc,
+                                   all_set=orc.BarcodeSet(allk) if bc else None, all_ed=3, empty_set=orc.BarcodeSet(empk) if bc else None, empty_ed=2)
+        exp = z["res"][z["res"][:, 0] == i][:, 1:]
+        assert n == len(exp), (i, n, len(exp))
+        for g, e in zip(got, exp):
+            where = (orc.W_GENE if int(e[5]) & fg else 0) | (orc.W_ALL if int(e[5]) & fa else 0) | (orc.W_EMPTY if int(e[5]) & fe else 0)
+            assert (int(g["seq"]), g["n_sub"], g["n_ins"], g["n_del"], g["offset"], g["where"]) == (int(e[0]) & M64, e[1], e[2], e[3], e[4], where), (i, g, e)
+            flags_seen.add(where)
+        # the independent Python restatement as well
+        sets = dict(umis=set(int(k) for k in keys)) if not bc else dict(gene=set(int(k) for k in keys) or None, all_bcs=set(int(k) for k in allk), all_ed=3,
+                                                                        empty=set(int(k) for k in empk), empty_ed=2)
+        t = pyref.GuidedTester(ed, L, post4, bailout=None if bail < 0 else bail, bc_flavour=bc, **sets)
+        py = [(n_.seq, n_.nSub, n_.nIns, n_.nDel, n_.offset, n_.flag) for n_ in t.run(w, off)]
+        assert py == [(int(g["seq"]), g["n_sub"], g["n_ins"], g["n_del"], g["offset"], g["where"]) for g in got]
+        n_entries += len(exp)
+    assert n_entries >= 100
+    assert {orc.W_GENE, orc.W_ALL, orc.W_EMPTY, orc.W_GENE | orc.W_ALL} <= flags_seen      # the inherited GENE bit occurs in the reference's own output
+
+
+def test_best_of_nine_and_packing_match_reference_bytecode(orc):
+    """new ClusteringEditDistanceBase(eds) run by the reference's own class files (eds from its LevenshteinDistance.apply): the visiting
+    order ZERO, PLUSONE, MINUSONE with strict '<', the BestEditDistance int and its transposed copy, the equality constant"""
+    z = np.load(os.path.join(GOLDEN, "ref_best9.npz"))
+    L = orc.lib()
+    assert L.orc_umi_equality() == int(z["equality"])
+    shifted = 0
+    for row in z["rows"]:
+        a, b = row[:14].astype(np.uint8).tobytes(), row[14:28].astype(np.uint8).tobytes()
+        packed = L.orc_umi_best9(a, b, 12)
+        assert packed == int(np.int32(row[28])), (row, hex(packed))
+        assert L.orc_umi_transpose(packed) == int(np.int32(row[29]))
+        shifted += (packed >> 24) != 0x12
+    assert shifted > 20                                   # best distance found at a non-central window in a good share of the pairs
+
+
+def test_assign_barcode_matches_reference_bytecode(orc):
+    """Parser.assignBarcode run by the reference's own class files on whole reads (3' and 5' geometry, several offsets / ED levels, N around
+    the window, windows that run off the read): assigned barcode, ed, ed_sec, bcStart, bcEnd, rank, the BarcodeCounts update, the unassigned
+    and the throwing reads.  The HashSet<OneMatch> iteration order behind `matches.stream().sorted()` is the JDK algorithm as modelled by
+    oracle/minijvm.JdkHashSet (there is no JDK here); everything else is the reference's bytecode."""
+    z = np.load(os.path.join(GOLDEN, "ref_assign.npz"))
+    n = len(z["read"])
+    seen = np.zeros(3, dtype=int)
+    for i in range(n):
+        read = str(z["read"][i]).encode()
+        keys = z["keys"][z["key_offsets"][i]:z["key_offsets"][i + 1]]
+        rank = np.arange(1, len(keys) + 1, dtype=np.int32)
+        ap, tp, ed, pm = int(z["adapterpos"][i]), bool(z["three_prime"][i]), int(z["ed"][i]), int(z["pm"][i])
+        anchor = (ap - 16) - 1 if tp else ap                    # Parser.java:L206-L210 (1-based adapterpos -> 0-based window start)
+        sl = np.frombuffer(read, dtype=np.uint8).reshape(1, -1).copy()
+        res, _ = orc.assign_barcode_batch(orc.BarcodeSet(keys, rank), sl, np.array([anchor], dtype=np.int32), ed, pm, tp, slice_len=len(read))
+        r = res[0]
+        status = int(z["status"][i])
+        seen[status] += 1
+        if status == 2:
+            assert r["flags"] & orc.F_EXCEPTION, (i, str(z["exc"][i]), r)
+            continue
+        assert not (r["flags"] & orc.F_EXCEPTION), (i, r)
+        if status == 0:
+            assert not (r["flags"] & orc.F_ASSIGNED), (i, r)
+            continue
+        bc, e, e2, start, end, rk, _flag = (int(x) for x in z["result"][i])
+        assert r["flags"] & orc.F_ASSIGNED, (i, r)
+        off = int(r["offset"])
+        g_start = ap - 1 + off if tp else ap + 1 + off          # Parser.java:L274-L276
+        g_end = g_start - 15 - (int(r["n_ins"]) - int(r["n_del"])) if tp else g_start + 15 + (int(r["n_ins"]) - int(r["n_del"]))   # L278-L279
+        assert (int(r["bc"]), int(r["ed"]), int(r["ed_second"]), g_start, g_end, int(r["rank"])) == (bc, e, int(np.int32(e2)), start, end, rk), (i, r, z["result"][i])
+        cnt = z["counts"][z["counts"][:, 0] == i]
+        assert len(cnt) == 1 and int(cnt[0, 1]) == bc and int(cnt[0, 2]) == e and int(cnt[0, 3]) == 1      # BarcodeCounts.addCountForEd (L305-L311)
+    assert seen[1] >= 10 and seen[0] >= 3 and seen[2] >= 1, seen
+
+
+# ------------------------------------------------------------------------------------------------------------- GPU vs the reference's bytecode
+@pytest.mark.gpu
+def test_gpu_assign_barcode_matches_reference_bytecode(pkg, ctx):
+    """the CUDA kernel through the C ABI, directly against Parser.assignBarcode as run from the reference's class files"""
+    z = np.load(os.path.join(GOLDEN, "ref_assign.npz"))
+    checked = 0
+    for i in range(len(z["read"])):
+        read = str(z["read"][i]).encode()
+        keys = z["keys"][z["key_offsets"][i]:z["key_offsets"][i + 1]]
+        rank = np.arange(1, len(keys) + 1, dtype=np.int32)
+        ap, tp, ed, pm = int(z["adapterpos"][i]), bool(z["three_prime"][i]), int(z["ed"][i]), int(z["pm"][i])
+        anchor = (ap - 16) - 1 if tp else ap
+        start = min(max(anchor - 8, 0), max(len(read) - 32, 0))               # a 32-byte slice of the read around the windows
+        sl = np.zeros((1, 32), dtype=np.uint8)
+        piece = read[start:start + 32]
+        sl[0, :len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+        table = pkg.BarcodesMapForBCfinding(ctx, keys, rank)
+        r = pkg.Parser(ctx, table, bcEditDistance=ed, testPlusMinusPos=pm, three_prime=tp).assign_barcodes(
+            sl, np.array([anchor - start], dtype=np.int32), lens=np.array([len(piece)], dtype=np.int32))[0]
+        status = int(z["status"][i])
+        if status == 2:
+            assert r["flags"] & 2, (i, r)
+        elif status == 0:
+            assert not (r["flags"] & 3), (i, r)
+        else:
+            bc, e, e2, bstart, bend, rk, _ = (int(x) for x in z["result"][i])
+            off = int(r["offset"])
+            g_start = ap - 1 + off if tp else ap + 1 + off
+            g_end = g_start - 15 - (int(r["n_ins"]) - int(r["n_del"])) if tp else g_start + 15 + (int(r["n_ins"]) - int(r["n_del"]))
+            assert r["flags"] & 1 and (int(r["bc"]), int(r["ed"]), int(r["ed_second"]), g_start, g_end, int(r["rank"])) == \
+                   (bc, e, int(np.int32(e2)), bstart, bend, rk), (i, r, z["result"][i])
+            counts = table.counts()
+            assert counts.sum() == 1 and counts[list(keys).index(bc), e] == 1
+        checked += 1
+    assert checked == 40
+
+
+@pytest.mark.gpu
+def test_gpu_guided_engine_matches_reference_bytecode(pkg, ctx):
+    """the guided kernel's raw list (plusminus 0: one tester) against UMInuc / BCnucTwoBitPerBaseEDtester.matchesSeqEditDistance as run from the
+    reference's class files; startOffsetFromPredicted is a label the caller passes and is not compared"""
+    import workloads
+    z = np.load(os.path.join(GOLDEN, "ref_guided.npz"))
+    fg, fa, fe = int(z["flag_gene"]), int(z["flag_all"]), int(z["flag_empty"])
+    for i in range(len(z["w"])):
+        sl_ = lambda k, o: z[k][z[o][i]:z[o][i + 1]]
+        keys, allk, empk = sl_("keys", "key_offsets"), sl_("all_keys", "all_offsets"), sl_("empty_keys", "empty_offsets")
+        bc, L, ed, bail, w = bool(z["bc"][i]), int(z["L"][i]), int(z["ed"][i]), int(z["bail"][i]), int(z["w"][i])
+        post = str(z["post"][i]).rstrip("-")
+        s = (workloads.g_unpack(w, L) + post).ljust(32, "A").encode()
+        sets = pkg.GuidedSets(ctx, keys, np.array([0, len(keys)], dtype=np.int64), L, bc_flavour=bc, all_keys=allk if bc else None, all_ed=3,
+                              empty_keys=empk if bc else None, empty_ed=2)
+        res, raw = sets.match(np.frombuffer(s, dtype=np.uint8).reshape(1, 32), np.array([0], dtype=np.int32), np.array([0], dtype=np.int32), ed, 0,
+                              len(post), bailout=None if bail < 0 else bail, slice_len=32, raw_cap=64)
+        exp = z["res"][z["res"][:, 0] == i][:, 1:]
+        assert not res[0]["flags"] and res[0]["n_raw"] == len(exp), (i, res[0], len(exp))
+        for g, e in zip(raw[0], exp[:64]):
+            where = (1 if int(e[5]) & fg else 0) | (2 if int(e[5]) & fa else 0) | (4 if int(e[5]) & fe else 0)
+            assert (int(g["seq"]), g["n_sub"], g["n_ins"], g["n_del"], g["where"]) == (int(e[0]) & M64, e[1], e[2], e[3], where), (i, g, e)
