@@ -1,6 +1,6 @@
 /*
- * slr_oracle.c — CPU ORACLE (test infrastructure, NOT product code).  See slr_oracle.h for status:
- * "parity unpinned" (no reference tests / golden vectors exist, reference is JVM bytecode only).
+ * slr_oracle.c — CPU ORACLE (test infrastructure, NOT product code).  See slr_oracle.h for the parity status (pinned against the
+ * reference's own class files executed by oracle/minijvm.py; what is only restated is listed there).
  *
  * Every function restates one reference method, cited as  jar!class (File.java:Lnnn).
  *   F! = /root/reference/Jar/NanoporeBC_UMI_finder-2.1.jar

@@ -6,10 +6,13 @@
  * notation:  F! = Jar/NanoporeBC_UMI_finder-2.1.jar,  T! = Jar/lib/TwoFourBitNucAcidLibraryMaven-1.0.jar,
  * (Foo.java:Lnnn) = original source line recovered from the LineNumberTable (tools/jdis.py).
  *
- * PARITY STATUS: "parity unpinned".  The reference ships no tests / golden vectors for this path and
- * cannot be executed in the build container (no JVM).  The oracle is pinned only by (i) the two
- * read-name examples of /root/reference/README.md:400,452, (ii) an independent second restatement
- * (oracle/pyref.py) and (iii) brute-force property checks (tests/).
+ * PARITY STATUS: the reference ships no tests / golden vectors for this path and there is no JVM in the build container, but its class
+ * files are: oracle/minijvm.py (a JVM-subset interpreter) executes them unmodified and oracle/make_ref_vectors.py freezes the outputs in
+ * tests/golden/ref_*.npz.  Pinned that way (tests/test_ref_vectors.py): the 2-bit primitives, limitedCompare, best-of-9 + packing,
+ * BarcodeMatchTester.doJob, the Illumina-guided testers and Parser.assignBarcode.  JDK / third-party containers are shims there
+ * (java.util.HashSet iteration order = the JDK HashMap algorithm as modelled, not executed).  Restated only: the UMI window slicing, the
+ * guided consumers' offset loop + sorted().distinct(), getmaxED, the pass-1 exact lookup.  Also: the two read-name examples of
+ * /root/reference/README.md:400,452, an independent second restatement (oracle/pyref.py) and brute-force property checks (tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may link
  * or call this file.  The product (libsicelore_gpu.so) never does.
