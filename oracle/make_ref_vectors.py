@@ -242,6 +242,52 @@ def best9_cases(vm, rng, n, umi_len=12):
     return np.array(rows, dtype=np.int64), eq
 
 
+def umi_pair_cases(vm, rng, n, umi_len=12):
+    """calcEditDistances itself (ClusteringEditDistanceBase.lambda$static$7, java:L297-L350): two reads with their X= mini-sequences and the
+    barcode end on the stranded mini-sequence -> window slicing (getSeqRevComp / getSeq, getSubSequence(bcEnd + 1 + i, umi_length)), the
+    equal-bytes shortcut, the nine thresholded distances, best-of-9 and packing.  Only getCellBCendOnStrandedShortTestedSeq (the mapping
+    of the read-name bcEnd onto the mini-sequence) is replaced by the value given here."""
+    CED = "com/rw/clustering/ClusteringEditDistanceBase"
+    ONR = "com/rw/umifinder/reads/nanopore/OneNanoporeResult"
+    vm.init_class(vm.load(CED))
+    onr = vm.load(ONR)
+    vm.init_class(onr)
+    comp = str.maketrans("ACGTN", "TGCAN")
+    rows = []
+    for t in range(n):
+        five = t % 4 == 3
+        params = bare(vm, "com/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams")
+        up = bare(vm, "com/rw/parameters/UMIparameters")
+        up.f["umi_length"] = umi_len
+        params.f["umis"] = up
+        st = vm.load("com/rw/parameters/ParametersMainBase$SCANTYPE")
+        vm.init_class(st)
+        params.f["scantype"] = st.statics["FIVEP_BARCODE" if five else "THREEP_BARCODE"]
+        umi = rseq(rng, umi_len)
+        recs, ends, strs = [], [], []
+        for k in range(2):
+            u = umi if k == 0 or t % 5 == 0 else mutate(rng, umi, int(rng.integers(0, 4)))
+            if t % 7 == 0 and k == 1:
+                u = u[:3] + "N" + u[4:]
+            lead = int(rng.integers(3, 9))
+            stranded = rseq(rng, lead) + u + rseq(rng, 24)                    # ... barcode end | UMI | polyA side
+            bc_end = lead + (int(rng.integers(-1, 2)) if t % 3 == 0 else 0)    # 1-based end of the barcode on the stranded mini-sequence
+            x = stranded if five else stranded[::-1].translate(comp)           # what the read name carries (read orientation)
+            sd = vm.new_object(vm.load("com/rw/umifinder/reads/nanopore/NanoporeRead$ReadScanData"))
+            vm.call_virtual(sd, "setSeq", "(Ljava/lang/CharSequence;)V", x)
+            nr = bare(vm, "com/rw/umifinder/reads/nanopore/NanoporeRead")
+            nr.f["readScanData"] = J.JNative("com/google/common/base/Optional", (sd,))
+            r = bare(vm, ONR)
+            r.f["nanoporeRead"] = nr
+            recs.append(r); ends.append(bc_end); strs.append(stranded)
+        table = {id(recs[0]): ends[0], id(recs[1]): ends[1]}
+        onr.statics["getCellBCendOnStrandedShortTestedSeq"] = J.JNative("pyfunc", lambda r, p: J.JNative("java/util/Optional", (table[id(r)],)))
+        o = vm.invoke_exact(CED, "lambda$static$7", "(L%s;L%s;Lcom/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams;)L%s;" % (ONR, ONR, CED),
+                            [recs[0], recs[1], params])
+        rows.append((strs[0], strs[1], ends[0], ends[1], int(five), o.f["bestEditDistance"].f["ed"]))
+    return rows
+
+
 PKG = "com/rw/nanoporereadscanner/"
 
 
@@ -331,6 +377,81 @@ def assign_cases(vm, rng, n_cases):
     return cases
 
 
+TAGS = dict(paStartPrefix="PS=", paEndPrefix="PE=", adapterPosPrefix="AE=", tsoPosPrefix="T=", seqPrefix="X=", qvPrefix="Q=", barcodeSeqPrefix="bc=",
+            barcodeEdPrefix="ed=", barcodeEdSecondaryPrefix="ed_sec=", barcodeStartPrefix="bcStart=", barcodeEndPrefix="bcEnd=", barcodeRankPrefix="rk=")
+
+
+def read_name_cases(vm, rng, n):
+    """FastqRecordExt.getScanDatFromReadName (the assignumis side of the read-name format) on the reference's bytecode: the two README
+    examples and generated names (missing tags, T=, sp2 prefix, ed above the assignumis limit).  Output: the parsed fields."""
+    F = PKG + "readerwriter/FastqRecordExt"
+    names = ["b5c7-read_FWD_PS=566_PE=590_AE=619_bc=TCCGATCGTGCCAAGA_ed=0_ed_sec=2147483647_bcStart=618_bcEnd=603_rk=2987_X=AAAAAAAAAAAATGGCGTGTATTGTCTTGGCACGATCGGAAGA_Q=27.1",
+             "sp2_REV_PS=1257_PE=1305_AE=1327_T=40_bc=GAGTGAGGTTGGGTAG_ed=1_ed_sec=2147483647_bcStart=1326_bcEnd=1311_rk=3883_X=AAAAAAAAAAACAAACCAAGTAACCAACCCAACCTCACTCAGA_Q=15.9",
+             "no_tags_at_all", "r_FWD_PS=5_PE=9_"]
+    for t in range(n):
+        nm = "read%d" % t + ("_REV" if t % 2 else "_FWD") + "_"
+        if t % 3:
+            nm += "PS=%d_PE=%d_" % (rng.integers(10, 900), rng.integers(10, 900))
+        nm += "AE=%d_" % rng.integers(20, 2000)
+        if t % 4 == 0:
+            nm += "T=%d_" % rng.integers(1, 99)
+        if t % 5:
+            nm += "bc=%s_ed=%d_" % (rseq(rng, 16), rng.integers(0, 4))
+            if t % 7:
+                nm += "ed_sec=%d_" % rng.choice([1, 2, 3, 2147483647])
+            nm += "bcStart=%d_bcEnd=%d_" % (rng.integers(20, 2000), rng.integers(20, 2000))
+            if t % 6:
+                nm += "rk=%d_" % rng.integers(1, 9000)
+        nm += "X=%s_Q=%.1f" % (rseq(rng, 43), rng.uniform(5, 40))
+        if t % 8 == 7:
+            pass                                                   # no trailing '_': the base-36 read-id parse throws (like the README's trimmed examples)
+        elif t % 2 == 0:
+            nm += "_"                                              # what scanfastq writes: '_' after Q= (FastqRecordExt.java:L271) ...
+        else:
+            nm += "_" + vm.call_static(F + "$NumberToAndFromAscii", "convertInt", "(I)Ljava/lang/String;", int(rng.integers(0, 10 ** 8)))   # ... + the base-36 read id
+        names.append(nm)
+    out = []
+    for lim in (None, 1):
+        params = bare(vm, "com/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams")
+        rsp, bp = bare(vm, "com/rw/parameters/ReadScannerParameters"), bare(vm, "com/rw/parameters/BarcodeParameters")
+        for k, v in TAGS.items():
+            rsp.f[k] = v
+        bp.f["cellBC_editdistance"] = lim
+        params.f["readScannerParameters"], params.f["barcodes"] = rsp, bp
+        for nm in names:
+            sup = J.JNative("pyfunc", lambda: vm.new_object(vm.load(PKG + "readerwriter/ReadScanResult")))
+            try:
+                r = vm.call_static(F, "getScanDatFromReadName", "(Ljava/lang/String;Lcom/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams;"
+                                                                "Ljava/util/function/Supplier;)Lcom/google/common/base/Optional;", nm, params, sup)
+            except J.JavaThrow as ex:
+                out.append((nm, -1 if lim is None else lim, "EXC:" + ex.cls.split("$")[-1].split("/")[-1]))
+                continue
+            if not r.v:
+                out.append((nm, -1 if lim is None else lim, "ABSENT"))
+                continue
+            sr = r.v[0]
+            d = {}
+            sub = lambda o: o.f if isinstance(o, J.JObj) else {}
+            for k, v in sr.f.items():
+                if isinstance(v, J.JObj):
+                    cn = v.cls.name.split("$")[-1]
+                    for kk, vv in v.f.items():
+                        if isinstance(vv, (int, float)) and not isinstance(vv, bool):
+                            d[cn + "." + kk] = vv
+                        elif isinstance(vv, J.JObj) and "sequence" in vv.f:
+                            d[cn + "." + kk] = int(vv.f["sequence"]) & M64
+                        elif isinstance(vv, J.JNative) and vv.name.endswith("Optional") and vv.v:
+                            d[cn + "." + kk] = vv.v[0]
+            d["read_id"] = sr.f.get("read_id")
+            for k, v in sr.f.items():
+                if isinstance(v, float):
+                    d[k] = float(np.float32(v))
+            if isinstance(sr.f.get("seq"), J.JObj):
+                d["seq_len"] = len(sr.f["seq"].f["naData"].a)
+            out.append((nm, -1 if lim is None else lim, repr(sorted(d.items()))))
+    return out
+
+
 def flat(cases, key):
     off = np.cumsum([0] + [len(c[key]) for c in cases]).astype(np.int64)
     return np.array([k for c in cases for k in c[key]], dtype=np.uint64), off
@@ -353,6 +474,17 @@ def main():
     b9, eq = best9_cases(vm, np.random.default_rng(99), 300)
     np.savez_compressed(os.path.join(OUT, "ref_best9.npz"), rows=b9, equality=np.int64(eq))
     print("best-of-9", b9.shape, "ED histogram", np.bincount(b9[:, 28] & 0xFFFFFF), "equality %#x" % eq)
+
+    up = umi_pair_cases(vm, np.random.default_rng(4242), 200)
+    np.savez_compressed(os.path.join(OUT, "ref_umi_pairs.npz"), s1=np.array([r[0] for r in up]), s2=np.array([r[1] for r in up]),
+                        end1=np.array([r[2] for r in up], dtype=np.int32), end2=np.array([r[3] for r in up], dtype=np.int32),
+                        five_prime=np.array([r[4] for r in up], dtype=np.int32), packed=np.array([r[5] for r in up], dtype=np.int64))
+    print("calcEditDistances", len(up), "pairs, ED histogram", np.bincount(np.array([r[5] for r in up]) & 0xFFFFFF))
+
+    rn = read_name_cases(vm, np.random.default_rng(31), 40)
+    np.savez_compressed(os.path.join(OUT, "ref_read_names.npz"), name=np.array([r[0] for r in rn]), limit=np.array([r[1] for r in rn], dtype=np.int32),
+                        parsed=np.array([r[2] for r in rn]))
+    print("getScanDatFromReadName", len(rn), "names")
 
     dj = dojob_cases(vm, rng, 45)
     keys, koff = flat(dj, "keys")

@@ -19,6 +19,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import jdis  # noqa: E402
 
 
+def np_float32(x):
+    return struct.unpack("f", struct.pack("f", float(x)))[0]
+
+
 class L(int):
     """a Java long on the operand stack / in a local (category-2 value)"""
     __slots__ = ()
@@ -413,7 +417,10 @@ class VM:
         if cls in ("java/lang/Long", "java/lang/Integer", "java/lang/Boolean", "java/lang/Byte", "java/lang/Short"):
             if name == "valueOf":
                 return a[0]
-            if name.endswith("Value") and name != "shortValue" and name != "byteValue":
+            if name == "byteValue":
+                v = a[0] & 0xFF
+                return v - 256 if v & 0x80 else v
+            if name.endswith("Value") and name != "shortValue":
                 return a[0]
         if cls == "java/lang/Math":
             return {"abs": lambda: abs(a[0]), "max": lambda: max(a[0], a[1]), "min": lambda: min(a[0], a[1])}[name]()
@@ -540,16 +547,77 @@ class VM:
             if not a[0].v:
                 raise JavaThrow("java/util/NoSuchElementException")
             return a[0].v[0]
+        if cls in ("java/lang/String", "java/lang/CharSequence", "java/lang/Object") and isinstance(a[0] if a else None, str) and name in ("indexOf", "lastIndexOf", "split", "equals", "isEmpty", "trim",
+                                                                                          "startsWith", "endsWith", "contains", "toString", "hashCode"):
+            t = a[0]
+            arg = a[1] if len(a) > 1 else None
+            if name in ("indexOf", "lastIndexOf"):
+                needle = chr(arg) if isinstance(arg, int) else arg
+                return (t.find(needle, a[2]) if len(a) > 2 else t.find(needle)) if name == "indexOf" else t.rfind(needle)
+            if name == "split":
+                arr = JArr("L", 0, None)
+                arr.a = t.split(arg)
+                while arr.a and arr.a[-1] == "":
+                    arr.a.pop()
+                return arr
+            if name == "equals":
+                return int(t == arg)
+            if name == "isEmpty":
+                return int(not t)
+            if name == "trim":
+                return t.strip()
+            if name == "startsWith":
+                return int(t.startswith(arg))
+            if name == "endsWith":
+                return int(t.endswith(arg))
+            if name == "contains":
+                return int(arg in t)
+            if name == "toString":
+                return t
+            if name == "hashCode":
+                h = 0
+                for ch in t:
+                    h = i32(31 * h + ord(ch))
+                return h
+        if cls in ("java/lang/Integer", "java/lang/Float", "java/lang/Long") and name in ("parseInt", "parseFloat", "parseLong"):
+            try:
+                if name == "parseFloat":
+                    return float(np_float32(a[0]))
+                radix = a[1] if len(a) > 1 else 10
+                t = a[0]
+                digits = t[1:] if t[:1] in "+-" else t
+                if not digits or any(not ch.isalnum() or int(ch, 36) >= radix for ch in digits):      # Character.digit(ch, radix) < 0
+                    raise ValueError
+                v = int(t, radix)
+                if not -(1 << 31) <= v < (1 << 31) and name == "parseInt":
+                    raise ValueError
+                return v
+            except ValueError:
+                raise JavaThrow("java/lang/NumberFormatException", a[0])
+        if cls == "java/lang/Float" and name == "valueOf":
+            return a[0]
+        if cls == "java/lang/Integer" and name == "toString" and len(a) == 2:
+            n_, r_ = a
+            out = ""
+            m_ = abs(n_)
+            while True:
+                out = "0123456789abcdefghijklmnopqrstuvwxyz"[m_ % r_] + out
+                m_ //= r_
+                if m_ == 0:
+                    break
+            return ("-" if n_ < 0 else "") + out
         if cls == "java/lang/String" and name == "valueOf":
             return str(int(a[0])) if isinstance(a[0], int) else str(a[0])
         if cls == "java/lang/Integer" and name == "shortValue":
             v = a[0] & 0xFFFF
             return v - 0x10000 if v & 0x8000 else v
-        if cls == "java/lang/String" and name == "substring" and isinstance(a[0], str):
+        if cls in ("java/lang/String", "java/lang/CharSequence") and name in ("substring", "subSequence") and isinstance(a[0], str):
             b, e = a[1], (a[2] if len(a) > 2 else len(a[0]))
             if b < 0 or e > len(a[0]) or b > e:
                 raise JavaThrow("java/lang/StringIndexOutOfBoundsException", "begin %d, end %d, length %d" % (b, e, len(a[0])))
             return a[0][b:e]
+        if cls == "com/google/common/base/Optional" and name in ("absent", "of", "fromNullable"):
+            return JNative(cls, () if name == "absent" or a[0] is None else (a[0],))
         if cls == "java/util/Optional":
             if name == "empty":
                 return JNative("java/util/Optional", ())
@@ -608,6 +676,8 @@ class VM:
                 else:
                     a[0].a[a[1]:a[2]] = [a[3]] * (a[2] - a[1])
                 return None
+            if name == "equals":
+                return int(a[0] is a[1] or (a[0] is not None and a[1] is not None and a[0].a == a[1].a))
             if name == "hashCode":
                 h = 1
                 for b in a[0].a:
@@ -642,6 +712,8 @@ class VM:
                 return JNative("java/util/EnumSet", sorted([x for x in a if isinstance(x, JObj)], key=lambda e: e.f["$ordinal"]))
             if name == "iterator":
                 return JNative("java/util/Iterator", [list(a[0].v), 0])
+            if name == "size":
+                return len(a[0].v)
             if name == "contains":
                 return int(any(e is a[1] for e in a[0].v))
         if cls == "java/util/Iterator":

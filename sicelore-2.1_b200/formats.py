@@ -41,10 +41,32 @@ def mean_qv(quals, start, stop):
     return np.float32(sum(ord(c) - 33 for c in q) / len(q))
 
 
+def convert_int(number):
+    """FastqRecordExt$NumberToAndFromAscii.convertInt (L524): Integer.toString(number, 36)"""
+    digits, n, out = "0123456789abcdefghijklmnopqrstuvwxyz", abs(int(number)), ""
+    while True:
+        out = digits[n % 36] + out
+        n //= 36
+        if n == 0:
+            break
+    return ("-" if number < 0 else "") + out
+
+
+def convert_string(s):
+    """NumberToAndFromAscii.convertString (L535): Integer.parseInt(s, 36); ValueError = NumberFormatException"""
+    body = s[1:] if s[:1] in "+-" else s
+    if not body or any(not (ch.isascii() and ch.isalnum()) for ch in body):
+        raise ValueError("NumberFormatException: For input string: %r" % s)
+    v = int(s, 36)
+    if not -(1 << 31) <= v < (1 << 31):
+        raise ValueError("NumberFormatException: For input string: %r" % s)
+    return v
+
+
 def read_name_extension(reversed_read, stranded_seq, stranded_quals, adapter_end=None, polya_start=None, polya_end=None, tso_end=None,
-                        bc=None, ed=None, ed_second=None, bc_start=None, bc_end=None, rank=None, is5p=False, tags=ReadNameTags, bc_len=16):
-    """The `add` StringBuilder of getRecordForWriting for a read that passed (L226-L277), without the optional read id (L272-L273:
-    FastqRecordExt$NumberToAndFromAscii.convertInt, only written when scanfastq is asked to number the reads).
+                        bc=None, ed=None, ed_second=None, bc_start=None, bc_end=None, rank=None, is5p=False, tags=ReadNameTags, bc_len=16,
+                        read_id=None):
+    """The `add` StringBuilder of getRecordForWriting for a read that passed (L226-L277); read_id (optional) is appended in base 36 (L272-L273).
     bc = 2-bit barcode (int) or string; None = no barcode found.  Positions are the 1-based positions on the stranded read."""
     add = "_REV" if reversed_read else "_FWD"
     add += "_"
@@ -77,6 +99,8 @@ def read_name_extension(reversed_read, stranded_seq, stranded_quals, adapter_end
             add += "%s%s_" % (tags.seqPrefix, stranded_seq[begin:end])           # L261-L264
             add += "%s%s" % (tags.qvPrefix, _dec_format_1(mean_qv(stranded_quals, begin, end)))     # L270
             add += "_"                                                           # L271
+            if read_id is not None:
+                add += convert_int(read_id)                                      # L272-L273
     if bc is not None:
         add += " cellBC=" + (bc if isinstance(bc, str) else unpack2bit(bc, bc_len))                # L276-L277
     return add
@@ -94,7 +118,8 @@ def _extract(s, tag):
 
 def parse_read_name(name, tags=ReadNameTags, max_bc_ed=None):
     """getScanDatFromReadName (L411-L489).  Returns None when neither _REV_ nor _FWD_ is present (Optional.absent, L418); raises
-    KeyError when the adapter tag is missing (AdapterInfoNotFoundInReadException, L442-L443).  max_bc_ed = the assignumis limit on the
+    KeyError when the adapter tag is missing (AdapterInfoNotFoundInReadException, L442-L443) and ValueError when the text after the last
+    '_' is not a base-36 number (NumberFormatException from the read-id parse, L492-L494: scanfastq always writes '_' after Q=).  max_bc_ed = the assignumis limit on the
     barcode edit distance: a larger ed= drops the whole barcode block (L450-L459)."""
     k = name.find("_REV_")
     if k >= 0:
@@ -140,6 +165,9 @@ def parse_read_name(name, tags=ReadNameTags, max_bc_ed=None):
         out["seq"] = seq
     if qv is not None:
         out["mean_qv"] = float(np.float32(qv))
+    last = sub.rfind("_")                                                        # L492-L494: whatever follows the last '_' is the base-36 read id
+    if last < len(sub) - 1:
+        out["read_id"] = convert_string(sub[last + 1:])                          # a name that does not end in '_' [+ id] throws, like the Java
     return out
 
 

@@ -3,6 +3,7 @@
 import os
 
 import numpy as np
+import pytest
 
 import __graft_entry__ as g
 
@@ -20,15 +21,18 @@ def fmt():
 
 def test_parse_readme_examples():
     F = fmt()
-    a = F.parse_read_name("b5c7a1f2-read" + README_400)
+    with pytest.raises(ValueError):                      # as published (trimmed after Q=) the reference's own parser throws on the read-id field
+        F.parse_read_name("b5c7a1f2-read" + README_400)
+    a = F.parse_read_name("b5c7a1f2-read" + README_400 + "_")
     assert a == dict(reversed=False, polya_start=566, polya_end=590, adapter_end=619, ed=0, bc="TCCGATCGTGCCAAGA", ed_second=2147483647,
                      bc_start=618, bc_end=603, rank=2987, seq="AAAAAAAAAAAATGGCGTGTATTGTCTTGGCACGATCGGAAGA", mean_qv=float(np.float32(27.1)))
-    b = F.parse_read_name("sp2" + README_452)
+    b = F.parse_read_name("sp2" + README_452 + "_")
     assert b["reversed"] and b["tso_end"] == 40 and b["adapter_end"] == 1327 and b["bc"] == "GAGTGAGGTTGGGTAG" and b["ed"] == 1
     assert b["bc_start"] == 1326 and b["bc_end"] == 1311 and b["rank"] == 3883 and abs(b["mean_qv"] - 15.9) < 1e-6
     assert F.parse_read_name("read_without_tags") is None
     # the assignumis limit on the barcode ED drops the barcode block (FastqRecordExt.java:L450-L459)
-    c = F.parse_read_name("x" + README_452, max_bc_ed=0)
+    c = F.parse_read_name("x" + README_452 + "_1z", max_bc_ed=0)
+    assert c["read_id"] == 71
     assert "bc" not in c and "rank" not in c and c["adapter_end"] == 1327
 
 
@@ -36,7 +40,7 @@ def test_write_reproduces_readme_examples():
     """rebuild the stranded read around the published X= string and write the extension back: identical up to the published end"""
     F = fmt()
     for ex, qv in ((README_400, 27.1), (README_452, 15.9)):
-        p = F.parse_read_name("r" + ex)
+        p = F.parse_read_name("r" + ex + "_")
         ae, x = p["adapter_end"], p["seq"]
         begin = ae - 40 - 1                               # 3' geometry (L253): X = stranded[AE-41, AE+2)
         stranded = "C" * begin + x + "G" * 50
@@ -57,9 +61,9 @@ def test_barcode_geometry_of_readme_examples():
     """bc= is the reverse complement of X[-19:-3] up to `ed` edits; bcStart - bcEnd = 15 (3' reads count down towards the polyA)"""
     F = fmt()
     rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))
-    a = F.parse_read_name("r" + README_400)
+    a = F.parse_read_name("r" + README_400 + "_")
     assert rc(a["seq"][-19:-3]) == a["bc"] and a["bc_start"] - a["bc_end"] == 15 and a["bc_start"] == a["adapter_end"] - 1
-    b = F.parse_read_name("r" + README_452)
+    b = F.parse_read_name("r" + README_452 + "_")
     w = rc(b["seq"][-19:-3])
     assert sum(x != y for x, y in zip(w, b["bc"])) == b["ed"] == 1
 
@@ -86,3 +90,48 @@ def test_assigned_tsv_round_trip(tmp_path):
     assert rows[0] == ("CGGACTGTCTTGTACT", 140612, 118919, 21693) and len(rows) == 3
     F.write_assigned_tsv(path, keys, counts, 2)
     assert open(path).readline() == "Barcode\tn Reads with ED<=2 match\tED=0\tED=1\tED=2\n"
+
+
+def test_parser_matches_reference_bytecode():
+    """FastqRecordExt.getScanDatFromReadName run by the reference's own class files (oracle/minijvm.py, tests/golden/ref_read_names.npz): every
+    parsed field, the absent / adapter-missing / read-id NumberFormatException outcomes, with and without the assignumis barcode-ED limit"""
+    F = fmt()
+    pkg = g.load_package()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_read_names.npz"))
+    outcomes = set()
+    for name, lim, parsed in zip(z["name"], z["limit"], z["parsed"]):
+        name, parsed = str(name), str(parsed)
+        try:
+            got = F.parse_read_name(name, max_bc_ed=None if lim < 0 else int(lim))
+        except KeyError:
+            assert parsed == "EXC:AdapterInfoNotFoundInReadException", (name, parsed)
+            outcomes.add("adapter")
+            continue
+        except ValueError:
+            assert parsed == "EXC:NumberFormatException", (name, parsed)
+            outcomes.add("nfe")
+            continue
+        if got is None:
+            assert parsed == "ABSENT"
+            outcomes.add("absent")
+            continue
+        exp = dict(eval(parsed))
+        want = {"Adapterresult.end": got.get("adapter_end"), "Forward.$ordinal": int(got["reversed"]), "read_id": got.get("read_id", 0)}
+        if "tso_end" in got:
+            want["TSOresult.end"] = got["tso_end"]
+        if "polya_start" in got:
+            want["PolyAResult.start"] = got["polya_start"]
+        if "polya_end" in got:
+            want["PolyAResult.end"] = got["polya_end"]
+        for k, jk in (("ed", "editDistance"), ("ed_second", "editDistanceSecondBest"), ("bc_start", "start"), ("bc_end", "end"), ("rank", "rank")):
+            if k in got:
+                want["BarcodeResult." + jk] = got[k]
+        if "bc" in got:
+            want["BarcodeResult.barcodeseq"] = int(pkg.pack_barcode(got["bc"]))
+        if "seq" in got:
+            want["seq_len"] = len(got["seq"])
+        if "mean_qv" in got:
+            want["mean_qv"] = got["mean_qv"]
+        assert want == exp, (name, want, exp)
+        outcomes.add("ok" if "bc" in got else "ok_nobc")
+    assert outcomes == {"adapter", "nfe", "absent", "ok", "ok_nobc"}

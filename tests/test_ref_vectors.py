@@ -209,3 +209,34 @@ def test_gpu_guided_engine_matches_reference_bytecode(pkg, ctx):
         for g, e in zip(raw[0], exp[:64]):
             where = (1 if int(e[5]) & fg else 0) | (2 if int(e[5]) & fa else 0) | (4 if int(e[5]) & fe else 0)
             assert (int(g["seq"]), g["n_sub"], g["n_ins"], g["n_del"], g["where"]) == (int(e[0]) & M64, e[1], e[2], e[3], where), (i, g, e)
+
+
+def test_calc_edit_distances_matches_reference_bytecode(orc):
+    """calcEditDistances itself (ClusteringEditDistanceBase.lambda$static$7) run by the reference's class files: stranded mini-sequence (3' reads
+    through getSeqRevComp), the three windows getSubSequence(bcEnd + 1 + i, 12), the equal-bytes shortcut, nine distances, best-of-9, packing.
+    The S2 boundary hands the kernel the 14 codes stranded[bcEnd - 1, bcEnd + 13) — exactly what is checked here."""
+    z = np.load(os.path.join(GOLDEN, "ref_umi_pairs.npz"))
+    L = orc.lib()
+    codes = lambda s, e: bytes(pyref.ENCODE[ord(c)] for c in s[e - 1:e + 13])
+    nonzero = 0
+    for s1, s2, e1, e2, packed in zip(z["s1"], z["s2"], z["end1"], z["end2"], z["packed"]):
+        a, b = codes(str(s1), int(e1)), codes(str(s2), int(e2))
+        assert len(a) == 14 and len(b) == 14
+        assert L.orc_umi_best9(a, b, 12) == int(np.int32(packed)), (s1, s2, e1, e2, hex(int(packed)))
+        nonzero += (int(packed) & 0xFFFFFF) != 0
+    assert len(z["packed"]) == 200 and nonzero > 100
+
+
+@pytest.mark.gpu
+def test_gpu_umi_distance_matches_reference_bytecode(pkg, ctx):
+    """the UMI kernel through the C ABI against calcEditDistances as run from the reference's class files: every pair is a job of two reads"""
+    z = np.load(os.path.join(GOLDEN, "ref_umi_pairs.npz"))
+    n = len(z["packed"])
+    umis = np.zeros((2 * n, 16), dtype=np.uint8)
+    for i, (s1, s2, e1, e2) in enumerate(zip(z["s1"], z["s2"], z["end1"], z["end2"])):
+        for k, (s, e) in enumerate(((str(s1), int(e1)), (str(s2), int(e2)))):
+            umis[2 * i + k, :14] = [pyref.ENCODE[ord(c)] for c in s[e - 1:e + 13]]
+    offs = np.arange(0, 2 * n + 1, 2, dtype=np.int64)
+    m, oo = pkg.generate_distance_matrices(ctx, umis, offs, 12)
+    got = m.reshape(n, 4)[:, 1]                                  # cell (0, 1) of every 2 x 2 matrix
+    assert (got == z["packed"].astype(np.int32)).all(), np.nonzero(got != z["packed"].astype(np.int32))[0][:5]
