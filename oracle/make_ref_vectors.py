@@ -377,6 +377,70 @@ def assign_cases(vm, rng, n_cases):
     return cases
 
 
+def find_umi_cases(vm, rng, n):
+    """IlluminaUMIanalyzer.findUMI as a whole on the reference's bytecode (fixed edit distance path, java:L56-L58): the offset loop with its
+    window / post-sequence geometry, one UMInucTwoBitPerBaseEDtester per offset, getBestAndSecondBCorUMI (sorted().distinct(), both
+    NeedlemanWunsch alignments, MORE_THAN_ONE_MATCH) and the read positions.  Output: found, best and second entry, flag value, positions."""
+    U = "com/rw/umifinder/"
+    comp = str.maketrans("ACGTN", "TGCAN")
+    st = vm.load("com/rw/parameters/ParametersMainBase$SCANTYPE")
+    vm.init_class(st)
+    cases = []
+    for t in range(n):
+        ed, pm = [1, 2, 2, 2][t % 4], [1, 2][t % 2]
+        bail = None if t % 3 else 1
+        umi = rseq(rng, 12, "AAAGCT" if t % 5 == 0 else "AGCT")
+        umis = {pack(umi)} | {pack(rseq(rng, 12)) for _ in range(int(rng.integers(0, 6)))}
+        for _ in range(int(rng.integers(0, 3))):                                 # close relatives: a second-best match / ambiguity
+            umis.add(pack((mutate(rng, umi, int(rng.integers(1, 3))) + rseq(rng, 3))[:12]))
+        lead = int(rng.integers(4, 9))
+        obs = umi if t % 4 == 0 else mutate(rng, umi, int(rng.integers(0, ed + 2)))
+        stranded = rseq(rng, lead) + obs + rseq(rng, 26)
+        bc_end = lead + int(rng.integers(-pm, pm + 1)) * (t % 2)                 # predicted barcode end off by up to +-pm
+        if t % 13 == 12:
+            stranded = stranded[:bc_end + 12 + 2]                                # read ends inside the post sequence: padded with 'A' (java:L118-L124)
+        params = bare(vm, U + "parameters/ParametersBarcodeUMiFinderAppParams")
+        up = bare(vm, "com/rw/parameters/UMIparameters")
+        up.f.update(maxUMIfalseAssignmentPcnt=None, umi_editdistance=ed, incrementUMI_ED_ifFewUmis=0, umi_posplusminus=pm, umi_length=12,
+                    simulateRandomUmis=0, umi_bailout_afterED=bail, maxUMIsforincrementUMI_ED=50)
+        params.f["umis"] = up
+        params.f["scantype"] = st.statics["THREEP_BARCODE"]
+        nd = bare(vm, "com/rw/nanopore/analyzers/parameters/NeedlemanParameters")
+        nd.f["umi"] = vm.construct("com/rw/nuc/alignment/needleman/NeedlemanScores", "()V")
+        params.f["needleman"] = nd
+        ana = bare(vm, U + "analyzers/IlluminaUMIanalyzer")
+        ana.f["parameters"], ana.f["scanStats"] = params, bare(vm, U + "scanstats/ScanStats")
+        sd = vm.new_object(vm.load(U + "reads/nanopore/NanoporeRead$ReadScanData"))
+        vm.call_virtual(sd, "setSeq", "(Ljava/lang/CharSequence;)V", stranded[::-1].translate(comp))
+        nr = bare(vm, U + "reads/nanopore/NanoporeRead")
+        nr.f["readScanData"] = J.JNative("com/google/common/base/Optional", (sd,))
+        r = bare(vm, U + "reads/nanopore/OneNanoporeResult")
+        r.f["nanoporeRead"] = nr
+        m = bare(vm, "com/rw/nanopore/analyzers/Match")
+        m.f["endposInTestedSeq"], m.f["endPosRead"] = J.JNative("java/util/Optional", (bc_end,)), J.JNative("java/util/Optional", (500,))
+        r.f["cellBCMatch"], r.f["umiMatch"], r.f["umiFindingFlagValue"] = J.JNative("java/util/Optional", (m,)), J.JNative("java/util/Optional", ()), 0
+        try:
+            found = vm.call_virtual(ana, "findUMI", "(L%sreads/nanopore/OneNanoporeResult;Lcom/rw/nuc/reads/Illumina/byGene/IlluminaOneGeneOneCellData;)Z" % U,
+                                    r, J.PySet(umis))
+        except J.JavaThrow as ex:
+            cases.append(dict(stranded=stranded, bc_end=bc_end, umis=sorted(umis), ed=ed, pm=pm, bail=-1 if bail is None else bail, exc=ex.cls, row=[0] * 16))
+            continue
+        ent = lambda o: [int(o.f["sequence"]) & M64, o.f["nSubstitutions"], o.f["nInsertions"], o.f["nDeletions"], o.f["startOffsetFromPredicted"]]
+        row = [int(found), r.f["umiFindingFlagValue"]]
+        um = r.f["umiMatch"].v[0] if r.f["umiMatch"].v else None
+        best = r.f.get("umi")
+        row += ent(best) if isinstance(best, J.JObj) else [0, 0, 0, 0, 0]
+        sec = um.f["secondBestMatch"] if um is not None else None
+        secnode = sec.f["alignment"].f.get("mutSeq") if sec is not None and isinstance(sec.f.get("alignment"), J.JObj) else None
+        row += [int(sec is not None)]
+        row += [um.f["startposRead"].v[0], um.f["endPosRead"].v[0]] if um is not None and um.f["startposRead"].v else [0, 0]
+        row += [um.f["nMismatchDiffBestvsSecondBest"] if um is not None and um.f["nMismatchDiffBestvsSecondBest"] is not None else -99]
+        row += [len(sec.f["alignment"].f["read"]) if secnode is None and sec is not None else 0]
+        sec_read = sec.f["alignment"].f["match"].replace("-", "") if sec is not None else ""
+        cases.append(dict(stranded=stranded, bc_end=bc_end, umis=sorted(umis), ed=ed, pm=pm, bail=-1 if bail is None else bail, exc="", row=row, second=sec_read))
+    return cases
+
+
 TAGS = dict(paStartPrefix="PS=", paEndPrefix="PE=", adapterPosPrefix="AE=", tsoPosPrefix="T=", seqPrefix="X=", qvPrefix="Q=", barcodeSeqPrefix="bc=",
             barcodeEdPrefix="ed=", barcodeEdSecondaryPrefix="ed_sec=", barcodeStartPrefix="bcStart=", barcodeEndPrefix="bcEnd=", barcodeRankPrefix="rk=")
 
@@ -485,6 +549,14 @@ def main():
     np.savez_compressed(os.path.join(OUT, "ref_read_names.npz"), name=np.array([r[0] for r in rn]), limit=np.array([r[1] for r in rn], dtype=np.int32),
                         parsed=np.array([r[2] for r in rn]))
     print("getScanDatFromReadName", len(rn), "names")
+
+    fu = find_umi_cases(vm, np.random.default_rng(606), 48)
+    keys, koff = flat(fu, "umis")
+    np.savez_compressed(os.path.join(OUT, "ref_find_umi.npz"), stranded=np.array([c["stranded"] for c in fu]), bc_end=np.array([c["bc_end"] for c in fu], dtype=np.int32),
+                        umis=keys, umi_offsets=koff, ed=np.array([c["ed"] for c in fu], dtype=np.int32), pm=np.array([c["pm"] for c in fu], dtype=np.int32),
+                        bail=np.array([c["bail"] for c in fu], dtype=np.int32), exc=np.array([c["exc"] for c in fu]),
+                        row=np.array([c["row"][:12] for c in fu], dtype=np.int64), second=np.array([c.get("second", "") for c in fu]))
+    print("findUMI", len(fu), "reads, found", sum(c["row"][0] for c in fu), "with second", sum(c["row"][7] for c in fu if not c["exc"]), "%.1fs" % (time.time() - t0))
 
     dj = dojob_cases(vm, rng, 45)
     keys, koff = flat(dj, "keys")

@@ -339,6 +339,25 @@ class VM:
             return f.v(*args)
         raise NotImplementedError("functional object %s" % f.name)
 
+    def j_string(self, v):
+        """String.valueOf(Object) as string concatenation applies it"""
+        if v is None:
+            return "null"
+        if isinstance(v, str):
+            return v
+        if isinstance(v, JObj):
+            c, m = self.find_method(v.cls, "toString()Ljava/lang/String;")
+            if m is not None:
+                return self.run(c, "toString()Ljava/lang/String;", [v])
+            return v.cls.name.replace("/", ".") + "@0"
+        if isinstance(v, float):
+            return repr(float(v))
+        if isinstance(v, JNative):
+            if v.name.endswith("Optional"):
+                return "Optional[%s]" % self.j_string(v.v[0]) if v.v else "Optional.empty"
+            return v.name.replace("/", ".") + "@0"
+        return str(int(v))
+
     def j_hash(self, a):
         if isinstance(a, JObj):
             c, m = self.find_method(a.cls, "hashCode()I")
@@ -379,7 +398,7 @@ class VM:
                 else:
                     o.native = hs
                 return None
-            if cls in ("java/util/ArrayDeque", "java/util/ArrayList"):
+            if cls in ("java/util/ArrayDeque", "java/util/ArrayList", "java/util/LinkedList"):
                 (o if isinstance(o, JNative) else o).__setattr__("v" if isinstance(o, JNative) else "native", [])
                 return None
             if cls in ("java/util/concurrent/ConcurrentHashMap", "java/util/HashMap", "java/util/TreeMap"):
@@ -414,6 +433,8 @@ class VM:
         store = None
         if a:
             store = a[0].v if isinstance(a[0], JNative) else (a[0].native if isinstance(a[0], JObj) else None)
+        if a and isinstance(a[0], JNative) and a[0].name == "logger":
+            return None                                    # log4j / java.util.logging calls are dropped
         if cls in ("java/lang/Long", "java/lang/Integer", "java/lang/Boolean", "java/lang/Byte", "java/lang/Short"):
             if name == "valueOf":
                 return a[0]
@@ -439,7 +460,14 @@ class VM:
                 return store.pop() if store else None
             if name == "isEmpty":
                 return int(not store)
-        if cls in ("java/util/List", "java/util/ArrayList", "java/util/Collection"):
+        if cls in ("java/util/List", "java/util/ArrayList", "java/util/Collection", "java/util/LinkedList"):
+            if name == "add" and len(a) == 3:
+                store.insert(a[1], a[2])
+                return None
+            if name == "toArray":
+                arr = JArr("L", 0, None)
+                arr.a = list(store)
+                return arr
             if name == "add":
                 store.append(a[1])
                 return 1
@@ -448,7 +476,15 @@ class VM:
             if name == "size":
                 return len(store)
             if name == "get":
+                if not 0 <= a[1] < len(store):
+                    raise JavaThrow("java/lang/IndexOutOfBoundsException")
                 return store[a[1]]
+            if name == "addAll":
+                src = a[1].v if isinstance(a[1], JNative) else a[1].native
+                store.extend(src)
+                return int(bool(src))
+            if name == "stream":
+                return JNative("java/util/stream/Stream", JStream(list(store)))
         if isinstance(store, JdkHashSet):
             if name == "add":
                 return store.add(a[1])
@@ -466,7 +502,7 @@ class VM:
                 return int(any(self.j_equals(a[1], e) for e in store.items()))
             if name == "stream":
                 return JNative("java/util/stream/Stream", JStream(store.items()))
-        if a and isinstance(a[0], JNative) and a[0].name in ("lambda", "pyfunc") and name in ("apply", "test", "accept", "applyAsInt", "get"):
+        if a and isinstance(a[0], JNative) and a[0].name in ("lambda", "pyfunc") and name in ("apply", "test", "accept", "applyAsInt", "get", "compare"):
             return self.call_functional(a[0], a[1:])
         if cls == "java/util/stream/IntStream" and name == "rangeClosed":
             return JNative("java/util/stream/Stream", JStream(list(range(a[0], a[1] + 1))))
@@ -479,13 +515,33 @@ class VM:
             if name == "sorted":
                 import functools
                 items = st_.run(self)
-                if len(a) > 1:                              # Comparator.comparingInt(key)
+                if len(a) > 1 and isinstance(a[1], JNative) and a[1].name == "comparator":        # Comparator.comparingInt(key)
                     items.sort(key=lambda x: self.call_functional(a[1].v, [x]))
+                elif len(a) > 1:                            # a Comparator: lambda or an object whose class is in the jars
+                    cmpf = (lambda x, y: self.call_functional(a[1], [x, y])) if isinstance(a[1], JNative) else \
+                           (lambda x, y: self.invoke_virtual(a[1].cls.name, "compare", "(Ljava/lang/Object;Ljava/lang/Object;)I", [a[1], x, y]))
+                    items.sort(key=functools.cmp_to_key(cmpf))
                 else:                                       # natural order: the element's own compareTo (stable, like the JDK's TimSort)
                     items.sort(key=functools.cmp_to_key(lambda x, y: self.j_compare(x, y)))
                 return JNative("java/util/stream/Stream", JStream(items))
             if name == "skip":
                 return JNative("java/util/stream/Stream", JStream(st_.run(self)[int(a[1]):]))
+            if name == "mapToInt":
+                return JNative("java/util/stream/Stream", JStream(st_.src, st_.ops + [("map", a[1])]))
+            if name == "limit":
+                return JNative("java/util/stream/Stream", JStream(st_.run(self, limit=int(a[1]))))
+            if name == "count":
+                return L(len(st_.run(self)))
+            if name == "sum":
+                return i32(sum(st_.run(self)))
+            if name == "distinct":                         # LinkedHashSet semantics: first occurrence wins, equals() decides
+                out_ = []
+                for x in st_.run(self):
+                    if not any(self.j_equals(x, y) for y in out_):
+                        out_.append(x)
+                return JNative("java/util/stream/Stream", JStream(out_))
+            if name == "collect":
+                return JNative("java/util/ArrayList", st_.run(self))
             if name == "forEach":
                 for x in st_.run(self):
                     self.call_functional(a[1], [x])
@@ -493,6 +549,14 @@ class VM:
             if name == "findFirst":
                 r = st_.run(self, limit=1)
                 return JNative("java/util/Optional", (r[0],) if r else ())
+        if cls.endswith("lang3/ArrayUtils") and name == "toPrimitive":
+            arr = JArr("B", 0, 0)
+            arr.a = list(a[0].a)
+            return arr
+        if cls == "java/lang/String" and name == "chars" and isinstance(a[0], str):
+            return JNative("java/util/stream/Stream", JStream([ord(ch) for ch in a[0]]))
+        if cls == "java/util/stream/Collectors" and name == "toList":
+            return JNative("collector:toList")
         if cls == "java/util/Comparator" and name == "comparingInt":
             return JNative("comparator", a[0])
         if cls in ("java/util/Map", "java/util/concurrent/ConcurrentHashMap", "java/util/HashMap") and isinstance(store, dict):
@@ -640,6 +704,8 @@ class VM:
                 return int(int(a[1]) in store)
         if isinstance(a[0] if a else None, PySet) and name in ("contains", "containsKey"):
             return int(int(a[1]) in a[0].s)
+        if isinstance(a[0] if a else None, PySet) and name == "size":
+            return len(a[0].s)
         if cls in ("java/lang/String", "java/lang/CharSequence"):
             s = a[0].v if isinstance(a[0], JNative) else a[0]
             if isinstance(s, str):
@@ -978,8 +1044,20 @@ class VM:
                 del st[len(st) - len(at):]
                 # string concatenation (assert / log messages) yields a placeholder; a lambda becomes an opaque object that nothing on the
                 # interpreted paths ever invokes (static initialisers store them in fields)
-                if mn == "makeConcatWithConstants":
-                    push("<concat>")
+                if mn == "makeConcatWithConstants":        # StringConcatFactory: recipe with \x01 per dynamic argument, \x02 per constant
+                    ref, bargs = c.bootstrap[e[1]]
+                    recipe = cf.utf(cp[bargs[0]][1])
+                    consts = [cp[b_] for b_ in bargs[1:]]
+                    out_, ai, ci = [], 0, 0
+                    for ch in recipe:
+                        if ch == "\x01":
+                            out_.append(self.j_string(indy_args[ai])); ai += 1
+                        elif ch == "\x02":
+                            k_ = consts[ci]; ci += 1
+                            out_.append(cf.utf(k_[1]) if k_[0] == "String" else str(k_[1]))
+                        else:
+                            out_.append(ch)
+                    push("".join(out_))
                 else:
                     # LambdaMetafactory: bootstrap argument 1 is the handle of the synthetic method that implements the lambda
                     ref, bargs = c.bootstrap[e[1]]

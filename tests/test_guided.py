@@ -150,6 +150,35 @@ def test_candidate_filter_is_conservative(sim, orc):
         assert far > 0 or bc, (L, ed, bc)      # BC flavour: the all-passed list (maxEDtoCheckBCAll10xBCs 3) is still probed at level 3
 
 
+def sweep_cases(n=36):
+    """seeded sweep over the whole parameter space the ABI accepts: sequence length 4..16, +-0..3, ED 0..3, bailout null / 0..3, post length,
+    both flavours, group sizes around the filter's 64-slot limit"""
+    rng = np.random.default_rng(2026)
+    for it in range(n):
+        L = int(rng.integers(4, 17))
+        ed = int(rng.integers(0, 4 if L <= 12 else 3))
+        pm = int(rng.integers(0, 4))
+        post_len = int(rng.integers(ed + 1, ed + 6))
+        while 2 * pm + L + post_len + 2 > 32:
+            pm -= 1
+        bc = bool(it % 3 == 0)
+        bailout = None if it % 4 == 0 else int(rng.integers(0, 4))
+        sizes = (0, 1, int(rng.integers(2, 9)), int(rng.integers(9, 31)), 33, int(rng.integers(34, 90)))
+        w = workloads.guided(5000 + it, L, 14 if ed >= 3 else 40, ed, pm, post_len, bc, skew=bool(it % 2), group_sizes=sizes,
+                             n_all=int(rng.integers(1, 40)), n_empty=int(rng.integers(1, 80)))
+        yield it, w, L, ed, pm, post_len, bailout, bc
+
+
+def test_sim_random_parameter_sweep(sim, orc):
+    hits = 0
+    for it, w, L, ed, pm, post_len, bailout, bc in sweep_cases():
+        exp, eraw, _ = oracle_run(orc, w, L, ed, pm, post_len, bailout, bc)
+        got, graw = sim_run(sim, orc, w, L, ed, pm, post_len, bailout, bc)
+        assert_same(got, graw, exp, eraw, "sweep %d: L %d ed %d pm %d post %d bail %s bc %s" % (it, L, ed, pm, post_len, bailout, bc))
+        hits += int((exp["n_raw"] > 0).sum())
+    assert hits > 300
+
+
 def test_sim_mixed_edit_distances(sim, orc):
     """dynamic ED: every read carries its own maxEDdyn; the stamped visited table is shared by windows of different table sizes"""
     w = workloads.guided(77, 12, 120, 2, 2, 6, False)
@@ -308,6 +337,14 @@ def test_gpu_ed4_full_length(pkg, ctx, orc, L, post_len, bc):
     exp, eraw, _ = oracle_run(orc, w, L, 4, 1, post_len, 2 if bc else None, bc)
     got, graw = gpu_run(pkg, ctx, w, L, 4, 1, post_len, 2 if bc else None, bc)
     assert_same(got, graw, exp, eraw, "GPU ED 4")
+
+
+@pytest.mark.gpu
+def test_gpu_random_parameter_sweep(pkg, ctx, orc):
+    for it, w, L, ed, pm, post_len, bailout, bc in sweep_cases():
+        exp, eraw, _ = oracle_run(orc, w, L, ed, pm, post_len, bailout, bc)
+        got, graw = gpu_run(pkg, ctx, w, L, ed, pm, post_len, bailout, bc)
+        assert_same(got, graw, exp, eraw, "GPU sweep %d: L %d ed %d pm %d post %d bail %s bc %s" % (it, L, ed, pm, post_len, bailout, bc))
 
 
 @pytest.mark.gpu

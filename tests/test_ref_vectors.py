@@ -240,3 +240,67 @@ def test_gpu_umi_distance_matches_reference_bytecode(pkg, ctx):
     m, oo = pkg.generate_distance_matrices(ctx, umis, offs, 12)
     got = m.reshape(n, 4)[:, 1]                                  # cell (0, 1) of every 2 x 2 matrix
     assert (got == z["packed"].astype(np.int32)).all(), np.nonzero(got != z["packed"].astype(np.int32))[0][:5]
+
+
+def _find_umi_inputs(z, i):
+    """the S4 boundary for read i: 32-byte stranded slice, anchor = window start of offset 0 (IlluminaUMIanalyzer.java:L102, L112-L124)"""
+    s, bc_end, ed, pm = str(z["stranded"][i]), int(z["bc_end"][i]), int(z["ed"][i]), int(z["pm"][i])
+    post_len = ed + pm + 2                                             # lengthPostUMIseq (L113)
+    need = bc_end + pm + 12 + post_len
+    if len(s) < need:
+        s = s + "A" * 9                                                # "too short -> added some As" (L118-L124): the caller pads
+    start = max(bc_end - pm - 1, 0)
+    piece = s[start:start + 32].encode()
+    sl = np.zeros((1, 32), dtype=np.uint8)
+    sl[0, :len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+    return sl, np.array([bc_end - start], dtype=np.int32), ed, pm, post_len, min(len(piece), 32)
+
+
+def _check_find_umi(z, i, r, pack):
+    row = z["row"][i]
+    found, flag, bseq, bsub, bins, bdel, boff, has_second = (int(x) for x in row[:8])
+    if str(z["exc"][i]):
+        assert r["flags"] & 1, (i, str(z["exc"][i]))
+        return "exc"
+    assert not r["flags"], (i, r)
+    assert (r["n_distinct"] > 0) == bool(found), (i, r, row)            # found <=> the list is not empty (java:L220)
+    if not found:
+        assert flag & 2 or flag != 0                                    # UMI_NOT_FOUND was set
+        return "none"
+    assert (int(r["seq"][0]), r["n_sub"][0], r["n_ins"][0], r["n_del"][0], r["offset"][0]) == (bseq, bsub, bins, bdel, boff), (i, r, row)
+    assert (r["n_distinct"] == 2) == bool(has_second), (i, r, row)
+    if has_second:
+        assert int(r["seq"][1]) == pack(str(z["second"][i])), (i, r, str(z["second"][i]))
+    # read positions the host derives from the record (findUMI L205-L206, 3' reads): start = bcEndPosRead - (1 + offset), end = start - (11 + nIns - nDel)
+    start = 500 - (1 + boff)
+    assert (int(row[8]), int(row[9])) == (start, start - (12 - 1 + bins - bdel)), (i, row)
+    return "second" if has_second else "one"
+
+
+def test_find_umi_matches_reference_bytecode(orc):
+    """IlluminaUMIanalyzer.findUMI as a whole, run by the reference's class files: offset loop and window / post geometry, the testers,
+    getBestAndSecondBCorUMI (sorted().distinct(), Needleman alignments): found / not found, the best entry (sequence, counters, offset), whether a
+    second-best exists and which sequence it is, and the read positions derived from the record"""
+    import workloads
+    z = np.load(os.path.join(GOLDEN, "ref_find_umi.npz"))
+    kinds = set()
+    for i in range(len(z["ed"])):
+        sl, anchor, ed, pm, post_len, slen = _find_umi_inputs(z, i)
+        umis = z["umis"][z["umi_offsets"][i]:z["umi_offsets"][i + 1]]
+        res, _, _ = orc.guided_batch(umis, np.array([0, len(umis)], dtype=np.int64), sl, anchor, np.array([0], dtype=np.int32), ed, 12, pm, post_len,
+                                     bailout=int(z["bail"][i]), slice_len=slen)
+        kinds.add(_check_find_umi(z, i, res[0], workloads.g_pack))
+    assert {"none", "one", "second"} <= kinds
+
+
+@pytest.mark.gpu
+def test_gpu_find_umi_matches_reference_bytecode(pkg, ctx):
+    import workloads
+    z = np.load(os.path.join(GOLDEN, "ref_find_umi.npz"))
+    for i in range(len(z["ed"])):
+        sl, anchor, ed, pm, post_len, slen = _find_umi_inputs(z, i)
+        umis = z["umis"][z["umi_offsets"][i]:z["umi_offsets"][i + 1]]
+        bail = int(z["bail"][i])
+        res, _ = pkg.GuidedSets(ctx, umis, np.array([0, len(umis)], dtype=np.int64), 12).match(sl, anchor, np.array([0], dtype=np.int32), ed, pm, post_len,
+                                                                                               bailout=None if bail < 0 else bail, slice_len=slen)
+        _check_find_umi(z, i, res[0], workloads.g_pack)
