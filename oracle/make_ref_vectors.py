@@ -516,6 +516,60 @@ def read_name_cases(vm, rng, n):
     return out
 
 
+def write_name_cases(vm, rng, n):
+    """FastqRecordExt.getRecordForWriting (the scanfastq side of the read-name format) on the reference's bytecode: the read name it builds
+    for a passed read from polyA / adapter / TSO / barcode results, the X= slice of the stranded read and the mean quality"""
+    F = PKG + "readerwriter/FastqRecordExt"
+    fl = vm.load(PKG + "stats/ReadFlags$Flags")
+    vm.init_class(fl)
+    flagv = lambda k: int(vm.call_virtual(fl.statics[k], "getValue", "()J"))
+    rsp = bare(vm, "com/rw/parameters/ReadScannerParameters")
+    for k, v in TAGS.items():
+        rsp.f[k] = v
+    rsp.f["nbasesOfAdapterSeqInReadname"] = 3
+    rsp.f["trimFastq"] = 0
+    out = []
+    for t in range(n):
+        rev, five = bool(t % 2), t % 5 == 4
+        stranded = rseq(rng, 160)
+        quals = "".join(chr(33 + int(q)) for q in rng.integers(3, 42, 160))
+        ae = int(rng.integers(45, 110)) if t % 9 else int(rng.integers(20, 44))          # small adapter ends: "Beginrange inconsistent" -> no X= / Q=
+        fq = bare(vm, F)
+        fq.f["strandedSequence"] = stranded
+        sr = vm.new_object(vm.load(PKG + "readerwriter/ReadScanResult"))
+        sr.f["flag"] = J.L(flagv("PASSED_REV" if rev else "PASSED_FWD"))
+        fq.f["scanResult"] = sr
+        kw = dict(adapter_end=ae)
+        vm.call_virtual(sr, "getAdapterresultCreateIfNull", "()L" + PKG + "readerwriter/ReadScanResult$Adapterresult;").f["end"] = ae
+        if t % 3:
+            pa = vm.call_virtual(sr, "getPolyAResultCreateIfNull", "()L" + PKG + "readerwriter/ReadScanResult$PolyAResult;")
+            kw["polya_start"], kw["polya_end"] = int(rng.integers(1, 40)), int(rng.integers(40, 44))
+            pa.f["start"], pa.f["end"] = kw["polya_start"], kw["polya_end"]
+        if t % 4 == 0:
+            kw["tso_end"] = int(rng.integers(1, 90))
+            vm.call_virtual(sr, "getTSOresultCreateIfNull", "()L" + PKG + "readerwriter/ReadScanResult$TSOresult;").f["end"] = kw["tso_end"]
+        if t % 6:
+            br = vm.call_virtual(sr, "getBarcodeResultCreateIfNull", "()L" + PKG + "readerwriter/ReadScanResult$BarcodeResult;")
+            kw.update(bc=rseq(rng, 16), ed=int(rng.integers(0, 3)), bc_start=int(rng.integers(1, 150)), bc_end=int(rng.integers(1, 150)))
+            vm.call_virtual(br, "setBarcodeseq", "(Ljava/lang/String;)V", kw["bc"])
+            br.f["editDistance"], br.f["start"], br.f["end"] = kw["ed"], kw["bc_start"], kw["bc_end"]
+            if t % 7:
+                kw["ed_second"] = int(rng.choice([1, 2, 2147483647]))
+                br.f["editDistanceSecondBest"] = kw["ed_second"]
+            if t % 5:
+                kw["rank"] = int(rng.integers(1, 5000))
+                vm.call_virtual(br, "setRank", "(I)V", kw["rank"])
+        rid = None if t % 3 == 0 else int(rng.integers(0, 10 ** 7))
+        # the superclass htsjdk.samtools.fastq.FastqRecord is outside the jars: its three getters are answered from here
+        vm.fastq_fields = {"getReadName": "read%d some description" % t, "getBaseQualityString": quals[::-1] if rev else quals, "getReadString": stranded,
+                           "getBaseQualityHeader": "", "toString": "FastqRecord"}
+        fq.f["reverseComplementQualities"] = J.JNative("pyfunc", lambda rec: quals)       # FastqRecordExt's own lambda reverses the qualities of a reversed read
+        rec = vm.call_virtual(fq, "getRecordForWriting", "(Lcom/rw/parameters/ReadScannerParameters;ZLjava/lang/Integer;)Lhtsjdk/samtools/fastq/FastqRecord;",
+                              rsp, int(five), rid)
+        out.append(dict(name=rec.v[0], stranded=stranded, quals=quals, rev=rev, five=five, rid=-1 if rid is None else rid, kw=repr(sorted(kw.items()))))
+    return out
+
+
 def flat(cases, key):
     off = np.cumsum([0] + [len(c[key]) for c in cases]).astype(np.int64)
     return np.array([k for c in cases for k in c[key]], dtype=np.uint64), off
@@ -557,6 +611,13 @@ def main():
                         bail=np.array([c["bail"] for c in fu], dtype=np.int32), exc=np.array([c["exc"] for c in fu]),
                         row=np.array([c["row"][:12] for c in fu], dtype=np.int64), second=np.array([c.get("second", "") for c in fu]))
     print("findUMI", len(fu), "reads, found", sum(c["row"][0] for c in fu), "with second", sum(c["row"][7] for c in fu if not c["exc"]), "%.1fs" % (time.time() - t0))
+
+    wn = write_name_cases(vm, np.random.default_rng(52), 60)
+    np.savez_compressed(os.path.join(OUT, "ref_written_names.npz"), name=np.array([c["name"] for c in wn]), stranded=np.array([c["stranded"] for c in wn]),
+                        quals=np.array([c["quals"] for c in wn]), rev=np.array([c["rev"] for c in wn], dtype=np.int32),
+                        five=np.array([c["five"] for c in wn], dtype=np.int32), read_id=np.array([c["rid"] for c in wn], dtype=np.int64),
+                        kw=np.array([c["kw"] for c in wn]))
+    print("getRecordForWriting", len(wn), "names")
 
     dj = dojob_cases(vm, rng, 45)
     keys, koff = flat(dj, "keys")

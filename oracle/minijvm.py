@@ -353,6 +353,8 @@ class VM:
         if isinstance(v, float):
             return repr(float(v))
         if isinstance(v, JNative):
+            if v.name == "java/lang/String":
+                return v.v
             if v.name.endswith("Optional"):
                 return "Optional[%s]" % self.j_string(v.v[0]) if v.v else "Optional.empty"
             return v.name.replace("/", ".") + "@0"
@@ -414,7 +416,7 @@ class VM:
                 o.v = "".join(chr(c) for c in a[1].a)
                 return None
             if cls == "java/lang/StringBuilder":
-                o.v = []
+                o.v = [a[1]] if len(a) > 1 and isinstance(a[1], str) else []
                 return None
             if cls in ("java/lang/AssertionError", "java/lang/IllegalArgumentException", "java/lang/Enum"):
                 if cls == "java/lang/Enum":
@@ -433,6 +435,8 @@ class VM:
         store = None
         if a:
             store = a[0].v if isinstance(a[0], JNative) else (a[0].native if isinstance(a[0], JObj) else None)
+        if cls == "htsjdk/samtools/fastq/FastqRecord" and name in getattr(self, "fastq_fields", {}):
+            return self.fastq_fields[name]                 # the superclass of FastqRecordExt is outside the jars: the driver supplies its getters
         if a and isinstance(a[0], JNative) and a[0].name == "logger":
             return None                                    # log4j / java.util.logging calls are dropped
         if cls in ("java/lang/Long", "java/lang/Integer", "java/lang/Boolean", "java/lang/Byte", "java/lang/Short"):
@@ -510,8 +514,8 @@ class VM:
             st_ = a[0].v
             if name == "boxed":
                 return a[0]
-            if name in ("filter", "map"):
-                return JNative("java/util/stream/Stream", JStream(st_.src, st_.ops + [(name, a[1])]))
+            if name in ("filter", "map") or (name == "mapToObj"):
+                return JNative("java/util/stream/Stream", JStream(st_.src, st_.ops + [("map" if name == "mapToObj" else name, a[1])]))
             if name == "sorted":
                 import functools
                 items = st_.run(self)
@@ -534,6 +538,9 @@ class VM:
                 return L(len(st_.run(self)))
             if name == "sum":
                 return i32(sum(st_.run(self)))
+            if name == "average":
+                v_ = st_.run(self)
+                return JNative("java/util/OptionalDouble", (D(sum(v_) / len(v_)),) if v_ else ())
             if name == "distinct":                         # LinkedHashSet semantics: first occurrence wins, equals() decides
                 out_ = []
                 for x in st_.run(self):
@@ -553,6 +560,20 @@ class VM:
             arr = JArr("B", 0, 0)
             arr.a = list(a[0].a)
             return arr
+        if cls == "java/util/OptionalDouble" and name == "getAsDouble":
+            if not a[0].v:
+                raise JavaThrow("java/util/NoSuchElementException")
+            return a[0].v[0]
+        if cls == "java/text/DecimalFormat" and name == "format":
+            # DecimalFormat(pattern).format(Number): only the two patterns of the path ("##.#": at most one fraction digit; "###,###,###,###":
+            # grouping), RoundingMode.HALF_EVEN on the exact binary value (JDK >= 8)
+            from decimal import Decimal, ROUND_HALF_EVEN
+            pat, v_ = a[0].v[0], a[1]
+            if "," in pat:
+                return format(int(v_), ",")
+            d_ = Decimal(float(v_)).quantize(Decimal("0.1"), rounding=ROUND_HALF_EVEN)
+            t_ = format(d_, "f")
+            return t_[:-2] if t_.endswith(".0") else t_
         if cls == "java/lang/String" and name == "chars" and isinstance(a[0], str):
             return JNative("java/util/stream/Stream", JStream([ord(ch) for ch in a[0]]))
         if cls == "java/util/stream/Collectors" and name == "toList":
@@ -721,7 +742,7 @@ class VM:
                     return arr
         if cls == "java/lang/StringBuilder":
             if name == "append":
-                store.append(chr(a[1]) if desc.startswith("(C)") else str(a[1]))
+                store.append(chr(a[1]) if desc.startswith("(C)") else self.j_string(a[1]))
                 return a[0]
             if name == "toString":
                 return "".join(store)
@@ -905,6 +926,12 @@ class VM:
                 loc[bc[pc + 1]] = i32(loc[bc[pc + 1]] + (bc[pc + 2] - (256 if bc[pc + 2] & 0x80 else 0))); pc += 3
             elif op == 0x85:
                 push(L(pop())); pc += 1
+            elif op == 0x90:                                # d2f
+                push(np_float32(pop())); pc += 1
+            elif op == 0x8d:                                # f2d
+                push(D(pop())); pc += 1
+            elif op == 0x86 or op == 0x87:                  # i2f i2d
+                v = pop(); push(np_float32(v) if op == 0x86 else D(v)); pc += 1
             elif op == 0x88:
                 push(i32(pop())); pc += 1
             elif op == 0x91:

@@ -86,21 +86,25 @@ def read_name_extension(reversed_read, stranded_seq, stranded_quals, adapter_end
         add += "%s%d_%s%d_" % (tags.barcodeStartPrefix, bc_start, tags.barcodeEndPrefix, bc_end)
         if rank is not None:
             add += "%s%d_" % (tags.barcodeRankPrefix, rank)
-    if adapter_end is not None:                                                  # L247-L271
-        if is5p:
-            begin = adapter_end - tags.nbasesOfAdapterSeqInReadname               # L250-L251
-            end = adapter_end + tags.N_BASES_AFTER_ADAPTER_FOR_SEQ - 1
-        else:
-            begin = adapter_end - tags.N_BASES_AFTER_ADAPTER_FOR_SEQ - 1           # L253-L254
-            end = adapter_end + tags.nbasesOfAdapterSeqInReadname - 1
-        if begin >= 0:                                                           # L257-L259: else logged, nothing appended
-            if end > len(stranded_seq):
-                raise IndexError("StringIndexOutOfBoundsException: substring(%d, %d)" % (begin, end))
-            add += "%s%s_" % (tags.seqPrefix, stranded_seq[begin:end])           # L261-L264
-            add += "%s%s" % (tags.qvPrefix, _dec_format_1(mean_qv(stranded_quals, begin, end)))     # L270
-            add += "_"                                                           # L271
-            if read_id is not None:
-                add += convert_int(read_id)                                      # L272-L273
+    # L247-L259: the extension is appended to the read name at L298 only on the path through the X= / Q= block — a read without adapter, or
+    # whose adapter end is too close to the read start for the X= slice ("Beginrange inconsistent"), keeps its bare name
+    if adapter_end is None:
+        return ""
+    if is5p:
+        begin = adapter_end - tags.nbasesOfAdapterSeqInReadname                   # L250-L251
+        end = adapter_end + tags.N_BASES_AFTER_ADAPTER_FOR_SEQ - 1
+    else:
+        begin = adapter_end - tags.N_BASES_AFTER_ADAPTER_FOR_SEQ - 1               # L253-L254
+        end = adapter_end + tags.nbasesOfAdapterSeqInReadname - 1
+    if begin < 0:
+        return ""
+    if end > len(stranded_seq):
+        raise IndexError("StringIndexOutOfBoundsException: substring(%d, %d)" % (begin, end))
+    add += "%s%s_" % (tags.seqPrefix, stranded_seq[begin:end])                   # L261-L264
+    add += "%s%s" % (tags.qvPrefix, _dec_format_1(mean_qv(stranded_quals, begin, end)))     # L270
+    add += "_"                                                                   # L271
+    if read_id is not None:
+        add += convert_int(read_id)                                              # L272-L273
     if bc is not None:
         add += " cellBC=" + (bc if isinstance(bc, str) else unpack2bit(bc, bc_len))                # L276-L277
     return add

@@ -135,3 +135,24 @@ def test_parser_matches_reference_bytecode():
         assert want == exp, (name, want, exp)
         outcomes.add("ok" if "bc" in got else "ok_nobc")
     assert outcomes == {"adapter", "nfe", "absent", "ok", "ok_nobc"}
+
+
+def test_writer_matches_reference_bytecode():
+    """FastqRecordExt.getRecordForWriting run by the reference's own class files (tests/golden/ref_written_names.npz): the whole read name for
+    forward / reversed, 3' / 5' reads with and without polyA, TSO, barcode, second-best ED, rank, read id, and the adapter end too close to the
+    read start for an X= slice"""
+    F = fmt()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_written_names.npz"))
+    shapes = set()
+    for name, stranded, quals, rev, five, rid, kw in zip(z["name"], z["stranded"], z["quals"], z["rev"], z["five"], z["read_id"], z["kw"]):
+        kw = dict(eval(str(kw)))
+        ext = F.read_name_extension(bool(rev), str(stranded), str(quals), is5p=bool(five), read_id=None if rid < 0 else int(rid), **kw)
+        name = str(name)
+        assert name == name.split("_")[0] + ext, (name, ext)
+        shapes.add(("X=" in ext, "bc=" in ext, "T=" in ext, "PS=" in ext, rid >= 0))
+        if ext == "":
+            assert name == name.split("_")[0] and kw["adapter_end"] < 42          # "Beginrange inconsistent": the name stays bare
+        if " cellBC=" in name:                           # the parser reads its own output back
+            p = F.parse_read_name(name.split(" ")[0])
+            assert p["bc"] == kw["bc"] and p["adapter_end"] == kw["adapter_end"] and p.get("read_id", 0) == max(int(rid), 0)
+    assert len(shapes) >= 5
