@@ -570,6 +570,41 @@ def write_name_cases(vm, rng, n):
     return out
 
 
+def getmaxed_cases(vm):
+    """DynamicEditDistances.getmaxED on the reference's bytecode, fed with the reference's own tables (Jar/bcMaxEditDistances.xml,
+    Jar/umiMaxEditDistances.xml, parsed here instead of through JAXB)"""
+    import xml.etree.ElementTree as ET
+    DED = "com/rw/parameters/DynamicEditDistances"
+    rows = []
+    for fn in ("bcMaxEditDistances.xml", "umiMaxEditDistances.xml"):
+        tables = {}
+        for lc in ET.parse(REF + "/" + fn).getroot().iter("dataForUMIlength"):
+            L = int(lc.find("umiBCLength").text)
+            for ec in lc.iter("dataForErr"):
+                tables[(L, int(ec.find("errorpercent").text))] = {int(d.find("editDistance").text): int(d.find("maxBarcodes").text) for d in ec.iter("dataForED")}
+        d = bare(vm, DED)
+        entries = {}
+        for (L, err), col in tables.items():
+            le = entries.get(L)
+            if le is None:
+                le = entries[L] = bare(vm, DED + "$OneUMIBClengthEntry")
+                le.native = {}
+            ee = bare(vm, DED + "$OneErrPctEntry")
+            ee.native = {k: J.L(v) for k, v in col.items()}
+            le.native[err] = ee
+        d.f["entries"] = J.JNative("java/util/HashMap", entries)
+        for (L, err), col in sorted(tables.items()):
+            for count in (1, 2, 3, 7, 20, 21, 100, 570, 2849, 2850, 26362, 100000, 600001):
+                for pm in (0, 1, 2):
+                    for cap in (None, 0, 2, 3):
+                        try:
+                            r = vm.call_virtual(d, "getmaxED", "(IIIILjava/lang/Integer;)I", count, pm, err, L, cap)
+                        except J.JavaThrow:
+                            r = -1
+                        rows.append([L, err, count, pm, -1 if cap is None else cap, r] + [col.get(e, -1) for e in range(6)])
+    return np.array(rows, dtype=np.int64)
+
+
 def flat(cases, key):
     off = np.cumsum([0] + [len(c[key]) for c in cases]).astype(np.int64)
     return np.array([k for c in cases for k in c[key]], dtype=np.uint64), off
@@ -618,6 +653,10 @@ def main():
                         five=np.array([c["five"] for c in wn], dtype=np.int32), read_id=np.array([c["rid"] for c in wn], dtype=np.int64),
                         kw=np.array([c["kw"] for c in wn]))
     print("getRecordForWriting", len(wn), "names")
+
+    gm = getmaxed_cases(vm)
+    np.savez_compressed(os.path.join(OUT, "ref_getmaxed.npz"), rows=gm)
+    print("getmaxED", gm.shape, "result histogram", np.bincount(gm[:, 5] + 1))
 
     dj = dojob_cases(vm, rng, 45)
     keys, koff = flat(dj, "keys")

@@ -556,6 +556,15 @@ class VM:
             if name == "findFirst":
                 r = st_.run(self, limit=1)
                 return JNative("java/util/Optional", (r[0],) if r else ())
+            if name == "max":                               # Stream.max(comparator): the LAST of equal maxima wins (reduce with a >= b ? a : b ... keeps b on ties)
+                items = st_.run(self)
+                if not items:
+                    return JNative("java/util/Optional", ())
+                best = items[0]
+                for x in items[1:]:
+                    if self.call_functional(a[1].v, [x]) >= self.call_functional(a[1].v, [best]):
+                        best = x
+                return JNative("java/util/Optional", (best,))
         if cls.endswith("lang3/ArrayUtils") and name == "toPrimitive":
             arr = JArr("B", 0, 0)
             arr.a = list(a[0].a)
@@ -580,7 +589,13 @@ class VM:
             return JNative("collector:toList")
         if cls == "java/util/Comparator" and name == "comparingInt":
             return JNative("comparator", a[0])
-        if cls in ("java/util/Map", "java/util/concurrent/ConcurrentHashMap", "java/util/HashMap") and isinstance(store, dict):
+        if name == "entrySet" and isinstance(store, dict):      # TreeMap: ascending keys (the only ordered map on the path)
+            return JNative("java/util/ArrayList", [JNative("entry", (k_, store[k_])) for k_ in sorted(store)])
+        if a and isinstance(a[0], JNative) and a[0].name == "entry" and name in ("getKey", "getValue"):
+            return a[0].v[0 if name == "getKey" else 1]
+        if cls == "java/util/Map$Entry" and name == "comparingByKey":
+            return JNative("comparator", lambda e_: e_.v[0])
+        if cls in ("java/util/Map", "java/util/concurrent/ConcurrentHashMap", "java/util/HashMap", "java/util/TreeMap") and isinstance(store, dict):
             k = a[1]
             if name == "get":
                 return store.get(k)
@@ -789,11 +804,7 @@ class VM:
             a[0].f[part] = a[1]
             return None
         if name == "stream" and isinstance(a[0], JNative) and isinstance(a[0].v, list):
-            return JNative("java/util/stream/Stream", list(a[0].v))
-        if cls == "java/util/stream/Stream" and name == "forEach":
-            for x in a[0].v:
-                self.call_lambda(a[1], [x])
-            return None
+            return JNative("java/util/stream/Stream", JStream(list(a[0].v)))
         if cls == "java/util/EnumSet":
             if name in ("of", "allOf", "noneOf"):
                 return JNative("java/util/EnumSet", sorted([x for x in a if isinstance(x, JObj)], key=lambda e: e.f["$ordinal"]))

@@ -304,3 +304,18 @@ def test_gpu_find_umi_matches_reference_bytecode(pkg, ctx):
         res, _ = pkg.GuidedSets(ctx, umis, np.array([0, len(umis)], dtype=np.int64), 12).match(sl, anchor, np.array([0], dtype=np.int32), ed, pm, post_len,
                                                                                                bailout=None if bail < 0 else bail, slice_len=slen)
         _check_find_umi(z, i, res[0], workloads.g_pack)
+
+
+def test_getmaxed_matches_reference_bytecode(pkg):
+    """DynamicEditDistances.getmaxED run by the reference's class files on its own tables (bcMaxEditDistances.xml, umiMaxEditDistances.xml): every
+    (length, error %) column x candidate counts x posplusminus x cap, incl. the NoSuchElementException cases — against slr_dyn_max_ed"""
+    z = np.load(os.path.join(GOLDEN, "ref_getmaxed.npz"))["rows"]
+    lib = pkg.gpu_lib()
+    seen = set()
+    for row in z:
+        L, err, count, pm, cap, exp = (int(x) for x in row[:6])
+        col = np.array([x for x in row[6:] if x >= 0], dtype=np.int64)
+        got = lib.slr_dyn_max_ed(col.ctypes.data, len(col), count, pm, cap)
+        assert got == exp, (row, got)
+        seen.add(exp)
+    assert seen == {-1, 0, 1, 2, 3, 4} and len(z) > 6000
