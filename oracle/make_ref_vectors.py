@@ -570,6 +570,56 @@ def write_name_cases(vm, rng, n):
     return out
 
 
+def exact_lookup_cases(vm, rng, n):
+    """pass 1, UsedCellBCListGenerator$Worker.lambda$call$1 (UsedCellBCListGenerator.java:L206-L232) on the reference's bytecode: the window at
+    the predicted position (3' reverse-complemented), the whitelist test, the per-barcode read counts"""
+    G = PKG + "analyzers/UsedCellBCListGenerator"
+    st = vm.load("com/rw/parameters/ParametersMainBase$SCANTYPE")
+    vm.init_class(st)
+    comp = str.maketrans("ACGT", "TGCA")
+    out = []
+    for tp in (True, False):
+        params, bp = bare(vm, PKG + "parameters/ParametersReadScannerApp"), bare(vm, "com/rw/parameters/BarcodeParameters")
+        bp.f["cell_bc_length"] = 16
+        params.f["barcodes"], params.f["scantype"] = bp, st.statics["THREEP_BARCODE" if tp else [k for k in st.statics if k.startswith("FIVEP")][0]]
+        gen, dbg, used = bare(vm, G), bare(vm, G + "$DebugInfo"), bare(vm, G + "$UsedBarcodesListData")
+        for k in list(dbg.f):
+            dbg.f[k] = J.JNative("java/util/concurrent/atomic/AtomicInteger", [0])
+        used.f["unfilteredUsedBarcodeMap"] = J.JNative("it/unimi/dsi/fastutil/longs/Long2ObjectMap", {})
+        used.f["recordCount"] = J.JNative("java/util/concurrent/atomic/AtomicInteger", [0])
+        gen.f["params"], gen.f["debugInfo"], gen.f["barcodesUsedData"] = params, dbg, used
+        wk = bare(vm, G + "$Worker")
+        wk.f["this$0"] = gen
+        whitelist = {pack(rseq(rng, 16)) for _ in range(60)}
+        pred = J.JNative("pyfunc", lambda k: int(int(k) in whitelist))
+        reads = []
+        for t in range(n):
+            read = rseq(rng, 70)
+            ap = int(rng.integers(20, 50)) if t % 10 else int(rng.integers(5, 17))
+            if t % 3:                                                                    # plant a whitelist barcode at the predicted position
+                b = unpack(sorted(whitelist)[int(rng.integers(len(whitelist)))], 16)
+                if tp and ap - 17 >= 0:
+                    read = read[:ap - 17] + b[::-1].translate(comp) + read[ap - 1:]
+                elif not tp:
+                    read = (read[:ap] + b + read[ap + 16:])[:70]
+            if t % 11 == 0:
+                read = read[:ap - 5] + "N" + read[ap - 4:]
+            fq = bare(vm, PKG + "readerwriter/FastqRecordExt")
+            fq.f["strandedSequence"] = read
+            sr = vm.new_object(vm.load(PKG + "readerwriter/ReadScanResult"))
+            fq.f["scanResult"] = sr
+            vm.call_virtual(sr, "getAdapterresultCreateIfNull", "()L" + PKG + "readerwriter/ReadScanResult$Adapterresult;").f["end"] = ap
+            try:
+                r = vm.invoke_exact(G + "$Worker", "lambda$call$1", "(L" + PKG + "readerwriter/FastqRecordExt;Ljava/util/function/Predicate;)Ljava/lang/Boolean;",
+                                    [wk, fq, pred])
+            except J.JavaThrow as ex:
+                r = -1
+            reads.append((read, ap, int(r)))
+        counts = {k: v.v[0] for k, v in used.f["unfilteredUsedBarcodeMap"].v.items()}
+        out.append(dict(tp=tp, whitelist=sorted(whitelist), reads=reads, counts=counts))
+    return out
+
+
 def getmaxed_cases(vm):
     """DynamicEditDistances.getmaxED on the reference's bytecode, fed with the reference's own tables (Jar/bcMaxEditDistances.xml,
     Jar/umiMaxEditDistances.xml, parsed here instead of through JAXB)"""
@@ -653,6 +703,15 @@ def main():
                         five=np.array([c["five"] for c in wn], dtype=np.int32), read_id=np.array([c["rid"] for c in wn], dtype=np.int64),
                         kw=np.array([c["kw"] for c in wn]))
     print("getRecordForWriting", len(wn), "names")
+
+    ex = exact_lookup_cases(vm, np.random.default_rng(8), 80)
+    np.savez_compressed(os.path.join(OUT, "ref_exact_lookup.npz"), three_prime=np.array([c["tp"] for c in ex], dtype=np.int32),
+                        whitelist=np.array([c["whitelist"] for c in ex], dtype=np.uint64), read=np.array([[r[0] for r in c["reads"]] for c in ex]),
+                        adapterpos=np.array([[r[1] for r in c["reads"]] for c in ex], dtype=np.int32),
+                        found=np.array([[r[2] for r in c["reads"]] for c in ex], dtype=np.int32),
+                        count_keys=np.array([sorted(c["counts"]) + [0] * (80 - len(c["counts"])) for c in ex], dtype=np.uint64),
+                        count_vals=np.array([[c["counts"][k] for k in sorted(c["counts"])] + [0] * (80 - len(c["counts"])) for c in ex], dtype=np.int64))
+    print("pass-1 exact lookup", [(sum(r[2] == 1 for r in c["reads"]), sum(r[2] == -1 for r in c["reads"])) for c in ex], "(found, throwing) per geometry")
 
     gm = getmaxed_cases(vm)
     np.savez_compressed(os.path.join(OUT, "ref_getmaxed.npz"), rows=gm)

@@ -611,11 +611,23 @@ class VM:
             if name == "containsKey":
                 return int(k in store)
         if cls == "java/util/concurrent/atomic/AtomicInteger":
+            if name == "addAndGet":
+                store[0] += a[1]
+                return store[0]
             if name in ("incrementAndGet", "getAndIncrement"):
                 store[0] += 1
                 return store[0] if name == "incrementAndGet" else store[0] - 1
             if name == "get":
                 return store[0]
+        if cls.endswith("fastutil/longs/Long2ObjectMap") and isinstance(store, dict):
+            if name == "containsKey":
+                return int(int(a[1]) in store)
+            if name == "get":
+                return store.get(int(a[1]))
+            if name == "put":
+                old_ = store.get(int(a[1]))
+                store[int(a[1])] = a[2]
+                return old_
         if cls.endswith("Long2ObjectOpenHashMap") or cls.endswith("BarcodesMapForBCfinding"):
             if name == "keySet":
                 return PySet(a[0].native.keys())

@@ -12,7 +12,7 @@
  * BarcodeMatchTester.doJob, the Illumina-guided testers and IlluminaUMIanalyzer.findUMI as a whole, calcEditDistances (UMI window slicing
  * included) and Parser.assignBarcode.  JDK / third-party containers are shims there
  * (java.util.HashSet iteration order = the JDK HashMap algorithm as modelled, not executed).  Restated only: IlluminaBarcodeAnalyzer.testBarcodes'
- * offset loop and reduction, the pass-1 exact lookup.  Also: the two read-name examples of
+ * offset loop and reduction.  Also: the two read-name examples of
  * /root/reference/README.md:400,452, an independent second restatement (oracle/pyref.py) and brute-force property checks (tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may link

@@ -319,3 +319,48 @@ def test_getmaxed_matches_reference_bytecode(pkg):
         assert got == exp, (row, got)
         seen.add(exp)
     assert seen == {-1, 0, 1, 2, 3, 4} and len(z) > 6000
+
+
+def _exact_inputs(z, g):
+    """32-byte slices of the reads around the predicted window (the S1 / pass-1 boundary), anchor relative to the slice"""
+    tp = bool(z["three_prime"][g])
+    reads = [str(r) for r in z["read"][g]]
+    ap = z["adapterpos"][g].astype(np.int64)
+    anchor = (ap - 16) - 1 if tp else ap                             # UsedCellBCListGenerator.java:L211-L215
+    sl = np.zeros((len(reads), 32), dtype=np.uint8)
+    rel, lens = np.zeros(len(reads), dtype=np.int32), np.zeros(len(reads), dtype=np.int32)
+    for i, r in enumerate(reads):
+        start = min(max(int(anchor[i]) - 8, 0), max(len(r) - 32, 0))
+        piece = r[start:start + 32].encode()
+        sl[i, :len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+        rel[i], lens[i] = int(anchor[i]) - start, len(piece)
+    exp = {int(k): int(v) for k, v in zip(z["count_keys"][g], z["count_vals"][g]) if v > 0}
+    return tp, sl, rel, lens, exp, int((z["found"][g] == -1).sum())
+
+
+def test_exact_lookup_matches_reference_bytecode(orc):
+    """pass 1: UsedCellBCListGenerator$Worker's per-read lambda run by the reference's class files (window at the predicted position, whitelist
+    test, unfilteredUsedBarcodeMap counts, reads whose window leaves the read) against the oracle's exact lookup"""
+    z = np.load(os.path.join(GOLDEN, "ref_exact_lookup.npz"))
+    for g in range(len(z["three_prime"])):
+        tp, sl, anchor, lens, exp, n_throw = _exact_inputs(z, g)
+        wl = z["whitelist"][g]
+        res = orc.exact_lookup_batch(orc.BarcodeSet(wl, np.arange(1, len(wl) + 1, dtype=np.int32)), sl, anchor, tp, lens=lens)
+        got = {}
+        for r in res[(res["flags"] & 1) != 0]:
+            got[int(r["bc"])] = got.get(int(r["bc"]), 0) + 1
+        assert got == exp and len(exp) > 20
+        assert int(((res["flags"] & 2) != 0).sum()) == n_throw
+
+
+@pytest.mark.gpu
+def test_gpu_exact_lookup_matches_reference_bytecode(pkg, ctx):
+    z = np.load(os.path.join(GOLDEN, "ref_exact_lookup.npz"))
+    for g in range(len(z["three_prime"])):
+        tp, sl, anchor, lens, exp, n_throw = _exact_inputs(z, g)
+        wl = z["whitelist"][g]
+        table = pkg.BarcodesMapForBCfinding(ctx, wl, np.arange(1, len(wl) + 1, dtype=np.int32))
+        res = pkg.UsedCellBCListGenerator(ctx, table, three_prime=tp).addFastqs(sl, anchor, lens=lens)
+        counts = table.counts()[:, 0]                                # unfilteredUsedBarcodeMap = the ED-0 counters of the table
+        assert {int(k): int(c) for k, c in zip(wl, counts) if c} == exp
+        assert int(((res["flags"] & 2) != 0).sum()) == n_throw
