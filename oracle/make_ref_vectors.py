@@ -441,6 +441,73 @@ def find_umi_cases(vm, rng, n):
     return cases
 
 
+def test_barcodes_cases(vm, rng, n):
+    """IlluminaBarcodeAnalyzer.testBarcodes (one gene) + getBestAndSecondBCorUMI(CELLBC) on the reference's bytecode: the BC-flavour offset loop
+    (window = 16 bases after the nbasesOfAdapterSeqInReadname adapter bases of the X= mini-sequence, 10 post bases), BCnucTwoBitPerBaseEDtester with
+    the gene / all-passed / empty-drop lists and the bailout, then the sort with scoreWhereFound + distinct and the Needleman alignments"""
+    U = "com/rw/umifinder/"
+    IBA = U + "analyzers/IlluminaBarcodeAnalyzer"
+    comp = str.maketrans("ACGTN", "TGCAN")
+    st = vm.load("com/rw/parameters/ParametersMainBase$SCANTYPE")
+    vm.init_class(st)
+    sw = vm.load("com/rw/nanopore/analyzers/AnalyzerBase$ScanningWhat")
+    vm.init_class(sw)
+    cases = []
+    for t in range(n):
+        ed, pm = [1, 2][t % 2], [1, 2, 2][t % 3]
+        bail = [None, 1, 2][t % 3]
+        bc = rseq(rng, 16, "AAAGCT" if t % 5 == 0 else "AGCT")
+        gene = {pack(rseq(rng, 16)) for _ in range(int(rng.integers(0, 12)))}
+        if t % 4:
+            gene.add(pack(bc))
+        allk = set(gene) | {pack(rseq(rng, 16)) for _ in range(10)} | {pack((mutate(rng, bc, int(rng.integers(0, 3))) + rseq(rng, 3))[:16]) for _ in range(3)}
+        empk = {pack(rseq(rng, 16)) for _ in range(10)} | {pack((mutate(rng, bc, int(rng.integers(1, 3))) + rseq(rng, 3))[:16]) for _ in range(2)}
+        obs = mutate(rng, bc, int(rng.integers(0, ed + 2)))
+        lead = 3 + (int(rng.integers(-pm, pm + 1)) if t % 2 else 0)
+        stranded = rseq(rng, max(lead, 0)) + obs + rseq(rng, 30)
+        params = bare(vm, U + "parameters/ParametersBarcodeUMiFinderAppParams")
+        bp, rsp = bare(vm, "com/rw/parameters/BarcodeParameters"), bare(vm, "com/rw/parameters/ReadScannerParameters")
+        bp.f.update(bc_posplusminus=pm, simulateRandomBCs=0, cell_bc_length=16, cell_BC_bailout_after_ED=bail, maxEDtoCheckBCAll10xBCs=3,
+                    maxEDtoCheckBCEmptyDrops=2, checkAllassignedBarcodes=1, checkEmptyDrops=1)
+        rsp.f["nbasesOfAdapterSeqInReadname"] = 3
+        params.f["barcodes"], params.f["readScannerParameters"], params.f["scantype"] = bp, rsp, st.statics["THREEP_BARCODE"]
+        ill = J.JNative("ParsedIlluminaData")
+        ill.f["all10xselectedCells"] = J.PySet(allk)
+        params.f["illuminaData"] = J.JNative("com/google/common/base/Optional", (ill,))
+        scores = vm.construct("com/rw/nuc/alignment/needleman/NeedlemanScores", "()V")
+        sd = vm.new_object(vm.load(U + "reads/nanopore/NanoporeRead$ReadScanData"))
+        vm.call_virtual(sd, "setSeq", "(Ljava/lang/CharSequence;)V", stranded[::-1].translate(comp))
+        nr = bare(vm, U + "reads/nanopore/NanoporeRead")
+        nr.f["readScanData"] = J.JNative("com/google/common/base/Optional", (sd,))
+        r = bare(vm, U + "reads/nanopore/OneNanoporeResult")
+        r.f["nanoporeRead"], r.f["bcFindingFlagValue"] = nr, 0
+        ana = bare(vm, IBA)
+        ana.f["parameters"], ana.f["scanStats"], ana.f["oneNanoporeResult"] = params, bare(vm, U + "scanstats/ScanStats"), r
+        ogd = vm.construct(IBA + "$OneGeneOrRegionData", "(Lcom/rw/nuc/reads/Illumina/BarcodesMap;Ljava/lang/String;Z)V", J.PySet(gene, J.PySet(empk)), "GENE1", 0)
+        ogd.f["maxEDdyn"] = ed
+        row = dict(stranded=stranded, gene=sorted(gene), allk=sorted(allk), empk=sorted(empk), ed=ed, pm=pm, bail=-1 if bail is None else bail, exc="")
+        try:
+            e = vm.invoke_exact(IBA, "testBarcodes", "(Ljava/util/List;)Ljava/util/Map$Entry;", [ana, J.JNative("java/util/ArrayList", [ogd])])
+            ent = lambda o: [int(o.f["sequence"]) & M64, o.f["nSubstitutions"], o.f["nInsertions"], o.f["nDeletions"], o.f["startOffsetFromPredicted"], o.f["findingErrorFlag"]]
+            if e is None:
+                row.update(n_raw=0, best=[0] * 6, second=[0] * 6, n_distinct=0, min_err_gene=2147483647)
+            else:
+                lst = e.v[1].v
+                ge = [o.f["nSubstitutions"] + o.f["nInsertions"] + o.f["nDeletions"] for o in lst if o.f["findingErrorFlag"] & 512]
+                m = bare(vm, "com/rw/nanopore/analyzers/Match")
+                best = vm.invoke_exact(U + "analyzers/IlluminaBarcodeUMIAnalyzerBase", "getBestAndSecondBCorUMI",
+                                       "(L%sreads/nanopore/OneNanoporeResult;Ljava/util/List;Ljava/util/Optional;Lcom/rw/nanopore/analyzers/AnalyzerBase$ScanningWhat;"
+                                       "Lcom/rw/nuc/alignment/needleman/NeedlemanScores;)Lcom/rw/nuc/encoding/TwoBit/NucTwoBitPerBaseWithErrors;" % U,
+                                       [r, e.v[1], J.JNative("java/util/Optional", (m,)), sw.statics["CELLBC"], scores])
+                sec = m.f["secondBestMatch"]
+                sec_seq = pack(sec.f["alignment"].f["match"].replace("-", "")) if sec is not None else 0
+                row.update(n_raw=len(lst), best=ent(best), second=[sec_seq, 0, 0, 0, 0, 0], n_distinct=2 if sec is not None else 1, min_err_gene=min(ge) if ge else 2147483647)
+        except J.JavaThrow as ex:
+            row.update(exc=ex.cls, n_raw=0, best=[0] * 6, second=[0] * 6, n_distinct=0, min_err_gene=2147483647)
+        cases.append(row)
+    return cases
+
+
 TAGS = dict(paStartPrefix="PS=", paEndPrefix="PE=", adapterPosPrefix="AE=", tsoPosPrefix="T=", seqPrefix="X=", qvPrefix="Q=", barcodeSeqPrefix="bc=",
             barcodeEdPrefix="ed=", barcodeEdSecondaryPrefix="ed_sec=", barcodeStartPrefix="bcStart=", barcodeEndPrefix="bcEnd=", barcodeRankPrefix="rk=")
 
@@ -655,6 +722,17 @@ def getmaxed_cases(vm):
     return np.array(rows, dtype=np.int64)
 
 
+def save_test_barcodes(tb):
+    gk, go = flat(tb, "gene")
+    ak, ao = flat(tb, "allk")
+    ek, eo = flat(tb, "empk")
+    np.savez_compressed(os.path.join(OUT, "ref_test_barcodes.npz"), stranded=np.array([c["stranded"] for c in tb]), gene=gk, gene_offsets=go, all_keys=ak, all_offsets=ao,
+                        empty_keys=ek, empty_offsets=eo, ed=np.array([c["ed"] for c in tb], dtype=np.int32), pm=np.array([c["pm"] for c in tb], dtype=np.int32),
+                        bail=np.array([c["bail"] for c in tb], dtype=np.int32), exc=np.array([c["exc"] for c in tb]), n_raw=np.array([c["n_raw"] for c in tb], dtype=np.int64),
+                        best=np.array([c["best"] for c in tb], dtype=np.int64), second=np.array([c["second"] for c in tb], dtype=np.int64),
+                        n_distinct=np.array([c["n_distinct"] for c in tb], dtype=np.int32), min_err_gene=np.array([c["min_err_gene"] for c in tb], dtype=np.int64))
+
+
 def flat(cases, key):
     off = np.cumsum([0] + [len(c[key]) for c in cases]).astype(np.int64)
     return np.array([k for c in cases for k in c[key]], dtype=np.uint64), off
@@ -712,6 +790,10 @@ def main():
                         count_keys=np.array([sorted(c["counts"]) + [0] * (80 - len(c["counts"])) for c in ex], dtype=np.uint64),
                         count_vals=np.array([[c["counts"][k] for k in sorted(c["counts"])] + [0] * (80 - len(c["counts"])) for c in ex], dtype=np.int64))
     print("pass-1 exact lookup", [(sum(r[2] == 1 for r in c["reads"]), sum(r[2] == -1 for r in c["reads"])) for c in ex], "(found, throwing) per geometry")
+
+    tb = test_barcodes_cases(vm, np.random.default_rng(909), 24)
+    save_test_barcodes(tb)
+    print("testBarcodes", len(tb), "reads, with hits", sum(c["n_raw"] > 0 for c in tb), "with second", sum(c["n_distinct"] == 2 for c in tb), "%.1fs" % (time.time() - t0))
 
     gm = getmaxed_cases(vm)
     np.savez_compressed(os.path.join(OUT, "ref_getmaxed.npz"), rows=gm)

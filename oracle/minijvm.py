@@ -80,10 +80,12 @@ class ClassRef:
 
 
 class PySet:
-    """membership-only stand-in for fastutil LongSet / Long2LongOpenHashMap keys / the Illumina data holders"""
+    """membership-only stand-in for fastutil LongSet / Long2LongOpenHashMap keys / the Illumina data holders (BarcodesMap additionally
+    hands out its empty-drop list)"""
 
-    def __init__(self, keys):
+    def __init__(self, keys, empty_drops=None):
         self.s = set(int(k) for k in keys)
+        self.empty_drops = empty_drops
 
 
 class JdkHashSet:
@@ -437,6 +439,10 @@ class VM:
             store = a[0].v if isinstance(a[0], JNative) else (a[0].native if isinstance(a[0], JObj) else None)
         if cls == "htsjdk/samtools/fastq/FastqRecord" and name in getattr(self, "fastq_fields", {}):
             return self.fastq_fields[name]                 # the superclass of FastqRecordExt is outside the jars: the driver supplies its getters
+        if name == "clone" and a and isinstance(a[0], JArr):
+            c_ = JArr(a[0].t, 0)
+            c_.a = list(a[0].a)
+            return c_
         if a and isinstance(a[0], JNative) and a[0].name == "logger":
             return None                                    # log4j / java.util.logging calls are dropped
         if cls in ("java/lang/Long", "java/lang/Integer", "java/lang/Boolean", "java/lang/Byte", "java/lang/Short"):
@@ -487,6 +493,10 @@ class VM:
                 src = a[1].v if isinstance(a[1], JNative) else a[1].native
                 store.extend(src)
                 return int(bool(src))
+            if name == "forEach":
+                for x in list(store):
+                    self.call_functional(a[1], [x])
+                return None
             if name == "stream":
                 return JNative("java/util/stream/Stream", JStream(list(store)))
         if isinstance(store, JdkHashSet):
@@ -538,6 +548,9 @@ class VM:
                 return L(len(st_.run(self)))
             if name == "sum":
                 return i32(sum(st_.run(self)))
+            if name in ("min", "max") and len(a) == 1:      # IntStream.min / max
+                v_ = st_.run(self)
+                return JNative("java/util/OptionalInt", ((min(v_) if name == "min" else max(v_)),) if v_ else ())
             if name == "average":
                 v_ = st_.run(self)
                 return JNative("java/util/OptionalDouble", (D(sum(v_) / len(v_)),) if v_ else ())
@@ -569,6 +582,11 @@ class VM:
             arr = JArr("B", 0, 0)
             arr.a = list(a[0].a)
             return arr
+        if cls == "java/util/OptionalInt":
+            if name == "orElse":
+                return a[0].v[0] if a[0].v else a[1]
+            if name == "getAsInt":
+                return a[0].v[0]
         if cls == "java/util/OptionalDouble" and name == "getAsDouble":
             if not a[0].v:
                 raise JavaThrow("java/util/NoSuchElementException")
@@ -754,6 +772,25 @@ class VM:
             return int(int(a[1]) in a[0].s)
         if isinstance(a[0] if a else None, PySet) and name == "size":
             return len(a[0].s)
+        if isinstance(a[0] if a else None, PySet) and name == "isEmpty":
+            return int(not a[0].s)
+        if isinstance(a[0] if a else None, PySet) and name == "getEmptyDropBarcodes":
+            return a[0].empty_drops
+        if a and isinstance(a[0], JNative) and a[0].name == "java/util/AbstractMap$SimpleEntry":
+            if name == "getKey":
+                return a[0].v[0]
+            if name == "getValue":
+                return a[0].v[1]
+            if name == "setValue":
+                old_ = a[0].v[1]
+                a[0].v = (a[0].v[0], a[1])
+                return old_
+        if cls == "java/util/concurrent/atomic/AtomicBoolean":
+            if name == "get":
+                return int(bool(a[0].v[0])) if a[0].v else 0
+            if name == "set":
+                a[0].v = (a[1],)
+                return None
         if cls in ("java/lang/String", "java/lang/CharSequence"):
             s = a[0].v if isinstance(a[0], JNative) else a[0]
             if isinstance(s, str):

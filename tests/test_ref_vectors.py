@@ -364,3 +364,58 @@ def test_gpu_exact_lookup_matches_reference_bytecode(pkg, ctx):
         counts = table.counts()[:, 0]                                # unfilteredUsedBarcodeMap = the ED-0 counters of the table
         assert {int(k): int(c) for k, c in zip(wl, counts) if c} == exp
         assert int(((res["flags"] & 2) != 0).sum()) == n_throw
+
+
+def _test_barcodes_inputs(z, i):
+    """the S4 boundary of the BC flavour: window of offset 0 starts right after the nbasesOfAdapterSeqInReadname (3) adapter bases of the stranded
+    mini-sequence (IlluminaBarcodeAnalyzer.java:L285-L287), 10 post bases (L302)"""
+    s, pm = str(z["stranded"][i]), int(z["pm"][i])
+    start = max(3 - pm - 1, 0)
+    piece = s[start:start + 32].encode()
+    sl = np.zeros((1, 32), dtype=np.uint8)
+    sl[0, :len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+    cut = lambda k, o: z[k][z[o][i]:z[o][i + 1]]
+    return sl, np.array([3 - start], dtype=np.int32), min(len(piece), 32), cut("gene", "gene_offsets"), cut("all_keys", "all_offsets"), cut("empty_keys", "empty_offsets")
+
+
+def _check_test_barcodes(z, i, r):
+    fl = lambda w: (512 if w & 1 else 0) | (4 if w & 2 else 0) | (8 if w & 4 else 0)          # SLR_G_W_* -> BarcodeFindingFlag values
+    if str(z["exc"][i]):
+        assert r["flags"] & 1
+        return "exc"
+    assert not r["flags"] and int(r["n_raw"]) == int(z["n_raw"][i]), (i, r, z["n_raw"][i])
+    assert int(r["min_err_gene"]) == int(z["min_err_gene"][i])                                # testBarcodes L312-L314: goodMatchFound iff <= 1
+    if z["n_raw"][i] == 0:
+        assert r["n_distinct"] == 0
+        return "none"
+    b = z["best"][i]
+    assert (int(r["seq"][0]), r["n_sub"][0], r["n_ins"][0], r["n_del"][0], r["offset"][0], fl(int(r["where"][0]))) == tuple(int(x) for x in b), (i, r, b)
+    assert int(r["n_distinct"]) == int(z["n_distinct"][i])
+    if z["n_distinct"][i] == 2:
+        assert int(r["seq"][1]) == int(z["second"][i][0])
+    return "second" if z["n_distinct"][i] == 2 else "one"
+
+
+def test_test_barcodes_matches_reference_bytecode(orc):
+    """IlluminaBarcodeAnalyzer.testBarcodes (one gene) + getBestAndSecondBCorUMI(CELLBC) run by the reference's class files: BC-flavour offset loop
+    and geometry, the three candidate lists with their ED limits, bailout, the comparator with scoreWhereFound (ascending!), distinct, the
+    second-best match, the list size and the minimum error count of GENE entries"""
+    z = np.load(os.path.join(GOLDEN, "ref_test_barcodes.npz"))
+    kinds = set()
+    for i in range(len(z["ed"])):
+        sl, anchor, slen, gene, allk, empk = _test_barcodes_inputs(z, i)
+        res, _, _ = orc.guided_batch(gene, np.array([0, len(gene)], dtype=np.int64), sl, anchor, np.array([0], dtype=np.int32), int(z["ed"][i]), 16, int(z["pm"][i]), 10,
+                                     bailout=int(z["bail"][i]), bc_flavour=True, all_keys=allk, all_ed=3, empty_keys=empk, empty_ed=2, slice_len=slen)
+        kinds.add(_check_test_barcodes(z, i, res[0]))
+    assert {"none", "one", "second"} <= kinds or {"none", "second"} <= kinds
+
+
+@pytest.mark.gpu
+def test_gpu_test_barcodes_matches_reference_bytecode(pkg, ctx):
+    z = np.load(os.path.join(GOLDEN, "ref_test_barcodes.npz"))
+    for i in range(len(z["ed"])):
+        sl, anchor, slen, gene, allk, empk = _test_barcodes_inputs(z, i)
+        bail = int(z["bail"][i])
+        sets = pkg.GuidedSets(ctx, gene, np.array([0, len(gene)], dtype=np.int64), 16, bc_flavour=True, all_keys=allk, all_ed=3, empty_keys=empk, empty_ed=2)
+        res, _ = sets.match(sl, anchor, np.array([0], dtype=np.int32), int(z["ed"][i]), int(z["pm"][i]), 10, bailout=None if bail < 0 else bail, slice_len=slen)
+        _check_test_barcodes(z, i, res[0])
