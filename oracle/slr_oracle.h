@@ -9,9 +9,10 @@
  * PARITY STATUS: the reference ships no tests / golden vectors for this path and there is no JVM in the build container, but its class
  * files are: oracle/minijvm.py (a JVM-subset interpreter) executes them unmodified and oracle/make_ref_vectors.py freezes the outputs in
  * tests/golden/ref_*.npz.  Pinned that way (tests/test_ref_vectors.py): the 2-bit primitives, limitedCompare, best-of-9 + packing,
- * BarcodeMatchTester.doJob, the Illumina-guided testers, IlluminaUMIanalyzer.findUMI as a whole, getmaxED, the pass-1 exact lookup, calcEditDistances (UMI window slicing
- * included) and Parser.assignBarcode.  JDK / third-party containers are shims there
- * (java.util.HashSet iteration order = the JDK HashMap algorithm as modelled, not executed).  IlluminaBarcodeAnalyzer.testBarcodes (one gene) likewise.  Also: the two read-name examples of
+ * calcEditDistances (UMI window slicing included), BarcodeMatchTester.doJob, Parser.assignBarcode, the pass-1 exact lookup, the
+ * Illumina-guided testers, IlluminaUMIanalyzer.findUMI and IlluminaBarcodeAnalyzer.testBarcodes (one gene) with getBestAndSecondBCorUMI,
+ * getmaxED.  JDK / third-party containers are shims there (java.util.HashSet iteration order = the JDK HashMap algorithm as modelled,
+ * not executed).  Also: the two read-name examples of
  * /root/reference/README.md:400,452, an independent second restatement (oracle/pyref.py) and brute-force property checks (tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may link
