@@ -53,17 +53,36 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML through pynvml (a query takes microseconds, so even a
+    270 ms region of an 8-GPU run gets samples); `nvidia-smi` is the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]            # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.source = index, [], False, "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv, self.source = None, "nvidia-smi"
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nv is not None:
+                    sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                    get = getattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or self.nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                    mask = int(get(self.h))
+                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if mask & b else "Not Active" for b in self.BITS])
+                    time.sleep(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -76,10 +95,9 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({self.NAMES[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 class CudaArrayView:
@@ -157,8 +175,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's banner (NCCL_DEBUG=VERSION/INFO) off stdout: one JSON line only
+        # NCCL prints its version banner to stdout when the communicator is created (NCCL_DEBUG=VERSION on the box): fd 1 is pointed at
+        # stderr until the JSON line is printed, so that stdout carries that one line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = pkg.Context(local_rank, n_streams=2)
@@ -337,7 +360,10 @@ def main():
                                    "the kernel answers the same queries with ~0.5 k 32-byte L2-resident bucket loads per read (one load "
                                    "tests every mutant of a digit group, ED-2 searches that cannot reach the record are skipped), so "
                                    "frac > 1 is not HBM saturation: the kernel is issue-bound (ncu: profiles/), see DESIGN.md 4.1"}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
