@@ -11,18 +11,19 @@ struct SlrGuidedSetsHost {
     uint2 all_set, empty_set;
 };
 
-// one open-addressing table (capacity = power of two >= 2 * distinct keys, >= 2) appended to `slots`; returns (first slot, meta).
-// Keys that do not fit 2 * seq_len bits can never equal a probe (clean sequences only match) and are left out.
+// one bucketised table (capacity = power of two >= 2 * keys, >= 8 slots = one bucket) appended to `slots`; returns (first slot, meta).
+// A key goes into the first free slot of its bucket, a full bucket spills into the next one.  Keys that do not fit 2 * seq_len bits can
+// never equal a probe (clean sequences only match) and are left out.
 inline uint2 slr_guided_add_set(std::vector<uint32_t> &slots, const uint64_t *keys, int64_t n, int seq_len)
 {
     uint2 r;
     r.x = (uint32_t)slots.size();
     r.y = 0u;
     if (n <= 0) return r;
-    uint32_t lg = 1;
+    uint32_t lg = 3;
     while ((1ull << lg) < 2ull * (uint64_t)n) lg++;
-    const uint32_t cap = 1u << lg, mask = cap - 1u;
-    const size_t base = slots.size();
+    const uint32_t cap = 1u << lg, nb_mask = (cap >> 3) - 1u;
+    const size_t base = slots.size();                          // a multiple of 8: every table is
     slots.resize(base + cap, SLR_G_EMPTY);
     bool all_t = false, any = false;
     for (int64_t i = 0; i < n; i++) {
@@ -30,9 +31,16 @@ inline uint2 slr_guided_add_set(std::vector<uint32_t> &slots, const uint64_t *ke
         const uint32_t key = (uint32_t)keys[i];
         any = true;
         if (key == SLR_G_EMPTY) { all_t = true; continue; }
-        uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;
-        while (slots[base + slot] != SLR_G_EMPTY && slots[base + slot] != key) slot = (slot + 1u) & mask;
-        slots[base + slot] = key;
+        uint32_t bucket = slr_g_bucket_of(key, lg);
+        bool done = false;
+        while (!done) {
+            uint32_t *q = &slots[base + 8u * bucket];
+            for (int k = 0; k < 8 && !done; k++) {
+                if (q[k] == key) done = true;                  // duplicate
+                else if (q[k] == SLR_G_EMPTY) { q[k] = key; done = true; }
+            }
+            bucket = (bucket + 1u) & nb_mask;
+        }
     }
     r.y = lg | (all_t ? 0x100u : 0u) | (any ? 0x200u : 0u);
     return r;

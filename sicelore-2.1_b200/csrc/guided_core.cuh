@@ -27,11 +27,13 @@ constexpr int SLR_G_STACK = 48;                 // deque depth: (continuation + 
 constexpr uint32_t SLR_G_EMPTY = 0xFFFFFFFFu;   // empty slot of a candidate table
 
 // ---- candidate sets -------------------------------------------------------------------------------------------------------
-// Every set (one per candidate group + the two global lists of the BC flavour) is an open-addressing table of 32-bit keys
-// (L <= 16 => a clean 2-bit sequence fits 32 bits; values with garbage in bits 62-63 never match, see slr_g_child).
-// meta: bits 0-4 log2(capacity), bit 8 "holds the all-T key 0xFFFFFFFF" (the empty marker), bit 9 "non-empty".
+// Every set (one per candidate group + the two global lists of the BC flavour) is a bucketised open-addressing table of 32-bit keys
+// (L <= 16 => a clean 2-bit sequence fits 32 bits; values with garbage in bits 62-63 never match, see slr_g_child): a key hashes to
+// a bucket of 8 slots = one 32-byte sector, read with two 128-bit loads and compared as a whole, so a lookup is one sector and the
+// lanes of a warp do not diverge over probe chains (a full bucket without the key continues in the next one; at load <= 0.5 that is rare).
+// meta: bits 0-4 log2(capacity in slots, >= 3), bit 8 "holds the all-T key 0xFFFFFFFF" (the empty marker), bit 9 "non-empty".
 struct SlrGuidedSetsDev {
-    const uint32_t *slots;
+    const uint32_t *slots;          // every table starts on a 32-byte boundary
     const uint2 *groups;            // x = first slot, y = meta
     int n_groups;
     uint2 all_set, empty_set;       // BC flavour: allPassed10xBCs / outOfCellsBarcodes (meta 0 = absent)
@@ -40,25 +42,32 @@ struct SlrGuidedSetsDev {
 };
 
 SLR_GHD uint32_t slr_g_hash(uint32_t key) { return key * 0x9E3779B1u; }
+SLR_GHD uint32_t slr_g_bucket_of(uint32_t key, uint32_t lg_slots)          // lg_slots >= 3
+{
+    return lg_slots == 3u ? 0u : (slr_g_hash(key) >> (35u - lg_slots));     // top lg_slots - 3 bits
+}
 
 SLR_GHD bool slr_g_contains(const uint32_t *slots, uint2 set, uint32_t key)
 {
     const uint32_t meta = set.y;
     if (!(meta & 0x200u)) return false;
     if (key == SLR_G_EMPTY) return (meta & 0x100u) != 0u;
-    const uint32_t lg = meta & 31u, mask = (1u << lg) - 1u;
-    uint32_t slot = (slr_g_hash(key) >> (32u - lg)) & mask;       // lg >= 1
+    const uint32_t lg = meta & 31u, nb_mask = (1u << (lg - 3u)) - 1u;
+    uint32_t bucket = slr_g_bucket_of(key, lg);
     const uint32_t *tab = slots + set.x;
-    while (true) {
+    for (uint32_t i = 0; i <= nb_mask; i++) {
 #if defined(__CUDA_ARCH__)
-        const uint32_t v = __ldg(tab + slot);
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(tab + 8u * bucket)), b = __ldg(reinterpret_cast<const uint4 *>(tab + 8u * bucket) + 1);
+        const uint32_t v0 = a.x, v1 = a.y, v2 = a.z, v3 = a.w, v4 = b.x, v5 = b.y, v6 = b.z, v7 = b.w;
 #else
-        const uint32_t v = tab[slot];
+        const uint32_t *q = tab + 8u * bucket;
+        const uint32_t v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5], v6 = q[6], v7 = q[7];
 #endif
-        if (v == key) return true;
-        if (v == SLR_G_EMPTY) return false;
-        slot = (slot + 1u) & mask;
+        if (v0 == key || v1 == key || v2 == key || v3 == key || v4 == key || v5 == key || v6 == key || v7 == key) return true;
+        if (v7 == SLR_G_EMPTY) return false;                  // slots of a bucket fill front to back: a free last slot ends the chain
+        bucket = (bucket + 1u) & nb_mask;
     }
+    return false;
 }
 
 // ---- visited set: IntHashSet on (int) seq of every node that has run a position (java:L105-L120), active for ed >= 2 ----
