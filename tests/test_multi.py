@@ -145,3 +145,49 @@ def test_umi_cross_shard_merge():
     assert P(meta, 0, 64) == (0, [(1, 2), (2, 4)]) and P(meta, 1, 64) == (2, []) and P(meta, 2, 64) == (4, [])
     with pytest.raises(pkg.SiceloreGpuError):
         P(meta, 0, 5)
+
+
+def _guided_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from oracle import orc
+    w = pkg.synth_guided(1200, 12, seed=21, n_groups=200, group_size=6, pm=2, post_len=6)          # every rank derives the same batch ...
+    lo, hi = rank * 600, (rank + 1) * 600                                                          # ... and takes its contiguous shard of the reads
+    res, _, _ = orc.guided_batch(w["group_keys"], w["group_offsets"], w["slices"][lo:hi], w["anchor"][lo:hi], w["group_id"][lo:hi],
+                                 (np.arange(1200) % 3)[lo:hi].astype(np.int32), 12, 2, 6, n_threads=2)             # candidate sets replicated
+    found = torch.tensor([int((res["n_distinct"] > 0).sum()), int((res["n_distinct"] > 1).sum())])
+    dist.all_reduce(found)                                                                          # run statistics are the only exchange
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res.tobytes())
+    if rank == 0:
+        q.put((found.numpy().copy(), b"".join(gathered)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_guided_search_shards_by_read():
+    """Illumina-guided search at N > 1: reads shard by rank, the candidate sets are replicated, results are positional — no data-path
+    collective (the per-shard compute here is the CPU oracle; the GPU path is checked against it elsewhere)"""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    pkg.build()
+    from oracle import orc
+    orc.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_guided_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    found, blob = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w = pkg.synth_guided(1200, 12, seed=21, n_groups=200, group_size=6, pm=2, post_len=6)
+    res, _, _ = orc.guided_batch(w["group_keys"], w["group_offsets"], w["slices"], w["anchor"], w["group_id"], (np.arange(1200) % 3).astype(np.int32), 12, 2, 6)
+    assert res.tobytes() == blob
+    assert found[0] == (res["n_distinct"] > 0).sum() > 600 and found[1] == (res["n_distinct"] > 1).sum()
