@@ -5,6 +5,7 @@ import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import __graft_entry__ as g
+from bench import ClockSampler
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--flavour", default="umi", choices=["umi", "bc"])
@@ -48,12 +49,16 @@ for _ in range(a.warmup):
     step_device()
 torch.cuda.synchronize()
 l0 = pkg.launch_count()
+sampler = ClockSampler(0)
+sampler.start()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps):
     step_device()
 e1.record()
 torch.cuda.synchronize()
+clocks = sampler.summary()
+sampler.join(timeout=10)
 launches = pkg.launch_count() - l0
 ms = e0.elapsed_time(e1) / a.steps
 for _ in range(max(2, a.warmup)):
@@ -82,7 +87,7 @@ print(json.dumps({
     "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "u32", "data": "synthetic",
     "config": {"workload": "guided_%s_ed%d: %d synthetic stranded slices, L %d, candidate groups of ~%d%s, bailout %s" % (
         a.flavour, a.ed, n, L, gsize, " + %d all-passed + %d empty-drop barcodes" % (len(w["all_keys"]), len(w["empty_keys"])) if bc else "", bailout)},
-    "gpu_launches": int(launches), "found_fraction": float((res["n_distinct"] > 0).mean()), "second_fraction": float((res["n_distinct"] > 1).mean()),
+    "clocks": clocks, "gpu_launches": int(launches), "found_fraction": float((res["n_distinct"] > 0).mean()), "second_fraction": float((res["n_distinct"] > 1).mean()),
     "e2e": {"value": n / (e2e_ms / 1e3), "unit": "reads/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * 44, "d2h_bytes_per_step": n * 40},
     "cpu_baseline": {"value": n_s / tcpu, "unit": "reads/s", "cores": os.cpu_count(), "kind": "port", "sample": "first %d reads of the batch, CPU oracle (orc_guided_batch, OpenMP over reads)" % n_s,
                      "probes_per_read": ppr, "gpu_matches_oracle_on_sample": same},
