@@ -165,6 +165,41 @@ int  slr_umi_dist_dev(slr_ctx *ctx, const uint8_t *d_umis, int stride, int umi_l
                       int64_t n_jobs, int64_t n_reads, int32_t *d_out, const int64_t *d_out_offsets,
                       int64_t n_out, void *stream);
 
+/* ---- S5: neighbour-set clustering on the matrices ------------------------------------------------- */
+
+/* Replaces the two O(n^2) steps of ClusterOne_MyClustering.clusterLocal (F!com/rw/umifinder/analyzers/clustering/
+ * ClusterOne_MyClustering.class, ClusterOne_MyClustering.java:L175-L219) for ALL jobs of one BAM chunk, fused behind
+ * the S2 matrices (which stay on the device):
+ *   possibleClusters  a -> N(a) = { v in indices : getED(matrix[a][v]) <= ed }, kept when |N(a)| > 1   (L179-L185;
+ *                     getED = (byte)(packed & 0xFFFFFF), ClusteringEditDistanceBase$BestEditDistance.java:L382)
+ *   per key c         the entry l with c in N(l) and the largest |N(l)|; Stream.max keeps the FIRST maximum of
+ *                     possibleClusters.int2ObjectEntrySet() (L190-L196)
+ * The grouping of the keys by that entry (L199, L219) is an O(n) pass that stays with the caller.
+ *   umis, stride, umi_len, job_offsets, n_jobs   as slr_umi_dist
+ *   ed          ClusterOne_MyClustering.ed (config.xml:270-272: 2 = first pass, 1 = second), 0..5
+ *   member      NULL = every read is in `indices`; else m bytes, 1 = in `indices` (the re-clustering call of
+ *               ClusterOne_MyClustering.call, …java:L107, passes the unclustered subset)
+ *   rank        NULL, or m int32: iteration rank of key l in the caller's possibleClusters map (smaller = earlier;
+ *               job-local).  The fastutil slot order depends on how the map was filled (for > 30 reads the
+ *               reference fills it from a parallel stream), so only the caller knows it.  With NULL a tie goes to
+ *               the smallest index and n_ties > 1 marks exactly the reads whose choice depends on that order.
+ *   out, out_offsets   the matrices as slr_umi_dist writes them, or out = NULL to leave them on the device
+ *   rec         m records, positional */
+typedef struct slr_umi_cluster_rec {
+    int32_t n_neighbours;    /* |N(c)|, the read itself included when matrix[c][c] <= ed; 0 for a non-member        */
+    int32_t best_key;        /* job-local index of the chosen entry; -1 when c is no key (|N(c)| <= 1)             */
+    int32_t best_count;      /* |N(best_key)|                                                                       */
+    int32_t n_ties;          /* entries containing c whose |N| equals best_count                                    */
+} slr_umi_cluster_rec;       /* 16 bytes */
+int  slr_umi_cluster(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets,
+                     int64_t n_jobs, int ed, const uint8_t *member, const int32_t *rank, int32_t *out,
+                     const int64_t *out_offsets, slr_umi_cluster_rec *rec);
+/* the same two steps on matrices already on the device (as slr_umi_dist_dev left them); d_counts: m int32 scratch */
+int  slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets,
+                         const int64_t *d_out_offsets, int64_t n_jobs, int64_t n_reads, int ed,
+                         const uint8_t *d_member, const int32_t *d_rank, int32_t *d_counts,
+                         slr_umi_cluster_rec *d_rec, void *stream);
+
 /* ---- S4: Illumina-guided barcode / UMI search ------------------------------------------------- */
 
 /* Replaces, for a batch of reads, the offset loop of IlluminaUMIanalyzer.findUMI (F!com/rw/umifinder/analyzers/

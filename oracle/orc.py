@@ -166,6 +166,29 @@ def umi_matrix_batch(umis, job_offsets, umi_len=12, n_threads=0):
     return out, out_offsets
 
 
+CLUSTER_REC = np.dtype([("n_neighbours", "<i4"), ("best_key", "<i4"), ("best_count", "<i4"), ("n_ties", "<i4")])
+
+
+def umi_cluster_batch(matrices, job_offsets, out_offsets, ed, member=None, rank=None, n_threads=0):
+    """orc_umi_cluster_batch: ClusterOne_MyClustering.clusterLocal's neighbour counts and chosen entries, all jobs."""
+    matrices = np.ascontiguousarray(matrices, dtype=np.int32)
+    job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+    out_offsets = np.ascontiguousarray(out_offsets, dtype=np.int64)
+    m = int(job_offsets[-1]) if len(job_offsets) else 0
+    rec = np.zeros(m, dtype=CLUSTER_REC)
+    if member is not None:
+        member = np.ascontiguousarray(member, dtype=np.uint8)
+    if rank is not None:
+        rank = np.ascontiguousarray(rank, dtype=np.int32)
+    L = lib()
+    L.orc_umi_cluster_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_umi_cluster_batch.restype = None
+    L.orc_umi_cluster_batch(matrices.ctypes.data, job_offsets.ctypes.data, out_offsets.ctypes.data, len(job_offsets) - 1, int(ed),
+                            member.ctypes.data if member is not None else None, rank.ctypes.data if rank is not None else None,
+                            rec.ctypes.data, n_threads)
+    return rec
+
+
 # ---- Illumina-guided search (SURVEY.md §8 a15) -------------------------------------------------------------------------
 GUIDED_HIT = np.dtype([("seq", "<u8"), ("n_sub", "i1"), ("n_ins", "i1"), ("n_del", "i1"), ("offset", "i1"), ("where", "u1"),
                        ("level", "u1"), ("pad", "<u2")], align=True)

@@ -610,3 +610,86 @@ def guided_query(slice_ascii, anchor, L, ed, plusminus, post_len, bailout=None, 
                 seen.add(n.seq)
                 lst.append(n)
     return [as_dict(n) for n in raw], [as_dict(n) for n in lst]
+
+
+# ---- neighbour-set clustering: ClusterOne_MyClustering.clusterLocal (ClusterOne_MyClustering.java:L175-L219) -----------
+def _i8(x):
+    x &= 0xFF
+    return x - 256 if x >= 128 else x
+
+
+def fastutil_mix(x):
+    """it.unimi.dsi.fastutil.HashCommon.mix(int) (fastutil 8.2.2, jar absent from the mount: restated from the
+    published source): h = x * 0x9E3779B9; h ^ (h >>> 16)."""
+    h = (x * 0x9E3779B9) & 0xFFFFFFFF
+    return h ^ (h >> 16)
+
+
+def fastutil_key_order(keys_in_insertion_order):
+    """Iteration order of an Int2ObjectOpenHashMap (fastutil 8.2.2 defaults: 16 expected, load factor .75) filled by
+    put() in the given order: key 0 first (it lives outside the table), then table slots from the last to the first.
+    Restated from the published source, NOT pinned (the jar is a missing blob); the tests use it only as one example
+    of an order the caller may pass as `rank`."""
+    n, size, has_zero = 32, 0, False
+    table = [0] * n
+
+    def place(tab, mask, k):
+        pos = fastutil_mix(k) & mask
+        while tab[pos] != 0:
+            pos = (pos + 1) & mask
+        tab[pos] = k
+
+    for k in keys_in_insertion_order:
+        if k == 0:
+            if has_zero:
+                continue
+            has_zero = True
+        else:
+            pos = fastutil_mix(k) & (n - 1)
+            dup = False
+            while table[pos] != 0:
+                if table[pos] == k:
+                    dup = True
+                    break
+                pos = (pos + 1) & (n - 1)
+            if dup:
+                continue
+            table[pos] = k
+        size += 1
+        if size - 1 >= int(n * 0.75):          # if (size++ >= maxFill) rehash(arraySize(size + 1, f))
+            need = -(-(size + 1) * 4 // 3)      # ceil((size + 1) / .75)
+            new_n = 2
+            while new_n < need:
+                new_n *= 2
+            new = [0] * new_n
+            for i in range(n - 1, -1, -1):      # rehash walks the old table downwards
+                if table[i] != 0:
+                    place(new, new_n - 1, table[i])
+            table, n = new, new_n
+    order = [0] if has_zero else []
+    order += [table[i] for i in range(n - 1, -1, -1) if table[i] != 0]
+    return order
+
+
+def cluster_local(matrix, indices, ed, key_order=None):
+    """clusterLocal, stream by stream.  matrix[a][v] = packed BestEditDistance ints; indices = the Collection<Integer>;
+    key_order(keys) -> iteration order of possibleClusters (default: ascending).  Returns None (Optional.empty) or the
+    set of clusters (frozensets of indices)."""
+    indices = list(indices)
+    possible = {}
+    for a in indices:                                                            # L179-L185
+        s = {v for v in indices if _i8(matrix[a][v] & 0xFFFFFF) <= ed}
+        if len(s) > 1 and a not in possible:                                     # merge function keeps the first
+            possible[a] = s
+    order = list(key_order(list(possible))) if key_order else sorted(possible)
+    id_map = {}
+    for c in order:                                                              # L190-L199
+        best = None
+        for l in order:
+            if c in possible[l]:
+                if best is None or not (len(possible[best]) >= len(possible[l])):   # compare(a, b) >= 0 ? a : b
+                    best = l
+        id_map.setdefault(best, set()).add(c)
+    if not id_map:                                                               # L219
+        return None
+    return {frozenset(v) for v in id_map.values()}

@@ -718,6 +718,76 @@ void orc_umi_matrix_batch(const uint8_t *umis, int stride, int umi_len, const in
 }
 
 /* ================================================================================================
+ * Neighbour-set clustering: ClusterOne_MyClustering.clusterLocal (ClusterOne_MyClustering.java:L175-L219)
+ *   L179-L185  indices.stream().map(a -> (a, indices.stream().filter(v -> dm.distanceNonReducedSet(a, v) <= ed)
+ *              .collect(HashSet))).filter(set.size() > 1).collect(toMap(..., Int2ObjectOpenHashMap::new))
+ *   L190-L196  keySet().stream().map(c -> (c, entrySet().stream().filter(l -> l.value.contains(c))
+ *              .max(comparing(l -> l.value.size())).get().key))      -- Stream.max keeps the first maximum
+ *   L199, L219 grouped by the chosen entry (done by the caller from rec[].best_key)
+ * distanceNonReducedSet = matrix[a][v].bestEditDistance.getED() (DistanceMatrix.java:L169), getED = (byte)(ed & 0xFFFFFF).
+ * ============================================================================================== */
+static int cluster_ed(int32_t packed) { return (int)(int8_t)(packed & 0xFFFFFF); }
+
+void orc_umi_cluster(const int32_t *matrix, int64_t n, int ed, const uint8_t *member, const int32_t *order, int64_t n_order,
+                     orc_cluster_rec *rec)
+{
+    /* possibleClusters: the neighbour sets as one n x n bit matrix (in[a*n+v] = v in N(a)) */
+    uint8_t *in = (uint8_t *)calloc((size_t)(n * n ? n * n : 1), 1);
+    for (int64_t a = 0; a < n; a++) {
+        rec[a].n_neighbours = 0; rec[a].best_key = -1; rec[a].best_count = 0; rec[a].n_ties = 0;
+        if (member && !member[a]) continue;
+        for (int64_t v = 0; v < n; v++) {
+            if (member && !member[v]) continue;
+            if (cluster_ed(matrix[a * n + v]) <= ed) { in[a * n + v] = 1; rec[a].n_neighbours++; }
+        }
+    }
+    for (int64_t c = 0; c < n; c++) {
+        if (rec[c].n_neighbours <= 1) continue;                       /* c is no key */
+        const int64_t n_it = order ? n_order : n;
+        for (int64_t k = 0; k < n_it; k++) {                          /* entries in iteration order */
+            const int64_t l = order ? order[k] : k;
+            if (l < 0 || l >= n || rec[l].n_neighbours <= 1) continue;
+            if (!in[l * n + c]) continue;                             /* l.getValue().contains(c) */
+            if (rec[l].n_neighbours > rec[c].best_count) {            /* compare(a, b) >= 0 ? a : b  -> first maximum stays */
+                rec[c].best_count = rec[l].n_neighbours; rec[c].best_key = (int32_t)l; rec[c].n_ties = 1;
+            } else if (rec[l].n_neighbours == rec[c].best_count) rec[c].n_ties++;
+        }
+    }
+    free(in);
+}
+
+typedef struct { int32_t rank, key; } cluster_rk;
+static int cluster_rk_cmp(const void *a, const void *b)
+{
+    const cluster_rk *x = (const cluster_rk *)a, *y = (const cluster_rk *)b;
+    if (x->rank != y->rank) return x->rank < y->rank ? -1 : 1;
+    return (x->key > y->key) - (x->key < y->key);
+}
+
+void orc_umi_cluster_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs, int ed,
+                           const uint8_t *member, const int32_t *rank, orc_cluster_rec *rec, int n_threads)
+{
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+    for (int64_t j = 0; j < n_jobs; j++) {
+        const int64_t s = job_offsets[j], n = job_offsets[j + 1] - s;
+        int32_t *order = NULL;
+        if (rank && n > 0) {
+            cluster_rk *rk = (cluster_rk *)malloc((size_t)n * sizeof(cluster_rk));
+            for (int64_t i = 0; i < n; i++) { rk[i].rank = rank[s + i]; rk[i].key = (int32_t)i; }
+            qsort(rk, (size_t)n, sizeof(cluster_rk), cluster_rk_cmp);
+            order = (int32_t *)malloc((size_t)n * sizeof(int32_t));
+            for (int64_t i = 0; i < n; i++) order[i] = rk[i].key;
+            free(rk);
+        }
+        orc_umi_cluster(matrices + out_offsets[j], n, ed, member ? member + s : NULL, order, n, rec + s);
+        free(order);
+    }
+}
+
+/* ================================================================================================
  * Illumina-guided search engine
  * F!com/rw/nuc/encoding/TwoBit/ed/BCUMIEDtesterBase (BCUMIEDtesterBase.java:L82-L203) on top of
  * NucTwoBitPerBaseEDtesterBase (visited set L82-L120, goNextEDlevel with bailout L133-L144).

@@ -171,6 +171,18 @@ void    orc_umi_matrix(const uint8_t *umis, int stride, int umi_len, int64_t n, 
 void    orc_umi_matrix_batch(const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
                              int32_t *out, const int64_t *out_offsets, int n_threads);
 
+
+/* ---------- neighbour-set clustering (F!com/rw/umifinder/analyzers/clustering/ClusterOne_MyClustering.java:L175-L219) ------
+ * clusterLocal on one job's n x n packed matrix.  member: NULL = all reads are in `indices`.  order: NULL, or the
+ * keys of possibleClusters in the map's iteration order (n_order entries, job-local indices; non-keys are skipped).
+ * rec[c] = { |N(c)|, chosen entry or -1, |N(entry)|, number of entries tied for the maximum }. */
+typedef struct { int32_t n_neighbours, best_key, best_count, n_ties; } orc_cluster_rec;
+void    orc_umi_cluster(const int32_t *matrix, int64_t n, int ed, const uint8_t *member, const int32_t *order, int64_t n_order,
+                        orc_cluster_rec *rec);
+/* all jobs; rank (per read, job-local iteration rank of the key, NULL = ascending index) is turned into `order` per job */
+void    orc_umi_cluster_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs, int ed,
+                              const uint8_t *member, const int32_t *rank, orc_cluster_rec *rec, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,7 +45,7 @@ assert GUIDED_HIT.itemsize == 16
 
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
-           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
+           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
            "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count"]
 
 
@@ -73,7 +73,7 @@ def build(force=False, verbose=False):
     """Compile libsicelore_gpu.so (nvcc, sm_100a only) and libslr_synth.so (g++) in-tree."""
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
-    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "guided_match.cu")]
+    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "guided_match.cu")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -120,6 +120,8 @@ def gpu_lib():
         L.slr_bc_collide_dev.argtypes = [vp, vp, i32, vp, i64, vp, vp]
         L.slr_umi_dist.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
         L.slr_umi_dist_dev.argtypes = [vp, vp, i32, i32, vp, i64, i64, vp, vp, i64, vp]
+        L.slr_umi_cluster.argtypes = [vp, vp, i32, i32, vp, i64, i32, vp, vp, vp, vp, vp]
+        L.slr_umi_cluster_dev.argtypes = [vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
         L.slr_guided_sets_create.argtypes = [vp, vp, vp, i64, vp, i64, i32, vp, i64, i32, i32, i32, C.POINTER(vp)]
         L.slr_guided_sets_destroy.argtypes = [vp]
         L.slr_guided_sets_destroy.restype = None
@@ -556,6 +558,53 @@ def generate_distance_matrices(ctx, umis, job_offsets, umi_len=12, out=None, out
     _check(gpu_lib().slr_umi_dist(ctx.h, umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(job_offsets) - 1,
                                   out.ctypes.data, out_offsets.ctypes.data))
     return out, out_offsets
+
+
+UMI_CLUSTER_REC = np.dtype([("n_neighbours", "<i4"), ("best_key", "<i4"), ("best_count", "<i4"), ("n_ties", "<i4")])
+
+
+def cluster_local(ctx, umis, job_offsets, ed, umi_len=12, member=None, rank=None, want_matrices=False):
+    """The two O(n^2) steps of ClusterOne_MyClustering.clusterLocal (ClusterOne_MyClustering.java:L175-L219) for all
+    jobs at once, fused behind the distance matrices: per read |N(c)| and the chosen entry (first maximum of |N(l)|
+    over the entries containing c; `rank` = the caller's iteration rank of the keys, None = ascending index, ties
+    counted in n_ties).  Returns UMI_CLUSTER_REC [m] (+ the flat matrices and their offsets when asked)."""
+    umis = np.ascontiguousarray(umis, dtype=np.uint8)
+    job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+    m = int(job_offsets[-1]) if len(job_offsets) else 0
+    rec = np.zeros(m, dtype=UMI_CLUSTER_REC)
+    if member is not None:
+        member = np.ascontiguousarray(member, dtype=np.uint8)
+        if member.shape != (m,):
+            raise ValueError("member must hold one byte per read")
+    if rank is not None:
+        rank = np.ascontiguousarray(rank, dtype=np.int32)
+        if rank.shape != (m,):
+            raise ValueError("rank must hold one int32 per read")
+    out = out_offsets = None
+    if want_matrices:
+        out_offsets = out_offsets_for(job_offsets)
+        out = np.empty(int(out_offsets[-1]), dtype=np.int32)
+    _check(gpu_lib().slr_umi_cluster(ctx.h, umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(job_offsets) - 1,
+                                     int(ed), member.ctypes.data if member is not None else None,
+                                     rank.ctypes.data if rank is not None else None,
+                                     out.ctypes.data if out is not None else None,
+                                     out_offsets.ctypes.data if out_offsets is not None else None, rec.ctypes.data))
+    return (rec, out, out_offsets) if want_matrices else rec
+
+
+def clusters_from_records(rec, job_offsets):
+    """The grouping step the caller keeps (ClusterOne_MyClustering.java:L199, L219): per job the set of clusters,
+    each the frozenset of keys that chose the same entry.  Jobs without any key give an empty set (Optional.empty)."""
+    res = []
+    for j in range(len(job_offsets) - 1):
+        a, b = int(job_offsets[j]), int(job_offsets[j + 1])
+        groups = {}
+        for c in range(a, b):
+            k = int(rec["best_key"][c])
+            if k >= 0:
+                groups.setdefault(k, set()).add(c - a)
+        res.append({frozenset(v) for v in groups.values()})
+    return res
 
 
 # ---------------------------------------------------------------------------------------------- cross-shard UMI merge

@@ -60,6 +60,7 @@ struct Slot {
     cudaStream_t stream[2] = {nullptr, nullptr};
     DevBuf slices[2], anchor[2], lens[2], out[2];
     DevBuf umi[2], joff[2], ooff[2], uout[2], uscr[2];
+    DevBuf ucl[2];                             // slr_umi_cluster: counts | records | rank | member of the range in flight
     cudaEvent_t uscr_free = nullptr;           // recorded after the last launch that uses uscr[0] on a caller's stream (slr_umi_dist_dev)
     DevBuf gsl, ganc, ggid, ged, gout, graw, gvis;   // Illumina-guided search: staging buffers + the per-warp visited tables
     cudaEvent_t gvis_free = nullptr;           // recorded after the last guided launch that uses gvis
@@ -139,7 +140,7 @@ void slr_ctx_destroy(slr_ctx *c)
             if (s->stream[k]) { cudaStreamSynchronize(s->stream[k]); cudaStreamDestroy(s->stream[k]); }
             s->slices[k].release(); s->anchor[k].release(); s->lens[k].release(); s->out[k].release();
         }
-        for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); }
+        for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); s->ucl[k].release(); }
         if (s->uscr_free) cudaEventDestroy(s->uscr_free);
         if (s->gvis_free) cudaEventDestroy(s->gvis_free);
         s->gsl.release(); s->ganc.release(); s->ggid.release(); s->ged.release(); s->gout.release(); s->graw.release(); s->gvis.release();
@@ -405,13 +406,21 @@ int slr_umi_dist_dev(slr_ctx *ctx, const uint8_t *d_umis, int stride, int umi_le
     return SLR_OK;
 }
 
-int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs, int32_t *out,
-                 const int64_t *out_offsets)
+}  // extern "C"
+
+namespace {
+struct ClusterArgs {                           // slr_umi_cluster rides on the range loop of slr_umi_dist
+    int ed = 0;
+    const uint8_t *member = nullptr;
+    const int32_t *rank = nullptr;
+    slr_umi_cluster_rec *rec = nullptr;
+};
+}  // namespace
+
+static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
+                           int32_t *out, const int64_t *out_offsets, const ClusterArgs *cl)
 {
-    int rc = check_umi_args(ctx, stride, umi_len, n_jobs);
-    if (rc) return rc;
-    if (n_jobs == 0) return SLR_OK;
-    if (!umis || !job_offsets || !out || !out_offsets) return fail(SLR_E_INVALID, "slr_umi_dist: NULL buffer");
+    int rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
     Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
     std::lock_guard<std::mutex> lock(s->mtx);
@@ -452,8 +461,21 @@ int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, con
             CUDA_TRY(slr_launch_umi_dist((const uint8_t *)s->umi[b].p, stride, umi_len, (const long long *)s->joff[b].p, nj_range, nr,
                                          (int32_t *)s->uout[b].p, (const long long *)s->ooff[b].p, s->uscr[b].p, st));
             g_launches += SLR_UMI_LAUNCHES;
+            if (cl) {
+                const size_t o_rec = ((size_t)nr * 4 + 15) & ~(size_t)15, o_rank = o_rec + (size_t)nr * 16, o_mem = o_rank + (size_t)nr * 4;
+                if ((rc = s->ucl[b].reserve(o_mem + (size_t)nr))) return rc;
+                char *base = (char *)s->ucl[b].p;
+                if (cl->rank) CUDA_TRY(cudaMemcpyAsync(base + o_rank, cl->rank + r0, (size_t)nr * 4, cudaMemcpyHostToDevice, st));
+                if (cl->member) CUDA_TRY(cudaMemcpyAsync(base + o_mem, cl->member + r0, (size_t)nr, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(slr_launch_umi_cluster((const int32_t *)s->uout[b].p, (const long long *)s->joff[b].p, (const long long *)s->ooff[b].p,
+                                                nj_range, nr, cl->ed, cl->member ? (const uint8_t *)(base + o_mem) : nullptr,
+                                                cl->rank ? (const int32_t *)(base + o_rank) : nullptr, (int32_t *)base,
+                                                (slr_umi_cluster_rec *)(base + o_rec), st));
+                g_launches += SLR_UMI_CLUSTER_LAUNCHES;
+                CUDA_TRY(cudaMemcpyAsync(cl->rec + r0, base + o_rec, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
+            }
             // jobs may sit anywhere in the caller's `out`: copy back per contiguous run
-            int64_t a = j;
+            int64_t a = out ? j : j1;
             while (a < j1) {
                 int64_t e = a;
                 while (e + 1 < j1) {
@@ -476,9 +498,51 @@ int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, con
     return SLR_OK;
 }
 
+extern "C" {
+
+int slr_umi_dist(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs, int32_t *out,
+                 const int64_t *out_offsets)
+{
+    int rc = check_umi_args(ctx, stride, umi_len, n_jobs);
+    if (rc) return rc;
+    if (n_jobs == 0) return SLR_OK;
+    if (!umis || !job_offsets || !out || !out_offsets) return fail(SLR_E_INVALID, "slr_umi_dist: NULL buffer");
+    return umi_dist_ranges(ctx, umis, stride, umi_len, job_offsets, n_jobs, out, out_offsets, nullptr);
+}
+
+int slr_umi_cluster(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs, int ed,
+                    const uint8_t *member, const int32_t *rank, int32_t *out, const int64_t *out_offsets, slr_umi_cluster_rec *rec)
+{
+    int rc = check_umi_args(ctx, stride, umi_len, n_jobs);
+    if (rc) return rc;
+    if (ed < 0 || ed > 5) return fail(SLR_E_INVALID, "slr_umi_cluster: ed %d outside 0..5", ed);
+    if (n_jobs == 0) return SLR_OK;
+    if (!umis || !job_offsets || !rec || (out && !out_offsets)) return fail(SLR_E_INVALID, "slr_umi_cluster: NULL buffer");
+    ClusterArgs cl;
+    cl.ed = ed; cl.member = member; cl.rank = rank; cl.rec = rec;
+    return umi_dist_ranges(ctx, umis, stride, umi_len, job_offsets, n_jobs, out, out_offsets, &cl);
+}
+
+int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
+                        int64_t n_reads, int ed, const uint8_t *d_member, const int32_t *d_rank, int32_t *d_counts,
+                        slr_umi_cluster_rec *d_rec, void *stream)
+{
+    if (!ctx) return fail(SLR_E_INVALID, "slr_umi_cluster_dev: ctx is NULL");
+    if (ed < 0 || ed > 5) return fail(SLR_E_INVALID, "slr_umi_cluster_dev: ed %d outside 0..5", ed);
+    if (n_jobs < 0 || n_reads < 0) return fail(SLR_E_INVALID, "slr_umi_cluster_dev: negative size");
+    if (n_jobs == 0 || n_reads == 0) return SLR_OK;
+    if (!d_matrices || !d_job_offsets || !d_out_offsets || !d_counts || !d_rec) return fail(SLR_E_INVALID, "slr_umi_cluster_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(slr_launch_umi_cluster(d_matrices, (const long long *)d_job_offsets, (const long long *)d_out_offsets, n_jobs, n_reads, ed,
+                                    d_member, d_rank, d_counts, d_rec, (cudaStream_t)stream));
+    g_launches += SLR_UMI_CLUSTER_LAUNCHES;
+    return SLR_OK;
+}
+
+}  // extern "C"
+
 // ---------------------------------------------------------------------------------------------------------
 // S4: Illumina-guided search
-}  // extern "C"
 
 struct slr_guided_sets {
     slr_ctx *ctx = nullptr;
