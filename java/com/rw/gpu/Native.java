@@ -32,6 +32,10 @@ public final class Native {
     /** ClusteringEditDistanceBase.generateDistanceMatrix for all jobs of a BAM chunk (…java:L168-L259) */
     public static native int umiDist(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, ByteBuffer out,
                                      ByteBuffer outOffsets);
+    /** the two O(n^2) steps of ClusterOne_MyClustering.clusterLocal (…java:L175-L219) behind the same matrices: rec = 16 bytes per read
+     *  {|N(c)|, chosen entry or -1, |N(entry)|, entries tied for the maximum}; member / rank / out / outOffsets nullable */
+    public static native int umiCluster(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, int ed,
+                                        ByteBuffer member, ByteBuffer rank, ByteBuffer out, ByteBuffer outOffsets, ByteBuffer rec);
     /** candidate sets of the Illumina-guided search: groupKeys / groupOffsets = CSR of the per-(gene, cell) UMIs (IlluminaOneGeneOneCellData) or of the
      *  per-gene cell barcodes (BarcodesMap); allKeys = All10xselectedCells, emptyKeys = EmptyDropBarcodes (BC flavour, nullable)  (0 = failed) */
     public static native long guidedSetsCreate(long ctx, long[] groupKeys, long[] groupOffsets, long[] allKeys, int allEd, long[] emptyKeys,

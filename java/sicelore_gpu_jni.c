@@ -99,6 +99,16 @@ JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_umiDist(JNIEnv *env, jclass cls, j
                         (int32_t *)BUF(out), (const int64_t *)BUF(outOffsets));
 }
 
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_umiCluster(JNIEnv *env, jclass cls, jlong ctx, jobject umis, jint stride, jint umiLen,
+                                                         jobject jobOffsets, jlong nJobs, jint ed, jobject member, jobject rank, jobject out,
+                                                         jobject outOffsets, jobject rec)
+{
+    (void)cls;
+    return slr_umi_cluster((slr_ctx *)(size_t)ctx, (const uint8_t *)BUF(umis), stride, umiLen, (const int64_t *)BUF(jobOffsets), (int64_t)nJobs, ed,
+                           member ? (const uint8_t *)BUF(member) : NULL, rank ? (const int32_t *)BUF(rank) : NULL,
+                           out ? (int32_t *)BUF(out) : NULL, outOffsets ? (const int64_t *)BUF(outOffsets) : NULL, (slr_umi_cluster_rec *)BUF(rec));
+}
+
 JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_guidedSetsCreate(JNIEnv *env, jclass cls, jlong ctx, jlongArray groupKeys, jlongArray groupOffsets,
                                                                 jlongArray allKeys, jint allEd, jlongArray emptyKeys, jint emptyEd,
                                                                 jboolean bcFlavour, jint seqLen)

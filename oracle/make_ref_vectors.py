@@ -733,13 +733,94 @@ def save_test_barcodes(tb):
                         n_distinct=np.array([c["n_distinct"] for c in tb], dtype=np.int32), min_err_gene=np.array([c["min_err_gene"] for c in tb], dtype=np.int64))
 
 
+CLUSTER_SIG = "clusterLocal(Ljava/util/Collection;Lcom/rw/clustering/DistanceMatrix;)Ljava/util/Optional;"
+
+
+def cluster_cases(vm, rng, n_cases):
+    """ClusterOne_MyClustering.clusterLocal (ClusterOne_MyClustering.java:L175-L219) on packed matrices: the reference's own streams,
+    lambdas, DistanceMatrix.distanceNonReducedSet and BestEditDistance.getED run as bytecode; java.util.stream, HashSet, Collectors
+    and fastutil's Int2ObjectOpenHashMap are shims (sequential pipelines; the map's iteration order is oracle/pyref.fastutil_key_order
+    and is stored with every case, because the reference's own order for > 30 reads depends on how its parallel stream was split)."""
+    out = []
+    for i in range(n_cases):
+        n = int(rng.integers(2, 40))
+        p_close = float(rng.choice([0.05, 0.2, 0.5, 0.9]))
+        ed_m = np.where(rng.random((n, n)) < p_close, rng.integers(0, 3, (n, n)), rng.integers(3, 6, (n, n))).astype(np.int64)
+        if i % 4:
+            ed_m = np.triu(ed_m, 1)
+            ed_m = ed_m + ed_m.T
+        if i % 5 == 0:                                       # blocks of identical reads: many equal neighbour counts
+            lab = rng.integers(0, max(1, n // 4), n)
+            ed_m = np.where(lab[:, None] == lab[None, :], 0, 5).astype(np.int64)
+        np.fill_diagonal(ed_m, 0)
+        packed = (ed_m | (rng.integers(0, 64, (n, n)) << 24)).astype(np.int32)
+        ed = int(rng.choice([0, 1, 2, 2, 3]))
+        member = np.ones(n, dtype=np.uint8) if i % 3 else (rng.random(n) < 0.7).astype(np.uint8)
+        me = bare(vm, "com/rw/umifinder/analyzers/clustering/ClusterOne_MyClustering")
+        me.f["ed"] = ed
+        dm = bare(vm, "com/rw/clustering/DistanceMatrix")
+        rows = J.JArr("[", n, None)
+        for a in range(n):
+            row = J.JArr("L", n, None)
+            for v in range(n):
+                cell = bare(vm, "com/rw/clustering/ClusteringEditDistanceBase")
+                best = bare(vm, "com/rw/clustering/ClusteringEditDistanceBase$BestEditDistance")
+                best.f["ed"] = int(packed[a, v])
+                cell.f["bestEditDistance"] = best
+                row.a[v] = cell
+            rows.a[a] = row
+        dm.f["distanceMatrix"] = rows
+        indices = J.JNative("java/util/ArrayList", [int(x) for x in np.flatnonzero(member)])
+        captured = {}
+        orig_collect = vm.collect
+
+        def spy(items, col, _orig=orig_collect):
+            r = _orig(items, col)
+            if isinstance(r.v, J.FastutilIntMap):
+                captured["order"] = list(r.v.order())
+            return r
+        vm.collect = spy
+        try:
+            opt = vm.run(me.cls, CLUSTER_SIG, [me, indices, dm])
+        finally:
+            vm.collect = orig_collect
+        label = np.full(n, -1, dtype=np.int32)               # cluster of read c = smallest member of its cluster, -1 = in no cluster
+        if opt.v:
+            for cl in opt.v[0].v.items():
+                mem = sorted(int(x) for x in cl.v.items())
+                for x in mem:
+                    assert label[x] == -1
+                    label[x] = mem[0]
+        rank = np.full(n, 2 ** 30, dtype=np.int32)
+        for r, k in enumerate(captured.get("order", [])):
+            rank[k] = r
+        out.append(dict(n=n, ed=ed, packed=packed, member=member, rank=rank, label=label, present=int(bool(opt.v))))
+    return out
+
+
+def save_cluster_cases(cc):
+    off = np.cumsum([0] + [c["n"] for c in cc]).astype(np.int64)
+    moff = np.cumsum([0] + [c["n"] ** 2 for c in cc]).astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "ref_cluster_local.npz"), job_offsets=off, out_offsets=moff,
+                        packed=np.concatenate([c["packed"].ravel() for c in cc]), ed=np.array([c["ed"] for c in cc], dtype=np.int32),
+                        member=np.concatenate([c["member"] for c in cc]), rank=np.concatenate([c["rank"] for c in cc]),
+                        label=np.concatenate([c["label"] for c in cc]), present=np.array([c["present"] for c in cc], dtype=np.int32))
+
+
 def flat(cases, key):
     off = np.cumsum([0] + [len(c[key]) for c in cases]).astype(np.int64)
     return np.array([k for c in cases for k in c[key]], dtype=np.uint64), off
 
 
 def main():
-    vm = J.VM(JARS)
+    vm = J.VM(JARS + [REF + "/lib/commons-lang3-3.17.0.jar"])      # ImmutablePair (ClusterOne_MyClustering's lambdas) runs as bytecode too
+    t0 = time.time()
+    cc = cluster_cases(vm, np.random.default_rng(1717), 60)
+    save_cluster_cases(cc)
+    print("clusterLocal", len(cc), "jobs, with clusters", sum(c["present"] for c in cc), "reads in clusters", sum(int((c["label"] >= 0).sum()) for c in cc),
+          "%.1fs" % (time.time() - t0), vm.n_insn, "bytecodes")
+    if len(sys.argv) > 1 and sys.argv[1] == "cluster":
+        return
     rng = np.random.default_rng(20261017)
     t0 = time.time()
     prim, seqs = primitives(vm, rng)

@@ -157,6 +157,25 @@ class JStream:
         return out
 
 
+class FastutilIntMap:
+    """it.unimi.dsi.fastutil.ints.Int2ObjectOpenHashMap as far as the path uses it: put / get and the ITERATION ORDER of keys and
+    entries (oracle/pyref.fastutil_key_order: the published open-addressing layout of fastutil 8.2.2, jar absent — the order is a
+    restatement, which is why the vectors record the order that was used)."""
+
+    def __init__(self):
+        self.d, self.inserted = {}, []
+
+    def put(self, k, v):
+        if k not in self.d:
+            self.inserted.append(k)
+        self.d[k] = v
+
+    def order(self):
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import pyref
+        return pyref.fastutil_key_order(self.inserted)
+
+
 def default_of(desc):
     c = desc[0]
     if c == "J":
@@ -340,6 +359,57 @@ class VM:
         if f.name == "pyfunc":
             return f.v(*args)
         raise NotImplementedError("functional object %s" % f.name)
+
+    def new_container(self, supplier):
+        """Supplier of a collector: a constructor reference (HashSet::new, ArrayList::new, Int2ObjectOpenHashMap::new, ConcurrentHashMap::new)"""
+        target = supplier.v[0]
+        if target == "java/util/HashSet":
+            return JNative(target, JdkHashSet(self))
+        if target in ("java/util/ArrayList", "java/util/LinkedList"):
+            return JNative(target, [])
+        if target.endswith("Int2ObjectOpenHashMap"):
+            return JNative(target, FastutilIntMap())
+        if target in ("java/util/concurrent/ConcurrentHashMap", "java/util/HashMap"):
+            return JNative(target, {})
+        raise NotImplementedError("collector supplier %s" % target)
+
+    def collect(self, items, col):
+        """Stream.collect(Collector) for the collectors the path uses"""
+        kind = col.name if col is not None else "collector:toList"
+        if kind == "collector:toList":
+            return JNative("java/util/ArrayList", list(items))
+        if kind == "collector:toSet":
+            hs = JdkHashSet(self)
+            for x in items:
+                hs.add(x)
+            return JNative("java/util/HashSet", hs)
+        if kind == "collector:toCollection":
+            c = self.new_container(col.v[0])
+            for x in items:
+                c.v.add(x) if isinstance(c.v, JdkHashSet) else c.v.append(x)
+            return c
+        if kind == "collector:mapping":
+            return self.collect([self.call_functional(col.v[0], [x]) for x in items], col.v[1])
+        if kind == "collector:toMap":                       # (keyMapper, valueMapper, mergeFunction, mapSupplier): Map.merge per element
+            kf, vf, merge, sup = col.v
+            c = self.new_container(sup)
+            for x in items:
+                k_, v_ = self.call_functional(kf, [x]), self.call_functional(vf, [x])
+                if isinstance(c.v, FastutilIntMap):
+                    c.v.put(k_, self.call_functional(merge, [c.v.d[k_], v_]) if k_ in c.v.d else v_)
+                else:
+                    c.v[k_] = self.call_functional(merge, [c.v[k_], v_]) if k_ in c.v else v_
+            return c
+        if kind == "collector:groupingBy":                  # (classifier, mapFactory, downstream)
+            classifier, sup, down = col.v
+            c = self.new_container(sup)
+            groups = {}
+            for x in items:
+                groups.setdefault(self.call_functional(classifier, [x]), []).append(x)
+            for k_, xs in groups.items():
+                c.v[k_] = self.collect(xs, down)
+            return c
+        raise NotImplementedError(kind)
 
     def j_string(self, v):
         """String.valueOf(Object) as string concatenation applies it"""
@@ -560,8 +630,10 @@ class VM:
                     if not any(self.j_equals(x, y) for y in out_):
                         out_.append(x)
                 return JNative("java/util/stream/Stream", JStream(out_))
+            if name in ("parallel", "sequential"):          # the interpreter runs every pipeline sequentially
+                return a[0]
             if name == "collect":
-                return JNative("java/util/ArrayList", st_.run(self))
+                return self.collect(st_.run(self), a[1] if len(a) > 1 else None)
             if name == "forEach":
                 for x in st_.run(self):
                     self.call_functional(a[1], [x])
@@ -569,13 +641,13 @@ class VM:
             if name == "findFirst":
                 r = st_.run(self, limit=1)
                 return JNative("java/util/Optional", (r[0],) if r else ())
-            if name == "max":                               # Stream.max(comparator): the LAST of equal maxima wins (reduce with a >= b ? a : b ... keeps b on ties)
-                items = st_.run(self)
+            if name == "max":                               # Stream.max(comparator) = reduce(BinaryOperator.maxBy): compare(a, b) >= 0 ? a : b,
+                items = st_.run(self)                       # the FIRST of equal maxima stays
                 if not items:
                     return JNative("java/util/Optional", ())
                 best = items[0]
                 for x in items[1:]:
-                    if self.call_functional(a[1].v, [x]) >= self.call_functional(a[1].v, [best]):
+                    if not self.call_functional(a[1].v, [best]) >= self.call_functional(a[1].v, [x]):
                         best = x
                 return JNative("java/util/Optional", (best,))
         if cls.endswith("lang3/ArrayUtils") and name == "toPrimitive":
@@ -605,6 +677,28 @@ class VM:
             return JNative("java/util/stream/Stream", JStream([ord(ch) for ch in a[0]]))
         if cls == "java/util/stream/Collectors" and name == "toList":
             return JNative("collector:toList")
+        if cls == "java/util/stream/Collectors" and name in ("toCollection", "toSet", "toMap", "mapping", "groupingBy", "groupingByConcurrent"):
+            return JNative("collector:" + name.replace("Concurrent", ""), tuple(a))
+        if cls == "java/util/Comparator" and name == "comparing":
+            return JNative("comparator", a[0])
+        if a and isinstance(a[0], JNative) and isinstance(a[0].v, FastutilIntMap):
+            fm = a[0].v
+            if name == "keySet":
+                return JNative("pylist", list(fm.order()))
+            if name == "int2ObjectEntrySet":
+                return JNative("pylist", [JNative("entry", (k_, fm.d[k_])) for k_ in fm.order()])
+            if name == "get":
+                return fm.d.get(a[1])
+            if name == "size":
+                return len(fm.d)
+        if a and isinstance(a[0], JNative) and a[0].name == "pylist" and name in ("stream", "parallelStream"):
+            return JNative("java/util/stream/Stream", JStream(list(a[0].v)))
+        if a and isinstance(a[0], JNative) and a[0].name == "entry" and name == "getIntKey":
+            return a[0].v[0]
+        if isinstance(store, dict) and name in ("isEmpty", "values", "size") and len(a) == 1:
+            if name == "values":
+                return JNative("java/util/ArrayList", list(store.values()))
+            return int(not store) if name == "isEmpty" else len(store)
         if cls == "java/util/Comparator" and name == "comparingInt":
             return JNative("comparator", a[0])
         if name == "entrySet" and isinstance(store, dict):      # TreeMap: ascending keys (the only ordered map on the path)

@@ -8,8 +8,8 @@
 // Both steps are O(n^2) matrix reads per (cell, region) job.  getED = (byte)(packed & 0xFFFFFF)
 // (ClusteringEditDistanceBase$BestEditDistance.java:L382).
 //
-// Kernel 1: one warp per matrix row -> |N(a)|.  Kernel 2: one thread per read c, rows l walked in ascending order,
-// column reads coalesced across the lanes of a warp.  A tie for the maximum is broken by `rank` (the caller's
+// Kernel 1: one warp per matrix row -> |N(a)|.  Kernel 2: one thread per read c, rows l walked in ascending order in
+// batches of 8 loads, column reads coalesced across the lanes of a warp.  A tie for the maximum is broken by `rank` (the caller's
 // iteration rank of key l) or by ascending index when no rank is given; the number of tied entries is reported so
 // that the caller can re-evaluate exactly those reads with its own map.
 #include "slr_kernels.h"
@@ -26,6 +26,8 @@ __device__ __forceinline__ long long uc_job_of(const long long *__restrict__ jof
     return lo;
 }
 
+constexpr int UC_BATCH = 8;          // matrix cells in flight per thread in the column walk
+
 __device__ __forceinline__ int uc_ed(int32_t packed) { return (int)(int8_t)(packed & 0xFF); }
 
 __global__ void __launch_bounds__(256) umi_neigh_kernel(const int32_t *__restrict__ mat, const long long *__restrict__ joff,
@@ -41,6 +43,7 @@ __global__ void __launch_bounds__(256) umi_neigh_kernel(const int32_t *__restric
         int cnt = 0;
         if (!member || member[r]) {
             const int32_t *row = mat + ooff[j] + (r - r0) * n;
+#pragma unroll 8
             for (long long v = lane; v < n; v += 32)
                 cnt += (!member || member[r0 + v]) && uc_ed(row[v]) <= ed;
         }
@@ -64,15 +67,27 @@ __global__ void __launch_bounds__(256) umi_assign_kernel(const int32_t *__restri
             const long long r0 = joff[j], n = joff[j + 1] - r0;
             const int32_t *col = mat + ooff[j] + (c - r0);
             int best_rank = 0;
-            for (long long l = 0; l < n; l++) {
-                const int cl = counts[r0 + l];
-                if (cl <= 1 || cl < rec.best_count) continue;
-                if (uc_ed(col[l * n]) > ed) continue;
-                const int rl = rank ? rank[r0 + l] : (int)l;
-                if (cl > rec.best_count) { rec.best_count = cl; rec.best_key = (int32_t)l; rec.n_ties = 1; best_rank = rl; }
-                else {
-                    rec.n_ties++;
-                    if (rl < best_rank) { rec.best_key = (int32_t)l; best_rank = rl; }
+            for (long long l0 = 0; l0 < n; l0 += UC_BATCH) {
+                // the choice is a running maximum, so the loads of a batch are issued together before any of them is looked at
+                int cnt[UC_BATCH];
+                int32_t cell[UC_BATCH];
+#pragma unroll
+                for (int k = 0; k < UC_BATCH; k++) {
+                    const long long l = l0 + k < n ? l0 + k : n - 1;
+                    cnt[k] = counts[r0 + l];
+                    cell[k] = col[l * n];
+                }
+#pragma unroll
+                for (int k = 0; k < UC_BATCH; k++) {
+                    const long long l = l0 + k;
+                    const int cl = cnt[k];
+                    if (l >= n || cl <= 1 || cl < rec.best_count || uc_ed(cell[k]) > ed) continue;
+                    const int rl = rank ? rank[r0 + l] : (int)l;
+                    if (cl > rec.best_count) { rec.best_count = cl; rec.best_key = (int32_t)l; rec.n_ties = 1; best_rank = rl; }
+                    else {
+                        rec.n_ties++;
+                        if (rl < best_rank) { rec.best_key = (int32_t)l; best_rank = rl; }
+                    }
                 }
             }
         }

@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE: a plain-C caller of libsicelore_gpu.so (no Python, no torch) that replays recorded boundary buffers
  * through the C ABI and compares the records byte for byte with the recorded reference results — what the JNI glue does
  * from Java (java/sicelore_gpu_jni.c), minus the JVM.
- *   abi_driver <file>      file = "SLRB" | u32 kind (1 bc_assign, 2 umi_dist, 3 bc_collide, 4 bc_exact, 5 guided_match) | kind-specific payload
+ *   abi_driver <file>      file = "SLRB" | u32 kind (1 bc_assign, 2 umi_dist, 3 bc_collide, 4 bc_exact, 5 guided_match, 6 umi_cluster) | kind-specific payload
  * exit code 0 = identical, 1 = mismatch, 2 = bad file, 3 = no CUDA device (the library has no CPU fallback). */
 #include <stddef.h>
 #include <stdint.h>
@@ -83,6 +83,21 @@ int main(int argc, char **argv)
         CHECK(slr_umi_dist(ctx, umis, 16, (int)umi_len, joff, n_jobs, got, ooff));
         bad = memcmp(got, exp, (size_t)cells * 4) != 0;
         printf("umi_dist: %lld jobs, %lld reads, %lld cells: %s\n", (long long)n_jobs, (long long)m, (long long)cells, bad ? "MISMATCH" : "OK");
+    } else if (kind == 6) {
+        const int64_t umi_len = rd64(f), n_jobs = rd64(f), m = rd64(f), cells = rd64(f), ed = rd64(f);
+        uint8_t *umis = rd(f, (size_t)m * 16);
+        int64_t *joff = rd(f, (size_t)(n_jobs + 1) * 8), *ooff = rd(f, (size_t)(n_jobs + 1) * 8);
+        int32_t *exp_m = rd(f, (size_t)cells * 4), *got_m = malloc((size_t)cells * 4 + 4);
+        slr_umi_cluster_rec *exp = rd(f, (size_t)m * sizeof(slr_umi_cluster_rec)), *got = malloc((size_t)m * sizeof(slr_umi_cluster_rec) + 1);
+        CHECK(slr_umi_cluster(ctx, umis, 16, (int)umi_len, joff, n_jobs, (int)ed, NULL, NULL, got_m, ooff, got));
+        bad = memcmp(got_m, exp_m, (size_t)cells * 4) != 0 || memcmp(got, exp, (size_t)m * sizeof(slr_umi_cluster_rec)) != 0;
+        memset(got, 0xff, (size_t)m * sizeof(slr_umi_cluster_rec));
+        CHECK(slr_umi_cluster(ctx, umis, 16, (int)umi_len, joff, n_jobs, (int)ed, NULL, NULL, NULL, NULL, got));      /* matrices stay on the device */
+        bad |= memcmp(got, exp, (size_t)m * sizeof(slr_umi_cluster_rec)) != 0;
+        int64_t keys = 0;
+        for (int64_t i = 0; i < m; i++) keys += exp[i].best_key >= 0;
+        printf("umi_cluster: %lld jobs, %lld reads, ED %lld, %lld keys: %s\n", (long long)n_jobs, (long long)m, (long long)ed, (long long)keys,
+               bad ? "MISMATCH" : "OK");
     } else if (kind == 5) {
         const int64_t L = rd64(f), bc = rd64(f), pm = rd64(f), post_len = rd64(f), bailout = rd64(f), slice_len = rd64(f), raw_cap = rd64(f);
         const int64_t n_groups = rd64(f), n_keys = rd64(f), n_all = rd64(f), n_empty = rd64(f), n = rd64(f);

@@ -112,6 +112,9 @@ def driver_inputs(tmp_path, orc):
     u = np.load(os.path.join(gold, "umi_len12.npz"))
     files.append(write_driver_file(tmp_path / "umi.bin", 2, [int(u["umi_len"]), len(u["job_offsets"]) - 1, len(u["umis"]), len(u["matrix"]),
                                                            u["umis"], u["job_offsets"], u["out_offsets"], u["matrix"]]) or tmp_path / "umi.bin")
+    crec = orc.umi_cluster_batch(u["matrix"], u["job_offsets"], u["out_offsets"], 2)
+    files.append(write_driver_file(tmp_path / "cluster.bin", 6, [int(u["umi_len"]), len(u["job_offsets"]) - 1, len(u["umis"]), len(u["matrix"]), 2,
+                                                               u["umis"], u["job_offsets"], u["out_offsets"], u["matrix"], crec]) or tmp_path / "cluster.bin")
     for name in ("guided_umi_ed2", "guided_bc_mixed"):
         z = np.load(os.path.join(gold, name + ".npz"))
         raw = z["raw"].view(orc.GUIDED_HIT).reshape(len(z["slices"]), -1)

@@ -419,3 +419,73 @@ def test_gpu_test_barcodes_matches_reference_bytecode(pkg, ctx):
         sets = pkg.GuidedSets(ctx, gene, np.array([0, len(gene)], dtype=np.int64), 16, bc_flavour=True, all_keys=allk, all_ed=3, empty_keys=empk, empty_ed=2)
         res, _ = sets.match(sl, anchor, np.array([0], dtype=np.int32), int(z["ed"][i]), int(z["pm"][i]), 10, bailout=None if bail < 0 else bail, slice_len=slen)
         _check_test_barcodes(z, i, res[0])
+
+
+# ---- ClusterOne_MyClustering.clusterLocal (ClusterOne_MyClustering.java:L175-L219), SURVEY.md §8f-3 ---------------------
+def _cluster_labels(rec, job_offsets):
+    """cluster of a read = smallest member of the set of keys that chose the same entry (the grouping of L199 / L219)"""
+    label = np.full(len(rec), -1, dtype=np.int32)
+    for j in range(len(job_offsets) - 1):
+        a, b = int(job_offsets[j]), int(job_offsets[j + 1])
+        groups = {}
+        for c in range(a, b):
+            k = int(rec["best_key"][c])
+            if k >= 0:
+                groups.setdefault(k, []).append(c - a)
+        for mem in groups.values():
+            for x in mem:
+                label[a + x] = min(mem)
+    return label
+
+
+def _check_cluster_records(z, rec):
+    assert np.array_equal(_cluster_labels(rec, z["job_offsets"]), z["label"])
+    has = np.array([(rec["best_key"][a:b] >= 0).any() for a, b in zip(z["job_offsets"][:-1], z["job_offsets"][1:])])
+    assert np.array_equal(has.astype(np.int32), z["present"])                      # Optional.empty <=> no key at all
+
+
+def test_cluster_local_matches_reference_bytecode(orc):
+    z = np.load(os.path.join(GOLDEN, "ref_cluster_local.npz"))
+    assert len(z["ed"]) >= 50 and (z["label"] >= 0).sum() > 500
+    rec = np.zeros(len(z["member"]), dtype=orc.CLUSTER_REC)
+    for j in range(len(z["ed"])):                                                  # ed differs per job: one oracle call each
+        a, b = int(z["job_offsets"][j]), int(z["job_offsets"][j + 1])
+        m = z["packed"][z["out_offsets"][j]:z["out_offsets"][j + 1]]
+        rec[a:b] = orc.umi_cluster_batch(m, [0, b - a], [0, (b - a) ** 2], int(z["ed"][j]), z["member"][a:b], z["rank"][a:b])
+    _check_cluster_records(z, rec)
+    assert (rec["n_ties"] > 1).sum() > 50                                          # the order of the map did decide some of them
+    # and the stream-by-stream Python restatement agrees as well
+    for j in range(len(z["ed"])):
+        a, b = int(z["job_offsets"][j]), int(z["job_offsets"][j + 1])
+        n = b - a
+        m = z["packed"][z["out_offsets"][j]:z["out_offsets"][j + 1]].reshape(n, n)
+        got = pyref.cluster_local(m.tolist(), [i for i in range(n) if z["member"][a + i]], int(z["ed"][j]), pyref.fastutil_key_order)
+        want = {}
+        for i in range(n):
+            if z["label"][a + i] >= 0:
+                want.setdefault(int(z["label"][a + i]), set()).add(i)
+        assert (got or set()) == {frozenset(v) for v in want.values()}
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_local_matches_reference_bytecode(pkg, ctx):
+    import torch
+    z = np.load(os.path.join(GOLDEN, "ref_cluster_local.npz"))
+    m = len(z["member"])
+    rec = np.zeros(m, dtype=pkg.UMI_CLUSTER_REC)
+    d_m = torch.from_numpy(z["packed"]).cuda()
+    d_mem, d_rank = torch.from_numpy(z["member"]).cuda(), torch.from_numpy(z["rank"]).cuda()
+    d_cnt = torch.empty(m, dtype=torch.int32, device="cuda")
+    d_rec = torch.empty(m * 4, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for j in range(len(z["ed"])):
+        a, b = int(z["job_offsets"][j]), int(z["job_offsets"][j + 1])
+        jo = torch.tensor([0, b - a], dtype=torch.int64, device="cuda")
+        oo = torch.tensor([0, (b - a) ** 2], dtype=torch.int64, device="cuda")
+        rc = pkg.gpu_lib().slr_umi_cluster_dev(ctx.h, d_m.data_ptr() + 4 * int(z["out_offsets"][j]), jo.data_ptr(), oo.data_ptr(), 1, b - a,
+                                               int(z["ed"][j]), d_mem.data_ptr() + a, d_rank.data_ptr() + 4 * a, d_cnt.data_ptr() + 4 * a,
+                                               d_rec.data_ptr() + 16 * a, st)
+        assert rc == 0
+        torch.cuda.synchronize()
+    rec = d_rec.cpu().numpy().view(pkg.UMI_CLUSTER_REC).reshape(m)
+    _check_cluster_records(z, rec)
