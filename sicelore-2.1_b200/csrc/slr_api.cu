@@ -469,7 +469,8 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
                 if (cl->member) CUDA_TRY(cudaMemcpyAsync(base + o_mem, cl->member + r0, (size_t)nr, cudaMemcpyHostToDevice, st));
                 CUDA_TRY(slr_launch_umi_cluster((const int32_t *)s->uout[b].p, (const long long *)s->joff[b].p, (const long long *)s->ooff[b].p,
                                                 nj_range, nr, cl->ed, cl->member ? (const uint8_t *)(base + o_mem) : nullptr,
-                                                cl->rank ? (const int32_t *)(base + o_rank) : nullptr, (int32_t *)base,
+                                                cl->rank ? (const int32_t *)(base + o_rank) : nullptr,
+                                                slr_umi_scratch_rowjob(s->uscr[b].p, nr), (int32_t *)base,
                                                 (slr_umi_cluster_rec *)(base + o_rec), st));
                 g_launches += SLR_UMI_CLUSTER_LAUNCHES;
                 CUDA_TRY(cudaMemcpyAsync(cl->rec + r0, base + o_rec, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
@@ -534,7 +535,7 @@ int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *
     if (!d_matrices || !d_job_offsets || !d_out_offsets || !d_counts || !d_rec) return fail(SLR_E_INVALID, "slr_umi_cluster_dev: NULL buffer");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(slr_launch_umi_cluster(d_matrices, (const long long *)d_job_offsets, (const long long *)d_out_offsets, n_jobs, n_reads, ed,
-                                    d_member, d_rank, d_counts, d_rec, (cudaStream_t)stream));
+                                    d_member, d_rank, nullptr, d_counts, d_rec, (cudaStream_t)stream));
     g_launches += SLR_UMI_CLUSTER_LAUNCHES;
     return SLR_OK;
 }

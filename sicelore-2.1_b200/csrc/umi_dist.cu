@@ -233,6 +233,12 @@ size_t slr_umi_scratch_bytes(long long n_reads)
     return (size_t)n_reads * 20 + (nb + 1) * 8 + 64;
 }
 
+const int32_t *slr_umi_scratch_rowjob(const void *d_scratch, long long n_reads)
+{
+    const long long nb = (n_reads + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;     // same layout as in slr_launch_umi_dist
+    return reinterpret_cast<const int32_t *>(reinterpret_cast<const unsigned long long *>(d_scratch) + 2 * n_reads + nb + 1);
+}
+
 cudaError_t slr_launch_umi_dist(const uint8_t *d_umis, int stride, int umi_len, const long long *d_job_offsets, long long n_jobs,
                                 long long n_reads, int32_t *d_out, const long long *d_out_offsets, void *d_scratch, cudaStream_t stream)
 {
