@@ -87,7 +87,9 @@ def _umi_worker(rank, world, port, cuts, q):
     mine = buf[row0:row0 + n_rows].numpy()
     mats, oo = orc.umi_matrix_batch(mine, moffs, 12, n_threads=1)
     first_job = j0 + (1 if row0 else 0)
-    out = {first_job + i: mats[oo[i]:oo[i + 1]].copy() for i in range(len(moffs) - 1) if moffs[i + 1] > moffs[i]}
+    crec = orc.umi_cluster_batch(mats, moffs, oo, 2, n_threads=1)          # clusterLocal needs whole jobs too (neighbour sets span the job)
+    out = {first_job + i: (mats[oo[i]:oo[i + 1]].copy(), crec[moffs[i]:moffs[i + 1]].tobytes())
+           for i in range(len(moffs) - 1) if moffs[i + 1] > moffs[i]}
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:
@@ -137,8 +139,10 @@ def test_umi_cross_shard_merge():
             assert j not in seen                              # every job is clustered on exactly one rank
             seen[j] = mat
     assert sorted(seen) == list(range(len(offs) - 1))
-    for j, mat in seen.items():
+    ecl = orc.umi_cluster_batch(exp, offs, eo, 2)
+    for j, (mat, crec) in seen.items():
         assert (mat == exp[eo[j]:eo[j + 1]]).all(), j         # ... as ONE job: identical to the unsharded matrix
+        assert crec == ecl[offs[j]:offs[j + 1]].tobytes(), j  # ... and so are its neighbour sets / chosen entries
     # the pure planning function: chains and the size guard
     P = pkg.UmiShardMerger.plan
     meta = [[0, 0, 5, 3, 0, 4], [3, 0, 2, 3, 0, 1], [3, 0, 4, 9, 0, 3]]       # job 3 spans ranks 0, 1 (entirely) and 2
