@@ -65,8 +65,13 @@ __global__ void __launch_bounds__(32 * UC_SLICES) umi_neigh_kernel(const int32_t
             }
             const bool wide = in && n > UC_LANE_ROW;
             int cnt = 0;
-            if (in && !wide)
-                for (long long v = 0; v < n; v++) cnt += (!member || member[r0 + v]) && uc_ed(row[v]) <= ed;
+            if (in && !wide) {
+                int32_t cell[UC_LANE_ROW];
+#pragma unroll
+                for (int v = 0; v < UC_LANE_ROW; v++) cell[v] = v < n ? row[v] : 0x7f;       // all loads of the row in flight together
+#pragma unroll
+                for (int v = 0; v < UC_LANE_ROW; v++) cnt += v < n && (!member || member[r0 + v]) && uc_ed(cell[v]) <= ed;
+            }
             if (live && !wide) counts[r] = cnt;
             s_r0[x] = r0; s_n[x] = n; s_row[x] = row;
             const unsigned todo = __ballot_sync(0xffffffffu, wide);
@@ -127,26 +132,36 @@ __global__ void __launch_bounds__(32 * UC_SLICES) umi_assign_kernel(const int32_
         const bool deep = n >= UC_DEEP;
         UcBest b = {0, 0, -1, 0};
         if (n > 0 && (deep || y == 0)) {
-            const int32_t *col = mat + s_oo[x] + (c - r0);
-            const long long per = deep ? (n + UC_SLICES - 1) / UC_SLICES : n;
-            const long long l_begin = deep ? y * per : 0, l_end = l_begin + per < n ? l_begin + per : n;
-            for (long long l0 = l_begin; l0 < l_end; l0 += UC_BATCH) {
+            const int ni = (int)n;                                                  // a job's read count fits an int (its matrix must fit the GPU)
+            const int per = deep ? (ni + UC_SLICES - 1) / UC_SLICES : ni;
+            const int l_begin = deep ? y * per : 0, l_end = l_begin + per < ni ? l_begin + per : ni;
+            const int32_t *p = mat + s_oo[x] + (c - r0) + (long long)l_begin * n;    // matrix[l][c], one row further per step
+            const int32_t *pc = counts + r0 + l_begin;
+            const int32_t *pr = rank ? rank + r0 : nullptr;
+            int l = l_begin;
+            for (; l + UC_BATCH <= l_end; l += UC_BATCH, pc += UC_BATCH) {
                 // the choice is a running maximum, so the loads of a batch are issued together before any of them is looked at
                 int cnt[UC_BATCH];
                 int32_t cell[UC_BATCH];
 #pragma unroll
-                for (int k = 0; k < UC_BATCH; k++) {
-                    const long long l = l0 + k < l_end ? l0 + k : l_end - 1;
-                    cnt[k] = counts[r0 + l];
-                    cell[k] = col[l * n];
-                }
+                for (int k = 0; k < UC_BATCH; k++) { cnt[k] = pc[k]; cell[k] = *p; p += n; }
+#pragma unroll
+                for (int k = 0; k < UC_BATCH; k++)
+                    if (cnt[k] > 1 && cnt[k] >= b.count && uc_ed(cell[k]) <= ed) uc_merge(b, cnt[k], pr ? pr[l + k] : l + k, l + k, 1);
+            }
+            if (l < l_end) {                                                        // the last (for small jobs: the only) batch, predicated
+                const int rem = l_end - l;
+                int cnt[UC_BATCH];
+                int32_t cell[UC_BATCH];
 #pragma unroll
                 for (int k = 0; k < UC_BATCH; k++) {
-                    const long long l = l0 + k;
-                    const int cl = cnt[k];
-                    if (l >= l_end || cl <= 1 || cl < b.count || uc_ed(cell[k]) > ed) continue;
-                    uc_merge(b, cl, rank ? rank[r0 + l] : (int)l, (int)l, 1);
+                    cnt[k] = k < rem ? pc[k] : 0;
+                    cell[k] = k < rem ? *p : 0;
+                    if (k < rem) p += n;
                 }
+#pragma unroll
+                for (int k = 0; k < UC_BATCH; k++)
+                    if (cnt[k] > 1 && cnt[k] >= b.count && uc_ed(cell[k]) <= ed) uc_merge(b, cnt[k], pr ? pr[l + k] : l + k, l + k, 1);
             }
         }
         s_part[y][x] = b;
