@@ -74,6 +74,7 @@ struct slr_ctx {
     unsigned long long *d_work = nullptr;
     std::atomic<unsigned> next_work{0};
     unsigned long long *work_counter() { return d_work + next_work.fetch_add(1) % WORK_COUNTERS; }
+    unsigned long long *work_pair() { return d_work + next_work.fetch_add(2) % WORK_COUNTERS; }     // two slots (the array has one spare)
     int device = 0;
     int n_slots = 1;
     std::vector<Slot *> slots;
@@ -113,7 +114,7 @@ int slr_ctx_create(int device, int n_streams, slr_ctx **out)
         return fail(SLR_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     slr_ctx *c = new slr_ctx();
     c->device = device;
-    e = cudaMalloc((void **)&c->d_work, WORK_COUNTERS * sizeof(unsigned long long));
+    e = cudaMalloc((void **)&c->d_work, (WORK_COUNTERS + 1) * sizeof(unsigned long long));
     if (e != cudaSuccess) { delete c; return fail(SLR_E_NOMEM, "cudaMalloc(work counters): %s", cudaGetErrorString(e)); }
     c->n_slots = n_streams < 1 ? 1 : (n_streams > 64 ? 64 : n_streams);
     for (int i = 0; i < c->n_slots; i++) {
@@ -471,7 +472,7 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
                                                 nj_range, nr, cl->ed, cl->member ? (const uint8_t *)(base + o_mem) : nullptr,
                                                 cl->rank ? (const int32_t *)(base + o_rank) : nullptr,
                                                 slr_umi_scratch_rowjob(s->uscr[b].p, nr), (int32_t *)base,
-                                                (slr_umi_cluster_rec *)(base + o_rec), st));
+                                                (slr_umi_cluster_rec *)(base + o_rec), ctx->work_pair(), st));
                 g_launches += SLR_UMI_CLUSTER_LAUNCHES;
                 CUDA_TRY(cudaMemcpyAsync(cl->rec + r0, base + o_rec, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
             }
@@ -535,7 +536,7 @@ int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *
     if (!d_matrices || !d_job_offsets || !d_out_offsets || !d_counts || !d_rec) return fail(SLR_E_INVALID, "slr_umi_cluster_dev: NULL buffer");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(slr_launch_umi_cluster(d_matrices, (const long long *)d_job_offsets, (const long long *)d_out_offsets, n_jobs, n_reads, ed,
-                                    d_member, d_rank, nullptr, d_counts, d_rec, (cudaStream_t)stream));
+                                    d_member, d_rank, nullptr, d_counts, d_rec, ctx->work_pair(), (cudaStream_t)stream));
     g_launches += SLR_UMI_CLUSTER_LAUNCHES;
     return SLR_OK;
 }

@@ -18,12 +18,13 @@ cudaError_t slr_launch_umi_dist(const uint8_t *d_umis, int stride, int umi_len, 
                                 long long n_reads, int32_t *d_out, const long long *d_out_offsets, void *d_scratch, cudaStream_t stream);
 
 // neighbour counts + best cluster key on the matrices slr_launch_umi_dist wrote (umi_cluster.cu); d_counts: n_reads int32
-constexpr int SLR_UMI_CLUSTER_LAUNCHES = 2;
+constexpr int SLR_UMI_CLUSTER_LAUNCHES = 4;
+// d_range: 16 bytes of device memory owned by this launch (the read range of the deep jobs, filled by the first kernel)
 // d_rowjob: the job of every read as slr_launch_umi_dist left it in its scratch (slr_umi_scratch_rowjob), or NULL (binary search)
 const int32_t *slr_umi_scratch_rowjob(const void *d_scratch, long long n_reads);
 cudaError_t slr_launch_umi_cluster(const int32_t *d_mat, const long long *d_job_offsets, const long long *d_out_offsets, long long n_jobs,
                                    long long n_reads, int ed, const uint8_t *d_member, const int32_t *d_rank, const int32_t *d_rowjob,
-                                   int32_t *d_counts, slr_umi_cluster_rec *d_out, cudaStream_t stream);
+                                   int32_t *d_counts, slr_umi_cluster_rec *d_out, unsigned long long *d_range, cudaStream_t stream);
 
 cudaError_t slr_launch_bc_collide(const SlrTableDev &tab, int ed_max, const unsigned long long *d_queries, long long n,
                                   slr_collide_result *d_out, cudaStream_t stream);
