@@ -60,6 +60,7 @@ struct Slot {
     cudaStream_t stream[2] = {nullptr, nullptr};
     DevBuf slices[2], anchor[2], lens[2], out[2];
     DevBuf umi[2], joff[2], ooff[2], uout[2], uscr[2];
+    DevBuf jraw[2], jtmp[2];                   // the caller's job offsets of the range in flight + scan scratch (rebased on the device)
     DevBuf ucl[2];                             // slr_umi_cluster: counts | records | rank | member of the range in flight
     cudaEvent_t uscr_free = nullptr;           // recorded after the last launch that uses uscr[0] on a caller's stream (slr_umi_dist_dev)
     DevBuf gsl, ganc, ggid, ged, gout, graw, gvis;   // Illumina-guided search: staging buffers + the per-warp visited tables
@@ -141,7 +142,7 @@ void slr_ctx_destroy(slr_ctx *c)
             if (s->stream[k]) { cudaStreamSynchronize(s->stream[k]); cudaStreamDestroy(s->stream[k]); }
             s->slices[k].release(); s->anchor[k].release(); s->lens[k].release(); s->out[k].release();
         }
-        for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); s->ucl[k].release(); }
+        for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); s->ucl[k].release(); s->jraw[k].release(); s->jtmp[k].release(); }
         if (s->uscr_free) cudaEventDestroy(s->uscr_free);
         if (s->gvis_free) cudaEventDestroy(s->gvis_free);
         s->gsl.release(); s->ganc.release(); s->ggid.release(); s->ged.release(); s->gout.release(); s->graw.release(); s->gvis.release();
@@ -426,9 +427,10 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
     Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
     std::lock_guard<std::mutex> lock(s->mtx);
     // job ranges of at most ~2^23 output cells (a single larger job still goes in one launch), ping-pong on the slot's two
-    // streams: H2D of range c+1 and D2H of range c-1 overlap the kernels of range c
+    // streams: H2D of range c+1 and D2H of range c-1 overlap the kernels of range c.  The host only walks the job sizes to cut the
+    // ranges; the offsets relative to the range and the matrix offsets (prefix sums of n^2) are made on the device.
     const int64_t CELL_LIMIT = 1LL << 23;
-    std::vector<long long> joff[2], ooff[2];
+    std::vector<long long> ooff[2];                                        // only for a caller whose matrices are not packed back to back
     CUDA_TRY(cudaStreamWaitEvent(s->stream[0], s->uscr_free, 0));         // uscr[0] may still serve a slr_umi_dist_dev launch
     int64_t j = 0;
     for (int c = 0; j < n_jobs; c++) {
@@ -436,29 +438,31 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
         cudaStream_t st = s->stream[b];
         CUDA_TRY(cudaStreamSynchronize(st));                               // buffers (and host vectors) of this parity are free again
         int64_t j1 = j, cells = 0;
-        joff[b].clear(); ooff[b].clear();
+        bool packed = true;                                                // out_offsets of the range = running sum of n^2
         const int64_t r0 = job_offsets[j];
         while (j1 < n_jobs) {
             const int64_t nj = job_offsets[j1 + 1] - job_offsets[j1];
             if (nj < 0) return fail(SLR_E_INVALID, "job_offsets not monotone at %lld", (long long)j1);
             if (j1 > j && cells + nj * nj > CELL_LIMIT) break;
-            joff[b].push_back(job_offsets[j1] - r0);
-            ooff[b].push_back(cells);
+            if (out) packed &= out_offsets[j1] - out_offsets[j] == cells;
             cells += nj * nj;
             j1++;
         }
-        joff[b].push_back(job_offsets[j1] - r0);
-        ooff[b].push_back(cells);
         const int64_t nr = job_offsets[j1] - r0, nj_range = j1 - j;
         if (nr > 0) {
+            const size_t off_bytes = (size_t)(nj_range + 1) * 8;
             if ((rc = s->umi[b].reserve((size_t)nr * stride))) return rc;
-            if ((rc = s->joff[b].reserve(joff[b].size() * 8))) return rc;
-            if ((rc = s->ooff[b].reserve(ooff[b].size() * 8))) return rc;
+            if ((rc = s->jraw[b].reserve(off_bytes))) return rc;
+            if ((rc = s->jtmp[b].reserve(slr_umi_rebase_tmp_bytes(nj_range)))) return rc;
+            if ((rc = s->joff[b].reserve(off_bytes))) return rc;
+            if ((rc = s->ooff[b].reserve(off_bytes))) return rc;
             if ((rc = s->uout[b].reserve((size_t)cells * 4))) return rc;
             if ((rc = s->uscr[b].reserve(slr_umi_scratch_bytes(nr)))) return rc;
             CUDA_TRY(cudaMemcpyAsync(s->umi[b].p, umis + r0 * stride, (size_t)nr * stride, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(s->joff[b].p, joff[b].data(), joff[b].size() * 8, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(s->ooff[b].p, ooff[b].data(), ooff[b].size() * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s->jraw[b].p, job_offsets + j, off_bytes, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(slr_launch_umi_rebase((const long long *)s->jraw[b].p, nj_range, r0, (long long *)s->joff[b].p, (long long *)s->ooff[b].p,
+                                           s->jtmp[b].p, st));
+            g_launches += SLR_UMI_REBASE_LAUNCHES;
             CUDA_TRY(slr_launch_umi_dist((const uint8_t *)s->umi[b].p, stride, umi_len, (const long long *)s->joff[b].p, nj_range, nr,
                                          (int32_t *)s->uout[b].p, (const long long *)s->ooff[b].p, s->uscr[b].p, st));
             g_launches += SLR_UMI_LAUNCHES;
@@ -476,21 +480,32 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
                 g_launches += SLR_UMI_CLUSTER_LAUNCHES;
                 CUDA_TRY(cudaMemcpyAsync(cl->rec + r0, base + o_rec, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
             }
-            // jobs may sit anywhere in the caller's `out`: copy back per contiguous run
-            int64_t a = out ? j : j1;
-            while (a < j1) {
-                int64_t e = a;
-                while (e + 1 < j1) {
-                    const int64_t ne = job_offsets[e + 1] - job_offsets[e];
-                    if (out_offsets[e + 1] != out_offsets[e] + ne * ne) break;
-                    e++;
+            if (out && packed) {                                           // the usual layout: the range is one contiguous piece of `out`
+                if (cells > 0)
+                    CUDA_TRY(cudaMemcpyAsync(out + out_offsets[j], s->uout[b].p, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
+            } else if (out) {                                              // jobs may sit anywhere in the caller's `out`: one copy per contiguous run
+                ooff[b].clear();
+                int64_t acc = 0;
+                for (int64_t k = j; k < j1; k++) {
+                    ooff[b].push_back(acc);
+                    const int64_t nk = job_offsets[k + 1] - job_offsets[k];
+                    acc += nk * nk;
                 }
-                const int64_t ne = job_offsets[e + 1] - job_offsets[e];
-                const int64_t ncell = ooff[b][e - j] + ne * ne - ooff[b][a - j];
-                if (ncell > 0)
-                    CUDA_TRY(cudaMemcpyAsync(out + out_offsets[a], (int32_t *)s->uout[b].p + ooff[b][a - j], (size_t)ncell * 4,
-                                             cudaMemcpyDeviceToHost, st));
-                a = e + 1;
+                int64_t a = j;
+                while (a < j1) {
+                    int64_t e = a;
+                    while (e + 1 < j1) {
+                        const int64_t ne = job_offsets[e + 1] - job_offsets[e];
+                        if (out_offsets[e + 1] != out_offsets[e] + ne * ne) break;
+                        e++;
+                    }
+                    const int64_t ne = job_offsets[e + 1] - job_offsets[e];
+                    const int64_t ncell = ooff[b][e - j] + ne * ne - ooff[b][a - j];
+                    if (ncell > 0)
+                        CUDA_TRY(cudaMemcpyAsync(out + out_offsets[a], (int32_t *)s->uout[b].p + ooff[b][a - j], (size_t)ncell * 4,
+                                                 cudaMemcpyDeviceToHost, st));
+                    a = e + 1;
+                }
             }
         }
         j = j1;

@@ -26,6 +26,13 @@ cudaError_t slr_launch_umi_cluster(const int32_t *d_mat, const long long *d_job_
                                    long long n_reads, int ed, const uint8_t *d_member, const int32_t *d_rank, const int32_t *d_rowjob,
                                    int32_t *d_counts, slr_umi_cluster_rec *d_out, unsigned long long *d_range, cudaStream_t stream);
 
+// a range of the caller's CSR job offsets (d_raw: n_jobs + 1 entries) rebased on the device: d_joff = raw - r0, d_ooff = exclusive prefix
+// sum of the squared job sizes (both n_jobs + 1 entries); d_tmp: slr_umi_rebase_tmp_bytes(n_jobs); three kernels
+constexpr int SLR_UMI_REBASE_LAUNCHES = 3;
+size_t slr_umi_rebase_tmp_bytes(long long n_jobs);
+cudaError_t slr_launch_umi_rebase(const long long *d_raw, long long n_jobs, long long r0, long long *d_joff, long long *d_ooff, void *d_tmp,
+                                  cudaStream_t stream);
+
 cudaError_t slr_launch_bc_collide(const SlrTableDev &tab, int ed_max, const unsigned long long *d_queries, long long n,
                                   slr_collide_result *d_out, cudaStream_t stream);
 

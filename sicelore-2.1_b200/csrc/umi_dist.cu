@@ -130,6 +130,52 @@ __global__ void __launch_bounds__(1024) umi_scan_blocks(unsigned long long *__re
     if (threadIdx.x == 0) block_tot[nb] = carry_s;
 }
 
+// Rebasing of a range of the caller's CSR job offsets on the device: joff[k] = raw[k] - r0 and ooff = exclusive prefix sum of the
+// n_k^2 matrix sizes (block-local scan here, block totals by umi_scan_blocks, then umi_rebase_add).  k runs over 0..n_jobs.
+__global__ void __launch_bounds__(1024) umi_rebase_local(const long long *__restrict__ raw, long long n_jobs, long long r0,
+                                                          long long *__restrict__ joff, unsigned long long *__restrict__ ooff,
+                                                          unsigned long long *__restrict__ block_tot)
+{
+    __shared__ unsigned long long warp_tot[32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long k = (long long)blockIdx.x * 1024 + threadIdx.x;
+    unsigned long long sq = 0;
+    if (k <= n_jobs) joff[k] = raw[k] - r0;
+    if (k < n_jobs) {
+        const unsigned long long nj = (unsigned long long)(raw[k + 1] - raw[k]);
+        sq = nj * nj;
+    }
+    unsigned long long incl = sq;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long up = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) warp_tot[wib] = incl;
+    __syncthreads();
+    if (wib == 0) {
+        const unsigned long long t = warp_tot[lane];
+        unsigned long long ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long up = __shfl_up_sync(FULL, ti, d);
+            if (lane >= d) ti += up;
+        }
+        warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    const unsigned long long excl = warp_tot[wib] + incl - sq;
+    if (k <= n_jobs) ooff[k] = excl;
+    if (threadIdx.x == 1023) block_tot[blockIdx.x] = excl + sq;
+}
+
+__global__ void __launch_bounds__(1024) umi_rebase_add(unsigned long long *__restrict__ ooff, long long n_jobs,
+                                                        const unsigned long long *__restrict__ block_tot)
+{
+    const long long k = (long long)blockIdx.x * 1024 + threadIdx.x;
+    if (k <= n_jobs) ooff[k] += block_tot[blockIdx.x];
+}
+
 template <int L>
 __global__ void __launch_bounds__(PAIR_THREADS)
 umi_pairs_kernel(const uint8_t *__restrict__ umis, int stride, bool vec, const long long *__restrict__ job_offsets,
@@ -226,6 +272,19 @@ cudaError_t launch_pairs(const uint8_t *d_umis, int stride, bool vec, const long
 }
 
 }  // namespace
+
+size_t slr_umi_rebase_tmp_bytes(long long n_jobs) { return (size_t)((n_jobs + 1 + 1023) / 1024 + 1) * 8; }
+
+cudaError_t slr_launch_umi_rebase(const long long *d_raw, long long n_jobs, long long r0, long long *d_joff, long long *d_ooff, void *d_tmp,
+                                  cudaStream_t stream)
+{
+    const long long nb = (n_jobs + 1 + 1023) / 1024;
+    unsigned long long *block_tot = reinterpret_cast<unsigned long long *>(d_tmp);
+    umi_rebase_local<<<(unsigned)nb, 1024, 0, stream>>>(d_raw, n_jobs, r0, d_joff, reinterpret_cast<unsigned long long *>(d_ooff), block_tot);
+    umi_scan_blocks<<<1, 1024, 0, stream>>>(block_tot, nb);
+    umi_rebase_add<<<(unsigned)nb, 1024, 0, stream>>>(reinterpret_cast<unsigned long long *>(d_ooff), n_jobs, block_tot);
+    return cudaGetLastError();
+}
 
 size_t slr_umi_scratch_bytes(long long n_reads)
 {
