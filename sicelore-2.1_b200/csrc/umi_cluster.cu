@@ -32,7 +32,7 @@ __device__ __forceinline__ long long uc_job_of(const int32_t *__restrict__ rowjo
 
 constexpr int UC_BATCH = 8;          // matrix cells in flight per thread in the column walk
 constexpr int UC_SLICES = 8;         // warps per CTA of the deep kernels: rows in flight in pass 1, row slices per column tile in pass 2
-constexpr int UC_DEEP = 256;         // jobs with at least this many reads go to the deep kernels
+constexpr int UC_DEEP = 1024;        // jobs with at least this many reads go to the deep kernels
 constexpr int UC_LANE_ROW = 8;       // rows of at most this many cells (one 32-byte sector) are summed by a single lane in pass 1
 constexpr int UC_DEEP_BIT = 1 << 30; // counts[r]: the read belongs to a deep job (set by the flat kernel of pass 1)
 constexpr int UC_CNT_MASK = UC_DEEP_BIT - 1;

@@ -141,6 +141,31 @@ def test_gpu_cluster_member_subset_and_rank(pkg, orc, ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_cluster_deep_job_between_small_ones_with_member_and_rank(pkg, orc, ctx):
+    """the deep kernels (jobs of >= 1024 reads) with a member subset and a caller order, a deep job that starts and ends inside a
+    32-read tile shared with small jobs, and two deep jobs in one launch"""
+    rng = np.random.default_rng(11)
+    small, so = workloads.umi_jobs(5, 12, n_jobs=9, max_n=20)
+    deep1, _ = pkg.synth_umi_jobs(1, mean=1e9, cap=1500, seed=3)
+    deep2, _ = pkg.synth_umi_jobs(1, mean=1e9, cap=1100, seed=4)
+    k = int(so[4])
+    umis = np.concatenate([small[:k], deep1, small[k:], deep2])
+    sizes = np.concatenate([np.diff(so[:5]), [len(deep1)], np.diff(so[4:]), [len(deep2)]])
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    assert int(offs[4]) % 32 != 0 and int(offs[5]) % 32 != 0 and len(umis) == offs[-1] and offs[5] - offs[4] == len(deep1)
+    m = len(umis)
+    member = (rng.random(m) < 0.8).astype(np.uint8)
+    rank = np.concatenate([rng.permutation(int(n)) for n in sizes]).astype(np.int32)
+    mats, oo = orc.umi_matrix_batch(umis, offs, 12)
+    for ed in (1, 2):
+        for mem, rk in ((None, None), (member, None), (None, rank), (member, rank)):
+            want = orc.umi_cluster_batch(mats, offs, oo, ed, mem, rk)
+            got = pkg.cluster_local(ctx, umis, offs, ed, member=mem, rank=rk)
+            assert got.tobytes() == want.tobytes(), (ed, mem is not None, rk is not None)
+    assert (want["best_key"][offs[4]:offs[5]] >= 0).sum() > 500
+
+
+@pytest.mark.gpu
 def test_gpu_cluster_deep_job_and_many_ranges(pkg, orc, ctx):
     # one deep job (row loop over thousands of reads) and a batch large enough to be cut into several ranges
     umis, offs = pkg.synth_umi_jobs(1, mean=1e9, cap=3000, seed=8)
