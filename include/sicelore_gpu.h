@@ -200,6 +200,24 @@ int  slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t 
                          const uint8_t *d_member, const int32_t *d_rank, int32_t *d_counts,
                          slr_umi_cluster_rec *d_rec, void *stream);
 
+/* A session keeps the matrices of one batch of jobs on the device between calls.  clusterLocal's first maximum depends on the
+ * iteration order of the caller's map, ties are frequent (two reads that are each other's only neighbour already tie), and the
+ * keys of that map are known only after the neighbour counts: the practical protocol is  create  ->  cluster(rank = NULL)  ->
+ * the caller fills its map with the keys (n_neighbours > 1) and reads their iteration ranks  ->  cluster(rank)  [-> cluster(member,
+ * rank) for the re-clustering call]  ->  matrices (when the distances are needed on the host)  ->  destroy, with the distance kernels run once.
+ *   create     umis / stride / umi_len / job_offsets / n_jobs as slr_umi_dist; uploads the reads and computes every matrix
+ *   cluster    as slr_umi_cluster on the resident matrices; callable any number of times
+ *   matrices   copies the matrices back, packed back to back in job order (job j at sum of n_k^2 over k < j)
+ * Device memory: 4 bytes per matrix cell + 61 bytes per read; a batch that does not fit fails with SLR_E_NOMEM (split it). */
+typedef struct slr_umi_session slr_umi_session;
+int  slr_umi_session_create(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets,
+                            int64_t n_jobs, slr_umi_session **out);
+int  slr_umi_session_cluster(slr_umi_session *s, int ed, const uint8_t *member, const int32_t *rank,
+                             slr_umi_cluster_rec *rec);
+int  slr_umi_session_matrices(slr_umi_session *s, int32_t *out, int64_t n_cells);
+int64_t slr_umi_session_cells(const slr_umi_session *s);
+void slr_umi_session_destroy(slr_umi_session *s);
+
 /* ---- S4: Illumina-guided barcode / UMI search ------------------------------------------------- */
 
 /* Replaces, for a batch of reads, the offset loop of IlluminaUMIanalyzer.findUMI (F!com/rw/umifinder/analyzers/

@@ -36,6 +36,14 @@ public final class Native {
      *  {|N(c)|, chosen entry or -1, |N(entry)|, entries tied for the maximum}; member / rank / out / outOffsets nullable */
     public static native int umiCluster(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, int ed,
                                         ByteBuffer member, ByteBuffer rank, ByteBuffer out, ByteBuffer outOffsets, ByteBuffer rec);
+    /** the same with the matrices kept on the device between calls: create (distance kernels run once), cluster with rank = null, fill the
+     *  map with the keys, cluster again with their iteration ranks (and once more with the unclustered reads as member), fetch the matrices
+     *  if the distances are needed, destroy  (0 = failed) */
+    public static native long umiSessionCreate(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs);
+    public static native int umiSessionCluster(long session, int ed, ByteBuffer member, ByteBuffer rank, ByteBuffer rec);
+    public static native long umiSessionCells(long session);
+    public static native int umiSessionMatrices(long session, ByteBuffer out, long nCells);
+    public static native void umiSessionDestroy(long session);
     /** candidate sets of the Illumina-guided search: groupKeys / groupOffsets = CSR of the per-(gene, cell) UMIs (IlluminaOneGeneOneCellData) or of the
      *  per-gene cell barcodes (BarcodesMap); allKeys = All10xselectedCells, emptyKeys = EmptyDropBarcodes (BC flavour, nullable)  (0 = failed) */
     public static native long guidedSetsCreate(long ctx, long[] groupKeys, long[] groupOffsets, long[] allKeys, int allEd, long[] emptyKeys,

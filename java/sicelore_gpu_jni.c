@@ -109,6 +109,42 @@ JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_umiCluster(JNIEnv *env, jclass cls
                            out ? (int32_t *)BUF(out) : NULL, outOffsets ? (const int64_t *)BUF(outOffsets) : NULL, (slr_umi_cluster_rec *)BUF(rec));
 }
 
+JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_umiSessionCreate(JNIEnv *env, jclass cls, jlong ctx, jobject umis, jint stride, jint umiLen,
+                                                                jobject jobOffsets, jlong nJobs)
+{
+    (void)cls;
+    slr_umi_session *s = NULL;
+    const int rc = slr_umi_session_create((slr_ctx *)(size_t)ctx, (const uint8_t *)BUF(umis), stride, umiLen, (const int64_t *)BUF(jobOffsets),
+                                          (int64_t)nJobs, &s);
+    return rc == SLR_OK ? (jlong)(size_t)s : 0;
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_umiSessionCluster(JNIEnv *env, jclass cls, jlong session, jint ed, jobject member, jobject rank,
+                                                                jobject rec)
+{
+    (void)cls;
+    return slr_umi_session_cluster((slr_umi_session *)(size_t)session, ed, member ? (const uint8_t *)BUF(member) : NULL,
+                                   rank ? (const int32_t *)BUF(rank) : NULL, (slr_umi_cluster_rec *)BUF(rec));
+}
+
+JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_umiSessionCells(JNIEnv *env, jclass cls, jlong session)
+{
+    (void)env; (void)cls;
+    return (jlong)slr_umi_session_cells((const slr_umi_session *)(size_t)session);
+}
+
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_umiSessionMatrices(JNIEnv *env, jclass cls, jlong session, jobject out, jlong nCells)
+{
+    (void)cls;
+    return slr_umi_session_matrices((slr_umi_session *)(size_t)session, (int32_t *)BUF(out), (int64_t)nCells);
+}
+
+JNIEXPORT void JNICALL Java_com_rw_gpu_Native_umiSessionDestroy(JNIEnv *env, jclass cls, jlong session)
+{
+    (void)env; (void)cls;
+    slr_umi_session_destroy((slr_umi_session *)(size_t)session);
+}
+
 JNIEXPORT jlong JNICALL Java_com_rw_gpu_Native_guidedSetsCreate(JNIEnv *env, jclass cls, jlong ctx, jlongArray groupKeys, jlongArray groupOffsets,
                                                                 jlongArray allKeys, jint allEd, jlongArray emptyKeys, jint emptyEd,
                                                                 jboolean bcFlavour, jint seqLen)

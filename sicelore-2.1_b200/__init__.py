@@ -45,7 +45,8 @@ assert GUIDED_HIT.itemsize == 16
 
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
-           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
+           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_umi_session_create", "slr_umi_session_cluster",
+           "slr_umi_session_matrices", "slr_umi_session_cells", "slr_umi_session_destroy", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
            "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count"]
 
 
@@ -122,6 +123,13 @@ def gpu_lib():
         L.slr_umi_dist_dev.argtypes = [vp, vp, i32, i32, vp, i64, i64, vp, vp, i64, vp]
         L.slr_umi_cluster.argtypes = [vp, vp, i32, i32, vp, i64, i32, vp, vp, vp, vp, vp]
         L.slr_umi_cluster_dev.argtypes = [vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
+        L.slr_umi_session_create.argtypes = [vp, vp, i32, i32, vp, i64, C.POINTER(vp)]
+        L.slr_umi_session_cluster.argtypes = [vp, i32, vp, vp, vp]
+        L.slr_umi_session_matrices.argtypes = [vp, vp, i64]
+        L.slr_umi_session_cells.argtypes = [vp]
+        L.slr_umi_session_cells.restype = i64
+        L.slr_umi_session_destroy.argtypes = [vp]
+        L.slr_umi_session_destroy.restype = None
         L.slr_guided_sets_create.argtypes = [vp, vp, vp, i64, vp, i64, i32, vp, i64, i32, i32, i32, C.POINTER(vp)]
         L.slr_guided_sets_destroy.argtypes = [vp]
         L.slr_guided_sets_destroy.restype = None
@@ -590,6 +598,50 @@ def cluster_local(ctx, umis, job_offsets, ed, umi_len=12, member=None, rank=None
                                      out.ctypes.data if out is not None else None,
                                      out_offsets.ctypes.data if out_offsets is not None else None, rec.ctypes.data))
     return (rec, out, out_offsets) if want_matrices else rec
+
+
+class UmiSession:
+    """The matrices of one batch of (cell, region) jobs kept on the device between calls (slr_umi_session_*): the distance kernels run
+    once, cluster() can then be called with the caller's key order (`rank`) once the keys are known, and again on the unclustered
+    subset (`member`) like ClusterOne_MyClustering.call does (…java:L73, L107)."""
+
+    def __init__(self, ctx, umis, job_offsets, umi_len=12):
+        umis = np.ascontiguousarray(umis, dtype=np.uint8)
+        self.job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+        self.n_reads = int(self.job_offsets[-1] - self.job_offsets[0]) if len(self.job_offsets) else 0
+        h = C.c_void_p()
+        _check(gpu_lib().slr_umi_session_create(ctx.h, umis.ctypes.data, umis.shape[1] if umis.ndim == 2 else 16, umi_len,
+                                                self.job_offsets.ctypes.data, max(0, len(self.job_offsets) - 1), C.byref(h)))
+        self.h = h
+
+    def cluster(self, ed, member=None, rank=None):
+        rec = np.zeros(self.n_reads, dtype=UMI_CLUSTER_REC)
+        if member is not None:
+            member = np.ascontiguousarray(member, dtype=np.uint8)
+            assert member.shape == (self.n_reads,)
+        if rank is not None:
+            rank = np.ascontiguousarray(rank, dtype=np.int32)
+            assert rank.shape == (self.n_reads,)
+        _check(gpu_lib().slr_umi_session_cluster(self.h, int(ed), member.ctypes.data if member is not None else None,
+                                                 rank.ctypes.data if rank is not None else None, rec.ctypes.data))
+        return rec
+
+    def matrices(self):
+        cells = int(gpu_lib().slr_umi_session_cells(self.h))
+        out = np.empty(cells, dtype=np.int32)
+        _check(gpu_lib().slr_umi_session_matrices(self.h, out.ctypes.data, cells))
+        return out, out_offsets_for(self.job_offsets)
+
+    def close(self):
+        if self.h:
+            gpu_lib().slr_umi_session_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def clusters_from_records(rec, job_offsets):

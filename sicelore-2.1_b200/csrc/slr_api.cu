@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <memory>
 #include <vector>
 #include "slr_kernels.h"
 #include "slr_table_build.h"
@@ -80,7 +81,11 @@ struct slr_ctx {
     int n_slots = 1;
     std::vector<Slot *> slots;
     std::atomic<unsigned> next{0};
+    std::mutex pool_mtx;                       // device buffers of destroyed UMI sessions, reused by the next one (cudaMalloc / cudaFree of
+    std::vector<struct slr_umi_session *> session_pool;   // several GB cost more than the kernels)
 };
+
+static void free_session_pool(slr_ctx *c);     // defined with slr_umi_session below
 
 struct slr_bc_table {
     slr_ctx *ctx = nullptr;
@@ -148,6 +153,7 @@ void slr_ctx_destroy(slr_ctx *c)
         s->gsl.release(); s->ganc.release(); s->ggid.release(); s->ged.release(); s->gout.release(); s->graw.release(); s->gvis.release();
         delete s;
     }
+    free_session_pool(c);
     cudaFree(c->d_work);
     delete c;
 }
@@ -554,6 +560,129 @@ int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *
                                     d_member, d_rank, nullptr, d_counts, d_rec, ctx->work_pair(), (cudaStream_t)stream));
     g_launches += SLR_UMI_CLUSTER_LAUNCHES;
     return SLR_OK;
+}
+
+}  // extern "C"
+
+// ---- UMI session: the matrices of one batch stay on the device between the cluster calls ----------------------------------
+struct slr_umi_session {
+    slr_ctx *ctx = nullptr;
+    int64_t n_jobs = 0, n_reads = 0, cells = 0;
+    DevBuf umis, jraw, jtmp, joff, ooff, mat, scr, counts, rec, rank, member;
+    void release()
+    {
+        umis.release(); jraw.release(); jtmp.release(); joff.release(); ooff.release(); mat.release(); scr.release(); counts.release();
+        rec.release(); rank.release(); member.release();
+    }
+    ~slr_umi_session() { release(); }
+};
+constexpr size_t SESSION_POOL = 2;             // sessions whose buffers a context keeps for reuse
+
+static void free_session_pool(slr_ctx *c)
+{
+    std::lock_guard<std::mutex> lk(c->pool_mtx);
+    for (slr_umi_session *p : c->session_pool) delete p;
+    c->session_pool.clear();
+}
+
+extern "C" {
+
+int slr_umi_session_create(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
+                           slr_umi_session **out)
+{
+    if (!out) return fail(SLR_E_INVALID, "slr_umi_session_create: out is NULL");
+    *out = nullptr;
+    int rc = check_umi_args(ctx, stride, umi_len, n_jobs);
+    if (rc) return rc;
+    if (n_jobs > 0 && (!umis || !job_offsets)) return fail(SLR_E_INVALID, "slr_umi_session_create: NULL buffer");
+    int64_t bad = 0;
+    for (int64_t k = 0; k < n_jobs; k++) bad |= job_offsets[k + 1] - job_offsets[k];       // the sign bit survives the OR
+    if (bad < 0) return fail(SLR_E_INVALID, "job_offsets not monotone");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::unique_ptr<slr_umi_session> S;
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mtx);
+        if (!ctx->session_pool.empty()) { S.reset(ctx->session_pool.back()); ctx->session_pool.pop_back(); }
+    }
+    if (!S) S.reset(new slr_umi_session());
+    S->ctx = ctx; S->n_jobs = n_jobs; S->cells = 0;
+    const int64_t r0 = n_jobs > 0 ? job_offsets[0] : 0;
+    S->n_reads = n_jobs > 0 ? job_offsets[n_jobs] - r0 : 0;
+    if (S->n_reads > 0) {
+        Slot *sl = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+        std::lock_guard<std::mutex> lock(sl->mtx);
+        cudaStream_t st = sl->stream[0];
+        const size_t off_bytes = (size_t)(n_jobs + 1) * 8, m = (size_t)S->n_reads;
+        if ((rc = S->umis.reserve(m * stride)) || (rc = S->jraw.reserve(off_bytes)) || (rc = S->jtmp.reserve(slr_umi_rebase_tmp_bytes(n_jobs))) ||
+            (rc = S->joff.reserve(off_bytes)) || (rc = S->ooff.reserve(off_bytes)) || (rc = S->scr.reserve(slr_umi_scratch_bytes(S->n_reads))) ||
+            (rc = S->counts.reserve(m * 4)) || (rc = S->rec.reserve(m * 16)) || (rc = S->rank.reserve(m * 4)) || (rc = S->member.reserve(m)))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(S->umis.p, umis + r0 * stride, m * stride, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(S->jraw.p, job_offsets, off_bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(slr_launch_umi_rebase((const long long *)S->jraw.p, n_jobs, r0, (long long *)S->joff.p, (long long *)S->ooff.p, S->jtmp.p, st));
+        g_launches += SLR_UMI_REBASE_LAUNCHES;
+        long long cells = 0;
+        CUDA_TRY(cudaMemcpyAsync(&cells, (const long long *)S->ooff.p + n_jobs, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        S->cells = cells;
+        if ((rc = S->mat.reserve((size_t)cells * 4 + 4))) return rc;
+        CUDA_TRY(slr_launch_umi_dist((const uint8_t *)S->umis.p, stride, umi_len, (const long long *)S->joff.p, n_jobs, S->n_reads,
+                                     (int32_t *)S->mat.p, (const long long *)S->ooff.p, S->scr.p, st));
+        g_launches += SLR_UMI_LAUNCHES;
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    *out = S.release();
+    return SLR_OK;
+}
+
+int slr_umi_session_cluster(slr_umi_session *S, int ed, const uint8_t *member, const int32_t *rank, slr_umi_cluster_rec *rec)
+{
+    if (!S) return fail(SLR_E_INVALID, "slr_umi_session_cluster: session is NULL");
+    if (ed < 0 || ed > 5) return fail(SLR_E_INVALID, "slr_umi_session_cluster: ed %d outside 0..5", ed);
+    if (S->n_reads == 0) return SLR_OK;
+    if (!rec) return fail(SLR_E_INVALID, "slr_umi_session_cluster: rec is NULL");
+    slr_ctx *ctx = S->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Slot *sl = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(sl->mtx);
+    cudaStream_t st = sl->stream[0];
+    const size_t m = (size_t)S->n_reads;
+    if (rank) CUDA_TRY(cudaMemcpyAsync(S->rank.p, rank, m * 4, cudaMemcpyHostToDevice, st));
+    if (member) CUDA_TRY(cudaMemcpyAsync(S->member.p, member, m, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(slr_launch_umi_cluster((const int32_t *)S->mat.p, (const long long *)S->joff.p, (const long long *)S->ooff.p, S->n_jobs, S->n_reads,
+                                    ed, member ? (const uint8_t *)S->member.p : nullptr, rank ? (const int32_t *)S->rank.p : nullptr,
+                                    slr_umi_scratch_rowjob(S->scr.p, S->n_reads), (int32_t *)S->counts.p, (slr_umi_cluster_rec *)S->rec.p,
+                                    ctx->work_pair(), st));
+    g_launches += SLR_UMI_CLUSTER_LAUNCHES;
+    CUDA_TRY(cudaMemcpyAsync(rec, S->rec.p, m * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SLR_OK;
+}
+
+int slr_umi_session_matrices(slr_umi_session *S, int32_t *out, int64_t n_cells)
+{
+    if (!S) return fail(SLR_E_INVALID, "slr_umi_session_matrices: session is NULL");
+    if (n_cells != S->cells) return fail(SLR_E_INVALID, "slr_umi_session_matrices: %lld cells asked, the session holds %lld", (long long)n_cells,
+                                         (long long)S->cells);
+    if (S->cells == 0) return SLR_OK;
+    if (!out) return fail(SLR_E_INVALID, "slr_umi_session_matrices: out is NULL");
+    CUDA_TRY(cudaSetDevice(S->ctx->device));
+    CUDA_TRY(cudaMemcpy(out, S->mat.p, (size_t)S->cells * 4, cudaMemcpyDeviceToHost));
+    return SLR_OK;
+}
+
+int64_t slr_umi_session_cells(const slr_umi_session *S) { return S ? S->cells : 0; }
+
+void slr_umi_session_destroy(slr_umi_session *S)
+{
+    if (!S) return;
+    slr_ctx *ctx = S->ctx;
+    cudaSetDevice(ctx->device);
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mtx);
+        if (ctx->session_pool.size() < SESSION_POOL) { ctx->session_pool.push_back(S); return; }
+    }
+    delete S;
 }
 
 }  // extern "C"

@@ -209,3 +209,40 @@ def test_gpu_cluster_dev_entry_and_refusals(pkg, orc, ctx):
     with pytest.raises(pkg.SiceloreGpuError):
         pkg.cluster_local(ctx, umis, offs, 2, umi_len=15)
     assert len(pkg.cluster_local(ctx, np.zeros((0, 16), np.uint8), np.zeros(1, np.int64), 2)) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_session_two_call_protocol(pkg, orc, ctx):
+    """create -> cluster(rank = None) -> the caller derives the iteration rank of the keys -> cluster(rank) -> cluster(member, rank)
+    -> matrices, all on the matrices of ONE run of the distance kernels"""
+    rng = np.random.default_rng(3)
+    umis, offs = workloads.umi_jobs(123, 12, n_jobs=200, max_n=70)
+    deep, _ = pkg.synth_umi_jobs(1, mean=1e9, cap=1300, seed=6)
+    umis = np.concatenate([umis, deep])
+    offs = np.concatenate([offs, [offs[-1] + len(deep)]]).astype(np.int64)
+    mats, oo = orc.umi_matrix_batch(umis, offs, 12)
+    l0 = pkg.launch_count()
+    with pkg.UmiSession(ctx, umis, offs) as s:
+        first = s.cluster(2)
+        assert first.tobytes() == orc.umi_cluster_batch(mats, offs, oo, 2).tobytes()
+        rank = np.full(len(umis), 2 ** 30, dtype=np.int32)             # the caller's map: here the restated fastutil order of the keys
+        for j in range(len(offs) - 1):
+            a, b = int(offs[j]), int(offs[j + 1])
+            keys = [i for i in range(b - a) if first["n_neighbours"][a + i] > 1]
+            for r, k in enumerate(pyref.fastutil_key_order(keys)):
+                rank[a + k] = r
+        second = s.cluster(2, rank=rank)
+        want = orc.umi_cluster_batch(mats, offs, oo, 2, None, rank)
+        assert second.tobytes() == want.tobytes()
+        assert (second["best_key"] != first["best_key"]).any()         # the order did change some choices
+        member = (rng.random(len(umis)) < 0.5).astype(np.uint8)
+        third = s.cluster(2, member=member, rank=rank)
+        assert third.tobytes() == orc.umi_cluster_batch(mats, offs, oo, 2, member, rank).tobytes()
+        got_m, got_oo = s.matrices()
+        assert np.array_equal(got_m, mats) and np.array_equal(got_oo, oo)
+    # distance kernels once (3 + 3 launches), cluster kernels three times (4 each)
+    assert pkg.launch_count() - l0 == 6 + 3 * 4
+    with pkg.UmiSession(ctx, np.zeros((0, 16), np.uint8), np.zeros(1, np.int64)) as s:
+        assert len(s.cluster(2)) == 0 and len(s.matrices()[0]) == 0
+    with pytest.raises(pkg.SiceloreGpuError):
+        pkg.UmiSession(ctx, umis, offs[::-1].copy())

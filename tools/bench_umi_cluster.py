@@ -87,7 +87,30 @@ for key, wm in (("e2e", True), ("e2e_records_only", False)):
     t = (time.perf_counter() - t0) / a.steps
     e2e[key] = {"value": m / t, "unit": "reads/s", "ms_per_step": t * 1e3, "h2d_bytes_per_step": m * 16 + (n_jobs + 1) * 8,
                 "d2h_bytes_per_step": m * 16 + (cells * 4 if wm else 0)}
-same_e2e = bool(np.array_equal(h_rec.numpy().view(pkg.UMI_CLUSTER_REC).reshape(m), rec_dev))
+# the two-call protocol of a session: distance kernels once, cluster without and then with the caller's key order (a stand-in order here)
+h_rank = pin((np.arange(m, dtype=np.int64) - np.repeat(offs[:-1], np.diff(offs))).astype(np.int32)[::1].copy())
+h_rec2 = torch.empty(m * 4, dtype=torch.int32).pin_memory()
+import ctypes as C
+
+
+def step_session():
+    h = C.c_void_p()
+    pkg._check(lib.slr_umi_session_create(ctx.h, h_u.data_ptr(), 16, 12, h_o.data_ptr(), n_jobs, C.byref(h)))
+    pkg._check(lib.slr_umi_session_cluster(h, a.ed, None, None, h_rec2.data_ptr()))
+    pkg._check(lib.slr_umi_session_cluster(h, a.ed, None, h_rank.data_ptr(), h_rec2.data_ptr()))
+    lib.slr_umi_session_destroy(h)
+
+
+for _ in range(2):
+    step_session()
+t0 = time.perf_counter()
+for _ in range(a.steps):
+    step_session()
+t = (time.perf_counter() - t0) / a.steps
+e2e["e2e_session_two_cluster_calls"] = {"value": m / t, "unit": "reads/s", "ms_per_step": t * 1e3, "h2d_bytes_per_step": m * 20 + (n_jobs + 1) * 8,
+                                        "d2h_bytes_per_step": m * 32}
+same_session = bool(np.array_equal(h_rec2.numpy().view(pkg.UMI_CLUSTER_REC).reshape(m), rec_dev))     # ascending rank = no rank
+same_e2e = same_session and bool(np.array_equal(h_rec.numpy().view(pkg.UMI_CLUSTER_REC).reshape(m), rec_dev))
 
 # CPU oracle on a bounded sample of the same jobs (all host threads): matrices + clusterLocal's two passes
 js = min(a.cpu_jobs, a.jobs)
@@ -109,7 +132,8 @@ print(json.dumps({
                            "(%.1f GB, larger than L2), 12-nt UMIs +-1" % (a.jobs, a.deep, m, cells, cells * 4 / 1e9)},
     "clocks": clocks, "gpu_launches": int(launches), "ms_distance_kernels": ms_dist, "ms_cluster_kernels": ms - ms_dist,
     "pairs_per_s": pairs / (ms_dist / 1e3), "keys_fraction": float((rec_dev["best_key"] >= 0).mean()),
-    "e2e": e2e["e2e"], "e2e_records_only": e2e["e2e_records_only"], "e2e_matches_device": same_e2e,
+    "e2e": e2e["e2e"], "e2e_records_only": e2e["e2e_records_only"], "e2e_session_two_cluster_calls": e2e["e2e_session_two_cluster_calls"],
+    "e2e_matches_device": same_e2e,
     "cpu_baseline": {"value": ms_ / tcpu, "unit": "reads/s", "cores": os.cpu_count(), "kind": "port",
                      "sample": "first %d jobs (%d reads) of the batch, CPU oracle (orc_umi_matrix_batch + orc_umi_cluster_batch, OpenMP over jobs)" % (js, ms_),
                      "gpu_matches_oracle_on_sample": same},
