@@ -50,13 +50,40 @@ __device__ __forceinline__ UcJob uc_lookup(const int32_t *__restrict__ rowjob, c
     return J;
 }
 
-// one matrix row walked by a whole warp
+// cells [b, n) of a row, at most 32 * NB of them: one predicated batch, all loads issued before the first use
+template <int NB>
+__device__ __forceinline__ int uc_row_tail(const int32_t *__restrict__ row, long long r0, long long b, long long n, int ed,
+                                           const uint8_t *__restrict__ member, int lane)
+{
+    int32_t cell[NB];
+    bool mv[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        const long long v = b + 32 * k + lane;
+        const bool ok = v < n;
+        cell[k] = ok ? row[v] : 0x7f;
+        mv[k] = ok && (!member || member[r0 + v]);
+    }
+    int part = 0;
+#pragma unroll
+    for (int k = 0; k < NB; k++) part += mv[k] && uc_ed(cell[k]) <= ed;
+    return part;
+}
+
+// one matrix row walked by a whole warp: full batches of 32 * UC_BATCH cells, then one predicated batch for the rest
 __device__ __forceinline__ int uc_row_count(const int32_t *__restrict__ row, long long r0, long long n, int ed,
                                             const uint8_t *__restrict__ member, int lane)
 {
     int part = 0;
-#pragma unroll 8
-    for (long long v = lane; v < n; v += 32) part += (!member || member[r0 + v]) && uc_ed(row[v]) <= ed;
+    long long b = 0;
+    for (; b + 32 * UC_BATCH <= n; b += 32 * UC_BATCH) {
+        int32_t cell[UC_BATCH];
+#pragma unroll
+        for (int k = 0; k < UC_BATCH; k++) cell[k] = row[b + 32 * k + lane];
+#pragma unroll
+        for (int k = 0; k < UC_BATCH; k++) part += (!member || member[r0 + b + 32 * k + lane]) && uc_ed(cell[k]) <= ed;
+    }
+    if (b < n) part += n - b <= 64 ? uc_row_tail<2>(row, r0, b, n, ed, member, lane) : uc_row_tail<UC_BATCH>(row, r0, b, n, ed, member, lane);
     return __reduce_add_sync(0xffffffffu, part);
 }
 
