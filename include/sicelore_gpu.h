@@ -58,7 +58,9 @@ typedef struct {
 /* Replaces nothing in the reference (there is no device there); the JNI shim calls it once from
  * WorkerReadscanner's constructor (F!…/WorkerReadscanner.class, WorkerReadscanner.java:L186-L190), where the
  * reference creates its two work-stealing pools.  device < 0 selects the current device.  n_streams = how
- * many host threads may have a batch in flight at once (the reference's nCPU Parser workers). */
+ * many host threads may have a batch in flight at once (the reference's nCPU Parser workers).
+ * The library contains sm_100a code only: a device of any other compute capability is refused with SLR_E_UNSUPPORTED.
+ * Tables, candidate sets and sessions belong to the context they were created with; passing them to another context is SLR_E_INVALID. */
 int  slr_ctx_create(int device, int n_streams, slr_ctx **out);
 void slr_ctx_destroy(slr_ctx *ctx);
 int  slr_ctx_device(const slr_ctx *ctx);
@@ -103,7 +105,9 @@ int  slr_bc_assign_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plus
  * BarcodeCounts.addCountForEd) that feed BarcodesAssigned.tsv: the table accumulates, on the device, one
  * counter per (barcode index, ED 0..2) for every assigned read of every slr_bc_assign* call.
  * counts_out: n_barcodes * 3 int64 (host).  slr_bc_counts_device returns the device buffer itself so that
- * a multi-GPU driver can all-reduce it (NCCL) before reading it back. */
+ * a multi-GPU driver can all-reduce it (NCCL) before reading it back.
+ * slr_bc_counts_read is ordered behind every host-pointer call issued on this context before it (no device-wide synchronisation);
+ * launches of the *_dev entry points run on the caller's streams, which the caller synchronises first. */
 int  slr_bc_counts_read(slr_ctx *ctx, const slr_bc_table *t, int64_t *counts_out);
 int  slr_bc_counts_reset(slr_ctx *ctx, slr_bc_table *t);
 int  slr_bc_counts_device(const slr_bc_table *t, int64_t **d_counts, int64_t *n_elems);
@@ -155,7 +159,7 @@ int  slr_bc_collide_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const u
  *   umis        m * stride bytes; per read umi_len+2 4-bit codes (A=1 G=2 C=4 T=8 N=15 ...,
  *               NucleicAcidByteCodeBase.java:L45-L78) = getSubSequence(bcEnd, umi_len+2) of the strand-corrected
  *               X= mini sequence, i.e. the predicted UMI window widened by one base on each side
- *   umi_len     config.xml:264 umi_length (<= 30)
+ *   umi_len     config.xml:264 umi_length, 1..14 (the nine comparisons of a pair run on one 32-bit word; longer UMIs: SLR_E_UNSUPPORTED)
  *   job_offsets n_jobs+1 CSR offsets into the reads
  *   out_offsets n_jobs+1 offsets into `out`; job j writes an n_j x n_j row-major int32 matrix at out_offsets[j]
  *               (diagonal = the reference's equalityEditDistance, lower triangle = transposed copy) */

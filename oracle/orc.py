@@ -29,7 +29,7 @@ class Match(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "liborc.so")
-    src = [os.path.join(_HERE, f) for f in ("slr_oracle.c", "slr_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("slr_oracle.c", "slr_oracle_assign.c", "slr_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -186,6 +186,40 @@ def umi_cluster_batch(matrices, job_offsets, out_offsets, ed, member=None, rank=
     L.orc_umi_cluster_batch(matrices.ctypes.data, job_offsets.ctypes.data, out_offsets.ctypes.data, len(job_offsets) - 1, int(ed),
                             member.ctypes.data if member is not None else None, rank.ctypes.data if rank is not None else None,
                             rec.ctypes.data, n_threads)
+    return rec
+
+
+# ---- clustering + UMI assignment of a job (ClusterOneHierarchical.call, slr_oracle_assign.c) ---------------------------------------
+ASSIGN_REC = np.dtype([("center", "<i4"), ("u1", "i1"), ("u2", "i1"), ("pos2", "i1"), ("off_mean", "i1"), ("flags", "<u2"),
+                       ("cluster_size", "<u2"), ("n_clusters", "<i4")], align=True)
+assert ASSIGN_REC.itemsize == 16
+UA_ASSIGNED, UA_SKIPPED, UA_TIE_UNPIN, UA_DEEP = 1, 2, 4, 8
+
+
+class AssignParams(C.Structure):
+    """config.xml:270-278 + UMIparameters defaults: complete-link ED 2, single-link ED 1, switch above 3000 reads with a neighbour,
+    foldDepthBelowMaxDiscardForClustering 50, ClusterOneHierarchical up to 100 reads"""
+    _fields_ = [("ed_complete", C.c_int32), ("ed_single", C.c_int32), ("single_threshold", C.c_int32), ("fold_depth", C.c_int32),
+                ("max_hier", C.c_int32)]
+
+    def __init__(self, ed_complete=2, ed_single=1, single_threshold=3000, fold_depth=50, max_hier=100):
+        super().__init__(ed_complete, ed_single, single_threshold, fold_depth, max_hier)
+
+
+def umi_assign_batch(matrices, job_offsets, out_offsets, params=None, job_qv01=None, n_threads=0):
+    """orc_umi_assign_batch: ClusterOneHierarchical.call for every job of at most params.max_hier reads -> ASSIGN_REC per read."""
+    matrices = np.ascontiguousarray(matrices, dtype=np.int32)
+    job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+    out_offsets = np.ascontiguousarray(out_offsets, dtype=np.int64)
+    params = params or AssignParams()
+    m = int(job_offsets[-1]) if len(job_offsets) else 0
+    rec = np.zeros(m, dtype=ASSIGN_REC)
+    qv = None if job_qv01 is None else np.ascontiguousarray(job_qv01, dtype=np.uint8)
+    L = lib()
+    L.orc_umi_assign_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_umi_assign_batch.restype = None
+    L.orc_umi_assign_batch(matrices.ctypes.data, job_offsets.ctypes.data, out_offsets.ctypes.data, len(job_offsets) - 1, C.byref(params),
+                           None if qv is None else qv.ctypes.data, rec.ctypes.data, n_threads)
     return rec
 
 

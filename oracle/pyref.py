@@ -693,3 +693,246 @@ def cluster_local(matrix, indices, ed, key_order=None):
     if not id_map:                                                               # L219
         return None
     return {frozenset(v) for v in id_map.values()}
+
+
+# ---- ClusterOneHierarchical.call: LingPipe complete / single link + centres + per-read values ------------------------------------------
+# Second, object-for-object restatement (the C oracle works on index arrays): F!…/clustering/ClusterOneHierarchical.java:L61-L217,
+# A!com/aliasi/cluster/{CompleteLinkClusterer (L146-L237), SingleLinkClusterer (L198-L268), Dendrogram (L205-L215), LinkDendrogram},
+# A!com/aliasi/util/{BoundedPriorityQueue (L131-L153, L342-L346, L458-L464), ObjectToSet}, F!com/rw/clustering/{DistanceMatrix, OneUmiCluster}.
+class _JInt:
+    """java.lang.Integer as a HashSet element"""
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = int(v)
+
+    def jhash(self):
+        return self.v
+
+    def jequals(self, o):
+        return self.v == o.v
+
+
+def jdk_int_set(values_in_insertion_order):
+    """iteration order of a java.util.HashSet<Integer> filled by add() in the given order"""
+    hs = JHashSet()
+    for v in values_in_insertion_order:
+        hs.add(_JInt(v))
+    return [e.v for e in hs]
+
+
+def fastutil_intset_order(keys_in_insertion_order):
+    """fastutil IntOpenHashSet (OneUmiCluster's superclass): same open-addressing layout as Int2ObjectOpenHashMap"""
+    return fastutil_key_order(keys_in_insertion_order)
+
+
+class _Dendro:
+    def __init__(self, left=None, right=None, score=0.0, obj=None):
+        self.left, self.right, self.score, self.obj, self.parent = left, right, float(score), obj, None
+        if left is not None:
+            left.parent = self
+            right.parent = self
+
+    def dereference(self):                                     # Dendrogram.dereference
+        d = self
+        while d.parent is not None:
+            d = d.parent
+        return d
+
+    def member_list(self):                                     # addMembers: dendrogram1 first, then dendrogram2; into a HashSet
+        if self.left is None:
+            return [self.obj]
+        return self.left.member_list() + self.right.member_list()
+
+    def partition_distance(self, max_distance):                # Dendrogram.java:L205-L215 (stack via addFirst / removeFirst)
+        out, stack = [], [self]
+        while stack:
+            cur = stack.pop(0)
+            if cur.score <= max_distance:
+                out.append(jdk_int_set(cur.member_list()))     # memberSet(): new HashSet + addMembers
+            elif cur.left is not None:
+                stack.insert(0, cur.left)
+                stack.insert(0, cur.right)
+        return out
+
+
+class _Pair:
+    __slots__ = ("d1", "d2", "score", "entry_id", "step")
+
+    def __init__(self, d1, d2, score):
+        self.d1, self.d2, self.score, self.entry_id, self.step = d1, d2, float(score), None, 0
+
+
+class _Queue:
+    """BoundedPriorityQueue(ScoredObject.reverseComparator(), MAX): a TreeSet ordered by EntryComparator — ascending score, among equal
+    scores the entry offered LAST comes first"""
+
+    def __init__(self):
+        self.items, self.next_id = [], 0
+
+    def offer(self, p):
+        p.entry_id = self.next_id
+        self.next_id += 1
+        self.items.append(p)
+
+    def poll(self):
+        if not self.items:
+            return None
+        best = min(self.items, key=lambda p: (p.score, -p.entry_id))
+        self.items.remove(best)
+        return best
+
+    def remove_all(self, ps):
+        s = set(id(p) for p in ps)
+        self.items = [p for p in self.items if id(p) not in s]
+
+
+def complete_link(m, distance, max_distance=float("inf"), stop_above=None):
+    """CompleteLinkClusterer.hierarchicalCluster over elements 0..m-1.  Returns (root or forest roots, tie_seen).  ObjectToSet's HashSet<PairScore>
+    iterates in identity-hash order in the JVM; here: insertion order (Python dicts), the canonical order of oracle and GPU kernel.
+    stop_above: stop once the cheapest pair costs more (the links above the cut do not change partitionDistance(stop_above))."""
+    leafs = [_Dendro(obj=i) for i in range(m)]
+    if m == 1:
+        return [leafs[0]], False
+    queue, index = _Queue(), {}
+    for i in range(m):
+        for j in range(i + 1, m):
+            ps = _Pair(leafs[i], leafs[j], distance(i, j))
+            queue.offer(ps)
+            index.setdefault(leafs[i], {})[ps] = None
+            index.setdefault(leafs[j], {})[ps] = None
+    tie_seen, step, last = False, 0, None
+    while queue.items:
+        nxt = queue.poll()
+        if stop_above is not None and nxt.score > stop_above:
+            queue.items.append(nxt)
+            break
+        if nxt.step > 0 and any(p.score == nxt.score and p.step == nxt.step for p in queue.items):
+            tie_seen = True
+        step += 1
+        d1, d2 = nxt.d1.dereference(), nxt.d2.dereference()
+        d12 = _Dendro(d1, d2, nxt.score)
+        last = d12
+        buf = {}
+        ps3set = index.pop(d1)
+        queue.remove_all(ps3set)
+        for ps3 in ps3set:
+            d3 = ps3.d2 if ps3.d1 is d1 else ps3.d1
+            index[d3].pop(ps3, None)
+            buf[d3] = ps3.score
+        ps3set = index.pop(d2)
+        queue.remove_all(ps3set)
+        for ps3 in ps3set:
+            d3 = ps3.d2 if ps3.d1 is d2 else ps3.d1
+            index[d3].pop(ps3, None)
+            if d3 not in buf:
+                continue
+            ps = _Pair(d12, d3, max(buf[d3], ps3.score))
+            ps.step = step
+            queue.offer(ps)
+            index.setdefault(d12, {})[ps] = None
+            index.setdefault(d3, {})[ps] = None
+        if not queue.items:
+            return [d12], tie_seen
+    roots = [d for d in leafs if d.parent is None]
+    seen = set()
+    for d in leafs:
+        r = d.dereference()
+        if id(r) not in seen:
+            seen.add(id(r))
+            if r.left is not None:
+                roots.append(r)
+    return roots, tie_seen
+
+
+def single_link(m, distance, max_distance):
+    leafs = [_Dendro(obj=i) for i in range(m)]
+    pairs = [(float(distance(i, j)), i, j) for i in range(m) for j in range(i + 1, m)]
+    pairs.sort(key=lambda t: t[0])                              # stable
+    clusters = m
+    for sc, i, j in pairs:
+        if clusters <= 1 or sc > max_distance:
+            break
+        d1, d2 = leafs[i].dereference(), leafs[j].dereference()
+        if d1 is d2:
+            continue
+        _Dendro(d1, d2, sc)
+        clusters -= 1
+    roots, seen = [], set()
+    for d in leafs:
+        r = d.dereference()
+        if id(r) not in seen:
+            seen.add(id(r))
+            roots.append(r)
+    return roots
+
+
+def assign_hier(matrix, ed_complete=2, ed_single=1, single_threshold=3000, fold_depth=50, qv01=False):
+    """ClusterOneHierarchical.call on one job's packed matrix (list of lists / 2-D array).  Returns one dict per read:
+    center (-1 = none), u1, u2 (-1 = absent), pos2, off_mean, assigned, skipped, cluster_size, n_clusters, tie_unpin."""
+    n = len(matrix)
+    ED = lambda a, b: _i8(int(matrix[a][b]) & 0xFFFFFF)
+    rec = [dict(center=-1, u1=0, u2=-1, pos2=0, off_mean=0, assigned=False, skipped=False, cluster_size=0, n_clusters=0, tie_unpin=False)
+           for _ in range(n)]
+    iwn = [i for i in range(n) if sum(1 for j in range(n) if i != j and ED(i, j) <= ed_complete) > 0]     # DistanceMatrix.java:L87-L90
+    if len(iwn) <= 1:
+        return rec
+    single = len(iwn) > single_threshold
+    cut = ed_single if single else ed_complete
+    dist = lambda a, b: float(ED(iwn[a], iwn[b]))
+    m = len(iwn)
+    if single:
+        roots, tie_seen = single_link(m, dist, float(cut)), False
+    else:
+        roots, tie_seen = complete_link(m, dist, stop_above=float(cut))
+    reduced = []
+    for r in roots:
+        reduced += r.partition_distance(float(cut))
+    reduced = [c for c in reduced if len(c) > 1]                                                         # L101
+    chain_dep = False
+    full = []
+    for c in reduced:                                                                                    # DistanceMatrix.java:L145
+        b = jdk_int_set([iwn[k] for k in c])
+        cap = 16
+        while len(c) > cap * 3 // 4:
+            cap *= 2
+        if len({k & (cap - 1) for k in c}) < len(c) or len({k & (cap - 1) for k in b}) < len(b):
+            chain_dep = True
+        if len(b) > 1:
+            full.append(b)
+    if not full:
+        return rec
+    thr = lambda a, b: ED(iwn[a], iwn[b]) <= cut
+    cluster_graph = all((thr(a, c) == thr(b, c)) for a in range(m) for b in range(m) if a != b and thr(a, b) for c in range(m) if c != a and c != b)
+    unpin = tie_seen and (not cluster_graph or chain_dep)
+    maxdepth = max(len(c) for c in full)
+    cluster_list = []
+    for c in full:
+        if len(c) * fold_depth > maxdepth:
+            cluster_list.append(fastutil_intset_order(c))                                                 # OneUmiCluster
+        else:
+            for x in c:
+                rec[x]["skipped"], rec[x]["cluster_size"] = True, len(c)
+    for it in cluster_list:
+        k = len(it)
+        if k == 2:
+            center = it[0] if qv01 else it[1]
+        else:
+            sums = [(sum(int(float(ED(s, w)) ** 2.0) for w in it if w != s), i) for i, s in enumerate(it)]
+            center = it[min(sums)[1]]                                                                    # stable sort, first
+        offs = [(-1 if matrix[center][v] & 0x08000000 else 0 if matrix[center][v] & 0x10000000 else 1 if matrix[center][v] & 0x20000000 else 0)
+                for v in it if v != center]
+        import math
+        off_mean = int(math.floor(sum(offs) / len(offs) + 0.5))
+        for x in it:
+            r = rec[x]
+            r.update(center=center, assigned=True, cluster_size=k, off_mean=off_mean, u1=ED(center, x))
+            p = int(matrix[center][x])
+            r["pos2"] = 0 if p & 0x01000000 else 1 if p & 0x02000000 else 2 if p & 0x04000000 else 1
+            if len(cluster_list) > 1:
+                outside = [ED(x, y) for y in range(n) if y not in it]
+                if outside:
+                    r["u2"] = min(outside)
+    for r in rec:
+        r["n_clusters"], r["tie_unpin"] = len(cluster_list), unpin
+    return rec

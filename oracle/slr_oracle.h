@@ -183,6 +183,36 @@ void    orc_umi_cluster(const int32_t *matrix, int64_t n, int ed, const uint8_t 
 void    orc_umi_cluster_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs, int ed,
                               const uint8_t *member, const int32_t *rank, orc_cluster_rec *rec, int n_threads);
 
+/* ---------- clustering + UMI assignment of a job (oracle/slr_oracle_assign.c) ------------------------------------------------
+ * ClusterOneHierarchical.call (F!com/rw/umifinder/analyzers/clustering/ClusterOneHierarchical.java:L61-L217): the clusterer of every job of at
+ * most 100 reads (UmiClustering.java:L240) — LingPipe complete link (CompleteLinkClusterer.java:L146-L237) / single link on the reads that
+ * have a neighbour, Dendrogram.partitionDistance, the depth rule, OneUmiCluster.setClusterCenter (OneUmiCluster.java:L49-L65) and the
+ * per-read values ClusterOneBase.setSamflagsAndStatsForClustered writes (ClusterOneBase.java:L118-L168). */
+#define ORC_UA_ASSIGNED  1u   /* the read is in a cluster of the final list: setSamflagsAndStatsForClustered runs for it */
+#define ORC_UA_SKIPPED   2u   /* its cluster failed the depth rule: flagDontUMIassignRecords (UMI_CLUSTERING_SKIPPED_HIGHCOMPLEXITY) */
+#define ORC_UA_TIE_UNPIN 4u   /* the job's result can depend on the JVM's identity-hash order (ObjectToSet's HashSet<PairScore>) */
+#define ORC_UA_DEEP      8u   /* job of more than max_hier reads: ClusterOne_MyClustering's, not clustered here */
+typedef struct {
+    int32_t ed_complete;      /* umi_completelinkclusteringED (config.xml:270) */
+    int32_t ed_single;        /* umi_singlelinkclusteringED (config.xml:272) */
+    int32_t single_threshold; /* complexity_threshold_for_switch_to_single_link_clustering (config.xml:278) */
+    int32_t fold_depth;       /* foldDepthBelowMaxDiscardForClustering (UMIparameters.java:L118: 50) */
+    int32_t max_hier;         /* largest job ClusterOneHierarchical gets (UmiClustering.java:L240: 100) */
+} orc_assign_params;
+typedef struct {
+    int32_t  center;          /* job-local index of OneUmiCluster.getCenter() of the read's cluster; -1 = not clustered */
+    int8_t   u1;              /* UMI_ED: distanceNonReducedSet(center, read) */
+    int8_t   u2;              /* UMI_ED_SECOND_BEST_MATCH: least distance to a read outside the cluster; -1 = tag not written */
+    int8_t   pos2;            /* matrix[center][read].getPos2(): 0 MINUSONE, 1 ZERO, 2 PLUSONE */
+    int8_t   off_mean;        /* offsetcentermean of the cluster (ClusterOneHierarchical.java:L143-L147) */
+    uint16_t flags;           /* ORC_UA_* */
+    uint16_t cluster_size;
+    int32_t  n_clusters;      /* cluster_list.size() of the job */
+} orc_assign_rec;             /* 16 bytes, same layout as slr_umi_assign_rec */
+void orc_umi_assign_hier(const int32_t *matrix, int64_t n, const orc_assign_params *P, int qv01, orc_assign_rec *rec);
+void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs,
+                          const orc_assign_params *P, const uint8_t *job_qv01, orc_assign_rec *rec, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,329 @@
+/*
+ * slr_oracle_assign.c — CPU ORACLE (test infrastructure, NOT product code): clustering of one (cell, region) job on its packed
+ * distance matrix and the per-read "UMI assignment" derived from the clusters.
+ *
+ * Restated from the bytecode (F! = Jar/NanoporeBC_UMI_finder-2.1.jar, A! = Jar/lib/Aliasi_ClusteringLib-1.0.jar):
+ *   UmiClustering$Submitter dispatch            F!…/clustering/UmiClustering$Submitter.class (UmiClustering.java:L239-L261): n <= 100 -> ClusterOneHierarchical,
+ *                                               n > 100 -> ClusterOne_MyClustering; CLUSTERHOW is the constant DECIDEONCOMPLEXITY (…java:L50), so
+ *                                               the pre-grouping branch (L242-L244: size > 1000 AND ALIASI) is unreachable: wasPregrouped is false.
+ *   ClusterOneHierarchical.call                 F!…/clustering/ClusterOneHierarchical.class (ClusterOneHierarchical.java:L61-L217)
+ *   DistanceMatrix (indicesWithNeighbors, distance, transformIndices_AndRemoveSingletons)   F!com/rw/clustering/DistanceMatrix.class (…java:L77-L90, L145, L158, L169)
+ *   CompleteLinkClusterer.hierarchicalCluster   A!com/aliasi/cluster/CompleteLinkClusterer.class (CompleteLinkClusterer.java:L146-L237)
+ *   SingleLinkClusterer.hierarchicalCluster     A!com/aliasi/cluster/SingleLinkClusterer.class (SingleLinkClusterer.java:L198-L268)
+ *   BoundedPriorityQueue / EntryComparator      A!com/aliasi/util/BoundedPriorityQueue.class (BoundedPriorityQueue.java:L131-L153, L342-L346, L372-L379, L458-L464)
+ *   Dendrogram.partitionDistance                A!com/aliasi/cluster/Dendrogram.class (Dendrogram.java:L205-L215), LinkDendrogram (LinkDendrogram.java:L85-L94, L129-L130)
+ *   OneUmiCluster.setClusterCenterNotPreGrouped F!com/rw/clustering/OneUmiCluster.class (OneUmiCluster.java:L49-L65)
+ *   ClusterOneBase.setSamflagsAndStatsForClustered   F!…/clustering/ClusterOneBase.class (ClusterOneBase.java:L118-L168)
+ *
+ * Containers whose iteration order reaches the result are modelled explicitly:
+ *   java.util.HashSet<Integer>  (JDK HashMap: table of 16 doubling above a load of .75, bucket = hash & (cap - 1), hash(Integer) = value,
+ *                                chains in insertion order, resize keeps the relative order)
+ *   fastutil IntOpenHashSet     (OneUmiCluster's superclass; 8.2.2 layout as published: 32 slots for <= 24 keys, slot = mix(k) & mask,
+ *                                linear probing, key 0 outside the table and iterated first, then the slots from the last to the first)
+ *   ObjectToSet's HashSet<PairScore> is keyed by IDENTITY hash codes: the reference's own iteration order is JVM-run dependent.  The
+ *   canonical order used here (and by the GPU kernel) is the creation order of the pairs; a job whose result can depend on that order is
+ *   flagged ORC_UA_TIE_UNPIN.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "slr_oracle.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static int ed_of(int32_t packed) { return (int)(int8_t)(packed & 0xFFFFFF); }            /* BestEditDistance.getED: iand, i2b (L382) */
+static int pos1_offset(int32_t p) { return (p & 0x08000000) ? -1 : (p & 0x10000000) ? 0 : (p & 0x20000000) ? 1 : 0; }   /* getPos1().getOffSet() */
+static int pos2_code(int32_t p) { return (p & 0x01000000) ? 0 : (p & 0x02000000) ? 1 : (p & 0x04000000) ? 2 : 1; }      /* getPos2(): MINUSONE, ZERO, PLUSONE */
+
+/* ---- java.util.HashSet<Integer> iteration order --------------------------------------------------------------------------- */
+static int jdk_cap_for(int size)
+{
+    int cap = 16;
+    while (size > cap * 3 / 4) cap <<= 1;          /* resize when ++size > threshold (= .75 * cap) */
+    return cap;
+}
+/* in: elements in insertion order; out: iteration order.  Returns 1 when two elements share a bucket (chain order = insertion order). */
+static int jdk_hashset_order(const int *in, int k, int *out)
+{
+    const int cap = jdk_cap_for(k);
+    int o = 0, collide = 0;
+    for (int b = 0; b < cap; b++) {
+        int cnt = 0;
+        for (int i = 0; i < k; i++)
+            if ((in[i] & (cap - 1)) == b) { out[o++] = in[i]; cnt++; }
+        if (cnt > 1) collide = 1;
+    }
+    return collide;
+}
+
+/* ---- fastutil IntOpenHashSet iteration order -------------------------------------------------------------------------------- */
+static uint32_t fu_mix(int k) { const uint32_t h = (uint32_t)k * 0x9E3779B9u; return h ^ (h >> 16); }     /* HashCommon.mix */
+static int fu_array_size(int expected)      /* HashCommon.arraySize(expected, .75f) = max(2, nextPowerOfTwo(ceil(expected / f))) */
+{
+    long need = (long)ceil(expected / 0.75f), n = 2;
+    while (n < need) n <<= 1;
+    return (int)n;
+}
+static void fastutil_intset_order(const int *in, int k, int *out)
+{
+    int n = 32, size = 0, has_zero = 0;
+    int *tab = (int *)calloc((size_t)n, sizeof(int));
+    for (int i = 0; i < k; i++) {
+        const int key = in[i];
+        if (key == 0) { if (has_zero) continue; has_zero = 1; }
+        else {
+            int pos = (int)(fu_mix(key) & (uint32_t)(n - 1)), dup = 0;
+            while (tab[pos] != 0) { if (tab[pos] == key) { dup = 1; break; } pos = (pos + 1) & (n - 1); }
+            if (dup) continue;
+            tab[pos] = key;
+        }
+        if (size++ >= n * 3 / 4) {                                                      /* maxFill(n, .75f) */
+            const int nn = fu_array_size(size + 1);
+            int *nt = (int *)calloc((size_t)nn, sizeof(int));
+            for (int j = n - 1; j >= 0; j--)                                            /* rehash walks the old table downwards */
+                if (tab[j] != 0) {
+                    int pos = (int)(fu_mix(tab[j]) & (uint32_t)(nn - 1));
+                    while (nt[pos] != 0) pos = (pos + 1) & (nn - 1);
+                    nt[pos] = tab[j];
+                }
+            free(tab); tab = nt; n = nn;
+        }
+    }
+    int o = 0;
+    if (has_zero) out[o++] = 0;
+    for (int j = n - 1; j >= 0; j--) if (tab[j] != 0) out[o++] = tab[j];
+    free(tab);
+}
+
+/* ---- dendrograms ------------------------------------------------------------------------------------------------------------ */
+typedef struct { int left, right, leaf, parent; double score; } dnode;     /* leaf >= 0: LeafDendrogram(object), score 0 */
+typedef struct { int d1, d2; double score; long id; int in_queue; } pscore; /* PairScore + its BoundedPriorityQueue entry id */
+
+static int deref(const dnode *D, int x) { while (D[x].parent >= 0) x = D[x].parent; return x; }     /* Dendrogram.dereference */
+static int members(const dnode *D, int x, int *out, int o)                                           /* addMembers: left, then right */
+{
+    if (D[x].leaf >= 0) { out[o++] = D[x].leaf; return o; }
+    o = members(D, D[x].left, out, o);
+    return members(D, D[x].right, out, o);
+}
+
+/* CompleteLinkClusterer.hierarchicalCluster over elements 0..m-1 (the HashSet {0..m-1} iterates ascending: every value is below the
+ * table size).  Stops once the cheapest pair costs more than max_ed: every later link is above the cut of partitionDistance(max_ed).
+ * Returns the number of dendrogram nodes; *tie_seen = some poll at cost <= max_ed had a same-cost rival created in the same merge step
+ * (their relative order in the queue follows the identity-hash order of ObjectToSet's HashSet). */
+static int complete_link(const int *dist, int m, int max_ed, dnode *D, int *tie_seen)
+{
+    int nd = m, np = 0, cap = m * (m - 1) / 2 + m * m + 8;
+    long next_id = 0;
+    pscore *P = (pscore *)malloc((size_t)cap * sizeof(pscore));
+    /* index: per dendrogram node the pairs it is part of, in insertion order */
+    int **idx = (int **)calloc((size_t)(2 * m), sizeof(int *)), *idx_n = (int *)calloc((size_t)(2 * m), sizeof(int));
+    int *born = (int *)calloc((size_t)cap, sizeof(int));                                /* merge step that created the pair (0 = initial) */
+    for (int i = 0; i < 2 * m; i++) idx[i] = (int *)malloc((size_t)(2 * m + 4) * sizeof(int));
+    for (int i = 0; i < m; i++) { D[i].left = D[i].right = -1; D[i].leaf = i; D[i].parent = -1; D[i].score = 0.0; }
+    for (int i = 0; i < m; i++)
+        for (int j = i + 1; j < m; j++) {                                               /* L169-L180 */
+            P[np].d1 = i; P[np].d2 = j; P[np].score = (double)dist[i * m + j]; P[np].id = next_id++; P[np].in_queue = 1; born[np] = 0;
+            idx[i][idx_n[i]++] = np; idx[j][idx_n[j]++] = np;
+            np++;
+        }
+    *tie_seen = 0;
+    int step = 0;
+    for (;;) {
+        int best = -1;                                                                  /* poll(): least cost, among equals the LARGEST id (L458-L464) */
+        for (int p = 0; p < np; p++)
+            if (P[p].in_queue && (best < 0 || P[p].score < P[best].score || (P[p].score == P[best].score && P[p].id > P[best].id))) best = p;
+        if (best < 0) break;
+        if (P[best].score > (double)max_ed) break;
+        if (born[best] > 0)
+            for (int p = 0; p < np; p++)
+                if (p != best && P[p].in_queue && P[p].score == P[best].score && born[p] == born[best]) *tie_seen = 1;
+        step++;
+        P[best].in_queue = 0;
+        const int d1 = deref(D, P[best].d1), d2 = deref(D, P[best].d2), d12 = nd++;     /* L186-L189 */
+        D[d12].left = d1; D[d12].right = d2; D[d12].leaf = -1; D[d12].parent = -1; D[d12].score = P[best].score;
+        D[d1].parent = d12; D[d2].parent = d12;
+        idx[d12] = idx[d12] ? idx[d12] : (int *)malloc((size_t)(2 * m + 4) * sizeof(int));
+        double *buf = (double *)malloc((size_t)(2 * m) * sizeof(double));               /* distanceBuf (L193) */
+        char *has = (char *)calloc((size_t)(2 * m), 1);
+        for (int q = 0; q < idx_n[d1]; q++) {                                           /* L195-L205 */
+            const int p = idx[d1][q];
+            if (p < 0) continue;
+            P[p].in_queue = 0;
+            const int d3 = (P[p].d1 == d1) ? P[p].d2 : P[p].d1;
+            for (int r = 0; r < idx_n[d3]; r++) if (idx[d3][r] == p) idx[d3][r] = -1;
+            buf[d3] = P[p].score; has[d3] = 1;
+        }
+        idx_n[d1] = 0;
+        for (int q = 0; q < idx_n[d2]; q++) {                                           /* L208-L225: canonical order = insertion order */
+            const int p = idx[d2][q];
+            if (p < 0) continue;
+            P[p].in_queue = 0;
+            const int d3 = (P[p].d1 == d2) ? P[p].d2 : P[p].d1;
+            for (int r = 0; r < idx_n[d3]; r++) if (idx[d3][r] == p) idx[d3][r] = -1;
+            if (!has[d3]) continue;
+            P[np].d1 = d12; P[np].d2 = d3; P[np].score = buf[d3] > P[p].score ? buf[d3] : P[p].score;     /* Math.max (L220) */
+            P[np].id = next_id++; P[np].in_queue = 1; born[np] = step;
+            idx[d12][idx_n[d12]++] = np; idx[d3][idx_n[d3]++] = np;
+            np++;
+        }
+        idx_n[d2] = 0;
+        free(buf); free(has);
+    }
+    for (int i = 0; i < 2 * m; i++) free(idx[i]);
+    free(idx); free(idx_n); free(P); free(born);
+    return nd;
+}
+
+typedef struct { double score; int i, j, seq; } slpair;
+static int slpair_cmp(const void *a, const void *b)       /* ScoredObject.comparator() under the stable Arrays.sort (TimSort) */
+{
+    const slpair *x = (const slpair *)a, *y = (const slpair *)b;
+    if (x->score != y->score) return x->score < y->score ? -1 : 1;
+    return x->seq - y->seq;
+}
+/* SingleLinkClusterer.hierarchicalCluster (L205-L268): pairs sorted by cost, merged while cost <= maxDistance */
+static int single_link(const int *dist, int m, int max_ed, dnode *D)
+{
+    int nd = m, np = 0;
+    slpair *P = (slpair *)malloc((size_t)(m * (m - 1) / 2 + 1) * sizeof(slpair));
+    for (int i = 0; i < m; i++) { D[i].left = D[i].right = -1; D[i].leaf = i; D[i].parent = -1; D[i].score = 0.0; }
+    for (int i = 0; i < m; i++)
+        for (int j = i + 1; j < m; j++) { P[np].score = (double)dist[i * m + j]; P[np].i = i; P[np].j = j; P[np].seq = np; np++; }
+    qsort(P, (size_t)np, sizeof(slpair), slpair_cmp);
+    int clusters = m;
+    for (int p = 0; p < np && clusters > 1; p++) {
+        if (P[p].score > (double)max_ed) break;
+        const int d1 = deref(D, P[p].i), d2 = deref(D, P[p].j);
+        if (d1 == d2) continue;
+        D[nd].left = d1; D[nd].right = d2; D[nd].leaf = -1; D[nd].parent = -1; D[nd].score = P[p].score;
+        D[d1].parent = nd; D[d2].parent = nd;
+        nd++; clusters--;
+    }
+    free(P);
+    return nd;
+}
+
+/* ClusterOneHierarchical.call for one job (n reads, n x n packed matrix). */
+void orc_umi_assign_hier(const int32_t *matrix, int64_t n64, const orc_assign_params *P, int qv01, orc_assign_rec *rec)
+{
+    const int n = (int)n64;
+    for (int i = 0; i < n; i++) { memset(&rec[i], 0, sizeof(rec[i])); rec[i].center = -1; rec[i].u2 = -1; }
+    if (n < 2) return;
+    /* DistanceMatrix.generateIndicesWithNeighbours (L87-L90): always against umi_completelinkclusteringED */
+    int *iwn = (int *)malloc((size_t)n * sizeof(int)), m = 0;
+    for (int i = 0; i < n; i++) {
+        int any = 0;
+        for (int j = 0; j < n; j++) if (i != j && ed_of(matrix[(size_t)i * n + j]) <= P->ed_complete) any = 1;
+        if (any) iwn[m++] = i;
+    }
+    if (m <= 1) { free(iwn); return; }                                                   /* L86 */
+    const int single = m > P->single_threshold;                                          /* L79 */
+    const int cut = single ? P->ed_single : P->ed_complete;                              /* L83-L84, L101 */
+    int *dist = (int *)malloc((size_t)m * m * sizeof(int));
+    for (int a = 0; a < m; a++)
+        for (int b = 0; b < m; b++) dist[a * m + b] = ed_of(matrix[(size_t)iwn[a] * n + iwn[b]]);      /* DistanceMatrix.distance (L158) */
+    dnode *D = (dnode *)malloc((size_t)(2 * m) * sizeof(dnode));
+    int tie_seen = 0;
+    const int nd = single ? single_link(dist, m, cut, D) : complete_link(dist, m, cut, D, &tie_seen);
+    /* is the threshold graph a disjoint union of cliques?  (then every merge order ends in the same partition) */
+    int cluster_graph = 1;
+    for (int a = 0; a < m && cluster_graph; a++)
+        for (int b = 0; b < m && cluster_graph; b++)
+            if (a != b && dist[a * m + b] <= cut)
+                for (int c = 0; c < m; c++)
+                    if (c != a && c != b && (dist[a * m + c] <= cut) != (dist[b * m + c] <= cut)) { cluster_graph = 0; break; }
+    /* partitionDistance(cut): the roots left over are the maximal subtrees with cost <= cut (later links cost more); size > 1 (L101);
+     * transformIndices_AndRemoveSingletons (L104, DistanceMatrix.java:L145) */
+    int *cl_of = (int *)malloc((size_t)n * sizeof(int));
+    for (int i = 0; i < n; i++) cl_of[i] = -1;
+    int n_cl = 0, maxdepth = 0, chain_dep = 0;
+    int *cl_size = (int *)calloc((size_t)m, sizeof(int)), **cl_it = (int **)calloc((size_t)m, sizeof(int *));
+    int *tmpA = (int *)malloc((size_t)m * sizeof(int)), *tmpB = (int *)malloc((size_t)m * sizeof(int));
+    for (int x = 0; x < nd; x++) {
+        if (D[x].parent >= 0) continue;
+        const int k = members(D, x, tmpA, 0);
+        if (k <= 1) continue;
+        chain_dep |= jdk_hashset_order(tmpA, k, tmpB);                                   /* memberSet(): HashSet of reduced indices */
+        for (int i = 0; i < k; i++) tmpA[i] = iwn[tmpB[i]];                              /* stream().map(k -> indicesWithNeighbors.get(k)) */
+        chain_dep |= jdk_hashset_order(tmpA, k, tmpB);                                   /* collect(toSet()) */
+        cl_it[n_cl] = (int *)malloc((size_t)k * sizeof(int));
+        fastutil_intset_order(tmpB, k, cl_it[n_cl]);                                     /* toCollection(OneUmiCluster::new) (L129) */
+        cl_size[n_cl] = k;
+        if (k > maxdepth) maxdepth = k;                                                  /* L118 */
+        n_cl++;
+    }
+    const int unpinned = tie_seen && (!cluster_graph || chain_dep);
+    /* depth rule (L121-L127) */
+    int n_list = 0;
+    for (int c = 0; c < n_cl; c++) if (cl_size[c] * P->fold_depth > maxdepth) n_list++;
+    for (int c = 0; c < n_cl; c++) {
+        const int k = cl_size[c], *it = cl_it[c];
+        if (!(k * P->fold_depth > maxdepth)) {                                           /* flagDontUMIassignRecords (ClusterOneBase.java:L57, L71) */
+            for (int i = 0; i < k; i++) { rec[it[i]].flags |= ORC_UA_SKIPPED; rec[it[i]].cluster_size = (uint16_t)k; }
+            continue;
+        }
+        int center;
+        if (k == 2) center = qv01 ? it[0] : it[1];                                       /* OneUmiCluster.java:L52-L54 */
+        else {                                                                           /* L57-L63: least sum of squared distances, first wins */
+            long bests = -1; center = it[0];
+            for (int i = 0; i < k; i++) {
+                long s = 0;
+                for (int j = 0; j < k; j++) if (it[j] != it[i]) { const int e = ed_of(matrix[(size_t)it[i] * n + it[j]]); s += (long)pow((double)e, 2.0); }
+                if (bests < 0 || s < bests) { bests = s; center = it[i]; }
+            }
+        }
+        long sum = 0, cnt = 0;                                                           /* ClusterOneHierarchical.java:L143-L147 */
+        for (int i = 0; i < k; i++) if (it[i] != center) { sum += pos1_offset(matrix[(size_t)center * n + it[i]]); cnt++; }
+        const int off_mean = (int)floor((double)sum / (double)cnt + 0.5);                /* Math.round(average) */
+        for (int i = 0; i < k; i++) {                                                    /* L178-L195 -> setSamflagsAndStatsForClustered */
+            const int x = it[i];
+            orc_assign_rec *r = &rec[x];
+            r->center = center; r->flags |= ORC_UA_ASSIGNED; r->cluster_size = (uint16_t)k; r->off_mean = (int8_t)off_mean;
+            r->u1 = (int8_t)ed_of(matrix[(size_t)center * n + x]);                        /* distanceNonReducedSet(center, index) (L156) */
+            r->pos2 = (int8_t)pos2_code(matrix[(size_t)center * n + x]);                  /* L133 */
+            cl_of[x] = c;
+        }
+    }
+    for (int c = 0; c < n_cl; c++) {                                                     /* U2 (L161-L164): cluster_list.size() > 1, min over y outside thisCluster */
+        if (!(cl_size[c] * P->fold_depth > maxdepth)) continue;
+        for (int i = 0; i < cl_size[c]; i++) {
+            const int x = cl_it[c][i];
+            if (n_list > 1) {
+                int best = -1;
+                for (int y = 0; y < n; y++) {
+                    int inside = 0;
+                    for (int j = 0; j < cl_size[c]; j++) if (cl_it[c][j] == y) inside = 1;
+                    if (inside) continue;
+                    const int e = ed_of(matrix[(size_t)x * n + y]);
+                    if (best < 0 || e < best) best = e;
+                }
+                rec[x].u2 = (int8_t)best;
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        rec[i].n_clusters = n_list;
+        if (unpinned) rec[i].flags |= ORC_UA_TIE_UNPIN;
+    }
+    for (int c = 0; c < n_cl; c++) free(cl_it[c]);
+    free(cl_it); free(cl_size); free(tmpA); free(tmpB); free(cl_of); free(D); free(dist); free(iwn);
+}
+
+void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs,
+                          const orc_assign_params *P, const uint8_t *job_qv01, orc_assign_rec *rec, int n_threads)
+{
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+    for (int64_t j = 0; j < n_jobs; j++) {
+        const int64_t r0 = job_offsets[j], n = job_offsets[j + 1] - r0;
+        if (n > P->max_hier) {                                                           /* UmiClustering.java:L240: ClusterOne_MyClustering's job */
+            for (int64_t i = 0; i < n; i++) { memset(&rec[r0 + i], 0, sizeof(rec[0])); rec[r0 + i].center = -1; rec[r0 + i].u2 = -1; rec[r0 + i].flags = ORC_UA_DEEP; }
+            continue;
+        }
+        orc_umi_assign_hier(matrices + out_offsets[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0);
+    }
+}

@@ -38,6 +38,16 @@ int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(SLR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// one kernel launch that needs a work-counter cell: `work` names the cell inside expr
+#define CUDA_TRY_WORK(ctx_, stream_, expr)                                                                      \
+    do {                                                                                                        \
+        unsigned cell_;                                                                                         \
+        unsigned long long *work = (ctx_)->work_acquire((stream_), cell_);                                      \
+        cudaError_t e_ = (expr);                                                                                \
+        (ctx_)->work_release((stream_), cell_);                                                                 \
+        if (e_ != cudaSuccess) return fail(SLR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
 // reads per pipelined chunk of the host-pointer path (SLR_BC_CHUNK overrides, for tuning)
 static long long bc_chunk()
 {
@@ -78,15 +88,45 @@ struct Slot {
     cudaEvent_t gvis_free = nullptr;           // recorded after the last guided launch that uses gvis
 };
 
+// Every error exit of a pipelined host-pointer call must leave nothing in flight: the D2H copy of the previous chunk may still be
+// writing into the caller's (pinned) result buffer on the other ping-pong stream, and the caller is free to release it once we return.
+struct SlotDrain {
+    Slot *s;
+    bool armed = true;
+    explicit SlotDrain(Slot *slot) : s(slot) {}
+    ~SlotDrain()
+    {
+        if (!armed) return;
+        cudaStreamSynchronize(s->stream[0]);
+        cudaStreamSynchronize(s->stream[1]);
+    }
+};
+
 }  // namespace
 
-constexpr unsigned WORK_COUNTERS = 4096;       // one 8-byte work counter per kernel launch in flight, handed out round-robin
+constexpr unsigned WORK_COUNTERS = 1024;       // ring of 16-byte work-counter cells, one per kernel launch; a cell is handed out again only
+                                               // behind the event of its previous user, whatever stream that launch ran on
 
 struct slr_ctx {
-    unsigned long long *d_work = nullptr;
-    std::atomic<unsigned> next_work{0};
-    unsigned long long *work_counter() { return d_work + next_work.fetch_add(1) % WORK_COUNTERS; }
-    unsigned long long *work_pair() { return d_work + next_work.fetch_add(2) % WORK_COUNTERS; }     // two slots (the array has one spare)
+    unsigned long long *d_work = nullptr;      // WORK_COUNTERS cells of two counters (umi_cluster uses both)
+    cudaEvent_t work_done[WORK_COUNTERS] = {};
+    std::mutex work_mtx;
+    unsigned next_work = 0;
+    // Cell for one launch on `stream`: the stream first waits for the launch that used the cell last (a no-op unless more than
+    // WORK_COUNTERS launches are queued), the caller enqueues its reset + kernel, then calls work_release.
+    unsigned long long *work_acquire(cudaStream_t stream, unsigned &cell)
+    {
+        std::lock_guard<std::mutex> lk(work_mtx);
+        cell = next_work++ % WORK_COUNTERS;
+        cudaStreamWaitEvent(stream, work_done[cell], 0);
+        return d_work + 2 * (size_t)cell;
+    }
+    void work_release(cudaStream_t stream, unsigned cell)
+    {
+        std::lock_guard<std::mutex> lk(work_mtx);
+        cudaEventRecord(work_done[cell], stream);
+    }
+    cudaStream_t aux = nullptr;                // counter read-back
     int device = 0;
     int n_slots = 1;
     std::vector<Slot *> slots;
@@ -126,12 +166,16 @@ int slr_ctx_create(int device, int n_streams, slr_ctx **out)
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(SLR_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    if (prop.major != 10 || prop.minor != 0)   // the library holds sm_100a SASS only (no PTX): any other device would fail at the first launch
+        return fail(SLR_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200, compute capability 10.0) only", device,
+                    prop.major, prop.minor);
     slr_ctx *c = new slr_ctx();
     c->device = device;
-    e = cudaMalloc((void **)&c->d_work, (WORK_COUNTERS + 1) * sizeof(unsigned long long));
+    e = cudaMalloc((void **)&c->d_work, 2 * WORK_COUNTERS * sizeof(unsigned long long));
     if (e != cudaSuccess) { delete c; return fail(SLR_E_NOMEM, "cudaMalloc(work counters): %s", cudaGetErrorString(e)); }
+    for (unsigned i = 0; i < WORK_COUNTERS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->work_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { slr_ctx_destroy(c); return fail(SLR_E_CUDA, "slr_ctx_create: %s", cudaGetErrorString(e)); }
     c->n_slots = n_streams < 1 ? 1 : (n_streams > 64 ? 64 : n_streams);
     for (int i = 0; i < c->n_slots; i++) {
         Slot *s = new Slot();
@@ -164,6 +208,10 @@ void slr_ctx_destroy(slr_ctx *c)
         delete s;
     }
     free_session_pool(c);
+    cudaDeviceSynchronize();                   // launches of the *_dev entry points on the caller's streams may still use the counter cells
+    for (unsigned i = 0; i < WORK_COUNTERS; i++)
+        if (c->work_done[i]) cudaEventDestroy(c->work_done[i]);
+    if (c->aux) cudaStreamDestroy(c->aux);
     cudaFree(c->d_work);
     delete c;
 }
@@ -242,10 +290,12 @@ int64_t slr_bc_table_size(const slr_bc_table *t) { return t ? t->n_distinct : 0;
 static int check_bc_args(const slr_ctx *ctx, const slr_bc_table *t, int ed_max, int plusminus, int stride, int slice_len, int64_t n)
 {
     if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_assign: ctx / table is NULL");
+    if (t->ctx != ctx) return fail(SLR_E_INVALID, "slr_bc_assign: the table belongs to another context (device %d, this context: device %d)",
+                                   t->ctx ? t->ctx->device : -1, ctx->device);
     if (ed_max < 0) return fail(SLR_E_INVALID, "bcEditDistance %d < 0", ed_max);
     if (ed_max > 2) return fail(SLR_E_UNSUPPORTED, "bcEditDistance %d not supported by the GPU path (0, 1 or 2)", ed_max);
     if (plusminus < 0 || 2 * plusminus + 1 > SLR_MAX_OFFSETS) return fail(SLR_E_UNSUPPORTED, "testPlusMinusPos %d not supported (0..4)", plusminus);
-    if (slice_len < 1 || slice_len > 32 || stride < slice_len) return fail(SLR_E_INVALID, "slice_len %d / stride %d invalid (1 <= slice_len <= 32 <= stride)", slice_len, stride);
+    if (slice_len < 1 || slice_len > 32 || stride < slice_len) return fail(SLR_E_INVALID, "slice_len %d / stride %d invalid (1 <= slice_len <= 32, slice_len <= stride)", slice_len, stride);
     if (n < 0) return fail(SLR_E_INVALID, "n < 0");
     return SLR_OK;
 }
@@ -261,8 +311,9 @@ static int bc_assign_dev_impl(slr_ctx *ctx, const slr_bc_table *t, int ed_max, i
     CUDA_TRY(cudaSetDevice(ctx->device));
     for (int64_t off = 0; off < n; off += (1LL << 30)) {           // grid.x limit: 2^31-1 blocks of 8 reads
         const int64_t m = (n - off) < (1LL << 30) ? (n - off) : (1LL << 30);
-        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, d_slices + off * stride, stride, slice_len,
-                                      d_lens ? d_lens + off : nullptr, d_anchor + off, m, d_out + off, ctx->work_counter(), (cudaStream_t)stream));
+        CUDA_TRY_WORK(ctx, (cudaStream_t)stream,
+                      slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, d_slices + off * stride, stride, slice_len,
+                                           d_lens ? d_lens + off : nullptr, d_anchor + off, m, d_out + off, work, (cudaStream_t)stream));
         g_launches++;
     }
     return SLR_OK;
@@ -292,6 +343,7 @@ static int bc_assign_host_impl(slr_ctx *ctx, const slr_bc_table *t, int ed_max, 
     CUDA_TRY(cudaSetDevice(ctx->device));
     Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
     std::lock_guard<std::mutex> lock(s->mtx);
+    SlotDrain drain(s);                                                // on any error exit: nothing left in flight on the caller's buffers
     // chunked ping-pong pipeline: H2D of chunk c+1 (stream B) overlaps the kernel of chunk c (stream A)
     int c = 0;
     const int64_t BC_CHUNK = bc_chunk();
@@ -307,9 +359,9 @@ static int bc_assign_host_impl(slr_ctx *ctx, const slr_bc_table *t, int ed_max, 
         CUDA_TRY(cudaMemcpyAsync(s->slices[b].p, slices + off * stride, (size_t)m * stride, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(s->anchor[b].p, anchor + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
         if (lens) CUDA_TRY(cudaMemcpyAsync(s->lens[b].p, lens + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, (const uint8_t *)s->slices[b].p, stride, slice_len,
-                                      lens ? (const int32_t *)s->lens[b].p : nullptr, (const int32_t *)s->anchor[b].p, m,
-                                      (slr_bc_result *)s->out[b].p, ctx->work_counter(), st));
+        CUDA_TRY_WORK(ctx, st, slr_launch_bc_assign(t->dev, ed_max, plusminus, three_prime, need_post, (const uint8_t *)s->slices[b].p, stride,
+                                                    slice_len, lens ? (const int32_t *)s->lens[b].p : nullptr, (const int32_t *)s->anchor[b].p, m,
+                                                    (slr_bc_result *)s->out[b].p, work, st));
         g_launches++;
         CUDA_TRY(cudaMemcpyAsync(out + off, s->out[b].p, (size_t)m * sizeof(slr_bc_result), cudaMemcpyDeviceToHost, st));
     }
@@ -333,9 +385,23 @@ int slr_bc_exact(slr_ctx *ctx, const slr_bc_table *t, int three_prime, const uin
 int slr_bc_counts_read(slr_ctx *ctx, const slr_bc_table *t, int64_t *counts_out)
 {
     if (!ctx || !t || !counts_out) return fail(SLR_E_INVALID, "slr_bc_counts_read: NULL argument");
+    if (t->ctx != ctx) return fail(SLR_E_INVALID, "slr_bc_counts_read: the table belongs to another context");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(counts_out, t->d_counts, (size_t)t->n * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    // The copy is ordered behind everything the host-pointer calls have enqueued on the context's slot streams so far (an event per
+    // stream, no device-wide synchronisation: callers that are still submitting are not held up).  Launches of the *_dev entry points
+    // run on the caller's streams: the caller synchronises those before reading the counters.
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaSuccess;
+    for (Slot *s : ctx->slots)
+        for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+            e = cudaEventRecord(ev, s->stream[k]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux, ev, 0);
+        }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts_out, t->d_counts, (size_t)t->n * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->aux);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->aux);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return fail(SLR_E_CUDA, "slr_bc_counts_read: %s", cudaGetErrorString(e));
     return SLR_OK;
 }
 
@@ -343,8 +409,9 @@ int slr_bc_counts_reset(slr_ctx *ctx, slr_bc_table *t)
 {
     if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_counts_reset: NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemset(t->d_counts, 0, (size_t)(t->n > 0 ? t->n : 1) * 3 * sizeof(int64_t)));
+    CUDA_TRY(cudaDeviceSynchronize());                                 // every launch that still adds to the counters has finished
+    CUDA_TRY(cudaMemsetAsync(t->d_counts, 0, (size_t)(t->n > 0 ? t->n : 1) * 3 * sizeof(int64_t), ctx->aux));
+    CUDA_TRY(cudaStreamSynchronize(ctx->aux));                         // (a plain cudaMemset is not ordered against the non-blocking slot streams)
     return SLR_OK;
 }
 
@@ -361,6 +428,7 @@ int slr_bc_collide_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const ui
                        void *stream)
 {
     if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_collide: ctx / table is NULL");
+    if (t->ctx != ctx) return fail(SLR_E_INVALID, "slr_bc_collide: the table belongs to another context");
     if (ed_max < 0 || n < 0) return fail(SLR_E_INVALID, "slr_bc_collide: mergeBCsED %d / n %lld invalid", ed_max, (long long)n);
     if (ed_max > 2) return fail(SLR_E_UNSUPPORTED, "mergeBCsED %d not supported by the GPU path (0, 1 or 2)", ed_max);
     if (n == 0) return SLR_OK;
@@ -374,6 +442,7 @@ int slr_bc_collide_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const ui
 int slr_bc_collide(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint64_t *barcodes, int64_t n, slr_collide_result *out)
 {
     if (!ctx || !t) return fail(SLR_E_INVALID, "slr_bc_collide: ctx / table is NULL");
+    if (t->ctx != ctx) return fail(SLR_E_INVALID, "slr_bc_collide: the table belongs to another context");
     if (n > 0 && (!barcodes || !out)) return fail(SLR_E_INVALID, "slr_bc_collide: NULL buffer");
     if (ed_max < 0 || n < 0) return fail(SLR_E_INVALID, "slr_bc_collide: mergeBCsED %d / n %lld invalid", ed_max, (long long)n);
     if (ed_max > 2) return fail(SLR_E_UNSUPPORTED, "mergeBCsED %d not supported by the GPU path (0, 1 or 2)", ed_max);
@@ -443,6 +512,7 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
     CUDA_TRY(cudaSetDevice(ctx->device));
     Slot *s = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
     std::lock_guard<std::mutex> lock(s->mtx);
+    SlotDrain drain(s);                                                    // on any error exit: nothing left in flight on the caller's buffers
     // job ranges of at most ~2^23 output cells (a single larger job still goes in one launch), ping-pong on the slot's two
     // streams: H2D of range c+1 and D2H of range c-1 overlap the kernels of range c.  The host only walks the job sizes to cut the
     // ranges; the offsets relative to the range and the matrix offsets (prefix sums of n^2) are made on the device.
@@ -489,11 +559,12 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
                 char *base = (char *)s->ucl[b].p;
                 if (cl->rank) CUDA_TRY(cudaMemcpyAsync(base + o_rank, cl->rank + r0, (size_t)nr * 4, cudaMemcpyHostToDevice, st));
                 if (cl->member) CUDA_TRY(cudaMemcpyAsync(base + o_mem, cl->member + r0, (size_t)nr, cudaMemcpyHostToDevice, st));
-                CUDA_TRY(slr_launch_umi_cluster((const int32_t *)s->uout[b].p, (const long long *)s->joff[b].p, (const long long *)s->ooff[b].p,
-                                                nj_range, nr, cl->ed, cl->member ? (const uint8_t *)(base + o_mem) : nullptr,
-                                                cl->rank ? (const int32_t *)(base + o_rank) : nullptr,
-                                                slr_umi_scratch_rowjob(s->uscr[b].p, nr), (int32_t *)base,
-                                                (slr_umi_cluster_rec *)(base + o_rec), ctx->work_pair(), st));
+                CUDA_TRY_WORK(ctx, st, slr_launch_umi_cluster((const int32_t *)s->uout[b].p, (const long long *)s->joff[b].p,
+                                                              (const long long *)s->ooff[b].p, nj_range, nr, cl->ed,
+                                                              cl->member ? (const uint8_t *)(base + o_mem) : nullptr,
+                                                              cl->rank ? (const int32_t *)(base + o_rank) : nullptr,
+                                                              slr_umi_scratch_rowjob(s->uscr[b].p, nr), (int32_t *)base,
+                                                              (slr_umi_cluster_rec *)(base + o_rec), work, st));
                 g_launches += SLR_UMI_CLUSTER_LAUNCHES;
                 CUDA_TRY(cudaMemcpyAsync(cl->rec + r0, base + o_rec, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
             }
@@ -567,8 +638,9 @@ int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *
     if (n_jobs == 0 || n_reads == 0) return SLR_OK;
     if (!d_matrices || !d_job_offsets || !d_out_offsets || !d_counts || !d_rec) return fail(SLR_E_INVALID, "slr_umi_cluster_dev: NULL buffer");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(slr_launch_umi_cluster(d_matrices, (const long long *)d_job_offsets, (const long long *)d_out_offsets, n_jobs, n_reads, ed,
-                                    d_member, d_rank, nullptr, d_counts, d_rec, ctx->work_pair(), (cudaStream_t)stream));
+    CUDA_TRY_WORK(ctx, (cudaStream_t)stream,
+                  slr_launch_umi_cluster(d_matrices, (const long long *)d_job_offsets, (const long long *)d_out_offsets, n_jobs, n_reads, ed,
+                                         d_member, d_rank, nullptr, d_counts, d_rec, work, (cudaStream_t)stream));
     g_launches += SLR_UMI_CLUSTER_LAUNCHES;
     return SLR_OK;
 }
@@ -660,10 +732,10 @@ int slr_umi_session_cluster(slr_umi_session *S, int ed, const uint8_t *member, c
     const size_t m = (size_t)S->n_reads;
     if (rank) CUDA_TRY(cudaMemcpyAsync(S->rank.p, rank, m * 4, cudaMemcpyHostToDevice, st));
     if (member) CUDA_TRY(cudaMemcpyAsync(S->member.p, member, m, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(slr_launch_umi_cluster((const int32_t *)S->mat.p, (const long long *)S->joff.p, (const long long *)S->ooff.p, S->n_jobs, S->n_reads,
-                                    ed, member ? (const uint8_t *)S->member.p : nullptr, rank ? (const int32_t *)S->rank.p : nullptr,
-                                    slr_umi_scratch_rowjob(S->scr.p, S->n_reads), (int32_t *)S->counts.p, (slr_umi_cluster_rec *)S->rec.p,
-                                    ctx->work_pair(), st));
+    CUDA_TRY_WORK(ctx, st, slr_launch_umi_cluster((const int32_t *)S->mat.p, (const long long *)S->joff.p, (const long long *)S->ooff.p, S->n_jobs,
+                                                  S->n_reads, ed, member ? (const uint8_t *)S->member.p : nullptr,
+                                                  rank ? (const int32_t *)S->rank.p : nullptr, slr_umi_scratch_rowjob(S->scr.p, S->n_reads),
+                                                  (int32_t *)S->counts.p, (slr_umi_cluster_rec *)S->rec.p, work, st));
     g_launches += SLR_UMI_CLUSTER_LAUNCHES;
     CUDA_TRY(cudaMemcpyAsync(rec, S->rec.p, m * 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -780,8 +852,8 @@ int slr_guided_match_dev(slr_ctx *ctx, const slr_guided_sets *s, int plusminus, 
     CUDA_TRY(cudaStreamWaitEvent(st, sl->gvis_free, 0));                  // the slot's visited tables may still serve an earlier launch
     if (slr_guided_vis_bytes(max_ed, nullptr) > sl->gvis.cap) CUDA_TRY(cudaEventSynchronize(sl->gvis_free));   // about to be reallocated
     if ((rc = sl->gvis.reserve(slr_guided_vis_bytes(max_ed, nullptr)))) return rc;
-    CUDA_TRY(slr_launch_guided_match(s->dev, s->seq_len, plusminus, post_len, bailout, d_slices, stride, slice_len, d_anchor, d_group_id, d_ed,
-                                     max_ed, n, d_out, d_raw_out, raw_cap, sl->gvis.p, ctx->work_counter(), st));
+    CUDA_TRY_WORK(ctx, st, slr_launch_guided_match(s->dev, s->seq_len, plusminus, post_len, bailout, d_slices, stride, slice_len, d_anchor,
+                                                   d_group_id, d_ed, max_ed, n, d_out, d_raw_out, raw_cap, sl->gvis.p, work, st));
     CUDA_TRY(cudaEventRecord(sl->gvis_free, st));
     g_launches++;
     return SLR_OK;
@@ -803,6 +875,7 @@ int slr_guided_match(slr_ctx *ctx, const slr_guided_sets *s, int plusminus, int 
     CUDA_TRY(cudaSetDevice(ctx->device));
     Slot *sl = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
     std::lock_guard<std::mutex> lock(sl->mtx);
+    SlotDrain drain(sl);
     cudaStream_t st = sl->stream[0];
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaEventSynchronize(sl->gvis_free));
@@ -823,9 +896,10 @@ int slr_guided_match(slr_ctx *ctx, const slr_guided_sets *s, int plusminus, int 
         CUDA_TRY(cudaMemcpyAsync(sl->ged.p, ed + off, m * 4, cudaMemcpyHostToDevice, st));
         slr_guided_hit *d_raw = (raw_out && raw_cap > 0) ? (slr_guided_hit *)sl->graw.p : nullptr;
         if (d_raw) CUDA_TRY(cudaMemsetAsync(d_raw, 0, m * raw_cap * sizeof(slr_guided_hit), st));
-        CUDA_TRY(slr_launch_guided_match(s->dev, s->seq_len, plusminus, post_len, bailout, (const uint8_t *)sl->gsl.p, stride, slice_len,
-                                         (const int32_t *)sl->ganc.p, (const int32_t *)sl->ggid.p, (const int32_t *)sl->ged.p, max_ed,
-                                         (long long)m, (slr_guided_result *)sl->gout.p, d_raw, raw_cap, sl->gvis.p, ctx->work_counter(), st));
+        CUDA_TRY_WORK(ctx, st, slr_launch_guided_match(s->dev, s->seq_len, plusminus, post_len, bailout, (const uint8_t *)sl->gsl.p, stride,
+                                                       slice_len, (const int32_t *)sl->ganc.p, (const int32_t *)sl->ggid.p,
+                                                       (const int32_t *)sl->ged.p, max_ed, (long long)m, (slr_guided_result *)sl->gout.p, d_raw,
+                                                       raw_cap, sl->gvis.p, work, st));
         g_launches++;
         CUDA_TRY(cudaMemcpyAsync(out + off, sl->gout.p, m * sizeof(slr_guided_result), cudaMemcpyDeviceToHost, st));
         if (d_raw) CUDA_TRY(cudaMemcpyAsync(raw_out + off * raw_cap, d_raw, m * raw_cap * sizeof(slr_guided_hit), cudaMemcpyDeviceToHost, st));

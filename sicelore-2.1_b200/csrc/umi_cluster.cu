@@ -21,7 +21,8 @@ namespace {
 __device__ __forceinline__ long long uc_job_of(const int32_t *__restrict__ rowjob, const long long *__restrict__ joff, long long n_jobs,
                                                long long r)
 {
-    if (rowjob) return rowjob[r];                     // left behind by the distance kernels
+    if (rowjob) return rowjob[r];                     // left behind by the distance kernels (-1: the read is in no job)
+    if (r < joff[0] || r >= joff[n_jobs]) return -1;  // padding rows before the first / behind the last job (as umi_rows_kernel marks them)
     long long lo = 0, hi = n_jobs;                    // last j with joff[j] <= r
     while (hi - lo > 1) {
         const long long mid = (lo + hi) >> 1;
