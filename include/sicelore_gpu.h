@@ -222,6 +222,59 @@ int  slr_umi_session_matrices(slr_umi_session *s, int32_t *out, int64_t n_cells)
 int64_t slr_umi_session_cells(const slr_umi_session *s);
 void slr_umi_session_destroy(slr_umi_session *s);
 
+/* ---- S6: clustering of the small jobs + UMI assignment --------------------------------------------------------- */
+
+/* Replaces ClusterOneHierarchical.call (F!com/rw/umifinder/analyzers/clustering/ClusterOneHierarchical.class,
+ * ClusterOneHierarchical.java:L61-L217) — the clusterer UmiClustering$Submitter picks for every job of at most 100 reads
+ * (UmiClustering.java:L239-L261; its static CLUSTERHOW is DECIDEONCOMPLEXITY, L50, so the pre-grouping branch L242-L244 is unreachable) —
+ * for ALL such jobs of a BAM chunk, fused behind the S2 matrices:
+ *   reads with a neighbour within umi_completelinkclusteringED              DistanceMatrix.java:L87-L90
+ *   LingPipe CompleteLinkClusterer (or SingleLinkClusterer above the switch threshold) on them, Dendrogram.partitionDistance(ED), clusters of
+ *   more than one read                                                      A!com/aliasi/cluster/CompleteLinkClusterer.java:L146-L237, Dendrogram.java:L205-L215
+ *   depth rule: size * foldDepthBelowMaxDiscardForClustering > largest cluster, else flagDontUMIassignRecords   ClusterOneHierarchical.java:L118-L127
+ *   OneUmiCluster.setClusterCenter                                          F!com/rw/clustering/OneUmiCluster.java:L49-L65
+ *   per read what ClusterOneBase.setSamflagsAndStatsForClustered derives    ClusterOneBase.java:L118-L168
+ * The caller keeps: the strings (U8 = getPostBCUMIseqOffset(centre read, offset_center_mean), U7 = the read's own window), the noUMIsoFar /
+ * SKIPPED_HIGHCOMPLEXITY guards (ClusterOneBase.java:L118-L123) and the statistics counters. */
+#define SLR_UA_ASSIGNED  1u   /* the read is in a cluster of the final list: setSamflagsAndStatsForClustered runs for it */
+#define SLR_UA_SKIPPED   2u   /* its cluster failed the depth rule: UMI_CLUSTERING_SKIPPED_HIGHCOMPLEXITY is set on the read */
+#define SLR_UA_TIE_UNPIN 4u   /* the reference's own result for this job depends on JVM identity hash codes (LingPipe's ObjectToSet keeps its
+                                 PairScores in a HashSet without hashCode()): equal-cost pairs created by one merge have no defined queue order
+                                 there.  The records follow creation order; a caller that wants its JVM's choice re-runs exactly these jobs. */
+#define SLR_UA_DEEP      8u   /* job of more than max_hier reads: ClusterOne_MyClustering's (slr_umi_cluster / the session API), untouched here */
+typedef struct slr_umi_assign_params {
+    int32_t ed_complete;      /* umi_completelinkclusteringED (config.xml:270), also the neighbour threshold */
+    int32_t ed_single;        /* umi_singlelinkclusteringED (config.xml:272) */
+    int32_t single_threshold; /* complexity_threshold_for_switch_to_single_link_clustering (config.xml:278: 3000, i.e. never for <= 100 reads) */
+    int32_t fold_depth;       /* foldDepthBelowMaxDiscardForClustering (UMIparameters.java:L118: 50) */
+    int32_t max_hier;         /* jobs up to this size are ClusterOneHierarchical's (UmiClustering.java:L240: 100; at most 100 here) */
+} slr_umi_assign_params;      /* NULL = { 2, 1, 3000, 50, 100 } */
+typedef struct slr_umi_assign_rec {
+    int32_t  center;              /* job-local index of OneUmiCluster.getCenter() of the read's cluster (U8 comes from that read); -1 = none */
+    int8_t   u1;                  /* UMI_ED (U1): distanceNonReducedSet(center, read) */
+    int8_t   u2;                  /* UMI_ED_SECOND_BEST_MATCH (U2): least distance to a read outside the cluster; -1 = the tag is not written */
+    int8_t   pos2;                /* matrix[center][read].getPos2(): 0 MINUSONE, 1 ZERO, 2 PLUSONE (the PREDICTED_POS statistics flag) */
+    int8_t   offset_center_mean;  /* offsetcentermean of the cluster: round(mean getPos1().getOffSet() of matrix[center][member]) */
+    uint16_t flags;               /* SLR_UA_* */
+    uint16_t cluster_size;
+    int32_t  n_clusters;          /* cluster_list.size() of the job (U2 is written only when > 1) */
+} slr_umi_assign_rec;             /* 16 bytes */
+/*   umis, stride, umi_len, job_offsets, n_jobs   as slr_umi_dist
+ *   job_qv01   NULL or one byte per job: mean_qv(job's read 0) > mean_qv(job's read 1) — the rule OneUmiCluster.java:L53 uses for clusters of two
+ *   out, out_offsets   the matrices as slr_umi_dist writes them, or out = NULL to leave them on the device
+ *   rec        one record per read, positional */
+int  slr_umi_assign(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
+                    const slr_umi_assign_params *params, const uint8_t *job_qv01, int32_t *out, const int64_t *out_offsets,
+                    slr_umi_assign_rec *rec);
+/* the same on matrices already on the device (as slr_umi_dist_dev left them); d_scratch: slr_umi_assign_scratch_bytes(n_jobs) bytes */
+int64_t slr_umi_assign_scratch_bytes(int64_t n_jobs);
+int  slr_umi_assign_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
+                        int64_t n_reads, const slr_umi_assign_params *params, const uint8_t *d_job_qv01, void *d_scratch,
+                        slr_umi_assign_rec *d_rec, void *stream);
+/* on the resident matrices of a session (see below) */
+struct slr_umi_session;
+int  slr_umi_session_assign(struct slr_umi_session *s, const slr_umi_assign_params *params, const uint8_t *job_qv01, slr_umi_assign_rec *rec);
+
 /* ---- S4: Illumina-guided barcode / UMI search ------------------------------------------------- */
 
 /* Replaces, for a batch of reads, the offset loop of IlluminaUMIanalyzer.findUMI (F!com/rw/umifinder/analyzers/

@@ -45,7 +45,7 @@ assert GUIDED_HIT.itemsize == 16
 
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
-           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_umi_session_create", "slr_umi_session_cluster",
+           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_umi_assign", "slr_umi_assign_dev", "slr_umi_assign_scratch_bytes", "slr_umi_session_assign", "slr_umi_session_create", "slr_umi_session_cluster",
            "slr_umi_session_matrices", "slr_umi_session_cells", "slr_umi_session_destroy", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
            "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count"]
 
@@ -74,7 +74,8 @@ def build(force=False, verbose=False):
     """Compile libsicelore_gpu.so (nvcc, sm_100a only) and libslr_synth.so (g++) in-tree."""
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
-    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "guided_match.cu")]
+    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu",
+                                           "guided_match.cu")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -123,6 +124,11 @@ def gpu_lib():
         L.slr_umi_dist_dev.argtypes = [vp, vp, i32, i32, vp, i64, i64, vp, vp, i64, vp]
         L.slr_umi_cluster.argtypes = [vp, vp, i32, i32, vp, i64, i32, vp, vp, vp, vp, vp]
         L.slr_umi_cluster_dev.argtypes = [vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
+        L.slr_umi_assign.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp]
+        L.slr_umi_assign_dev.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp]
+        L.slr_umi_assign_scratch_bytes.argtypes = [i64]
+        L.slr_umi_assign_scratch_bytes.restype = i64
+        L.slr_umi_session_assign.argtypes = [vp, vp, vp, vp]
         L.slr_umi_session_create.argtypes = [vp, vp, i32, i32, vp, i64, C.POINTER(vp)]
         L.slr_umi_session_cluster.argtypes = [vp, i32, vp, vp, vp]
         L.slr_umi_session_matrices.argtypes = [vp, vp, i64]
@@ -600,6 +606,46 @@ def cluster_local(ctx, umis, job_offsets, ed, umi_len=12, member=None, rank=None
     return (rec, out, out_offsets) if want_matrices else rec
 
 
+UMI_ASSIGN_REC = np.dtype([("center", "<i4"), ("u1", "i1"), ("u2", "i1"), ("pos2", "i1"), ("offset_center_mean", "i1"), ("flags", "<u2"),
+                           ("cluster_size", "<u2"), ("n_clusters", "<i4")], align=True)
+assert UMI_ASSIGN_REC.itemsize == 16
+UA_ASSIGNED, UA_SKIPPED, UA_TIE_UNPIN, UA_DEEP = 1, 2, 4, 8
+
+
+class UmiAssignParams(C.Structure):
+    """The clustering knobs ClusterOneHierarchical reads (config.xml:270-278, UMIparameters.java:L96-L118, UmiClustering.java:L240)."""
+    _fields_ = [("ed_complete", C.c_int32), ("ed_single", C.c_int32), ("single_threshold", C.c_int32), ("fold_depth", C.c_int32),
+                ("max_hier", C.c_int32)]
+
+    def __init__(self, umi_completelinkclusteringED=2, umi_singlelinkclusteringED=1, complexity_threshold_for_switch_to_single_link_clustering=3000,
+                 foldDepthBelowMaxDiscardForClustering=50, max_hier=100):
+        super().__init__(umi_completelinkclusteringED, umi_singlelinkclusteringED, complexity_threshold_for_switch_to_single_link_clustering,
+                         foldDepthBelowMaxDiscardForClustering, max_hier)
+
+
+def cluster_one_hierarchical(ctx, umis, job_offsets, umi_len=12, params=None, job_qv01=None, want_matrices=False):
+    """ClusterOneHierarchical.call (ClusterOneHierarchical.java:L61-L217) for all jobs of at most 100 reads at once, fused behind the distance
+    matrices: LingPipe complete link on the reads with a neighbour, the cut at umi_completelinkclusteringED, the depth rule, the cluster
+    centres and, per read, the values setSamflagsAndStatsForClustered writes (centre, U1, U2, +-1 shift, mean shift of the cluster).
+    Returns UMI_ASSIGN_REC [m] (+ the flat matrices and their offsets when asked)."""
+    umis = np.ascontiguousarray(umis, dtype=np.uint8)
+    job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+    m = int(job_offsets[-1]) if len(job_offsets) else 0
+    rec = np.zeros(m, dtype=UMI_ASSIGN_REC)
+    qv = None if job_qv01 is None else np.ascontiguousarray(job_qv01, dtype=np.uint8)
+    if qv is not None and qv.shape != (len(job_offsets) - 1,):
+        raise ValueError("job_qv01 must hold one byte per job")
+    out = out_offsets = None
+    if want_matrices:
+        out_offsets = out_offsets_for(job_offsets)
+        out = np.empty(int(out_offsets[-1]), dtype=np.int32)
+    _check(gpu_lib().slr_umi_assign(ctx.h, umis.ctypes.data, umis.shape[1] if umis.ndim == 2 else 16, umi_len, job_offsets.ctypes.data,
+                                    len(job_offsets) - 1, C.byref(params) if params is not None else None,
+                                    qv.ctypes.data if qv is not None else None, out.ctypes.data if out is not None else None,
+                                    out_offsets.ctypes.data if out_offsets is not None else None, rec.ctypes.data))
+    return (rec, out, out_offsets) if want_matrices else rec
+
+
 class UmiSession:
     """The matrices of one batch of (cell, region) jobs kept on the device between calls (slr_umi_session_*): the distance kernels run
     once, cluster() can then be called with the caller's key order (`rank`) once the keys are known, and again on the unclustered
@@ -624,6 +670,14 @@ class UmiSession:
             assert rank.shape == (self.n_reads,)
         _check(gpu_lib().slr_umi_session_cluster(self.h, int(ed), member.ctypes.data if member is not None else None,
                                                  rank.ctypes.data if rank is not None else None, rec.ctypes.data))
+        return rec
+
+    def assign(self, params=None, job_qv01=None):
+        """ClusterOneHierarchical.call on the resident matrices (jobs of at most 100 reads): UMI_ASSIGN_REC per read"""
+        rec = np.zeros(self.n_reads, dtype=UMI_ASSIGN_REC)
+        qv = None if job_qv01 is None else np.ascontiguousarray(job_qv01, dtype=np.uint8)
+        _check(gpu_lib().slr_umi_session_assign(self.h, C.byref(params) if params is not None else None,
+                                                qv.ctypes.data if qv is not None else None, rec.ctypes.data))
         return rec
 
     def matrices(self):

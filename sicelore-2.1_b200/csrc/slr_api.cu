@@ -83,6 +83,7 @@ struct Slot {
     DevBuf umi[2], joff[2], ooff[2], uout[2], uscr[2];
     DevBuf jraw[2], jtmp[2];                   // the caller's job offsets of the range in flight + scan scratch (rebased on the device)
     DevBuf ucl[2];                             // slr_umi_cluster: counts | records | rank | member of the range in flight
+    DevBuf uas[2];                             // slr_umi_assign: records | qv flags | job lists of the range in flight
     cudaEvent_t uscr_free = nullptr;           // recorded after the last launch that uses uscr[0] on a caller's stream (slr_umi_dist_dev)
     DevBuf gsl, ganc, ggid, ged, gout, graw, gvis;   // Illumina-guided search: staging buffers + the per-warp visited tables
     cudaEvent_t gvis_free = nullptr;           // recorded after the last guided launch that uses gvis
@@ -201,7 +202,7 @@ void slr_ctx_destroy(slr_ctx *c)
             if (s->stream[k]) { cudaStreamSynchronize(s->stream[k]); cudaStreamDestroy(s->stream[k]); }
             s->slices[k].release(); s->anchor[k].release(); s->lens[k].release(); s->out[k].release();
         }
-        for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); s->ucl[k].release(); s->jraw[k].release(); s->jtmp[k].release(); }
+        for (int k = 0; k < 2; k++) { s->umi[k].release(); s->joff[k].release(); s->ooff[k].release(); s->uout[k].release(); s->uscr[k].release(); s->ucl[k].release(); s->uas[k].release(); s->jraw[k].release(); s->jtmp[k].release(); }
         if (s->uscr_free) cudaEventDestroy(s->uscr_free);
         if (s->gvis_free) cudaEventDestroy(s->gvis_free);
         s->gsl.release(); s->ganc.release(); s->ggid.release(); s->ged.release(); s->gout.release(); s->graw.release(); s->gvis.release();
@@ -503,10 +504,28 @@ struct ClusterArgs {                           // slr_umi_cluster rides on the r
     const int32_t *rank = nullptr;
     slr_umi_cluster_rec *rec = nullptr;
 };
+struct AssignArgs {                            // slr_umi_assign: the same ride
+    slr_umi_assign_params P;
+    const uint8_t *job_qv01 = nullptr;
+    slr_umi_assign_rec *rec = nullptr;
+};
+const slr_umi_assign_params ASSIGN_DEFAULTS = {2, 1, 3000, 50, 100};   // config.xml:270-278, UMIparameters.java:L118, UmiClustering.java:L240
+
+int check_assign_params(const slr_umi_assign_params *p, slr_umi_assign_params &out)
+{
+    out = p ? *p : ASSIGN_DEFAULTS;
+    if (out.ed_complete < 0 || out.ed_complete > 5 || out.ed_single < 0 || out.ed_single > 5)
+        return fail(SLR_E_INVALID, "slr_umi_assign: clustering edit distances %d / %d outside 0..5", out.ed_complete, out.ed_single);
+    if (out.fold_depth < 1) return fail(SLR_E_INVALID, "slr_umi_assign: foldDepthBelowMaxDiscardForClustering %d < 1", out.fold_depth);
+    if (out.max_hier < 0 || out.max_hier > 100)
+        return fail(SLR_E_UNSUPPORTED, "slr_umi_assign: max_hier %d (ClusterOneHierarchical takes jobs of at most 100 reads)", out.max_hier);
+    if (out.single_threshold < 0) return fail(SLR_E_INVALID, "slr_umi_assign: negative single-link threshold");
+    return SLR_OK;
+}
 }  // namespace
 
 static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
-                           int32_t *out, const int64_t *out_offsets, const ClusterArgs *cl)
+                           int32_t *out, const int64_t *out_offsets, const ClusterArgs *cl, const AssignArgs *as = nullptr)
 {
     int rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -568,6 +587,17 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
                 g_launches += SLR_UMI_CLUSTER_LAUNCHES;
                 CUDA_TRY(cudaMemcpyAsync(cl->rec + r0, base + o_rec, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
             }
+            if (as) {
+                const size_t o_qv = (size_t)nr * sizeof(slr_umi_assign_rec), o_list = (o_qv + (size_t)nj_range + 15) & ~(size_t)15;
+                if ((rc = s->uas[b].reserve(o_list + slr_umi_assign_scratch(nj_range)))) return rc;
+                char *base = (char *)s->uas[b].p;
+                if (as->job_qv01) CUDA_TRY(cudaMemcpyAsync(base + o_qv, as->job_qv01 + j, (size_t)nj_range, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(slr_launch_umi_assign((const int32_t *)s->uout[b].p, (const long long *)s->joff[b].p, (const long long *)s->ooff[b].p,
+                                               nj_range, nr, as->P, as->job_qv01 ? (const uint8_t *)(base + o_qv) : nullptr,
+                                               slr_umi_scratch_rowjob(s->uscr[b].p, nr), (slr_umi_assign_rec *)base, base + o_list, st));
+                g_launches += SLR_UMI_ASSIGN_LAUNCHES;
+                CUDA_TRY(cudaMemcpyAsync(as->rec + r0, base, (size_t)nr * sizeof(slr_umi_assign_rec), cudaMemcpyDeviceToHost, st));
+            }
             if (out && packed) {                                           // the usual layout: the range is one contiguous piece of `out`
                 if (cells > 0)
                     CUDA_TRY(cudaMemcpyAsync(out + out_offsets[j], s->uout[b].p, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
@@ -628,6 +658,40 @@ int slr_umi_cluster(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, 
     return umi_dist_ranges(ctx, umis, stride, umi_len, job_offsets, n_jobs, out, out_offsets, &cl);
 }
 
+int slr_umi_assign(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
+                   const slr_umi_assign_params *params, const uint8_t *job_qv01, int32_t *out, const int64_t *out_offsets,
+                   slr_umi_assign_rec *rec)
+{
+    int rc = check_umi_args(ctx, stride, umi_len, n_jobs);
+    if (rc) return rc;
+    AssignArgs as;
+    if ((rc = check_assign_params(params, as.P))) return rc;
+    if (n_jobs == 0) return SLR_OK;
+    if (!umis || !job_offsets || !rec || (out && !out_offsets)) return fail(SLR_E_INVALID, "slr_umi_assign: NULL buffer");
+    as.job_qv01 = job_qv01; as.rec = rec;
+    return umi_dist_ranges(ctx, umis, stride, umi_len, job_offsets, n_jobs, out, out_offsets, nullptr, &as);
+}
+
+int64_t slr_umi_assign_scratch_bytes(int64_t n_jobs) { return (int64_t)slr_umi_assign_scratch(n_jobs > 0 ? n_jobs : 0); }
+
+int slr_umi_assign_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
+                       int64_t n_reads, const slr_umi_assign_params *params, const uint8_t *d_job_qv01, void *d_scratch,
+                       slr_umi_assign_rec *d_rec, void *stream)
+{
+    if (!ctx) return fail(SLR_E_INVALID, "slr_umi_assign_dev: ctx is NULL");
+    slr_umi_assign_params P;
+    int rc = check_assign_params(params, P);
+    if (rc) return rc;
+    if (n_jobs < 0 || n_reads < 0) return fail(SLR_E_INVALID, "slr_umi_assign_dev: negative size");
+    if (n_jobs == 0 || n_reads == 0) return SLR_OK;
+    if (!d_matrices || !d_job_offsets || !d_out_offsets || !d_scratch || !d_rec) return fail(SLR_E_INVALID, "slr_umi_assign_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(slr_launch_umi_assign(d_matrices, (const long long *)d_job_offsets, (const long long *)d_out_offsets, n_jobs, n_reads, P, d_job_qv01,
+                                   nullptr, d_rec, d_scratch, (cudaStream_t)stream));
+    g_launches += SLR_UMI_ASSIGN_LAUNCHES;
+    return SLR_OK;
+}
+
 int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
                         int64_t n_reads, int ed, const uint8_t *d_member, const int32_t *d_rank, int32_t *d_counts,
                         slr_umi_cluster_rec *d_rec, void *stream)
@@ -651,11 +715,11 @@ int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *
 struct slr_umi_session {
     slr_ctx *ctx = nullptr;
     int64_t n_jobs = 0, n_reads = 0, cells = 0;
-    DevBuf umis, jraw, jtmp, joff, ooff, mat, scr, counts, rec, rank, member;
+    DevBuf umis, jraw, jtmp, joff, ooff, mat, scr, counts, rec, rank, member, arec, aqv, ascr;
     void release()
     {
         umis.release(); jraw.release(); jtmp.release(); joff.release(); ooff.release(); mat.release(); scr.release(); counts.release();
-        rec.release(); rank.release(); member.release();
+        rec.release(); rank.release(); member.release(); arec.release(); aqv.release(); ascr.release();
     }
     ~slr_umi_session() { release(); }
 };
@@ -738,6 +802,33 @@ int slr_umi_session_cluster(slr_umi_session *S, int ed, const uint8_t *member, c
                                                   (int32_t *)S->counts.p, (slr_umi_cluster_rec *)S->rec.p, work, st));
     g_launches += SLR_UMI_CLUSTER_LAUNCHES;
     CUDA_TRY(cudaMemcpyAsync(rec, S->rec.p, m * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SLR_OK;
+}
+
+int slr_umi_session_assign(slr_umi_session *S, const slr_umi_assign_params *params, const uint8_t *job_qv01, slr_umi_assign_rec *rec)
+{
+    if (!S) return fail(SLR_E_INVALID, "slr_umi_session_assign: session is NULL");
+    slr_umi_assign_params P;
+    int rc = check_assign_params(params, P);
+    if (rc) return rc;
+    if (S->n_reads == 0) return SLR_OK;
+    if (!rec) return fail(SLR_E_INVALID, "slr_umi_session_assign: rec is NULL");
+    slr_ctx *ctx = S->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Slot *sl = ctx->slots[ctx->next.fetch_add(1) % (unsigned)ctx->n_slots];
+    std::lock_guard<std::mutex> lock(sl->mtx);
+    cudaStream_t st = sl->stream[0];
+    const size_t m = (size_t)S->n_reads;
+    if ((rc = S->arec.reserve(m * sizeof(slr_umi_assign_rec))) || (rc = S->aqv.reserve((size_t)S->n_jobs + 1)) ||
+        (rc = S->ascr.reserve(slr_umi_assign_scratch(S->n_jobs))))
+        return rc;
+    if (job_qv01) CUDA_TRY(cudaMemcpyAsync(S->aqv.p, job_qv01, (size_t)S->n_jobs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(slr_launch_umi_assign((const int32_t *)S->mat.p, (const long long *)S->joff.p, (const long long *)S->ooff.p, S->n_jobs, S->n_reads, P,
+                                   job_qv01 ? (const uint8_t *)S->aqv.p : nullptr, slr_umi_scratch_rowjob(S->scr.p, S->n_reads),
+                                   (slr_umi_assign_rec *)S->arec.p, S->ascr.p, st));
+    g_launches += SLR_UMI_ASSIGN_LAUNCHES;
+    CUDA_TRY(cudaMemcpyAsync(rec, S->arec.p, m * sizeof(slr_umi_assign_rec), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return SLR_OK;
 }

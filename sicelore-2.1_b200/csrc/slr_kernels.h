@@ -26,6 +26,14 @@ cudaError_t slr_launch_umi_cluster(const int32_t *d_mat, const long long *d_job_
                                    long long n_reads, int ed, const uint8_t *d_member, const int32_t *d_rank, const int32_t *d_rowjob,
                                    int32_t *d_counts, slr_umi_cluster_rec *d_out, unsigned long long *d_range, cudaStream_t stream);
 
+// ClusterOneHierarchical.call for every job of at most P.max_hier reads + the per-read assignment values (umi_assign.cu); three kernels.
+// d_scratch: slr_umi_assign_scratch(n_jobs) bytes (job lists); d_rowjob as for slr_launch_umi_cluster (NULL: binary search)
+constexpr int SLR_UMI_ASSIGN_LAUNCHES = 3;
+size_t slr_umi_assign_scratch(long long n_jobs);
+cudaError_t slr_launch_umi_assign(const int32_t *d_mat, const long long *d_job_offsets, const long long *d_out_offsets, long long n_jobs,
+                                  long long n_reads, const slr_umi_assign_params &P, const uint8_t *d_job_qv01, const int32_t *d_rowjob,
+                                  slr_umi_assign_rec *d_rec, void *d_scratch, cudaStream_t stream);
+
 // a range of the caller's CSR job offsets (d_raw: n_jobs + 1 entries) rebased on the device: d_joff = raw - r0, d_ooff = exclusive prefix
 // sum of the squared job sizes (both n_jobs + 1 entries); d_tmp: slr_umi_rebase_tmp_bytes(n_jobs); three kernels
 constexpr int SLR_UMI_REBASE_LAUNCHES = 3;

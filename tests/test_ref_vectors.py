@@ -150,7 +150,98 @@ def test_assign_barcode_matches_reference_bytecode(orc):
     assert seen[1] >= 10 and seen[0] >= 3 and seen[2] >= 1, seen
 
 
+def _check_wide_row(i, r, status, row, ap, tp, what):
+    """one record (oracle or GPU) against the BarcodeResult fields Parser.assignBarcode produced in the interpreter"""
+    if status == 2:
+        assert r["flags"] & 2, (what, i, r)
+        return
+    assert not (r["flags"] & 2), (what, i, r)
+    if status == 0:
+        assert not (r["flags"] & 1), (what, i, r)
+        return
+    bc, e, e2, start, end, rk, _flag = (int(x) for x in row)
+    off = int(r["offset"])
+    g_start = ap - 1 + off if tp else ap + 1 + off              # Parser.java:L274-L276
+    d = int(r["n_ins"]) - int(r["n_del"])
+    g_end = g_start - 15 - d if tp else g_start + 15 + d        # L278-L279
+    assert r["flags"] & 1 and (int(r["bc"]), int(r["ed"]), int(r["ed_second"]), g_start, g_end, int(r["rank"])) == \
+           (bc, e, int(np.int32(e2)), start, end, rk), (what, i, r, row)
+
+
+def _wide_constructed(z):
+    for t in range(len(z["c_read"])):
+        keys = z["c_keys"][z["c_key_offsets"][t]:z["c_key_offsets"][t + 1]]
+        yield t, str(z["c_read"][t]).encode(), keys, np.arange(1, len(keys) + 1, dtype=np.int32), int(z["c_ap"][t]), bool(z["c_tp"][t]), int(z["c_pm"][t])
+
+
+def test_assign_barcode_wide_matches_reference_bytecode(orc):
+    """>= 550 whole reads through the reference's own Parser.assignBarcode bytecode at --bcEditDistance 2 (oracle/make_ref_assign_wide.py):
+    the first reads of bench.py's bc3m_ed2 workload against the part of the 3 M list the reference can probe for them (so the frozen
+    results are its results on the full list), and constructed periodic reads whose merged HashSet<OneMatch> holds 9 ... 27 entries
+    (same-bin chains, 16 -> 32 -> 64 resizes, +-1 ... +-4 windows)."""
+    z = np.load(os.path.join(GOLDEN, "ref_assign_wide.npz"))
+    n = len(z["anchor"])
+    assert n >= 500 and len(z["c_read"]) >= 50
+    res, _ = orc.assign_barcode_batch(orc.BarcodeSet(z["U"], z["U_rank"]), z["slices"], z["anchor"], 2, 2, True)
+    for i in range(n):
+        _check_wide_row(i, res[i], int(z["status"][i]), z["result"][i], int(z["anchor"][i]) + 17, True, "oracle/bench")
+    assert np.bincount(z["status"], minlength=3)[1] > 0.5 * n
+    many = 0
+    for t, read, keys, rank, ap, tp, pm in _wide_constructed(z):
+        anchor = (ap - 16) - 1 if tp else ap
+        sl = np.frombuffer(read, dtype=np.uint8).reshape(1, -1).copy()
+        bset = orc.BarcodeSet(keys, rank)
+        r, _ = orc.assign_barcode_batch(bset, sl, np.array([anchor], dtype=np.int32), 2, pm, tp, slice_len=len(read))
+        _check_wide_row(t, r[0], int(z["c_status"][t]), z["c_result"][t], ap, tp, "oracle/constructed")
+        entries = 0                                              # merged OneMatch entries = hits per (window, ED level)
+        for o in range(-pm, pm + 1):
+            ws = anchor + o
+            if ws < 4 or ws + 21 > len(read):
+                continue
+            w = read[ws:ws + 16]
+            if tp:
+                seq = orc.lib().orc_revcomp2bit(orc.lib().orc_pack2bit(w, 16, None), 16)
+            else:
+                seq = orc.lib().orc_pack2bit(w, 16, None)
+            post = read[ws - 4:ws + 1][::-1].translate(bytes.maketrans(b"ACGT", b"TGCA")) if tp else read[ws + 16:ws + 21]
+            p4 = np.array([orc.lib().orc_encode4bit(c) for c in post], dtype=np.uint8)
+            m = orc.match_tester(bset, seq, 16, 2, post4=p4, offset=o)
+            entries += 0 if m is None else len(m)
+        many += entries >= 9
+    assert many >= 20, many                                      # the resize / chain paths of slr_decide are really exercised
+
+
 # ------------------------------------------------------------------------------------------------------------- GPU vs the reference's bytecode
+@pytest.mark.gpu
+def test_gpu_assign_barcode_wide_matches_reference_bytecode(pkg, ctx):
+    """the CUDA kernel through the C ABI against the wide vectors: once with the probe-able part of the list as the table, once with the
+    FULL 3 M list (same records: the reference cannot probe anything else for these reads), and the constructed many-entry reads"""
+    z = np.load(os.path.join(GOLDEN, "ref_assign_wide.npz"))
+    n = len(z["anchor"])
+    wl = pkg.synth_whitelist(3_000_000, 3_000_000)
+    for keys, rank, what in ((z["U"], z["U_rank"], "gpu/U"), (wl, np.arange(1, len(wl) + 1, dtype=np.int32), "gpu/3M")):
+        table = pkg.BarcodesMapForBCfinding(ctx, keys, rank)
+        res = pkg.Parser(ctx, table, bcEditDistance=2, testPlusMinusPos=2, three_prime=True).assign_barcodes(z["slices"], z["anchor"])
+        for i in range(n):
+            _check_wide_row(i, res[i], int(z["status"][i]), z["result"][i], int(z["anchor"][i]) + 17, True, what)
+        table.close()
+    for t, read, keys, rank, ap, tp, pm in _wide_constructed(z):
+        anchor = (ap - 16) - 1 if tp else ap
+        start = min(max(anchor - 10, 0), max(len(read) - 32, 0))
+        piece = read[start:start + 32]
+        sl = np.zeros((1, 32), dtype=np.uint8)
+        sl[0, :len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+        table = pkg.BarcodesMapForBCfinding(ctx, keys, rank)
+        r = pkg.Parser(ctx, table, bcEditDistance=2, testPlusMinusPos=pm, three_prime=tp).assign_barcodes(
+            sl, np.array([anchor - start], dtype=np.int32), lens=np.array([len(piece)], dtype=np.int32))[0]
+        # a 32-byte slice cannot hold +-4 windows with their flanks: those reads are oracle-only (the C ABI takes slices of <= 32 bytes)
+        lo, hi = (anchor - pm - 4, anchor + pm + 16) if tp else (anchor - pm, anchor + pm + 21)
+        if lo - start < 0 or hi - start > len(piece):
+            continue
+        _check_wide_row(t, r, int(z["c_status"][t]), z["c_result"][t], ap, tp, "gpu/constructed")
+        table.close()
+
+
 @pytest.mark.gpu
 def test_gpu_assign_barcode_matches_reference_bytecode(pkg, ctx):
     """the CUDA kernel through the C ABI, directly against Parser.assignBarcode as run from the reference's class files"""
