@@ -4,20 +4,27 @@
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
   python bench.py --impl reference ...      # the reference algorithm on the host cores (CPU oracle port, see below)
+  python bench.py --workload umi5kx2k       # BASELINE.json configs[3]; bc737k_ed1 = configs[1]; default bc3m_ed2 = configs[2] (configs[4] at N = 8)
 
-One step = one pass of the hot path over one batch per GPU (weak scaling: every rank gets its own shard of the run):
-  S1  slr_bc_assign    R reads x 5 window offsets vs the 3 M-barcode list at --bcEditDistance 2   (BASELINE.json configs[2])
-  S2  slr_umi_dist     the same R reads grouped into (cell, region) jobs (geometric, mean 4) -> packed 3x3 distance matrices
-  (N > 1) two cross-shard exchanges over NCCL: the (cell, region) group cut by every shard boundary is merged onto the lower rank
-          (all_gather of the boundary reads, UmiShardMerger) and the per-barcode x ED counters (BarcodesAssigned.tsv) are all-reduced.
+One step = one pass of the hot path over one batch per GPU (weak scaling: every rank owns its shard of the run's read stream):
+  S1  slr_bc_assign   R reads x 5 window offsets vs the barcode list at --bcEditDistance                 (Parser.assignBarcode)
+  S2  slr_umi_dist    the (cell, region) jobs of the shard -> packed 3x3 distance matrices, left in HBM  (generateDistanceMatrix)
+  S6  slr_umi_assign  ClusterOneHierarchical on every job of <= 100 reads: clusters, centres, U1 / U2     (UMI assignment to SAM records)
+  S5  slr_umi_cluster clusterLocal's two matrix passes on the deeper jobs (workload umi5kx2k only: the bc workloads have none)
+  N > 1: the UMI read stream is the run's global (cell, region)-sorted stream cut by read index, so a job can straddle a shard boundary: it
+  is clustered as ONE job on the lower rank (UmiShardMerger: all_gather of the boundary reads over NCCL, inside every step).  The
+  per-barcode x ED counters (BarcodesAssigned.tsv) are all-reduced once per run, after the timed steps.
 `value`  : reads/s with all inputs already resident in HBM, timed with CUDA events on the launching stream.
-`e2e`    : the same step through the host-pointer C ABI (slr_bc_assign / slr_umi_dist) from pinned host buffers, H2D and
-           D2H copies inside the timed region.
-The reference arm cannot be the real thing: the path exists only as JVM bytecode and this image has no JVM.  It times
-the CPU oracle (a restatement of the reference algorithm, oracle/slr_oracle.c, kind = "port") with every host thread
-on a bounded sample of the same workload.
+`e2e`    : the same step through the host-pointer C ABI (slr_bc_assign / slr_umi_assign) from pinned host buffers, H2D and D2H copies
+           inside the timed region, a barrier before every step so that `ms_steps` means the same on every rank.
+`roofline`: the dominant kernel against the INT-issue peak (warp instructions per unit from an ncu profile under profiles/ whose source
+           hash equals the loaded library's, x units, / (SMs x 4 schedulers x SM clock x kernel time)); `roofline_hbm` = its measured DRAM
+           bytes against MEASURED_PEAKS.json; `reference_equivalent_gbs` = SURVEY.md 8d's bytes of the REFERENCE algorithm (not a utilisation).
+The reference arm cannot be the real thing: the path exists only as JVM bytecode and this image has no JVM.  It times the CPU oracle
+(a restatement of the reference algorithm, oracle/, kind = "port") with every host thread on a bounded sample of the same workload.
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -32,10 +39,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "reads/sec barcode+UMI assigned (ED<=2, 3M list) at 1/2/4/8 B200 vs host CPU"
 WORKLOADS = {
-    # name: (list size, list seed, read seed, bcEditDistance)
-    "bc3m_ed2": (3_000_000, 3_000_000, 2, 2),       # BASELINE.json configs[2] — the configuration `metric` is quoted on
-    "bc737k_ed1": (737_280, 737, 1, 1),             # configs[1]
+    # name: (list size, list seed, read seed, bcEditDistance, kind)
+    "bc3m_ed2": (3_000_000, 3_000_000, 2, 2, "bc"),       # BASELINE.json configs[2] — the configuration `metric` is quoted on; configs[4] at N = 8
+    "bc737k_ed1": (737_280, 737, 1, 1, "bc"),             # configs[1]
+    "umi5kx2k": (0, 0, 0, 0, "umi"),                      # configs[3]: UMI distance + clustering + assignment, 5 k cells x 2 k genes
 }
+UMI_SEED, UMI_MEAN, UMI_CAP = 4, 4.0, 2000
+DEEP_JOB = 20_000                                          # the targeted-sequencing stress job of configs[3]
 
 
 def parse():
@@ -45,10 +55,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bc3m_ed2", choices=sorted(WORKLOADS))
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = 10 M; 12.5 M at 8 GPUs = the 100 M-read run of configs[4]; "
+                                                         "40 M for umi5kx2k)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads of the CPU sample (0 = sized for ~20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-umi", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the NUMA node of its GPU")
     return ap.parse_args()
 
 
@@ -107,25 +119,76 @@ class CudaArrayView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def umi_jobs_for(pkg, n_reads, seed):
-    """(cell, region) jobs whose sizes sum to exactly n_reads (geometric, mean 4, cap 2000): SURVEY.md §8d config 4 shape"""
-    n_jobs = int(n_reads / 4 * 1.05) + 1000            # enough jobs for the sizes to sum past n_reads
-    umis, offs = pkg.synth_umi_jobs(n_jobs, mean=4.0, cap=2000, seed=seed)
-    k = int(np.searchsorted(offs, n_reads, side="right")) - 1
-    offs = offs[:k + 1].copy()
-    if offs[-1] < n_reads:
-        offs = np.append(offs, n_reads)
-    return np.ascontiguousarray(umis[:n_reads]), offs
+def bind_to_gpu_numa(local_rank):
+    """Run this rank (and first-touch its pinned staging memory) on the NUMA node its GPU hangs off: at N = 8 every rank moves ~1 GB per step
+    through the host, and a remote socket halves the link.  Returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "bound to numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as ex:
+        return "not bound (%s)" % type(ex).__name__
 
 
-def cpu_reference_step(orc, bset, slices, anchor, ed, umis, offs, threads):
+def umi_jobs_for(pkg, n_reads, rank=0):
+    """this rank's piece of the global (cell, region)-sorted read stream: reads [rank * n, (rank + 1) * n)"""
+    return pkg.synth_umi_shard(rank * n_reads, n_reads, UMI_MEAN, UMI_CAP, UMI_SEED)
+
+
+def umi5kx2k_batch(pkg, n_reads, rank):
+    """configs[3]-shaped batch: geometric (cell, gene) jobs (mean 4, cap 2000) + one deep targeted-sequencing job of DEEP_JOB reads"""
+    umis, offs, j0, j1 = pkg.synth_umi_shard(rank * n_reads, n_reads - DEEP_JOB, UMI_MEAN, UMI_CAP, UMI_SEED)
+    du, doff = pkg.synth_umi_jobs(1, mean=1e9, cap=DEEP_JOB, seed=77 + rank)
+    return np.concatenate([umis, du]), np.concatenate([offs, [offs[-1] + DEEP_JOB]]).astype(np.int64), j0, j1
+
+
+def cpu_reference_step(orc, kind, bset, slices, anchor, ed, umis, offs, threads):
     t0 = time.perf_counter()
-    res, probes = orc.assign_barcode_batch(bset, slices, anchor, ed, 2, True, n_threads=threads)
+    res, probes = (None, 0)
+    if kind == "bc":
+        res, probes = orc.assign_barcode_batch(bset, slices, anchor, ed, 2, True, n_threads=threads)
     t1 = time.perf_counter()
+    arec = None
     if umis is not None:
-        orc.umi_matrix_batch(umis, offs, 12, n_threads=threads)
+        mats, oo = orc.umi_matrix_batch(umis, offs, 12, n_threads=threads)
+        arec = orc.umi_assign_batch(mats, offs, oo, None, None, n_threads=threads)
+        if kind == "umi":
+            orc.umi_cluster_batch(mats, offs, oo, 2, n_threads=threads)
     t2 = time.perf_counter()
-    return t2 - t0, t1 - t0, probes, res
+    return t2 - t0, t1 - t0, probes, res, arec
+
+
+def load_profile(pkg, kernel):
+    """newest profiles/r*_kernel_profile.json entry for `kernel` whose source hash equals the loaded library's; None otherwise"""
+    want = pkg.csrc_sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernel_profile*.json")), reverse=True):
+        try:
+            prof = json.load(open(f))
+        except Exception:
+            continue
+        if prof.get("csrc_sha256") != want:
+            continue
+        for k in prof.get("kernels", []):
+            if kernel == k.get("kernel", ""):
+                return dict(k, file=os.path.relpath(f, ROOT), csrc_sha256=want)
+    return None
 
 
 def main():
@@ -133,31 +196,45 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_wl, wl_seed, read_seed, ed = WORKLOADS[a.workload]
+    n_wl, wl_seed, read_seed, ed, kind = WORKLOADS[a.workload]
     import __graft_entry__ as g
     pkg = g.load_package()
     threads = os.cpu_count() or 1
-    config = {"workload": "%s: %d synthetic 3' reads/GPU/step vs %d-barcode synthetic whitelist, bcEditDistance %d, "
-                          "testPlusMinusPos 2%s" % (a.workload, a.reads, n_wl, ed, "" if a.no_umi else
-                                                    " + UMI distance matrices of the same reads in (cell,region) jobs (mean 4)"),
-              "reads_per_gpu_per_step": a.reads, "whitelist": n_wl, "bc_edit_distance": ed, "sharding": "reads sharded, list replicated; N>1: boundary UMI groups merged (all_gather) + counters all-reduced over NCCL",
-              "l2_policy": "inputs larger than L2 (320 MB of slices per step) + table random access"}
+    R = a.reads or (40_000_000 if kind == "umi" else (12_500_000 if world == 8 else 10_000_000))
+    use_umi = kind == "umi" or not a.no_umi
+    if kind == "bc":
+        wtxt = ("%s: %d synthetic 3' reads/GPU/step vs %d-barcode synthetic whitelist, bcEditDistance %d, testPlusMinusPos 2%s"
+                % (a.workload, R, n_wl, ed, "" if not use_umi else " + UMI distance matrices, ClusterOneHierarchical clustering and per-read UMI "
+                   "assignment of the same number of reads in (cell,region) jobs (geometric, mean 4)"))
+    else:
+        wtxt = ("umi5kx2k: %d reads/GPU/step in (cell,gene) jobs (geometric, mean 4, cap 2000) + one %d-read job: UMI distance matrices, "
+                "ClusterOneHierarchical (jobs <= 100 reads) / clusterLocal passes (deeper jobs), per-read UMI assignment" % (R, DEEP_JOB))
+    config = {"workload": wtxt, "reads_per_gpu_per_step": R, "whitelist": n_wl, "bc_edit_distance": ed,
+              "sharding": "reads sharded by index, list replicated; N>1: (cell,region) jobs cut by a shard boundary merged onto the lower rank "
+                          "(all_gather over NCCL, every step); counters all-reduced once per run",
+              "l2_policy": "inputs larger than L2 (%d MB of read slices / UMI codes per step) + table random access" % (R * 48 // 1_000_000)}
 
     # ------------------------------------------------------------------------------------------ reference arm
     if a.impl == "reference":
         if rank != 0:
             return
         from oracle import orc
-        wl = pkg.synth_whitelist(n_wl, wl_seed)
-        bset = orc.BarcodeSet(wl, np.arange(1, n_wl + 1, dtype=np.int32))
-        # bounded sample: calibrate on 2 000 reads, then size one step to ~4 s of host time
-        cs, ca, _ = pkg.synth_reads(wl, 2000, seed=read_seed)
-        cpu_reference_step(orc, bset, cs[:200], ca[:200], ed, None, None, threads)
-        tcal = cpu_reference_step(orc, bset, cs, ca, ed, None, None, threads)[0]
-        n_s = a.cpu_sample or int(min(2_000_000, max(2000, 4.0 * 2000 / tcal)))
-        slices, anchor, _ = pkg.synth_reads(wl, n_s, seed=read_seed)
-        umis, offs = (None, None) if a.no_umi else umi_jobs_for(pkg, n_s, 4)
-        ts = [cpu_reference_step(orc, bset, slices, anchor, ed, umis, offs, threads)[0] for _ in range(a.steps)]
+        bset = None
+        if kind == "bc":
+            wl = pkg.synth_whitelist(n_wl, wl_seed)
+            bset = orc.BarcodeSet(wl, np.arange(1, n_wl + 1, dtype=np.int32))
+            # bounded sample: calibrate on 2 000 reads, then size one step to ~4 s of host time
+            cs, ca, _ = pkg.synth_reads(wl, 2000, seed=read_seed)
+            cpu_reference_step(orc, kind, bset, cs[:200], ca[:200], ed, None, None, threads)
+            tcal = cpu_reference_step(orc, kind, bset, cs, ca, ed, None, None, threads)[0]
+            n_s = a.cpu_sample or int(min(2_000_000, max(2000, 4.0 * 2000 / tcal)))
+            slices, anchor, _ = pkg.synth_reads(wl, n_s, seed=read_seed)
+            umis, offs = (umi_jobs_for(pkg, n_s)[:2] if use_umi else (None, None))
+        else:
+            n_s = a.cpu_sample or 2_000_000
+            slices = anchor = None
+            umis, offs = umi5kx2k_batch(pkg, n_s, 0)[:2]
+        ts = [cpu_reference_step(orc, kind, bset, slices, anchor, ed, umis, offs, threads)[0] for _ in range(a.steps)]
         t = sum(ts) / len(ts)
         v = n_s / t
         print(json.dumps({"metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -170,6 +247,7 @@ def main():
         return
 
     # ------------------------------------------------------------------------------------------ our arm
+    numa_note = "off" if a.no_numa else bind_to_gpu_numa(local_rank)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -185,70 +263,103 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = pkg.Context(local_rank, n_streams=2)
-    wl = pkg.synth_whitelist(n_wl, wl_seed)
-    table = pkg.BarcodesMapForBCfinding.getMapFromCellRangerData(ctx, wl)
-    parser = pkg.Parser(ctx, table, bcEditDistance=ed, testPlusMinusPos=2, three_prime=True)
-    R = a.reads
-    # this rank's shard of the run: reads [rank*R, (rank+1)*R) — counter-based RNG, no communication
-    pin = lambda t: t.pin_memory()
-    h_slices = pin(torch.empty((R, 32), dtype=torch.uint8))
-    h_anchor = pin(torch.empty(R, dtype=torch.int32))
-    pkg.synth_reads(wl, R, seed=read_seed, first=rank * R, out=(h_slices.numpy(), h_anchor.numpy()))
-    h_res = pin(torch.empty((R, 32), dtype=torch.uint8))
-    d_slices, d_anchor = h_slices.to(dev), h_anchor.to(dev)
-    d_res = torch.empty((R, 32), dtype=torch.uint8, device=dev)
-    use_umi = not a.no_umi
-    if use_umi:
-        umis_np, offs_np = umi_jobs_for(pkg, R, seed=4 + rank)
-        oo_np = pkg.out_offsets_for(offs_np)
-        n_cells = int(oo_np[-1])
-        h_umis, h_offs, h_oo = pin(torch.from_numpy(umis_np)), pin(torch.from_numpy(offs_np)), pin(torch.from_numpy(oo_np))
-        h_mat = pin(torch.empty(n_cells, dtype=torch.int32))
-        MERGE_CAP = 4096
-        d_umis_all = torch.zeros((R + MERGE_CAP, 16), dtype=torch.uint8, device=dev)
-        d_umis_all[:R] = h_umis.to(dev)
-        d_umis, d_offs, d_oo = d_umis_all, h_offs.to(dev), h_oo.to(dev)
-        n_jobs, n_umi_rows, dev_cells = len(offs_np) - 1, R, n_cells
-        merger = None
-        if world > 1:
-            # cross-shard UMI merge: the (cell, region) group cut by every shard boundary is clustered as ONE job on the
-            # lower rank (the last job of rank r and the first job of rank r+1 carry the same key)
-            merger = pkg.UmiShardMerger(cap=MERGE_CAP)
-            row0, n_umi_rows, moffs = merger.merge(d_umis_all, R, offs_np, (rank << 32, 0), ((rank + 1) << 32, 0))
-            moo = pkg.out_offsets_for(moffs)
-            d_umis, d_offs, d_oo = d_umis_all[row0:], torch.from_numpy(moffs).to(dev), torch.from_numpy(moo).to(dev)
-            n_jobs, dev_cells = len(moffs) - 1, int(moo[-1])
-        d_mat = torch.empty(dev_cells, dtype=torch.int32, device=dev)
-    cptr, cn = table.counts_device_ptr()
-    d_counts = torch.as_tensor(CudaArrayView(cptr, cn), device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
     lib = pkg.gpu_lib()
+    pin = lambda t: t.pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
+    table_build_ms = None
+    if kind == "bc":
+        wl = pkg.synth_whitelist(n_wl, wl_seed)
+        t0 = time.perf_counter()
+        table = pkg.BarcodesMapForBCfinding.getMapFromCellRangerData(ctx, wl)
+        table_build_ms = (time.perf_counter() - t0) * 1e3
+        parser = pkg.Parser(ctx, table, bcEditDistance=ed, testPlusMinusPos=2, three_prime=True)
+        # this rank's shard of the run: reads [rank*R, (rank+1)*R) — counter-based RNG, no communication
+        h_slices = pin(torch.empty((R, 32), dtype=torch.uint8))
+        h_anchor = pin(torch.empty(R, dtype=torch.int32))
+        pkg.synth_reads(wl, R, seed=read_seed, first=rank * R, out=(h_slices.numpy(), h_anchor.numpy()))
+        h_res = pin(torch.empty((R, 32), dtype=torch.uint8))
+        d_slices, d_anchor = h_slices.to(dev), h_anchor.to(dev)
+        d_res = torch.empty((R, 32), dtype=torch.uint8, device=dev)
+        cptr, cn = table.counts_device_ptr()
+        d_counts = torch.as_tensor(CudaArrayView(cptr, cn), device=dev)
+        np_res = h_res.numpy().view(pkg.BC_RESULT).reshape(-1)
+    MERGE_CAP = 4096
+    merged = None
+    if use_umi:
+        umis_np, offs_np, job_first, job_last = (umi5kx2k_batch(pkg, R, rank) if kind == "umi" else umi_jobs_for(pkg, R, rank))
+        n_own = len(umis_np)
+        h_umis_all = pin(torch.zeros((n_own + MERGE_CAP, 16), dtype=torch.uint8))
+        h_umis_all[:n_own] = torch.from_numpy(umis_np)
+        d_umis_all = h_umis_all.to(dev)
+        row0, n_rows, moffs = 0, n_own, offs_np
+        merger = None
+        if world > 1 and kind == "bc":
+            # cross-shard UMI merge: the job cut by a shard boundary is clustered as ONE job on the lower rank; the keys are the jobs' ids in
+            # the global stream (cell = id // 2000, region = id % 2000)
+            merger = pkg.UmiShardMerger(cap=MERGE_CAP)
+            row0, n_rows, moffs = merger.merge(d_umis_all, n_own, offs_np, (job_first // 2000, job_first % 2000), (job_last // 2000, job_last % 2000))
+            merged = (merger.last_plan[1], list(merger.last_plan[2]))
+        moo = pkg.out_offsets_for(moffs)
+        n_jobs, dev_cells = len(moffs) - 1, int(moo[-1])
+        h_moffs = pin(torch.from_numpy(np.ascontiguousarray(moffs)))
+        d_umis, d_offs, d_oo = d_umis_all[row0:], h_moffs.to(dev), torch.from_numpy(moo).to(dev)
+        d_mat = torch.empty(dev_cells, dtype=torch.int32, device=dev)
+        d_arec = torch.empty((n_rows, 16), dtype=torch.uint8, device=dev)
+        d_ascr = torch.empty(int(lib.slr_umi_assign_scratch_bytes(n_jobs)), dtype=torch.uint8, device=dev)
+        h_arec = pin(torch.empty((n_rows, 16), dtype=torch.uint8))
+        if kind == "umi":
+            d_ccnt = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            d_crec = torch.empty((n_rows, 16), dtype=torch.uint8, device=dev)
+            h_crec = pin(torch.empty((n_rows, 16), dtype=torch.uint8))
+    n_units = R
 
     def step_device(ev=None):
         if ev:
             ev[0].record()
-        parser.assign_barcodes_dev(d_slices.data_ptr(), 32, d_anchor.data_ptr(), R, d_res.data_ptr(), stream)
+        if kind == "bc":
+            parser.assign_barcodes_dev(d_slices.data_ptr(), 32, d_anchor.data_ptr(), R, d_res.data_ptr(), stream)
         if ev:
             ev[1].record()
         if use_umi:
             if merger is not None:
-                merger.exchange(d_umis_all, R)            # NCCL all_gather of the boundary groups' reads
-            pkg._check(lib.slr_umi_dist_dev(ctx.h, d_umis.data_ptr(), 16, 12, d_offs.data_ptr(), n_jobs, n_umi_rows, d_mat.data_ptr(),
+                merger.exchange(d_umis_all, n_own)        # NCCL all_gather of the boundary jobs' reads
+            pkg._check(lib.slr_umi_dist_dev(ctx.h, d_umis.data_ptr(), 16, 12, d_offs.data_ptr(), n_jobs, n_rows, d_mat.data_ptr(),
                                             d_oo.data_ptr(), dev_cells, stream))
-        if world > 1:
-            dist.all_reduce(d_counts)                     # cross-shard merge of the BarcodesAssigned counters (sum, int64)
+            if ev:
+                ev[2].record()
+            if kind == "umi":
+                pkg._check(lib.slr_umi_cluster_dev(ctx.h, d_mat.data_ptr(), d_offs.data_ptr(), d_oo.data_ptr(), n_jobs, n_rows, 2, None, None,
+                                                   d_ccnt.data_ptr(), d_crec.data_ptr(), stream))
+            if ev:
+                ev[3].record()
+            pkg._check(lib.slr_umi_assign_dev(ctx.h, d_mat.data_ptr(), d_offs.data_ptr(), d_oo.data_ptr(), n_jobs, n_rows, None, None,
+                                              d_ascr.data_ptr(), d_arec.data_ptr(), stream))
+        if ev:
+            ev[4].record()
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=2)
-    np_res = h_res.numpy().view(pkg.BC_RESULT).reshape(-1)
+    h_umis_m = h_umis_all[row0:row0 + n_rows] if use_umi else None
+
+    def e2e_umi():
+        if merger is not None:                            # the absorbed boundary reads reach the host buffer behind the rank's own reads
+            extra = merger.exchange(d_umis_all, n_own)
+            if extra:
+                h_umis_all[n_own:n_own + extra].copy_(d_umis_all[n_own:n_own + extra])
+        arec = h_arec.numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
+        if kind == "umi":
+            crec = h_crec.numpy().view(pkg.UMI_CLUSTER_REC).reshape(-1)
+            pkg._check(lib.slr_umi_cluster(ctx.h, h_umis_m.data_ptr(), 16, 12, h_moffs.data_ptr(), n_jobs, 2, None, None, None, None, crec.ctypes.data))
+        pkg._check(lib.slr_umi_assign(ctx.h, h_umis_m.data_ptr(), 16, 12, h_moffs.data_ptr(), n_jobs, None, None, None, None, arec.ctypes.data))
 
     def step_e2e():
-        # the two seams are independent calls of two host threads (the reference's worker pools are concurrent too); each
-        # call copies its inputs H2D, runs its kernels and copies its results D2H before it returns
-        f = pool.submit(parser.assign_barcodes, h_slices.numpy(), h_anchor.numpy(), None, np_res)
+        # the two seams are independent calls of two host threads (the reference's worker pools are concurrent too); each call copies its
+        # inputs H2D, runs its kernels and copies its records D2H before it returns; the matrices stay on the device (records only)
+        f = pool.submit(parser.assign_barcodes, h_slices.numpy(), h_anchor.numpy(), None, np_res) if kind == "bc" else None
         if use_umi:
-            pkg.generate_distance_matrices(ctx, h_umis.numpy(), h_offs.numpy(), 12, out=h_mat.numpy(), out_offsets=h_oo.numpy())
-        f.result()
+            e2e_umi()
+        if f is not None:
+            f.result()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -259,21 +370,85 @@ def main():
     for _ in range(a.warmup):
         step_device()
     sync_all()
+    if kind == "bc":
+        table.reset_counts()                                  # the counters then hold exactly the K timed steps
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = pkg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    bc_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    legs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
     e0.record()
     for s in range(a.steps):
-        step_device(bc_ev[s])
+        step_device(legs[s])
     e1.record()
     sync_all()
     launches = pkg.launch_count() - l0
     clocks = sampler.summary()                             # stop sampling here: nvidia-smi takes driver locks that stall the
     sampler.join(timeout=10)                               # host-side submission of the end-to-end leg below
     ms_total = e0.elapsed_time(e1)
-    bc_ms = sum(x.elapsed_time(y) for x, y in bc_ev) / a.steps
+    bc_ms = sum(x[0].elapsed_time(x[1]) for x in legs) / a.steps
+    dist_ms = sum(x[1].elapsed_time(x[2]) for x in legs) / a.steps if use_umi else 0.0
+    cluster_ms = sum(x[2].elapsed_time(x[3]) for x in legs) / a.steps if use_umi else 0.0
+    assign_ms = sum(x[3].elapsed_time(x[4]) for x in legs) / a.steps if use_umi else 0.0
+
+    # ---- parity on THIS rank (every rank): a strided sample of the barcode records and of the UMI jobs against the oracle; the job absorbed
+    # ---- across a shard boundary against the oracle on the whole job as the unsharded run sees it; the all-reduced counters
+    parity = {"bc_sample": None, "umi_sample": None, "boundary_job": None, "counters": None}
+    if not a.no_cpu_baseline:
+        from oracle import orc
+        if kind == "bc":
+            sel = np.arange(0, R, max(1, R // (4000 if ed >= 2 else 40000)))
+            bset = orc.BarcodeSet(wl, np.arange(1, n_wl + 1, dtype=np.int32))
+            exp, _ = orc.assign_barcode_batch(bset, h_slices.numpy()[sel], h_anchor.numpy()[sel], ed, 2, True, n_threads=threads)
+            got = d_res.cpu().numpy().view(pkg.BC_RESULT).reshape(-1)
+            parity["bc_sample"] = bool((got[sel] == exp).all())
+            parity["bc_sample_reads"] = int(len(sel))
+        if use_umi:
+            h_m = d_umis.cpu().numpy()[:n_rows]
+            arec = d_arec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
+            jsel = np.unique(np.concatenate([np.arange(0, n_jobs, max(1, n_jobs // 20000)), [0, n_jobs - 1]]))
+            jsel = jsel[np.diff(moffs)[jsel] <= 2000]            # (the 20 000-read job of umi5kx2k is covered by tests/, not by this spot check)
+            ok, reads_checked = True, 0
+            sub_u = np.concatenate([h_m[moffs[j]:moffs[j + 1]] for j in jsel])
+            sub_o = np.concatenate([[0], np.cumsum([moffs[j + 1] - moffs[j] for j in jsel])]).astype(np.int64)
+            em, eoo = orc.umi_matrix_batch(sub_u, sub_o, 12, n_threads=threads)
+            erec = orc.umi_assign_batch(em, sub_o, eoo, None, None, n_threads=threads)
+            gmat = d_mat.cpu().numpy() if dev_cells < 4_000_000_000 else None
+            for k, j in enumerate(jsel):
+                n_j = int(moffs[j + 1] - moffs[j])
+                ok &= arec[moffs[j]:moffs[j + 1]].tobytes() == erec[sub_o[k]:sub_o[k + 1]].tobytes()
+                if gmat is not None:
+                    ok &= bool((gmat[moo[j]:moo[j] + n_j * n_j] == em[eoo[k]:eoo[k + 1]]).all())
+                reads_checked += n_j
+            parity["umi_sample"] = bool(ok)
+            parity["umi_sample_reads"] = int(reads_checked)
+            if merged is not None and merged[1]:
+                # this rank absorbed the head of the next shard(s): its last job must equal the global job `job_last` as a whole
+                gu, go = pkg.synth_umi_jobs_at(job_last, 1, UMI_MEAN, UMI_CAP, UMI_SEED)
+                j = n_jobs - 1
+                have = h_m[moffs[j]:moffs[j + 1]]
+                tail_ok = len(gu) >= len(have) and bool((gu[len(gu) - len(have):] == have).all())   # (its own head may lie on the rank before)
+                fm, foo = orc.umi_matrix_batch(have, np.array([0, len(have)], dtype=np.int64), 12)
+                frec = orc.umi_assign_batch(fm, np.array([0, len(have)], dtype=np.int64), foo)
+                parity["boundary_job"] = bool(tail_ok and arec[moffs[j]:moffs[j + 1]].tobytes() == frec.tobytes() and
+                                              (gmat is None or (gmat[moo[j]:moo[j + 1]] == fm).all()))
+                parity["boundary_job_reads"] = int(len(have))
+    if kind == "bc":
+        # BarcodesAssigned.tsv counters: all-reduced ONCE per run; = steps x the histogram of this run's assigned reads, summed over the ranks
+        got = d_res.cpu().numpy().view(pkg.BC_RESULT).reshape(-1)
+        okm = (got["flags"] & 1) != 0
+        hist = torch.zeros(3, dtype=torch.int64, device=dev)
+        hist += torch.from_numpy(np.bincount(got["ed"][okm], minlength=3)[:3].astype(np.int64)).to(dev)
+        if world > 1:
+            dist.all_reduce(d_counts)                     # cross-shard merge of the counters (sum, int64, NCCL)
+            dist.all_reduce(hist)
+        torch.cuda.synchronize()
+        csum = d_counts.view(-1, 3).sum(dim=0)
+        parity["counters"] = bool((csum == hist * a.steps).all().item())
+        assigned = int(okm.sum())
+    pvals = [v for k, v in parity.items() if k in ("bc_sample", "umi_sample", "boundary_job", "counters") and v is not None]
+    parity_rank = bool(all(pvals)) if pvals else None
+
     # host <-> device link of this box (pinned, 256 MB each way): explains e2e on a slow PCIe slot / remote NUMA node
     link = {}
     pb, db = pin(torch.empty(256 << 20, dtype=torch.uint8)), torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -290,76 +465,108 @@ def main():
     # end to end through the host-pointer ABI
     # warm-up: the context hands its stream slots out round-robin and every slot grows its own staging buffers on first
     # use, so each seam is called once per slot on its own before the W concurrent warm-up steps
-    for _ in range(2):
+    for _ in range(2 if kind == "bc" else 0):
         parser.assign_barcodes(h_slices.numpy(), h_anchor.numpy(), None, np_res)
     for _ in range(2 if use_umi else 0):
-        pkg.generate_distance_matrices(ctx, h_umis.numpy(), h_offs.numpy(), 12, out=h_mat.numpy(), out_offsets=h_oo.numpy())
+        e2e_umi()
     for _ in range(a.warmup):
         step_e2e()
     sync_all()
-    t0 = time.perf_counter()
     e2e_steps = []
     for _ in range(a.steps):
+        if world > 1:
+            dist.barrier()                                # every rank starts the step together: ms_steps means the same on every rank
+            torch.cuda.synchronize()
         t1 = time.perf_counter()
         step_e2e()
-        e2e_steps.append(round((time.perf_counter() - t1) * 1e3, 2))
+        e2e_steps.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / a.steps
-    t = torch.tensor([ms_total / a.steps, e2e_s * 1e3, bc_ms], dtype=torch.float64, device=dev)
+    # per step the slowest rank counts; the step time of the run is the mean of those maxima
+    t_steps = torch.tensor(e2e_steps, dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total / a.steps, bc_ms, dist_ms, assign_ms, 0.0 if parity_rank is False else 1.0, cluster_ms], dtype=torch.float64, device=dev)
+    lk = torch.tensor([link["h2d_gbs"], link["d2h_gbs"]], dtype=torch.float64, device=dev)
     if world > 1:
+        dist.all_reduce(t_steps, op=dist.ReduceOp.MAX)
+        tmin = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, e2e_ms, bc_ms = (float(x) for x in t.cpu())
-    assigned = int((d_res.cpu().numpy().view(pkg.BC_RESULT)["flags"] & 1).sum())
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        t[4] = tmin[4]
+        dist.all_reduce(lk, op=dist.ReduceOp.MIN)
+    e2e_steps = [round(float(x), 2) for x in t_steps.cpu()]
+    e2e_ms = float(t_steps.mean())
+    ms_step, bc_ms, dist_ms, assign_ms, parity_all, cluster_ms = (float(x) for x in t.cpu())
 
     if rank == 0:
-        out = {"metric": METRIC, "value": world * R / (ms_step / 1e3), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
+        out = {"metric": METRIC, "value": world * n_units / (ms_step / 1e3), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-               "assigned_fraction": assigned / R}
-        h2d = R * 36 + (int(h_umis.numel()) + 8 * (len(offs_np) + len(oo_np)) if use_umi else 0)
-        d2h = R * 32 + (n_cells * 4 if use_umi else 0)
-        out["e2e"] = {"value": world * R / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                      "ms_per_step": e2e_ms, "ms_steps": e2e_steps, "link": link}
+               "legs_ms": {"bc_assign": bc_ms, "umi_dist": dist_ms, "umi_cluster_local": cluster_ms, "umi_assign": assign_ms},
+               "parity_all_ranks": (None if a.no_cpu_baseline else bool(parity_all >= 1.0)), "parity_rank0": parity, "numa": numa_note}
+        if kind == "bc":
+            out["assigned_fraction"] = assigned / R
+            out["table_build_ms"] = table_build_ms
+        h2d = (R * 36 if kind == "bc" else 0) + (n_rows * 16 + 8 * (n_jobs + 1) if use_umi else 0)
+        d2h = (R * 32 if kind == "bc" else 0) + (n_rows * 16 * (2 if kind == "umi" else 1) if use_umi else 0)
+        out["e2e"] = {"value": world * n_units / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                      "ms_per_step": e2e_ms, "ms_steps": e2e_steps, "link_min_over_ranks": {"h2d_gbs": float(lk[0]), "d2h_gbs": float(lk[1])},
+                      "results": "records only (32 B/read barcode records, 16 B/read UMI assignment records); matrices stay in HBM"}
         # ---- CPU baseline (bounded sample, all host threads) + the reference's algorithmic bytes per read -------------
         probes_per_read = 55091.0 if ed >= 2 else 620.0       # App. A.5 of SURVEY.md; re-measured on the sample below
         if not a.no_cpu_baseline:
             from oracle import orc
-            n_s = a.cpu_sample or (30_000 if ed >= 2 else 2_000_000)
-            n_s = min(n_s, R)
-            bset = orc.BarcodeSet(wl, np.arange(1, n_wl + 1, dtype=np.int32))
-            su, so = (umi_jobs_for(pkg, n_s, 4) if use_umi else (None, None))
-            sl, an = h_slices.numpy()[:n_s], h_anchor.numpy()[:n_s]
-            tt, tbc, probes, cres = cpu_reference_step(orc, bset, sl, an, ed, su, so, threads)
-            probes_per_read = probes / n_s
-            gres = d_res[:n_s].cpu().numpy().view(pkg.BC_RESULT).reshape(-1)
-            out["cpu_baseline"] = {"value": n_s / tt, "unit": "reads/s", "cores": threads, "kind": "port",
-                                   "sample": "first %d reads of the step's batch (+ their UMI jobs); CPU oracle = restatement of the "
-                                             "reference's Java algorithm, OpenMP over reads" % n_s,
-                                   "bc_only_reads_per_s": n_s / tbc, "probes_per_read": probes_per_read,
-                                   "gpu_matches_oracle_on_sample": bool((gres == cres).all())}
-        # ---- roofline of the dominant kernel (bc_assign) -----------------------------------------------------------------
+            if kind == "bc":
+                n_s = min(a.cpu_sample or (30_000 if ed >= 2 else 2_000_000), R)
+                su, so = (umi_jobs_for(pkg, n_s)[:2] if use_umi else (None, None))
+                sl, an = h_slices.numpy()[:n_s], h_anchor.numpy()[:n_s]
+                tt, tbc, probes, cres, _ = cpu_reference_step(orc, kind, bset, sl, an, ed, su, so, threads)
+                probes_per_read = probes / n_s
+                gres = d_res[:n_s].cpu().numpy().view(pkg.BC_RESULT).reshape(-1)
+                out["cpu_baseline"] = {"value": n_s / tt, "unit": "reads/s", "cores": threads, "kind": "port",
+                                       "sample": "first %d reads of the step's batch (+ the UMI jobs of as many reads); CPU oracle = restatement "
+                                                 "of the reference's Java algorithm, OpenMP over reads / jobs" % n_s,
+                                       "bc_only_reads_per_s": n_s / tbc, "probes_per_read": probes_per_read,
+                                       "gpu_matches_oracle_on_sample": bool((gres == cres).all())}
+            else:
+                n_s = min(a.cpu_sample or 2_000_000, R)
+                su, so = umi5kx2k_batch(pkg, n_s, 0)[:2]
+                tt = cpu_reference_step(orc, kind, None, None, None, 0, su, so, threads)[0]
+                out["cpu_baseline"] = {"value": n_s / tt, "unit": "reads/s", "cores": threads, "kind": "port",
+                                       "sample": "a %d-read batch of the same shape (incl. the %d-read job); CPU oracle, OpenMP over jobs" % (n_s, DEEP_JOB)}
+        # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        bytes_per_read = probes_per_read * 8 + 36 + 32          # reference probes x 8 B key + boundary in / out
-        achieved = bytes_per_read * R / (bc_ms / 1e3) / 1e9
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_bc_assign_traffic.json")))
-            traffic = prof["dram_bytes_per_read"] * R
-        except Exception:
-            pass
-        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                           "kernel": "bc_assign_kernel", "kernel_ms_per_launch": bc_ms, "units_per_launch": R,
-                           "algorithmic_bytes_per_read": bytes_per_read,
-                           "note": "algorithmic bytes are the REFERENCE algorithm's (SURVEY.md 8d: hash probes x 8 B + boundary in/out); "
-                                   "the kernel answers the same queries with ~0.5 k 32-byte L2-resident bucket loads per read (one load "
-                                   "tests every mutant of a digit group, ED-2 searches that cannot reach the record are skipped), so "
-                                   "frac > 1 is not HBM saturation: the kernel is issue-bound (ncu: profiles/), see DESIGN.md 4.1"}
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_ghz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) / 1e3
+        issue_peak = sms * 4 * sm_ghz                          # G warp instructions / s: 4 schedulers per SM, one issue per cycle each
+        dom = max((("bc_assign_kernel<%d>" % ed, bc_ms, n_units, "read"), ("umi_pairs_kernel", dist_ms, n_units, "read"),
+                   ("umi_assign_kernel", assign_ms, n_units, "read")), key=lambda x: x[1])
+        kname, kms, kunits, unit = dom
+        prof = load_profile(pkg, kname)
+        roof = {"bound": "int_issue", "kernel": kname, "kernel_ms_per_launch": kms, "units_per_launch": kunits, "unit": "Ginst/s", "peak": issue_peak,
+                "peak_source": "%d SMs x 4 schedulers x %.3f GHz (SM clock sampled under load)" % (sms, sm_ghz)}
+        if prof is not None and prof.get("inst_executed_per_unit"):
+            ach = prof["inst_executed_per_unit"] * kunits / (kms / 1e3) / 1e9
+            roof.update({"achieved": ach, "frac": ach / issue_peak, "inst_per_" + unit: prof["inst_executed_per_unit"],
+                         "traffic": (prof.get("dram_bytes_per_unit") or 0) * kunits or None, "profile": prof["file"],
+                         "profile_csrc_sha256": prof["csrc_sha256"], "lib_sha256": pkg.lib_sha256()})
+            if prof.get("dram_bytes_per_unit"):
+                gbs = prof["dram_bytes_per_unit"] * kunits / (kms / 1e3) / 1e9
+                out["roofline_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                       "traffic": prof["dram_bytes_per_unit"] * kunits, "compulsory_bytes_per_" + unit: 68 if kname.startswith("bc") else 36,
+                                       "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+        else:
+            roof.update({"achieved": None, "frac": None, "traffic": None,
+                         "note": "no profile under profiles/ matches the loaded library's sources (csrc sha256 %s): run tools/make_profile.sh" % pkg.csrc_sha256()[:16]})
+        out["roofline"] = roof
+        if kind == "bc":
+            bytes_per_read = probes_per_read * 8 + 36 + 32      # reference probes x 8 B key + boundary in / out
+            out["reference_equivalent_gbs"] = {"value": bytes_per_read * R / (bc_ms / 1e3) / 1e9, "algorithmic_bytes_per_read": bytes_per_read,
+                                               "note": "bytes the REFERENCE algorithm would touch for the same reads (hash probes x 8 B + boundary "
+                                                       "in/out), divided by the kernel time: a work-equivalence figure, not a utilisation"}
         sys.stdout.flush()
         if saved_stdout is not None:
             os.dup2(saved_stdout, 1)

@@ -158,6 +158,25 @@ def launch_count():
     return int(gpu_lib().slr_launch_count())
 
 
+def lib_sha256():
+    """sha256 of the libsicelore_gpu.so that is loaded: ties a profile under profiles/ to the binary a bench line was measured with"""
+    import hashlib
+    with open(LIB_GPU, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+def csrc_sha256():
+    """sha256 over the CUDA / C++ sources of the library (csrc/ + the public header), in sorted file order: survives a rebuild"""
+    import hashlib
+    h = hashlib.sha256()
+    files = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f != "synth.cpp"] + [os.path.join(_HERE, "..", "include", "sicelore_gpu.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 class SynthParams(C.Structure):
     _fields_ = [("p_sub", C.c_double), ("p_ins", C.c_double), ("p_del", C.c_double), ("p_random", C.c_double),
                 ("p_n", C.c_double), ("jitter", C.c_double * 5), ("n_cells", C.c_int64), ("three_prime", C.c_int)]
@@ -179,6 +198,9 @@ def synth_lib():
         L.slr_synth_umi_jobs.argtypes = [C.c_int64, C.c_double, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_int,
                                          C.c_void_p, C.c_void_p]
         L.slr_synth_umi_jobs.restype = None
+        L.slr_synth_umi_jobs_at.argtypes = [C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+        L.slr_synth_umi_jobs_at.restype = None
         _syn = L
     return _syn
 
@@ -217,6 +239,45 @@ def synth_umi_jobs(n_jobs, mean=4.0, cap=2000, seed=4, p_err=0.05, p_shift=0.05,
     umis = np.zeros((int(offs[-1]), 16), dtype=np.uint8)
     synth_lib().slr_synth_umi_jobs(n_jobs, mean, cap, seed, p_err, p_shift, umi_len, offs.ctypes.data, umis.ctypes.data)
     return umis, offs
+
+
+def synth_umi_job_sizes(first_job, n_jobs, mean=4.0, cap=2000, seed=4):
+    """sizes of jobs first_job .. first_job + n_jobs - 1 of the global synthetic job stream (job j depends on (seed, j) only)"""
+    offs = np.zeros(n_jobs + 1, dtype=np.int64)
+    synth_lib().slr_synth_umi_jobs_at(first_job, n_jobs, mean, cap, seed, 0.05, 0.05, 12, offs.ctypes.data, None)
+    return np.diff(offs)
+
+
+def synth_umi_jobs_at(first_job, n_jobs, mean=4.0, cap=2000, seed=4, p_err=0.05, p_shift=0.05, umi_len=12):
+    """(umis, job_offsets) of jobs first_job .. first_job + n_jobs - 1 of the global stream"""
+    offs = np.zeros(n_jobs + 1, dtype=np.int64)
+    synth_lib().slr_synth_umi_jobs_at(first_job, n_jobs, mean, cap, seed, p_err, p_shift, umi_len, offs.ctypes.data, None)
+    umis = np.zeros((int(offs[-1]), 16), dtype=np.uint8)
+    synth_lib().slr_synth_umi_jobs_at(first_job, n_jobs, mean, cap, seed, p_err, p_shift, umi_len, offs.ctypes.data, umis.ctypes.data)
+    return umis, offs
+
+
+def synth_umi_shard(read_first, n_reads, mean=4.0, cap=2000, seed=4):
+    """Reads [read_first, read_first + n_reads) of the global (cell, region)-sorted synthetic read stream, the way a sorted BAM is cut when
+    it is sharded by read index: the first and the last job of the shard may be pieces of a job that continues on the neighbouring shard.
+    Returns (umis [n_reads, 16], job_offsets (local), first_job_id, last_job_id): the ids are the jobs' keys in the global stream
+    (cell = id // 2000, region = id % 2000 in the 5 k cells x 2 k genes picture)."""
+    # global job offsets up to the end of the shard: sizes in blocks until the shard end is covered
+    block = max(1 << 16, int((read_first + n_reads) / mean * 1.02) + 1024)
+    sizes = synth_umi_job_sizes(0, block, mean, cap, seed)
+    csum = np.cumsum(sizes)
+    while csum[-1] < read_first + n_reads:
+        more = synth_umi_job_sizes(len(sizes), block, mean, cap, seed)
+        sizes = np.concatenate([sizes, more])
+        csum = np.cumsum(sizes)
+    goff = np.concatenate([[0], csum])
+    j_lo = int(np.searchsorted(goff, read_first, side="right")) - 1
+    j_hi = int(np.searchsorted(goff, read_first + n_reads, side="left")) - 1          # last job with a read in the shard
+    umis, offs = synth_umi_jobs_at(j_lo, j_hi - j_lo + 1, mean, cap, seed)
+    a = read_first - int(goff[j_lo])
+    umis = np.ascontiguousarray(umis[a:a + n_reads])
+    loc = np.clip(offs - a, 0, n_reads)
+    return umis, np.ascontiguousarray(loc, dtype=np.int64), j_lo, j_hi
 
 
 # ---------------------------------------------------------------------------------------------- 2-bit helpers

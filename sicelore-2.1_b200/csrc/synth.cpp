@@ -139,14 +139,16 @@ void slr_synth_reads(const uint64_t *wl, int64_t n_wl, int64_t first, int64_t n,
 // come from true UMIs (1-3 reads each) with the same error model.  Each read = 16 bytes: umi_len + 2 4-bit codes
 // (one flanking base either side of the predicted 12-nt window), the window start is off by -1/+1 with p_shift.
 // Pass 1: sizes only (umis == NULL) fills job_offsets[n_jobs+1]; pass 2 fills umis (m x 16).
-void slr_synth_umi_jobs(int64_t n_jobs, double mean, int64_t cap, uint64_t seed, double p_err, double p_shift, int umi_len,
-                        int64_t *job_offsets, uint8_t *umis)
+// first_job: the jobs generated are first_job .. first_job + n_jobs - 1 of the run's global job stream (job j is a pure function of
+// (seed, j)), so that every rank of a sharded run — and the checker of a job that crosses a shard boundary — can produce any piece of it.
+void slr_synth_umi_jobs_at(int64_t first_job, int64_t n_jobs, double mean, int64_t cap, uint64_t seed, double p_err, double p_shift,
+                           int umi_len, int64_t *job_offsets, uint8_t *umis)
 {
     static const uint8_t CODE[4] = {1, 2, 4, 8};
     if (!umis) {
         job_offsets[0] = 0;
         for (int64_t j = 0; j < n_jobs; j++) {
-            Rng g(seed ^ 0x5151, (uint64_t)j);
+            Rng g(seed ^ 0x5151, (uint64_t)(first_job + j));
             int64_t n = 1;
             const double q = 1.0 - 1.0 / mean;
             while (n < cap && g.uni() < q) n++;
@@ -156,7 +158,7 @@ void slr_synth_umi_jobs(int64_t n_jobs, double mean, int64_t cap, uint64_t seed,
     }
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t j = 0; j < n_jobs; j++) {
-        Rng g(seed, (uint64_t)j);
+        Rng g(seed, (uint64_t)(first_job + j));
         const int64_t r0 = job_offsets[j], n = job_offsets[j + 1] - r0;
         int64_t i = 0;
         while (i < n) {
@@ -185,6 +187,12 @@ void slr_synth_umi_jobs(int64_t n_jobs, double mean, int64_t cap, uint64_t seed,
             }
         }
     }
+}
+
+void slr_synth_umi_jobs(int64_t n_jobs, double mean, int64_t cap, uint64_t seed, double p_err, double p_shift, int umi_len,
+                        int64_t *job_offsets, uint8_t *umis)
+{
+    slr_synth_umi_jobs_at(0, n_jobs, mean, cap, seed, p_err, p_shift, umi_len, job_offsets, umis);
 }
 
 }  // extern "C"

@@ -205,7 +205,7 @@ def test_assign_barcode_wide_matches_reference_bytecode(orc):
                 seq = orc.lib().orc_pack2bit(w, 16, None)
             post = read[ws - 4:ws + 1][::-1].translate(bytes.maketrans(b"ACGT", b"TGCA")) if tp else read[ws + 16:ws + 21]
             p4 = np.array([orc.lib().orc_encode4bit(c) for c in post], dtype=np.uint8)
-            m = orc.match_tester(bset, seq, 16, 2, post4=p4, offset=o)
+            m, _ = orc.match_tester(bset, seq, 16, 2, post4=p4, offset=o)
             entries += 0 if m is None else len(m)
         many += entries >= 9
     assert many >= 20, many                                      # the resize / chain paths of slr_decide are really exercised

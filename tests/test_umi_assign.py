@@ -174,6 +174,9 @@ def test_gpu_assign_on_synthetic_umis(pkg, orc, ctx):
     slr_umi_assign, the matrices optionally copied back, and the session entry — records bit-exact against the oracle run on the
     oracle's own matrices; the tie flag is rare on UMI-like data"""
     umis, offs = pkg.synth_umi_jobs(30_000, mean=5.0, cap=160, seed=21)
+    u2, o2 = pkg.synth_umi_jobs(60, mean=70.0, cap=160, seed=22)          # some jobs of 33 ... 100 reads and some above
+    umis, offs = np.concatenate([umis, u2]), np.concatenate([offs, offs[-1] + o2[1:]])
+    assert (np.diff(offs) > 100).sum() >= 5 and ((np.diff(offs) > 32) & (np.diff(offs) <= 100)).sum() >= 5
     em, oo = orc.umi_matrix_batch(umis, offs)
     qv = (np.arange(len(offs) - 1) % 2).astype(np.uint8)
     exp = orc.umi_assign_batch(em, offs, oo, None, qv)
