@@ -344,6 +344,42 @@ int  slr_guided_match_dev(slr_ctx *ctx, const slr_guided_sets *s, int plusminus,
  * throws NoSuchElementException).  Pure host arithmetic. */
 int  slr_dyn_max_ed(const int64_t *max_candidates, int n_ed, int count, int plusminus, int cap);
 
+/* ---- several GPUs behind one caller (slr_init(n_devices, device_ids), slr_counts_reduce; §8e) ----------------------- */
+
+/* The reference is ONE JVM (WorkerReadscanner.java:L186-L204: both worker pools live in the process that owns the FASTQ reader and the
+ * writers), so the 8 GPUs of a box must be reachable from a single caller.  slr_multi owns one context per device; every slr_multi_* call
+ * cuts its batch into contiguous shares, drives each device from its own host thread through the single-device entry point above and
+ * returns when all shares are done.  Results are positional, exactly as from one device.
+ *   n_devices <= 0 = every visible device; device_ids NULL = 0 .. n_devices-1; n_streams as slr_ctx_create (per device) */
+typedef struct slr_multi slr_multi;
+typedef struct slr_multi_table slr_multi_table;
+int  slr_multi_create(int n_devices, const int *device_ids, int n_streams, slr_multi **out);
+void slr_multi_destroy(slr_multi *m);
+int  slr_multi_n_devices(const slr_multi *m);
+slr_ctx *slr_multi_ctx(slr_multi *m, int i);                  /* the context of device i (borrowed), for the *_dev / session entries */
+int  slr_multi_peer_access(const slr_multi *m);               /* 1 = every device reads every other device's HBM (NVLink / NVSwitch) */
+/* BarcodesMapForBCfinding replicated on every device (the list is small: 3 M barcodes = 160 MB of tables) */
+int  slr_multi_bc_table_create(slr_multi *m, const uint64_t *barcodes2bit, const int32_t *rank, int64_t n, int bc_len, slr_multi_table **out);
+void slr_multi_bc_table_destroy(slr_multi_table *t);
+slr_bc_table *slr_multi_bc_table_replica(slr_multi_table *t, int i);
+/* Parser.assignBarcode / the pass-1 exact lookup for a batch spread over all devices (arguments as slr_bc_assign / slr_bc_exact) */
+int  slr_multi_bc_assign(slr_multi *m, const slr_multi_table *t, int ed_max, int plusminus, int three_prime, const uint8_t *slices, int stride,
+                         int slice_len, const int32_t *lens, const int32_t *anchor, int64_t n, slr_bc_result *out);
+int  slr_multi_bc_exact(slr_multi *m, const slr_multi_table *t, int three_prime, const uint8_t *slices, int stride, int slice_len,
+                        const int32_t *lens, const int32_t *anchor, int64_t n, slr_bc_result *out);
+/* assignedBarcodes2ndPass over all devices: the replicas' counters are summed on device 0 by one kernel that loads the peers' arrays over
+ * NVLink (staged copies when peer access is unavailable), then copied out — the run's single cross-device reduction */
+int  slr_multi_bc_counts_read(slr_multi *m, slr_multi_table *t, int64_t *counts_out);
+int  slr_multi_bc_counts_reset(slr_multi *m, slr_multi_table *t);
+/* UMI seams: the (cell, region) jobs are dealt to the devices in contiguous runs of WHOLE jobs balanced by n^2, so no job is ever cut and no
+ * cross-device merge exists (arguments as slr_umi_dist / slr_umi_cluster / slr_umi_assign; records and matrices positional) */
+int  slr_multi_umi_dist(slr_multi *m, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs, int32_t *out,
+                        const int64_t *out_offsets);
+int  slr_multi_umi_cluster(slr_multi *m, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs, int ed,
+                           const uint8_t *member, const int32_t *rank, slr_umi_cluster_rec *rec);
+int  slr_multi_umi_assign(slr_multi *m, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
+                          const slr_umi_assign_params *params, const uint8_t *job_qv01, slr_umi_assign_rec *rec);
+
 /* ---- misc ------------------------------------------------------------------------------------------- */
 const char *slr_last_error(void);
 int  slr_abi_version(void);

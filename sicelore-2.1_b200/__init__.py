@@ -47,7 +47,10 @@ EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
            "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_umi_assign", "slr_umi_assign_dev", "slr_umi_assign_scratch_bytes", "slr_umi_session_assign", "slr_umi_session_create", "slr_umi_session_cluster",
            "slr_umi_session_matrices", "slr_umi_session_cells", "slr_umi_session_destroy", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
-           "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count"]
+           "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count",
+           "slr_multi_create", "slr_multi_destroy", "slr_multi_n_devices", "slr_multi_ctx", "slr_multi_peer_access", "slr_multi_bc_table_create",
+           "slr_multi_bc_table_destroy", "slr_multi_bc_table_replica", "slr_multi_bc_assign", "slr_multi_bc_exact", "slr_multi_bc_counts_read",
+           "slr_multi_bc_counts_reset", "slr_multi_umi_dist", "slr_multi_umi_cluster", "slr_multi_umi_assign"]
 
 
 class SiceloreGpuError(RuntimeError):
@@ -75,7 +78,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
     cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu",
-                                           "guided_match.cu")]
+                                           "guided_match.cu", "slr_multi.cu")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -142,6 +145,25 @@ def gpu_lib():
         L.slr_guided_match.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, i64, vp, vp, i32]
         L.slr_guided_match_dev.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, i32, vp]
         L.slr_dyn_max_ed.argtypes = [vp, i32, i32, i32, i32]
+        L.slr_multi_create.argtypes = [i32, vp, i32, C.POINTER(vp)]
+        L.slr_multi_destroy.argtypes = [vp]
+        L.slr_multi_destroy.restype = None
+        L.slr_multi_n_devices.argtypes = [vp]
+        L.slr_multi_ctx.argtypes = [vp, i32]
+        L.slr_multi_ctx.restype = vp
+        L.slr_multi_peer_access.argtypes = [vp]
+        L.slr_multi_bc_table_create.argtypes = [vp, vp, vp, i64, i32, C.POINTER(vp)]
+        L.slr_multi_bc_table_destroy.argtypes = [vp]
+        L.slr_multi_bc_table_destroy.restype = None
+        L.slr_multi_bc_table_replica.argtypes = [vp, i32]
+        L.slr_multi_bc_table_replica.restype = vp
+        L.slr_multi_bc_assign.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, i64, vp]
+        L.slr_multi_bc_exact.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, i64, vp]
+        L.slr_multi_bc_counts_read.argtypes = [vp, vp, vp]
+        L.slr_multi_bc_counts_reset.argtypes = [vp, vp]
+        L.slr_multi_umi_dist.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
+        L.slr_multi_umi_cluster.argtypes = [vp, vp, i32, i32, vp, i64, i32, vp, vp, vp]
+        L.slr_multi_umi_assign.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp, vp]
         L.slr_last_error.restype = C.c_char_p
         L.slr_abi_version.restype = i32
         L.slr_launch_count.restype = i64
@@ -772,6 +794,99 @@ def clusters_from_records(rec, job_offsets):
                 groups.setdefault(k, set()).add(c - a)
         res.append({frozenset(v) for v in groups.values()})
     return res
+
+
+# ---------------------------------------------------------------------------------------------- several GPUs, one caller
+class MultiGpu:
+    """All (or some) GPUs of the box behind one caller, as the single-JVM reference needs them (slr_multi_*): the barcode list is replicated,
+    read batches and whole UMI jobs are dealt to the devices, results are positional, the BarcodesAssigned counters are summed on the device."""
+
+    def __init__(self, n_devices=0, device_ids=None, n_streams=2):
+        h = C.c_void_p()
+        ids = None if device_ids is None else np.ascontiguousarray(device_ids, dtype=np.int32)
+        _check(gpu_lib().slr_multi_create(int(n_devices if ids is None else len(ids)), None if ids is None else ids.ctypes.data, n_streams, C.byref(h)))
+        self.h, self.table, self.keys = h, None, None
+
+    @property
+    def n_devices(self):
+        return int(gpu_lib().slr_multi_n_devices(self.h))
+
+    @property
+    def peer_access(self):
+        return bool(gpu_lib().slr_multi_peer_access(self.h))
+
+    def load_barcodes(self, barcodes2bit, rank=None):
+        self.keys = np.ascontiguousarray(barcodes2bit, dtype=np.uint64)
+        r = None if rank is None else np.ascontiguousarray(rank, dtype=np.int32)
+        t = C.c_void_p()
+        _check(gpu_lib().slr_multi_bc_table_create(self.h, self.keys.ctypes.data, None if r is None else r.ctypes.data, len(self.keys), 16, C.byref(t)))
+        if self.table:
+            gpu_lib().slr_multi_bc_table_destroy(self.table)
+        self.table = t
+
+    def assign_barcodes(self, slices, anchor, ed, plusminus=2, three_prime=True, lens=None, out=None):
+        slices = np.ascontiguousarray(slices, dtype=np.uint8)
+        anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+        n, stride = slices.shape
+        if out is None:
+            out = np.empty(n, dtype=BC_RESULT)
+        lp = None
+        if lens is not None:
+            lens = np.ascontiguousarray(lens, dtype=np.int32)
+            lp = lens.ctypes.data
+        _check(gpu_lib().slr_multi_bc_assign(self.h, self.table, int(ed), int(plusminus), int(three_prime), slices.ctypes.data, stride,
+                                             min(stride, 32), lp, anchor.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def counts(self):
+        out = np.zeros((len(self.keys), 3), dtype=np.int64)
+        _check(gpu_lib().slr_multi_bc_counts_read(self.h, self.table, out.ctypes.data))
+        return out
+
+    def reset_counts(self):
+        _check(gpu_lib().slr_multi_bc_counts_reset(self.h, self.table))
+
+    def umi_assign(self, umis, job_offsets, umi_len=12, params=None, job_qv01=None, out=None):
+        umis = np.ascontiguousarray(umis, dtype=np.uint8)
+        job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+        rec = np.zeros(int(job_offsets[-1]), dtype=UMI_ASSIGN_REC) if out is None else out
+        qv = None if job_qv01 is None else np.ascontiguousarray(job_qv01, dtype=np.uint8)
+        _check(gpu_lib().slr_multi_umi_assign(self.h, umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(job_offsets) - 1,
+                                              C.byref(params) if params is not None else None, None if qv is None else qv.ctypes.data, rec.ctypes.data))
+        return rec
+
+    def umi_cluster(self, umis, job_offsets, ed, umi_len=12, member=None, rank=None):
+        umis = np.ascontiguousarray(umis, dtype=np.uint8)
+        job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+        rec = np.zeros(int(job_offsets[-1]), dtype=UMI_CLUSTER_REC)
+        mb = None if member is None else np.ascontiguousarray(member, dtype=np.uint8)
+        rk = None if rank is None else np.ascontiguousarray(rank, dtype=np.int32)
+        _check(gpu_lib().slr_multi_umi_cluster(self.h, umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(job_offsets) - 1, int(ed),
+                                               None if mb is None else mb.ctypes.data, None if rk is None else rk.ctypes.data, rec.ctypes.data))
+        return rec
+
+    def umi_dist(self, umis, job_offsets, umi_len=12):
+        umis = np.ascontiguousarray(umis, dtype=np.uint8)
+        job_offsets = np.ascontiguousarray(job_offsets, dtype=np.int64)
+        oo = out_offsets_for(job_offsets)
+        out = np.empty(int(oo[-1]), dtype=np.int32)
+        _check(gpu_lib().slr_multi_umi_dist(self.h, umis.ctypes.data, umis.shape[1], umi_len, job_offsets.ctypes.data, len(job_offsets) - 1,
+                                            out.ctypes.data, oo.ctypes.data))
+        return out, oo
+
+    def close(self):
+        if getattr(self, "table", None):
+            gpu_lib().slr_multi_bc_table_destroy(self.table)
+            self.table = None
+        if getattr(self, "h", None):
+            gpu_lib().slr_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------- cross-shard UMI merge

@@ -150,6 +150,7 @@ struct slr_bc_table {
 extern "C" {
 
 const char *slr_last_error(void) { return g_err.c_str(); }
+int slr_multi_fail(int code, const char *msg) { return fail(code, "%s", msg ? msg : ""); }     // slr_multi.cu reports through the same channel
 int slr_abi_version(void) { return SLR_ABI_VERSION; }
 int64_t slr_launch_count(void) { return g_launches.load(); }
 
