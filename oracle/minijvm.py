@@ -1096,6 +1096,32 @@ class VM:
                 v = pop() & 0xFFFF; push(v - 0x10000 if v & 0x8000 else v); pc += 1
             elif op == 0x94:
                 b = pop(); a = pop(); push((a > b) - (a < b)); pc += 1
+            elif op in (0x0e, 0x0f):                        # dconst_0 dconst_1
+                push(D(op - 0x0e)); pc += 1
+            elif op in (0x0b, 0x0c, 0x0d):                  # fconst_0 .. 2
+                push(float(op - 0x0b)); pc += 1
+            elif op in (0x95, 0x96, 0x97, 0x98):            # fcmpl fcmpg dcmpl dcmpg (NaN: -1 for the l forms, +1 for the g forms)
+                b = pop(); a = pop()
+                if a != a or b != b:
+                    push(-1 if op in (0x95, 0x97) else 1)
+                else:
+                    push((a > b) - (a < b))
+                pc += 1
+            elif op in (0x63, 0x67, 0x6b, 0x6f):            # dadd dsub dmul ddiv
+                b = float(pop()); a = float(pop())
+                if op == 0x6f:
+                    r_ = (a / b) if b != 0.0 else (float("nan") if a == 0.0 or a != a else float("inf") * (1 if (a > 0) == (str(b)[0] != "-") else -1))
+                else:
+                    r_ = a + b if op == 0x63 else a - b if op == 0x67 else a * b
+                push(D(r_)); pc += 1
+            elif op in (0x8e, 0x8b):                        # d2i f2i: truncation toward zero, saturating, NaN -> 0
+                v = float(pop())
+                push(0 if v != v else max(-(1 << 31), min((1 << 31) - 1, int(v)))); pc += 1
+            elif op == 0x8f:                                # d2l
+                v = float(pop())
+                push(L(0 if v != v else max(-(1 << 63), min((1 << 63) - 1, int(v))))); pc += 1
+            elif op == 0x8a:                                # l2d
+                push(D(float(pop()))); pc += 1
             # ---- branches ----
             elif 0x99 <= op <= 0x9e:
                 v = pop()

@@ -580,3 +580,77 @@ def test_gpu_cluster_local_matches_reference_bytecode(pkg, ctx):
         torch.cuda.synchronize()
     rec = d_rec.cpu().numpy().view(pkg.UMI_CLUSTER_REC).reshape(m)
     _check_cluster_records(z, rec)
+
+
+# ------------------------------------------------------------------------------------------------------------- ClusterOneHierarchical
+def _check_hier(z, rec_of_job):
+    """records (oracle or GPU) against what ClusterOneHierarchical.call wrote through OneNanoporeResult.setAttribute in the interpreter:
+    U8 = the centre read and the cluster's mean shift, U1, U2 (absent = -1), the PREDICTED_POS flag, the SKIPPED_HIGHCOMPLEXITY flag value,
+    nUMIfoundClustering"""
+    off = z["job_offsets"]
+    stats = np.zeros(4, dtype=int)
+    for j in range(len(off) - 1):
+        a, b = int(off[j]), int(off[j + 1])
+        rec = rec_of_job(j)
+        assert len(rec) == b - a
+        if rec["flags"][0] & 4:                               # the JVM's own result depends on identity hash codes: canonical order only
+            stats[3] += 1
+        for i in range(b - a):
+            r = rec[i]
+            want_assigned = int(z["assigned"][a + i])
+            assert int(r["flags"] & 1) == want_assigned, (j, i, r)
+            assert bool(r["flags"] & 2) == bool(z["flagval"][a + i] != 0 and not want_assigned) or want_assigned, (j, i, r, z["flagval"][a + i])
+            if want_assigned:
+                assert str(z["u8"][a + i]) == "UMI(%d,%d)" % (int(r["center"]), int(r[4])), (j, i, r, z["u8"][a + i])
+                assert (int(r["u1"]), int(r["u2"]), int(r["pos2"])) == (int(z["u1"][a + i]), int(z["u2"][a + i]), int(z["pos2"][a + i])), (j, i, r)
+                stats[0] += 1
+            elif r["flags"] & 2:
+                stats[1] += 1
+        assert int(z["n_found"][j]) == int((rec["flags"] & 1).sum())
+        stats[2] += 1
+    return stats
+
+
+def test_cluster_one_hierarchical_matches_reference_bytecode(orc):
+    """ClusterOneHierarchical.call as a whole — LingPipe's CompleteLinkClusterer / SingleLinkClusterer / Dendrogram / BoundedPriorityQueue /
+    ObjectToSet, DistanceMatrix, OneUmiCluster.setClusterCenter, ClusterOneBase.setSamflagsAndStatsForClustered — run from the reference's own
+    class files (oracle/make_ref_hier.py) on jobs of 2 ... 100 reads: the C oracle reproduces every value the bytecode wrote"""
+    z = np.load(os.path.join(GOLDEN, "ref_hier.npz"))
+    off, oo = z["job_offsets"], z["out_offsets"]
+
+    def rec_of_job(j):
+        n = int(off[j + 1] - off[j])
+        p = z["params"][j]
+        return orc.umi_assign_batch(z["packed"][oo[j]:oo[j + 1]], np.array([0, n]), np.array([0, n * n]),
+                                    orc.AssignParams(int(p[0]), int(p[1]), int(p[2]), int(p[3]), 100), z["qv01"][j:j + 1])
+    stats = _check_hier(z, rec_of_job)
+    assert stats[2] >= 200 and stats[0] > 1500 and stats[1] > 0, stats
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_one_hierarchical_matches_reference_bytecode(pkg, ctx):
+    """the CUDA kernels through slr_umi_assign_dev against the same vectors (jobs grouped by parameter set)"""
+    import ctypes as C
+    import torch
+    z = np.load(os.path.join(GOLDEN, "ref_hier.npz"))
+    off, oo = z["job_offsets"], z["out_offsets"]
+    recs = {}
+    for prm in sorted({tuple(int(x) for x in p) for p in z["params"]}):
+        js = [j for j in range(len(off) - 1) if tuple(int(x) for x in z["params"][j]) == prm]
+        sizes = np.array([off[j + 1] - off[j] for j in js], dtype=np.int64)
+        so = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        soo = np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)
+        mats = np.concatenate([z["packed"][oo[j]:oo[j + 1]] for j in js]).astype(np.int32)
+        qv = np.ascontiguousarray(z["qv01"][js])
+        d_m, d_o, d_oo, d_q = (torch.from_numpy(x).cuda() for x in (mats, so, soo, qv))
+        d_rec = torch.zeros((int(so[-1]), 16), dtype=torch.uint8, device="cuda")
+        d_scr = torch.zeros(int(pkg.gpu_lib().slr_umi_assign_scratch_bytes(len(js))), dtype=torch.uint8, device="cuda")
+        P = pkg.UmiAssignParams(prm[0], prm[1], prm[2], prm[3], 100)
+        pkg._check(pkg.gpu_lib().slr_umi_assign_dev(ctx.h, d_m.data_ptr(), d_o.data_ptr(), d_oo.data_ptr(), len(js), int(so[-1]), C.byref(P),
+                                                    d_q.data_ptr(), d_scr.data_ptr(), d_rec.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        got = d_rec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
+        for k, j in enumerate(js):
+            recs[j] = got[so[k]:so[k + 1]]
+    stats = _check_hier(z, lambda j: recs[j])
+    assert stats[2] >= 200 and stats[0] > 1500, stats
