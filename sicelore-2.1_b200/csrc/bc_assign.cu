@@ -19,6 +19,7 @@
 //     node already expanded) is a 256-entry per-warp shared-memory hash  value -> earliest processing time,
 //     consulted only for real whitelist hits.
 // Per-lane logic: bc_core.cuh (shared with tests/host_sim).
+#include <cstdlib>
 #include "bc_core.cuh"
 #include "slr_kernels.h"
 
@@ -38,6 +39,26 @@ struct alignas(16) WarpShared {
     uint32_t win[SLR_MAX_OFFSETS];             // per window: p1 | p2 << 2 | dead << 4   (the window itself is ms.m_w)
     uint32_t r1[SLR_MAX_OFFSETS];              // per window: traversal rank of the ED-1 hit kept so far
 };
+
+// -DSLR_BC_L2HINT=1: the read slices and the records are touched once, evict-first (.cs) accesses (no measurable effect, see slr_table.cuh)
+__device__ __forceinline__ uint32_t bc_ld_stream_u8(const uint8_t *p)
+{
+#if !defined(SLR_BC_L2HINT) || SLR_BC_L2HINT == 0
+    return (uint32_t)*p;
+#else
+    uint32_t v;
+    asm("ld.global.cs.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#endif
+}
+__device__ __forceinline__ void bc_st_stream(uint4 *p, uint4 v)
+{
+#if !defined(SLR_BC_L2HINT) || SLR_BC_L2HINT == 0
+    *p = v;
+#else
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
+}
 
 // First insertion wins: the caller inserts in increasing processing time (rounds in order, duplicates inside a
 // round removed with __match_any_sync), so an existing key always carries the smaller time.  Returns the time
@@ -147,7 +168,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
     for (long long read = batch0; read < batch1; read++) {
         // ---- the slice: lane i owns char i; bit planes by ballot --------------------------------------------
         const int len = lens ? min(lens[read], slice_len) : slice_len;
-        const uint32_t ch = (lane < len) ? (uint32_t)slices[read * (long long)stride + lane] : 0u;
+        const uint32_t ch = (lane < len) ? bc_ld_stream_u8(slices + read * (long long)stride + lane) : 0u;
         const int anc = anchor[read];
         const uint32_t c2 = slr_code2(ch);
         SlrSliceBits sb;
@@ -321,7 +342,7 @@ bc_assign_kernel(SlrTableDev tab, int plusminus, int three_prime, int need_post,
             v1.x = (uint32_t)(uint8_t)res.offset | ((uint32_t)(uint8_t)res.n_ins << 8) | ((uint32_t)(uint8_t)res.n_del << 16) |
                    ((uint32_t)(uint8_t)res.n_sub << 24);
             v1.y = (uint32_t)res.rank; v1.z = res.flags; v1.w = 0;
-            o[0] = v0; o[1] = v1;
+            bc_st_stream(o, v0); bc_st_stream(o + 1, v1);
         }
         __syncwarp();
     }
@@ -344,7 +365,8 @@ cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, int
     if (resident_ctas[dev] == 0) {
         int bps = 0, sms = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_assign_kernel<EDMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_assign_kernel<EDMAX>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                       (int)((sizeof(WarpShared) * WARPS_PER_BLOCK * 4 * 100) / (228 * 1024)) + 8);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bc_assign_kernel<EDMAX>, WARPS_PER_BLOCK * 32, 0);
         if (e != cudaSuccess) return e;
         resident_ctas[dev] = sms * (bps > 0 ? bps : 1);
@@ -352,6 +374,35 @@ cudaError_t launch_t(const SlrTableDev &tab, int plusminus, int three_prime, int
     const long long need = (n + WARPS_PER_BLOCK * READ_BATCH - 1) / (WARPS_PER_BLOCK * READ_BATCH);
     const long long resident = resident_ctas[dev];               // one wave of persistent CTAs: a multiple of the SM count
     const unsigned blocks = (unsigned)(need < resident ? need : resident);
+    // SLR_BC_APW=<hit ratio> (experiment, off by default): an access-policy window over the bucket tables for this launch (persisting hits,
+    // streaming misses).  Measured: 1.0 -> 48.08 ms vs 48.06 ms without, 0.6 -> 50.97 ms: the table (64 MiB) does not fit one die's half of the L2
+    // next to the index map and the counters whatever the policy
+    static const float apw = [] { const char *e = getenv("SLR_BC_APW"); return e ? (float)atof(e) : 0.0f; }();
+    if (apw > 0.0f) {
+        static bool limit_set[64];
+        if (!limit_set[dev]) {
+            int maxp = 0;
+            cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
+            limit_set[dev] = true;
+        }
+        int maxw = 0;
+        cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        size_t bytes = (size_t)128 << tab.bbits;
+        if (maxw > 0 && bytes > (size_t)maxw) bytes = (size_t)maxw;
+        at[0].val.accessPolicyWindow.base_ptr = const_cast<uint4 *>(tab.bk);
+        at[0].val.accessPolicyWindow.num_bytes = bytes;
+        at[0].val.accessPolicyWindow.hitRatio = apw > 1.0f ? 1.0f : apw;
+        at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(WARPS_PER_BLOCK * 32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, bc_assign_kernel<EDMAX>, tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens, d_anchor,
+                                  n, d_out, d_work);
+    }
     bc_assign_kernel<EDMAX><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(tab, plusminus, three_prime, need_post, d_slices, stride, slice_len, d_lens,
                                                                         d_anchor, n, d_out, d_work);
     return cudaGetLastError();

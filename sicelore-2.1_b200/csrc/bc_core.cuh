@@ -13,7 +13,10 @@
 constexpr int SLR_MAX_OFFSETS = 9;             // plusminus <= 4
 constexpr uint32_t SLR_NONE32 = 0xFFFFFFFFu;
 constexpr unsigned long long SLR_VH_EMPTY = 0xFFFFFFFFFFFFFFFFull;
-constexpr int SLR_VH_SIZE = 256;
+#ifndef SLR_VH_BITS
+#define SLR_VH_BITS 9                          // 512 slots for at most 144 values: at a load of 0.28 the warp-wide insert rarely probes twice
+#endif
+constexpr int SLR_VH_SIZE = 1 << SLR_VH_BITS;
 
 // matches of one read: one slot per (offset index, ED level) — Matches is a HashSet whose equals() is
 // (readSeq, ED, offset) (BarcodeMatchTester.java:L433-L436), i.e. first hit per ED level per offset wins.
@@ -27,7 +30,7 @@ struct SlrMatchStore {
 SLR_HD int slr_offset_of(int k) { return (k == 0) ? 0 : ((k & 1) ? -((k + 1) / 2) : (k / 2)); }   // 0,-1,1,-2,2 (Parser.java:L198-L200)
 
 // ---- visited-hash lookup (value -> earliest processing time); insertion is done by the orchestration ----
-SLR_HD uint32_t slr_vh_slot(uint32_t v) { return (v * 0x9E3779B1u) >> 24; }
+SLR_HD uint32_t slr_vh_slot(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - SLR_VH_BITS); }
 SLR_HD uint32_t slr_vh_tmin(const unsigned long long *tab, uint32_t v)
 {
     uint32_t slot = slr_vh_slot(v);

@@ -132,8 +132,14 @@ SLR_HD SlrBucket slr_load_bucket(const SlrTableDev &t, int g, uint32_t bucket)
     const uint4 *p = t.bk + 2 * (((size_t)g << t.bbits) + bucket);
     SlrBucket r;
 #ifdef __CUDA_ARCH__
-    // one 256-bit read-only load = one 32-byte L2 sector per lane (sm_100: LDG.E.256.CONSTANT)
+    // one 256-bit read-only load = one 32-byte L2 sector per lane (sm_100: LDG.E.256.CONSTANT).  -DSLR_BC_L2HINT=1 keeps the table's
+    // sectors with L2::evict_last and streams the read slices / records with evict-first (.cs) accesses; measured on B200 (10 M reads,
+    // 3 M list, ED 2): 48.33 ms with the hints, 48.06 ms without, L2 sector hit rate 76 % either way (profiles/r2_bc_variants.txt) — off.
+#if defined(SLR_BC_L2HINT) && SLR_BC_L2HINT == 1
+    asm("ld.global.nc.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
         : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
         : "l"(p));
 #else
