@@ -220,6 +220,8 @@ int  slr_umi_session_cluster(slr_umi_session *s, int ed, const uint8_t *member, 
                              slr_umi_cluster_rec *rec);
 int  slr_umi_session_matrices(slr_umi_session *s, int32_t *out, int64_t n_cells);
 int64_t slr_umi_session_cells(const slr_umi_session *s);
+int64_t slr_umi_session_reads(const slr_umi_session *s);   /* reads / jobs of the batch: the sizes the cluster / assign record buffers need */
+int64_t slr_umi_session_jobs(const slr_umi_session *s);
 void slr_umi_session_destroy(slr_umi_session *s);
 
 /* ---- S6: clustering of the small jobs + UMI assignment --------------------------------------------------------- */

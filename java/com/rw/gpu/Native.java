@@ -44,6 +44,32 @@ public final class Native {
     public static native long umiSessionCells(long session);
     public static native int umiSessionMatrices(long session, ByteBuffer out, long nCells);
     public static native void umiSessionDestroy(long session);
+    /** ClusterOneHierarchical.call for every job of at most 100 reads (ClusterOneHierarchical.java:L61-L217) behind the same matrices: rec = 16 bytes per
+     *  read {int center, byte u1, byte u2, byte pos2, byte offsetCenterMean, short flags, short clusterSize, int nClusters}; params = null (config.xml /
+     *  UMIparameters defaults) or int[5] {completeLinkED, singleLinkED, singleLinkThreshold, foldDepthBelowMax, maxHier}; jobQv01 nullable: one byte per
+     *  job, mean_qv(read 0) > mean_qv(read 1) (OneUmiCluster.java:L53) */
+    public static native int umiAssign(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, int[] params,
+                                       ByteBuffer jobQv01, ByteBuffer out, ByteBuffer outOffsets, ByteBuffer rec);
+    public static native int umiSessionAssign(long session, int[] params, ByteBuffer jobQv01, ByteBuffer rec);
+    /** all GPUs of the box from this one JVM (slr_multi_*): nDevices <= 0 = every visible device, deviceIds nullable  (0 = failed) */
+    public static native long multiCreate(int nDevices, int[] deviceIds, int nStreams);
+    public static native void multiDestroy(long multi);
+    public static native int multiDevices(long multi);
+    public static native long multiBcTableCreate(long multi, long[] barcodes2bit, int[] rank);                     // replicated on every device (0 = failed)
+    public static native void multiBcTableDestroy(long table);
+    public static native int multiBcAssign(long multi, long table, int edMax, int plusMinus, boolean threePrime, ByteBuffer slices, int stride,
+                                           int sliceLen, ByteBuffer lens, ByteBuffer anchor, long n, ByteBuffer out);
+    public static native int multiBcExact(long multi, long table, boolean threePrime, ByteBuffer slices, int stride, int sliceLen, ByteBuffer lens,
+                                          ByteBuffer anchor, long n, ByteBuffer out);
+    /** assignedBarcodes2ndPass summed over the devices on the GPU (peer loads over NVLink), countsOut.length = 3 * number of barcodes */
+    public static native int multiBcCountsRead(long multi, long table, long[] countsOut);
+    public static native int multiBcCountsReset(long multi, long table);
+    public static native int multiUmiDist(long multi, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, ByteBuffer out,
+                                          ByteBuffer outOffsets);
+    public static native int multiUmiCluster(long multi, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, int ed,
+                                             ByteBuffer member, ByteBuffer rank, ByteBuffer rec);
+    public static native int multiUmiAssign(long multi, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, int[] params,
+                                            ByteBuffer jobQv01, ByteBuffer rec);
     /** candidate sets of the Illumina-guided search: groupKeys / groupOffsets = CSR of the per-(gene, cell) UMIs (IlluminaOneGeneOneCellData) or of the
      *  per-gene cell barcodes (BarcodesMap); allKeys = All10xselectedCells, emptyKeys = EmptyDropBarcodes (BC flavour, nullable)  (0 = failed) */
     public static native long guidedSetsCreate(long ctx, long[] groupKeys, long[] groupOffsets, long[] allKeys, int allEd, long[] emptyKeys,

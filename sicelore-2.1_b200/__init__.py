@@ -46,7 +46,7 @@ assert GUIDED_HIT.itemsize == 16
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
            "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_umi_assign", "slr_umi_assign_dev", "slr_umi_assign_scratch_bytes", "slr_umi_session_assign", "slr_umi_session_create", "slr_umi_session_cluster",
-           "slr_umi_session_matrices", "slr_umi_session_cells", "slr_umi_session_destroy", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
+           "slr_umi_session_matrices", "slr_umi_session_cells", "slr_umi_session_reads", "slr_umi_session_jobs", "slr_umi_session_destroy", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
            "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count",
            "slr_multi_create", "slr_multi_destroy", "slr_multi_n_devices", "slr_multi_ctx", "slr_multi_peer_access", "slr_multi_bc_table_create",
            "slr_multi_bc_table_destroy", "slr_multi_bc_table_replica", "slr_multi_bc_assign", "slr_multi_bc_exact", "slr_multi_bc_counts_read",

@@ -847,6 +847,8 @@ int slr_umi_session_matrices(slr_umi_session *S, int32_t *out, int64_t n_cells)
 }
 
 int64_t slr_umi_session_cells(const slr_umi_session *S) { return S ? S->cells : 0; }
+int64_t slr_umi_session_reads(const slr_umi_session *S) { return S ? S->n_reads : 0; }
+int64_t slr_umi_session_jobs(const slr_umi_session *S) { return S ? S->n_jobs : 0; }
 
 void slr_umi_session_destroy(slr_umi_session *S)
 {

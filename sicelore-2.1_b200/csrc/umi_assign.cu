@@ -62,7 +62,7 @@ struct UaShared {
 };
 
 // iteration order of a java.util.HashSet<Integer> filled in the order in[0..k): stable by bucket.  Returns true when two share a bucket.
-__device__ bool ua_jdk_order(const uint8_t *in, int k, uint8_t *out)
+__device__ __noinline__ bool ua_jdk_order(const uint8_t *in, int k, uint8_t *out)
 {
     const int cap = ua_jdk_cap(k);
     bool collide = false;
@@ -83,8 +83,35 @@ __device__ bool ua_jdk_order(const uint8_t *in, int k, uint8_t *out)
 }
 
 // iteration order of a fastutil IntOpenHashSet (default constructor) filled by add() in the order in[0..k): key 0 first, then the slots from
-// the last to the first.  tab: 256 bytes (64 when k <= 48).  Keys are read indices < 128, stored + 1 so that 0 = free slot.
-__device__ void ua_fastutil_order(const uint8_t *in, int k, uint8_t *out, uint8_t *tab)
+// the last to the first.  tab: 256 bytes (64 when k <= 48).  Keys are read indices < 128.  Up to 24 keys the table keeps its 32 slots and
+// its occupancy is one register (no clearing, no rehash): that is every cluster of almost every job.
+__device__ __noinline__ void ua_fastutil_order_big(const uint8_t *in, int k, uint8_t *out, uint8_t *tab);
+__device__ __forceinline__ void ua_fastutil_order(const uint8_t *in, int k, uint8_t *out, uint8_t *tab)
+{
+    if (k <= 24) {
+        uint32_t occ = 0;
+        bool has_zero = false;
+        for (int i = 0; i < k; i++) {
+            const int key = in[i];
+            if (key == 0) { has_zero = true; continue; }
+            int pos = (int)(ua_fu_mix(key) & 31u);
+            while ((occ >> pos) & 1u) pos = (pos + 1) & 31;
+            occ |= 1u << pos;
+            tab[pos] = (uint8_t)key;
+        }
+        int o = 0;
+        if (has_zero) out[o++] = 0;
+        while (occ) {                                        // slots from the last to the first
+            const int pos = 31 - __clz((int)occ);
+            occ &= ~(1u << pos);
+            out[o++] = tab[pos];
+        }
+        return;
+    }
+    ua_fastutil_order_big(in, k, out, tab);
+}
+// more than 24 keys: the table is rehashed on the way (32 -> 64 -> 128 -> 256 slots); rare, kept out of the hot code
+__device__ __noinline__ void ua_fastutil_order_big(const uint8_t *in, int k, uint8_t *out, uint8_t *tab)
 {
     int n = 32, size = 0;
     bool has_zero = false;
@@ -118,6 +145,39 @@ __device__ void ua_fastutil_order(const uint8_t *in, int k, uint8_t *out, uint8_
     if (has_zero) out[o++] = 0;
     for (int j = n - 1; j >= 0; j--)
         if (tab[j] != 0) out[o++] = (uint8_t)(tab[j] - 1);
+}
+
+// single link (unreachable with the reference's thresholds: 3000 > 100): pairs by (cost, i, j), merged while cost <= cut; one lane
+template <int MAXN>
+__device__ __noinline__ void ua_single_link(UaShared<MAXN> &S, int m, int cut)
+{
+    for (int a = 0; a < m; a++) S.tmp[0][a] = (uint8_t)a;            // root of every leaf
+    for (int s = 0; s <= cut; s++)
+        for (int i = 0; i < m; i++)
+            for (int j = i + 1; j < m; j++) {
+                if (S.D[i][j] != s) continue;
+                const int r1 = S.tmp[0][i], r2 = S.tmp[0][j];
+                if (r1 == r2) continue;
+                S.nxt[S.tail[r1]] = S.head[r2]; S.tail[r1] = S.tail[r2]; S.csize[r1] = (uint8_t)(S.csize[r1] + S.csize[r2]); S.csize[r2] = 0;
+                for (int x = 0; x < m; x++) if (S.tmp[0][x] == r2) S.tmp[0][x] = (uint8_t)r1;
+            }
+}
+
+// is the threshold graph a disjoint union of cliques?  (only then is the partition the same for every merge order)  Returns true when NOT.
+template <int MAXN>
+__device__ __noinline__ bool ua_not_cluster_graph(const UaShared<MAXN> &S, int m, int cut, int lane)
+{
+    bool bad = false;
+    for (int a = lane; a < m && !bad; a += 32) {
+        const int ra = S.iwn[a];
+        for (int b = 0; b < m && !bad; b++) {
+            if (b == a || S.E[ra][S.iwn[b]] > cut) continue;
+            const int rb = S.iwn[b];
+            for (int c = 0; c < m; c++)
+                if (c != a && c != b && ((S.E[ra][S.iwn[c]] <= cut) != (S.E[rb][S.iwn[c]] <= cut))) { bad = true; break; }
+        }
+    }
+    return __any_sync(FULL, bad);
 }
 
 template <int MAXN>
@@ -230,17 +290,7 @@ __device__ void ua_job(UaShared<MAXN> &S, const int32_t *__restrict__ mat, int n
             __syncwarp();
         }
     } else if (lane == 0) {
-        // ---- single link (unreachable with the reference's thresholds: 3000 > 100): pairs by (cost, i, j), merged while cost <= cut ----
-        for (int a = 0; a < m; a++) S.tmp[0][a] = (uint8_t)a;            // root of every leaf
-        for (int s = 0; s <= cut; s++)
-            for (int i = 0; i < m; i++)
-                for (int j = i + 1; j < m; j++) {
-                    if (S.D[i][j] != s) continue;
-                    const int r1 = S.tmp[0][i], r2 = S.tmp[0][j];
-                    if (r1 == r2) continue;
-                    S.nxt[S.tail[r1]] = S.head[r2]; S.tail[r1] = S.tail[r2]; S.csize[r1] = (uint8_t)(S.csize[r1] + S.csize[r2]); S.csize[r2] = 0;
-                    for (int x = 0; x < m; x++) if (S.tmp[0][x] == r2) S.tmp[0][x] = (uint8_t)r1;
-                }
+        ua_single_link<MAXN>(S, m, cut);
     }
     __syncwarp();
     if (single) {
@@ -262,10 +312,17 @@ __device__ void ua_job(UaShared<MAXN> &S, const int32_t *__restrict__ mat, int n
             const int k = S.csize[s];
             if (k <= 1) continue;
             int x = S.head[s];
-            for (int i = 0; i < k; i++) { S.tmp[0][i] = (uint8_t)x; x = S.nxt[x]; }                     // memberSet(): reduced indices
-            chain_dep |= ua_jdk_order(S.tmp[0], k, S.tmp[1]);
-            for (int i = 0; i < k; i++) S.tmp[0][i] = S.iwn[S.tmp[1][i]];                              // transformIndices_AndRemoveSingletons
-            chain_dep |= ua_jdk_order(S.tmp[0], k, S.tmp[1]);
+            if (n <= 16) {
+                // every index is below the smallest HashSet table (16 buckets): both sets iterate in ascending order, no chain
+                uint32_t mem = 0;
+                for (int i = 0; i < k; i++) { mem |= 1u << S.iwn[x]; x = S.nxt[x]; }
+                for (int i = 0; i < k; i++) { const int b = __ffs((int)mem) - 1; mem &= mem - 1u; S.tmp[1][i] = (uint8_t)b; }
+            } else {
+                for (int i = 0; i < k; i++) { S.tmp[0][i] = (uint8_t)x; x = S.nxt[x]; }                 // memberSet(): reduced indices
+                chain_dep |= ua_jdk_order(S.tmp[0], k, S.tmp[1]);
+                for (int i = 0; i < k; i++) S.tmp[0][i] = S.iwn[S.tmp[1][i]];                          // transformIndices_AndRemoveSingletons
+                chain_dep |= ua_jdk_order(S.tmp[0], k, S.tmp[1]);
+            }
             ua_fastutil_order(S.tmp[1], k, &S.it[o], S.tab);                                           // toCollection(OneUmiCluster::new)
             S.cl_start[n_cl] = (uint8_t)o; S.cl_len[n_cl] = (uint8_t)k;
             for (int i = 0; i < k; i++) S.clid[S.it[o + i]] = (uint8_t)n_cl;
@@ -279,21 +336,8 @@ __device__ void ua_job(UaShared<MAXN> &S, const int32_t *__restrict__ mat, int n
     chain_dep = __shfl_sync(FULL, (int)chain_dep, 0) != 0;
     __syncwarp();
     if (n_cl == 0) return;
-    // ---- is the threshold graph a disjoint union of cliques?  (only then is the partition the same for every merge order) ------------
     bool unpinned = false;
-    if (tie_seen) {
-        bool bad = false;
-        for (int a = lane; a < m && !bad; a += 32) {
-            const int ra = S.iwn[a];
-            for (int b = 0; b < m && !bad; b++) {
-                if (b == a || S.E[ra][S.iwn[b]] > cut) continue;
-                const int rb = S.iwn[b];
-                for (int c = 0; c < m; c++)
-                    if (c != a && c != b && ((S.E[ra][S.iwn[c]] <= cut) != (S.E[rb][S.iwn[c]] <= cut))) { bad = true; break; }
-            }
-        }
-        unpinned = __any_sync(FULL, bad) || chain_dep;
-    }
+    if (tie_seen) unpinned = ua_not_cluster_graph<MAXN>(S, m, cut, lane) || chain_dep;
     // ---- depth rule, centres, mean shift: lane = cluster --------------------------------------------------------------------------
     int n_list = 0;
     for (int c0 = 0; c0 < n_cl; c0 += 32) {

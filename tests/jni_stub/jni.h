@@ -13,6 +13,7 @@ struct JNINativeInterface_;
 typedef const struct JNINativeInterface_ *JNIEnv;
 struct JNINativeInterface_ {
     void *(*GetDirectBufferAddress)(JNIEnv *, jobject);
+    jlong (*GetDirectBufferCapacity)(JNIEnv *, jobject);
     jsize (*GetArrayLength)(JNIEnv *, jarray);
     jlong *(*GetLongArrayElements)(JNIEnv *, jlongArray, jboolean *);
     jint *(*GetIntArrayElements)(JNIEnv *, jintArray, jboolean *);
