@@ -30,7 +30,7 @@ def fastq_records(path):
             seq = f.readline().strip()
             f.readline()
             f.readline()
-            yield name[1:].strip(), seq
+            yield name[1:].split()[0], seq                        # the read name ends at the first blank (' cellBC=' is the FASTQ comment)
 
 
 def build_slice(stranded, adapterpos, three_prime=True):
@@ -55,12 +55,8 @@ def main():
     a = ap.parse_args()
     import __graft_entry__ as g
     pkg = g.load_package()
-    fmt = __import__("importlib").import_module("sicelore_b200.formats") if "sicelore_b200.formats" in sys.modules else None
-    if fmt is None:
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("sicelore_b200.formats", os.path.join(ROOT, "sicelore-2.1_b200", "formats.py"))
-        fmt = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(fmt)
+    import importlib
+    fmt = importlib.import_module("sicelore_b200.formats")
     keys = pkg.read_whitelist(a.list)
     tp = not a.five_prime
     names, slices, anchors, lens, want = [], [], [], [], []
