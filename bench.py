@@ -191,6 +191,24 @@ def load_profile(pkg, kernel):
     return None
 
 
+def issue_roofline(pkg, kernel, units, ms, sm_mhz, sms, unit="read"):
+    """INT-issue roofline of one kernel: warp instructions per unit (ncu count of the profile that matches the loaded sources) x units / kernel time,
+    against SMs x 4 schedulers x SM clock.  Shared by bench.py and tools/bench_*.py so that every bench line of the repository names the bound
+    that actually limits its kernel."""
+    peak = sms * 4 * (sm_mhz or 1965.0) / 1e3
+    roof = {"bound": "int_issue", "kernel": kernel, "kernel_ms_per_launch": ms, "units_per_launch": units, "unit": "Ginst/s", "peak": peak,
+            "peak_source": "%d SMs x 4 schedulers x %.3f GHz (SM clock sampled under load)" % (sms, (sm_mhz or 1965.0) / 1e3)}
+    prof = load_profile(pkg, kernel)
+    if prof is not None and prof.get("inst_executed_per_unit"):
+        ach = prof["inst_executed_per_unit"] * units / (ms / 1e3) / 1e9
+        roof.update({"achieved": ach, "frac": ach / peak, "inst_per_" + unit: prof["inst_executed_per_unit"],
+                     "traffic": (prof.get("dram_bytes_per_unit") or 0) * units or None, "profile": prof["file"], "profile_csrc_sha256": prof["csrc_sha256"]})
+    else:
+        roof.update({"achieved": None, "frac": None, "traffic": None,
+                     "note": "no profile under profiles/ matches the loaded library's sources (csrc sha256 %s): run tools/make_profile.py" % pkg.csrc_sha256()[:16]})
+    return roof, prof
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))

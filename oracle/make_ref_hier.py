@@ -333,7 +333,7 @@ def make_params(vm, ed_complete, ed_single, single_thr, fold):
     return P
 
 
-def run_job(vm, packed, prm, qv01):
+def run_job(vm, packed, prm, qv01, cls="ClusterOneHierarchical"):
     n = len(packed)
     P = make_params(vm, *prm)
     reads = []
@@ -353,7 +353,7 @@ def run_job(vm, packed, prm, qv01):
     stats = bare(vm, "com/rw/umifinder/scanstats/ScanStats")
     stats.f["nUMIfoundClustering"] = J.JNative("java/util/concurrent/atomic/AtomicInteger", [0])
     vm.attrs, vm.flagged, vm.packed = {}, set(), packed
-    me = vm.construct(CL + "ClusterOneHierarchical", "(Lcom/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams;Lorg/apache/commons/lang3/tuple/ImmutablePair;"
+    me = vm.construct(CL + cls, "(Lcom/rw/umifinder/parameters/ParametersBarcodeUMiFinderAppParams;Lorg/apache/commons/lang3/tuple/ImmutablePair;"
                       "Lcom/rw/umifinder/scanstats/ScanStats;)V", P, pair, stats)
     vm.call_virtual(me, "call", "()Lorg/apache/commons/lang3/tuple/ImmutablePair;")
     skipped_flag = None

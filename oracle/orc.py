@@ -200,10 +200,10 @@ class AssignParams(C.Structure):
     """config.xml:270-278 + UMIparameters defaults: complete-link ED 2, single-link ED 1, switch above 3000 reads with a neighbour,
     foldDepthBelowMaxDiscardForClustering 50, ClusterOneHierarchical up to 100 reads"""
     _fields_ = [("ed_complete", C.c_int32), ("ed_single", C.c_int32), ("single_threshold", C.c_int32), ("fold_depth", C.c_int32),
-                ("max_hier", C.c_int32)]
+                ("max_hier", C.c_int32), ("deep", C.c_int32)]
 
-    def __init__(self, ed_complete=2, ed_single=1, single_threshold=3000, fold_depth=50, max_hier=100):
-        super().__init__(ed_complete, ed_single, single_threshold, fold_depth, max_hier)
+    def __init__(self, ed_complete=2, ed_single=1, single_threshold=3000, fold_depth=50, max_hier=100, deep=1):
+        super().__init__(ed_complete, ed_single, single_threshold, fold_depth, max_hier, deep)
 
 
 def umi_assign_batch(matrices, job_offsets, out_offsets, params=None, job_qv01=None, n_threads=0):

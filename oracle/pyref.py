@@ -936,3 +936,288 @@ def assign_hier(matrix, ed_complete=2, ed_single=1, single_threshold=3000, fold_
     for r in rec:
         r["n_clusters"], r["tie_unpin"] = len(cluster_list), unpin
     return rec
+
+
+# ---- F!com/rw/umifinder/analyzers/clustering/ClusterOne_MyClustering (jobs of more than 100 reads) ------------------------------------------
+# Every stream of this class is parallel above 30 reads (ClusterOne_MyClustering.java:L176-L177, L187-L189); the restatement follows the SEQUENTIAL
+# semantics (what a JVM with one worker thread produces).  Containers whose order reaches the result are modelled explicitly.
+class FuIntSet:
+    """fastutil 8.2.2 IntOpenHashSet as OneUmiCluster uses it: add, iteration, and java.util.AbstractCollection.removeAll(Collection) — the set's
+    iterator walks the slots downwards and removes through SetIterator.remove (backward-shift deletion, entries that wrap around the table end are
+    remembered in `wrapped` and visited last).  Restated from the published source (the jar is not in the mount)."""
+
+    def __init__(self):
+        self.n, self.size, self.has_zero = 32, 0, False
+        self.key = [0] * 32
+        self.min_n = 32
+
+    def _max_fill(self):
+        return min(int(-(-self.n * 3 // 4)), self.n - 1)                      # HashCommon.maxFill(n, .75f)
+
+    def add(self, k):
+        if k == 0:
+            if self.has_zero:
+                return False
+            self.has_zero = True
+        else:
+            mask = self.n - 1
+            pos = fastutil_mix(k) & mask
+            while self.key[pos] != 0:
+                if self.key[pos] == k:
+                    return False
+                pos = (pos + 1) & mask
+            self.key[pos] = k
+        self.size += 1
+        if self.size - 1 >= self._max_fill():                                 # if (size++ >= maxFill) rehash(arraySize(size + 1, f))
+            need = -(-(self.size + 1) * 4 // 3)
+            nn = 2
+            while nn < need:
+                nn *= 2
+            self._rehash(nn)
+        return True
+
+    def _rehash(self, nn):
+        new = [0] * nn
+        for i in range(self.n - 1, -1, -1):
+            if self.key[i] != 0:
+                pos = fastutil_mix(self.key[i]) & (nn - 1)
+                while new[pos] != 0:
+                    pos = (pos + 1) & (nn - 1)
+                new[pos] = self.key[i]
+        self.key, self.n = new, nn
+
+    def order(self):
+        return ([0] if self.has_zero else []) + [self.key[i] for i in range(self.n - 1, -1, -1) if self.key[i] != 0]
+
+    def __len__(self):
+        return self.size
+
+    def _shift(self, pos, wrapped=None):
+        key, mask = self.key, self.n - 1
+        while True:
+            last = pos
+            pos = (pos + 1) & mask
+            while True:
+                curr = key[pos]
+                if curr == 0:
+                    key[last] = 0
+                    return
+                slot = fastutil_mix(curr) & mask
+                if (last >= slot or slot > pos) if last <= pos else (last >= slot and slot > pos):
+                    break
+                pos = (pos + 1) & mask
+            if wrapped is not None and pos < last:
+                wrapped.append(key[pos])
+            key[last] = curr
+
+    def remove(self, k):                                                       # IntOpenHashSet.remove(int)
+        if k == 0:
+            if not self.has_zero:
+                return False
+            self.has_zero = False
+            self.size -= 1
+        else:
+            mask = self.n - 1
+            pos = fastutil_mix(k) & mask
+            while self.key[pos] != k:
+                if self.key[pos] == 0:
+                    return False
+                pos = (pos + 1) & mask
+            self.size -= 1
+            self._shift(pos)
+        if self.n > self.min_n and self.size < self._max_fill() // 4 and self.n > 16:
+            self._rehash(self.n // 2)
+        return True
+
+    def remove_all(self, victims):                                             # AbstractCollection.removeAll: iterate THIS, it.remove() on a hit
+        victims = set(victims)
+        pos, c, must_null, wrapped = self.n, self.size, self.has_zero, []
+        while c != 0:
+            c -= 1
+            if must_null:
+                must_null = False
+                if 0 in victims:
+                    self.has_zero = False
+                    self.size -= 1
+                continue
+            cur = None
+            while cur is None:
+                pos -= 1
+                if pos < 0:
+                    cur = wrapped[-pos - 1]
+                    if cur in victims:
+                        self.remove(cur)                                       # "we're removing wrapped entries": the set's own remove
+                    break
+                if self.key[pos] != 0:
+                    cur = self.key[pos]
+                    if cur in victims:
+                        self._shift(pos, wrapped)
+                        self.size -= 1
+
+
+class _JSetOfInts:
+    """a java.util.Set<Integer> as an element of another HashSet: AbstractSet.hashCode = sum of the elements, equals by content"""
+
+    def __init__(self, items):
+        self.items = list(items)
+        self.fs = frozenset(items)
+
+    def jhash(self):
+        s = sum(self.items) & 0xFFFFFFFF
+        return s
+
+    def jequals(self, o):
+        return self.fs == o.fs
+
+
+def chm_key_order(keys_in_insertion_order):
+    """iteration order of a java.util.concurrent.ConcurrentHashMap<Integer, ?> filled by computeIfAbsent in the given order by ONE thread:
+    table of 16, doubled when the count reaches .75 of it (addCount), bins are chains in insertion order, a transfer keeps the last run of a
+    bin and PREPENDS the nodes before it (so their order reverses).  Second value: a bin reached the treeify threshold (not modelled)."""
+    cap, sc, count, long_bin = 16, 12, 0, False
+    table = [[] for _ in range(cap)]
+    spread = lambda h: (h ^ (h >> 16)) & 0x7FFFFFFF
+    for k in keys_in_insertion_order:
+        h = spread(k & 0xFFFFFFFF)
+        b = table[h & (cap - 1)]
+        if any(x == k for (_, x) in b):
+            continue
+        if len(b) >= 8:
+            long_bin = True
+        b.append((h, k))
+        count += 1
+        while count >= sc:
+            new = [[] for _ in range(2 * cap)]
+            for i, chain in enumerate(table):
+                if not chain:
+                    continue
+                run_bit, last_run = chain[0][0] & cap, 0
+                for j in range(1, len(chain)):
+                    bb = chain[j][0] & cap
+                    if bb != run_bit:
+                        run_bit, last_run = bb, j
+                lo = list(chain[last_run:]) if run_bit == 0 else []
+                hi = list(chain[last_run:]) if run_bit != 0 else []
+                for j in range(last_run):
+                    if chain[j][0] & cap == 0:
+                        lo.insert(0, chain[j])
+                    else:
+                        hi.insert(0, chain[j])
+                new[i], new[i + cap] = lo, hi
+            table, cap = new, 2 * cap
+            sc = cap - (cap >> 2)
+    return [k for chain in table for (_, k) in chain], long_bin
+
+
+def _my_cluster_local(indices, ED, ed):
+    """ClusterOne_MyClustering.clusterLocal (…java:L175-L219).  Returns (list of clusters as HashSet<Integer> iteration orders, in the iteration
+    order of the resulting HashSet<Set<Integer>>; harmful_tie; long_bin)."""
+    nbr = {}
+    for a in indices:                                                          # L179-L184
+        s = [v for v in indices if ED(a, v) <= ed]
+        if len(s) > 1:
+            nbr[a] = s
+    keys = fastutil_key_order(list(nbr.keys()))                                # Int2ObjectOpenHashMap filled in the order of `indices` (L185)
+    nset = {a: frozenset(s) for a, s in nbr.items()}
+    chosen, harmful = {}, False
+    for c in keys:                                                             # L190-L196: Stream.max keeps the FIRST of equal maxima
+        best = None
+        for e in keys:
+            if c in nset[e]:
+                if best is None or len(nset[e]) > len(nset[best]):
+                    best = e
+        for e in keys:
+            if c in nset[e] and len(nset[e]) == len(nset[best]) and nset[e] != nset[best]:
+                harmful = True
+        chosen[c] = best
+    groups, first_seen = {}, []
+    for c in keys:                                                             # L199: groupingByConcurrent(right, mapping(left, toSet()))
+        e = chosen[c]
+        if e not in groups:
+            groups[e] = JHashSet()
+            first_seen.append(e)
+        groups[e].add(_JInt(c))
+    order, long_bin = chm_key_order(first_seen)
+    outer = JHashSet()                                                         # L219: idMap.values().stream().collect(toSet())
+    for e in order:
+        long_bin |= groups[e].treeified
+        outer.add(_JSetOfInts([x.v for x in groups[e]]))
+    long_bin |= outer.treeified
+    return [s.items for s in outer], harmful, long_bin
+
+
+def assign_myclust(matrix, ed=2, fold_depth=50, qv01=False):
+    """ClusterOne_MyClustering.call (…java:L59-L166) on one job's packed matrix, sequential-stream semantics.  Same records as assign_hier."""
+    import math
+    n = len(matrix)
+    ED = lambda a, b: _i8(int(matrix[a][b]) & 0xFFFFFF)
+    rec = [dict(center=-1, u1=0, u2=-1, pos2=0, off_mean=0, assigned=False, skipped=False, cluster_size=0, n_clusters=0, tie_unpin=False)
+           for _ in range(n)]
+
+    def make_cluster(members):                                                 # toCollection(OneUmiCluster::new) + setClusterCenter (L86-L87)
+        s = FuIntSet()
+        for x in members:
+            s.add(x)
+        return dict(set=s, center=center_of(s))
+
+    def center_of(s):                                                          # OneUmiCluster.setClusterCenterNotPreGrouped (OneUmiCluster.java:L49-L65)
+        it = s.order()
+        if len(it) == 2:
+            return it[0] if qv01 else it[1]
+        sums = [sum(int(float(ED(a, w)) ** 2.0) for w in it if w != a) for a in it]
+        return it[sums.index(min(sums))]                                       # sorted() is stable, findFirst
+
+    full, harmful, long_bin = _my_cluster_local(list(range(n)), ED, ed)        # L72-L73
+    if not full:                                                               # Optional.empty (L219): idMap is empty
+        return rec
+    maxdepth = max(len(c) for c in full)                                       # L77
+    cluster_list = []
+    for c in full:                                                             # L78-L88
+        if len(c) * fold_depth > maxdepth:
+            cluster_list.append(make_cluster(c))
+        else:
+            for x in c:
+                rec[x]["skipped"], rec[x]["cluster_size"] = True, len(c)
+    clustered = set(x for cl in cluster_list for x in cl["set"].order())       # L90
+    unclustered = [d for d in range(n) if d not in clustered]                  # L91
+    removed = []
+    for cl in cluster_list:                                                    # L102, L60-L65: removeOffCenter
+        rem = [s_ for s_ in cl["set"].order() if ED(s_, cl["center"]) > ed]
+        if rem:                                                                # OneUmiCluster.removeEntries (L114-L119)
+            cl["set"].remove_all(rem)
+            cl["center"] = center_of(cl["set"])
+        removed += rem
+    unclustered += removed                                                     # L104
+    if removed:                                                                # L106-L112
+        extra, h2, l2 = _my_cluster_local(unclustered, ED, ed)
+        harmful |= h2
+        long_bin |= l2
+        for c in extra:
+            if len(c) > 1:
+                cluster_list.append(make_cluster(c))
+    for cl in cluster_list:                                                    # L116-L164
+        it = cl["set"].order()
+        if len(it) <= 1:
+            continue
+        center = cl["center"]
+        offs = [(-1 if matrix[center][v] & 0x08000000 else 0 if matrix[center][v] & 0x10000000 else 1 if matrix[center][v] & 0x20000000 else 0)
+                for v in it if v != center]
+        off_mean = int(math.floor(sum(offs) / len(offs) + 0.5))
+        filtered = [s_ for s_ in it if ED(s_, center) <= ed]
+        if len(filtered) <= 1:
+            continue
+        inside = set(it)
+        for x in filtered:
+            r = rec[x]
+            if r["skipped"]:                                                   # ClusterOneBase.java:L122-L123: UMI_CLUSTERING_SKIPPED_HIGHCOMPLEXITY set in round 1
+                continue
+            r.update(center=center, assigned=True, cluster_size=len(it), off_mean=off_mean, u1=ED(center, x))
+            p = int(matrix[center][x])
+            r["pos2"] = 0 if p & 0x01000000 else 1 if p & 0x02000000 else 2 if p & 0x04000000 else 1
+            if len(cluster_list) > 1:
+                outside = [ED(x, y) for y in range(n) if y not in inside]
+                if outside:
+                    r["u2"] = min(outside)
+    for r in rec:
+        r["n_clusters"], r["tie_unpin"] = len(cluster_list), bool(harmful or long_bin)
+    return rec

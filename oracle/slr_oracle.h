@@ -191,13 +191,14 @@ void    orc_umi_cluster_batch(const int32_t *matrices, const int64_t *job_offset
 #define ORC_UA_ASSIGNED  1u   /* the read is in a cluster of the final list: setSamflagsAndStatsForClustered runs for it */
 #define ORC_UA_SKIPPED   2u   /* its cluster failed the depth rule: flagDontUMIassignRecords (UMI_CLUSTERING_SKIPPED_HIGHCOMPLEXITY) */
 #define ORC_UA_TIE_UNPIN 4u   /* the job's result can depend on the JVM's identity-hash order (ObjectToSet's HashSet<PairScore>) */
-#define ORC_UA_DEEP      8u   /* job of more than max_hier reads: ClusterOne_MyClustering's, not clustered here */
+#define ORC_UA_DEEP      8u   /* job of more than max_hier reads: ClusterOne_MyClustering's (clustered by orc_umi_assign_myclust when params.deep) */
 typedef struct {
     int32_t ed_complete;      /* umi_completelinkclusteringED (config.xml:270) */
     int32_t ed_single;        /* umi_singlelinkclusteringED (config.xml:272) */
     int32_t single_threshold; /* complexity_threshold_for_switch_to_single_link_clustering (config.xml:278) */
     int32_t fold_depth;       /* foldDepthBelowMaxDiscardForClustering (UMIparameters.java:L118: 50) */
     int32_t max_hier;         /* largest job ClusterOneHierarchical gets (UmiClustering.java:L240: 100) */
+    int32_t deep;             /* 1: larger jobs run ClusterOne_MyClustering.call (records carry ORC_UA_DEEP too); 0: they are only flagged ORC_UA_DEEP */
 } orc_assign_params;
 typedef struct {
     int32_t  center;          /* job-local index of OneUmiCluster.getCenter() of the read's cluster; -1 = not clustered */
@@ -210,6 +211,7 @@ typedef struct {
     int32_t  n_clusters;      /* cluster_list.size() of the job */
 } orc_assign_rec;             /* 16 bytes, same layout as slr_umi_assign_rec */
 void orc_umi_assign_hier(const int32_t *matrix, int64_t n, const orc_assign_params *P, int qv01, orc_assign_rec *rec);
+void orc_umi_assign_myclust(const int32_t *matrix, int64_t n, const orc_assign_params *P, int qv01, orc_assign_rec *rec);
 void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs,
                           const orc_assign_params *P, const uint8_t *job_qv01, orc_assign_rec *rec, int n_threads);
 

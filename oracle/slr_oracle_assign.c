@@ -311,6 +311,300 @@ void orc_umi_assign_hier(const int32_t *matrix, int64_t n64, const orc_assign_pa
     free(cl_it); free(cl_size); free(tmpA); free(tmpB); free(cl_of); free(D); free(dist); free(iwn);
 }
 
+/* =====================================================================================================================================
+ * ClusterOne_MyClustering.call — the clusterer of every job of MORE than 100 reads (UmiClustering.java:L240)
+ *   F!com/rw/umifinder/analyzers/clustering/ClusterOne_MyClustering.class (ClusterOne_MyClustering.java:L59-L166 call, L175-L219 clusterLocal)
+ *   OneUmiCluster.removeEntries / setClusterCenterNotPreGrouped (OneUmiCluster.java:L114-L119, L49-L65)
+ * All of its streams are parallel above 30 reads (L176-L177, L187-L189); this restatement has the SEQUENTIAL semantics (a JVM with one worker
+ * thread).  Containers whose order reaches the result: fastutil Int2ObjectOpenHashMap (possibleClusters, L185) and IntOpenHashSet (OneUmiCluster,
+ * incl. java.util.AbstractCollection.removeAll driven by the set's own iterator), java.util.HashSet<Integer>, ConcurrentHashMap (idMap, L199:
+ * bins in insertion order, a transfer keeps a bin's last run and prepends the nodes before it), HashSet<Set<Integer>> (L219, hash = element sum).
+ * ORC_UA_TIE_UNPIN here = (a) a read had several largest neighbour sets to choose from that are not the same set (Stream.max keeps the first in the
+ * map's iteration order, which a parallel toMap does not fix), or (b) a JDK/CHM bin reached the treeify threshold (not modelled). */
+static uint32_t jdk_spread(uint32_t h) { return h ^ (h >> 16); }
+static uint64_t sig_mix(int v)
+{
+    uint64_t h = (uint64_t)(v + 1) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    return h;
+}
+/* iteration order of a java.util.HashSet filled in the given order; hash[i] = hashCode of element i (elements are distinct) */
+static void jdk_order_by_hash(const uint32_t *hash, int k, int *perm, int *long_bin)
+{
+    const int cap = jdk_cap_for(k);
+    int *cnt = (int *)calloc((size_t)cap + 1, sizeof(int));
+    for (int i = 0; i < k; i++) cnt[(jdk_spread(hash[i]) & (uint32_t)(cap - 1)) + 1]++;
+    for (int b = 0; b < cap; b++) { if (cnt[b + 1] >= 9) *long_bin = 1; cnt[b + 1] += cnt[b]; }
+    for (int i = 0; i < k; i++) perm[cnt[jdk_spread(hash[i]) & (uint32_t)(cap - 1)]++] = i;
+    free(cnt);
+}
+/* iteration order of a ConcurrentHashMap<Integer, ?> filled by one thread in the given order (keys distinct) */
+typedef struct { uint32_t h; int k; } chm_node;
+static void chm_order(const int *keys, int K, int *out, int *long_bin)
+{
+    int cap = 16, sc = 12, count = 0;
+    chm_node **tab = (chm_node **)calloc((size_t)cap, sizeof(chm_node *));
+    int *len = (int *)calloc((size_t)cap, sizeof(int));
+    for (int t = 0; t < K; t++) {
+        const uint32_t h = jdk_spread((uint32_t)keys[t]) & 0x7FFFFFFFu;
+        const int b = (int)(h & (uint32_t)(cap - 1));
+        if (len[b] >= 8) *long_bin = 1;
+        tab[b] = (chm_node *)realloc(tab[b], (size_t)(len[b] + 1) * sizeof(chm_node));
+        tab[b][len[b]].h = h; tab[b][len[b]].k = keys[t]; len[b]++;
+        count++;
+        while (count >= sc) {                                                          /* addCount -> transfer */
+            chm_node **nt = (chm_node **)calloc((size_t)cap * 2, sizeof(chm_node *));
+            int *nl = (int *)calloc((size_t)cap * 2, sizeof(int));
+            for (int i = 0; i < cap; i++) {
+                if (!len[i]) continue;
+                const chm_node *c = tab[i];
+                uint32_t run_bit = c[0].h & (uint32_t)cap; int last_run = 0;
+                for (int j = 1; j < len[i]; j++) { const uint32_t bb = c[j].h & (uint32_t)cap; if (bb != run_bit) { run_bit = bb; last_run = j; } }
+                chm_node *lo = (chm_node *)malloc((size_t)len[i] * sizeof(chm_node)), *hi = (chm_node *)malloc((size_t)len[i] * sizeof(chm_node));
+                int nlo = 0, nhi = 0;
+                for (int j = last_run - 1; j >= 0; j--) {                               /* prepended one by one: they end up reversed, before the run */
+                    if ((c[j].h & (uint32_t)cap) == 0) lo[nlo++] = c[j]; else hi[nhi++] = c[j];
+                }
+                for (int j = last_run; j < len[i]; j++) { if (run_bit == 0) lo[nlo++] = c[j]; else hi[nhi++] = c[j]; }
+                nt[i] = lo; nl[i] = nlo; nt[i + cap] = hi; nl[i + cap] = nhi;
+                free(tab[i]);
+            }
+            free(tab); free(len); tab = nt; len = nl; cap *= 2; sc = cap - (cap >> 2);
+        }
+    }
+    int o = 0;
+    for (int i = 0; i < cap; i++) { for (int j = 0; j < len[i]; j++) out[o++] = tab[i][j].k; free(tab[i]); }
+    free(tab); free(len);
+}
+
+/* fastutil IntOpenHashSet with the operations OneUmiCluster sees */
+typedef struct { int n, size, has_zero, min_n; int *key; } fuset;
+static int fu_max_fill(int n) { const int c = (int)ceil(n * 0.75f); return c < n - 1 ? c : n - 1; }
+static void fu_init(fuset *s) { s->n = 32; s->size = 0; s->has_zero = 0; s->min_n = 32; s->key = (int *)calloc(32, sizeof(int)); }
+static void fu_rehash(fuset *s, int nn)
+{
+    int *nk = (int *)calloc((size_t)nn, sizeof(int));
+    for (int j = s->n - 1; j >= 0; j--)
+        if (s->key[j] != 0) { int pos = (int)(fu_mix(s->key[j]) & (uint32_t)(nn - 1)); while (nk[pos] != 0) pos = (pos + 1) & (nn - 1); nk[pos] = s->key[j]; }
+    free(s->key); s->key = nk; s->n = nn;
+}
+static void fu_add(fuset *s, int k)
+{
+    if (k == 0) { if (s->has_zero) return; s->has_zero = 1; }
+    else {
+        int pos = (int)(fu_mix(k) & (uint32_t)(s->n - 1));
+        while (s->key[pos] != 0) { if (s->key[pos] == k) return; pos = (pos + 1) & (s->n - 1); }
+        s->key[pos] = k;
+    }
+    if (s->size++ >= fu_max_fill(s->n)) fu_rehash(s, fu_array_size(s->size + 1));
+}
+static int fu_order(const fuset *s, int *out)
+{
+    int o = 0;
+    if (s->has_zero) out[o++] = 0;
+    for (int j = s->n - 1; j >= 0; j--) if (s->key[j] != 0) out[o++] = s->key[j];
+    return o;
+}
+static void fu_shift(fuset *s, int pos, int *wrapped, int *n_wrapped)
+{
+    const int mask = s->n - 1;
+    for (;;) {
+        const int last = pos;
+        int curr;
+        pos = (pos + 1) & mask;
+        for (;;) {
+            if ((curr = s->key[pos]) == 0) { s->key[last] = 0; return; }
+            const int slot = (int)(fu_mix(curr) & (uint32_t)mask);
+            if (last <= pos ? (last >= slot || slot > pos) : (last >= slot && slot > pos)) break;
+            pos = (pos + 1) & mask;
+        }
+        if (wrapped && pos < last) wrapped[(*n_wrapped)++] = curr;
+        s->key[last] = curr;
+    }
+}
+static void fu_remove(fuset *s, int k)                                                  /* IntOpenHashSet.remove(int) */
+{
+    if (k == 0) { if (!s->has_zero) return; s->has_zero = 0; s->size--; }
+    else {
+        int pos = (int)(fu_mix(k) & (uint32_t)(s->n - 1));
+        while (s->key[pos] != k) { if (s->key[pos] == 0) return; pos = (pos + 1) & (s->n - 1); }
+        s->size--;
+        fu_shift(s, pos, NULL, NULL);
+    }
+    if (s->n > s->min_n && s->size < fu_max_fill(s->n) / 4 && s->n > 16) fu_rehash(s, s->n / 2);
+}
+/* AbstractCollection.removeAll(c): walk THIS with the set's iterator, Iterator.remove() where victim[x] is set */
+static void fu_remove_all(fuset *s, const uint8_t *victim)
+{
+    int pos = s->n, c = s->size, must_null = s->has_zero, n_wrapped = 0;
+    int *wrapped = (int *)malloc((size_t)(s->size + 1) * sizeof(int));
+    while (c != 0) {
+        c--;
+        if (must_null) { must_null = 0; if (victim[0]) { s->has_zero = 0; s->size--; } continue; }
+        for (;;) {
+            if (--pos < 0) { const int cur = wrapped[-pos - 1]; if (victim[cur]) fu_remove(s, cur); break; }
+            if (s->key[pos] != 0) { if (victim[s->key[pos]]) { fu_shift(s, pos, wrapped, &n_wrapped); s->size--; } break; }
+        }
+    }
+    free(wrapped);
+}
+
+typedef struct { fuset set; int center; } mycluster;
+
+static int my_center(const int32_t *matrix, int n, const fuset *s, int qv01, int *tmp)  /* OneUmiCluster.java:L49-L65 */
+{
+    const int k = fu_order(s, tmp);
+    if (k == 2) return qv01 ? tmp[0] : tmp[1];
+    long best = -1; int center = tmp[0];
+    for (int i = 0; i < k; i++) {
+        long sum = 0;
+        for (int j = 0; j < k; j++) if (j != i) { const int e = ed_of(matrix[(size_t)tmp[i] * n + tmp[j]]); sum += (long)e * e; }
+        if (best < 0 || sum < best) { best = sum; center = tmp[i]; }
+    }
+    return center;
+}
+
+/* clusterLocal (L175-L219) over `idx` (L indices in the caller's order).  Clusters come back as one flat member array (each in the iteration order of
+ * its HashSet<Integer>) with n_cl + 1 offsets, in the iteration order of the HashSet<Set<Integer>>.  Returns n_cl. */
+static int my_cluster_local(const int32_t *matrix, int n, const int *idx, int L, int ed, int *members, int *cl_off, int *harmful, int *long_bin)
+{
+    int *cnt = (int *)calloc((size_t)n, sizeof(int)), *keys_in = (int *)malloc((size_t)L * sizeof(int)), nk = 0;
+    uint64_t *sig = (uint64_t *)calloc((size_t)n, sizeof(uint64_t));
+    for (int i = 0; i < L; i++) {                                                       /* L179-L184 */
+        const int a = idx[i];
+        for (int j = 0; j < L; j++) if (ed_of(matrix[(size_t)a * n + idx[j]]) <= ed) { cnt[a]++; sig[a] += sig_mix(idx[j]); }
+        if (cnt[a] > 1) keys_in[nk++] = a;
+    }
+    if (nk == 0) { free(cnt); free(keys_in); free(sig); return 0; }
+    int *keys = (int *)malloc((size_t)nk * sizeof(int));
+    {                                                                                   /* Int2ObjectOpenHashMap: same layout and iteration as the set */
+        fuset m; fu_init(&m);
+        for (int i = 0; i < nk; i++) fu_add(&m, keys_in[i]);
+        fu_order(&m, keys); free(m.key);
+    }
+    int *chosen = (int *)malloc((size_t)nk * sizeof(int));
+    for (int i = 0; i < nk; i++) {                                                      /* L190-L196 */
+        const int c = keys[i];
+        int best = -1;
+        for (int j = 0; j < nk; j++) { const int e = keys[j]; if (ed_of(matrix[(size_t)e * n + c]) <= ed && (best < 0 || cnt[e] > cnt[best])) best = e; }
+        for (int j = 0; j < nk; j++) { const int e = keys[j]; if (ed_of(matrix[(size_t)e * n + c]) <= ed && cnt[e] == cnt[best] && sig[e] != sig[best]) *harmful = 1; }
+        chosen[i] = best;
+    }
+    /* L199: groups in first-seen order, members in key order */
+    int *gid = (int *)malloc((size_t)n * sizeof(int)), *first = (int *)malloc((size_t)nk * sizeof(int)), ng = 0;
+    for (int i = 0; i < n; i++) gid[i] = -1;
+    for (int i = 0; i < nk; i++) if (gid[chosen[i]] < 0) { gid[chosen[i]] = ng; first[ng++] = chosen[i]; }
+    int *gsz = (int *)calloc((size_t)ng + 1, sizeof(int));
+    for (int i = 0; i < nk; i++) gsz[gid[chosen[i]] + 1]++;
+    for (int g = 0; g < ng; g++) gsz[g + 1] += gsz[g];
+    int *gm = (int *)malloc((size_t)nk * sizeof(int)), *fill = (int *)malloc((size_t)ng * sizeof(int));
+    for (int g = 0; g < ng; g++) fill[g] = gsz[g];
+    for (int i = 0; i < nk; i++) gm[fill[gid[chosen[i]]]++] = keys[i];
+    int *corder = (int *)malloc((size_t)ng * sizeof(int));
+    chm_order(first, ng, corder, long_bin);                                             /* idMap.values() */
+    uint32_t *hs = (uint32_t *)malloc((size_t)ng * sizeof(uint32_t));
+    for (int t = 0; t < ng; t++) { const int g = gid[corder[t]]; uint32_t h = 0; for (int i = gsz[g]; i < gsz[g + 1]; i++) h += (uint32_t)gm[i]; hs[t] = h; }
+    int *perm = (int *)malloc((size_t)ng * sizeof(int));
+    jdk_order_by_hash(hs, ng, perm, long_bin);                                          /* L219: collect(toSet()) of the value sets */
+    int o = 0;
+    cl_off[0] = 0;
+    for (int t = 0; t < ng; t++) {
+        const int g = gid[corder[perm[t]]], k = gsz[g + 1] - gsz[g];
+        uint32_t *hh = (uint32_t *)malloc((size_t)k * sizeof(uint32_t)); int *pp = (int *)malloc((size_t)k * sizeof(int));
+        for (int i = 0; i < k; i++) hh[i] = (uint32_t)gm[gsz[g] + i];
+        jdk_order_by_hash(hh, k, pp, long_bin);                                         /* mapping(left, toSet()): HashSet<Integer> in key order */
+        for (int i = 0; i < k; i++) members[o++] = gm[gsz[g] + pp[i]];
+        cl_off[t + 1] = o;
+        free(hh); free(pp);
+    }
+    free(cnt); free(keys_in); free(sig); free(keys); free(chosen); free(gid); free(first); free(gsz); free(gm); free(fill); free(corder); free(hs); free(perm);
+    return ng;
+}
+
+void orc_umi_assign_myclust(const int32_t *matrix, int64_t n64, const orc_assign_params *P, int qv01, orc_assign_rec *rec)
+{
+    const int n = (int)n64, ed = P->ed_complete;                                        /* ctor L52 */
+    for (int i = 0; i < n; i++) { memset(&rec[i], 0, sizeof(rec[i])); rec[i].center = -1; rec[i].u2 = -1; rec[i].flags = ORC_UA_DEEP; }
+    if (n < 1) return;
+    int harmful = 0, long_bin = 0;
+    int *idx = (int *)malloc((size_t)n * sizeof(int)), *mem = (int *)malloc((size_t)n * sizeof(int)), *off = (int *)malloc((size_t)(n + 1) * sizeof(int));
+    int *tmp = (int *)malloc((size_t)(n + 1) * sizeof(int));
+    for (int i = 0; i < n; i++) idx[i] = i;
+    const int n_full = my_cluster_local(matrix, n, idx, n, ed, mem, off, &harmful, &long_bin);       /* L72-L73 */
+    mycluster *cl = (mycluster *)malloc((size_t)(2 * n + 1) * sizeof(mycluster));
+    int n_cl = 0;
+    if (n_full > 0) {
+        int maxdepth = 0;
+        for (int c = 0; c < n_full; c++) if (off[c + 1] - off[c] > maxdepth) maxdepth = off[c + 1] - off[c];       /* L77 */
+        uint8_t *clustered = (uint8_t *)calloc((size_t)n, 1), *victim = (uint8_t *)calloc((size_t)n, 1);
+        for (int c = 0; c < n_full; c++) {                                              /* L78-L88 */
+            const int k = off[c + 1] - off[c];
+            if (!((long)k * P->fold_depth > maxdepth)) {
+                for (int i = off[c]; i < off[c + 1]; i++) { rec[mem[i]].flags |= ORC_UA_SKIPPED; rec[mem[i]].cluster_size = (uint16_t)(k > 65535 ? 65535 : k); }
+                continue;
+            }
+            fu_init(&cl[n_cl].set);
+            for (int i = off[c]; i < off[c + 1]; i++) { fu_add(&cl[n_cl].set, mem[i]); clustered[mem[i]] = 1; }
+            cl[n_cl].center = my_center(matrix, n, &cl[n_cl].set, qv01, tmp);
+            n_cl++;
+        }
+        int nu = 0, n_removed = 0;
+        for (int d = 0; d < n; d++) if (!clustered[d]) idx[nu++] = d;                   /* L91 */
+        for (int c = 0; c < n_cl; c++) {                                                /* L102, L60-L65 */
+            const int k = fu_order(&cl[c].set, tmp);
+            int nr = 0;
+            for (int i = 0; i < k; i++) if (ed_of(matrix[(size_t)tmp[i] * n + cl[c].center]) > ed) { victim[tmp[i]] = 1; idx[nu++] = tmp[i]; nr++; }
+            if (nr) {
+                fu_remove_all(&cl[c].set, victim);
+                for (int i = 0; i < k; i++) victim[tmp[i]] = 0;
+                cl[c].center = my_center(matrix, n, &cl[c].set, qv01, tmp);
+                n_removed += nr;
+            }
+        }
+        if (n_removed > 0) {                                                            /* L106-L112 */
+            const int n_extra = my_cluster_local(matrix, n, idx, nu, ed, mem, off, &harmful, &long_bin);
+            for (int c = 0; c < n_extra; c++) {
+                if (off[c + 1] - off[c] <= 1) continue;                                 /* L109 */
+                fu_init(&cl[n_cl].set);
+                for (int i = off[c]; i < off[c + 1]; i++) fu_add(&cl[n_cl].set, mem[i]);
+                cl[n_cl].center = my_center(matrix, n, &cl[n_cl].set, qv01, tmp);
+                n_cl++;
+            }
+        }
+        uint8_t *inside = clustered;
+        for (int c = 0; c < n_cl; c++) {                                                /* L116-L164 */
+            const int k = fu_order(&cl[c].set, tmp), center = cl[c].center;
+            if (k <= 1) continue;                                                       /* L117 (userObject is absent: no pre-grouping) */
+            long sum = 0, cntv = 0;
+            for (int i = 0; i < k; i++) if (tmp[i] != center) { sum += pos1_offset(matrix[(size_t)center * n + tmp[i]]); cntv++; }
+            const int off_mean = (int)floor((double)sum / (double)cntv + 0.5);          /* L126-L130 */
+            int nf = 0;
+            for (int i = 0; i < k; i++) if (ed_of(matrix[(size_t)tmp[i] * n + center]) <= ed) nf++;                 /* L135 */
+            if (nf <= 1) continue;                                                      /* L139 */
+            memset(inside, 0, (size_t)n);
+            for (int i = 0; i < k; i++) inside[tmp[i]] = 1;
+            for (int i = 0; i < k; i++) {
+                const int x = tmp[i];
+                if (ed_of(matrix[(size_t)x * n + center]) > ed) continue;
+                orc_assign_rec *r = &rec[x];
+                if (r->flags & ORC_UA_SKIPPED) continue;                                /* ClusterOneBase.java:L122-L123 */
+                r->center = center; r->flags |= ORC_UA_ASSIGNED; r->cluster_size = (uint16_t)(k > 65535 ? 65535 : k); r->off_mean = (int8_t)off_mean;
+                r->u1 = (int8_t)ed_of(matrix[(size_t)center * n + x]);
+                r->pos2 = (int8_t)pos2_code(matrix[(size_t)center * n + x]);
+                if (n_cl > 1) {                                                         /* L161-L164 */
+                    int best = -1;
+                    for (int y = 0; y < n; y++) if (!inside[y]) { const int e = ed_of(matrix[(size_t)x * n + y]); if (best < 0 || e < best) best = e; }
+                    r->u2 = (int8_t)best;
+                }
+            }
+        }
+        free(clustered); free(victim);
+    }
+    for (int i = 0; i < n; i++) { rec[i].n_clusters = n_cl; if (harmful || long_bin) rec[i].flags |= ORC_UA_TIE_UNPIN; }
+    for (int c = 0; c < n_cl; c++) free(cl[c].set.key);
+    free(cl); free(idx); free(mem); free(off); free(tmp);
+}
+
 void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs,
                           const orc_assign_params *P, const uint8_t *job_qv01, orc_assign_rec *rec, int n_threads)
 {
@@ -320,7 +614,11 @@ void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, c
 #endif
     for (int64_t j = 0; j < n_jobs; j++) {
         const int64_t r0 = job_offsets[j], n = job_offsets[j + 1] - r0;
-        if (n > P->max_hier) {                                                           /* UmiClustering.java:L240: ClusterOne_MyClustering's job */
+        if (n > P->max_hier && P->deep) {                                                /* UmiClustering.java:L240: ClusterOne_MyClustering's job */
+            orc_umi_assign_myclust(matrices + out_offsets[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0);
+            continue;
+        }
+        if (n > P->max_hier) {
             for (int64_t i = 0; i < n; i++) { memset(&rec[r0 + i], 0, sizeof(rec[0])); rec[r0 + i].center = -1; rec[r0 + i].u2 = -1; rec[r0 + i].flags = ORC_UA_DEEP; }
             continue;
         }

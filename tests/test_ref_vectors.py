@@ -654,3 +654,23 @@ def test_gpu_cluster_one_hierarchical_matches_reference_bytecode(pkg, ctx):
             recs[j] = got[so[k]:so[k + 1]]
     stats = _check_hier(z, lambda j: recs[j])
     assert stats[2] >= 200 and stats[0] > 1500, stats
+
+
+# ------------------------------------------------------------------------------------------------------------- ClusterOne_MyClustering
+def test_cluster_one_myclustering_matches_reference_bytecode(orc):
+    """ClusterOne_MyClustering.call as a whole — clusterLocal on the full set, the depth rule, OneUmiCluster.setClusterCenter, the off-centre removal
+    (removeEntries -> the fastutil iterator's backward-shift deletion -> re-centring), the second clusterLocal over the unclustered reads and
+    setSamflagsAndStatsForClustered — run from the reference's own class files (oracle/make_ref_myclust.py, sequential streams) on 40 jobs of
+    20 ... 330 reads: the C oracle reproduces every value the bytecode wrote"""
+    z = np.load(os.path.join(GOLDEN, "ref_myclust.npz"))
+    off, oo = z["job_offsets"], z["out_offsets"]
+
+    def rec_of_job(j):
+        n = int(off[j + 1] - off[j])
+        p = z["params"][j]
+        rec = orc.umi_assign_batch(z["packed"][oo[j]:oo[j + 1]], np.array([0, n]), np.array([0, n * n]),
+                                   orc.AssignParams(int(p[0]), int(p[1]), int(p[2]), int(p[3]), 0, 1), z["qv01"][j:j + 1])
+        assert (rec["flags"] & 8).all()                       # ORC_UA_DEEP marks the records of ClusterOne_MyClustering
+        return rec
+    stats = _check_hier(z, rec_of_job)
+    assert stats[2] >= 40 and stats[0] > 4000 and stats[1] > 0, stats

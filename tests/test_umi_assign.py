@@ -71,6 +71,58 @@ def test_oracle_matches_second_restatement(orc):
     assert tot > 5000 and 0 < flagged < 400
 
 
+def umi_like_packed(rng, n):
+    """a deep job as real data shape it: a few molecules with many reads each, reads 0-2 errors from their molecule, a few chimeric bridges"""
+    k = int(rng.integers(3, 12))
+    lab = rng.integers(0, k, n)
+    err = rng.integers(0, 3, n)
+    e = np.where(lab[:, None] == lab[None, :], np.minimum(err[:, None] + err[None, :], 5), np.minimum(3 + rng.integers(0, 3, (n, n)), 5))
+    e = np.where(rng.random((n, n)) < 0.01, rng.integers(1, 3, (n, n)), e)
+    e = np.triu(e, 1)
+    e = e + e.T
+    p1, p2 = rng.integers(0, 3, (n, n)), rng.integers(0, 3, (n, n))
+    up = e | (0x08000000 << p1) | (0x01000000 << p2)
+    lo = e | (0x08000000 << p2.T) | (0x01000000 << p1.T)
+    packed = np.where(np.arange(n)[:, None] <= np.arange(n)[None, :], up, lo)
+    np.fill_diagonal(packed, 0x10000000 | 0x02000000)
+    return packed.astype(np.int32)
+
+
+def test_myclustering_oracle_matches_second_restatement(orc):
+    """ClusterOne_MyClustering.call: the C oracle against the independent Python restatement (oracle/pyref.assign_myclust) on random and
+    UMI-shaped matrices of 2 ... 700 reads; the removal path (OneUmiCluster.removeEntries) and the second clusterLocal round must be exercised"""
+    rng = np.random.default_rng(77)
+    calls = [0]
+    orig = pyref.FuIntSet.remove_all
+
+    def counted(self, victims):
+        calls[0] += 1
+        return orig(self, victims)
+    pyref.FuIntSet.remove_all = counted
+    try:
+        tot = assigned = 0
+        for t in range(36):
+            n = int(rng.integers(2, 330)) if t % 9 else int(rng.integers(400, 700))
+            packed = random_packed(rng, n, t % 3) if t % 2 else umi_like_packed(rng, n)
+            qv, fold = int(rng.integers(0, 2)), int(rng.choice([50, 50, 3]))
+            rec = orc.umi_assign_batch(packed.ravel(), np.array([0, n]), np.array([0, n * n]), orc.AssignParams(fold_depth=fold, max_hier=0, deep=1),
+                                       np.array([qv], dtype=np.uint8))
+            pr = pyref.assign_myclust(packed.tolist(), 2, fold, bool(qv))
+            for i in range(n):
+                a, b = rec[i], pr[i]
+                got = (bool(a["flags"] & 1), bool(a["flags"] & 2), bool(a["flags"] & 4), int(a["cluster_size"]), int(a["n_clusters"])) + \
+                      ((int(a["center"]), int(a["u1"]), int(a["u2"]), int(a["pos2"]), int(a["off_mean"])) if a["flags"] & 1 else ())
+                exp = (b["assigned"], b["skipped"], b["tie_unpin"], b["cluster_size"], b["n_clusters"]) + \
+                      ((b["center"], b["u1"], b["u2"], b["pos2"], b["off_mean"]) if b["assigned"] else ())
+                assert got == exp, (t, n, i, got, exp)
+            assert (rec["flags"] & 8).all()
+            tot += n
+            assigned += int((rec["flags"] & 1).sum())
+    finally:
+        pyref.FuIntSet.remove_all = orig
+    assert tot > 5000 and assigned > 3000 and calls[0] > 50, (tot, assigned, calls)
+
+
 def _lingpipe_test_distance():
     """SingleLinkClustererTest$TestDistance (the fixture both of LingPipe's clusterer tests use): A..E"""
     d = np.zeros((5, 5), dtype=np.int64)

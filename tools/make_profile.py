@@ -19,6 +19,13 @@ RUNS = [
     ("bc_assign_kernel<1>", "bc_assign_kernel", 4_000_000, ["tools/prof_bc.py", "737280", "737", "1", "4000000", "1"], "4 M reads, 737 K list, ED 1"),
     ("umi_pairs_kernel", "umi_pairs_kernel", 4_000_000, ["tools/perf_assign.py", "4000000", "4", "2000", "1"], "4 M reads in jobs of mean 4"),
     ("umi_assign_kernel", "umi_assign_kernel", 4_000_000, ["tools/perf_assign.py", "4000000", "4", "2000", "1"], "4 M reads in jobs of mean 4"),
+    # the side benches: units = what their own JSON line reports (roofline.units_per_launch)
+    ("umi_pairs_kernel@umi_cluster_bench", "umi_pairs_kernel", None, ["tools/bench_umi_cluster.py", "--steps", "1", "--warmup", "1", "--cpu-jobs", "1000"],
+     "tools/bench_umi_cluster.py defaults: 10 M jobs of mean 4 + one 20 000-read job"),
+    ("guided_match_kernel<umi,2>", "guided_match_kernel", None, ["tools/bench_guided.py", "--flavour", "umi", "--ed", "2", "--steps", "1", "--warmup", "1", "--cpu-sample", "64"],
+     "tools/bench_guided.py defaults, UMI flavour, ED 2"),
+    ("guided_match_kernel<bc,2>", "guided_match_kernel", None, ["tools/bench_guided.py", "--flavour", "bc", "--ed", "2", "--steps", "1", "--warmup", "1", "--cpu-sample", "64"],
+     "tools/bench_guided.py defaults, BC flavour, ED 2"),
 ]
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "nsecond": 1e-6, "usecond": 1e-3,
         "msecond": 1.0, "second": 1e3}
@@ -27,6 +34,13 @@ for key, rx, units, cmd, what in RUNS:
     r = subprocess.run(["ncu", "--metrics", METRICS, "--clock-control", "none", "-k", "regex:" + rx, "--csv", sys.executable] + cmd,
                        capture_output=True, text=True, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if l.startswith('"')]
+    if units is None:
+        for l in r.stdout.splitlines():
+            if l.startswith("{") and "units_per_launch" in l:
+                units = int(json.loads(l)["roofline"]["units_per_launch"])
+        if units is None:
+            print("no JSON line from", cmd, r.stdout[-300:], r.stderr[-300:], file=sys.stderr)
+            continue
     rows = list(csv.DictReader(io.StringIO("\n".join(lines))))
     per = {}
     for row in rows:                                       # long format: one row per (launch id, metric)
