@@ -243,14 +243,25 @@ void slr_umi_session_destroy(slr_umi_session *s);
 #define SLR_UA_TIE_UNPIN 4u   /* the reference's own result for this job depends on JVM identity hash codes (LingPipe's ObjectToSet keeps its
                                  PairScores in a HashSet without hashCode()): equal-cost pairs created by one merge have no defined queue order
                                  there.  The records follow creation order; a caller that wants its JVM's choice re-runs exactly these jobs. */
-#define SLR_UA_DEEP      8u   /* job of more than max_hier reads: ClusterOne_MyClustering's (slr_umi_cluster / the session API), untouched here */
+#define SLR_UA_DEEP      8u   /* job of more than max_hier reads: ClusterOne_MyClustering's.  With params.deep (the default) its records are
+                                 filled by the large-job path below and carry this bit too; with deep = 0 (or no arena, slr_umi_assign_dev)
+                                 the job is only flagged and left to slr_umi_cluster / the session API */
 typedef struct slr_umi_assign_params {
     int32_t ed_complete;      /* umi_completelinkclusteringED (config.xml:270), also the neighbour threshold */
     int32_t ed_single;        /* umi_singlelinkclusteringED (config.xml:272) */
     int32_t single_threshold; /* complexity_threshold_for_switch_to_single_link_clustering (config.xml:278: 3000, i.e. never for <= 100 reads) */
     int32_t fold_depth;       /* foldDepthBelowMaxDiscardForClustering (UMIparameters.java:L118: 50) */
     int32_t max_hier;         /* jobs up to this size are ClusterOneHierarchical's (UmiClustering.java:L240: 100; at most 100 here) */
-} slr_umi_assign_params;      /* NULL = { 2, 1, 3000, 50, 100 } */
+    int32_t deep;             /* 1: jobs above max_hier run ClusterOne_MyClustering.call on the GPU (see below); 0: they are only flagged */
+} slr_umi_assign_params;      /* NULL = { 2, 1, 3000, 50, 100, 1 } */
+/* Jobs above max_hier: ClusterOne_MyClustering.call (F!com/rw/umifinder/analyzers/clustering/ClusterOne_MyClustering.class,
+ * ClusterOne_MyClustering.java:L59-L166) as a whole — clusterLocal over all reads (L175-L219), the depth rule (L77-L84), setClusterCenter, the
+ * off-centre removal (L60-L65, OneUmiCluster.removeEntries L114-L119), clusterLocal over the unclustered reads (L104-L112) and the per-read
+ * values (L116-L164).  Every stream of that class is parallel above 30 reads, so the reference's own result depends on thread timing wherever
+ * an iteration order decides; the records have the SEQUENTIAL semantics (a JVM with one worker thread), with the orders of fastutil's
+ * Int2ObjectOpenHashMap / IntOpenHashSet (incl. iterator-driven removeAll), java.util.HashSet and ConcurrentHashMap reproduced.  SLR_UA_TIE_UNPIN
+ * on such a job = a read could choose between largest neighbour sets that are not the same set (Stream.max keeps the first in map order),
+ * or a hash bin reached the JDK's treeify threshold (not modelled). */
 typedef struct slr_umi_assign_rec {
     int32_t  center;              /* job-local index of OneUmiCluster.getCenter() of the read's cluster (U8 comes from that read); -1 = none */
     int8_t   u1;                  /* UMI_ED (U1): distanceNonReducedSet(center, read) */
@@ -268,11 +279,18 @@ typedef struct slr_umi_assign_rec {
 int  slr_umi_assign(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
                     const slr_umi_assign_params *params, const uint8_t *job_qv01, int32_t *out, const int64_t *out_offsets,
                     slr_umi_assign_rec *rec);
-/* the same on matrices already on the device (as slr_umi_dist_dev left them); d_scratch: slr_umi_assign_scratch_bytes(n_jobs) bytes */
+/* the same on matrices already on the device (as slr_umi_dist_dev left them); d_scratch: slr_umi_assign_scratch_bytes(n_jobs) bytes.
+ * slr_umi_assign_dev has no room for the working arrays of the jobs above max_hier: they are only flagged SLR_UA_DEEP.  slr_umi_assign_dev2 takes
+ * scratch_bytes = slr_umi_assign_scratch_bytes(n_jobs) + the sum of slr_umi_assign_deep_job_bytes(n) over the jobs above max_hier (any upper
+ * bound will do; a deep job that does not fit is left flagged, n_clusters 0, never half-written). */
 int64_t slr_umi_assign_scratch_bytes(int64_t n_jobs);
+int64_t slr_umi_assign_deep_job_bytes(int64_t n_reads_of_job);
 int  slr_umi_assign_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
                         int64_t n_reads, const slr_umi_assign_params *params, const uint8_t *d_job_qv01, void *d_scratch,
                         slr_umi_assign_rec *d_rec, void *stream);
+int  slr_umi_assign_dev2(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
+                         int64_t n_reads, const slr_umi_assign_params *params, const uint8_t *d_job_qv01, void *d_scratch, int64_t scratch_bytes,
+                         slr_umi_assign_rec *d_rec, void *stream);
 /* on the resident matrices of a session (see below) */
 struct slr_umi_session;
 int  slr_umi_session_assign(struct slr_umi_session *s, const slr_umi_assign_params *params, const uint8_t *job_qv01, slr_umi_assign_rec *rec);

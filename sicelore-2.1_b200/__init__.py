@@ -45,7 +45,7 @@ assert GUIDED_HIT.itemsize == 16
 
 EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_create", "slr_bc_table_destroy",
            "slr_bc_table_size", "slr_bc_assign", "slr_bc_assign_dev", "slr_bc_counts_read", "slr_bc_counts_reset",
-           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_umi_assign", "slr_umi_assign_dev", "slr_umi_assign_scratch_bytes", "slr_umi_session_assign", "slr_umi_session_create", "slr_umi_session_cluster",
+           "slr_bc_counts_device", "slr_bc_exact", "slr_bc_exact_dev", "slr_bc_collide", "slr_bc_collide_dev", "slr_umi_dist", "slr_umi_dist_dev", "slr_umi_cluster", "slr_umi_cluster_dev", "slr_umi_assign", "slr_umi_assign_dev", "slr_umi_assign_dev2", "slr_umi_assign_scratch_bytes", "slr_umi_assign_deep_job_bytes", "slr_umi_session_assign", "slr_umi_session_create", "slr_umi_session_cluster",
            "slr_umi_session_matrices", "slr_umi_session_cells", "slr_umi_session_reads", "slr_umi_session_jobs", "slr_umi_session_destroy", "slr_guided_sets_create", "slr_guided_sets_destroy", "slr_guided_match", "slr_guided_match_dev",
            "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count",
            "slr_multi_create", "slr_multi_destroy", "slr_multi_n_devices", "slr_multi_ctx", "slr_multi_peer_access", "slr_multi_bc_table_create",
@@ -77,7 +77,7 @@ def build(force=False, verbose=False):
     """Compile libsicelore_gpu.so (nvcc, sm_100a only) and libslr_synth.so (g++) in-tree."""
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
-    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu",
+    cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu", "umi_assign_deep.cu",
                                            "guided_match.cu", "slr_multi.cu")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -129,8 +129,11 @@ def gpu_lib():
         L.slr_umi_cluster_dev.argtypes = [vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
         L.slr_umi_assign.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp]
         L.slr_umi_assign_dev.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp]
+        L.slr_umi_assign_dev2.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, vp, vp]
         L.slr_umi_assign_scratch_bytes.argtypes = [i64]
         L.slr_umi_assign_scratch_bytes.restype = i64
+        L.slr_umi_assign_deep_job_bytes.argtypes = [i64]
+        L.slr_umi_assign_deep_job_bytes.restype = i64
         L.slr_umi_session_assign.argtypes = [vp, vp, vp, vp]
         L.slr_umi_session_create.argtypes = [vp, vp, i32, i32, vp, i64, C.POINTER(vp)]
         L.slr_umi_session_cluster.argtypes = [vp, i32, vp, vp, vp]
@@ -698,12 +701,12 @@ UA_ASSIGNED, UA_SKIPPED, UA_TIE_UNPIN, UA_DEEP = 1, 2, 4, 8
 class UmiAssignParams(C.Structure):
     """The clustering knobs ClusterOneHierarchical reads (config.xml:270-278, UMIparameters.java:L96-L118, UmiClustering.java:L240)."""
     _fields_ = [("ed_complete", C.c_int32), ("ed_single", C.c_int32), ("single_threshold", C.c_int32), ("fold_depth", C.c_int32),
-                ("max_hier", C.c_int32)]
+                ("max_hier", C.c_int32), ("deep", C.c_int32)]
 
     def __init__(self, umi_completelinkclusteringED=2, umi_singlelinkclusteringED=1, complexity_threshold_for_switch_to_single_link_clustering=3000,
-                 foldDepthBelowMaxDiscardForClustering=50, max_hier=100):
+                 foldDepthBelowMaxDiscardForClustering=50, max_hier=100, deep=1):
         super().__init__(umi_completelinkclusteringED, umi_singlelinkclusteringED, complexity_threshold_for_switch_to_single_link_clustering,
-                         foldDepthBelowMaxDiscardForClustering, max_hier)
+                         foldDepthBelowMaxDiscardForClustering, max_hier, deep)
 
 
 def cluster_one_hierarchical(ctx, umis, job_offsets, umi_len=12, params=None, job_qv01=None, want_matrices=False):

@@ -510,7 +510,7 @@ struct AssignArgs {                            // slr_umi_assign: the same ride
     const uint8_t *job_qv01 = nullptr;
     slr_umi_assign_rec *rec = nullptr;
 };
-const slr_umi_assign_params ASSIGN_DEFAULTS = {2, 1, 3000, 50, 100};   // config.xml:270-278, UMIparameters.java:L118, UmiClustering.java:L240
+const slr_umi_assign_params ASSIGN_DEFAULTS = {2, 1, 3000, 50, 100, 1};   // config.xml:270-278, UMIparameters.java:L118, UmiClustering.java:L240
 
 int check_assign_params(const slr_umi_assign_params *p, slr_umi_assign_params &out)
 {
@@ -521,7 +521,19 @@ int check_assign_params(const slr_umi_assign_params *p, slr_umi_assign_params &o
     if (out.max_hier < 0 || out.max_hier > 100)
         return fail(SLR_E_UNSUPPORTED, "slr_umi_assign: max_hier %d (ClusterOneHierarchical takes jobs of at most 100 reads)", out.max_hier);
     if (out.single_threshold < 0) return fail(SLR_E_INVALID, "slr_umi_assign: negative single-link threshold");
+    if (out.deep != 0 && out.deep != 1) return fail(SLR_E_INVALID, "slr_umi_assign: deep must be 0 or 1");
     return SLR_OK;
+}
+// working arrays of the jobs ClusterOne_MyClustering gets (umi_assign_deep.cu), in 32-bit words
+long long deep_words_of(const int64_t *job_offsets, int64_t j0, int64_t j1, const slr_umi_assign_params &P)
+{
+    if (!P.deep) return 0;
+    long long w = 0;
+    for (int64_t k = j0; k < j1; k++) {
+        const int64_t n = job_offsets[k + 1] - job_offsets[k];
+        if (n > P.max_hier) w += slr_umi_assign_deep_words(n);
+    }
+    return w;
 }
 }  // namespace
 
@@ -590,13 +602,15 @@ static int umi_dist_ranges(slr_ctx *ctx, const uint8_t *umis, int stride, int um
             }
             if (as) {
                 const size_t o_qv = (size_t)nr * sizeof(slr_umi_assign_rec), o_list = (o_qv + (size_t)nj_range + 15) & ~(size_t)15;
-                if ((rc = s->uas[b].reserve(o_list + slr_umi_assign_scratch(nj_range)))) return rc;
+                const long long dw = deep_words_of(job_offsets, j, j1, as->P);
+                const size_t scr_bytes = slr_umi_assign_scratch(nj_range, dw);
+                if ((rc = s->uas[b].reserve(o_list + scr_bytes))) return rc;
                 char *base = (char *)s->uas[b].p;
                 if (as->job_qv01) CUDA_TRY(cudaMemcpyAsync(base + o_qv, as->job_qv01 + j, (size_t)nj_range, cudaMemcpyHostToDevice, st));
                 CUDA_TRY(slr_launch_umi_assign((const int32_t *)s->uout[b].p, (const long long *)s->joff[b].p, (const long long *)s->ooff[b].p,
                                                nj_range, nr, as->P, as->job_qv01 ? (const uint8_t *)(base + o_qv) : nullptr,
-                                               slr_umi_scratch_rowjob(s->uscr[b].p, nr), (slr_umi_assign_rec *)base, base + o_list, st));
-                g_launches += SLR_UMI_ASSIGN_LAUNCHES;
+                                               slr_umi_scratch_rowjob(s->uscr[b].p, nr), (slr_umi_assign_rec *)base, base + o_list, scr_bytes, st));
+                g_launches += SLR_UMI_ASSIGN_LAUNCHES + (dw > 0 ? SLR_UMI_ASSIGN_DEEP_LAUNCHES : 0);
                 CUDA_TRY(cudaMemcpyAsync(as->rec + r0, base, (size_t)nr * sizeof(slr_umi_assign_rec), cudaMemcpyDeviceToHost, st));
             }
             if (out && packed) {                                           // the usual layout: the range is one contiguous piece of `out`
@@ -673,11 +687,20 @@ int slr_umi_assign(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, c
     return umi_dist_ranges(ctx, umis, stride, umi_len, job_offsets, n_jobs, out, out_offsets, nullptr, &as);
 }
 
-int64_t slr_umi_assign_scratch_bytes(int64_t n_jobs) { return (int64_t)slr_umi_assign_scratch(n_jobs > 0 ? n_jobs : 0); }
+int64_t slr_umi_assign_scratch_bytes(int64_t n_jobs) { return (int64_t)slr_umi_assign_scratch(n_jobs > 0 ? n_jobs : 0, 0); }
+int64_t slr_umi_assign_deep_job_bytes(int64_t n_reads_of_job) { return n_reads_of_job > 0 ? 4 * (int64_t)slr_umi_assign_deep_words(n_reads_of_job) : 0; }
 
 int slr_umi_assign_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
                        int64_t n_reads, const slr_umi_assign_params *params, const uint8_t *d_job_qv01, void *d_scratch,
                        slr_umi_assign_rec *d_rec, void *stream)
+{
+    return slr_umi_assign_dev2(ctx, d_matrices, d_job_offsets, d_out_offsets, n_jobs, n_reads, params, d_job_qv01, d_scratch,
+                               slr_umi_assign_scratch_bytes(n_jobs), d_rec, stream);
+}
+
+int slr_umi_assign_dev2(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,
+                        int64_t n_reads, const slr_umi_assign_params *params, const uint8_t *d_job_qv01, void *d_scratch, int64_t scratch_bytes,
+                        slr_umi_assign_rec *d_rec, void *stream)
 {
     if (!ctx) return fail(SLR_E_INVALID, "slr_umi_assign_dev: ctx is NULL");
     slr_umi_assign_params P;
@@ -687,9 +710,13 @@ int slr_umi_assign_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d
     if (n_jobs == 0 || n_reads == 0) return SLR_OK;
     if (!d_matrices || !d_job_offsets || !d_out_offsets || !d_scratch || !d_rec) return fail(SLR_E_INVALID, "slr_umi_assign_dev: NULL buffer");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    if (scratch_bytes < slr_umi_assign_scratch_bytes(n_jobs))
+        return fail(SLR_E_INVALID, "slr_umi_assign_dev: %lld bytes of scratch, %lld needed for the job lists alone", (long long)scratch_bytes,
+                    (long long)slr_umi_assign_scratch_bytes(n_jobs));
+    const bool deep = P.deep && scratch_bytes > slr_umi_assign_scratch_bytes(n_jobs);
     CUDA_TRY(slr_launch_umi_assign(d_matrices, (const long long *)d_job_offsets, (const long long *)d_out_offsets, n_jobs, n_reads, P, d_job_qv01,
-                                   nullptr, d_rec, d_scratch, (cudaStream_t)stream));
-    g_launches += SLR_UMI_ASSIGN_LAUNCHES;
+                                   nullptr, d_rec, d_scratch, (size_t)scratch_bytes, (cudaStream_t)stream));
+    g_launches += SLR_UMI_ASSIGN_LAUNCHES + (deep ? SLR_UMI_ASSIGN_DEEP_LAUNCHES : 0);
     return SLR_OK;
 }
 
@@ -716,6 +743,7 @@ int slr_umi_cluster_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *
 struct slr_umi_session {
     slr_ctx *ctx = nullptr;
     int64_t n_jobs = 0, n_reads = 0, cells = 0;
+    std::vector<int64_t> hoff;                 // host copy of the job offsets (sizes the deep arena of slr_umi_session_assign)
     DevBuf umis, jraw, jtmp, joff, ooff, mat, scr, counts, rec, rank, member, arec, aqv, ascr;
     void release()
     {
@@ -754,6 +782,7 @@ int slr_umi_session_create(slr_ctx *ctx, const uint8_t *umis, int stride, int um
     }
     if (!S) S.reset(new slr_umi_session());
     S->ctx = ctx; S->n_jobs = n_jobs; S->cells = 0;
+    S->hoff.assign(job_offsets, job_offsets + (n_jobs > 0 ? n_jobs + 1 : 0));
     const int64_t r0 = n_jobs > 0 ? job_offsets[0] : 0;
     S->n_reads = n_jobs > 0 ? job_offsets[n_jobs] - r0 : 0;
     if (S->n_reads > 0) {
@@ -821,14 +850,15 @@ int slr_umi_session_assign(slr_umi_session *S, const slr_umi_assign_params *para
     std::lock_guard<std::mutex> lock(sl->mtx);
     cudaStream_t st = sl->stream[0];
     const size_t m = (size_t)S->n_reads;
-    if ((rc = S->arec.reserve(m * sizeof(slr_umi_assign_rec))) || (rc = S->aqv.reserve((size_t)S->n_jobs + 1)) ||
-        (rc = S->ascr.reserve(slr_umi_assign_scratch(S->n_jobs))))
+    const long long dw = deep_words_of(S->hoff.data(), 0, S->n_jobs, P);
+    const size_t scr_bytes = slr_umi_assign_scratch(S->n_jobs, dw);
+    if ((rc = S->arec.reserve(m * sizeof(slr_umi_assign_rec))) || (rc = S->aqv.reserve((size_t)S->n_jobs + 1)) || (rc = S->ascr.reserve(scr_bytes)))
         return rc;
     if (job_qv01) CUDA_TRY(cudaMemcpyAsync(S->aqv.p, job_qv01, (size_t)S->n_jobs, cudaMemcpyHostToDevice, st));
     CUDA_TRY(slr_launch_umi_assign((const int32_t *)S->mat.p, (const long long *)S->joff.p, (const long long *)S->ooff.p, S->n_jobs, S->n_reads, P,
                                    job_qv01 ? (const uint8_t *)S->aqv.p : nullptr, slr_umi_scratch_rowjob(S->scr.p, S->n_reads),
-                                   (slr_umi_assign_rec *)S->arec.p, S->ascr.p, st));
-    g_launches += SLR_UMI_ASSIGN_LAUNCHES;
+                                   (slr_umi_assign_rec *)S->arec.p, S->ascr.p, scr_bytes, st));
+    g_launches += SLR_UMI_ASSIGN_LAUNCHES + (dw > 0 ? SLR_UMI_ASSIGN_DEEP_LAUNCHES : 0);
     CUDA_TRY(cudaMemcpyAsync(rec, S->arec.p, m * sizeof(slr_umi_assign_rec), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return SLR_OK;

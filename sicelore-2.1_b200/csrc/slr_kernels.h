@@ -27,12 +27,23 @@ cudaError_t slr_launch_umi_cluster(const int32_t *d_mat, const long long *d_job_
                                    int32_t *d_counts, slr_umi_cluster_rec *d_out, unsigned long long *d_range, cudaStream_t stream);
 
 // ClusterOneHierarchical.call for every job of at most P.max_hier reads + the per-read assignment values (umi_assign.cu); three kernels.
-// d_scratch: slr_umi_assign_scratch(n_jobs) bytes (job lists); d_rowjob as for slr_launch_umi_cluster (NULL: binary search)
+// d_scratch: slr_umi_assign_scratch(n_jobs, deep_words) bytes — job lists + the working arrays of the jobs above max_hier (deep_words =
+// sum of slr_umi_assign_deep_words(n) over those jobs; 0 or P.deep == 0: they are only flagged SLR_UA_DEEP);
+// d_rowjob as for slr_launch_umi_cluster (NULL: binary search)
 constexpr int SLR_UMI_ASSIGN_LAUNCHES = 3;
-size_t slr_umi_assign_scratch(long long n_jobs);
+constexpr int SLR_UMI_ASSIGN_DEEP_LAUNCHES = 2;
+constexpr int SLR_UA_DEEP_SMALL = 1024;        // deep jobs up to this size run on one CTA, larger ones on a cluster of 8
+size_t slr_umi_assign_scratch(long long n_jobs, long long deep_words);
+// 32-bit words of working arrays umi_assign_deep.cu needs for a job of n reads (kept in step with carve() there)
+SLR_HD long long slr_umi_assign_deep_words(long long n) { return (64 + 52 * (n + 2) + 2 * (3 * n + 64) + 2 * (4 * n + 64) + 1) & ~1ll; }
 cudaError_t slr_launch_umi_assign(const int32_t *d_mat, const long long *d_job_offsets, const long long *d_out_offsets, long long n_jobs,
                                   long long n_reads, const slr_umi_assign_params &P, const uint8_t *d_job_qv01, const int32_t *d_rowjob,
-                                  slr_umi_assign_rec *d_rec, void *d_scratch, cudaStream_t stream);
+                                  slr_umi_assign_rec *d_rec, void *d_scratch, size_t scratch_bytes, cudaStream_t stream);
+cudaError_t slr_launch_umi_assign_deep(const int32_t *d_mat, const long long *d_job_offsets, const long long *d_out_offsets,
+                                       const slr_umi_assign_params &P, const uint8_t *d_job_qv01, slr_umi_assign_rec *d_rec,
+                                       const int32_t *d_list_small, const long long *d_off_small, const unsigned int *d_count_small,
+                                       const int32_t *d_list_big, const long long *d_off_big, const unsigned int *d_count_big, int *d_words,
+                                       long long max_jobs, cudaStream_t stream);
 
 // a range of the caller's CSR job offsets (d_raw: n_jobs + 1 entries) rebased on the device: d_joff = raw - r0, d_ooff = exclusive prefix
 // sum of the squared job sizes (both n_jobs + 1 entries); d_tmp: slr_umi_rebase_tmp_bytes(n_jobs); three kernels

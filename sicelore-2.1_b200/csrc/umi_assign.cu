@@ -402,10 +402,13 @@ __device__ void ua_job(UaShared<MAXN> &S, const int32_t *__restrict__ mat, int n
 
 // ---- kernels ---------------------------------------------------------------------------------------------------------------------------
 // records of every read: default values; reads of jobs above max_hier are flagged SLR_UA_DEEP.  The first read of a job files the job in
-// the list of its class: lists[0 .. n_jobs) small jobs (2 ... 32 reads), lists[n_jobs .. 2 n_jobs) large jobs (33 ... max_hier).
+// the list of its class: lists[0 .. n_jobs) small jobs (2 ... 32 reads), lists[n_jobs .. 2 n_jobs) large jobs (33 ... max_hier),
+// lists[2 n_jobs .. 3 n_jobs) / [3 n_jobs .. 4 n_jobs) deep jobs of up to / above SLR_UA_DEEP_SMALL reads (umi_assign_deep.cu) together with the
+// offset of their working arrays in the deep arena — a deep job that does not fit the arena stays flagged SLR_UA_DEEP only.
 __global__ void __launch_bounds__(256) umi_assign_init(const long long *__restrict__ joff, long long n_jobs, long long n_reads,
                                                         const int32_t *__restrict__ rowjob, int max_hier, slr_umi_assign_rec *__restrict__ rec,
-                                                        int32_t *__restrict__ lists, unsigned int *__restrict__ counts)
+                                                        int32_t *__restrict__ lists, unsigned int *__restrict__ counts,
+                                                        long long *__restrict__ deep_off, long long deep_cap_words)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
@@ -420,8 +423,19 @@ __global__ void __launch_bounds__(256) umi_assign_init(const long long *__restri
         d.center = -1; d.u1 = 0; d.u2 = -1; d.pos2 = 0; d.offset_center_mean = 0; d.flags = 0; d.cluster_size = 0; d.n_clusters = 0;
         if (j >= 0) {
             const long long r0 = joff[j], n = joff[j + 1] - r0;
-            if (n > max_hier) d.flags = SLR_UA_DEEP;
-            else if (r == r0 && n >= 2) {
+            if (n > max_hier) {
+                d.flags = SLR_UA_DEEP;
+                if (r == r0 && deep_cap_words > 0) {
+                    const long long need = slr_umi_assign_deep_words(n);
+                    const long long off = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(counts + 4), (unsigned long long)need);
+                    if (off + need <= deep_cap_words) {
+                        const int cls = n <= SLR_UA_DEEP_SMALL ? 2 : 3;
+                        const unsigned int k = atomicAdd(&counts[cls], 1u);
+                        lists[(long long)cls * n_jobs + k] = (int32_t)j;
+                        deep_off[(long long)(cls - 2) * n_jobs + k] = off;
+                    }
+                }
+            } else if (r == r0 && n >= 2) {
                 const int cls = n <= 32 ? 0 : 1;
                 lists[(long long)cls * n_jobs + atomicAdd(&counts[cls], 1u)] = (int32_t)j;
             }
@@ -450,25 +464,33 @@ __global__ void __launch_bounds__(WARPS * 32) umi_assign_kernel(const int32_t *_
 
 }  // namespace
 
-size_t slr_umi_assign_scratch(long long n_jobs) { return (size_t)(2 * n_jobs + 4) * 4 + 16; }
+// scratch: counts (8 words: 4 list lengths, the 64-bit arena cursor) | 4 job lists | 2 lists of arena offsets | the deep arena
+size_t slr_umi_assign_scratch(long long n_jobs, long long deep_words)
+{
+    return 32 + (size_t)(4 * n_jobs + 4) * 4 + (size_t)(2 * n_jobs + 2) * 8 + (size_t)(deep_words > 0 ? deep_words : 0) * 4 + 16;
+}
 
 cudaError_t slr_launch_umi_assign(const int32_t *d_mat, const long long *d_job_offsets, const long long *d_out_offsets, long long n_jobs,
                                   long long n_reads, const slr_umi_assign_params &P, const uint8_t *d_job_qv01, const int32_t *d_rowjob,
-                                  slr_umi_assign_rec *d_rec, void *d_scratch, cudaStream_t stream)
+                                  slr_umi_assign_rec *d_rec, void *d_scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     if (n_reads <= 0 || n_jobs <= 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (scratch_bytes < slr_umi_assign_scratch(n_jobs, 0)) return cudaErrorInvalidValue;
     unsigned int *counts = reinterpret_cast<unsigned int *>(d_scratch);
-    int32_t *lists = reinterpret_cast<int32_t *>(counts + 4);
-    cudaError_t e = cudaMemsetAsync(counts, 0, 16, stream);
+    int32_t *lists = reinterpret_cast<int32_t *>(counts + 8);
+    long long *deep_off = reinterpret_cast<long long *>(lists + 4 * n_jobs + 4);
+    int *arena = reinterpret_cast<int *>(deep_off + 2 * n_jobs + 2);
+    const long long deep_cap = P.deep ? (long long)((scratch_bytes - slr_umi_assign_scratch(n_jobs, 0)) / 4) & ~1ll : 0;
+    cudaError_t e = cudaMemsetAsync(counts, 0, 32, stream);
     if (e != cudaSuccess) return e;
     long long g0 = (n_reads + 255) / 256;
     if (g0 > (long long)sms * 16) g0 = (long long)sms * 16;
     slr_umi_assign_params Q = P;
     if (Q.max_hier > 100) Q.max_hier = 100;
-    umi_assign_init<<<(unsigned)g0, 256, 0, stream>>>(d_job_offsets, n_jobs, n_reads, d_rowjob, Q.max_hier, d_rec, lists, counts);
+    umi_assign_init<<<(unsigned)g0, 256, 0, stream>>>(d_job_offsets, n_jobs, n_reads, d_rowjob, Q.max_hier, d_rec, lists, counts, deep_off, deep_cap);
     // persistent grids, one wave; warps without a job return at once
     long long gs = (n_jobs + 7) / 8;
     if (gs > (long long)sms * 6) gs = (long long)sms * 6;
@@ -476,5 +498,8 @@ cudaError_t slr_launch_umi_assign(const int32_t *d_mat, const long long *d_job_o
     long long gl = n_jobs < (long long)sms * 4 ? n_jobs : (long long)sms * 4;
     umi_assign_kernel<100, 1><<<(unsigned)gl, 32, 0, stream>>>(d_mat, d_job_offsets, d_out_offsets, Q, d_job_qv01, d_rec, lists + n_jobs,
                                                              counts + 1);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess || deep_cap <= 0) return e;
+    return slr_launch_umi_assign_deep(d_mat, d_job_offsets, d_out_offsets, Q, d_job_qv01, d_rec, lists + 2 * n_jobs, deep_off, counts + 2,
+                                      lists + 3 * n_jobs, deep_off + n_jobs, counts + 3, arena, n_jobs, stream);
 }

@@ -674,3 +674,34 @@ def test_cluster_one_myclustering_matches_reference_bytecode(orc):
         return rec
     stats = _check_hier(z, rec_of_job)
     assert stats[2] >= 40 and stats[0] > 4000 and stats[1] > 0, stats
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_one_myclustering_matches_reference_bytecode(pkg, ctx):
+    """the large-job kernels (umi_assign_deep.cu) through slr_umi_assign_dev2 against the same vectors (max_hier = 0 sends every job there)"""
+    import ctypes as C
+    import torch
+    z = np.load(os.path.join(GOLDEN, "ref_myclust.npz"))
+    off, oo = z["job_offsets"], z["out_offsets"]
+    L = pkg.gpu_lib()
+    recs = {}
+    for prm in sorted({tuple(int(x) for x in p) for p in z["params"]}):
+        js = [j for j in range(len(off) - 1) if tuple(int(x) for x in z["params"][j]) == prm]
+        sizes = np.array([off[j + 1] - off[j] for j in js], dtype=np.int64)
+        so = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        soo = np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)
+        mats = np.concatenate([z["packed"][oo[j]:oo[j + 1]] for j in js]).astype(np.int32)
+        qv = np.ascontiguousarray(z["qv01"][js])
+        d_m, d_o, d_oo, d_q = (torch.from_numpy(x).cuda() for x in (mats, so, soo, qv))
+        d_rec = torch.zeros((int(so[-1]), 16), dtype=torch.uint8, device="cuda")
+        nbytes = int(L.slr_umi_assign_scratch_bytes(len(js))) + sum(int(L.slr_umi_assign_deep_job_bytes(int(n))) for n in sizes)
+        d_scr = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        P = pkg.UmiAssignParams(prm[0], prm[1], prm[2], prm[3], 0, 1)
+        pkg._check(L.slr_umi_assign_dev2(ctx.h, d_m.data_ptr(), d_o.data_ptr(), d_oo.data_ptr(), len(js), int(so[-1]), C.byref(P),
+                                         d_q.data_ptr(), d_scr.data_ptr(), nbytes, d_rec.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        got = d_rec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
+        for k, j in enumerate(js):
+            recs[j] = got[so[k]:so[k + 1]]
+    stats = _check_hier(z, lambda j: recs[j])
+    assert stats[2] >= 40 and stats[0] > 4000, stats

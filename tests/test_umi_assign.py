@@ -177,20 +177,25 @@ def test_queue_tie_rule_and_center_rules(orc):
     assert int(rec["n_clusters"][0]) == 2 and all(int(u) >= 0 for u in rec["u2"])
 
 
-def _dev_assign(pkg, ctx, mats, offs, oo, params=None, qv=None):
+def _dev_assign(pkg, ctx, mats, offs, oo, params=None, qv=None, n_rows=None, fill=0):
+    """slr_umi_assign_dev2 with an arena sized for the jobs above max_hier (slr_umi_assign_deep_job_bytes)"""
     import ctypes as C
     import torch
+    L = pkg.gpu_lib()
     d_m = torch.from_numpy(mats).cuda()
     d_o, d_oo = torch.from_numpy(offs).cuda(), torch.from_numpy(oo).cuda()
-    m = int(offs[-1])
-    d_rec = torch.zeros((m, 16), dtype=torch.uint8, device="cuda")
+    m = int(offs[-1]) if n_rows is None else n_rows
+    d_rec = torch.full((m, 16), fill, dtype=torch.uint8, device="cuda")
     n_jobs = len(offs) - 1
-    d_scr = torch.zeros(int(pkg.gpu_lib().slr_umi_assign_scratch_bytes(n_jobs)), dtype=torch.uint8, device="cuda")
+    max_hier = 100 if params is None else params.max_hier
+    deep = sum(int(L.slr_umi_assign_deep_job_bytes(int(n))) for n in np.diff(offs) if n > max_hier)
+    nbytes = int(L.slr_umi_assign_scratch_bytes(n_jobs)) + deep
+    d_scr = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     d_qv = None if qv is None else torch.from_numpy(qv).cuda()
     st = torch.cuda.current_stream().cuda_stream
-    pkg._check(pkg.gpu_lib().slr_umi_assign_dev(ctx.h, d_m.data_ptr(), d_o.data_ptr(), d_oo.data_ptr(), n_jobs, m,
-                                                C.byref(params) if params is not None else None, None if d_qv is None else d_qv.data_ptr(),
-                                                d_scr.data_ptr(), d_rec.data_ptr(), st))
+    pkg._check(L.slr_umi_assign_dev2(ctx.h, d_m.data_ptr(), d_o.data_ptr(), d_oo.data_ptr(), n_jobs, m,
+                                     C.byref(params) if params is not None else None, None if d_qv is None else d_qv.data_ptr(),
+                                     d_scr.data_ptr(), nbytes, d_rec.data_ptr(), st))
     torch.cuda.synchronize()
     return d_rec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
 
@@ -281,13 +286,51 @@ def test_gpu_assign_padding_rows_and_base_offset(pkg, orc, ctx):
 
 
 def _dev_assign_padded(pkg, ctx, mats, offs, oo, n_rows):
-    import torch
-    d_m, d_o, d_oo = torch.from_numpy(mats).cuda(), torch.from_numpy(offs).cuda(), torch.from_numpy(oo).cuda()
-    d_rec = torch.full((n_rows, 16), 0x55, dtype=torch.uint8, device="cuda")
-    n_jobs = len(offs) - 1
-    d_scr = torch.zeros(int(pkg.gpu_lib().slr_umi_assign_scratch_bytes(n_jobs)), dtype=torch.uint8, device="cuda")
     # rec is positional over rows: rec[r] for row r, jobs address rows joff[j] .. joff[j + 1]
-    pkg._check(pkg.gpu_lib().slr_umi_assign_dev(ctx.h, d_m.data_ptr(), d_o.data_ptr(), d_oo.data_ptr(), n_jobs, n_rows, None, None,
-                                                d_scr.data_ptr(), d_rec.data_ptr(), torch.cuda.current_stream().cuda_stream))
-    torch.cuda.synchronize()
-    return d_rec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
+    return _dev_assign(pkg, ctx, mats, offs, oo, n_rows=n_rows, fill=0x55)
+
+
+def _deep_batch(rng, sizes):
+    mats, qv = [], []
+    for t, n in enumerate(sizes):
+        mats.append((random_packed(rng, n, t % 3) if t % 2 else umi_like_packed(rng, n)).ravel())
+        qv.append(int(rng.integers(0, 2)))
+    sizes = np.array(sizes, dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    oo = np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)
+    return np.concatenate(mats).astype(np.int32), offs, oo, np.array(qv, dtype=np.uint8)
+
+
+@pytest.mark.gpu
+def test_gpu_deep_jobs_match_oracle(pkg, orc, ctx):
+    """ClusterOne_MyClustering.call on the GPU (umi_assign_deep.cu) against the oracle: jobs of 101 ... 1024 reads on one CTA, larger ones on a
+    cluster of 8 CTAs, mixed with small jobs in one batch; every field of every record"""
+    rng = np.random.default_rng(909)
+    sizes = [int(x) for x in rng.integers(101, 400, 24)] + [1024, 1025, 1500, 2600, 3, 17, 64, 100, 101, 7]
+    rng.shuffle(sizes)
+    mats, offs, oo, qv = _deep_batch(rng, sizes)
+    for fold in (50, 3):
+        P = pkg.UmiAssignParams(2, 1, 3000, fold, 100, 1)
+        got = _dev_assign(pkg, ctx, mats, offs, oo, P, qv)
+        exp = orc.umi_assign_batch(mats, offs, oo, orc.AssignParams(2, 1, 3000, fold, 100, 1), qv)
+        bad = np.nonzero(got.tobytes() != exp.tobytes())[0] if False else [i for i in range(len(got)) if rec_tuple(got[i]) != rec_tuple(exp[i])]
+        assert not bad, (fold, len(bad), bad[:5], [(rec_tuple(got[i]), rec_tuple(exp[i]), int(np.searchsorted(offs, i, side="right") - 1)) for i in bad[:5]])
+        deep = np.repeat(np.diff(offs) > 100, np.diff(offs))
+        assert int((got["flags"][deep] & 1).sum()) > 5000 and (got["flags"][deep] & 8).all() and not (got["flags"][~deep] & 8).any()
+    # deep = 0 and the arena-less entry point: the large jobs are only flagged
+    got0 = _dev_assign(pkg, ctx, mats, offs, oo, pkg.UmiAssignParams(2, 1, 3000, 50, 100, 0), qv)
+    assert (got0["flags"][deep] == 8).all() and (got0["center"][deep] == -1).all()
+
+
+@pytest.mark.gpu
+def test_gpu_deep_jobs_through_host_api_and_session(pkg, orc, ctx):
+    """slr_umi_assign (host buffers) and the session API size the arena themselves: synthetic UMI batches with jobs above 100 reads"""
+    umis, offs = pkg.synth_umi_jobs(300, mean=60.0, cap=900, seed=21)
+    assert (np.diff(offs) > 100).sum() >= 20
+    rec, mats, oo = pkg.cluster_one_hierarchical(ctx, umis, offs, want_matrices=True)
+    exp = orc.umi_assign_batch(mats, offs, oo, orc.AssignParams(), None)
+    assert [rec_tuple(r) for r in rec] == [rec_tuple(r) for r in exp]
+    deep = np.repeat(np.diff(offs) > 100, np.diff(offs))
+    assert int((rec["flags"][deep] & 1).sum()) > 1000
+    with pkg.UmiSession(ctx, umis, offs) as s:
+        assert [rec_tuple(r) for r in s.assign()] == [rec_tuple(r) for r in exp]

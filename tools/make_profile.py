@@ -20,7 +20,7 @@ RUNS = [
     ("umi_pairs_kernel", "umi_pairs_kernel", 4_000_000, ["tools/perf_assign.py", "4000000", "4", "2000", "1"], "4 M reads in jobs of mean 4"),
     ("umi_assign_kernel", "umi_assign_kernel", 4_000_000, ["tools/perf_assign.py", "4000000", "4", "2000", "1"], "4 M reads in jobs of mean 4"),
     # the side benches: units = what their own JSON line reports (roofline.units_per_launch)
-    ("umi_pairs_kernel@umi_cluster_bench", "umi_pairs_kernel", None, ["tools/bench_umi_cluster.py", "--steps", "1", "--warmup", "1", "--cpu-jobs", "1000"],
+    ("umi_pairs_kernel@umi_cluster_bench", "umi_pairs_kernel", None, ["tools/bench_umi_cluster.py", "--steps", "1", "--warmup", "0", "--cpu-jobs", "1000"],
      "tools/bench_umi_cluster.py defaults: 10 M jobs of mean 4 + one 20 000-read job"),
     ("guided_match_kernel<umi,2>", "guided_match_kernel", None, ["tools/bench_guided.py", "--flavour", "umi", "--ed", "2", "--steps", "1", "--warmup", "1", "--cpu-sample", "64"],
      "tools/bench_guided.py defaults, UMI flavour, ED 2"),
@@ -31,8 +31,12 @@ UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1
         "msecond": 1.0, "second": 1e3}
 kernels = []
 for key, rx, units, cmd, what in RUNS:
-    r = subprocess.run(["ncu", "--metrics", METRICS, "--clock-control", "none", "-k", "regex:" + rx, "--csv", sys.executable] + cmd,
-                       capture_output=True, text=True, cwd=ROOT)
+    try:
+        r = subprocess.run(["ncu", "--metrics", METRICS, "--clock-control", "none", "-k", "regex:" + rx, "--csv", sys.executable] + cmd,
+                           capture_output=True, text=True, cwd=ROOT, timeout=420)
+    except subprocess.TimeoutExpired:
+        print("timeout:", key, cmd, file=sys.stderr)
+        continue
     lines = [l for l in r.stdout.splitlines() if l.startswith('"')]
     if units is None:
         for l in r.stdout.splitlines():
@@ -70,7 +74,7 @@ for key, rx, units, cmd, what in RUNS:
                     "lts_sector_hit_rate_pct": best.get("lts__t_sector_hit_rate.pct"), "achieved_warps_per_sm": best.get("sm__warps_active.avg.per_cycle_active"),
                     "global_load_sectors_per_unit": best.get("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", 0) / units,
                     "registers": best.get("launch__registers_per_thread"), "grid": best.get("grid"), "block": best.get("block")})
-json.dump({"csrc_sha256": pkg.csrc_sha256(), "lib_sha256": pkg.lib_sha256(), "how": "ncu --metrics ... --clock-control none (tools/make_profile.py), durations are "
-           "cold-cache profiler times: the bench uses the per-unit COUNTS only and its own CUDA-event times", "kernels": kernels},
-          open(out_path, "w"), indent=1)
+    json.dump({"csrc_sha256": pkg.csrc_sha256(), "lib_sha256": pkg.lib_sha256(), "how": "ncu --metrics ... --clock-control none (tools/make_profile.py), durations are "
+               "cold-cache profiler times: the bench uses the per-unit COUNTS only and its own CUDA-event times", "kernels": kernels},
+              open(out_path, "w"), indent=1)                # rewritten after every kernel: a slow side bench cannot lose the earlier ones
 print(open(out_path).read())
