@@ -169,8 +169,6 @@ def cpu_reference_step(orc, kind, bset, slices, anchor, ed, umis, offs, threads)
     if umis is not None:
         mats, oo = orc.umi_matrix_batch(umis, offs, 12, n_threads=threads)
         arec = orc.umi_assign_batch(mats, offs, oo, None, None, n_threads=threads)
-        if kind == "umi":
-            orc.umi_cluster_batch(mats, offs, oo, 2, n_threads=threads)
     t2 = time.perf_counter()
     return t2 - t0, t1 - t0, probes, res, arec
 
@@ -226,7 +224,7 @@ def main():
                    "assignment of the same number of reads in (cell,region) jobs (geometric, mean 4)"))
     else:
         wtxt = ("umi5kx2k: %d reads/GPU/step in (cell,gene) jobs (geometric, mean 4, cap 2000) + one %d-read job: UMI distance matrices, "
-                "ClusterOneHierarchical (jobs <= 100 reads) / clusterLocal passes (deeper jobs), per-read UMI assignment" % (R, DEEP_JOB))
+                "ClusterOneHierarchical (jobs <= 100 reads) / ClusterOne_MyClustering (larger jobs), per-read UMI assignment" % (R, DEEP_JOB))
     config = {"workload": wtxt, "reads_per_gpu_per_step": R, "whitelist": n_wl, "bc_edit_distance": ed,
               "sharding": "reads sharded by index, list replicated; N>1: (cell,region) jobs cut by a shard boundary merged onto the lower rank "
                           "(all_gather over NCCL, every step); counters all-reduced once per run",
@@ -323,12 +321,11 @@ def main():
         d_umis, d_offs, d_oo = d_umis_all[row0:], h_moffs.to(dev), torch.from_numpy(moo).to(dev)
         d_mat = torch.empty(dev_cells, dtype=torch.int32, device=dev)
         d_arec = torch.empty((n_rows, 16), dtype=torch.uint8, device=dev)
-        d_ascr = torch.empty(int(lib.slr_umi_assign_scratch_bytes(n_jobs)), dtype=torch.uint8, device=dev)
+        # job lists + the working arrays of the jobs above 100 reads (ClusterOne_MyClustering's, clustered in the same call)
+        n_deep_jobs = int((np.diff(moffs) > 100).sum())
+        ascr_bytes = int(lib.slr_umi_assign_scratch_bytes(n_jobs)) + sum(int(lib.slr_umi_assign_deep_job_bytes(int(n))) for n in np.diff(moffs) if n > 100)
+        d_ascr = torch.empty(ascr_bytes, dtype=torch.uint8, device=dev)
         h_arec = pin(torch.empty((n_rows, 16), dtype=torch.uint8))
-        if kind == "umi":
-            d_ccnt = torch.empty(n_rows, dtype=torch.int32, device=dev)
-            d_crec = torch.empty((n_rows, 16), dtype=torch.uint8, device=dev)
-            h_crec = pin(torch.empty((n_rows, 16), dtype=torch.uint8))
     n_units = R
 
     def step_device(ev=None):
@@ -345,13 +342,10 @@ def main():
                                             d_oo.data_ptr(), dev_cells, stream))
             if ev:
                 ev[2].record()
-            if kind == "umi":
-                pkg._check(lib.slr_umi_cluster_dev(ctx.h, d_mat.data_ptr(), d_offs.data_ptr(), d_oo.data_ptr(), n_jobs, n_rows, 2, None, None,
-                                                   d_ccnt.data_ptr(), d_crec.data_ptr(), stream))
             if ev:
                 ev[3].record()
-            pkg._check(lib.slr_umi_assign_dev(ctx.h, d_mat.data_ptr(), d_offs.data_ptr(), d_oo.data_ptr(), n_jobs, n_rows, None, None,
-                                              d_ascr.data_ptr(), d_arec.data_ptr(), stream))
+            pkg._check(lib.slr_umi_assign_dev2(ctx.h, d_mat.data_ptr(), d_offs.data_ptr(), d_oo.data_ptr(), n_jobs, n_rows, None, None,
+                                               d_ascr.data_ptr(), ascr_bytes, d_arec.data_ptr(), stream))
         if ev:
             ev[4].record()
 
@@ -365,9 +359,6 @@ def main():
             if extra:
                 h_umis_all[n_own:n_own + extra].copy_(d_umis_all[n_own:n_own + extra])
         arec = h_arec.numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
-        if kind == "umi":
-            crec = h_crec.numpy().view(pkg.UMI_CLUSTER_REC).reshape(-1)
-            pkg._check(lib.slr_umi_cluster(ctx.h, h_umis_m.data_ptr(), 16, 12, h_moffs.data_ptr(), n_jobs, 2, None, None, None, None, crec.ctypes.data))
         pkg._check(lib.slr_umi_assign(ctx.h, h_umis_m.data_ptr(), 16, 12, h_moffs.data_ptr(), n_jobs, None, None, None, None, arec.ctypes.data))
 
     def step_e2e():
@@ -425,7 +416,7 @@ def main():
             h_m = d_umis.cpu().numpy()[:n_rows]
             arec = d_arec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
             jsel = np.unique(np.concatenate([np.arange(0, n_jobs, max(1, n_jobs // 20000)), [0, n_jobs - 1]]))
-            jsel = jsel[np.diff(moffs)[jsel] <= 2000]            # (the 20 000-read job of umi5kx2k is covered by tests/, not by this spot check)
+            jsel = np.unique(np.concatenate([jsel, np.nonzero(np.diff(moffs) > 100)[0][:64]]))     # + (up to 64 of) the jobs ClusterOne_MyClustering gets
             ok, reads_checked = True, 0
             sub_u = np.concatenate([h_m[moffs[j]:moffs[j + 1]] for j in jsel])
             sub_o = np.concatenate([[0], np.cumsum([moffs[j + 1] - moffs[j] for j in jsel])]).astype(np.int64)
@@ -518,7 +509,7 @@ def main():
         out = {"metric": METRIC, "value": world * n_units / (ms_step / 1e3), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-               "legs_ms": {"bc_assign": bc_ms, "umi_dist": dist_ms, "umi_cluster_local": cluster_ms, "umi_assign": assign_ms},
+               "legs_ms": {"bc_assign": bc_ms, "umi_dist": dist_ms, "umi_assign": assign_ms + cluster_ms},
                "parity_all_ranks": (None if a.no_cpu_baseline else bool(parity_all >= 1.0)), "parity_rank0": parity, "numa": numa_note}
         if kind == "bc":
             out["assigned_fraction"] = assigned / R

@@ -44,10 +44,12 @@ public final class Native {
     public static native long umiSessionCells(long session);
     public static native int umiSessionMatrices(long session, ByteBuffer out, long nCells);
     public static native void umiSessionDestroy(long session);
-    /** ClusterOneHierarchical.call for every job of at most 100 reads (ClusterOneHierarchical.java:L61-L217) behind the same matrices: rec = 16 bytes per
-     *  read {int center, byte u1, byte u2, byte pos2, byte offsetCenterMean, short flags, short clusterSize, int nClusters}; params = null (config.xml /
-     *  UMIparameters defaults) or int[5] {completeLinkED, singleLinkED, singleLinkThreshold, foldDepthBelowMax, maxHier}; jobQv01 nullable: one byte per
-     *  job, mean_qv(read 0) > mean_qv(read 1) (OneUmiCluster.java:L53) */
+    /** UmiClustering$Submitter's two clusterers behind the same matrices: ClusterOneHierarchical.call for every job of at most 100 reads
+     *  (ClusterOneHierarchical.java:L61-L217) and ClusterOne_MyClustering.call for the larger ones (ClusterOne_MyClustering.java:L59-L219, sequential-stream
+     *  semantics): rec = 16 bytes per read {int center, byte u1, byte u2, byte pos2, byte offsetCenterMean, short flags, short clusterSize, int nClusters};
+     *  params = null (config.xml / UMIparameters defaults) or int[5..6] {completeLinkED, singleLinkED, singleLinkThreshold, foldDepthBelowMax, maxHier,
+     *  deep (1 = cluster the jobs above maxHier too, the default; 0 = only flag them)}; jobQv01 nullable: one byte per job,
+     *  mean_qv(read 0) > mean_qv(read 1) (OneUmiCluster.java:L53) */
     public static native int umiAssign(long ctx, ByteBuffer umis, int stride, int umiLen, ByteBuffer jobOffsets, long nJobs, int[] params,
                                        ByteBuffer jobQv01, ByteBuffer out, ByteBuffer outOffsets, ByteBuffer rec);
     public static native int umiSessionAssign(long session, int[] params, ByteBuffer jobQv01, ByteBuffer rec);

@@ -82,7 +82,7 @@ public final class UmiBatch {
         }
     }
 
-    /** params = null (UMIparameters defaults) or {completeLinkED, singleLinkED, singleLinkThreshold, foldDepthBelowMax, maxHier} */
+    /** params = null (UMIparameters defaults) or {completeLinkED, singleLinkED, singleLinkThreshold, foldDepthBelowMax, maxHier[, deep]} */
     public void assign(long ctx, int[] params) {
         if (nJobs == 0) return;
         int rc = Native.umiAssign(ctx, umis, STRIDE, umiLen, jobOffsets, nJobs, params, qv01, null, null, rec);
@@ -106,7 +106,8 @@ public final class UmiBatch {
     public int clusterSize(int read) { return rec.getShort(read * REC + 10) & 0xFFFF; }
     public int nClusters(int read) { return rec.getInt(read * REC + 12); }
     public boolean assigned(int read) { return (flags(read) & ASSIGNED) != 0; }
-    /** job of more than maxHier reads: ClusterOne_MyClustering territory, run the jar's own class (or Native.umiCluster) for it */
+    /** job of more than maxHier reads: the record comes from the large-job path (ClusterOne_MyClustering.call, sequential-stream semantics) — or, with
+     *  params[5] == 0, the job was only flagged and is left to the jar's own class / Native.umiCluster */
     public boolean deep(int read) { return (flags(read) & DEEP) != 0; }
     /** equal-score merge order depended on identity hash codes in the reference JVM: re-run this job on the CPU if bit-for-bit agreement with one
      *  particular JVM run matters (the reference itself is not reproducible across runs for such a job) */

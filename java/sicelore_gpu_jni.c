@@ -186,14 +186,16 @@ static int mat_check(JNIEnv *env, const umi_bufs *U, jlong nJobs, jobject out, j
     *o = (int32_t *)buf(env, out, need * 4, 1, &ok);
     return ok;
 }
-/* int[5] clustering parameters or null */
+/* int[5] or int[6] clustering parameters (the sixth, `deep`, defaults to 1) or null */
 static int params_get(JNIEnv *env, jintArray params, slr_umi_assign_params *P)
 {
     if (!params) return 0;
-    if ((*env)->GetArrayLength(env, params) < 5) return -1;
+    const jsize len = (*env)->GetArrayLength(env, params);
+    if (len < 5) return -1;
     jint *v = (*env)->GetIntArrayElements(env, params, NULL);
     if (!v) return -1;
     P->ed_complete = v[0]; P->ed_single = v[1]; P->single_threshold = v[2]; P->fold_depth = v[3]; P->max_hier = v[4];
+    P->deep = len > 5 ? v[5] : 1;
     (*env)->ReleaseIntArrayElements(env, params, v, JNI_ABORT);
     return 1;
 }

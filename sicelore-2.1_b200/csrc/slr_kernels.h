@@ -31,11 +31,12 @@ cudaError_t slr_launch_umi_cluster(const int32_t *d_mat, const long long *d_job_
 // sum of slr_umi_assign_deep_words(n) over those jobs; 0 or P.deep == 0: they are only flagged SLR_UA_DEEP);
 // d_rowjob as for slr_launch_umi_cluster (NULL: binary search)
 constexpr int SLR_UMI_ASSIGN_LAUNCHES = 3;
-constexpr int SLR_UMI_ASSIGN_DEEP_LAUNCHES = 2;
-constexpr int SLR_UA_DEEP_SMALL = 1024;        // deep jobs up to this size run on one CTA, larger ones on a cluster of 8
+constexpr int SLR_UMI_ASSIGN_DEEP_LAUNCHES = 3;
+constexpr int SLR_UA_DEEP_SMALL = 1024;        // deep jobs up to this size run on one CTA, up to SLR_UA_DEEP_MEDIUM on a cluster of 8 CTAs,
+constexpr int SLR_UA_DEEP_MEDIUM = 4096;       // larger ones on the whole GPU (cooperative grid), one job after the other
 size_t slr_umi_assign_scratch(long long n_jobs, long long deep_words);
 // 32-bit words of working arrays umi_assign_deep.cu needs for a job of n reads (kept in step with carve() there)
-SLR_HD long long slr_umi_assign_deep_words(long long n) { return (64 + 52 * (n + 2) + 2 * (3 * n + 64) + 2 * (4 * n + 64) + 1) & ~1ll; }
+SLR_HD long long slr_umi_assign_deep_words(long long n) { return (64 + 52 * (n + 4) + 2 * (3 * n + 64) + 2 * (4 * n + 64) + 1) & ~1ll; }
 cudaError_t slr_launch_umi_assign(const int32_t *d_mat, const long long *d_job_offsets, const long long *d_out_offsets, long long n_jobs,
                                   long long n_reads, const slr_umi_assign_params &P, const uint8_t *d_job_qv01, const int32_t *d_rowjob,
                                   slr_umi_assign_rec *d_rec, void *d_scratch, size_t scratch_bytes, cudaStream_t stream);

@@ -17,10 +17,12 @@
 // HashSet of the clusters (hash = sum of the members).  SLR_UA_TIE_UNPIN marks a job in which a read could choose between largest neighbour
 // sets that are not the same set, or a bin reached the treeify threshold.
 //
-// One TEAM per job: one CTA (jobs up to DEEP_SMALL reads) or a thread-block cluster of 8 CTAs.  The O(n^2) passes over the matrix (neighbour
+// One TEAM per job: one CTA (jobs up to SLR_UA_DEEP_SMALL reads), a thread-block cluster of 8 CTAs (up to SLR_UA_DEEP_MEDIUM), or — one giant job
+// after the other — the whole GPU as a cooperative grid.  The O(n^2) passes over the matrix (neighbour
 // counts, entry choice, sums of squared distances, U2) are spread over the team's warps with coalesced row reads; the hash-table emulations are
 // inherently sequential and run on the team's first thread between team barriers.  All working arrays live in the caller's scratch.
 #include <cooperative_groups.h>
+#include <mutex>
 #include "slr_kernels.h"
 
 namespace cg = cooperative_groups;
@@ -52,44 +54,47 @@ __device__ __forceinline__ int dp_array_size(int expected)
 }
 
 // header words of a job's scratch
-enum { H_NK = 0, H_NG, H_NCL, H_NU, H_NREM, H_FLAG, H_TOTAL, H_ROUND2_FIRST, H_NDIRTY, H_WORDS = 16 };
+enum { H_NK = 0, H_NG, H_NCL, H_NU, H_NREM, H_FLAG, H_TOTAL, H_NBIG, H_Q0, H_WORDS = 16 };
+constexpr int SMALL_K = 24;                    // clusters up to this size never grow fastutil's initial 32-slot table: one thread, local arrays
 
 struct DeepW {
-    int *hdr, *cnt, *chosen, *keys, *tmp, *gid, *first, *gsz, *gm, *fill, *corder, *perm, *mem, *it, *pos_cl, *sumsq;
-    int *cl_beg, *cl_len0, *cl_len, *cl_center, *cl_nvict, *cl_dirty, *cl_offmean, *cl_nf;
+    int *hdr, *cnt, *chosen, *keys, *tmp, *first, *corder, *perm, *mem, *it, *pos_cl, *sumsq, *gm, *pscr;
+    int *cl_beg, *cl_len0, *cl_len, *cl_center, *cl_nvict, *cl_dirty, *cl_offmean, *cl_nf, *cl_entry, *rem_off, *big_list;
     int *clid, *victim, *idx, *inU, *tabA, *tabB, *wrapped, *chmA, *chmB, *chm_nxt;
-    unsigned *hs, *chm_h;
+    int *ck, *firstpos, *gcount, *isfirst, *grp_q;
+    unsigned *ht, *chm_h, *gsum;
     unsigned long long *sig;
 };
 __device__ inline void carve(int *W, int n, DeepW &w)
 {
-    const int s = n + 2;
+    const int s = (n + 3) & ~1;                                    // even: the 64-bit views (sig, best64 in gm, ksig in pscr) stay 8-byte aligned
     w.sig = reinterpret_cast<unsigned long long *>(W);             // 8-byte aligned: every arena offset is even
     int *p = W + 2 * s;
     w.hdr = p; p += 64;
     auto take = [&](int words) { int *q = p; p += words; return q; };
-    w.cnt = take(s); w.chosen = take(s); w.keys = take(s); w.tmp = take(s); w.gid = take(s); w.first = take(s); w.gsz = take(s); w.gm = take(s);
-    w.fill = take(s); w.corder = take(s); w.perm = take(s);
-    w.mem = take(2 * s); w.it = take(2 * s); w.pos_cl = take(2 * s); w.sumsq = take(2 * s);
+    w.cnt = take(s); w.chosen = take(s); w.keys = take(s); w.tmp = take(s); w.first = take(s); w.corder = take(s); w.perm = take(s);          // 7
+    w.mem = take(2 * s); w.it = take(2 * s); w.pos_cl = take(2 * s); w.sumsq = take(2 * s); w.gm = take(2 * s); w.pscr = take(2 * s);        // 12
     w.cl_beg = take(s); w.cl_len0 = take(s); w.cl_len = take(s); w.cl_center = take(s); w.cl_nvict = take(s); w.cl_dirty = take(s);
-    w.cl_offmean = take(s); w.cl_nf = take(s);
-    w.clid = take(s); w.victim = take(s); w.idx = take(2 * s); w.inU = take(s); w.wrapped = take(s); w.chm_nxt = take(s);
-    w.hs = reinterpret_cast<unsigned *>(take(s)); w.chm_h = reinterpret_cast<unsigned *>(take(s));
-    // 11 + 8 + 8 + 7 + 2 = 36 single + 4 double + idx double = 36 + 8 + 2 = 46 s  (<= 50 s)
+    w.cl_offmean = take(s); w.cl_nf = take(s); w.cl_entry = take(s); w.rem_off = take(s); w.big_list = take(s);                                 // 11
+    w.clid = take(s); w.victim = take(s); w.idx = take(2 * s); w.inU = take(s); w.wrapped = take(s); w.chm_nxt = take(s);                      // 7
+    w.ck = take(s); w.firstpos = take(s); w.gcount = take(s); w.isfirst = take(s); w.grp_q = take(s);                                         // 5
+    w.ht = reinterpret_cast<unsigned *>(take(s)); w.chm_h = reinterpret_cast<unsigned *>(take(s)); w.gsum = reinterpret_cast<unsigned *>(take(s));   // 3
+    // 2 (sig) + 45 of the 52 (n + 2)-word units slr_umi_assign_deep_words() grants
     w.tabA = take(3 * n + 64); w.tabB = take(3 * n + 64); w.chmA = take(4 * n + 64); w.chmB = take(4 * n + 64);
 }
 
 // ---- team = 1 CTA or a cluster of CS CTAs ---------------------------------------------------------------------------------------------------
-template <int CS>
+template <int CS>                              // CS = 1: one CTA, CS = 8: a cluster of 8 CTAs, CS = 0: the whole (cooperative) grid
 struct Team {
     __device__ static __forceinline__ void sync()
     {
         if (CS == 1) __syncthreads();
+        else if (CS == 0) { __threadfence(); cg::this_grid().sync(); }
         else { __threadfence(); cg::this_cluster().sync(); }
     }
-    __device__ static __forceinline__ int rank() { return CS == 1 ? 0 : (int)cg::this_cluster().block_rank(); }
+    __device__ static __forceinline__ int rank() { return CS == 1 ? 0 : (CS == 0 ? (int)blockIdx.x : (int)cg::this_cluster().block_rank()); }
     __device__ static __forceinline__ int tid() { return rank() * DEEP_THREADS + (int)threadIdx.x; }
-    __device__ static __forceinline__ int size() { return CS * DEEP_THREADS; }
+    __device__ static __forceinline__ int size() { return (CS == 0 ? (int)gridDim.x : CS) * DEEP_THREADS; }
 };
 
 // ---- sequential container emulations (one thread) ---------------------------------------------------------------------------------------------
@@ -99,24 +104,31 @@ __device__ int fu_fill(const int *in, int k, int *bufA, int *bufB, int **tab_out
     int n = 32, size = 0, hz = 0;
     int *tab = bufA, *alt = bufB;
     for (int i = 0; i < n; i++) tab[i] = 0;
-    for (int i = 0; i < k; i++) {
-        const int key = in[i];
-        if (key == 0) hz = 1;
-        else {
-            int pos = (int)(dp_mix(key) & (uint32_t)(n - 1));
-            while (tab[pos] != 0) pos = (pos + 1) & (n - 1);
-            tab[pos] = key;
-        }
-        if (size++ >= dp_max_fill(n)) {
-            const int nn = dp_array_size(size + 1);
-            for (int j = 0; j < nn; j++) alt[j] = 0;
-            for (int j = n - 1; j >= 0; j--)
-                if (tab[j] != 0) {
-                    int pos = (int)(dp_mix(tab[j]) & (uint32_t)(nn - 1));
-                    while (alt[pos] != 0) pos = (pos + 1) & (nn - 1);
-                    alt[pos] = tab[j];
-                }
-            int *t = tab; tab = alt; alt = t; n = nn;
+    for (int i0 = 0; i0 < k; i0 += 8) {
+        int kk[8];                                                      // the input loads of 8 inserts in flight together (one thread: latency is all)
+#pragma unroll
+        for (int u = 0; u < 8; u++) kk[u] = i0 + u < k ? in[i0 + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int key = kk[u];
+            if (i0 + u >= k) break;
+            if (key == 0) hz = 1;
+            else {
+                int pos = (int)(dp_mix(key) & (uint32_t)(n - 1));
+                while (tab[pos] != 0) pos = (pos + 1) & (n - 1);
+                tab[pos] = key;
+            }
+            if (size++ >= dp_max_fill(n)) {
+                const int nn = dp_array_size(size + 1);
+                for (int j = 0; j < nn; j++) alt[j] = 0;
+                for (int j = n - 1; j >= 0; j--)
+                    if (tab[j] != 0) {
+                        int pos = (int)(dp_mix(tab[j]) & (uint32_t)(nn - 1));
+                        while (alt[pos] != 0) pos = (pos + 1) & (nn - 1);
+                        alt[pos] = tab[j];
+                    }
+                int *t = tab; tab = alt; alt = t; n = nn;
+            }
         }
     }
     *tab_out = tab; *has_zero = hz;
@@ -234,6 +246,7 @@ __device__ void chm_order(const int *keys, int K, int *out, int *headA, int *hea
 
 // ---- parallel passes ---------------------------------------------------------------------------------------------------------------------------
 // neighbour counts and set signatures of idx[0 .. L) against the reads marked in inU (NULL = all)
+constexpr int DU = 8;                          // independent loads a lane keeps in flight in the row passes
 template <int CS>
 __device__ void pass_counts(const int32_t *__restrict__ M, int n, int ed, const int *idx, int L, const int *inU, DeepW &w)
 {
@@ -243,32 +256,74 @@ __device__ void pass_counts(const int32_t *__restrict__ M, int n, int ed, const 
         const int32_t *row = M + (size_t)a * n;
         int c = 0;
         unsigned long long s = 0;
-        for (int j = lane; j < n; j += 32)
-            if ((!inU || inU[j]) && dp_ed(row[j]) <= ed) { c++; s += dp_sig(j); }
+        for (int j0 = 0; j0 < n; j0 += 32 * DU) {
+            int32_t v[DU];
+            int in[DU];
+#pragma unroll
+            for (int u = 0; u < DU; u++) {
+                const int j = j0 + u * 32 + lane;
+                v[u] = j < n ? __ldg(row + j) : 0x7F;
+                in[u] = (j < n && inU) ? inU[j] : 1;
+            }
+#pragma unroll
+            for (int u = 0; u < DU; u++)
+                if (in[u] && dp_ed(v[u]) <= ed) { c++; s += dp_sig(j0 + u * 32 + lane); }
+        }
         c = __reduce_add_sync(FULLM, c);
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
         if (lane == 0) { w.cnt[a] = c; w.sig[a] = s; }
     }
 }
-// every key c joins the first entry (in key order) with the largest neighbour set that contains c
+// every key c joins the first entry (in key order) with the largest neighbour set that contains c.  The key range is cut into slices so that the
+// whole team works on a job of any size: slice maxima meet in a 64-bit atomicMax on (|N(e)|, -position), a second sweep looks for entries tied
+// with the winner whose neighbour set is a different one.  kcnt / ksig: |N| and set signature of the keys in key order.
 template <int CS>
-__device__ void pass_choose(const int32_t *__restrict__ M, int n, int ed, const int *inU, DeepW &w)
+__device__ void pass_choose_prepare(DeepW &w, unsigned long long *best64)
 {
     const int nk = w.hdr[H_NK];
+    for (int p = Team<CS>::tid(); p < nk; p += Team<CS>::size()) {
+        const int e = w.keys[p];
+        w.ck[p] = w.cnt[e];                                             // (ck is rewritten by groups_scan afterwards)
+        reinterpret_cast<unsigned long long *>(w.pscr)[p] = w.sig[e];
+        best64[e] = 0;
+    }
+}
+template <int CS, bool SECOND>
+__device__ void pass_choose_sweep(const int32_t *__restrict__ M, int n, int ed, const int *inU, DeepW &w, unsigned long long *best64)
+{
+    const int nk = w.hdr[H_NK], T = Team<CS>::size();
+    const unsigned long long *ksig = reinterpret_cast<const unsigned long long *>(w.pscr);
+    const int n_slices = T / n > 0 ? T / n : 1, per = (nk + n_slices - 1) / n_slices;
     int harmful = 0;
-    for (int c = Team<CS>::tid(); c < n; c += Team<CS>::size()) {
+    for (int t = Team<CS>::tid(); t < n * n_slices; t += T) {
+        const int c = t % n, sl = t / n;
         if ((inU && !inU[c]) || w.cnt[c] <= 1) continue;
-        int best = -1, bestcnt = -1, tie_diff = 0;
+        const int p_lo = sl * per, p_hi = min(nk, p_lo + per);
+        int bestcnt = -1, bestp = -1;
         unsigned long long bestsig = 0;
-        for (int p = 0; p < nk; p++) {
-            const int e = w.keys[p];
-            if (dp_ed(M[(size_t)e * n + c]) > ed) continue;
-            const int ce = w.cnt[e];
-            if (ce > bestcnt) { best = e; bestcnt = ce; bestsig = w.sig[e]; tie_diff = 0; }
-            else if (ce == bestcnt && w.sig[e] != bestsig) tie_diff = 1;
+        if (SECOND) {
+            const unsigned long long b = best64[c];
+            bestcnt = (int)(b >> 32); bestp = (int)(0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFu));
+            bestsig = ksig[bestp];
         }
-        w.chosen[c] = best;
-        harmful |= tie_diff;
+        for (int p0 = p_lo; p0 < p_hi; p0 += DU) {
+            int e[DU];
+            int32_t v[DU];
+#pragma unroll
+            for (int u = 0; u < DU; u++) {
+                e[u] = p0 + u < p_hi ? w.keys[p0 + u] : -1;
+                v[u] = e[u] >= 0 ? __ldg(M + (size_t)e[u] * n + c) : 0x7F;
+            }
+#pragma unroll
+            for (int u = 0; u < DU; u++) {
+                if (e[u] < 0 || dp_ed(v[u]) > ed) continue;
+                const int ce = w.ck[p0 + u];
+                if (SECOND) { if (ce == bestcnt && ksig[p0 + u] != bestsig) harmful = 1; }
+                else if (ce > bestcnt) { bestcnt = ce; bestp = p0 + u; }
+            }
+        }
+        if (!SECOND && bestp >= 0) atomicMax(&best64[c], ((unsigned long long)(unsigned)bestcnt << 32) | (0xFFFFFFFFu - (unsigned)bestp));
+        if (SECOND && sl == 0) w.chosen[c] = w.keys[bestp];
     }
     if (harmful) atomicOr(&w.hdr[H_FLAG], 1);
 }
@@ -286,11 +341,34 @@ __device__ void pass_sumsq(const int32_t *__restrict__ M, int n, DeepW &w)
         const int32_t *row = M + (size_t)a * n;
         int s = 0;
         if ((long long)m * 8 >= n) {
-            for (int j = lane; j < n; j += 32)
-                if (w.clid[j] == c && j != a) { const int e = dp_ed(row[j]); s += e * e; }
+            for (int j0 = 0; j0 < n; j0 += 32 * DU) {
+                int32_t v[DU];
+                int cl[DU];
+#pragma unroll
+                for (int u = 0; u < DU; u++) {
+                    const int j = j0 + u * 32 + lane;
+                    v[u] = j < n ? __ldg(row + j) : 0;
+                    cl[u] = j < n ? w.clid[j] : -2;
+                }
+#pragma unroll
+                for (int u = 0; u < DU; u++)
+                    if (cl[u] == c && j0 + u * 32 + lane != a) { const int e = dp_ed(v[u]); s += e * e; }
+            }
         } else {
             const int *seg = w.it + w.cl_beg[c];
-            for (int q = lane; q < m; q += 32) { const int x = seg[q]; if (x != a) { const int e = dp_ed(row[x]); s += e * e; } }
+            for (int q0 = 0; q0 < m; q0 += 32 * DU) {
+                int x[DU];
+                int32_t v[DU];
+#pragma unroll
+                for (int u = 0; u < DU; u++) {
+                    const int q = q0 + u * 32 + lane;
+                    x[u] = q < m ? seg[q] : a;
+                    v[u] = __ldg(row + x[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < DU; u++)
+                    if (x[u] != a) { const int e = dp_ed(v[u]); s += e * e; }
+            }
         }
         s = __reduce_add_sync(FULLM, s);
         if (lane == 0) w.sumsq[pos] = s;
@@ -324,88 +402,291 @@ __device__ void pass_victims(const int32_t *__restrict__ M, int n, int ed, DeepW
     }
 }
 
-// ---- sequential phases -------------------------------------------------------------------------------------------------------------------------
-__device__ void seq_keys(int n, const int *idx, int L, DeepW &w)
+// phase time stamps (ns, %globaltimer) in the job's header words 32 ... 63: read by tools/perf_deep.py, free otherwise
+#define DEEP_STAMP(w, i) do { if (Team<CS>::tid() == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+                                                       reinterpret_cast<unsigned long long *>((w).hdr + 32)[i] = t_; } } while (0)
+
+// ---- table buffers: the team's shared memory when the table fits, the job's global scratch otherwise ----------------------------------------------
+struct TabBufs { int *A, *B, *cnt; };          // A >= final table, B >= half of it, cnt >= JDK capacity + 1 words
+template <int SM_INTS>
+__device__ __forceinline__ bool fits_smem(int k)
+{
+    constexpr int A = SM_INTS / 3 * 2;         // 2/3 + 1/3 split: A is a power of two, B = A / 2
+    return dp_array_size(k + 1) <= A && dp_jdk_cap(k) + 1 <= SM_INTS;
+}
+template <int SM_INTS>
+__device__ __forceinline__ TabBufs bufs_for(int k, int *smem, DeepW &w)
+{
+    TabBufs t;
+    if (fits_smem<SM_INTS>(k)) { t.A = smem; t.B = smem + SM_INTS / 3 * 2; t.cnt = smem; }
+    else { t.A = w.tabA; t.B = w.tabB; t.cnt = w.tabA; }
+    return t;
+}
+// fastutil table of k keys with the FINAL table in bufs.A (the growth steps alternate between the two buffers)
+__device__ int fu_fill_into_a(const int *in, int k, const TabBufs &tb, int **tab_out, int *has_zero)
+{
+    int T = 32, g = 0;
+    for (int sz = 1; sz <= k; sz++) if (sz - 1 >= dp_max_fill(T)) { T = dp_array_size(sz + 1); g++; }
+    return (g & 1) ? fu_fill(in, k, tb.B, tb.A, tab_out, has_zero) : fu_fill(in, k, tb.A, tb.B, tab_out, has_zero);
+}
+
+// ---- keys of clusterLocal in the iteration order of the Int2ObjectOpenHashMap (team leader) ---------------------------------------------------
+template <int SM_INTS>
+__device__ void seq_keys(const int *idx, int L, DeepW &w, int *smem)
 {
     int nk = 0;
-    for (int i = 0; i < L; i++) { const int a = idx ? idx[i] : i; if (w.cnt[a] > 1) w.tmp[nk++] = a; }
+    for (int i0 = 0; i0 < L; i0 += 16) {
+        int a[16], c[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) a[u] = i0 + u < L ? (idx ? idx[i0 + u] : i0 + u) : -1;
+#pragma unroll
+        for (int u = 0; u < 16; u++) c[u] = a[u] >= 0 ? w.cnt[a[u]] : 0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) if (c[u] > 1) w.tmp[nk++] = a[u];
+    }
+    const TabBufs tb = bufs_for<SM_INTS>(nk, smem, w);
     int *tab, hz;
-    const int tn = fu_fill(w.tmp, nk, w.tabA, w.tabB, &tab, &hz);      // Int2ObjectOpenHashMap: the set's layout and iteration
+    const int tn = fu_fill_into_a(w.tmp, nk, tb, &tab, &hz);
     fu_iter(tab, tn, hz, w.keys);
     w.hdr[H_NK] = nk;
 }
-// groups of the keys by their chosen entry -> clusters appended to the job's list.  round 1 applies the depth rule, round 2 keeps sizes > 1
-__device__ void seq_groups(int n, int round, int fold_depth, slr_umi_assign_rec *rec, DeepW &w)
+
+// ---- groups of the keys by their chosen entry -> clusters appended to the job's list ------------------------------------------------------------
+// G1 (parallel over the key positions): entry of every key, first position / size / member sum of every entry
+template <int CS>
+__device__ void groups_scan(DeepW &w)
+{
+    const int nk = w.hdr[H_NK];
+    for (int p = Team<CS>::tid(); p < nk; p += Team<CS>::size()) {
+        const int x = w.keys[p], e = w.chosen[x];
+        w.ck[p] = e;
+        atomicMin(&w.firstpos[e], p);
+        atomicAdd(&w.gcount[e], 1);
+        atomicAdd(&w.gsum[e], (unsigned)x);
+    }
+}
+template <int CS>
+__device__ void groups_first(DeepW &w)
+{
+    const int nk = w.hdr[H_NK];
+    for (int p = Team<CS>::tid(); p < nk; p += Team<CS>::size()) w.isfirst[p] = w.firstpos[w.ck[p]] == p;
+}
+// G2 (leader): the groups in first-seen order -> ConcurrentHashMap order -> HashSet<Set<Integer>> order -> cluster slots.  round 1 applies the
+// depth rule (L77-L84), round 2 keeps the groups of more than one read (L109)
+template <int SM_INTS>
+__device__ void groups_layout(int round, int fold_depth, DeepW &w, int *smem)
 {
     const int nk = w.hdr[H_NK];
     int ng = 0, long_bin = 0;
-    for (int i = 0; i < n; i++) w.gid[i] = -1;
-    for (int i = 0; i < nk; i++) { const int e = w.chosen[w.keys[i]]; if (w.gid[e] < 0) { w.gid[e] = ng; w.first[ng++] = e; } }
-    for (int g = 0; g <= ng; g++) w.gsz[g] = 0;
-    for (int i = 0; i < nk; i++) w.gsz[w.gid[w.chosen[w.keys[i]]] + 1]++;
-    for (int g = 0; g < ng; g++) w.gsz[g + 1] += w.gsz[g];
-    for (int g = 0; g < ng; g++) w.fill[g] = w.gsz[g];
-    for (int i = 0; i < nk; i++) w.gm[w.fill[w.gid[w.chosen[w.keys[i]]]]++] = w.keys[i];
-    chm_order(w.first, ng, w.corder, w.chmA, w.chmB, w.chm_nxt, w.chm_h, &long_bin);
-    int maxdepth = 0;
-    for (int t = 0; t < ng; t++) {
-        const int g = w.gid[w.corder[t]];
-        unsigned h = 0;
-        for (int i = w.gsz[g]; i < w.gsz[g + 1]; i++) h += (unsigned)w.gm[i];
-        w.hs[t] = h;
-        if (w.gsz[g + 1] - w.gsz[g] > maxdepth) maxdepth = w.gsz[g + 1] - w.gsz[g];
+    for (int p0 = 0; p0 < nk; p0 += 16) {
+        int f[16], e[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) { f[u] = p0 + u < nk ? w.isfirst[p0 + u] : 0; e[u] = p0 + u < nk ? w.ck[p0 + u] : 0; }
+#pragma unroll
+        for (int u = 0; u < 16; u++) if (f[u]) w.first[ng++] = e[u];
     }
-    jdk_order(w.hs, ng, w.perm, w.tabA, &long_bin);
-    int n_cl = w.hdr[H_NCL], total = w.hdr[H_TOTAL];
+    int chm_cap = 16;
+    while (ng >= chm_cap - (chm_cap >> 2)) chm_cap <<= 1;              // the map's final table
+    if (2 * chm_cap <= SM_INTS) chm_order(w.first, ng, w.corder, smem, smem + chm_cap, w.chm_nxt, w.chm_h, &long_bin);
+    else chm_order(w.first, ng, w.corder, w.chmA, w.chmB, w.chm_nxt, w.chm_h, &long_bin);
+    int maxdepth = 0;
+    for (int t0 = 0; t0 < ng; t0 += 8) {
+        int e[8], k[8];
+        unsigned h[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) e[u] = t0 + u < ng ? w.corder[t0 + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 8; u++) { k[u] = e[u] >= 0 ? w.gcount[e[u]] : 0; h[u] = e[u] >= 0 ? w.gsum[e[u]] : 0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (e[u] >= 0) { w.ht[t0 + u] = h[u]; if (k[u] > maxdepth) maxdepth = k[u]; }
+    }
+    jdk_order(w.ht, ng, w.perm, dp_jdk_cap(ng) + 1 <= SM_INTS ? smem : w.tabA, &long_bin);
+    int n_cl = w.hdr[H_NCL], total = w.hdr[H_TOTAL], n_big = 0;
+    w.hdr[H_Q0] = n_cl;
     for (int t = 0; t < ng; t++) {
-        const int g = w.gid[w.corder[w.perm[t]]], k = w.gsz[g + 1] - w.gsz[g];
-        const int *src = w.gm + w.gsz[g];
-        if (round == 2 && k <= 1) continue;
-        // HashSet<Integer> of the group, filled in key order: hash = value
-        unsigned *hh = reinterpret_cast<unsigned *>(w.tmp);
-        for (int i = 0; i < k; i++) hh[i] = (unsigned)src[i];
-        int *pp = w.fill;                                               // free by now (k <= nk <= n)
-        jdk_order(hh, k, pp, w.tabA, &long_bin);
-        if (round == 1 && !((long long)k * fold_depth > maxdepth)) {
-            for (int i = 0; i < k; i++) { rec[src[i]].flags |= SLR_UA_SKIPPED; rec[src[i]].cluster_size = (uint16_t)(k > 65535 ? 65535 : k); }
-            continue;
-        }
-        int *mem = w.mem + total;
-        for (int i = 0; i < k; i++) mem[i] = src[pp[i]];
-        int *tab, hz;
-        const int tn = fu_fill(mem, k, w.tabA, w.tabB, &tab, &hz);      // toCollection(OneUmiCluster::new)
-        fu_iter(tab, tn, hz, w.it + total);
-        for (int i = 0; i < k; i++) { w.clid[mem[i]] = n_cl; w.pos_cl[total + i] = n_cl; }
-        w.cl_beg[n_cl] = total; w.cl_len0[n_cl] = k; w.cl_len[n_cl] = k; w.cl_nvict[n_cl] = 0; w.cl_dirty[n_cl] = 1; w.cl_center[n_cl] = -1;
+        const int e = w.corder[w.perm[t]], k = w.gcount[e];
+        if (round == 2 && k <= 1) { w.grp_q[e] = -1; continue; }
+        if (round == 1 && !((long long)k * fold_depth > maxdepth)) { w.grp_q[e] = -2; continue; }
+        w.grp_q[e] = n_cl;
+        w.cl_entry[n_cl] = e; w.cl_beg[n_cl] = total; w.cl_len0[n_cl] = k; w.cl_len[n_cl] = k; w.cl_nvict[n_cl] = 0; w.cl_dirty[n_cl] = 1;
+        w.cl_center[n_cl] = -1;
+        if (k > SMALL_K) w.big_list[n_big++] = n_cl;
         n_cl++; total += k;
     }
-    w.hdr[H_NG] = ng; w.hdr[H_NCL] = n_cl; w.hdr[H_TOTAL] = total;
+    w.hdr[H_NG] = ng; w.hdr[H_NCL] = n_cl; w.hdr[H_TOTAL] = total; w.hdr[H_NBIG] = n_big;
     if (long_bin) w.hdr[H_FLAG] |= 2;
 }
-// unclustered list + off-centre removal (the clusters are visited in list order)
-__device__ void seq_remove(int n, DeepW &w)
+// members of one small cluster in the iteration order of its HashSet<Integer> (filled in key order); returns 1 when a bin reached 9 entries
+__device__ __forceinline__ int small_jdk_order(const int *in, int k, int *out)
 {
-    int nu = 0, n_removed = 0;
+    const int cap = dp_jdk_cap(k);
+    int o = 0, long_bin = 0;
+    for (int b = 0; b < cap; b++) {
+        int c = 0;
+        for (int i = 0; i < k; i++) if ((int)(dp_spread((unsigned)in[i]) & (unsigned)(cap - 1)) == b) { out[o++] = in[i]; c++; }
+        if (c >= 9) long_bin = 1;
+    }
+    return long_bin;
+}
+// G3 (parallel): member lists, HashSet order, OneUmiCluster (IntOpenHashSet) order of every new cluster; SKIPPED flags of the dropped groups
+template <int CS, int SM_INTS>
+__device__ void groups_build(slr_umi_assign_rec *rec, DeepW &w, int *smem)
+{
+    const int nk = w.hdr[H_NK], n_cl = w.hdr[H_NCL], q0 = w.hdr[H_Q0], n_big = w.hdr[H_NBIG];
+    const int tid = Team<CS>::tid(), T = Team<CS>::size();
+    for (int p = tid; p < nk; p += T) {                                 // flagDontUMIassignRecords (ClusterOneBase.java:L57, L71)
+        const int e = w.ck[p];
+        if (w.grp_q[e] == -2) {
+            const int k = w.gcount[e], x = w.keys[p];
+            rec[x].flags |= SLR_UA_SKIPPED; rec[x].cluster_size = (uint16_t)(k > 65535 ? 65535 : k);
+        }
+    }
+    int long_bin = 0;
+    for (int q = q0 + tid; q < n_cl; q += T) {                          // small clusters: one thread each, tables in local memory
+        const int k = w.cl_len0[q];
+        if (k > SMALL_K) continue;
+        const int e = w.cl_entry[q], base = w.cl_beg[q];
+        int arr[SMALL_K], ord[SMALL_K], tab[32];
+        int c = 0;
+        for (int p = w.firstpos[e]; c < k; p++) if (w.ck[p] == e) arr[c++] = w.keys[p];
+        long_bin |= small_jdk_order(arr, k, ord);
+        int *tp, hz;
+        const int tn = fu_fill(ord, k, tab, tab, &tp, &hz);
+        fu_iter(tp, tn, hz, arr);
+        for (int i = 0; i < k; i++) { w.mem[base + i] = ord[i]; w.it[base + i] = arr[i]; w.pos_cl[base + i] = q; w.clid[ord[i]] = q; }
+    }
+    // big clusters: one CTA each (its first thread walks the tables, which live in shared memory when they fit; clusters whose tables need the
+    // job's single global pair all go to CTA 0)
+    const int n_ctas = T / DEEP_THREADS, cta = Team<CS>::rank();
+    for (int bi = 0; bi < n_big; bi++) {
+        const int q = w.big_list[bi], k = w.cl_len0[q];
+        const bool sm = fits_smem<SM_INTS>(k);
+        if ((sm ? bi % n_ctas : 0) != cta) continue;
+        const int e = w.cl_entry[q], base = w.cl_beg[q];
+        if (threadIdx.x == 0) {
+            int c = 0;
+            for (int p = w.firstpos[e]; c < k; p++) if (w.ck[p] == e) w.gm[base + c++] = w.keys[p];
+            const TabBufs tb = bufs_for<SM_INTS>(k, smem, w);
+            jdk_order(reinterpret_cast<const unsigned *>(w.gm + base), k, w.pscr + base, tb.cnt, &long_bin);
+            for (int i = 0; i < k; i++) w.mem[base + i] = w.gm[base + w.pscr[base + i]];
+            int *tp, hz;
+            const int tn = fu_fill_into_a(w.mem + base, k, tb, &tp, &hz);
+            fu_iter(tp, tn, hz, w.it + base);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < k; i += DEEP_THREADS) { w.pos_cl[base + i] = q; w.clid[w.mem[base + i]] = q; }
+        __syncthreads();
+    }
+    if (long_bin) atomicOr(&w.hdr[H_FLAG], 2);
+}
+
+// ---- off-centre removal ----------------------------------------------------------------------------------------------------------------------------
+// R1 (leader): the unclustered reads in ascending order, then room for the removed ones cluster by cluster (list order)
+__device__ void remove_layout(int n, DeepW &w)
+{
+    int nu = 0, n_removed = 0, n_big = 0;
     for (int d = 0; d < n; d++) if (w.clid[d] < 0) w.idx[nu++] = d;
     const int n_cl = w.hdr[H_NCL];
     for (int c = 0; c < n_cl; c++) {
-        w.cl_dirty[c] = 0;
-        if (w.cl_nvict[c] == 0) continue;
-        const int b = w.cl_beg[c], k = w.cl_len[c];
-        for (int q = 0; q < k; q++) { const int x = w.it[b + q]; if (w.victim[x]) { w.idx[nu++] = x; w.clid[x] = -1; n_removed++; } }
-        int *tab, hz, *alt;
-        int tn = fu_fill(w.mem + b, k, w.tabA, w.tabB, &tab, &hz), size = k;
-        alt = tab == w.tabA ? w.tabB : w.tabA;
-        fu_remove_all(&tab, &alt, &tn, &size, &hz, w.victim, w.wrapped);
-        const int k2 = fu_iter(tab, tn, hz, w.it + b);
-        for (int q = 0; q < k; q++) w.victim[w.mem[b + q]] = 0;
-        w.cl_len[c] = k2; w.cl_dirty[c] = 1; w.cl_nvict[c] = 0;
+        const int v = w.cl_nvict[c];
+        w.cl_dirty[c] = v > 0;
+        if (!v) continue;
+        w.rem_off[c] = nu; nu += v; n_removed += v;
+        if (w.cl_len[c] > SMALL_K) w.big_list[n_big++] = c;
     }
-    w.hdr[H_NU] = nu; w.hdr[H_NREM] = n_removed;
+    w.hdr[H_NU] = nu; w.hdr[H_NREM] = n_removed; w.hdr[H_NBIG] = n_big;
+}
+// R2 (parallel over the clusters that lose members): OneUmiCluster.removeEntries (OneUmiCluster.java:L114-L119)
+template <int CS, int SM_INTS>
+__device__ void remove_apply(DeepW &w, int *smem)
+{
+    const int n_cl = w.hdr[H_NCL], n_big = w.hdr[H_NBIG];
+    const int tid = Team<CS>::tid(), T = Team<CS>::size();
+    for (int c = tid; c < n_cl; c += T) {
+        const int k = w.cl_len[c];
+        if (w.cl_nvict[c] == 0 || k > SMALL_K) continue;
+        const int base = w.cl_beg[c];
+        int arr[SMALL_K], tab[32], wrapped[SMALL_K];
+        for (int i = 0; i < k; i++) arr[i] = w.mem[base + i];
+        int *tp, hz, *alt = tab, tn, size = k, o = w.rem_off[c];
+        tn = fu_fill(arr, k, tab, tab, &tp, &hz);
+        fu_iter(tp, tn, hz, arr);
+        for (int i = 0; i < k; i++) if (w.victim[arr[i]]) { w.idx[o++] = arr[i]; w.clid[arr[i]] = -1; }
+        fu_remove_all(&tp, &alt, &tn, &size, &hz, w.victim, wrapped);
+        const int k2 = fu_iter(tp, tn, hz, w.it + base);
+        for (int i = 0; i < k; i++) w.victim[arr[i]] = 0;
+        w.cl_len[c] = k2; w.cl_nvict[c] = 0;
+    }
+    const int n_ctas = T / DEEP_THREADS, cta = Team<CS>::rank();
+    for (int bi = 0; bi < n_big; bi++) {
+        const int c = w.big_list[bi], k = w.cl_len[c];
+        const bool sm = fits_smem<SM_INTS>(k);
+        if ((sm ? bi % n_ctas : 0) != cta) continue;
+        const int base = w.cl_beg[c];
+        if (threadIdx.x == 0) {
+            int o = w.rem_off[c];
+            for (int i = 0; i < k; i++) { const int x = w.it[base + i]; if (w.victim[x]) { w.idx[o++] = x; w.clid[x] = -1; } }
+            const TabBufs tb = bufs_for<SM_INTS>(k, smem, w);
+            int *tp, hz, tn, size = k;
+            tn = fu_fill_into_a(w.mem + base, k, tb, &tp, &hz);
+            int *alt = tp == tb.A ? tb.B : tb.A;
+            fu_remove_all(&tp, &alt, &tn, &size, &hz, w.victim, w.pscr + base);
+            w.cl_len[c] = fu_iter(tp, tn, hz, w.it + base);
+            w.cl_nvict[c] = 0;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < k; i += DEEP_THREADS) w.victim[w.mem[base + i]] = 0;
+        __syncthreads();
+    }
 }
 
-template <int CS>
-__device__ void deep_job(const int32_t *__restrict__ M, int n, const slr_umi_assign_params P, int qv01, slr_umi_assign_rec *__restrict__ rec, int *W)
+template <int CS, int SM_INTS>
+__device__ void cluster_local_round(const int32_t *__restrict__ M, int n, int round, const slr_umi_assign_params &P, int qv01,
+                                    slr_umi_assign_rec *__restrict__ rec, DeepW &w, int *smem)
+{
+    const bool leader = Team<CS>::tid() == 0;
+    const int tid = Team<CS>::tid(), T = Team<CS>::size();
+    const int *idx = round == 1 ? nullptr : w.idx, *inU = round == 1 ? nullptr : w.inU;
+    const int L = round == 1 ? n : w.hdr[H_NU];
+    const int sb = round == 1 ? 0 : 8;
+    DEEP_STAMP(w, sb + 0);
+    pass_counts<CS>(M, n, P.ed_complete, idx, L, inU, w);
+    for (int i = tid; i < n; i += T) { w.firstpos[i] = 0x7FFFFFFF; w.gcount[i] = 0; w.gsum[i] = 0; w.grp_q[i] = -1; }
+    Team<CS>::sync();
+    DEEP_STAMP(w, sb + 1);
+    if (leader) seq_keys<SM_INTS>(idx, L, w, smem);
+    Team<CS>::sync();
+    DEEP_STAMP(w, sb + 2);
+    if (w.hdr[H_NK] == 0) return;
+    unsigned long long *best64 = reinterpret_cast<unsigned long long *>(w.gm);      // 2 (n + 2) words, free until groups_build
+    pass_choose_prepare<CS>(w, best64);
+    Team<CS>::sync();
+    pass_choose_sweep<CS, false>(M, n, P.ed_complete, inU, w, best64);
+    Team<CS>::sync();
+    pass_choose_sweep<CS, true>(M, n, P.ed_complete, inU, w, best64);
+    Team<CS>::sync();
+    DEEP_STAMP(w, sb + 3);
+    groups_scan<CS>(w);
+    Team<CS>::sync();
+    groups_first<CS>(w);
+    Team<CS>::sync();
+    DEEP_STAMP(w, sb + 4);
+    if (leader) groups_layout<SM_INTS>(round, P.fold_depth, w, smem);
+    Team<CS>::sync();
+    DEEP_STAMP(w, sb + 5);
+    groups_build<CS, SM_INTS>(rec, w, smem);
+    Team<CS>::sync();
+    DEEP_STAMP(w, sb + 6);
+    pass_sumsq<CS>(M, n, w);
+    Team<CS>::sync();
+    pass_centers<CS>(qv01, w);
+    Team<CS>::sync();
+    DEEP_STAMP(w, sb + 7);
+}
+
+template <int CS, int SM_INTS>
+__device__ void deep_job(const int32_t *__restrict__ M, int n, const slr_umi_assign_params P, int qv01, slr_umi_assign_rec *__restrict__ rec, int *W,
+                         int *smem)
 {
     DeepW w;
     carve(W, n, w);
@@ -416,51 +697,31 @@ __device__ void deep_job(const int32_t *__restrict__ M, int n, const slr_umi_ass
     for (int i = tid; i < n; i += T) { w.clid[i] = -1; w.victim[i] = 0; w.cnt[i] = 0; w.chosen[i] = -1; }
     if (leader) for (int i = 0; i < H_WORDS; i++) w.hdr[i] = 0;
     Team<CS>::sync();
-    // ---- round 1: clusterLocal over all reads
-    pass_counts<CS>(M, n, ed, nullptr, n, nullptr, w);
-    Team<CS>::sync();
-    if (leader) seq_keys(n, nullptr, n, w);
-    Team<CS>::sync();
-    if (w.hdr[H_NK] > 0) {
-        pass_choose<CS>(M, n, ed, nullptr, w);
-        Team<CS>::sync();
-        if (leader) seq_groups(n, 1, P.fold_depth, rec, w);
-        Team<CS>::sync();
-        pass_sumsq<CS>(M, n, w);
-        Team<CS>::sync();
-        pass_centers<CS>(qv01, w);
-        Team<CS>::sync();
+    cluster_local_round<CS, SM_INTS>(M, n, 1, P, qv01, rec, w, smem);     // clusterLocal over all reads, depth rule, centres
+    if (w.hdr[H_NCL] > 0) {
         pass_victims<CS>(M, n, ed, w);
         Team<CS>::sync();
-        if (leader) seq_remove(n, w);
+        if (leader) remove_layout(n, w);
         Team<CS>::sync();
         if (w.hdr[H_NREM] > 0) {
+            remove_apply<CS, SM_INTS>(w, smem);
+            Team<CS>::sync();
             pass_sumsq<CS>(M, n, w);
             Team<CS>::sync();
             pass_centers<CS>(qv01, w);
-            // ---- round 2: clusterLocal over the unclustered reads
+            // clusterLocal over the unclustered reads
             const int nu = w.hdr[H_NU];
             for (int i = tid; i < n; i += T) { w.inU[i] = 0; w.cnt[i] = 0; }
             Team<CS>::sync();
             for (int i = tid; i < nu; i += T) w.inU[w.idx[i]] = 1;
-            if (leader) { const int ncl = w.hdr[H_NCL]; for (int c = 0; c < ncl; c++) w.cl_dirty[c] = 0; w.hdr[H_ROUND2_FIRST] = ncl; }
+            const int ncl = w.hdr[H_NCL];
+            for (int c = tid; c < ncl; c += T) w.cl_dirty[c] = 0;
             Team<CS>::sync();
-            pass_counts<CS>(M, n, ed, w.idx, nu, w.inU, w);
-            Team<CS>::sync();
-            if (leader) seq_keys(n, w.idx, nu, w);
-            Team<CS>::sync();
-            if (w.hdr[H_NK] > 0) {
-                pass_choose<CS>(M, n, ed, w.inU, w);
-                Team<CS>::sync();
-                if (leader) seq_groups(n, 2, P.fold_depth, rec, w);
-                Team<CS>::sync();
-                pass_sumsq<CS>(M, n, w);
-                Team<CS>::sync();
-                pass_centers<CS>(qv01, w);
-            }
+            cluster_local_round<CS, SM_INTS>(M, n, 2, P, qv01, rec, w, smem);
         }
         Team<CS>::sync();
         // ---- per cluster: mean shift against the centre and the number of members within ED of it (L126-L139)
+        DEEP_STAMP(w, 14);
         const int n_cl = w.hdr[H_NCL];
         for (int c = warp; c < n_cl; c += n_warps) {
             const int m = w.cl_len[c], b = w.cl_beg[c], center = w.cl_center[c];
@@ -490,7 +751,19 @@ __device__ void deep_job(const int32_t *__restrict__ M, int n, const slr_umi_ass
             int best = 127;
             if (n_cl > 1) {
                 const int32_t *row = M + (size_t)x * n;
-                for (int y = lane; y < n; y += 32) if (w.clid[y] != c) { const int e = dp_ed(row[y]); best = e < best ? e : best; }
+                for (int y0 = 0; y0 < n; y0 += 32 * DU) {
+                    int32_t v[DU];
+                    int cl[DU];
+#pragma unroll
+                    for (int u = 0; u < DU; u++) {
+                        const int y = y0 + u * 32 + lane;
+                        v[u] = y < n ? __ldg(row + y) : 0x7F;
+                        cl[u] = y < n ? w.clid[y] : c;
+                    }
+#pragma unroll
+                    for (int u = 0; u < DU; u++)
+                        if (cl[u] != c) { const int e = dp_ed(v[u]); best = e < best ? e : best; }
+                }
                 best = __reduce_min_sync(FULLM, best);
             }
             if (lane == 0) {
@@ -506,24 +779,29 @@ __device__ void deep_job(const int32_t *__restrict__ M, int n, const slr_umi_ass
     const int n_cl = w.hdr[H_NCL], flag = w.hdr[H_FLAG];
     for (int i = tid; i < n; i += T) { rec[i].n_clusters = n_cl; if (flag) rec[i].flags |= SLR_UA_TIE_UNPIN; }
     Team<CS>::sync();
+    DEEP_STAMP(w, 15);
 }
 
-template <int CS>
+template <int CS, int SM_INTS>
 __global__ void __launch_bounds__(DEEP_THREADS) umi_assign_deep_kernel(const int32_t *__restrict__ mat, const long long *__restrict__ joff,
                                                                        const long long *__restrict__ ooff, const slr_umi_assign_params P,
                                                                        const uint8_t *__restrict__ job_qv01, slr_umi_assign_rec *__restrict__ rec,
                                                                        const int32_t *__restrict__ list, const long long *__restrict__ list_off,
                                                                        const unsigned int *__restrict__ count, int *__restrict__ scratch)
 {
+    extern __shared__ int deep_smem[];
     const unsigned int total = *count;
-    const unsigned int team = blockIdx.x / CS, n_teams = gridDim.x / CS;
+    const unsigned int team = CS == 0 ? 0 : blockIdx.x / (CS == 0 ? 1 : CS), n_teams = CS == 0 ? 1 : gridDim.x / (CS == 0 ? 1 : CS);
     for (unsigned int k = team; k < total; k += n_teams) {
         const long long j = list[k];
         const long long r0 = joff[j];
         const int n = (int)(joff[j + 1] - r0);
-        deep_job<CS>(mat + ooff[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0, scratch + list_off[k]);
+        if ((CS == 8 && n > SLR_UA_DEEP_MEDIUM) || (CS == 0 && n <= SLR_UA_DEEP_MEDIUM)) continue;      // the two big classes share one list
+        deep_job<CS, SM_INTS>(mat + ooff[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0, scratch + list_off[k], deep_smem);
     }
 }
+
+constexpr int SM_SMALL = 3 * 1024, SM_BIG = 48 * 1024;     // words of dynamic shared memory of the one-CTA / multi-CTA teams
 
 }  // namespace
 
@@ -537,20 +815,33 @@ cudaError_t slr_launch_umi_assign_deep(const int32_t *d_mat, const long long *d_
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(umi_assign_deep_kernel<8, SM_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BIG * 4);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(umi_assign_deep_kernel<0, SM_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BIG * 4);
+    });
+    if (attr_err != cudaSuccess) return attr_err;
     long long gs = max_jobs < (long long)sms * 2 ? max_jobs : (long long)sms * 2;
     if (gs < 1) gs = 1;
-    umi_assign_deep_kernel<1><<<(unsigned)gs, DEEP_THREADS, 0, stream>>>(d_mat, d_job_offsets, d_out_offsets, P, d_job_qv01, d_rec, d_list_small,
-                                                                         d_off_small, d_count_small, d_words);
+    umi_assign_deep_kernel<1, SM_SMALL><<<(unsigned)gs, DEEP_THREADS, SM_SMALL * 4, stream>>>(d_mat, d_job_offsets, d_out_offsets, P, d_job_qv01, d_rec,
+                                                                                           d_list_small, d_off_small, d_count_small, d_words);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     long long teams = max_jobs < (long long)sms / 8 ? max_jobs : (long long)sms / 8;
     if (teams < 1) teams = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(teams * 8)); cfg.blockDim = dim3(DEEP_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cfg.gridDim = dim3((unsigned)(teams * 8)); cfg.blockDim = dim3(DEEP_THREADS); cfg.dynamicSmemBytes = SM_BIG * 4; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, umi_assign_deep_kernel<8>, d_mat, d_job_offsets, d_out_offsets, P, d_job_qv01, d_rec, d_list_big, d_off_big,
-                              d_count_big, d_words);
+    e = cudaLaunchKernelEx(&cfg, umi_assign_deep_kernel<8, SM_BIG>, d_mat, d_job_offsets, d_out_offsets, P, d_job_qv01, d_rec, d_list_big, d_off_big,
+                           d_count_big, d_words);
+    if (e != cudaSuccess) return e;
+    // giant jobs (above SLR_UA_DEEP_MEDIUM reads): one after the other on the whole GPU, grid-wide barriers between the phases
+    void *args[] = {(void *)&d_mat, (void *)&d_job_offsets, (void *)&d_out_offsets, (void *)&P, (void *)&d_job_qv01, (void *)&d_rec,
+                    (void *)&d_list_big, (void *)&d_off_big, (void *)&d_count_big, (void *)&d_words};
+    return cudaLaunchCooperativeKernel((const void *)umi_assign_deep_kernel<0, SM_BIG>, dim3((unsigned)sms), dim3(DEEP_THREADS), args, SM_BIG * 4, stream);
 }
