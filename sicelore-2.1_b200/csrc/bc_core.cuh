@@ -205,15 +205,27 @@ SLR_HD uint32_t slr_probe_eval(const SlrTableDev &t, const SlrExpand &e, const u
     const uint32_t csg0 = (e.cs >> (24 - 8 * g)) & 0xFFu;
     const uint32_t nx = (g < 3) ? ((e.cs >> (22 - 8 * g)) & 3u) : e.cbase;
     const bool fix3 = op == 2 && !(e.nopost && g == 3);          // a deletion pins digit 3 (unless every appended base is tried)
+    const uint32_t want = (0x80u | pr.tag) * 0x01010101u;
+#if SLR_NIBBLE_FILTER
+    // the two alternatives are kept nibble-disjoint — leading digits (high nibble) as the node's, or trailing digits (low nibble) as the op
+    // shifts them: SUB the node's, INS the node's digits 1,2, DEL the node's digit 3 and the digit after the group — so that ONE masked XOR and
+    // one zero-NIBBLE test per word answer both (a DEL keeps only its last two digits of the old three-digit test: weaker, still necessary)
+    const uint32_t mB = (op == 2 && !fix3) ? 0x0Cu : 0x0Fu;
+    const uint32_t vB = (op == 0) ? (csg0 & 0x0Fu) : ((op == 1) ? ((csg0 >> 2) & 0x0Fu) : (((csg0 & 3u) << 2) | (fix3 ? nx : 0u)));
+    const uint32_t M4 = (0xF0u | mB) * 0x01010101u, V4 = ((csg0 & 0xF0u) | vB) * 0x01010101u;
+#define SLR_PAT_OK(bw, tw) (slr_nibble_ok(((bw) ^ V4) & M4) & slr_eq_bytes((tw), want))
+    uint32_t match = (SLR_PAT_OK(k.b.x, k.a.x) >> 7) | (SLR_PAT_OK(k.b.y, k.a.y) >> 6) | (SLR_PAT_OK(k.b.z, k.a.z) >> 5) | (SLR_PAT_OK(k.b.w, k.a.w) >> 4);
+#undef SLR_PAT_OK
+#else
     const uint32_t mA = fix3 ? 0xF3u : 0xF0u, vA = (csg0 & 0xF0u) | (fix3 ? nx : 0u);
     const uint32_t mB = (op == 2) ? (fix3 ? 0x3Fu : 0x3Cu) : 0x0Fu;
     const uint32_t vB = (op == 0) ? (csg0 & 0x0Fu) : ((op == 1) ? ((csg0 >> 2) & 0x0Fu) : (((csg0 & 0x0Fu) << 2) | (fix3 ? nx : 0u)));
     const uint32_t mA4 = mA * 0x01010101u, vA4 = vA * 0x01010101u, mB4 = mB * 0x01010101u, vB4 = vB * 0x01010101u;
-    const uint32_t want = (0x80u | pr.tag) * 0x01010101u;
     uint32_t match = ((slr_eq_bytes(k.a.x, want) & (slr_eq_bytes(k.b.x & mA4, vA4) | slr_eq_bytes(k.b.x & mB4, vB4))) >> 7) |
                      ((slr_eq_bytes(k.a.y, want) & (slr_eq_bytes(k.b.y & mA4, vA4) | slr_eq_bytes(k.b.y & mB4, vB4))) >> 6) |
                      ((slr_eq_bytes(k.a.z, want) & (slr_eq_bytes(k.b.z & mA4, vA4) | slr_eq_bytes(k.b.z & mB4, vB4))) >> 5) |
                      ((slr_eq_bytes(k.a.w, want) & (slr_eq_bytes(k.b.w & mA4, vA4) | slr_eq_bytes(k.b.w & mB4, vB4))) >> 4);
+#endif
     uint32_t best = SLR_NONE32;
     while (match) {
         const int b = slr_ffs(match) - 1;

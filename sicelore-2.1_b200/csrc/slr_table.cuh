@@ -155,6 +155,15 @@ SLR_HD uint32_t slr_eq_bytes(uint32_t x, uint32_t want)
     const uint32_t h = x ^ want;
     return ~(((h & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | h) & 0x80808080u;
 }
+// bit 7 of every byte of the result set <=> the high OR the low nibble of that byte of h is zero (exact, carry-free per nibble)
+#ifndef SLR_NIBBLE_FILTER
+#define SLR_NIBBLE_FILTER 1
+#endif
+SLR_HD uint32_t slr_nibble_ok(uint32_t h)
+{
+    const uint32_t z = ~(((h & 0x77777777u) + 0x77777777u) | h) & 0x88888888u;
+    return z | (z << 4);
+}
 // Bit 8*byte + word of the result set  <=>  slot 4*word + byte (byte `byte` of tag word `word`) is valid and
 // carries `tag` (the four per-word byte masks are interleaved with four shifts; the order of the set bits is
 // irrelevant to the callers, which take a minimum over all matches).

@@ -148,8 +148,11 @@ __device__ __noinline__ void ua_fastutil_order_big(const uint8_t *in, int k, uin
 }
 
 // single link (unreachable with the reference's thresholds: 3000 > 100): pairs by (cost, i, j), merged while cost <= cut; one lane
+#ifndef UA_NI
+#define UA_NI
+#endif
 template <int MAXN>
-__device__ void ua_single_link(UaShared<MAXN> &S, int m, int cut)
+__device__ UA_NI void ua_single_link(UaShared<MAXN> &S, int m, int cut)
 {
     for (int a = 0; a < m; a++) S.tmp[0][a] = (uint8_t)a;            // root of every leaf
     for (int s = 0; s <= cut; s++)
@@ -165,7 +168,7 @@ __device__ void ua_single_link(UaShared<MAXN> &S, int m, int cut)
 
 // is the threshold graph a disjoint union of cliques?  (only then is the partition the same for every merge order)  Returns true when NOT.
 template <int MAXN>
-__device__ bool ua_not_cluster_graph(const UaShared<MAXN> &S, int m, int cut, int lane)
+__device__ UA_NI bool ua_not_cluster_graph(const UaShared<MAXN> &S, int m, int cut, int lane)
 {
     bool bad = false;
     for (int a = lane; a < m && !bad; a += 32) {

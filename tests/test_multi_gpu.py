@@ -40,6 +40,12 @@ def test_multi_matches_single_device_and_oracle(pkg, orc, ctx):
     assert mg.umi_cluster(umis, offs, 2).tobytes() == orc.umi_cluster_batch(em, offs, oo, 2).tobytes()
     m, moo = mg.umi_dist(umis, offs)
     assert (m == em).all() and (moo == oo).all()
+    # jobs above 100 reads (ClusterOne_MyClustering on every device: each shard sizes its own arena)
+    du, doff = pkg.synth_umi_jobs(60, mean=150.0, cap=700, seed=12)
+    dm, doo = orc.umi_matrix_batch(du, doff)
+    drec = mg.umi_assign(du, doff)
+    assert drec.tobytes() == orc.umi_assign_batch(dm, doff, doo).tobytes()
+    assert int(((drec["flags"] & 9) == 9).sum()) > 1000
     if n_dev > 1:
         assert mg.peer_access                                # NVSwitch box: the counter reduction reads the peers' HBM directly
     mg.close()

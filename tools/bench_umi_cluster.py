@@ -126,7 +126,8 @@ peak = float(json.load(open(peaks_path)).get("hbm_gbs", 6550.0)) if os.path.exis
 ach = alg / (ms / 1e3) / 1e9
 pairs = int(((np.diff(offs) * (np.diff(offs) - 1)) // 2).sum())
 from bench import issue_roofline
-roof, _ = issue_roofline(pkg, "umi_pairs_kernel@umi_cluster_bench" if (a.jobs, a.deep) == (10_000_000, 20_000) else "umi_pairs_kernel(no profile for these sizes)", m, ms_dist, clocks.get("sm_mhz"), torch.cuda.get_device_properties(0).multi_processor_count)
+roof, _ = issue_roofline(pkg, "umi_pairs_kernel/pair", int(((np.diff(offs) * (np.diff(offs) - 1)) // 2).sum()), ms_dist, clocks.get("sm_mhz"),
+                         torch.cuda.get_device_properties(0).multi_processor_count, unit="pair")
 print(json.dumps({
     "metric": "reads/sec UMI distance matrices + neighbour-set clustering (ED %d)" % a.ed, "value": m / (ms / 1e3), "unit": "reads/s", "n_gpus": 1,
     "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "u32", "data": "synthetic",

@@ -20,8 +20,8 @@ RUNS = [
     ("umi_pairs_kernel", "umi_pairs_kernel", 4_000_000, ["tools/perf_assign.py", "4000000", "4", "2000", "1"], "4 M reads in jobs of mean 4"),
     ("umi_assign_kernel", "umi_assign_kernel", 4_000_000, ["tools/perf_assign.py", "4000000", "4", "2000", "1"], "4 M reads in jobs of mean 4"),
     # the side benches: units = what their own JSON line reports (roofline.units_per_launch)
-    ("umi_pairs_kernel@umi_cluster_bench", "umi_pairs_kernel", None, ["tools/bench_umi_cluster.py", "--steps", "1", "--warmup", "0", "--cpu-jobs", "1000"],
-     "tools/bench_umi_cluster.py defaults: 10 M jobs of mean 4 + one 20 000-read job"),
+    # the same kernel per READ PAIR (units = pairs of the run, from the script's own JSON line): what tools/bench_umi_cluster.py scales by
+    ("umi_pairs_kernel/pair", "umi_pairs_kernel", "pairs", ["tools/perf_assign.py", "2000000", "12", "2000", "1"], "2 M reads in jobs of mean 12, per read pair"),
     ("guided_match_kernel<umi,2>", "guided_match_kernel", None, ["tools/bench_guided.py", "--flavour", "umi", "--ed", "2", "--steps", "1", "--warmup", "1", "--cpu-sample", "64"],
      "tools/bench_guided.py defaults, UMI flavour, ED 2"),
     ("guided_match_kernel<bc,2>", "guided_match_kernel", None, ["tools/bench_guided.py", "--flavour", "bc", "--ed", "2", "--steps", "1", "--warmup", "1", "--cpu-sample", "64"],
@@ -38,6 +38,15 @@ for key, rx, units, cmd, what in RUNS:
         print("timeout:", key, cmd, file=sys.stderr)
         continue
     lines = [l for l in r.stdout.splitlines() if l.startswith('"')]
+    if units == "pairs":
+        units = None
+        for l in r.stdout.splitlines():
+            if l.startswith("{") and '"cells"' in l:
+                d = json.loads(l)
+                units = (int(d["cells"]) - int(d["reads"])) // 2
+        if not units:
+            print("no JSON line from", cmd, r.stdout[-300:], r.stderr[-300:], file=sys.stderr)
+            continue
     if units is None:
         for l in r.stdout.splitlines():
             if l.startswith("{") and "units_per_launch" in l:
