@@ -98,6 +98,18 @@ int main(int argc, char **argv)
         for (int64_t i = 0; i < m; i++) keys += exp[i].best_key >= 0;
         printf("umi_cluster: %lld jobs, %lld reads, ED %lld, %lld keys: %s\n", (long long)n_jobs, (long long)m, (long long)ed, (long long)keys,
                bad ? "MISMATCH" : "OK");
+    } else if (kind == 7) {                              /* clustering + UMI assignment (S6): small jobs and jobs above 100 reads in one call */
+        const int64_t umi_len = rd64(f), n_jobs = rd64(f), m = rd64(f);
+        uint8_t *umis = rd(f, (size_t)m * 16);
+        int64_t *joff = rd(f, (size_t)(n_jobs + 1) * 8);
+        uint8_t *qv = rd(f, (size_t)n_jobs);
+        slr_umi_assign_rec *exp = rd(f, (size_t)m * sizeof(slr_umi_assign_rec)), *got = malloc((size_t)m * sizeof(slr_umi_assign_rec) + 1);
+        CHECK(slr_umi_assign(ctx, umis, 16, (int)umi_len, joff, n_jobs, NULL, qv, NULL, NULL, got));
+        bad = memcmp(got, exp, (size_t)m * sizeof(slr_umi_assign_rec)) != 0;
+        int64_t assigned = 0, deep = 0;
+        for (int64_t i = 0; i < m; i++) { assigned += exp[i].flags & SLR_UA_ASSIGNED; deep += (exp[i].flags & SLR_UA_DEEP) != 0; }
+        printf("umi_assign: %lld jobs, %lld reads (%lld in jobs above 100 reads), %lld assigned: %s\n", (long long)n_jobs, (long long)m, (long long)deep,
+               (long long)assigned, bad ? "MISMATCH" : "OK");
     } else if (kind == 5) {
         const int64_t L = rd64(f), bc = rd64(f), pm = rd64(f), post_len = rd64(f), bailout = rd64(f), slice_len = rd64(f), raw_cap = rd64(f);
         const int64_t n_groups = rd64(f), n_keys = rd64(f), n_all = rd64(f), n_empty = rd64(f), n = rd64(f);

@@ -95,6 +95,16 @@ def write_driver_file(path, kind, arrays):
             f.write(np.int64(a).tobytes() if np.isscalar(a) or isinstance(a, (int, np.integer)) else np.ascontiguousarray(a).tobytes())
 
 
+def pkg_synth_assign_batch():
+    import numpy as np
+    """400 jobs of mean 6 and three jobs above 100 reads (the synthetic UMI generator needs no GPU)"""
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    u1, o1 = pkg.synth_umi_jobs(400, mean=6.0, cap=90, seed=3)
+    u2, o2 = pkg.synth_umi_jobs(3, mean=1e9, cap=180, seed=9)
+    return np.concatenate([u1, u2]), np.concatenate([o1, o1[-1] + o2[1:]]).astype(np.int64)
+
+
 def driver_inputs(tmp_path, orc):
     import numpy as np
     gold = os.path.join(ROOT, "tests", "golden")
@@ -115,6 +125,11 @@ def driver_inputs(tmp_path, orc):
     crec = orc.umi_cluster_batch(u["matrix"], u["job_offsets"], u["out_offsets"], 2)
     files.append(write_driver_file(tmp_path / "cluster.bin", 6, [int(u["umi_len"]), len(u["job_offsets"]) - 1, len(u["umis"]), len(u["matrix"]), 2,
                                                                u["umis"], u["job_offsets"], u["out_offsets"], u["matrix"], crec]) or tmp_path / "cluster.bin")
+    au, aoff = pkg_synth_assign_batch()
+    am, aoo = orc.umi_matrix_batch(au, aoff)
+    aqv = (np.arange(len(aoff) - 1) % 2).astype(np.uint8)
+    arec = orc.umi_assign_batch(am, aoff, aoo, None, aqv)
+    files.append(write_driver_file(tmp_path / "assign.bin", 7, [12, len(aoff) - 1, len(au), au, aoff, aqv, arec]) or tmp_path / "assign.bin")
     for name in ("guided_umi_ed2", "guided_bc_mixed"):
         z = np.load(os.path.join(gold, name + ".npz"))
         raw = z["raw"].view(orc.GUIDED_HIT).reshape(len(z["slices"]), -1)
