@@ -411,7 +411,9 @@ __device__ void ua_job(UaShared<MAXN> &S, const int32_t *__restrict__ mat, int n
 __global__ void __launch_bounds__(256) umi_assign_init(const long long *__restrict__ joff, long long n_jobs, long long n_reads,
                                                         const int32_t *__restrict__ rowjob, int max_hier, slr_umi_assign_rec *__restrict__ rec,
                                                         int32_t *__restrict__ lists, unsigned int *__restrict__ counts,
-                                                        long long *__restrict__ deep_off, long long deep_cap_words)
+                                                        long long *__restrict__ deep_off, long long deep_cap_words,
+                                                        const int32_t *__restrict__ mat, const long long *__restrict__ ooff,
+                                                        const slr_umi_assign_params P, const uint8_t *__restrict__ job_qv01)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
@@ -437,6 +439,23 @@ __global__ void __launch_bounds__(256) umi_assign_init(const long long *__restri
                         lists[(long long)cls * n_jobs + k] = (int32_t)j;
                         deep_off[(long long)(cls - 2) * n_jobs + k] = off;
                     }
+                }
+            } else if (n == 2) {
+                // a job of two reads (a quarter of all jobs that have anything to cluster) needs no warp: one pair, no ties, the HashSet and
+                // fastutil orders of {0, 1} are (0, 1); each of its two reads writes its own record
+                const int32_t *M = mat + ooff[j];
+                const int32_t m01 = M[1], m10 = M[2];
+                const int edc = P.ed_complete, e01 = (int)(int8_t)(m01 & 0xFF), e10 = (int)(int8_t)(m10 & 0xFF);
+                const int nn = (e01 <= edc) + (e10 <= edc);                       // reads with a neighbour (DistanceMatrix.java:L87-L90)
+                const int cut = nn > P.single_threshold ? P.ed_single : edc;
+                if (nn == 2 && e01 <= cut) {
+                    if (2 * P.fold_depth > 2) {
+                        const int center = (job_qv01 && job_qv01[j]) ? 0 : 1, x = (int)(r - r0);
+                        const int32_t cell = M[center * 2 + x];
+                        d.center = center; d.flags = SLR_UA_ASSIGNED; d.cluster_size = 2; d.n_clusters = 1;
+                        d.offset_center_mean = (int8_t)ua_pos1_offset(M[center * 2 + (1 - center)]);
+                        d.u1 = (int8_t)(int)(int8_t)(cell & 0xFF); d.pos2 = (int8_t)ua_pos2_code(cell);
+                    } else { d.flags = SLR_UA_SKIPPED; d.cluster_size = 2; }
                 }
             } else if (r == r0 && n >= 2) {
                 const int cls = n <= 32 ? 0 : 1;
@@ -493,7 +512,8 @@ cudaError_t slr_launch_umi_assign(const int32_t *d_mat, const long long *d_job_o
     if (g0 > (long long)sms * 16) g0 = (long long)sms * 16;
     slr_umi_assign_params Q = P;
     if (Q.max_hier > 100) Q.max_hier = 100;
-    umi_assign_init<<<(unsigned)g0, 256, 0, stream>>>(d_job_offsets, n_jobs, n_reads, d_rowjob, Q.max_hier, d_rec, lists, counts, deep_off, deep_cap);
+    umi_assign_init<<<(unsigned)g0, 256, 0, stream>>>(d_job_offsets, n_jobs, n_reads, d_rowjob, Q.max_hier, d_rec, lists, counts, deep_off, deep_cap, d_mat,
+                                                        d_out_offsets, Q, d_job_qv01);
     // persistent grids, one wave; warps without a job return at once
     long long gs = (n_jobs + 7) / 8;
     if (gs > (long long)sms * 6) gs = (long long)sms * 6;
