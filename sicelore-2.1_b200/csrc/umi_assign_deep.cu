@@ -430,25 +430,195 @@ __device__ int fu_fill_into_a(const int *in, int k, const TabBufs &tb, int **tab
     return (g & 1) ? fu_fill(in, k, tb.B, tb.A, tab_out, has_zero) : fu_fill(in, k, tb.A, tb.B, tab_out, has_zero);
 }
 
+// ---- the same table, filled by a whole CTA --------------------------------------------------------------------------------------------------
+// Linear probing is first-come-first-served: a key ends in the first slot at or after its home that no EARLIER key holds.  That fixed point is
+// reached from any schedule in which a slot always goes to the earliest key that asked for it, so all keys probe at once: atomicMin of the
+// insertion time per slot, losers step on, until nobody moves (as many rounds as the longest probe run).  Growth is replayed stage by stage: a
+// rehash re-inserts the old table from its last slot to its first, i.e. the old keys get the times T_old - 1 - slot, the keys that follow keep
+// their insertion order behind them.  own: the table (>= final size words), pos / tim: k words each.  Returns the table size; the table then
+// holds the keys (0 = empty).  Collective over the CTA.
+__device__ int fu_fill_par(const int *in, int k, int *own, int *pos, int *tim, int *has_zero)
+{
+    __shared__ int s_moved, s_zero;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_zero = -1;
+    __syncthreads();
+    for (int i = tid; i < k; i += DEEP_THREADS) if (in[i] == 0) s_zero = i;
+    __syncthreads();
+    const int zero_idx = s_zero;
+    int T = 32, done = 0, Tprev = 0;
+    for (;;) {
+        const int mf = dp_max_fill(T), n_end = k < mf + 1 ? k : mf + 1, mask = T - 1;
+        for (int i = tid; i < n_end; i += DEEP_THREADS) {
+            if (i == zero_idx) continue;
+            tim[i] = i < done ? Tprev - 1 - pos[i] : Tprev + i;
+            pos[i] = (int)(dp_mix(in[i]) & (uint32_t)mask);
+        }
+        for (int j = tid; j < T; j += DEEP_THREADS) own[j] = 0x7FFFFFFF;
+        __syncthreads();
+        for (;;) {
+            if (tid == 0) s_moved = 0;
+            __syncthreads();
+            int moved = 0;
+            for (int i = tid; i < n_end; i += DEEP_THREADS) {
+                if (i == zero_idx) continue;
+                const int t = tim[i];
+                int p = pos[i];
+                if (own[p] == t) continue;                              // holds its slot (so far)
+                for (;;) {                                              // a slot claimed by an earlier key stays with an earlier key: step on at once
+                    const int old = atomicMin(&own[p], t);
+                    if (old >= t) break;
+                    p = (p + 1) & mask;
+                }
+                pos[i] = p;
+                moved = 1;
+            }
+            if (moved) s_moved = 1;
+            __syncthreads();
+            const int again = s_moved;
+            __syncthreads();
+            if (!again) break;
+        }
+        done = n_end;
+        if (n_end == k && k <= mf) break;                               // the last insert did not trigger a rehash
+        Tprev = T;
+        T = dp_array_size(n_end + 1);                                   // if (size++ >= maxFill) rehash(arraySize(size + 1, f))
+    }
+    for (int j = tid; j < T; j += DEEP_THREADS) own[j] = 0;
+    __syncthreads();
+    for (int i = tid; i < k; i += DEEP_THREADS) if (i != zero_idx) own[pos[i]] = in[i];
+    __syncthreads();
+    *has_zero = zero_idx >= 0;
+    return T;
+}
+// iteration order of a table (key 0 first, then the slots from the last to the first), by a whole CTA; returns the number of keys
+__device__ int fu_iter_par(const int *tab, int T, int has_zero, int *out)
+{
+    __shared__ int s_cnt[DEEP_THREADS + 1];
+    const int tid = threadIdx.x, per = (T + DEEP_THREADS - 1) / DEEP_THREADS;
+    const int hi = T - 1 - tid * per, lo = hi - per + 1 < 0 ? 0 : hi - per + 1;      // thread 0 owns the last slots
+    int c = 0;
+    for (int j = hi; j >= lo; j--) c += tab[j] != 0;
+    s_cnt[tid] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = has_zero ? 1 : 0;
+        if (has_zero) out[0] = 0;
+        for (int t = 0; t < DEEP_THREADS; t++) { const int v = s_cnt[t]; s_cnt[t] = acc; acc += v; }
+        s_cnt[DEEP_THREADS] = acc;
+    }
+    __syncthreads();
+    int o = s_cnt[tid];
+    for (int j = hi; j >= lo; j--) if (tab[j] != 0) out[o++] = tab[j];
+    const int total = s_cnt[DEEP_THREADS];
+    __syncthreads();
+    return total;
+}
+// ordered compaction by a whole CTA: out = (val(i) for i in 0 .. n - 1 if pred(i)), returns the count; every thread owns a contiguous piece
+template <typename P, typename V>
+__device__ int compact_par(int n, P pred, V val, int *out)
+{
+    __shared__ int s_c[DEEP_THREADS + 1];
+    const int tid = threadIdx.x, per = (n + DEEP_THREADS - 1) / DEEP_THREADS, lo = tid * per, hi = lo + per < n ? lo + per : n;
+    int c = 0;
+    for (int i = lo; i < hi; i++) c += pred(i) ? 1 : 0;
+    s_c[tid] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int t = 0; t < DEEP_THREADS; t++) { const int v = s_c[t]; s_c[t] = acc; acc += v; }
+        s_c[DEEP_THREADS] = acc;
+    }
+    __syncthreads();
+    int o = s_c[tid];
+    for (int i = lo; i < hi; i++) if (pred(i)) out[o++] = val(i);
+    const int total = s_c[DEEP_THREADS];
+    __syncthreads();
+    return total;
+}
+// ConcurrentHashMap order by a CTA: the 16 bins of the initial table never mix (a transfer sends bin i to i and i + capacity), so 16 threads
+// replay one sixteenth of the map each, in the keys' global order (the transfers are triggered by the global count).  Tables, links and hashes
+// live in shared memory: F + F / 2 + 2 K words (F = final capacity); returns false when that does not fit.  out_idx: K words of scratch.
+template <int SM_INTS>
+__device__ bool chm_order_par(const int *keys, int K, int *out, int *out_idx, int *smem, int *long_bin)
+{
+    int F = 16, doublings = 0;
+    while (K >= F - (F >> 2)) { F <<= 1; doublings++; }
+    if (F + F / 2 + 2 * K > SM_INTS) return false;
+    int *A = smem, *B = smem + F, *nxt = smem + F + F / 2;
+    unsigned *hsh = reinterpret_cast<unsigned *>(nxt + K);
+    __shared__ int s_long;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < K; t += DEEP_THREADS) { hsh[t] = dp_spread((unsigned)keys[t]) & 0x7FFFFFFFu; nxt[t] = -1; }
+    if (tid == 0) s_long = 0;
+    __syncthreads();
+    if (tid < 16) {
+        const int r = tid;
+        int cap = 16, sc = 12, lb = 0;
+        int *head = (doublings & 1) ? B : A, *alt = (doublings & 1) ? A : B;      // the final table lands in A
+        head[r] = -1;
+        for (int t = 0; t < K; t++) {
+            const unsigned h = hsh[t];
+            if ((int)(h & 15u) == r) {
+                const int b = (int)(h & (unsigned)(cap - 1));
+                int len = 0, last = -1;
+                for (int p = head[b]; p >= 0; p = nxt[p]) { last = p; len++; }
+                if (len >= 8) lb = 1;
+                if (last < 0) head[b] = t; else nxt[last] = t;
+            }
+            while (t + 1 >= sc) {                                       // addCount -> transfer (this thread's bins: i = r mod 16)
+                for (int i = r; i < cap; i += 16) {
+                    const int f = head[i];
+                    int ln = -1, hn = -1;
+                    if (f >= 0) {
+                        unsigned run_bit = hsh[f] & (unsigned)cap;
+                        int last_run = f;
+                        for (int p = nxt[f]; p >= 0; p = nxt[p]) { const unsigned bb = hsh[p] & (unsigned)cap; if (bb != run_bit) { run_bit = bb; last_run = p; } }
+                        if (run_bit == 0) ln = last_run; else hn = last_run;
+                        for (int p = f; p != last_run;) {
+                            const int pn = nxt[p];
+                            if ((hsh[p] & (unsigned)cap) == 0) { nxt[p] = ln; ln = p; } else { nxt[p] = hn; hn = p; }
+                            p = pn;
+                        }
+                    }
+                    alt[i] = ln; alt[i + cap] = hn;
+                }
+                int *tsw = head; head = alt; alt = tsw;
+                cap *= 2; sc = cap - (cap >> 2);
+            }
+        }
+        if (lb) s_long = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int o = 0;
+        for (int i = 0; i < F; i++) for (int p = A[i]; p >= 0; p = nxt[p]) out_idx[o++] = p;
+        if (s_long) *long_bin = 1;
+    }
+    __syncthreads();
+    for (int t = tid; t < K; t += DEEP_THREADS) out[t] = keys[out_idx[t]];
+    __syncthreads();
+    return true;
+}
+constexpr int PAR_MIN = 192;                   // below this many keys one thread is faster than the CTA's barriers
+
 // ---- keys of clusterLocal in the iteration order of the Int2ObjectOpenHashMap (team leader) ---------------------------------------------------
 template <int SM_INTS>
-__device__ void seq_keys(const int *idx, int L, DeepW &w, int *smem)
+__device__ void seq_keys(const int *idx, int L, DeepW &w, int *smem)     // collective over the team's first CTA
 {
-    int nk = 0;
-    for (int i0 = 0; i0 < L; i0 += 16) {
-        int a[16], c[16];
-#pragma unroll
-        for (int u = 0; u < 16; u++) a[u] = i0 + u < L ? (idx ? idx[i0 + u] : i0 + u) : -1;
-#pragma unroll
-        for (int u = 0; u < 16; u++) c[u] = a[u] >= 0 ? w.cnt[a[u]] : 0;
-#pragma unroll
-        for (int u = 0; u < 16; u++) if (c[u] > 1) w.tmp[nk++] = a[u];
-    }
+    const int nk = compact_par(L, [&](int i) { return w.cnt[idx ? idx[i] : i] > 1; }, [&](int i) { return idx ? idx[i] : i; }, w.tmp);
+    if (threadIdx.x == 0) w.hdr[H_NK] = nk;
     const TabBufs tb = bufs_for<SM_INTS>(nk, smem, w);
-    int *tab, hz;
-    const int tn = fu_fill_into_a(w.tmp, nk, tb, &tab, &hz);
-    fu_iter(tab, tn, hz, w.keys);
-    w.hdr[H_NK] = nk;
+    if (nk >= PAR_MIN) {
+        int hz;
+        const int tn = fu_fill_par(w.tmp, nk, tb.A, w.first, w.corder, &hz);
+        fu_iter_par(tb.A, tn, hz, w.keys);
+    } else if (threadIdx.x == 0) {
+        int *tab, hz;
+        const int tn = fu_fill_into_a(w.tmp, nk, tb, &tab, &hz);
+        fu_iter(tab, tn, hz, w.keys);
+    }
+    __syncthreads();
 }
 
 // ---- groups of the keys by their chosen entry -> clusters appended to the job's list ------------------------------------------------------------
@@ -471,50 +641,58 @@ __device__ void groups_first(DeepW &w)
     const int nk = w.hdr[H_NK];
     for (int p = Team<CS>::tid(); p < nk; p += Team<CS>::size()) w.isfirst[p] = w.firstpos[w.ck[p]] == p;
 }
-// G2 (leader): the groups in first-seen order -> ConcurrentHashMap order -> HashSet<Set<Integer>> order -> cluster slots.  round 1 applies the
+// G2 (the team's first CTA; its first thread after the compaction): the groups in first-seen order -> ConcurrentHashMap order -> HashSet<Set<Integer>> order -> cluster slots.  round 1 applies the
 // depth rule (L77-L84), round 2 keeps the groups of more than one read (L109)
 template <int SM_INTS>
 __device__ void groups_layout(int round, int fold_depth, DeepW &w, int *smem)
 {
     const int nk = w.hdr[H_NK];
-    int ng = 0, long_bin = 0;
-    for (int p0 = 0; p0 < nk; p0 += 16) {
-        int f[16], e[16];
-#pragma unroll
-        for (int u = 0; u < 16; u++) { f[u] = p0 + u < nk ? w.isfirst[p0 + u] : 0; e[u] = p0 + u < nk ? w.ck[p0 + u] : 0; }
-#pragma unroll
-        for (int u = 0; u < 16; u++) if (f[u]) w.first[ng++] = e[u];
+    const int ng = compact_par(nk, [&](int p) { return w.isfirst[p] != 0; }, [&](int p) { return w.ck[p]; }, w.first);
+    __shared__ int s_long, s_maxdepth;
+    if (threadIdx.x == 0) { s_long = 0; s_maxdepth = 0; }
+    __syncthreads();
+    int lb = 0;
+    if (!chm_order_par<SM_INTS>(w.first, ng, w.corder, w.perm, smem, &lb)) {
+        if (threadIdx.x == 0) chm_order(w.first, ng, w.corder, w.chmA, w.chmB, w.chm_nxt, w.chm_h, &lb);
+        __syncthreads();
     }
-    int chm_cap = 16;
-    while (ng >= chm_cap - (chm_cap >> 2)) chm_cap <<= 1;              // the map's final table
-    if (2 * chm_cap <= SM_INTS) chm_order(w.first, ng, w.corder, smem, smem + chm_cap, w.chm_nxt, w.chm_h, &long_bin);
-    else chm_order(w.first, ng, w.corder, w.chmA, w.chmB, w.chm_nxt, w.chm_h, &long_bin);
-    int maxdepth = 0;
-    for (int t0 = 0; t0 < ng; t0 += 8) {
-        int e[8], k[8];
-        unsigned h[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) e[u] = t0 + u < ng ? w.corder[t0 + u] : -1;
-#pragma unroll
-        for (int u = 0; u < 8; u++) { k[u] = e[u] >= 0 ? w.gcount[e[u]] : 0; h[u] = e[u] >= 0 ? w.gsum[e[u]] : 0; }
-#pragma unroll
-        for (int u = 0; u < 8; u++) if (e[u] >= 0) { w.ht[t0 + u] = h[u]; if (k[u] > maxdepth) maxdepth = k[u]; }
+    if (lb) s_long = 1;
+    int *gk = w.gm;                                                     // sizes of the groups in map order (gm is free until groups_build)
+    for (int t = threadIdx.x; t < ng; t += DEEP_THREADS) {
+        const int e = w.corder[t], k = w.gcount[e];
+        w.ht[t] = w.gsum[e];
+        gk[t] = k;
+        atomicMax(&s_maxdepth, k);
     }
-    jdk_order(w.ht, ng, w.perm, dp_jdk_cap(ng) + 1 <= SM_INTS ? smem : w.tabA, &long_bin);
+    __syncthreads();
+    if (threadIdx.x == 0) { int l2 = 0; jdk_order(w.ht, ng, w.perm, dp_jdk_cap(ng) + 1 <= SM_INTS ? smem : w.tabA, &l2); if (l2) s_long = 1; }
+    __syncthreads();
+    int *pe = w.gm + ng, *pk = w.pscr;                                   // entry and size of the groups in HashSet order, contiguous for the walk below
+    for (int t = threadIdx.x; t < ng; t += DEEP_THREADS) { const int g = w.perm[t]; pe[t] = w.corder[g]; pk[t] = gk[g]; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int maxdepth = s_maxdepth;
     int n_cl = w.hdr[H_NCL], total = w.hdr[H_TOTAL], n_big = 0;
     w.hdr[H_Q0] = n_cl;
-    for (int t = 0; t < ng; t++) {
-        const int e = w.corder[w.perm[t]], k = w.gcount[e];
-        if (round == 2 && k <= 1) { w.grp_q[e] = -1; continue; }
-        if (round == 1 && !((long long)k * fold_depth > maxdepth)) { w.grp_q[e] = -2; continue; }
-        w.grp_q[e] = n_cl;
-        w.cl_entry[n_cl] = e; w.cl_beg[n_cl] = total; w.cl_len0[n_cl] = k; w.cl_len[n_cl] = k; w.cl_nvict[n_cl] = 0; w.cl_dirty[n_cl] = 1;
-        w.cl_center[n_cl] = -1;
-        if (k > SMALL_K) w.big_list[n_big++] = n_cl;
-        n_cl++; total += k;
+    for (int t0 = 0; t0 < ng; t0 += 8) {
+        int ee[8], kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { ee[u] = t0 + u < ng ? pe[t0 + u] : 0; kk[u] = t0 + u < ng ? pk[t0 + u] : 0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (t0 + u >= ng) break;
+            const int e = ee[u], k = kk[u];
+            if (round == 2 && k <= 1) { w.grp_q[e] = -1; continue; }
+            if (round == 1 && !((long long)k * fold_depth > maxdepth)) { w.grp_q[e] = -2; continue; }
+            w.grp_q[e] = n_cl;
+            w.cl_entry[n_cl] = e; w.cl_beg[n_cl] = total; w.cl_len0[n_cl] = k; w.cl_len[n_cl] = k; w.cl_nvict[n_cl] = 0; w.cl_dirty[n_cl] = 1;
+            w.cl_center[n_cl] = -1;
+            if (k > SMALL_K) w.big_list[n_big++] = n_cl;
+            n_cl++; total += k;
+        }
     }
     w.hdr[H_NG] = ng; w.hdr[H_NCL] = n_cl; w.hdr[H_TOTAL] = total; w.hdr[H_NBIG] = n_big;
-    if (long_bin) w.hdr[H_FLAG] |= 2;
+    if (s_long) w.hdr[H_FLAG] |= 2;
 }
 // members of one small cluster in the iteration order of its HashSet<Integer> (filled in key order); returns 1 when a bin reached 9 entries
 __device__ __forceinline__ int small_jdk_order(const int *in, int k, int *out)
@@ -542,13 +720,21 @@ __device__ void groups_build(slr_umi_assign_rec *rec, DeepW &w, int *smem)
         }
     }
     int long_bin = 0;
-    for (int q = q0 + tid; q < n_cl; q += T) {                          // small clusters: one thread each, tables in local memory
+    const int n_ctas_s = T / DEEP_THREADS;                               // clusters dealt round-robin to the CTAs: every thread scans the key list
+    for (int qq = Team<CS>::rank() + n_ctas_s * (int)threadIdx.x; q0 + qq < n_cl; qq += T) {     // small clusters: one thread each, local tables
+        const int q = q0 + qq;
         const int k = w.cl_len0[q];
         if (k > SMALL_K) continue;
         const int e = w.cl_entry[q], base = w.cl_beg[q];
         int arr[SMALL_K], ord[SMALL_K], tab[32];
         int c = 0;
-        for (int p = w.firstpos[e]; c < k; p++) if (w.ck[p] == e) arr[c++] = w.keys[p];
+        for (int p0 = w.firstpos[e]; c < k; p0 += 8) {                  // 8 loads of the scan in flight (the exit test would serialise them)
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = p0 + u < nk ? w.ck[p0 + u] : -1;
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (v[u] == e && c < k) arr[c++] = w.keys[p0 + u];
+        }
         long_bin |= small_jdk_order(arr, k, ord);
         int *tp, hz;
         const int tn = fu_fill(ord, k, tab, tab, &tp, &hz);
@@ -565,15 +751,29 @@ __device__ void groups_build(slr_umi_assign_rec *rec, DeepW &w, int *smem)
         const int e = w.cl_entry[q], base = w.cl_beg[q];
         if (threadIdx.x == 0) {
             int c = 0;
-            for (int p = w.firstpos[e]; c < k; p++) if (w.ck[p] == e) w.gm[base + c++] = w.keys[p];
+            for (int p0 = w.firstpos[e]; c < k; p0 += 8) {
+                int v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = p0 + u < nk ? w.ck[p0 + u] : -1;
+#pragma unroll
+                for (int u = 0; u < 8; u++) if (v[u] == e && c < k) w.gm[base + c++] = w.keys[p0 + u];
+            }
             const TabBufs tb = bufs_for<SM_INTS>(k, smem, w);
             jdk_order(reinterpret_cast<const unsigned *>(w.gm + base), k, w.pscr + base, tb.cnt, &long_bin);
             for (int i = 0; i < k; i++) w.mem[base + i] = w.gm[base + w.pscr[base + i]];
-            int *tp, hz;
-            const int tn = fu_fill_into_a(w.mem + base, k, tb, &tp, &hz);
-            fu_iter(tp, tn, hz, w.it + base);
+            if (k < PAR_MIN) {
+                int *tp, hz;
+                const int tn = fu_fill_into_a(w.mem + base, k, tb, &tp, &hz);
+                fu_iter(tp, tn, hz, w.it + base);
+            }
         }
         __syncthreads();
+        if (k >= PAR_MIN) {
+            const TabBufs tb = bufs_for<SM_INTS>(k, smem, w);
+            int hz;
+            const int tn = fu_fill_par(w.mem + base, k, tb.A, w.gm + base, w.sumsq + base, &hz);
+            fu_iter_par(tb.A, tn, hz, w.it + base);
+        }
         for (int i = threadIdx.x; i < k; i += DEEP_THREADS) { w.pos_cl[base + i] = q; w.clid[w.mem[base + i]] = q; }
         __syncthreads();
     }
@@ -602,7 +802,7 @@ __device__ void remove_apply(DeepW &w, int *smem)
 {
     const int n_cl = w.hdr[H_NCL], n_big = w.hdr[H_NBIG];
     const int tid = Team<CS>::tid(), T = Team<CS>::size();
-    for (int c = tid; c < n_cl; c += T) {
+    for (int c = Team<CS>::rank() + (T / DEEP_THREADS) * (int)threadIdx.x; c < n_cl; c += T) {
         const int k = w.cl_len[c];
         if (w.cl_nvict[c] == 0 || k > SMALL_K) continue;
         const int base = w.cl_beg[c];
@@ -623,12 +823,19 @@ __device__ void remove_apply(DeepW &w, int *smem)
         const bool sm = fits_smem<SM_INTS>(k);
         if ((sm ? bi % n_ctas : 0) != cta) continue;
         const int base = w.cl_beg[c];
+        const TabBufs tb = bufs_for<SM_INTS>(k, smem, w);
+        __shared__ int s_tn, s_hz;
+        if (k >= PAR_MIN) {
+            int hz;
+            const int tn = fu_fill_par(w.mem + base, k, tb.A, w.gm + base, w.sumsq + base, &hz);
+            if (threadIdx.x == 0) { s_tn = tn; s_hz = hz; }
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
             int o = w.rem_off[c];
             for (int i = 0; i < k; i++) { const int x = w.it[base + i]; if (w.victim[x]) { w.idx[o++] = x; w.clid[x] = -1; } }
-            const TabBufs tb = bufs_for<SM_INTS>(k, smem, w);
-            int *tp, hz, tn, size = k;
-            tn = fu_fill_into_a(w.mem + base, k, tb, &tp, &hz);
+            int *tp = tb.A, hz = s_hz, tn = s_tn, size = k;
+            if (k < PAR_MIN) tn = fu_fill_into_a(w.mem + base, k, tb, &tp, &hz);
             int *alt = tp == tb.A ? tb.B : tb.A;
             fu_remove_all(&tp, &alt, &tn, &size, &hz, w.victim, w.pscr + base);
             w.cl_len[c] = fu_iter(tp, tn, hz, w.it + base);
@@ -654,7 +861,7 @@ __device__ void cluster_local_round(const int32_t *__restrict__ M, int n, int ro
     for (int i = tid; i < n; i += T) { w.firstpos[i] = 0x7FFFFFFF; w.gcount[i] = 0; w.gsum[i] = 0; w.grp_q[i] = -1; }
     Team<CS>::sync();
     DEEP_STAMP(w, sb + 1);
-    if (leader) seq_keys<SM_INTS>(idx, L, w, smem);
+    if (Team<CS>::rank() == 0) seq_keys<SM_INTS>(idx, L, w, smem);
     Team<CS>::sync();
     DEEP_STAMP(w, sb + 2);
     if (w.hdr[H_NK] == 0) return;
@@ -671,7 +878,7 @@ __device__ void cluster_local_round(const int32_t *__restrict__ M, int n, int ro
     groups_first<CS>(w);
     Team<CS>::sync();
     DEEP_STAMP(w, sb + 4);
-    if (leader) groups_layout<SM_INTS>(round, P.fold_depth, w, smem);
+    if (Team<CS>::rank() == 0) groups_layout<SM_INTS>(round, P.fold_depth, w, smem);
     Team<CS>::sync();
     DEEP_STAMP(w, sb + 5);
     groups_build<CS, SM_INTS>(rec, w, smem);

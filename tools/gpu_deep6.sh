@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests/test_umi_assign.py tests/test_ref_vectors.py -x -q -m gpu -k "deep or myclust" > gpurun_out/d6_tests.log 2>&1; tail -2 gpurun_out/d6_tests.log
+timeout 600 python tools/perf_deep.py 1000 20000 2>&1 | tee gpurun_out/d6_perf_deep.log
