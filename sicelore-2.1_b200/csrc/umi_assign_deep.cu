@@ -781,18 +781,28 @@ __device__ void groups_build(slr_umi_assign_rec *rec, DeepW &w, int *smem)
 }
 
 // ---- off-centre removal ----------------------------------------------------------------------------------------------------------------------------
-// R1 (leader): the unclustered reads in ascending order, then room for the removed ones cluster by cluster (list order)
+// R1 (the team's first CTA): the unclustered reads in ascending order, then room for the removed ones cluster by cluster (list order)
 __device__ void remove_layout(int n, DeepW &w)
 {
-    int nu = 0, n_removed = 0, n_big = 0;
-    for (int d = 0; d < n; d++) if (w.clid[d] < 0) w.idx[nu++] = d;
     const int n_cl = w.hdr[H_NCL];
-    for (int c = 0; c < n_cl; c++) {
-        const int v = w.cl_nvict[c];
-        w.cl_dirty[c] = v > 0;
-        if (!v) continue;
-        w.rem_off[c] = nu; nu += v; n_removed += v;
-        if (w.cl_len[c] > SMALL_K) w.big_list[n_big++] = c;
+    const int nu0 = compact_par(n, [&](int d) { return w.clid[d] < 0; }, [&](int d) { return d; }, w.idx);
+    // clusters that lose members, in list order (tmp is free here)
+    const int n_hit = compact_par(n_cl, [&](int c) { return w.cl_nvict[c] > 0; }, [&](int c) { return c; }, w.tmp);
+    for (int c = threadIdx.x; c < n_cl; c += DEEP_THREADS) w.cl_dirty[c] = w.cl_nvict[c] > 0;
+    if (threadIdx.x != 0) return;
+    int nu = nu0, n_removed = 0, n_big = 0;
+    for (int i0 = 0; i0 < n_hit; i0 += 8) {
+        int cc[8], vv[8], ll[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) cc[u] = i0 + u < n_hit ? w.tmp[i0 + u] : 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) { vv[u] = w.cl_nvict[cc[u]]; ll[u] = w.cl_len[cc[u]]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (i0 + u >= n_hit) break;
+            w.rem_off[cc[u]] = nu; nu += vv[u]; n_removed += vv[u];
+            if (ll[u] > SMALL_K) w.big_list[n_big++] = cc[u];
+        }
     }
     w.hdr[H_NU] = nu; w.hdr[H_NREM] = n_removed; w.hdr[H_NBIG] = n_big;
 }
@@ -908,7 +918,7 @@ __device__ void deep_job(const int32_t *__restrict__ M, int n, const slr_umi_ass
     if (w.hdr[H_NCL] > 0) {
         pass_victims<CS>(M, n, ed, w);
         Team<CS>::sync();
-        if (leader) remove_layout(n, w);
+        if (Team<CS>::rank() == 0) remove_layout(n, w);
         Team<CS>::sync();
         if (w.hdr[H_NREM] > 0) {
             remove_apply<CS, SM_INTS>(w, smem);
