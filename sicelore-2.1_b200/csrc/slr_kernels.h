@@ -35,8 +35,9 @@ constexpr int SLR_UMI_ASSIGN_DEEP_LAUNCHES = 3;
 constexpr int SLR_UA_DEEP_SMALL = 1024;        // deep jobs up to this size run on one CTA, up to SLR_UA_DEEP_MEDIUM on a cluster of 8 CTAs,
 constexpr int SLR_UA_DEEP_MEDIUM = 4096;       // larger ones on the whole GPU (cooperative grid), one job after the other
 size_t slr_umi_assign_scratch(long long n_jobs, long long deep_words);
-// 32-bit words of working arrays umi_assign_deep.cu needs for a job of n reads (kept in step with carve() there)
-SLR_HD long long slr_umi_assign_deep_words(long long n) { return (64 + 52 * (n + 4) + 2 * (3 * n + 64) + 2 * (4 * n + 64) + 1) & ~1ll; }
+// 32-bit words of working arrays umi_assign_deep.cu needs for a job of n reads (kept in step with carve() there): ~70 n words of lists and
+// hash tables + the n x n threshold bit matrix (n^2 / 32 words)
+SLR_HD long long slr_umi_assign_deep_words(long long n) { return (64 + 52 * (n + 4) + 2 * (3 * n + 64) + 2 * (4 * n + 64) + n * ((n + 31) / 32) + 1) & ~1ll; }
 cudaError_t slr_launch_umi_assign(const int32_t *d_mat, const long long *d_job_offsets, const long long *d_out_offsets, long long n_jobs,
                                   long long n_reads, const slr_umi_assign_params &P, const uint8_t *d_job_qv01, const int32_t *d_rowjob,
                                   slr_umi_assign_rec *d_rec, void *d_scratch, size_t scratch_bytes, cudaStream_t stream);

@@ -62,7 +62,7 @@ struct DeepW {
     int *cl_beg, *cl_len0, *cl_len, *cl_center, *cl_nvict, *cl_dirty, *cl_offmean, *cl_nf, *cl_entry, *rem_off, *big_list;
     int *clid, *victim, *idx, *inU, *tabA, *tabB, *wrapped, *chmA, *chmB, *chm_nxt;
     int *ck, *firstpos, *gcount, *isfirst, *grp_q;
-    unsigned *ht, *chm_h, *gsum;
+    unsigned *ht, *chm_h, *gsum, *adj;        // adj: n rows of (n + 31) / 32 words, bit j of row a = ED(matrix[a][j]) <= ed
     unsigned long long *sig;
 };
 __device__ inline void carve(int *W, int n, DeepW &w)
@@ -81,6 +81,7 @@ __device__ inline void carve(int *W, int n, DeepW &w)
     w.ht = reinterpret_cast<unsigned *>(take(s)); w.chm_h = reinterpret_cast<unsigned *>(take(s)); w.gsum = reinterpret_cast<unsigned *>(take(s));   // 3
     // 2 (sig) + 45 of the 52 (n + 2)-word units slr_umi_assign_deep_words() grants
     w.tabA = take(3 * n + 64); w.tabB = take(3 * n + 64); w.chmA = take(4 * n + 64); w.chmB = take(4 * n + 64);
+    w.adj = reinterpret_cast<unsigned *>(p);                       // n * ((n + 31) / 32) words, the last piece of the job's arena
 }
 
 // ---- team = 1 CTA or a cluster of CS CTAs ---------------------------------------------------------------------------------------------------
@@ -251,23 +252,37 @@ template <int CS>
 __device__ void pass_counts(const int32_t *__restrict__ M, int n, int ed, const int *idx, int L, const int *inU, DeepW &w)
 {
     const int lane = threadIdx.x & 31, warp = Team<CS>::tid() >> 5, n_warps = Team<CS>::size() >> 5;
+    const int W = (n + 31) >> 5;
     for (int i = warp; i < L; i += n_warps) {
         const int a = idx ? idx[i] : i;
-        const int32_t *row = M + (size_t)a * n;
+        unsigned *arow = w.adj + (size_t)a * W;
         int c = 0;
         unsigned long long s = 0;
-        for (int j0 = 0; j0 < n; j0 += 32 * DU) {
-            int32_t v[DU];
-            int in[DU];
+        if (!inU) {
+            // round 1: one pass over the packed row; the threshold test is kept as one bit per cell — the entry choice (two sweeps over
+            // keys x reads) and round 2 then move 1/32 of the bytes, and the bit matrix of a 20 000-read job (50 MB) stays in L2
+            const int32_t *row = M + (size_t)a * n;
+            for (int j0 = 0; j0 < n; j0 += 32 * DU) {
+                int32_t v[DU];
 #pragma unroll
-            for (int u = 0; u < DU; u++) {
-                const int j = j0 + u * 32 + lane;
-                v[u] = j < n ? __ldg(row + j) : 0x7F;
-                in[u] = (j < n && inU) ? inU[j] : 1;
+                for (int u = 0; u < DU; u++) { const int j = j0 + u * 32 + lane; v[u] = j < n ? __ldg(row + j) : 0x7F; }
+#pragma unroll
+                for (int u = 0; u < DU; u++) {
+                    const bool hit = dp_ed(v[u]) <= ed;
+                    const unsigned bits = __ballot_sync(FULLM, hit);
+                    if (j0 + u * 32 < n && lane == 0) arow[(j0 >> 5) + u] = bits;
+                    if (hit) { c++; s += dp_sig(j0 + u * 32 + lane); }
+                }
             }
-#pragma unroll
-            for (int u = 0; u < DU; u++)
-                if (in[u] && dp_ed(v[u]) <= ed) { c++; s += dp_sig(j0 + u * 32 + lane); }
+        } else {
+            for (int wd = lane; wd < W; wd += 32) {
+                unsigned bits = arow[wd];
+                while (bits) {
+                    const int j = (wd << 5) + __ffs((int)bits) - 1;
+                    bits &= bits - 1;
+                    if (inU[j]) { c++; s += dp_sig(j); }
+                }
+            }
         }
         c = __reduce_add_sync(FULLM, c);
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
@@ -306,17 +321,18 @@ __device__ void pass_choose_sweep(const int32_t *__restrict__ M, int n, int ed, 
             bestcnt = (int)(b >> 32); bestp = (int)(0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFu));
             bestsig = ksig[bestp];
         }
+        const int W = (n + 31) >> 5, cw = c >> 5, cb = c & 31;
         for (int p0 = p_lo; p0 < p_hi; p0 += DU) {
             int e[DU];
-            int32_t v[DU];
+            unsigned v[DU];
 #pragma unroll
             for (int u = 0; u < DU; u++) {
                 e[u] = p0 + u < p_hi ? w.keys[p0 + u] : -1;
-                v[u] = e[u] >= 0 ? __ldg(M + (size_t)e[u] * n + c) : 0x7F;
+                v[u] = e[u] >= 0 ? w.adj[(size_t)e[u] * W + cw] : 0u;     // matrix[e][c] <= ed (L195: entries whose neighbour set contains c)
             }
 #pragma unroll
             for (int u = 0; u < DU; u++) {
-                if (e[u] < 0 || dp_ed(v[u]) > ed) continue;
+                if (e[u] < 0 || !((v[u] >> cb) & 1u)) continue;
                 const int ce = w.ck[p0 + u];
                 if (SECOND) { if (ce == bestcnt && ksig[p0 + u] != bestsig) harmful = 1; }
                 else if (ce > bestcnt) { bestcnt = ce; bestp = p0 + u; }
