@@ -282,7 +282,8 @@ int  slr_umi_assign(slr_ctx *ctx, const uint8_t *umis, int stride, int umi_len, 
 /* the same on matrices already on the device (as slr_umi_dist_dev left them); d_scratch: slr_umi_assign_scratch_bytes(n_jobs) bytes.
  * slr_umi_assign_dev has no room for the working arrays of the jobs above max_hier: they are only flagged SLR_UA_DEEP.  slr_umi_assign_dev2 takes
  * scratch_bytes = slr_umi_assign_scratch_bytes(n_jobs) + the sum of slr_umi_assign_deep_job_bytes(n) over the jobs above max_hier (any upper
- * bound will do; a deep job that does not fit is left flagged, n_clusters 0, never half-written). */
+ * bound will do; a deep job that does not fit is left flagged, n_clusters 0, never half-written).  slr_umi_assign_deep_job_bytes(n) is about
+ * 300 n + n * n / 8 bytes: lists and hash tables of the emulated containers + one threshold bit per matrix cell. */
 int64_t slr_umi_assign_scratch_bytes(int64_t n_jobs);
 int64_t slr_umi_assign_deep_job_bytes(int64_t n_reads_of_job);
 int  slr_umi_assign_dev(slr_ctx *ctx, const int32_t *d_matrices, const int64_t *d_job_offsets, const int64_t *d_out_offsets, int64_t n_jobs,

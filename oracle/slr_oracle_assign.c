@@ -470,11 +470,17 @@ static int my_cluster_local(const int32_t *matrix, int n, const int *idx, int L,
 {
     int *cnt = (int *)calloc((size_t)n, sizeof(int)), *keys_in = (int *)malloc((size_t)L * sizeof(int)), nk = 0;
     uint64_t *sig = (uint64_t *)calloc((size_t)n, sizeof(uint64_t));
+    /* (a giant job is handed over outside the batch's parallel loop, orc_umi_assign_batch: its two O(L^2) passes then use all threads) */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (L > 1500)
+#endif
     for (int i = 0; i < L; i++) {                                                       /* L179-L184 */
         const int a = idx[i];
-        for (int j = 0; j < L; j++) if (ed_of(matrix[(size_t)a * n + idx[j]]) <= ed) { cnt[a]++; sig[a] += sig_mix(idx[j]); }
-        if (cnt[a] > 1) keys_in[nk++] = a;
+        int c = 0; uint64_t sg = 0;
+        for (int j = 0; j < L; j++) if (ed_of(matrix[(size_t)a * n + idx[j]]) <= ed) { c++; sg += sig_mix(idx[j]); }
+        cnt[a] = c; sig[a] = sg;
     }
+    for (int i = 0; i < L; i++) if (cnt[idx[i]] > 1) keys_in[nk++] = idx[i];
     if (nk == 0) { free(cnt); free(keys_in); free(sig); return 0; }
     int *keys = (int *)malloc((size_t)nk * sizeof(int));
     {                                                                                   /* Int2ObjectOpenHashMap: same layout and iteration as the set */
@@ -483,13 +489,18 @@ static int my_cluster_local(const int32_t *matrix, int n, const int *idx, int L,
         fu_order(&m, keys); free(m.key);
     }
     int *chosen = (int *)malloc((size_t)nk * sizeof(int));
+    int harm = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(|:harm) if (nk > 1500)
+#endif
     for (int i = 0; i < nk; i++) {                                                      /* L190-L196 */
         const int c = keys[i];
         int best = -1;
         for (int j = 0; j < nk; j++) { const int e = keys[j]; if (ed_of(matrix[(size_t)e * n + c]) <= ed && (best < 0 || cnt[e] > cnt[best])) best = e; }
-        for (int j = 0; j < nk; j++) { const int e = keys[j]; if (ed_of(matrix[(size_t)e * n + c]) <= ed && cnt[e] == cnt[best] && sig[e] != sig[best]) *harmful = 1; }
+        for (int j = 0; j < nk; j++) { const int e = keys[j]; if (ed_of(matrix[(size_t)e * n + c]) <= ed && cnt[e] == cnt[best] && sig[e] != sig[best]) harm |= 1; }
         chosen[i] = best;
     }
+    if (harm) *harmful = 1;
     /* L199: groups in first-seen order, members in key order */
     int *gid = (int *)malloc((size_t)n * sizeof(int)), *first = (int *)malloc((size_t)nk * sizeof(int)), ng = 0;
     for (int i = 0; i < n; i++) gid[i] = -1;
@@ -615,8 +626,8 @@ void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, c
     for (int64_t j = 0; j < n_jobs; j++) {
         const int64_t r0 = job_offsets[j], n = job_offsets[j + 1] - r0;
         if (n > P->max_hier && P->deep) {                                                /* UmiClustering.java:L240: ClusterOne_MyClustering's job */
-            orc_umi_assign_myclust(matrices + out_offsets[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0);
-            continue;
+            if (n <= 1500) orc_umi_assign_myclust(matrices + out_offsets[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0);
+            continue;                                                                    /* giant jobs: below, one at a time with all threads inside */
         }
         if (n > P->max_hier) {
             for (int64_t i = 0; i < n; i++) { memset(&rec[r0 + i], 0, sizeof(rec[0])); rec[r0 + i].center = -1; rec[r0 + i].u2 = -1; rec[r0 + i].flags = ORC_UA_DEEP; }
@@ -624,4 +635,9 @@ void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, c
         }
         orc_umi_assign_hier(matrices + out_offsets[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0);
     }
+    if (P->deep)
+        for (int64_t j = 0; j < n_jobs; j++) {
+            const int64_t r0 = job_offsets[j], n = job_offsets[j + 1] - r0;
+            if (n > P->max_hier && n > 1500) orc_umi_assign_myclust(matrices + out_offsets[j], n, P, job_qv01 ? job_qv01[j] : 0, rec + r0);
+        }
 }

@@ -660,7 +660,7 @@ def test_gpu_cluster_one_hierarchical_matches_reference_bytecode(pkg, ctx):
 def test_cluster_one_myclustering_matches_reference_bytecode(orc):
     """ClusterOne_MyClustering.call as a whole — clusterLocal on the full set, the depth rule, OneUmiCluster.setClusterCenter, the off-centre removal
     (removeEntries -> the fastutil iterator's backward-shift deletion -> re-centring), the second clusterLocal over the unclustered reads and
-    setSamflagsAndStatsForClustered — run from the reference's own class files (oracle/make_ref_myclust.py, sequential streams) on 40 jobs of
+    setSamflagsAndStatsForClustered — run from the reference's own class files (oracle/make_ref_myclust.py, sequential streams) on 72 jobs of
     20 ... 330 reads: the C oracle reproduces every value the bytecode wrote"""
     z = np.load(os.path.join(GOLDEN, "ref_myclust.npz"))
     off, oo = z["job_offsets"], z["out_offsets"]
@@ -673,7 +673,7 @@ def test_cluster_one_myclustering_matches_reference_bytecode(orc):
         assert (rec["flags"] & 8).all()                       # ORC_UA_DEEP marks the records of ClusterOne_MyClustering
         return rec
     stats = _check_hier(z, rec_of_job)
-    assert stats[2] >= 40 and stats[0] > 4000 and stats[1] > 0, stats
+    assert stats[2] >= 72 and stats[0] > 9000 and stats[1] > 0, stats
 
 
 @pytest.mark.gpu
@@ -704,4 +704,4 @@ def test_gpu_cluster_one_myclustering_matches_reference_bytecode(pkg, ctx):
         for k, j in enumerate(js):
             recs[j] = got[so[k]:so[k + 1]]
     stats = _check_hier(z, lambda j: recs[j])
-    assert stats[2] >= 40 and stats[0] > 4000, stats
+    assert stats[2] >= 72 and stats[0] > 9000, stats
