@@ -36,7 +36,12 @@ def run(umis, offs, label):
         print("   dbg stamps (us, relative to stamp 4):", [(int(x) - int(hdr[4])) / 1e3 if x > 0 else None for x in dbg[:4]], "stamp5:", (int(hdr[5]) - int(hdr[4])) / 1e3)
         seq = [(i, int(hdr[i])) for i in range(16) if hdr[i] > 0]
         print("   phases (us):", ", ".join("%s %.0f" % (names[a], (tb - ta) / 1e3) for (a, ta), (b, tb) in zip(seq, seq[1:])), flush=True)
-    print(json.dumps({"what": label, "reads": m, "jobs": nj, "assign_ms": min(ts), "assigned": int((rec["flags"] & 1 != 0).sum()),
+    parity = None
+    if m <= 30000:                                             # the CPU oracle on the same matrices (its O(n^2) passes use all host threads)
+        from oracle import orc
+        want = orc.umi_assign_batch(d_m.cpu().numpy(), offs, oo)
+        parity = bool(want.tobytes() == rec.tobytes())
+    print(json.dumps({"what": label, "reads": m, "jobs": nj, "parity": parity, "assign_ms": min(ts), "assigned": int((rec["flags"] & 1 != 0).sum()),
                       "clusters": int(rec["n_clusters"][0]), "tie_unpin": bool(rec["flags"][0] & 4), "scratch_MB": nb / 1e6}), flush=True)
 
 
