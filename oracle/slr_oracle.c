@@ -713,7 +713,25 @@ void orc_umi_matrix_batch(const uint8_t *umis, int stride, int umi_len, const in
 #endif
     for (int64_t j = 0; j < n_jobs; j++) {
         int64_t s = job_offsets[j], n = job_offsets[j + 1] - s;
-        orc_umi_matrix(umis + s * stride, stride, umi_len, n, out + out_offsets[j]);
+        if (n <= 1500) orc_umi_matrix(umis + s * stride, stride, umi_len, n, out + out_offsets[j]);
+    }
+    /* giant jobs one at a time, their rows over all threads (a 20 000-read job is 2 x 10^8 pairs: minutes on one core) */
+    for (int64_t j = 0; j < n_jobs; j++) {
+        const int64_t s = job_offsets[j], n = job_offsets[j + 1] - s;
+        if (n <= 1500) continue;
+        const uint8_t *u = umis + s * stride;
+        int32_t *o = out + out_offsets[j];
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8)
+#endif
+        for (int64_t i = 0; i < n; i++) {
+            o[i * n + i] = orc_umi_equality();
+            for (int64_t v = i + 1; v < n; v++) {
+                const int32_t e = orc_umi_best9(u + i * stride, u + v * stride, umi_len);
+                o[i * n + v] = e;
+                o[v * n + i] = orc_umi_transpose(e);
+            }
+        }
     }
 }
 
