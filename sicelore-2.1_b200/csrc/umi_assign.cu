@@ -457,6 +457,66 @@ __global__ void __launch_bounds__(256) umi_assign_init(const long long *__restri
                         d.u1 = (int8_t)(int)(int8_t)(cell & 0xFF); d.pos2 = (int8_t)ua_pos2_code(cell);
                     } else { d.flags = SLR_UA_SKIPPED; d.cluster_size = 2; }
                 }
+            } else if (n == 3 && 3 <= P.single_threshold) {
+                // three reads, complete link: three pairs in the queue (least cost first, among equals the pair offered last: (1,2), (0,2), (0,1)),
+                // at most two merges, and the only pair a merge creates has no rival, so no tie can matter.  HashSet order of any subset of
+                // {0, 1, 2} is ascending; fastutil iterates key 0 first, then slot 28 (key 2) before slot 14 (key 1).
+                const int32_t *M = mat + ooff[j];
+                const int edc = P.ed_complete, x = (int)(r - r0);
+                int e[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int b = 0; b < 3; b++) e[a][b] = (int)(int8_t)(M[a * 3 + b] & 0xFF);
+                const bool nb0 = e[0][1] <= edc || e[0][2] <= edc, nb1 = e[1][0] <= edc || e[1][2] <= edc, nb2 = e[2][0] <= edc || e[2][1] <= edc;
+                const int m = (int)nb0 + (int)nb1 + (int)nb2;
+                unsigned members = 0;                                            // bit i = read i is in THE cluster (there is at most one)
+                if (m == 2) {
+                    const int a = nb0 ? 0 : 1, b = nb2 ? 2 : 1;
+                    if (e[a][b] <= edc) members = (1u << a) | (1u << b);
+                } else if (m == 3) {
+                    const int d01 = e[0][1], d02 = e[0][2], d12 = e[1][2];
+                    int fa, fb, fz, fd;                                          // first poll: least cost, the largest pair id among equals
+                    if (d12 <= d02 && d12 <= d01) { fa = 1; fb = 2; fz = 0; fd = d12; }
+                    else if (d02 <= d01) { fa = 0; fb = 2; fz = 1; fd = d02; }
+                    else { fa = 0; fb = 1; fz = 2; fd = d01; }
+                    if (fd <= edc) {
+                        members = (1u << fa) | (1u << fb);
+                        const int da = fa < fz ? e[fa][fz] : e[fz][fa], db = fb < fz ? e[fb][fz] : e[fz][fb];     // the queue holds upper-triangle costs
+                        if ((da > db ? da : db) <= edc) members = 7u;
+                    }
+                }
+                if (members) {
+                    const int k = __popc(members);
+                    if (k * P.fold_depth > k) {
+                        int it[3], c = 0;                                        // OneUmiCluster iteration order
+                        if (members & 1u) it[c++] = 0;
+                        if (members & 4u) it[c++] = 2;
+                        if (members & 2u) it[c++] = 1;
+                        int center;
+                        if (k == 2) center = (job_qv01 && job_qv01[j]) ? it[0] : it[1];
+                        else {
+                            int best = 0x7FFFFFFF; center = it[0];
+#pragma unroll
+                            for (int q = 0; q < 3; q++) {
+                                const int a = it[q];
+                                int sum = 0;
+#pragma unroll
+                                for (int b = 0; b < 3; b++) if (b != a) sum += e[a][b] * e[a][b];
+                                if (sum < best) { best = sum; center = a; }
+                            }
+                        }
+                        d.n_clusters = 1;
+                        if ((members >> x) & 1u) {
+                            int sum = 0;
+                            for (int q = 0; q < k; q++) if (it[q] != center) sum += ua_pos1_offset(M[center * 3 + it[q]]);
+                            const int32_t cell = M[center * 3 + x];
+                            d.center = center; d.flags = SLR_UA_ASSIGNED; d.cluster_size = (uint16_t)k;
+                            d.offset_center_mean = (int8_t)(k == 2 ? sum : ((sum + 1) >> 1));      // Math.round of the mean of one or two shifts
+                            d.u1 = (int8_t)(int)(int8_t)(cell & 0xFF); d.pos2 = (int8_t)ua_pos2_code(cell);
+                        }
+                    } else if ((members >> x) & 1u) { d.flags = SLR_UA_SKIPPED; d.cluster_size = (uint16_t)k; }
+                }
             } else if (r == r0 && n >= 2) {
                 const int cls = n <= 32 ? 0 : 1;
                 lists[(long long)cls * n_jobs + atomicAdd(&counts[cls], 1u)] = (int32_t)j;
