@@ -750,7 +750,7 @@ void orc_umi_cluster(const int32_t *matrix, int64_t n, int ed, const uint8_t *me
                      orc_cluster_rec *rec)
 {
     /* possibleClusters: the neighbour sets as one n x n bit matrix (in[a*n+v] = v in N(a)) */
-    uint8_t *in = (uint8_t *)calloc((size_t)(n * n ? n * n : 1), 1);
+    uint8_t *in = (uint8_t *)calloc((size_t)(n > 0 ? n * n : 1), 1);
     for (int64_t a = 0; a < n; a++) {
         rec[a].n_neighbours = 0; rec[a].best_key = -1; rec[a].best_count = 0; rec[a].n_ties = 0;
         if (member && !member[a]) continue;

@@ -513,7 +513,7 @@ static int my_cluster_local(const int32_t *matrix, int n, const int *idx, int L,
     for (int i = 0; i < nk; i++) gm[fill[gid[chosen[i]]]++] = keys[i];
     int *corder = (int *)malloc((size_t)ng * sizeof(int));
     chm_order(first, ng, corder, long_bin);                                             /* idMap.values() */
-    uint32_t *hs = (uint32_t *)malloc((size_t)ng * sizeof(uint32_t));
+    uint32_t *hs = (uint32_t *)calloc((size_t)ng + 1, sizeof(uint32_t));
     for (int t = 0; t < ng; t++) { const int g = gid[corder[t]]; uint32_t h = 0; for (int i = gsz[g]; i < gsz[g + 1]; i++) h += (uint32_t)gm[i]; hs[t] = h; }
     int *perm = (int *)malloc((size_t)ng * sizeof(int));
     jdk_order_by_hash(hs, ng, perm, long_bin);                                          /* L219: collect(toSet()) of the value sets */
