@@ -732,6 +732,18 @@ def cluster_one_hierarchical(ctx, umis, job_offsets, umi_len=12, params=None, jo
     return (rec, out, out_offsets) if want_matrices else rec
 
 
+def split_oversized_group(n, ram_reserved):
+    """UmiClustering.lambda$cluster$7 (UmiClustering.java:L136-L142): a (cell, region) group of n reads is cut into
+    nChunks = ceil((float) n / sqrt(RAM_RESERVED / 300)) consecutive parts of n / nChunks + 1 reads (ListUtils.partition: the last part takes the
+    rest) BEFORE it is clustered — the JVM's memory bound on one n x n matrix.  Caller-side: it changes the clusters, so a shadow class keeps it.
+    Returns the part sizes."""
+    import math
+    max_square = int(ram_reserved) // 300
+    n_chunks = int(math.ceil(float(np.float32(n)) / math.sqrt(float(max_square))))
+    size = n // max(n_chunks, 1) + 1 if n_chunks > 0 else n + 1
+    return [min(size, n - k) for k in range(0, n, size)]
+
+
 class UmiSession:
     """The matrices of one batch of (cell, region) jobs kept on the device between calls (slr_umi_session_*): the distance kernels run
     once, cluster() can then be called with the caller's key order (`rank`) once the keys are known, and again on the unclustered

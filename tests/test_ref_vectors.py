@@ -705,3 +705,14 @@ def test_gpu_cluster_one_myclustering_matches_reference_bytecode(pkg, ctx):
             recs[j] = got[so[k]:so[k + 1]]
     stats = _check_hier(z, lambda j: recs[j])
     assert stats[2] >= 72 and stats[0] > 9000, stats
+
+
+def test_oversized_group_split_matches_reference_bytecode(pkg):
+    """the caller-side split of a huge (cell, region) group (UmiClustering.lambda$cluster$7 + ListUtils.partition, run from the class files by
+    oracle/make_ref_split.py) against the host mirror split_oversized_group"""
+    z = np.load(os.path.join(GOLDEN, "ref_split.npz"))
+    o = 0
+    for ram, n, k in zip(z["ram"], z["n"], z["n_parts"]):
+        assert pkg.split_oversized_group(int(n), int(ram)) == [int(x) for x in z["parts"][o:o + k]], (ram, n)
+        o += int(k)
+    assert len(z["n"]) >= 80 and int(z["n_parts"].max()) >= 10
