@@ -744,6 +744,26 @@ def split_oversized_group(n, ram_reserved):
     return [min(size, n - k) for k in range(0, n, size)]
 
 
+def group_by_cell_and_region(cell_bc, region, valid=None, min_size=2):
+    """UmiClustering.groupDataByCellAndRegion + the size filter of cluster() (UmiClustering.java:L97-L118, L135): the reads that have a cell barcode
+    and a genomic region number, grouped by (barcode, region); groups of fewer than min_size reads are dropped.  Host-side (O(n log n), the caller's):
+    returns (order, job_offsets) — order[job_offsets[j]:job_offsets[j + 1]] are the read indices of job j in INPUT order (the reference fills its
+    lists from a parallel stream, so its order inside a group is arrival order; input order is the one-thread result), jobs in ascending
+    (barcode, region) order (the reference iterates two ConcurrentHashMaps; the job order does not reach any per-read result)."""
+    cell_bc = np.asarray(cell_bc, dtype=np.uint64)
+    region = np.asarray(region, dtype=np.int64)
+    idx = np.arange(len(cell_bc), dtype=np.int64) if valid is None else np.nonzero(np.asarray(valid, dtype=bool))[0].astype(np.int64)
+    o = idx[np.lexsort((idx, region[idx], cell_bc[idx]))]
+    if len(o) == 0:
+        return o, np.zeros(1, dtype=np.int64)
+    new = np.ones(len(o), dtype=bool)
+    new[1:] = (cell_bc[o][1:] != cell_bc[o][:-1]) | (region[o][1:] != region[o][:-1])
+    starts = np.nonzero(new)[0]
+    sizes = np.diff(np.concatenate([starts, [len(o)]]))
+    keep = np.repeat(sizes >= min_size, sizes)
+    return o[keep], np.concatenate([[0], np.cumsum(sizes[sizes >= min_size])]).astype(np.int64)
+
+
 class UmiSession:
     """The matrices of one batch of (cell, region) jobs kept on the device between calls (slr_umi_session_*): the distance kernels run
     once, cluster() can then be called with the caller's key order (`rank`) once the keys are known, and again on the unclustered

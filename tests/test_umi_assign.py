@@ -334,3 +334,26 @@ def test_gpu_deep_jobs_through_host_api_and_session(pkg, orc, ctx):
     assert int((rec["flags"][deep] & 1).sum()) > 1000
     with pkg.UmiSession(ctx, umis, offs) as s:
         assert [rec_tuple(r) for r in s.assign()] == [rec_tuple(r) for r in exp]
+
+
+def test_group_by_cell_and_region():
+    """host mirror of UmiClustering.groupDataByCellAndRegion + the size filter: groups by (barcode, region), input order inside a group"""
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    rng = np.random.default_rng(3)
+    n = 5000
+    cell = rng.integers(0, 40, n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15 & 0xFFFFFFFF)
+    region = rng.integers(0, 30, n).astype(np.int64)
+    valid = rng.random(n) < 0.9
+    order, off = pkg.group_by_cell_and_region(cell, region, valid)
+    seen = set()
+    for j in range(len(off) - 1):
+        m = order[off[j]:off[j + 1]]
+        assert len(m) >= 2 and (np.diff(m) > 0).all() and valid[m].all()
+        assert len(set(cell[m].tolist())) == 1 and len(set(region[m].tolist())) == 1
+        key = (int(cell[m[0]]), int(region[m[0]]))
+        assert key not in seen
+        seen.add(key)
+    import collections
+    cnt = collections.Counter((int(c), int(r)) for c, r, v in zip(cell, region, valid) if v)
+    assert seen == {k for k, v in cnt.items() if v >= 2} and off[-1] == sum(v for v in cnt.values() if v >= 2)
