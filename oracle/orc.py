@@ -223,6 +223,19 @@ def umi_assign_batch(matrices, job_offsets, out_offsets, params=None, job_qv01=N
     return rec
 
 
+def fu_set_ops(keys, victims):
+    """orc_fu_set_ops: fastutil IntOpenHashSet filled with `keys`, removeAll(victims) -> (order before, order after)"""
+    keys = np.ascontiguousarray(keys, dtype=np.int32)
+    victims = np.ascontiguousarray(victims, dtype=np.int32)
+    before, after = np.zeros(len(keys) + 1, dtype=np.int32), np.zeros(len(keys) + 1, dtype=np.int32)
+    L = lib()
+    L.orc_fu_set_ops.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_fu_set_ops.restype = C.c_int
+    n = L.orc_fu_set_ops(keys.ctypes.data, len(keys), victims.ctypes.data, len(victims), int(keys.max()) if len(keys) else 0, before.ctypes.data,
+                         after.ctypes.data)
+    return before[:len(keys)].tolist(), after[:n].tolist()
+
+
 # ---- Illumina-guided search (SURVEY.md §8 a15) -------------------------------------------------------------------------
 GUIDED_HIT = np.dtype([("seq", "<u8"), ("n_sub", "i1"), ("n_ins", "i1"), ("n_del", "i1"), ("offset", "i1"), ("where", "u1"),
                        ("level", "u1"), ("pad", "<u2")], align=True)

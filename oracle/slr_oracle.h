@@ -211,6 +211,7 @@ typedef struct {
     int32_t  n_clusters;      /* cluster_list.size() of the job */
 } orc_assign_rec;             /* 16 bytes, same layout as slr_umi_assign_rec */
 void orc_umi_assign_hier(const int32_t *matrix, int64_t n, const orc_assign_params *P, int qv01, orc_assign_rec *rec);
+int  orc_fu_set_ops(const int *keys, int k, const int *victims, int nv, int max_key, int *order_before, int *order_after);   /* test hook */
 void orc_umi_assign_myclust(const int32_t *matrix, int64_t n, const orc_assign_params *P, int qv01, orc_assign_rec *rec);
 void orc_umi_assign_batch(const int32_t *matrices, const int64_t *job_offsets, const int64_t *out_offsets, int64_t n_jobs,
                           const orc_assign_params *P, const uint8_t *job_qv01, orc_assign_rec *rec, int n_threads);

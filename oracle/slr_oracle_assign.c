@@ -449,6 +449,21 @@ static void fu_remove_all(fuset *s, const uint8_t *victim)
     free(wrapped);
 }
 
+/* test hook: an IntOpenHashSet filled with keys[0 .. k), its iteration order, then removeAll(victims) and the order after it.  max_key = the
+ * largest key (sizes the victim map).  Returns the size after the removal. */
+int orc_fu_set_ops(const int *keys, int k, const int *victims, int nv, int max_key, int *order_before, int *order_after)
+{
+    fuset s; fu_init(&s);
+    for (int i = 0; i < k; i++) fu_add(&s, keys[i]);
+    fu_order(&s, order_before);
+    uint8_t *vm = (uint8_t *)calloc((size_t)max_key + 2, 1);
+    for (int i = 0; i < nv; i++) vm[victims[i]] = 1;
+    fu_remove_all(&s, vm);
+    const int n = fu_order(&s, order_after);
+    free(vm); free(s.key);
+    return n;
+}
+
 typedef struct { fuset set; int center; } mycluster;
 
 static int my_center(const int32_t *matrix, int n, const fuset *s, int qv01, int *tmp)  /* OneUmiCluster.java:L49-L65 */

@@ -357,3 +357,43 @@ def test_group_by_cell_and_region():
     import collections
     cnt = collections.Counter((int(c), int(r)) for c, r, v in zip(cell, region, valid) if v)
     assert seen == {k for k, v in cnt.items() if v >= 2} and off[-1] == sum(v for v in cnt.values() if v >= 2)
+
+
+def test_fastutil_set_removal_wraparound(orc):
+    """IntOpenHashSet + AbstractCollection.removeAll through the set's iterator (OneUmiCluster.removeEntries): the C oracle against the Python
+    restatement on sets built to wrap around the table end (home slots in the last few slots, long probe runs), with growth, with key 0, with
+    removals that empty runs and removals that trigger the shrink rule — the path the clustering fuzz reaches only a few times"""
+    rng = np.random.default_rng(2026)
+    wrapped_cases = 0
+    for t in range(1500):
+        k = int(rng.choice([3, 8, 20, 24, 25, 40, 49, 97, 150, 400]))
+        table = 32
+        size = 0
+        for _ in range(k):                                   # the table size the set will have (for the home-slot filter below)
+            size += 1
+            if size - 1 >= min(-(-table * 3 // 4), table - 1):
+                need, nn = -(-(size + 1) * 4 // 3), 2
+                while nn < need:
+                    nn *= 2
+                table = nn
+        pool = np.arange(0, 60000)
+        home = np.array([pyref.fastutil_mix(int(x)) & (table - 1) for x in pool[:6000]])
+        near_end = pool[:6000][(home >= table - 4) | (home < 2)] if t % 2 else pool[:6000]
+        keys = rng.choice(near_end if len(near_end) >= k else pool, size=k, replace=False).astype(np.int32)
+        if t % 7 == 0:
+            keys[int(rng.integers(k))] = 0
+            keys = np.unique(keys)[rng.permutation(len(np.unique(keys)))].astype(np.int32)
+        nv = int(rng.integers(1, len(keys) + 1)) if t % 5 else len(keys) - 1
+        victims = rng.choice(keys, size=nv, replace=False).astype(np.int32)
+        s = pyref.FuIntSet()
+        for x in keys:
+            s.add(int(x))
+        exp_before = s.order()
+        s.remove_all([int(v) for v in victims])
+        exp_after = s.order()
+        got_before, got_after = orc.fu_set_ops(keys, victims)
+        assert got_before == exp_before, (t, keys.tolist())
+        assert got_after == exp_after, (t, keys.tolist(), victims.tolist())
+        assert sorted(exp_after) == sorted(set(keys.tolist()) - set(victims.tolist()))
+        wrapped_cases += t % 2
+    assert wrapped_cases > 500
