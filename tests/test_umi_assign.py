@@ -397,3 +397,83 @@ def test_fastutil_set_removal_wraparound(orc):
         assert sorted(exp_after) == sorted(set(keys.tolist()) - set(victims.tolist()))
         wrapped_cases += t % 2
     assert wrapped_cases > 500
+
+
+def wraparound_job(rng, n):
+    """a job of more than 100 reads with ONE cluster whose members sit at the end / start of fastutil's 32-slot table (home slots 28 ... 31, 0, 1) and
+    lose a few members to the off-centre removal: hub h (every member within ED 2 of it, so all join its entry), a tight group G that wins the
+    centre, outsiders O farther than ED 2 from G — they leave through OneUmiCluster.removeEntries, across the table's wrap-around"""
+    home = np.array([pyref.fastutil_mix(int(x)) & 31 for x in range(n)])
+    pool = np.nonzero((home >= 28) | (home <= 1))[0]
+    pool = pool[pool > 0] if rng.random() < 0.7 else pool                 # with and without key 0
+    k = int(rng.integers(6, min(22, len(pool) - 1)))
+    mem = rng.choice(pool, size=k + 1, replace=False)
+    h, rest = int(mem[0]), mem[1:]
+    n_out = int(rng.integers(1, 4))
+    O, G = rest[:n_out], rest[n_out:]
+    e = np.full((n, n), 5, dtype=np.int64)
+    for g in G:
+        e[h, g] = e[g, h] = 2
+        for g2 in G:
+            e[g, g2] = int(rng.integers(0, 2))
+    for o in O:
+        e[h, o] = e[o, h] = 2
+        for g in G:
+            e[o, g] = e[g, o] = 4
+    e = np.triu(e, 1)
+    e = e + e.T
+    p1, p2 = rng.integers(0, 3, (n, n)), rng.integers(0, 3, (n, n))
+    up = e | (0x08000000 << p1) | (0x01000000 << p2)
+    lo = e | (0x08000000 << p2.T) | (0x01000000 << p1.T)
+    packed = np.where(np.arange(n)[:, None] <= np.arange(n)[None, :], up, lo)
+    np.fill_diagonal(packed, 0x10000000 | 0x02000000)
+    return packed.astype(np.int32)
+
+
+def test_myclustering_removal_across_the_table_end(orc):
+    """oracle vs the Python restatement on jobs built so that the off-centre removal walks fastutil's wrap-around (wrapped entries, removal through
+    the set's own remove) — counted, so the path is known to run"""
+    rng = np.random.default_rng(8)
+    cnt = {"wrapped": 0}
+    orig = pyref.FuIntSet._shift
+
+    def shift(self, pos, wrapped=None):
+        n0 = len(wrapped) if wrapped is not None else 0
+        orig(self, pos, wrapped)
+        if wrapped is not None:
+            cnt["wrapped"] += len(wrapped) - n0
+    pyref.FuIntSet._shift = shift
+    try:
+        removed_jobs = 0
+        for t in range(80):
+            n = int(rng.integers(101, 330))
+            packed = wraparound_job(rng, n)
+            qv = int(rng.integers(0, 2))
+            rec = orc.umi_assign_batch(packed.ravel(), np.array([0, n]), np.array([0, n * n]), orc.AssignParams(), np.array([qv], dtype=np.uint8))
+            pr = pyref.assign_myclust(packed.tolist(), 2, 50, bool(qv))
+            for i in range(n):
+                a, b = rec[i], pr[i]
+                assert (bool(a["flags"] & 1), int(a["cluster_size"]), int(a["n_clusters"])) == (b["assigned"], b["cluster_size"], b["n_clusters"]), (t, i)
+                if b["assigned"]:
+                    assert (int(a["center"]), int(a["u1"]), int(a["u2"]), int(a["pos2"]), int(a["off_mean"])) == \
+                           (b["center"], b["u1"], b["u2"], b["pos2"], b["off_mean"]), (t, i)
+            removed_jobs += int((rec["flags"] & 1).sum() > 0 and int(rec["cluster_size"].max()) < int((packed.ravel() & 0xFF <= 2).reshape(n, n).sum(axis=1).max()))
+    finally:
+        pyref.FuIntSet._shift = orig
+    assert cnt["wrapped"] >= 10 and removed_jobs >= 40, (cnt, removed_jobs)
+
+
+@pytest.mark.gpu
+def test_gpu_deep_removal_across_the_table_end(pkg, orc, ctx):
+    """the same constructed jobs through the large-job kernels: thread-per-cluster local tables (<= 24 members) with wrap-around removal"""
+    rng = np.random.default_rng(8)
+    sizes = [int(rng.integers(101, 330)) for _ in range(80)]
+    mats = np.concatenate([wraparound_job(rng, n).ravel() for n in sizes]).astype(np.int32)
+    sizes = np.array(sizes, dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    oo = np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)
+    qv = (np.arange(len(sizes)) % 2).astype(np.uint8)
+    got = _dev_assign(pkg, ctx, mats, offs, oo, None, qv)
+    exp = orc.umi_assign_batch(mats, offs, oo, None, qv)
+    assert [rec_tuple(r) for r in got] == [rec_tuple(r) for r in exp]
+    assert int((got["flags"] & 1).sum()) > 400
