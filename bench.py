@@ -174,18 +174,20 @@ def cpu_reference_step(orc, kind, bset, slices, anchor, ed, umis, offs, threads)
 
 
 def load_profile(pkg, kernel):
-    """newest profiles/r*_kernel_profile.json entry for `kernel` whose source hash equals the loaded library's; None otherwise"""
-    want = pkg.csrc_sha256()
+    """newest profiles/r*_kernel_profile.json entry for `kernel` measured on the sources this library was built from: the entry's own source hash
+    (translation unit + transitive includes of that kernel, pkg.kernel_src_sha256) must match, or — older files — the hash over all of csrc/.
+    None otherwise"""
+    want_all, want_k = pkg.csrc_sha256(), pkg.kernel_src_sha256(kernel)
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernel_profile*.json")), reverse=True):
         try:
             prof = json.load(open(f))
         except Exception:
             continue
-        if prof.get("csrc_sha256") != want:
-            continue
         for k in prof.get("kernels", []):
-            if kernel == k.get("kernel", ""):
-                return dict(k, file=os.path.relpath(f, ROOT), csrc_sha256=want)
+            if kernel != k.get("kernel", ""):
+                continue
+            if (k.get("src_sha256") and k["src_sha256"] == want_k) or (not k.get("src_sha256") and prof.get("csrc_sha256") == want_all):
+                return dict(k, file=os.path.relpath(f, ROOT), csrc_sha256=k.get("src_sha256") or want_all)
     return None
 
 

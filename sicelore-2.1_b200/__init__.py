@@ -202,6 +202,41 @@ def csrc_sha256():
     return h.hexdigest()
 
 
+KERNEL_TU = {"bc_assign_kernel": "bc_assign.cu", "umi_pairs_kernel": "umi_dist.cu", "umi_assign_kernel": "umi_assign.cu",
+             "guided_match_kernel": "guided_match.cu", "umi_assign_deep_kernel": "umi_assign_deep.cu"}
+
+
+def kernel_src_sha256(kernel):
+    """sha256 over the translation unit of `kernel` (name up to '<', '/', '@') and every header it includes, transitively, from csrc/ and include/:
+    a profile entry describes a kernel as long as THESE files are unchanged, whatever happens to the other translation units"""
+    import hashlib
+    import re
+    base = re.split(r"[<@/]", kernel)[0]
+    if base not in KERNEL_TU:
+        return None
+    inc_dir = os.path.join(_HERE, "..", "include")
+    seen, todo = {}, [os.path.join(_CSRC, KERNEL_TU[base])]
+    while todo:
+        f = todo.pop()
+        name = os.path.basename(f)
+        if name in seen:
+            continue
+        with open(f, "rb") as fh:
+            data = fh.read()
+        seen[name] = data
+        for inc in re.findall(rb'#include\s+"([^"]+)"', data):
+            for d in (_CSRC, inc_dir):
+                cand = os.path.join(d, inc.decode())
+                if os.path.exists(cand):
+                    todo.append(cand)
+                    break
+    h = hashlib.sha256()
+    for name in sorted(seen):
+        h.update(name.encode())
+        h.update(seen[name])
+    return h.hexdigest()
+
+
 class SynthParams(C.Structure):
     _fields_ = [("p_sub", C.c_double), ("p_ins", C.c_double), ("p_del", C.c_double), ("p_random", C.c_double),
                 ("p_n", C.c_double), ("jitter", C.c_double * 5), ("n_cells", C.c_int64), ("three_prime", C.c_int)]

@@ -2,7 +2,8 @@
 
 One ncu pass (--clock-control none, a few counters, no --set full) over short single-purpose runs of the hot kernels; per kernel the warp
 instructions, DRAM bytes and duration of one launch, divided by the units (reads) the launch processed.  The file carries the sha256 of the
-library's SOURCES (pkg.csrc_sha256(): csrc/ + the public header): bench.py uses a profile only when that hash equals the loaded library's,
+library's SOURCES (pkg.csrc_sha256(): csrc/ + the public header) and, per kernel, of that kernel's translation unit + transitive includes
+(pkg.kernel_src_sha256): bench.py uses an entry only when the kernel's hash equals the one of the sources the loaded library was built from,
 i.e. the numbers describe the code that ran (the .so itself is not bit-reproducible across rebuilds: nvcc's anonymous-namespace names)."""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -74,7 +75,7 @@ for key, rx, units, cmd, what in RUNS:
         by_name.setdefault(d["name"], []).append(d)
     tot = {k: sum(sum(d.get(k, 0) for d in ds) / len(ds) for ds in by_name.values())
            for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum")}
-    kernels.append({"kernel": key, "launch": best["name"][:100], "what": what, "instances": len(by_name), "launches_seen": len(per), "units_per_launch": units,
+    kernels.append({"kernel": key, "src_sha256": pkg.kernel_src_sha256(key), "launch": best["name"][:100], "what": what, "instances": len(by_name), "launches_seen": len(per), "units_per_launch": units,
                     "duration_ms": tot["gpu__time_duration.sum"], "inst_executed_per_unit": tot["smsp__inst_executed.sum"] / units,
                     "dram_bytes_per_unit": (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) / units,
                     "issue_slots_busy_pct": best.get("sm__inst_issued.avg.pct_of_peak_sustained_active"),
