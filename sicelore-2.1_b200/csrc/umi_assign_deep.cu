@@ -1048,14 +1048,19 @@ cudaError_t slr_launch_umi_assign_deep(const int32_t *d_mat, const long long *d_
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(umi_assign_deep_kernel<8, SM_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BIG * 4);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(umi_assign_deep_kernel<0, SM_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BIG * 4);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    // function attributes belong to the device (one module per context): set once per device, not once per process
+    static std::mutex attr_mtx;
+    static bool attr_done[64];
+    {
+        std::lock_guard<std::mutex> lk(attr_mtx);
+        if (!attr_done[dev & 63]) {
+            cudaError_t ae = cudaFuncSetAttribute(umi_assign_deep_kernel<8, SM_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BIG * 4);
+            if (ae == cudaSuccess)
+                ae = cudaFuncSetAttribute(umi_assign_deep_kernel<0, SM_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BIG * 4);
+            if (ae != cudaSuccess) return ae;
+            attr_done[dev & 63] = true;
+        }
+    }
     long long gs = max_jobs < (long long)sms * 2 ? max_jobs : (long long)sms * 2;
     if (gs < 1) gs = 1;
     umi_assign_deep_kernel<1, SM_SMALL><<<(unsigned)gs, DEEP_THREADS, SM_SMALL * 4, stream>>>(d_mat, d_job_offsets, d_out_offsets, P, d_job_qv01, d_rec,

@@ -42,6 +42,9 @@ def test_multi_matches_single_device_and_oracle(pkg, orc, ctx):
     assert (m == em).all() and (moo == oo).all()
     # jobs above 100 reads (ClusterOne_MyClustering on every device: each shard sizes its own arena)
     du, doff = pkg.synth_umi_jobs(60, mean=150.0, cap=700, seed=12)
+    for cap_, seed_ in ((1500, 31), (4200, 32)):            # + a cluster-of-8-CTAs job and a cooperative-grid job: they end up on the LAST device,
+        gu, go = pkg.synth_umi_jobs(1, mean=1e9, cap=cap_, seed=seed_)      # whose function attributes (192 KB of dynamic shared memory) are its own
+        du, doff = np.concatenate([du, gu]), np.concatenate([doff, doff[-1] + go[1:]]).astype(np.int64)
     dm, doo = orc.umi_matrix_batch(du, doff)
     drec = mg.umi_assign(du, doff)
     assert drec.tobytes() == orc.umi_assign_batch(dm, doff, doo).tobytes()
