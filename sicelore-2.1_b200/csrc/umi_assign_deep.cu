@@ -568,8 +568,8 @@ __device__ bool chm_order_par(const int *keys, int K, int *out, int *out_idx, in
     for (int t = tid; t < K; t += DEEP_THREADS) { hsh[t] = dp_spread((unsigned)keys[t]) & 0x7FFFFFFFu; nxt[t] = -1; }
     if (tid == 0) s_long = 0;
     __syncthreads();
-    if (tid < 16) {
-        const int r = tid;
+    if ((tid & 31) == 0 && (tid >> 5) < 16) {                           // 16 workers, one per warp (lanes of one warp would serialise)
+        const int r = tid >> 5;
         int cap = 16, sc = 12, lb = 0;
         int *head = (doublings & 1) ? B : A, *alt = (doublings & 1) ? A : B;      // the final table lands in A
         head[r] = -1;
@@ -606,13 +606,22 @@ __device__ bool chm_order_par(const int *keys, int K, int *out, int *out_idx, in
         if (lb) s_long = 1;
     }
     __syncthreads();
-    if (tid == 0) {
-        int o = 0;
-        for (int i = 0; i < F; i++) for (int p = A[i]; p >= 0; p = nxt[p]) out_idx[o++] = p;
-        if (s_long) *long_bin = 1;
+    {                                                                   // the map's iteration: bins ascending, chains in link order
+        __shared__ int s_b[DEEP_THREADS + 1];
+        const int per = (F + DEEP_THREADS - 1) / DEEP_THREADS, lo = tid * per, hi = lo + per < F ? lo + per : F;
+        int c = 0;
+        for (int i = lo; i < hi; i++) for (int p = A[i]; p >= 0; p = nxt[p]) c++;
+        s_b[tid] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int t = 0; t < DEEP_THREADS; t++) { const int v = s_b[t]; s_b[t] = acc; acc += v; }
+            if (s_long) *long_bin = 1;
+        }
+        __syncthreads();
+        int o = s_b[tid];
+        for (int i = lo; i < hi; i++) for (int p = A[i]; p >= 0; p = nxt[p]) out[o++] = keys[p];
     }
-    __syncthreads();
-    for (int t = tid; t < K; t += DEEP_THREADS) out[t] = keys[out_idx[t]];
     __syncthreads();
     return true;
 }
@@ -681,34 +690,67 @@ __device__ void groups_layout(int round, int fold_depth, DeepW &w, int *smem)
         atomicMax(&s_maxdepth, k);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { int l2 = 0; jdk_order(w.ht, ng, w.perm, dp_jdk_cap(ng) + 1 <= SM_INTS ? smem : w.tabA, &l2); if (l2) s_long = 1; }
+    // HashSet<Set<Integer>> order of the groups (hash = member sum): counting sort by bucket, chains in insertion (= map) order
+    const int cap = dp_jdk_cap(ng);
+    if (2 * (cap + 1) <= SM_INTS) {
+        int *cnt = smem, *cur = smem + cap + 1;
+        for (int b = threadIdx.x; b <= cap; b += DEEP_THREADS) cnt[b] = 0;
+        __syncthreads();
+        for (int t = threadIdx.x; t < ng; t += DEEP_THREADS) atomicAdd(&cnt[(dp_spread(w.ht[t]) & (unsigned)(cap - 1)) + 1], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) for (int b = 0; b < cap; b++) { if (cnt[b + 1] >= 9) s_long = 1; cnt[b + 1] += cnt[b]; }
+        __syncthreads();
+        for (int b = threadIdx.x; b < cap; b += DEEP_THREADS) cur[b] = cnt[b];
+        __syncthreads();
+        for (int t = threadIdx.x; t < ng; t += DEEP_THREADS) w.perm[atomicAdd(&cur[dp_spread(w.ht[t]) & (unsigned)(cap - 1)], 1)] = t;
+        __syncthreads();
+        for (int b = threadIdx.x; b < cap; b += DEEP_THREADS) {          // a bucket's chain keeps insertion order: sort its few entries by t
+            const int lo = cnt[b], hi = cnt[b + 1];
+            for (int i = lo + 1; i < hi; i++) {
+                const int v = w.perm[i];
+                int j = i - 1;
+                while (j >= lo && w.perm[j] > v) { w.perm[j + 1] = w.perm[j]; j--; }
+                w.perm[j + 1] = v;
+            }
+        }
+    } else if (threadIdx.x == 0) { int l2 = 0; jdk_order(w.ht, ng, w.perm, w.tabA, &l2); if (l2) s_long = 1; }
     __syncthreads();
-    int *pe = w.gm + ng, *pk = w.pscr;                                   // entry and size of the groups in HashSet order, contiguous for the walk below
+    int *pe = w.gm + ng, *pk = w.pscr;                                   // entry and size of the groups in HashSet order
     for (int t = threadIdx.x; t < ng; t += DEEP_THREADS) { const int g = w.perm[t]; pe[t] = w.corder[g]; pk[t] = gk[g]; }
     __syncthreads();
-    if (threadIdx.x != 0) return;
+    // cluster slots in that order: round 1 applies the depth rule, round 2 keeps the groups of more than one read; every thread lays out a
+    // contiguous piece after a prefix sum over (clusters kept, reads in them)
     const int maxdepth = s_maxdepth;
-    int n_cl = w.hdr[H_NCL], total = w.hdr[H_TOTAL], n_big = 0;
-    w.hdr[H_Q0] = n_cl;
-    for (int t0 = 0; t0 < ng; t0 += 8) {
-        int ee[8], kk[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) { ee[u] = t0 + u < ng ? pe[t0 + u] : 0; kk[u] = t0 + u < ng ? pk[t0 + u] : 0; }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            if (t0 + u >= ng) break;
-            const int e = ee[u], k = kk[u];
-            if (round == 2 && k <= 1) { w.grp_q[e] = -1; continue; }
-            if (round == 1 && !((long long)k * fold_depth > maxdepth)) { w.grp_q[e] = -2; continue; }
-            w.grp_q[e] = n_cl;
-            w.cl_entry[n_cl] = e; w.cl_beg[n_cl] = total; w.cl_len0[n_cl] = k; w.cl_len[n_cl] = k; w.cl_nvict[n_cl] = 0; w.cl_dirty[n_cl] = 1;
-            w.cl_center[n_cl] = -1;
-            if (k > SMALL_K) w.big_list[n_big++] = n_cl;
-            n_cl++; total += k;
-        }
+    const int n_cl0 = w.hdr[H_NCL], total0 = w.hdr[H_TOTAL];
+    __shared__ int s_nc[DEEP_THREADS + 1], s_nr[DEEP_THREADS + 1], s_nbig;
+    const int per = (ng + DEEP_THREADS - 1) / DEEP_THREADS, lo = threadIdx.x * per, hi = lo + per < ng ? lo + per : ng;
+    auto kept = [&](int k) { return round == 1 ? ((long long)k * fold_depth > maxdepth) : (k > 1); };
+    int c = 0, rsum = 0;
+    for (int t = lo; t < hi; t++) if (kept(pk[t])) { c++; rsum += pk[t]; }
+    s_nc[threadIdx.x] = c; s_nr[threadIdx.x] = rsum;
+    if (threadIdx.x == 0) s_nbig = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ac = 0, ar = 0;
+        for (int t = 0; t < DEEP_THREADS; t++) { const int vc = s_nc[t], vr = s_nr[t]; s_nc[t] = ac; s_nr[t] = ar; ac += vc; ar += vr; }
+        s_nc[DEEP_THREADS] = ac; s_nr[DEEP_THREADS] = ar;
     }
-    w.hdr[H_NG] = ng; w.hdr[H_NCL] = n_cl; w.hdr[H_TOTAL] = total; w.hdr[H_NBIG] = n_big;
-    if (s_long) w.hdr[H_FLAG] |= 2;
+    __syncthreads();
+    int q = n_cl0 + s_nc[threadIdx.x], off = total0 + s_nr[threadIdx.x];
+    for (int t = lo; t < hi; t++) {
+        const int e = pe[t], k = pk[t];
+        if (!kept(k)) { w.grp_q[e] = round == 1 ? -2 : -1; continue; }
+        w.grp_q[e] = q;
+        w.cl_entry[q] = e; w.cl_beg[q] = off; w.cl_len0[q] = k; w.cl_len[q] = k; w.cl_nvict[q] = 0; w.cl_dirty[q] = 1; w.cl_center[q] = -1;
+        if (k > SMALL_K) w.big_list[atomicAdd(&s_nbig, 1)] = q;
+        q++; off += k;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        w.hdr[H_Q0] = n_cl0;
+        w.hdr[H_NG] = ng; w.hdr[H_NCL] = n_cl0 + s_nc[DEEP_THREADS]; w.hdr[H_TOTAL] = total0 + s_nr[DEEP_THREADS]; w.hdr[H_NBIG] = s_nbig;
+        if (s_long) w.hdr[H_FLAG] |= 2;
+    }
 }
 // members of one small cluster in the iteration order of its HashSet<Integer> (filled in key order); returns 1 when a bin reached 9 entries
 __device__ __forceinline__ int small_jdk_order(const int *in, int k, int *out)

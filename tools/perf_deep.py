@@ -32,8 +32,6 @@ def run(umis, offs, label):
         hdr = d_scr[arena + 2 * ((m + 3) & ~1) * 4: arena + 2 * ((m + 3) & ~1) * 4 + 256].cpu().numpy().view(np.uint64)[16:32].astype(np.int64)
         names = ["r1 counts", "r1 keys", "r1 choose", "r1 scan", "r1 layout", "r1 build", "r1 centres", "(victims/remove)", "r2 counts", "r2 keys", "r2 choose",
                  "r2 scan", "r2 layout", "r2 build", "r2 centres+per-cluster", "per-read"]
-        dbg = d_scr[arena + 2 * ((m + 3) & ~1) * 4 + 64: arena + 2 * ((m + 3) & ~1) * 4 + 128].cpu().numpy().view(np.uint64).astype(np.int64)
-        print("   dbg stamps (us, relative to stamp 4):", [(int(x) - int(hdr[4])) / 1e3 if x > 0 else None for x in dbg[:4]], "stamp5:", (int(hdr[5]) - int(hdr[4])) / 1e3)
         seq = [(i, int(hdr[i])) for i in range(16) if hdr[i] > 0]
         print("   phases (us):", ", ".join("%s %.0f" % (names[a], (tb - ta) / 1e3) for (a, ta), (b, tb) in zip(seq, seq[1:])), flush=True)
     parity = None
