@@ -1042,6 +1042,12 @@ class VM:
                     raise JavaThrow("java/lang/ArithmeticException")
                 q = abs(a) // abs(b) * (1 if (a < 0) == (b < 0) else -1)
                 push(i32(q) if op == 0x6c else i32(a - q * b)); pc += 1
+            elif op == 0x6d or op == 0x71:                  # ldiv lrem (truncating, like idiv)
+                b = pop(); a = pop()
+                if b == 0:
+                    raise JavaThrow("java/lang/ArithmeticException")
+                q = abs(a) // abs(b) * (1 if (a < 0) == (b < 0) else -1)
+                push(i64(q) if op == 0x6d else i64(a - q * b)); pc += 1
             elif op == 0x74:
                 push(i32(-pop())); pc += 1
             elif op == 0x78:
