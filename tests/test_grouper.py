@@ -182,3 +182,28 @@ def test_grouper_feeds_the_job_former(grouping):
     for j in range(len(off) - 1):
         ids = order[off[j]:off[j + 1]]
         assert len(ids) >= 2 and len(set(cell[ids].tolist())) == 1 and len(set(region[ids].tolist())) == 1
+
+
+def test_job_former_matches_reference_bytecode():
+    """UmiClustering.cluster up to its Submitter (groupDataByCellAndRegion, size filter, split of oversized groups; UmiClustering.java:L97-L145)
+    run from the class files by oracle/make_ref_jobs.py: the host mirrors form the same set of jobs, reads inside a job in input order"""
+    pkg = g.load_package()
+    z = np.load(os.path.join(os.path.dirname(GOLD), "ref_jobs.npz"))
+    off, joff = z["offsets"], z["job_offsets"]
+    assert len(off) - 1 >= 80 and len(joff) - 1 >= 2500
+    n_split = 0
+    for c in range(len(off) - 1):
+        bc, region = z["barcode"][off[c]:off[c + 1]], z["region"][off[c]:off[c + 1]]
+        want = sorted(z["job_reads"][joff[j]:joff[j + 1]].tolist() for j in np.nonzero(z["job_case"] == c)[0])
+        order, o = pkg.group_by_cell_and_region(bc.astype(np.uint64), region, (bc >= 0) & (region >= 0))
+        got = []
+        for j in range(len(o) - 1):
+            ids = order[o[j]:o[j + 1]].tolist()
+            a = 0
+            parts = pkg.split_oversized_group(len(ids), int(z["ram"][c]))
+            n_split += len(parts) > 1
+            for sz in parts:
+                got.append(ids[a:a + sz])
+                a += sz
+        assert sorted(got) == want, c
+    assert n_split > 20
