@@ -30,7 +30,8 @@ enum {
     SLR_E_NODEVICE = -2,     /* no CUDA device / driver: the library never falls back to the CPU */
     SLR_E_CUDA = -3,         /* a CUDA runtime call failed (message has the detail) */
     SLR_E_NOMEM = -4,
-    SLR_E_UNSUPPORTED = -5   /* e.g. --bcEditDistance > 2, barcode length != 16 */
+    SLR_E_UNSUPPORTED = -5,  /* e.g. --bcEditDistance > 2, barcode length != 16 */
+    SLR_E_REFERENCE_THROWS = -6   /* the reference itself throws on this input (host-side grouping only; the message names the exception and line) */
 };
 
 typedef struct slr_ctx slr_ctx;           /* one per (process, device) */
@@ -400,6 +401,39 @@ int  slr_multi_umi_cluster(slr_multi *m, const uint8_t *umis, int stride, int um
                            const uint8_t *member, const int32_t *rank, slr_umi_cluster_rec *rec);
 int  slr_multi_umi_assign(slr_multi *m, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
                           const slr_umi_assign_params *params, const uint8_t *job_qv01, slr_umi_assign_rec *rec);
+
+/* ---- host side of the clustering seam: forming the (cell, region) jobs ------------------------------- */
+/* Plain host code (no device, no context): the reference does this on its BAM reader thread, a JVM caller keeps its own classes; these entry
+ * points exist for callers WITHOUT a JVM, so that they feed slr_umi_assign with the same jobs.  Pinned against the reference's class files
+ * (tests/golden/ref_grouper.npz, ref_jobs.npz). */
+typedef struct slr_grouper slr_grouper;   /* the process-wide state of ReadGrouper: MAX_GENOME_DISTANCE_FOR_SAME_GENOMIC_REGION + the static region counter */
+
+/* ReadGrouper.setMaxGenomeDistance (config.xml:247 max_GenomeDistance_forGrouping, default 500) + ReadGrouper$Cluster.CURRENT_GENOMIC_REGION_ID
+ * (ReadGrouper.java:L460; 0 at JVM start). */
+int  slr_grouper_create(int max_genome_distance, int64_t first_region_id, slr_grouper **out);
+void slr_grouper_destroy(slr_grouper *g);
+int64_t slr_grouper_next_region_id(const slr_grouper *g);
+
+/* Replaces ReadGrouper.groupSams (F!com/rw/umifinder/bamreaders/ReadGrouper.class, ReadGrouper.java:L82-L230; caller BamReader.run,
+ * BamReader.java:L134-L145) for one chunk of n SAM records in BAM order.  position[i] = ReadScanData.positionOnGenomeForClustering (read only
+ * where has_position[i] != 0; has_position NULL = every read has one), flags[i] = SAMRecord.getFlags() (bit 16 = reverse strand),
+ * region_io[i] = NanoporeRead.genomicRegionNmber, -1 = absent: the reads of every surviving cluster receive its number, the others keep
+ * what they had (a read carried over from the previous chunk keeps that round's number).  *last_index_out: records [0, last_index] are the
+ * grouped chunk the clustering stage receives; with keep_data_end the records behind it open the caller's next chunk (BamReader.java:L134), without
+ * they are dropped (the reference returns an empty chunk).  n == 0: *last_index_out = -1, nothing is handed on (L82-L83).
+ * SLR_E_REFERENCE_THROWS: the reference's NullPointerException at L173 (keep_data_end, one surviving cluster whose centre cache is empty). */
+int  slr_grouper_group_sams(slr_grouper *g, const int32_t *position, const uint8_t *has_position, const int32_t *flags, int64_t n,
+                            int keep_data_end, int64_t *region_io, int64_t *last_index_out);
+
+/* Replaces UmiClustering.cluster up to the hand-over to its Submitter (F!…/clustering/UmiClustering.class, UmiClustering.java:L97-L118
+ * groupDataByCellAndRegion, L135 size filter, L136-L142 split of oversized groups): the reads with valid[i] != 0 (a cell barcode AND a region
+ * number; NULL = all) grouped by (cell_bc, region); groups of fewer than min_size reads (the reference: 2) are dropped; ram_reserved != 0 cuts a
+ * group of n reads into ceil((float) n / sqrt(ram_reserved / 300)) consecutive parts of n / nChunks + 1 reads like the reference's memory bound
+ * does (RAM_RESERVED, UmiClustering.java:L59; 0 = never split — the GPU has no such bound, but the split changes the clusters).
+ * order_out (capacity n): read indices, job j = order_out[job_offsets_out[j] .. job_offsets_out[j + 1]) in input order; job_offsets_out has
+ * capacity n + 1; jobs in ascending (cell_bc, region) order (the reference's map iteration order reaches no per-read result). */
+int  slr_group_jobs(const uint64_t *cell_bc, const int64_t *region, const uint8_t *valid, int64_t n, int min_size, int64_t ram_reserved,
+                    int64_t *order_out, int64_t *job_offsets_out, int64_t *n_jobs_out);
 
 /* ---- misc ------------------------------------------------------------------------------------------- */
 const char *slr_last_error(void);

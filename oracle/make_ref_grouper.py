@@ -210,11 +210,7 @@ def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 160
     vm = make_vm()
     rng = np.random.default_rng(20261018)
-    sys.path.insert(0, os.path.join(ROOT))
-    import importlib
-    import __graft_entry__ as g
-    g.load_package()
-    grouping = importlib.import_module("sicelore_b200.grouping")
+    from oracle import pyref_group as grouping
     t0 = time.time()
     rows = []                                                                 # one row per groupSams call
     carried = []                                                              # (objects, pos, flags, has, region) of the running chain
@@ -246,7 +242,7 @@ def main():
         id1 = region_counter(vm)
         rows.append(dict(pos=pos, flags=flags, has=has, reg_in=reg_in, keep=keep, max_dist=max_dist, id0=id0, id1=id1, thrown=thrown,
                          n_done=n_done, n_carried=len(car), reg=np.array(reg, dtype=np.int64)))
-        # the mirror, for immediate feedback
+        # the Python restatement, for immediate feedback
         G = grouping.ReadGrouper(max_dist, id0)
         r2 = reg_in.copy()
         try:
@@ -257,7 +253,7 @@ def main():
         got = (thrown, n_done, id1, reg)
         if exp[:3] != got[:3] or (not thrown and exp[3] != got[3]):
             n_bad += 1
-            print("    MIRROR DIFFERS case %d: exp %s got %s" % (t, exp[:3], got[:3]))
+            print("    PYREF DIFFERS case %d: exp %s got %s" % (t, exp[:3], got[:3]))
         k = len(objs) - len(car)
         carried = (car, pos[k:], flags[k:], has[k:], np.array(reg[k:], dtype=np.int64)) if car and not thrown else []
         print("  case %d / %d (n = %d, max %d, keep %d): done %d carried %d regions %d..%d %s, %.0f s, %d bytecodes" %
@@ -269,7 +265,7 @@ def main():
                         region_in=cat("reg_in", np.int64), region_out=cat("reg", np.int64), keep_data_end=col("keep", np.uint8),
                         max_dist=col("max_dist", np.int32), id_before=col("id0", np.int64), id_after=col("id1", np.int64),
                         thrown=np.array([r["thrown"] for r in rows]), n_done=col("n_done", np.int64), n_carried=col("n_carried", np.int64))
-    print("ReadGrouper.groupSams: %d calls, %d reads, %d region numbers consumed, %d thrown, mirror differs on %d, %.0f s, %d bytecodes" %
+    print("ReadGrouper.groupSams: %d calls, %d reads, %d region numbers consumed, %d thrown, pyref differs on %d, %.0f s, %d bytecodes" %
           (len(rows), int(off[-1]), region_counter(vm), sum(bool(r["thrown"]) for r in rows), n_bad, time.time() - t0, vm.n_insn))
 
 

@@ -25,7 +25,7 @@ LIB_SYNTH = os.path.join(_HERE, "libslr_synth.so")
 NVCC = os.environ.get("SLR_NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++"            # $CXX in this image points at a gcc without libgomp
 
-SLR_OK, SLR_E_INVALID, SLR_E_NODEVICE, SLR_E_CUDA, SLR_E_NOMEM, SLR_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+SLR_OK, SLR_E_INVALID, SLR_E_NODEVICE, SLR_E_CUDA, SLR_E_NOMEM, SLR_E_UNSUPPORTED, SLR_E_REFERENCE_THROWS = 0, -1, -2, -3, -4, -5, -6
 F_ASSIGNED, F_EXCEPTION, F_TIE_UNPIN = 1, 2, 4
 INT_MAX = 2147483647
 
@@ -50,7 +50,8 @@ EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_
            "slr_dyn_max_ed", "slr_last_error", "slr_abi_version", "slr_launch_count",
            "slr_multi_create", "slr_multi_destroy", "slr_multi_n_devices", "slr_multi_ctx", "slr_multi_peer_access", "slr_multi_bc_table_create",
            "slr_multi_bc_table_destroy", "slr_multi_bc_table_replica", "slr_multi_bc_assign", "slr_multi_bc_exact", "slr_multi_bc_counts_read",
-           "slr_multi_bc_counts_reset", "slr_multi_umi_dist", "slr_multi_umi_cluster", "slr_multi_umi_assign"]
+           "slr_multi_bc_counts_reset", "slr_multi_umi_dist", "slr_multi_umi_cluster", "slr_multi_umi_assign",
+           "slr_grouper_create", "slr_grouper_destroy", "slr_grouper_next_region_id", "slr_grouper_group_sams", "slr_group_jobs"]
 
 
 class SiceloreGpuError(RuntimeError):
@@ -78,7 +79,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
     cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu", "umi_assign_deep.cu",
-                                           "guided_match.cu", "slr_multi.cu")]
+                                           "guided_match.cu", "slr_multi.cu", "slr_group.cpp")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -110,6 +111,13 @@ def gpu_lib():
         L.slr_ctx_destroy.restype = None
         L.slr_ctx_device.argtypes = [vp]
         L.slr_bc_table_create.argtypes = [vp, vp, vp, i64, i32, C.POINTER(vp)]
+        L.slr_grouper_create.argtypes = [i32, i64, C.POINTER(vp)]
+        L.slr_grouper_destroy.argtypes = [vp]
+        L.slr_grouper_destroy.restype = None
+        L.slr_grouper_next_region_id.argtypes = [vp]
+        L.slr_grouper_next_region_id.restype = i64
+        L.slr_grouper_group_sams.argtypes = [vp, vp, vp, vp, i64, i32, vp, C.POINTER(i64)]
+        L.slr_group_jobs.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, C.POINTER(i64)]
         L.slr_bc_table_destroy.argtypes = [vp]
         L.slr_bc_table_destroy.restype = None
         L.slr_bc_table_size.argtypes = [vp]

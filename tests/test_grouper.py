@@ -1,6 +1,7 @@
-"""ReadGrouper.groupSams (the grouping that produces the clustering jobs): the host mirror `sicelore_b200.grouping` against
-vectors the reference's own bytecode produced (oracle/make_ref_grouper.py -> tests/golden/ref_grouper.npz), and the properties of the
-chunk loop around it.  CPU only — the grouping is the caller's side of the C ABI."""
+"""ReadGrouper.groupSams and the job former (the grouping that produces the clustering jobs): the library's native host code
+(csrc/slr_group.cpp through `sicelore_b200.grouping`) and the Python restatement `oracle/pyref_group.py` against vectors the reference's own
+bytecode produced (oracle/make_ref_grouper.py -> tests/golden/ref_grouper.npz, oracle/make_ref_jobs.py -> ref_jobs.npz), and the properties
+of the chunk loop around it.  No GPU needed: this is host code on both sides (the reference runs it on its BAM reader thread)."""
 import importlib
 import os
 
@@ -14,8 +15,14 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_g
 
 @pytest.fixture(scope="module")
 def grouping():
-    g.load_package()
+    g.load_package().build()
     return importlib.import_module("sicelore_b200.grouping")
+
+
+@pytest.fixture(scope="module")
+def pyg():
+    from oracle import pyref_group
+    return pyref_group
 
 
 @pytest.fixture(scope="module")
@@ -47,18 +54,20 @@ def replay(grouping, z, make_grouper=None):
     return bad
 
 
-def test_mirror_matches_reference_bytecode(grouping, gold):
+def test_native_grouper_matches_reference_bytecode(grouping, pyg, gold):
     z = gold
     assert len(z["offsets"]) - 1 >= 400 and int(z["offsets"][-1]) >= 15000
-    assert replay(grouping, z) == []
+    assert replay(grouping, z) == []                                        # slr_grouper_group_sams
+    assert replay(pyg, z) == []                                             # the independent Python restatement
     # what the vectors contain: an exception case, carried-over reads with a region number from the previous round, reads without a position
     assert (z["thrown"] != "").sum() >= 1
     assert (z["region_in"] >= 0).sum() > 100 and (z["has_position"] == 0).sum() > 10 and (z["n_carried"] > 0).sum() > 50
     assert (z["position"] > (1 << 24)).sum() > 1000
 
 
-def test_vectors_pin_every_quirk(grouping, gold):
-    """each behaviour a cleaner implementation would not have (grouping.py docstring) changes at least one recorded outcome"""
+def test_vectors_pin_every_quirk(pyg, gold):
+    """each behaviour a cleaner implementation would not have (oracle/pyref_group.py docstring) changes at least one recorded outcome"""
+    grouping = pyg
     G0, C0 = grouping.ReadGrouper, grouping._Cluster
 
     def variant(**patch):
@@ -177,14 +186,16 @@ def test_grouper_feeds_the_job_former(grouping):
     cell = rng.integers(1, 40, n).astype(np.uint64)
     G = grouping.ReadGrouper(500)
     region, _ = grouping.group_stream(G, pos, flags, np.zeros(n, dtype=np.int64), 1000)
-    order, off = pkg.group_by_cell_and_region(cell, region, region >= 0)
+    order, off = grouping.group_jobs(cell, region, region >= 0)
+    o2, off2 = pkg.group_by_cell_and_region(cell, region, region >= 0)
+    assert np.array_equal(order, o2) and np.array_equal(off, off2)
     assert len(off) > 100 and off[-1] == len(order)
     for j in range(len(off) - 1):
         ids = order[off[j]:off[j + 1]]
         assert len(ids) >= 2 and len(set(cell[ids].tolist())) == 1 and len(set(region[ids].tolist())) == 1
 
 
-def test_job_former_matches_reference_bytecode():
+def test_job_former_matches_reference_bytecode(grouping):
     """UmiClustering.cluster up to its Submitter (groupDataByCellAndRegion, size filter, split of oversized groups; UmiClustering.java:L97-L145)
     run from the class files by oracle/make_ref_jobs.py: the host mirrors form the same set of jobs, reads inside a job in input order"""
     pkg = g.load_package()
@@ -206,4 +217,6 @@ def test_job_former_matches_reference_bytecode():
                 got.append(ids[a:a + sz])
                 a += sz
         assert sorted(got) == want, c
+        order, o = grouping.group_jobs(bc.astype(np.uint64), region, (bc >= 0) & (region >= 0), 2, int(z["ram"][c]))      # slr_group_jobs
+        assert sorted(order[o[j]:o[j + 1]].tolist() for j in range(len(o) - 1)) == want, c
     assert n_split > 20
