@@ -12,6 +12,10 @@ import pytest
 from oracle import pyref
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# narrow sets (oracle/make_ref_vectors.py) + wide sets with other seeds (oracle/make_ref_guided_wide.py), same layout
+FIND_UMI_FILES = ["ref_find_umi.npz", "ref_find_umi_wide.npz"]
+TEST_BARCODES_FILES = ["ref_test_barcodes.npz", "ref_test_barcodes_wide.npz"]
+GUIDED_FILES = ["ref_guided.npz", "ref_guided_wide.npz"]
 M64 = (1 << 64) - 1
 
 
@@ -66,10 +70,11 @@ def test_dojob_matches_reference_bytecode(orc):
     assert {int(e) for e in z["res"][:, 3]} == {0, 1, 2}                        # hits at every ED level
 
 
-def test_guided_engine_matches_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", GUIDED_FILES)
+def test_guided_engine_matches_reference_bytecode(orc, fname):
     """UMInuc / BCnucTwoBitPerBaseEDtester.matchesSeqEditDistance run by the reference's own class files: the whole ArrayList in list order
     (duplicates, counters, startOffsetFromPredicted, findingErrorFlag incl. the GENE bit inherited by descendants), with and without bailout"""
-    z = np.load(os.path.join(GOLDEN, "ref_guided.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     fg, fa, fe = int(z["flag_gene"]), int(z["flag_all"]), int(z["flag_empty"])
     n_entries = 0
     flags_seen = set()
@@ -278,12 +283,37 @@ def test_gpu_assign_barcode_matches_reference_bytecode(pkg, ctx):
     assert checked == 40
 
 
+@pytest.mark.parametrize("fname", GUIDED_FILES)
+def test_sim_guided_engine_matches_reference_bytecode(sim, orc, fname):
+    """the guided kernel's per-lane code (CPU replay) against the reference's own matchesSeqEditDistance lists: raw list in list order"""
+    import workloads
+    z = np.load(os.path.join(GOLDEN, fname))
+    fg, fa, fe = int(z["flag_gene"]), int(z["flag_all"]), int(z["flag_empty"])
+    n_entries = 0
+    for i in range(len(z["w"])):
+        sl_ = lambda k, o: z[k][z[o][i]:z[o][i + 1]]
+        keys, allk, empk = sl_("keys", "key_offsets"), sl_("all_keys", "all_offsets"), sl_("empty_keys", "empty_offsets")
+        bc, L, ed, bail, w = bool(z["bc"][i]), int(z["L"][i]), int(z["ed"][i]), int(z["bail"][i]), int(z["w"][i])
+        post = str(z["post"][i]).rstrip("-")
+        s = (workloads.g_unpack(w, L) + post).ljust(32, "A").encode()
+        res, raw = _sim_guided_one(sim, orc, keys, L, np.frombuffer(s, dtype=np.uint8).reshape(1, 32), np.array([0], dtype=np.int32), ed, 0, len(post),
+                                   bail, 32, bc=bc, allk=allk if bc else None, empk=empk if bc else None)
+        exp = z["res"][z["res"][:, 0] == i][:, 1:]
+        assert not res[0]["flags"] and res[0]["n_raw"] == len(exp), (i, res[0], len(exp))
+        for g, e in zip(raw[0], exp[:64]):
+            where = (1 if int(e[5]) & fg else 0) | (2 if int(e[5]) & fa else 0) | (4 if int(e[5]) & fe else 0)
+            assert (int(g["seq"]), g["n_sub"], g["n_ins"], g["n_del"], g["where"]) == (int(e[0]) & M64, e[1], e[2], e[3], where), (i, g, e)
+        n_entries += len(exp)
+    assert n_entries >= (400 if "wide" in fname else 100)
+
+
 @pytest.mark.gpu
-def test_gpu_guided_engine_matches_reference_bytecode(pkg, ctx):
+@pytest.mark.parametrize("fname", GUIDED_FILES)
+def test_gpu_guided_engine_matches_reference_bytecode(pkg, ctx, fname):
     """the guided kernel's raw list (plusminus 0: one tester) against UMInuc / BCnucTwoBitPerBaseEDtester.matchesSeqEditDistance as run from the
     reference's class files; startOffsetFromPredicted is a label the caller passes and is not compared"""
     import workloads
-    z = np.load(os.path.join(GOLDEN, "ref_guided.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     fg, fa, fe = int(z["flag_gene"]), int(z["flag_all"]), int(z["flag_empty"])
     for i in range(len(z["w"])):
         sl_ = lambda k, o: z[k][z[o][i]:z[o][i + 1]]
@@ -333,6 +363,26 @@ def test_gpu_umi_distance_matches_reference_bytecode(pkg, ctx):
     assert (got == z["packed"].astype(np.int32)).all(), np.nonzero(got != z["packed"].astype(np.int32))[0][:5]
 
 
+def _sim_guided_one(sim, orc, keys, L, sl, anchor, ed, pm, post_len, bail, slen, bc=False, allk=None, empk=None, raw_cap=64):
+    """one read through the CPU replay of the guided kernel's per-lane code (tests/host_sim): what the GPU computes, without a GPU"""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    goff = np.array([0, len(keys)], dtype=np.int64)
+    ak = None if allk is None else np.ascontiguousarray(allk, dtype=np.uint64)
+    ek = None if empk is None else np.ascontiguousarray(empk, dtype=np.uint64)
+    out = np.zeros(1, dtype=orc.GUIDED_RESULT)
+    raw = np.zeros((1, raw_cap), dtype=orc.GUIDED_HIT)
+    sl = np.ascontiguousarray(sl, dtype=np.uint8)
+    anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+    gid = np.zeros(1, dtype=np.int32)
+    edv = np.array([ed], dtype=np.int32)
+    sim.sim_guided_batch(keys.ctypes.data, goff.ctypes.data, 1, None if ak is None else ak.ctypes.data, 0 if ak is None else len(ak), 3,
+                         None if ek is None else ek.ctypes.data, 0 if ek is None else len(ek), 2, int(bc), L, pm, bail, post_len,
+                         sl.ctypes.data, 32, slen, anchor.ctypes.data, gid.ctypes.data, edv.ctypes.data, 1, out.ctypes.data, raw.ctypes.data, raw_cap)
+    return out, raw
+
+
+
+
 def _find_umi_inputs(z, i):
     """the S4 boundary for read i: 32-byte stranded slice, anchor = window start of offset 0 (IlluminaUMIanalyzer.java:L102, L112-L124)"""
     s, bc_end, ed, pm = str(z["stranded"][i]), int(z["bc_end"][i]), int(z["ed"][i]), int(z["pm"][i])
@@ -354,7 +404,17 @@ def _check_find_umi(z, i, r, pack):
         assert r["flags"] & 1, (i, str(z["exc"][i]))
         return "exc"
     assert not r["flags"], (i, r)
-    assert (r["n_distinct"] > 0) == bool(found), (i, r, row)            # found <=> the list is not empty (java:L220)
+    if not found and has_second:
+        # MORE_THAN_ONE_MATCH: the list holds two distinct survivors whose NeedlemanWunsch alignments tie (nMismatchDiffBestvsSecondBest == 0), so
+        # failedUMIfinding(flag) turns found off (java:L203, L208, L220).  The alignment step stays Java; the record must deliver both
+        # survivors, and the best one's geometry is what the reference derived the read positions from (L205-L206)
+        assert flag & 4 and flag & 2 and int(row[10]) == 0, (i, row)
+        assert r["n_distinct"] == 2, (i, r, row)
+        assert int(r["seq"][1]) == pack(str(z["second"][i])), (i, r, str(z["second"][i]))
+        start = 500 - (1 + int(r["offset"][0]))
+        assert (int(row[8]), int(row[9])) == (start, start - (12 - 1 + int(r["n_ins"][0]) - int(r["n_del"][0]))), (i, r, row)
+        return "ambiguous"
+    assert (r["n_distinct"] > 0) == bool(found), (i, r, row)            # otherwise found <=> the list is not empty (java:L220)
     if not found:
         assert flag & 2 or flag != 0                                    # UMI_NOT_FOUND was set
         return "none"
@@ -368,12 +428,14 @@ def _check_find_umi(z, i, r, pack):
     return "second" if has_second else "one"
 
 
-def test_find_umi_matches_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", FIND_UMI_FILES)
+def test_find_umi_matches_reference_bytecode(orc, fname):
     """IlluminaUMIanalyzer.findUMI as a whole, run by the reference's class files: offset loop and window / post geometry, the testers,
     getBestAndSecondBCorUMI (sorted().distinct(), Needleman alignments): found / not found, the best entry (sequence, counters, offset), whether a
     second-best exists and which sequence it is, and the read positions derived from the record"""
     import workloads
-    z = np.load(os.path.join(GOLDEN, "ref_find_umi.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
+    assert len(z["ed"]) >= (150 if "wide" in fname else 40)
     kinds = set()
     for i in range(len(z["ed"])):
         sl, anchor, ed, pm, post_len, slen = _find_umi_inputs(z, i)
@@ -381,13 +443,26 @@ def test_find_umi_matches_reference_bytecode(orc):
         res, _, _ = orc.guided_batch(umis, np.array([0, len(umis)], dtype=np.int64), sl, anchor, np.array([0], dtype=np.int32), ed, 12, pm, post_len,
                                      bailout=int(z["bail"][i]), slice_len=slen)
         kinds.add(_check_find_umi(z, i, res[0], workloads.g_pack))
-    assert {"none", "one", "second"} <= kinds
+    assert {"none", "one", "second"} <= kinds and ("ambiguous" in kinds or "wide" not in fname)
+
+
+@pytest.mark.parametrize("fname", FIND_UMI_FILES)
+def test_sim_find_umi_matches_reference_bytecode(sim, orc, fname):
+    """the same vectors through the CPU replay of the guided kernel's per-lane code"""
+    import workloads
+    z = np.load(os.path.join(GOLDEN, fname))
+    for i in range(len(z["ed"])):
+        sl, anchor, ed, pm, post_len, slen = _find_umi_inputs(z, i)
+        umis = z["umis"][z["umi_offsets"][i]:z["umi_offsets"][i + 1]]
+        res, _ = _sim_guided_one(sim, orc, umis, 12, sl, anchor, ed, pm, post_len, int(z["bail"][i]), slen)
+        _check_find_umi(z, i, res[0], workloads.g_pack)
 
 
 @pytest.mark.gpu
-def test_gpu_find_umi_matches_reference_bytecode(pkg, ctx):
+@pytest.mark.parametrize("fname", FIND_UMI_FILES)
+def test_gpu_find_umi_matches_reference_bytecode(pkg, ctx, fname):
     import workloads
-    z = np.load(os.path.join(GOLDEN, "ref_find_umi.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     for i in range(len(z["ed"])):
         sl, anchor, ed, pm, post_len, slen = _find_umi_inputs(z, i)
         umis = z["umis"][z["umi_offsets"][i]:z["umi_offsets"][i + 1]]
@@ -487,11 +562,13 @@ def _check_test_barcodes(z, i, r):
     return "second" if z["n_distinct"][i] == 2 else "one"
 
 
-def test_test_barcodes_matches_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", TEST_BARCODES_FILES)
+def test_test_barcodes_matches_reference_bytecode(orc, fname):
     """IlluminaBarcodeAnalyzer.testBarcodes (one gene) + getBestAndSecondBCorUMI(CELLBC) run by the reference's class files: BC-flavour offset loop
     and geometry, the three candidate lists with their ED limits, bailout, the comparator with scoreWhereFound (ascending!), distinct, the
     second-best match, the list size and the minimum error count of GENE entries"""
-    z = np.load(os.path.join(GOLDEN, "ref_test_barcodes.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
+    assert len(z["ed"]) >= (80 if "wide" in fname else 20)
     kinds = set()
     for i in range(len(z["ed"])):
         sl, anchor, slen, gene, allk, empk = _test_barcodes_inputs(z, i)
@@ -501,9 +578,20 @@ def test_test_barcodes_matches_reference_bytecode(orc):
     assert {"none", "one", "second"} <= kinds or {"none", "second"} <= kinds
 
 
+@pytest.mark.parametrize("fname", TEST_BARCODES_FILES)
+def test_sim_test_barcodes_matches_reference_bytecode(sim, orc, fname):
+    """the same vectors through the CPU replay of the guided kernel's per-lane code"""
+    z = np.load(os.path.join(GOLDEN, fname))
+    for i in range(len(z["ed"])):
+        sl, anchor, slen, gene, allk, empk = _test_barcodes_inputs(z, i)
+        res, _ = _sim_guided_one(sim, orc, gene, 16, sl, anchor, int(z["ed"][i]), int(z["pm"][i]), 10, int(z["bail"][i]), slen, bc=True, allk=allk, empk=empk)
+        _check_test_barcodes(z, i, res[0])
+
+
 @pytest.mark.gpu
-def test_gpu_test_barcodes_matches_reference_bytecode(pkg, ctx):
-    z = np.load(os.path.join(GOLDEN, "ref_test_barcodes.npz"))
+@pytest.mark.parametrize("fname", TEST_BARCODES_FILES)
+def test_gpu_test_barcodes_matches_reference_bytecode(pkg, ctx, fname):
+    z = np.load(os.path.join(GOLDEN, fname))
     for i in range(len(z["ed"])):
         sl, anchor, slen, gene, allk, empk = _test_barcodes_inputs(z, i)
         bail = int(z["bail"][i])
