@@ -305,7 +305,8 @@ int  slr_umi_session_assign(struct slr_umi_session *s, const slr_umi_assign_para
  * per offset (F!com/rw/nuc/encoding/TwoBit/ed/BCUMIEDtesterBase.class, BCUMIEDtesterBase.java:L82-L203) with the
  * checkMatchWithTestSets of UMInucTwoBitPerBaseEDtester (…java:L52-L67) or BCnucTwoBitPerBaseEDtester (…java:L72-L92) — and
  * the sorted().distinct() reduction of the collected list (IlluminaBarcodeUMIAnalyzerBase.getBestAndSecondBCorUMI,
- * …java:L52-L60; testBarcodes L336-L339).  The host keeps the Needleman alignment of the two survivors and all flags. */
+ * …java:L52-L60; testBarcodes L336-L339).  The Needleman comparison of the two survivors is slr_guided_mismatch_diff below (host arithmetic);
+ * the host keeps the flags. */
 typedef struct slr_guided_sets slr_guided_sets;    /* device-resident candidate sets */
 
 #define SLR_G_W_GENE  1u   /* entry (or an ancestor node) was found in the per-gene list: BARCODE_FOUND_FOR_GENE_OR_GENOMIC_REGION */
@@ -359,6 +360,21 @@ int  slr_guided_match_dev(slr_ctx *ctx, const slr_guided_sets *s, int plusminus,
                           const uint8_t *d_slices, int stride, int slice_len, const int32_t *d_anchor, const int32_t *d_group_id,
                           const int32_t *d_ed, int max_ed, int64_t n, slr_guided_result *d_out, slr_guided_hit *d_raw_out,
                           int raw_cap, void *stream);
+
+/* The alignment comparison that decides MORE_THAN_ONE_MATCH (host arithmetic on the two survivors of a record, no device): replaces the two
+ * NeedlemanWunsch alignments of IlluminaBarcodeUMIAnalyzerBase.getBestAndSecondBCorUMI (…java:L66-L79; T!com/rw/nuc/alignment/needleman/
+ * NeedlemanWunsch.class) and NeedlemanMatch.countNeedlemanErrorsInRead (F!com/rw/nanopore/analyzers/NeedlemanMatch.class, …java:L68-L86).
+ * scores = the reference's NeedlemanScores (NeedlemanParameters.umi / .bc), NULL = its defaults (-4, -5, -5, -5, -5, -5, 5). */
+typedef struct { int32_t leading_gap_1, leading_gap_2, trailing_gap_1, trailing_gap_2, indel, mismatch, match; } slr_needleman_scores;
+#define SLR_G_NO_SECOND INT32_MIN      /* slr_guided_mismatch_diff: the record has no second-best entry (or is flagged) */
+/* one alignment: candidate (template) vs read window, both 2-bit packed, len <= 32; counts_out[4] = insertionsNeedleman, deletionsNeedleman
+ * (gaps at the end of the read row are not counted), substitutionsNeedleman, their sum (getNerrorsNeedleman) */
+int  slr_needleman_errors(uint64_t template2bit, uint64_t read2bit, int len, const slr_needleman_scores *scores, int32_t *counts_out);
+/* per record of slr_guided_match (same slices / anchor / seq_len): diff_out[i] = nMismatchDiffBestvsSecondBest = errors(second) - errors(best),
+ * each entry aligned to the window at anchor + offset it was found from (its unMutatedSeq); SLR_G_NO_SECOND when n_distinct < 2.
+ * diff == 0 <=> the reference sets MORE_THAN_ONE_MATCH (…java:L80-L86), i.e. the read counts as not found (IlluminaUMIanalyzer.java:L203-L220). */
+int  slr_guided_mismatch_diff(const slr_guided_result *res, int64_t n, const uint8_t *slices, int stride, int slice_len, const int32_t *anchor,
+                              int seq_len, const slr_needleman_scores *scores, int32_t *diff_out);
 
 /* DynamicEditDistances.getmaxED (F!com/rw/parameters/DynamicEditDistances.class, DynamicEditDistances.java:L93-L98): the largest
  * edit distance e whose max_candidates[e] >= count * (2 * plusminus + 1), capped at `cap` (< 0 = null).  max_candidates = one

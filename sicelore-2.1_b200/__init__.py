@@ -51,7 +51,7 @@ EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_
            "slr_multi_create", "slr_multi_destroy", "slr_multi_n_devices", "slr_multi_ctx", "slr_multi_peer_access", "slr_multi_bc_table_create",
            "slr_multi_bc_table_destroy", "slr_multi_bc_table_replica", "slr_multi_bc_assign", "slr_multi_bc_exact", "slr_multi_bc_counts_read",
            "slr_multi_bc_counts_reset", "slr_multi_umi_dist", "slr_multi_umi_cluster", "slr_multi_umi_assign",
-           "slr_grouper_create", "slr_grouper_destroy", "slr_grouper_next_region_id", "slr_grouper_group_sams", "slr_group_jobs"]
+           "slr_grouper_create", "slr_grouper_destroy", "slr_grouper_next_region_id", "slr_grouper_group_sams", "slr_group_jobs", "slr_needleman_errors", "slr_guided_mismatch_diff"]
 
 
 class SiceloreGpuError(RuntimeError):
@@ -79,7 +79,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
     cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu", "umi_assign_deep.cu",
-                                           "guided_match.cu", "slr_multi.cu", "slr_group.cpp")]
+                                           "guided_match.cu", "slr_multi.cu", "slr_group.cpp", "slr_needleman.cpp")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -118,6 +118,8 @@ def gpu_lib():
         L.slr_grouper_next_region_id.restype = i64
         L.slr_grouper_group_sams.argtypes = [vp, vp, vp, vp, i64, i32, vp, C.POINTER(i64)]
         L.slr_group_jobs.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, C.POINTER(i64)]
+        L.slr_needleman_errors.argtypes = [C.c_uint64, C.c_uint64, i32, vp, vp]
+        L.slr_guided_mismatch_diff.argtypes = [vp, i64, vp, i32, i32, vp, i32, vp, vp]
         L.slr_bc_table_destroy.argtypes = [vp]
         L.slr_bc_table_destroy.restype = None
         L.slr_bc_table_size.argtypes = [vp]
@@ -660,6 +662,39 @@ class GuidedSets:
             self.close()
         except Exception:
             pass
+
+G_NO_SECOND = -(1 << 31)
+
+
+class NeedlemanScores(C.Structure):
+    """NeedlemanScores (T!com/rw/nuc/alignment/needleman/NeedlemanScores.class, …java:L44-L56), defaults as in the reference"""
+    _fields_ = [(k, C.c_int32) for k in ("leading_gap_1", "leading_gap_2", "trailing_gap_1", "trailing_gap_2", "indel", "mismatch", "match")]
+
+    def __init__(self, leading_gap_1=-4, leading_gap_2=-5, trailing_gap_1=-5, trailing_gap_2=-5, indel=-5, mismatch=-5, match=5):
+        super().__init__(leading_gap_1, leading_gap_2, trailing_gap_1, trailing_gap_2, indel, mismatch, match)
+
+
+def needleman_errors(template2bit, read2bit, length, scores=None):
+    """NeedlemanWunsch(template, read, scores) + NeedlemanMatch.countNeedlemanErrorsInRead (slr_needleman_errors): (insertions, deletions,
+    substitutions, total) of the alignment of two 2-bit packed sequences"""
+    cnt = (C.c_int32 * 4)()
+    _check(gpu_lib().slr_needleman_errors(int(template2bit), int(read2bit), int(length), C.byref(scores) if scores is not None else None, cnt))
+    return tuple(cnt)
+
+
+def guided_mismatch_diff(res, slices, anchor, seq_len, slice_len=None, scores=None):
+    """nMismatchDiffBestvsSecondBest per record of GuidedSets.match (slr_guided_mismatch_diff; IlluminaBarcodeUMIAnalyzerBase.java:L66-L86):
+    0 = MORE_THAN_ONE_MATCH (the reference then reports the read as not found), G_NO_SECOND = no second-best entry"""
+    res = np.ascontiguousarray(res, dtype=GUIDED_RESULT)
+    slices = np.ascontiguousarray(slices, dtype=np.uint8)
+    anchor = np.ascontiguousarray(anchor, dtype=np.int32)
+    n, stride = slices.shape
+    assert res.shape == (n,) and anchor.shape == (n,)
+    out = np.empty(n, dtype=np.int32)
+    _check(gpu_lib().slr_guided_mismatch_diff(res.ctypes.data, n, slices.ctypes.data, stride, stride if slice_len is None else int(slice_len),
+                                              anchor.ctypes.data, int(seq_len), C.byref(scores) if scores is not None else None, out.ctypes.data))
+    return out
+
 
 # ---------------------------------------------------------------------------------------------- UMI distances
 class BestEditDistance:
