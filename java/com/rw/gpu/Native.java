@@ -82,6 +82,10 @@ public final class Native {
     public static native int guidedMatch(long ctx, long sets, int plusMinus, int postLen, int bailout, ByteBuffer slices, int stride, int sliceLen,
                                          ByteBuffer anchor, ByteBuffer groupId, ByteBuffer ed, long n, ByteBuffer out, ByteBuffer rawOut, int rawCap);
     /** DynamicEditDistances.getmaxED (DynamicEditDistances.java:L93-L98); cap < 0 = null; -1 = NoSuchElementException */
+    /** nMismatchDiffBestvsSecondBest per record of guidedMatch (IlluminaBarcodeUMIAnalyzerBase.java:L66-L86): 0 = MORE_THAN_ONE_MATCH,
+     *  Integer.MIN_VALUE = no second-best entry; scores7 = NeedlemanScores fields in declaration order or null = defaults */
+    public static native int guidedMismatchDiff(ByteBuffer records, long n, ByteBuffer slices, int stride, int sliceLen, ByteBuffer anchor,
+                                                int seqLen, int[] scores7, ByteBuffer diffOut);
     public static native int dynMaxEd(long[] maxCandidates, int count, int plusMinus, int cap);
     public static native String lastError();
     public static native int abiVersion();

@@ -479,6 +479,30 @@ JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_guidedMatch(JNIEnv *env, jclass cl
                             ro, rawCap);
 }
 
+/* scores7: NeedlemanScores {leading_gap_1, leading_gap_2, trailing_gap_1, trailing_gap_2, indel, mismatch, match} or null = the reference's defaults */
+JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_guidedMismatchDiff(JNIEnv *env, jclass cls, jobject records, jlong n, jobject slices, jint stride,
+                                                                 jint sliceLen, jobject anchor, jint seqLen, jintArray scores7, jobject diffOut)
+{
+    (void)cls;
+    int ok = n >= 0 && stride > 0;
+    const slr_guided_result *r = (const slr_guided_result *)buf(env, records, (int64_t)n * (int64_t)sizeof(slr_guided_result), 1, &ok);
+    const uint8_t *sl = (const uint8_t *)buf(env, slices, (int64_t)n * stride, 1, &ok);
+    const int32_t *an = (const int32_t *)buf(env, anchor, (int64_t)n * 4, 1, &ok);
+    int32_t *d = (int32_t *)buf(env, diffOut, (int64_t)n * 4, 1, &ok);
+    if (!ok) return SLR_E_INVALID;
+    slr_needleman_scores sc;
+    const slr_needleman_scores *psc = NULL;
+    if (scores7) {
+        if ((*env)->GetArrayLength(env, scores7) != 7) return SLR_E_INVALID;
+        jint *v = (*env)->GetIntArrayElements(env, scores7, NULL);
+        if (!v) return SLR_E_INVALID;
+        sc.leading_gap_1 = v[0]; sc.leading_gap_2 = v[1]; sc.trailing_gap_1 = v[2]; sc.trailing_gap_2 = v[3]; sc.indel = v[4]; sc.mismatch = v[5]; sc.match = v[6];
+        (*env)->ReleaseIntArrayElements(env, scores7, v, JNI_ABORT);
+        psc = &sc;
+    }
+    return slr_guided_mismatch_diff(r, (int64_t)n, sl, stride, sliceLen, an, seqLen, psc, d);
+}
+
 JNIEXPORT jint JNICALL Java_com_rw_gpu_Native_dynMaxEd(JNIEnv *env, jclass cls, jlongArray maxCandidates, jint count, jint plusMinus, jint cap)
 {
     (void)cls;

@@ -501,7 +501,8 @@ def test_barcodes_cases(vm, rng, n):
                                        [r, e.v[1], J.JNative("java/util/Optional", (m,)), sw.statics["CELLBC"], scores])
                 sec = m.f["secondBestMatch"]
                 sec_seq = pack(sec.f["alignment"].f["match"].replace("-", "")) if sec is not None else 0
-                row.update(n_raw=len(lst), best=ent(best), second=[sec_seq, 0, 0, 0, 0, 0], n_distinct=2 if sec is not None else 1, min_err_gene=min(ge) if ge else 2147483647)
+                row.update(n_raw=len(lst), best=ent(best), second=[sec_seq, 0, 0, 0, 0, 0], n_distinct=2 if sec is not None else 1, min_err_gene=min(ge) if ge else 2147483647,
+                           mismatch_diff=-99 if m.f["nMismatchDiffBestvsSecondBest"] is None else int(m.f["nMismatchDiffBestvsSecondBest"]), bc_flag=int(r.f["bcFindingFlagValue"]))
         except J.JavaThrow as ex:
             row.update(exc=ex.cls, n_raw=0, best=[0] * 6, second=[0] * 6, n_distinct=0, min_err_gene=2147483647)
         cases.append(row)
@@ -730,7 +731,9 @@ def save_test_barcodes(tb):
                         empty_keys=ek, empty_offsets=eo, ed=np.array([c["ed"] for c in tb], dtype=np.int32), pm=np.array([c["pm"] for c in tb], dtype=np.int32),
                         bail=np.array([c["bail"] for c in tb], dtype=np.int32), exc=np.array([c["exc"] for c in tb]), n_raw=np.array([c["n_raw"] for c in tb], dtype=np.int64),
                         best=np.array([c["best"] for c in tb], dtype=np.int64), second=np.array([c["second"] for c in tb], dtype=np.int64),
-                        n_distinct=np.array([c["n_distinct"] for c in tb], dtype=np.int32), min_err_gene=np.array([c["min_err_gene"] for c in tb], dtype=np.int64))
+                        n_distinct=np.array([c["n_distinct"] for c in tb], dtype=np.int32), min_err_gene=np.array([c["min_err_gene"] for c in tb], dtype=np.int64),
+                        mismatch_diff=np.array([c.get("mismatch_diff", -99) for c in tb], dtype=np.int32),      # nMismatchDiffBestvsSecondBest, -99 = no second
+                        bc_flag=np.array([c.get("bc_flag", 0) for c in tb], dtype=np.int64))                     # bcFindingFlagValue after getBestAndSecondBCorUMI
 
 
 CLUSTER_SIG = "clusterLocal(Ljava/util/Collection;Lcom/rw/clustering/DistanceMatrix;)Ljava/util/Optional;"

@@ -11,7 +11,7 @@ import pytest
 import __graft_entry__ as g
 import workloads
 from oracle import pyref_needleman as P
-from test_ref_vectors import FIND_UMI_FILES, GOLDEN, _find_umi_inputs
+from test_ref_vectors import FIND_UMI_FILES, GOLDEN, TEST_BARCODES_FILES, _find_umi_inputs, _test_barcodes_inputs
 
 KEYS = ("leading_gap_1", "leading_gap_2", "trailing_gap_1", "trailing_gap_2", "indel", "mismatch", "match")
 
@@ -79,6 +79,42 @@ def test_gpu_mismatch_diff_matches_find_umi_bytecode(pk, ctx):
         return pk.GuidedSets(ctx, umis, np.array([0, len(umis)], dtype=np.int64), 12).match(sl, anchor, np.array([0], dtype=np.int32), ed, pm, post_len,
                                                                                             bailout=None if bail < 0 else bail, slice_len=slen)[0]
     _diff_check(pk, res_of)
+
+
+def _bc_diff_check(pk, res_of):
+    n_second = n_tie = 0
+    for fname in TEST_BARCODES_FILES:
+        z = np.load(os.path.join(GOLDEN, fname))
+        for i in range(len(z["ed"])):
+            if str(z["exc"][i]):
+                continue
+            sl, anchor, slen, gene, allk, empk = _test_barcodes_inputs(z, i)
+            res = res_of(gene, allk, empk, sl, anchor, int(z["ed"][i]), int(z["pm"][i]), int(z["bail"][i]), slen)
+            d = int(pk.guided_mismatch_diff(res, sl, anchor, 16, slice_len=slen)[0])
+            if z["n_distinct"][i] == 2:
+                assert d == int(z["mismatch_diff"][i]), (fname, i, d, z["mismatch_diff"][i])
+                assert (d == 0) == bool(int(z["bc_flag"][i]) & 64), (fname, i)                     # BarcodeFindingFlag.MORE_THAN_ONE_MATCH
+                n_second += 1
+                n_tie += d == 0
+            else:
+                assert d == pk.G_NO_SECOND and not int(z["bc_flag"][i]) & 64
+    assert n_second >= 60 and n_tie >= 10
+
+
+def test_mismatch_diff_matches_test_barcodes_bytecode(pk, orc):
+    """BC flavour (getBestAndSecondBCorUMI(CELLBC) after testBarcodes): records from the CPU oracle, the Needleman step from the library"""
+    def res_of(gene, allk, empk, sl, anchor, ed, pm, bail, slen):
+        return orc.guided_batch(gene, np.array([0, len(gene)], dtype=np.int64), sl, anchor, np.array([0], dtype=np.int32), ed, 16, pm, 10, bailout=bail,
+                                bc_flavour=True, all_keys=allk, all_ed=3, empty_keys=empk, empty_ed=2, slice_len=slen)[0]
+    _bc_diff_check(pk, res_of)
+
+
+@pytest.mark.gpu
+def test_gpu_mismatch_diff_matches_test_barcodes_bytecode(pk, ctx):
+    def res_of(gene, allk, empk, sl, anchor, ed, pm, bail, slen):
+        sets = pk.GuidedSets(ctx, gene, np.array([0, len(gene)], dtype=np.int64), 16, bc_flavour=True, all_keys=allk, all_ed=3, empty_keys=empk, empty_ed=2)
+        return sets.match(sl, anchor, np.array([0], dtype=np.int32), ed, pm, 10, bailout=None if bail < 0 else bail, slice_len=slen)[0]
+    _bc_diff_check(pk, res_of)
 
 
 def test_mismatch_diff_refuses_foreign_records(pk):
