@@ -425,7 +425,8 @@ int  slr_multi_umi_assign(slr_multi *m, const uint8_t *umis, int stride, int umi
 typedef struct slr_grouper slr_grouper;   /* the process-wide state of ReadGrouper: MAX_GENOME_DISTANCE_FOR_SAME_GENOMIC_REGION + the static region counter */
 
 /* ReadGrouper.setMaxGenomeDistance (config.xml:247 max_GenomeDistance_forGrouping, default 500) + ReadGrouper$Cluster.CURRENT_GENOMIC_REGION_ID
- * (ReadGrouper.java:L460; 0 at JVM start). */
+ * (ReadGrouper.java:L460; 0 at JVM start).  Like the reference's static state it is meant for ONE reader thread: calls on the same grouper must
+ * not overlap (different groupers are independent). */
 int  slr_grouper_create(int max_genome_distance, int64_t first_region_id, slr_grouper **out);
 void slr_grouper_destroy(slr_grouper *g);
 int64_t slr_grouper_next_region_id(const slr_grouper *g);

@@ -42,8 +42,11 @@ class ReadGrouper:
         """One chunk of SAM records in BAM order (arguments as slr_grouper_group_sams, include/sicelore_gpu.h).  `region` (int64, in / out):
         -1 = no region number.  Returns last_index (None for an empty chunk): reads [0, last_index] are the grouped chunk, the reads behind
         it open the next chunk when keep_data_end."""
-        position = np.ascontiguousarray(position, dtype=np.int32)
-        flags = np.ascontiguousarray(flags, dtype=np.int32)
+        p64 = np.asarray(position, dtype=np.int64)
+        if len(p64) and (p64.min() < -(1 << 31) or p64.max() >= (1 << 31)):
+            raise SiceloreGpuError(-1, "group_sams: positions are Java ints (SAM coordinates), got a value outside int32")
+        position = np.ascontiguousarray(p64, dtype=np.int32)
+        flags = np.ascontiguousarray(np.asarray(flags, dtype=np.int64) & 0xFFFF, dtype=np.int32)
         n = len(position)
         assert flags.shape == (n,) and region.shape == (n,) and region.dtype == np.int64 and region.flags.c_contiguous
         has = None if has_position is None else np.ascontiguousarray(has_position, dtype=np.uint8)
