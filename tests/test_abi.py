@@ -160,3 +160,52 @@ def test_c_driver_replays_golden_buffers(pkg, orc, tmp_path):
     for f in driver_inputs(tmp_path, orc):
         r = subprocess.run([exe, str(f)], capture_output=True, text=True)
         assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (f, r.stdout, r.stderr)
+
+
+def host_driver_inputs(tmp_path):
+    """binary dumps of the interpreter-run vectors of the host-side entry points (tests/c_driver/host_driver.c reads them)"""
+    import numpy as np
+    import __graft_entry__ as g
+    import workloads
+    pkg = g.load_package()
+    gold = os.path.join(ROOT, "tests", "golden")
+    i32, i64 = (lambda v: np.int32(v).tobytes()), (lambda v: np.int64(v).tobytes())
+    z = np.load(os.path.join(gold, "ref_grouper.npz"))
+    off = z["offsets"]
+    with open(tmp_path / "grouper.bin", "wb") as f:
+        f.write(b"SLRH" + np.uint32(1).tobytes() + i64(len(off) - 1))
+        for c in range(len(off) - 1):
+            a, b = int(off[c]), int(off[c + 1])
+            f.write(i64(b - a) + i32(z["max_dist"][c]) + i64(z["id_before"][c]) + i64(z["id_after"][c]) + i32(z["keep_data_end"][c]) +
+                    i32(bool(str(z["thrown"][c]))) + i64(z["n_done"][c]))
+            for k, dt in (("position", np.int32), ("flags", np.int32), ("has_position", np.uint8), ("region_in", np.int64), ("region_out", np.int64)):
+                f.write(np.ascontiguousarray(z[k][a:b], dtype=dt).tobytes())
+    z = np.load(os.path.join(gold, "ref_jobs.npz"))
+    off, joff = z["offsets"], z["job_offsets"]
+    with open(tmp_path / "jobs.bin", "wb") as f:
+        f.write(b"SLRH" + np.uint32(2).tobytes() + i64(len(off) - 1))
+        for c in range(len(off) - 1):
+            bc, region = z["barcode"][off[c]:off[c + 1]], z["region"][off[c]:off[c + 1]]
+            valid = ((bc >= 0) & (region >= 0)).astype(np.uint8)
+            # the recorded set of jobs, laid out in the library's documented order: groups by ascending (barcode, region), parts of a split group in sequence
+            jobs = [z["job_reads"][joff[j]:joff[j + 1]] for j in np.nonzero(z["job_case"] == c)[0]]
+            jobs.sort(key=lambda ids: (int(np.uint64(bc[ids[0]])), int(region[ids[0]]), int(ids[0])))
+            o = np.concatenate([[0], np.cumsum([len(j) for j in jobs])]).astype(np.int64)
+            f.write(i64(len(bc)) + i64(z["ram"][c]) + i64(len(jobs)) + bc.astype(np.uint64).tobytes() + region.astype(np.int64).tobytes() + valid.tobytes() +
+                    o.tobytes() + (np.concatenate(jobs).astype(np.int64).tobytes() if jobs else b""))
+    z = np.load(os.path.join(gold, "ref_needleman.npz"))
+    with open(tmp_path / "needleman.bin", "wb") as f:
+        f.write(b"SLRH" + np.uint32(3).tobytes() + i64(len(z["L"])))
+        for i in range(len(z["L"])):
+            f.write(np.uint64(workloads.g_pack(str(z["template"][i]))).tobytes() + np.uint64(workloads.g_pack(str(z["read"][i]))).tobytes() +
+                    i32(z["L"][i]) + i32(z["custom"][i]) + z["scores"][i].astype(np.int32).tobytes() + z["counts"][i].astype(np.int32).tobytes())
+    return [tmp_path / "grouper.bin", tmp_path / "jobs.bin", tmp_path / "needleman.bin"]
+
+
+def test_c_host_driver_replays_reference_vectors(pkg, tmp_path):
+    """a C program without JVM, Python or GPU forms the reference's regions, jobs and Needleman counts through the C ABI's host-side entry points"""
+    import subprocess
+    exe = build_c(str(tmp_path / "host_driver"), os.path.join(ROOT, "tests", "c_driver", "host_driver.c"), [])
+    for f in host_driver_inputs(tmp_path):
+        r = subprocess.run([exe, str(f)], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (f, r.stdout, r.stderr)
