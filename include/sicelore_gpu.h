@@ -150,6 +150,26 @@ int  slr_bc_collide(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint6
 int  slr_bc_collide_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint64_t *d_barcodes, int64_t n,
                         slr_collide_result *d_out, void *stream);
 
+/* ---- between the passes: from the pass-1 counts and the collision records to the used-barcode list of pass 2 (host arithmetic, no device) ---- */
+
+/* UsedBarcodesListData.filterLowCounts as finalizeData calls it (F!…/UsedCellBCListGenerator$UsedBarcodesListData.class,
+ * UsedCellBCListGenerator.java:L359-L363, L391-L392): keep_out[i] = counts[i] > 2.0f * record_count / 5000000.0f (float) && counts[i] > 1.
+ * counts = unfilteredUsedBarcodeMap (slr_bc_counts_read after slr_bc_exact), record_count = reads scanned in pass 1.  The kept barcodes are the
+ * list the collision tester runs on (slr_bc_table_create + slr_bc_collide of the list against itself). */
+int  slr_bc_used_filter_low_counts(const int32_t *counts, int64_t n, int64_t record_count, uint8_t *keep_out);
+
+#define SLR_UL_ORDER_UNPIN 1u  /* a java.util.HashMap bin reached 9 entries at >= 64 bins (a JDK tree bin): the iteration order that decides chains of removals is not reproduced */
+#define SLR_UL_RANK_TIES   2u  /* kept barcodes with equal counts: their relative ranks follow fastutil's table order in the reference, input order here */
+/* Replaces BarcodeDatasetColissionTester.generateColissionMergedBCmap (F!…/BarcodeDatasetColissionTester.class, …java:L158-L203) and the rank
+ * assignment of WorkerReadscanner.java:L264-L270.  barcodes / counts: the count-filtered list; collide[i]: the record slr_bc_collide returned
+ * for barcodes[i] against this same list; min_count_fold = minCountFold (config.xml:61), merge_ed = mergeBCsED (null = --bcEditDistance),
+ * cells_fold = cellsWithReadsnFoldBelowMaxToKeep (config.xml:27).  A barcode B removes every collider c (ED <= merge_ed) with
+ * counts[c] < counts[B] / min_count_fold — visited in the JDK HashMap's iteration order, and a barcode that has itself been removed removes
+ * nobody; the survivors with counts >= max / cells_fold are kept.  keep_out[n]; rank_out[n] (may be NULL): 1 = most reads, 0 = dropped;
+ * *flags_out (may be NULL): SLR_UL_*. */
+int  slr_bc_used_merge_collisions(const uint64_t *barcodes, const int32_t *counts, const slr_collide_result *collide, int64_t n,
+                                  int min_count_fold, int merge_ed, int cells_fold, uint8_t *keep_out, int32_t *rank_out, uint32_t *flags_out);
+
 /* ---- S2: UMI distance matrices ---------------------------------------------------------------------- */
 
 /* Replaces ClusteringEditDistanceBase.generateDistanceMatrix (F!com/rw/clustering/ClusteringEditDistanceBase.class,

@@ -139,8 +139,9 @@ class JStream:
     def __init__(self, src, ops=()):
         self.src, self.ops = src, list(ops)
 
-    def run(self, vm, limit=None):
-        out = []
+    def iterate(self, vm, limit=None):
+        """element by element, like the JDK's sequential pipeline: the consumer of element k runs before the filter of element k + 1"""
+        n = 0
         for x in self.src:
             keep = True
             for kind, f in self.ops:
@@ -151,10 +152,13 @@ class JStream:
                 elif kind == "map":
                     x = vm.call_functional(f, [x])
             if keep:
-                out.append(x)
-                if limit is not None and len(out) >= limit:
+                yield x
+                n += 1
+                if limit is not None and n >= limit:
                     break
-        return out
+
+    def run(self, vm, limit=None):
+        return list(self.iterate(vm, limit))
 
 
 class FastutilIntMap:
@@ -634,8 +638,8 @@ class VM:
                 return a[0]
             if name == "collect":
                 return self.collect(st_.run(self), a[1] if len(a) > 1 else None)
-            if name == "forEach":
-                for x in st_.run(self):
+            if name == "forEach":                           # lazily: a consumer that changes what the next filter reads is seen by it
+                for x in st_.iterate(self):
                     self.call_functional(a[1], [x])
                 return None
             if name == "findFirst":

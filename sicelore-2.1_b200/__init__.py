@@ -51,7 +51,7 @@ EXPORTS = ["slr_ctx_create", "slr_ctx_destroy", "slr_ctx_device", "slr_bc_table_
            "slr_multi_create", "slr_multi_destroy", "slr_multi_n_devices", "slr_multi_ctx", "slr_multi_peer_access", "slr_multi_bc_table_create",
            "slr_multi_bc_table_destroy", "slr_multi_bc_table_replica", "slr_multi_bc_assign", "slr_multi_bc_exact", "slr_multi_bc_counts_read",
            "slr_multi_bc_counts_reset", "slr_multi_umi_dist", "slr_multi_umi_cluster", "slr_multi_umi_assign",
-           "slr_grouper_create", "slr_grouper_destroy", "slr_grouper_next_region_id", "slr_grouper_group_sams", "slr_group_jobs", "slr_needleman_errors", "slr_guided_mismatch_diff"]
+           "slr_grouper_create", "slr_grouper_destroy", "slr_grouper_next_region_id", "slr_grouper_group_sams", "slr_group_jobs", "slr_needleman_errors", "slr_guided_mismatch_diff", "slr_bc_used_filter_low_counts", "slr_bc_used_merge_collisions"]
 
 
 class SiceloreGpuError(RuntimeError):
@@ -79,7 +79,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
     cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu", "umi_assign_deep.cu",
-                                           "guided_match.cu", "slr_multi.cu", "slr_group.cpp", "slr_needleman.cpp")]
+                                           "guided_match.cu", "slr_multi.cu", "slr_group.cpp", "slr_needleman.cpp", "slr_usedlist.cpp")]
     if force or _stale(LIB_GPU, srcs + [inc]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
@@ -119,6 +119,8 @@ def gpu_lib():
         L.slr_grouper_group_sams.argtypes = [vp, vp, vp, vp, i64, i32, vp, C.POINTER(i64)]
         L.slr_group_jobs.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, C.POINTER(i64)]
         L.slr_needleman_errors.argtypes = [C.c_uint64, C.c_uint64, i32, vp, vp]
+        L.slr_bc_used_filter_low_counts.argtypes = [vp, i64, i64, vp]
+        L.slr_bc_used_merge_collisions.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]
         L.slr_guided_mismatch_diff.argtypes = [vp, i64, vp, i32, i32, vp, i32, vp, vp]
         L.slr_bc_table_destroy.argtypes = [vp]
         L.slr_bc_table_destroy.restype = None
@@ -580,6 +582,33 @@ class BarcodeDatasetColissionTester:
             out = np.empty(len(q), dtype=COLLIDE_RESULT)
         _check(gpu_lib().slr_bc_collide(self.ctx.h, self.map.h, self.ed, q.ctypes.data, len(q), out.ctypes.data))
         return out
+
+
+UL_ORDER_UNPIN, UL_RANK_TIES = 1, 2
+
+
+def used_filter_low_counts(counts, record_count):
+    """UsedBarcodesListData.filterLowCounts with finalizeData's cutoff (slr_bc_used_filter_low_counts): bool mask of the barcodes that go on to
+    the collision test"""
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    keep = np.zeros(len(counts), dtype=np.uint8)
+    _check(gpu_lib().slr_bc_used_filter_low_counts(counts.ctypes.data, len(counts), int(record_count), keep.ctypes.data))
+    return keep.astype(bool)
+
+
+def used_merge_collisions(barcodes, counts, collide, min_count_fold=10, merge_ed=1, cells_fold=500):
+    """BarcodeDatasetColissionTester.generateColissionMergedBCmap + the ranks of WorkerReadscanner.java:L264-L270 on the records of
+    BarcodeDatasetColissionTester.colissionsFromScan (slr_bc_used_merge_collisions).  Returns (keep mask, rank, flags): the kept barcodes with
+    their ranks are the BarcodesMapForBCfinding of pass 2."""
+    barcodes = np.ascontiguousarray(barcodes, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    collide = np.ascontiguousarray(collide, dtype=COLLIDE_RESULT)
+    n = len(barcodes)
+    assert counts.shape == (n,) and collide.shape == (n,)
+    keep, rank, flags = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.int32), C.c_uint32(0)
+    _check(gpu_lib().slr_bc_used_merge_collisions(barcodes.ctypes.data, counts.ctypes.data, collide.ctypes.data, n, int(min_count_fold), int(merge_ed),
+                                                  int(cells_fold), keep.ctypes.data, rank.ctypes.data, C.byref(flags)))
+    return keep.astype(bool), rank, int(flags.value)
 
 
 def read_name_suffix(res_i, bc_start, bc_end):
