@@ -141,7 +141,8 @@ typedef struct {
  * BarcodeDatasetColissionTester.class, BarcodeDatasetColissionTester.java:L212-L229): for every barcode of the
  * used-barcode list one BarcodeMatchTester(seq, editDistance, skipFullMatches=true, allowIndels=true,
  * searchSet = the list's keySet(), offset 0, cell_bc_length, postSeq=null, doNextLevelIfMatchFound=false).call()
- * (L215-L222), whose Matches feed getUnfilteredColissionData / generateColissionMergedBCmap (L126-L203, host Java).
+ * (L215-L222), whose Matches feed getUnfilteredColissionData (L126-L150, host Java) and generateColissionMergedBCmap (L158-L203:
+ * slr_bc_used_merge_collisions below, host arithmetic on these records).
  *   t          the search set = barcodes_b4filtering.keySet()  (slr_bc_table_create of the same list)
  *   ed_max     mergeBCsED (config.xml:25; null = --bcEditDistance): 0, 1 or 2
  *   barcodes   n queries (2-bit longs), normally the list itself; out: n records, positional */
