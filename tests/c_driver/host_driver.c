@@ -5,7 +5,9 @@
  *   1 groupSams:  i64 n_calls; per call: i64 n, i32 max_dist, i64 id_before, i64 id_after, i32 keep, i32 thrown, i64 n_done,
  *                 i32 position[n], i32 flags[n], u8 has[n], i64 region_in[n], i64 region_out[n]
  *   2 jobs:       i64 n_cases; per case: i64 n, i64 ram, i64 n_jobs, u64 cell[n], i64 region[n], u8 valid[n], i64 offsets[n_jobs + 1], i64 order[offsets[n_jobs]]
- *   3 needleman:  i64 n_pairs; per pair: u64 template, u64 read, i32 len, i32 custom, i32 scores[7], i32 counts[4] */
+ *   3 needleman:  i64 n_pairs; per pair: u64 template, u64 read, i32 len, i32 custom, i32 scores[7], i32 counts[4]
+ *   4 used list:  i64 n_cases; per case: i64 n, i32 ed, i32 min_count_fold, i32 cells_fold, i64 record_count, u64 barcodes[n], i32 counts[n],
+ *                 slr_collide_result collide[n], u8 kept[n], u8 count_filter_keep[n] */
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -76,11 +78,30 @@ static int needleman(void)
     return 0;
 }
 
+static int used_list(void)
+{
+    int64_t cases = rd64(), total = 0;
+    for (int64_t c = 0; c < cases; c++) {
+        int64_t n = rd64(); int32_t ed = rd32(), fold = rd32(), cells = rd32(); int64_t rec = rd64();
+        uint64_t *bc = buf((size_t)n * 8); int32_t *cnt = buf((size_t)n * 4); slr_collide_result *col = buf((size_t)n * sizeof *col);
+        uint8_t *want = buf((size_t)n), *fwant = buf((size_t)n), *keep = buf((size_t)n), *fkeep = buf((size_t)n); int32_t *rank = buf((size_t)n * 4);
+        rd(bc, (size_t)n * 8); rd(cnt, (size_t)n * 4); rd(col, (size_t)n * sizeof *col); rd(want, (size_t)n); rd(fwant, (size_t)n);
+        uint32_t flags = 99;
+        if (slr_bc_used_merge_collisions(bc, cnt, col, n, fold, ed, cells, keep, rank, &flags)) FAIL("case %lld: slr_bc_used_merge_collisions", (long long)c);
+        if (memcmp(keep, want, (size_t)n) || (flags & SLR_UL_ORDER_UNPIN)) FAIL("case %lld: kept list differs", (long long)c);
+        if (slr_bc_used_filter_low_counts(cnt, n, rec, fkeep) || memcmp(fkeep, fwant, (size_t)n)) FAIL("case %lld: count filter differs", (long long)c);
+        free(bc); free(cnt); free(col); free(want); free(fwant); free(keep); free(fkeep); free(rank);
+        total += n;
+    }
+    printf("used list: %lld lists, %lld barcodes OK\n", (long long)cases, (long long)total);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc != 2 || !(f = fopen(argv[1], "rb"))) { fprintf(stderr, "usage: host_driver file\n"); return 2; }
     char magic[4]; rd(magic, 4);
     if (memcmp(magic, "SLRH", 4)) { fprintf(stderr, "bad magic\n"); return 2; }
     int32_t kind = rd32();
-    return kind == 1 ? group_sams() : kind == 2 ? jobs() : kind == 3 ? needleman() : 2;
+    return kind == 1 ? group_sams() : kind == 2 ? jobs() : kind == 3 ? needleman() : kind == 4 ? used_list() : 2;
 }

@@ -199,11 +199,20 @@ def host_driver_inputs(tmp_path):
         for i in range(len(z["L"])):
             f.write(np.uint64(workloads.g_pack(str(z["template"][i]))).tobytes() + np.uint64(workloads.g_pack(str(z["read"][i]))).tobytes() +
                     i32(z["L"][i]) + i32(z["custom"][i]) + z["scores"][i].astype(np.int32).tobytes() + z["counts"][i].astype(np.int32).tobytes())
-    return [tmp_path / "grouper.bin", tmp_path / "jobs.bin", tmp_path / "needleman.bin"]
+    z = np.load(os.path.join(gold, "ref_usedlist.npz"))
+    off = z["offsets"]
+    with open(tmp_path / "usedlist.bin", "wb") as f:
+        f.write(b"SLRH" + np.uint32(4).tobytes() + i64(len(off) - 1))
+        for c in range(len(off) - 1):
+            a, b = int(off[c]), int(off[c + 1])
+            f.write(i64(b - a) + i32(z["ed"][c]) + i32(z["min_count_fold"][c]) + i32(z["cells_fold"][c]) + i64(z["record_count"][c]) +
+                    z["barcodes"][a:b].astype(np.uint64).tobytes() + z["counts"][a:b].astype(np.int32).tobytes() + np.ascontiguousarray(z["collide"][a:b]).tobytes() +
+                    z["kept"][a:b].astype(np.uint8).tobytes() + z["count_filter_keep"][a:b].astype(np.uint8).tobytes())
+    return [tmp_path / "grouper.bin", tmp_path / "jobs.bin", tmp_path / "needleman.bin", tmp_path / "usedlist.bin"]
 
 
 def test_c_host_driver_replays_reference_vectors(pkg, tmp_path):
-    """a C program without JVM, Python or GPU forms the reference's regions, jobs and Needleman counts through the C ABI's host-side entry points"""
+    """a C program without JVM, Python or GPU forms the reference's regions, jobs, Needleman counts and used-barcode lists through the C ABI's host-side entry points"""
     import subprocess
     exe = build_c(str(tmp_path / "host_driver"), os.path.join(ROOT, "tests", "c_driver", "host_driver.c"), [])
     for f in host_driver_inputs(tmp_path):
