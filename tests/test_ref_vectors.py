@@ -16,6 +16,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FIND_UMI_FILES = ["ref_find_umi.npz", "ref_find_umi_wide.npz"]
 TEST_BARCODES_FILES = ["ref_test_barcodes.npz", "ref_test_barcodes_wide.npz"]
 GUIDED_FILES = ["ref_guided.npz", "ref_guided_wide.npz"]
+DOJOB_FILES = ["ref_dojob.npz", "ref_dojob_wide.npz"]                  # wide: oracle/make_ref_wide2.py
+UMI_PAIR_FILES = ["ref_umi_pairs.npz", "ref_umi_pairs_wide.npz"]
 M64 = (1 << 64) - 1
 
 
@@ -51,11 +53,12 @@ def test_limited_compare_matches_reference_bytecode(orc):
     assert seen == {-1, 0, 1, 2, 3, 4}
 
 
-def test_dojob_matches_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", DOJOB_FILES)
+def test_dojob_matches_reference_bytecode(orc, fname):
     """BarcodeMatchTester.doJob run by the reference's own class files: every OneMatch (readSeq, matchingBC, ED, counters, offset) in
     discovery order, for the second-pass settings (post sequence, doNextLevelIfMatchFound) and the collision tester's
     (skipFullMatches, postSeq = null, !doNext)"""
-    z = np.load(os.path.join(GOLDEN, "ref_dojob.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     n_cases, n_match = len(z["w"]), 0
     for i in range(n_cases):
         keys = z["keys"][z["key_offsets"][i]:z["key_offsets"][i + 1]]
@@ -66,7 +69,7 @@ def test_dojob_matches_reference_bytecode(orc):
         got_rows = [(m["read_seq"], m["bc"], m["ed"], m["n_sub"], m["n_ins"], m["n_del"], m["offset"]) for m in got]
         assert got_rows == [tuple(int(x) & M64 if k < 2 else int(x) for k, x in enumerate(r)) for r in exp], (i, mode, ed, got_rows, exp)
         n_match += len(exp)
-    assert n_cases == 45 and n_match >= 60
+    assert (n_cases, n_match >= 60) == (45, True) if "wide" not in fname else (n_cases >= 240 and n_match >= 300)
     assert {int(e) for e in z["res"][:, 3]} == {0, 1, 2}                        # hits at every ED level
 
 
@@ -332,26 +335,37 @@ def test_gpu_guided_engine_matches_reference_bytecode(pkg, ctx, fname):
             assert (int(g["seq"]), g["n_sub"], g["n_ins"], g["n_del"], g["where"]) == (int(e[0]) & M64, e[1], e[2], e[3], where), (i, g, e)
 
 
-def test_calc_edit_distances_matches_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", UMI_PAIR_FILES)
+def test_calc_edit_distances_matches_reference_bytecode(orc, sim, fname):
     """calcEditDistances itself (ClusteringEditDistanceBase.lambda$static$7) run by the reference's class files: stranded mini-sequence (3' reads
     through getSeqRevComp), the three windows getSubSequence(bcEnd + 1 + i, 12), the equal-bytes shortcut, nine distances, best-of-9, packing.
     The S2 boundary hands the kernel the 14 codes stranded[bcEnd - 1, bcEnd + 13) — exactly what is checked here."""
-    z = np.load(os.path.join(GOLDEN, "ref_umi_pairs.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     L = orc.lib()
     codes = lambda s, e: bytes(pyref.ENCODE[ord(c)] for c in s[e - 1:e + 13])
     nonzero = 0
-    for s1, s2, e1, e2, packed in zip(z["s1"], z["s2"], z["end1"], z["end2"], z["packed"]):
+    n = len(z["packed"])
+    umis = np.zeros((2 * n, 16), dtype=np.uint8)
+    for i, (s1, s2, e1, e2, packed) in enumerate(zip(z["s1"], z["s2"], z["end1"], z["end2"], z["packed"])):
         a, b = codes(str(s1), int(e1)), codes(str(s2), int(e2))
         assert len(a) == 14 and len(b) == 14
         assert L.orc_umi_best9(a, b, 12) == int(np.int32(packed)), (s1, s2, e1, e2, hex(int(packed)))
         nonzero += (int(packed) & 0xFFFFFF) != 0
-    assert len(z["packed"]) == 200 and nonzero > 100
+        umis[2 * i, :14], umis[2 * i + 1, :14] = list(a), list(b)
+    assert n == (2000 if "wide" in fname else 200) and nonzero > n // 2
+    # the same pairs through the CPU replay of the UMI kernel's per-lane code (what the GPU computes): every pair is a job of two reads
+    offs = np.arange(0, 2 * n + 1, 2, dtype=np.int64)
+    oo = np.arange(0, 4 * n + 1, 4, dtype=np.int64)
+    got = np.zeros(4 * n, dtype=np.int32)
+    sim.sim_umi_dist(umis.ctypes.data, 16, 12, offs.ctypes.data, n, got.ctypes.data, oo.ctypes.data)
+    assert (got.reshape(n, 4)[:, 1] == z["packed"].astype(np.int32)).all()
 
 
 @pytest.mark.gpu
-def test_gpu_umi_distance_matches_reference_bytecode(pkg, ctx):
+@pytest.mark.parametrize("fname", UMI_PAIR_FILES)
+def test_gpu_umi_distance_matches_reference_bytecode(pkg, ctx, fname):
     """the UMI kernel through the C ABI against calcEditDistances as run from the reference's class files: every pair is a job of two reads"""
-    z = np.load(os.path.join(GOLDEN, "ref_umi_pairs.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     n = len(z["packed"])
     umis = np.zeros((2 * n, 16), dtype=np.uint8)
     for i, (s1, s2, e1, e2) in enumerate(zip(z["s1"], z["s2"], z["end1"], z["end2"])):
