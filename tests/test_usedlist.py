@@ -112,6 +112,18 @@ def test_oracle_collision_records_match_reference_dojob(pk, orc):
         assert np.array_equal(keep, z["kept"][a:b].astype(bool)), c
 
 
+def test_sim_collision_records_match_reference_dojob(pk, sim, orc):
+    """the same lists (5 - 140 barcodes: tables far smaller than any other test builds) through the library's table builder and the CPU replay of
+    the collision kernel's per-lane code — what the GPU twin below runs on the device"""
+    import ctypes as C
+    for c, z, a, b, col in cases(pk):
+        bc = np.ascontiguousarray(z["barcodes"][a:b], dtype=np.uint64)
+        got = np.zeros(len(bc), dtype=orc.COLLIDE_RESULT)
+        loads = C.c_longlong(0)
+        sim.sim_bc_collide(bc.ctypes.data, len(bc), 0, int(z["ed"][c]), bc.ctypes.data, len(bc), got.ctypes.data, C.byref(loads))
+        assert same_collisions(got, col), c
+
+
 @pytest.mark.gpu
 def test_gpu_pass1_to_pass2_list(pk, ctx):
     """the whole hand-over with the collision records of the GPU kernel: identical to the list the reference's class files kept"""
