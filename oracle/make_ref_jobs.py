@@ -126,7 +126,6 @@ def run_case(vm, bc, region):
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     rng = np.random.default_rng(20261019)
-    import importlib
     import __graft_entry__ as g
     pkg = g.load_package()
     t0 = time.time()
