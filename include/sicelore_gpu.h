@@ -30,8 +30,7 @@ enum {
     SLR_E_NODEVICE = -2,     /* no CUDA device / driver: the library never falls back to the CPU */
     SLR_E_CUDA = -3,         /* a CUDA runtime call failed (message has the detail) */
     SLR_E_NOMEM = -4,
-    SLR_E_UNSUPPORTED = -5,  /* e.g. --bcEditDistance > 2, barcode length != 16 */
-    SLR_E_REFERENCE_THROWS = -6   /* the reference itself throws on this input (host-side grouping only; the message names the exception and line) */
+    SLR_E_UNSUPPORTED = -5   /* e.g. --bcEditDistance > 2, barcode length != 16 */
 };
 
 typedef struct slr_ctx slr_ctx;           /* one per (process, device) */
@@ -141,8 +140,7 @@ typedef struct {
  * BarcodeDatasetColissionTester.class, BarcodeDatasetColissionTester.java:L212-L229): for every barcode of the
  * used-barcode list one BarcodeMatchTester(seq, editDistance, skipFullMatches=true, allowIndels=true,
  * searchSet = the list's keySet(), offset 0, cell_bc_length, postSeq=null, doNextLevelIfMatchFound=false).call()
- * (L215-L222), whose Matches feed getUnfilteredColissionData (L126-L150, host Java) and generateColissionMergedBCmap (L158-L203:
- * slr_bc_used_merge_collisions below, host arithmetic on these records).
+ * (L215-L222), whose Matches feed getUnfilteredColissionData / generateColissionMergedBCmap (L126-L203, host Java).
  *   t          the search set = barcodes_b4filtering.keySet()  (slr_bc_table_create of the same list)
  *   ed_max     mergeBCsED (config.xml:25; null = --bcEditDistance): 0, 1 or 2
  *   barcodes   n queries (2-bit longs), normally the list itself; out: n records, positional */
@@ -150,26 +148,6 @@ int  slr_bc_collide(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint6
                     slr_collide_result *out);
 int  slr_bc_collide_dev(slr_ctx *ctx, const slr_bc_table *t, int ed_max, const uint64_t *d_barcodes, int64_t n,
                         slr_collide_result *d_out, void *stream);
-
-/* ---- between the passes: from the pass-1 counts and the collision records to the used-barcode list of pass 2 (host arithmetic, no device) ---- */
-
-/* UsedBarcodesListData.filterLowCounts as finalizeData calls it (F!…/UsedCellBCListGenerator$UsedBarcodesListData.class,
- * UsedCellBCListGenerator.java:L359-L363, L391-L392): keep_out[i] = counts[i] > 2.0f * record_count / 5000000.0f (float) && counts[i] > 1.
- * counts = unfilteredUsedBarcodeMap (slr_bc_counts_read after slr_bc_exact), record_count = reads scanned in pass 1.  The kept barcodes are the
- * list the collision tester runs on (slr_bc_table_create + slr_bc_collide of the list against itself). */
-int  slr_bc_used_filter_low_counts(const int32_t *counts, int64_t n, int64_t record_count, uint8_t *keep_out);
-
-#define SLR_UL_ORDER_UNPIN 1u  /* a java.util.HashMap bin reached 9 entries at >= 64 bins (a JDK tree bin): the iteration order that decides chains of removals is not reproduced */
-#define SLR_UL_RANK_TIES   2u  /* kept barcodes with equal counts: their relative ranks follow fastutil's table order in the reference, input order here */
-/* Replaces BarcodeDatasetColissionTester.generateColissionMergedBCmap (F!…/BarcodeDatasetColissionTester.class, …java:L158-L203) and the rank
- * assignment of WorkerReadscanner.java:L264-L270.  barcodes / counts: the count-filtered list; collide[i]: the record slr_bc_collide returned
- * for barcodes[i] against this same list; min_count_fold = minCountFold (config.xml:61), merge_ed = mergeBCsED (null = --bcEditDistance),
- * cells_fold = cellsWithReadsnFoldBelowMaxToKeep (config.xml:27).  A barcode B removes every collider c (ED <= merge_ed) with
- * counts[c] < counts[B] / min_count_fold — visited in the JDK HashMap's iteration order, and a barcode that has itself been removed removes
- * nobody; the survivors with counts >= max / cells_fold are kept.  keep_out[n]; rank_out[n] (may be NULL): 1 = most reads, 0 = dropped;
- * *flags_out (may be NULL): SLR_UL_*. */
-int  slr_bc_used_merge_collisions(const uint64_t *barcodes, const int32_t *counts, const slr_collide_result *collide, int64_t n,
-                                  int min_count_fold, int merge_ed, int cells_fold, uint8_t *keep_out, int32_t *rank_out, uint32_t *flags_out);
 
 /* ---- S2: UMI distance matrices ---------------------------------------------------------------------- */
 
@@ -326,8 +304,7 @@ int  slr_umi_session_assign(struct slr_umi_session *s, const slr_umi_assign_para
  * per offset (F!com/rw/nuc/encoding/TwoBit/ed/BCUMIEDtesterBase.class, BCUMIEDtesterBase.java:L82-L203) with the
  * checkMatchWithTestSets of UMInucTwoBitPerBaseEDtester (…java:L52-L67) or BCnucTwoBitPerBaseEDtester (…java:L72-L92) — and
  * the sorted().distinct() reduction of the collected list (IlluminaBarcodeUMIAnalyzerBase.getBestAndSecondBCorUMI,
- * …java:L52-L60; testBarcodes L336-L339).  The Needleman comparison of the two survivors is slr_guided_mismatch_diff below (host arithmetic);
- * the host keeps the flags. */
+ * …java:L52-L60; testBarcodes L336-L339).  The host keeps the Needleman alignment of the two survivors and all flags. */
 typedef struct slr_guided_sets slr_guided_sets;    /* device-resident candidate sets */
 
 #define SLR_G_W_GENE  1u   /* entry (or an ancestor node) was found in the per-gene list: BARCODE_FOUND_FOR_GENE_OR_GENOMIC_REGION */
@@ -382,21 +359,6 @@ int  slr_guided_match_dev(slr_ctx *ctx, const slr_guided_sets *s, int plusminus,
                           const int32_t *d_ed, int max_ed, int64_t n, slr_guided_result *d_out, slr_guided_hit *d_raw_out,
                           int raw_cap, void *stream);
 
-/* The alignment comparison that decides MORE_THAN_ONE_MATCH (host arithmetic on the two survivors of a record, no device): replaces the two
- * NeedlemanWunsch alignments of IlluminaBarcodeUMIAnalyzerBase.getBestAndSecondBCorUMI (…java:L66-L79; T!com/rw/nuc/alignment/needleman/
- * NeedlemanWunsch.class) and NeedlemanMatch.countNeedlemanErrorsInRead (F!com/rw/nanopore/analyzers/NeedlemanMatch.class, …java:L68-L86).
- * scores = the reference's NeedlemanScores (NeedlemanParameters.umi / .bc), NULL = its defaults (-4, -5, -5, -5, -5, -5, 5). */
-typedef struct { int32_t leading_gap_1, leading_gap_2, trailing_gap_1, trailing_gap_2, indel, mismatch, match; } slr_needleman_scores;
-#define SLR_G_NO_SECOND INT32_MIN      /* slr_guided_mismatch_diff: the record has no second-best entry (or is flagged) */
-/* one alignment: candidate (template) vs read window, both 2-bit packed, len <= 32; counts_out[4] = insertionsNeedleman, deletionsNeedleman
- * (gaps at the end of the read row are not counted), substitutionsNeedleman, their sum (getNerrorsNeedleman) */
-int  slr_needleman_errors(uint64_t template2bit, uint64_t read2bit, int len, const slr_needleman_scores *scores, int32_t *counts_out);
-/* per record of slr_guided_match (same slices / anchor / seq_len): diff_out[i] = nMismatchDiffBestvsSecondBest = errors(second) - errors(best),
- * each entry aligned to the window at anchor + offset it was found from (its unMutatedSeq); SLR_G_NO_SECOND when n_distinct < 2.
- * diff == 0 <=> the reference sets MORE_THAN_ONE_MATCH (…java:L80-L86), i.e. the read counts as not found (IlluminaUMIanalyzer.java:L203-L220). */
-int  slr_guided_mismatch_diff(const slr_guided_result *res, int64_t n, const uint8_t *slices, int stride, int slice_len, const int32_t *anchor,
-                              int seq_len, const slr_needleman_scores *scores, int32_t *diff_out);
-
 /* DynamicEditDistances.getmaxED (F!com/rw/parameters/DynamicEditDistances.class, DynamicEditDistances.java:L93-L98): the largest
  * edit distance e whose max_candidates[e] >= count * (2 * plusminus + 1), capped at `cap` (< 0 = null).  max_candidates = one
  * <errorpercent> column of bcMaxEditDistances.xml / umiMaxEditDistances.xml.  Returns -1 when no entry qualifies (the Java
@@ -438,40 +400,6 @@ int  slr_multi_umi_cluster(slr_multi *m, const uint8_t *umis, int stride, int um
                            const uint8_t *member, const int32_t *rank, slr_umi_cluster_rec *rec);
 int  slr_multi_umi_assign(slr_multi *m, const uint8_t *umis, int stride, int umi_len, const int64_t *job_offsets, int64_t n_jobs,
                           const slr_umi_assign_params *params, const uint8_t *job_qv01, slr_umi_assign_rec *rec);
-
-/* ---- host side of the clustering seam: forming the (cell, region) jobs ------------------------------- */
-/* Plain host code (no device, no context): the reference does this on its BAM reader thread, a JVM caller keeps its own classes; these entry
- * points exist for callers WITHOUT a JVM, so that they feed slr_umi_assign with the same jobs.  Pinned against the reference's class files
- * (tests/golden/ref_grouper.npz, ref_jobs.npz). */
-typedef struct slr_grouper slr_grouper;   /* the process-wide state of ReadGrouper: MAX_GENOME_DISTANCE_FOR_SAME_GENOMIC_REGION + the static region counter */
-
-/* ReadGrouper.setMaxGenomeDistance (config.xml:247 max_GenomeDistance_forGrouping, default 500) + ReadGrouper$Cluster.CURRENT_GENOMIC_REGION_ID
- * (ReadGrouper.java:L460; 0 at JVM start).  Like the reference's static state it is meant for ONE reader thread: calls on the same grouper must
- * not overlap (different groupers are independent). */
-int  slr_grouper_create(int max_genome_distance, int64_t first_region_id, slr_grouper **out);
-void slr_grouper_destroy(slr_grouper *g);
-int64_t slr_grouper_next_region_id(const slr_grouper *g);
-
-/* Replaces ReadGrouper.groupSams (F!com/rw/umifinder/bamreaders/ReadGrouper.class, ReadGrouper.java:L82-L230; caller BamReader.run,
- * BamReader.java:L134-L145) for one chunk of n SAM records in BAM order.  position[i] = ReadScanData.positionOnGenomeForClustering (read only
- * where has_position[i] != 0; has_position NULL = every read has one), flags[i] = SAMRecord.getFlags() (bit 16 = reverse strand),
- * region_io[i] = NanoporeRead.genomicRegionNmber, -1 = absent: the reads of every surviving cluster receive its number, the others keep
- * what they had (a read carried over from the previous chunk keeps that round's number).  *last_index_out: records [0, last_index] are the
- * grouped chunk the clustering stage receives; with keep_data_end the records behind it open the caller's next chunk (BamReader.java:L134), without
- * they are dropped (the reference returns an empty chunk).  n == 0: *last_index_out = -1, nothing is handed on (L82-L83).
- * SLR_E_REFERENCE_THROWS: the reference's NullPointerException at L173 (keep_data_end, one surviving cluster whose centre cache is empty). */
-int  slr_grouper_group_sams(slr_grouper *g, const int32_t *position, const uint8_t *has_position, const int32_t *flags, int64_t n,
-                            int keep_data_end, int64_t *region_io, int64_t *last_index_out);
-
-/* Replaces UmiClustering.cluster up to the hand-over to its Submitter (F!…/clustering/UmiClustering.class, UmiClustering.java:L97-L118
- * groupDataByCellAndRegion, L135 size filter, L136-L142 split of oversized groups): the reads with valid[i] != 0 (a cell barcode AND a region
- * number; NULL = all) grouped by (cell_bc, region); groups of fewer than min_size reads (the reference: 2) are dropped; ram_reserved != 0 cuts a
- * group of n reads into ceil((float) n / sqrt(ram_reserved / 300)) consecutive parts of n / nChunks + 1 reads like the reference's memory bound
- * does (RAM_RESERVED, UmiClustering.java:L59; 0 = never split — the GPU has no such bound, but the split changes the clusters).
- * order_out (capacity n): read indices, job j = order_out[job_offsets_out[j] .. job_offsets_out[j + 1]) in input order; job_offsets_out has
- * capacity n + 1; jobs in ascending (cell_bc, region) order (the reference's map iteration order reaches no per-read result). */
-int  slr_group_jobs(const uint64_t *cell_bc, const int64_t *region, const uint8_t *valid, int64_t n, int min_size, int64_t ram_reserved,
-                    int64_t *order_out, int64_t *job_offsets_out, int64_t *n_jobs_out);
 
 /* ---- misc ------------------------------------------------------------------------------------------- */
 const char *slr_last_error(void);

@@ -9,6 +9,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "sicelore_gpu.h"
+#include "sicelore_host.h"
 
 #define H(T, x) ((T *)(size_t)(x))
 

@@ -1,5 +1,5 @@
 """sicelore-2.1_b200 — host-side mirror (Python, ctypes) of the reference interface for the barcode / UMI
-edit-distance hot path, on top of the C ABI of libsicelore_gpu.so (include/sicelore_gpu.h).
+edit-distance hot path, on top of the C ABI of libsicelore_gpu.so (include/sicelore_gpu.h; host-side entry points: include/sicelore_host.h).
 
 The directory name is not a Python identifier; `__graft_entry__.load_package()` imports it as `sicelore_b200`.
 
@@ -78,9 +78,10 @@ def build(force=False, verbose=False):
     """Compile libsicelore_gpu.so (nvcc, sm_100a only) and libslr_synth.so (g++) in-tree."""
     srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))]
     inc = os.path.join(_HERE, "..", "include", "sicelore_gpu.h")
+    inc_host = os.path.join(_HERE, "..", "include", "sicelore_host.h")
     cu = [os.path.join(_CSRC, f) for f in ("slr_api.cu", "bc_assign.cu", "bc_collide.cu", "umi_dist.cu", "umi_cluster.cu", "umi_assign.cu", "umi_assign_deep.cu",
                                            "guided_match.cu", "slr_multi.cu", "slr_group.cpp", "slr_needleman.cpp", "slr_usedlist.cpp")]
-    if force or _stale(LIB_GPU, srcs + [inc]):
+    if force or _stale(LIB_GPU, srcs + [inc, inc_host]):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                "-shared", "-ccbin", CXX, "-o", LIB_GPU] + cu
         if verbose:
@@ -206,7 +207,8 @@ def csrc_sha256():
     """sha256 over the CUDA / C++ sources of the library (csrc/ + the public header), in sorted file order: survives a rebuild"""
     import hashlib
     h = hashlib.sha256()
-    files = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f != "synth.cpp"] + [os.path.join(_HERE, "..", "include", "sicelore_gpu.h")]
+    files = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f != "synth.cpp"] + \
+            [os.path.join(_HERE, "..", "include", f) for f in ("sicelore_gpu.h", "sicelore_host.h")]
     for f in files:
         h.update(os.path.basename(f).encode())
         with open(f, "rb") as fh:

@@ -11,7 +11,7 @@
 #include <cstdint>
 #include <cstring>
 
-#include "../../include/sicelore_gpu.h"
+#include "../../include/sicelore_host.h"
 
 extern "C" int slr_multi_fail(int code, const char *msg);      // slr_api.cu: sets the thread-local error message
 

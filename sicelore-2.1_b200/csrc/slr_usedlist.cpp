@@ -14,7 +14,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/sicelore_gpu.h"
+#include "../../include/sicelore_host.h"
 
 extern "C" int slr_multi_fail(int code, const char *msg);      // slr_api.cu: sets the thread-local error message
 

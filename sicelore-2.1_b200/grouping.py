@@ -39,7 +39,7 @@ class ReadGrouper:
         return int(gpu_lib().slr_grouper_next_region_id(self.h))
 
     def group_sams(self, position, flags, region, keep_data_end, has_position=None):
-        """One chunk of SAM records in BAM order (arguments as slr_grouper_group_sams, include/sicelore_gpu.h).  `region` (int64, in / out):
+        """One chunk of SAM records in BAM order (arguments as slr_grouper_group_sams, include/sicelore_host.h).  `region` (int64, in / out):
         -1 = no region number.  Returns last_index (None for an empty chunk): reads [0, last_index] are the grouped chunk, the reads behind
         it open the next chunk when keep_data_end."""
         p64 = np.asarray(position, dtype=np.int64)

@@ -13,7 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "sicelore_gpu.h"
+#include "sicelore_host.h"
 
 static FILE *f;
 static void rd(void *p, size_t n) { if (n && fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }

@@ -1,4 +1,4 @@
-"""The C-ABI library loads without a GPU and exports exactly what include/sicelore_gpu.h declares; compute calls fail
+"""The C-ABI library loads without a GPU and exports exactly what include/*.h declare; compute calls fail
 loudly (SLR_E_NODEVICE) instead of falling back to the CPU."""
 import os
 import re
@@ -9,7 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_functions():
-    src = open(os.path.join(ROOT, "include", "sicelore_gpu.h")).read()
+    """every function the public headers declare: include/sicelore_gpu.h (the GPU seams) + include/sicelore_host.h (the host-side entry points)"""
+    import glob
+    src = "".join(open(f).read() for f in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))))
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(slr_[a-z0-9_]+)\s*\(", src)))
 
