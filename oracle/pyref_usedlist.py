@@ -54,9 +54,11 @@ def hashmap_key_order(keys):
     return [done[i] for i in order], unpinned
 
 
-def merge_collisions(barcodes, counts, collide, min_count_fold, merge_ed, cells_fold):
+def merge_collisions(barcodes, counts, collide, min_count_fold, merge_ed, cells_fold, visiting="hashmap", lazy=True, strict=True):
     """generateColissionMergedBCmap + the ranks of WorkerReadscanner.java:L264-L269.  collide: COLLIDE_RESULT per barcode (slr_bc_collide of the
-    list against itself).  Returns (keep mask, rank (1-based, 0 = dropped), flags)."""
+    list against itself).  Returns (keep mask, rank (1-based, 0 = dropped), flags).  The keyword arguments switch single behaviours of the
+    reference OFF (tests/test_usedlist.py shows that the vectors notice): visiting="insertion" walks the map in count order instead of the JDK's
+    bin order, lazy=False lets removed barcodes remove others, strict=False removes colliders with count == cutoff too."""
     barcodes = [int(b) for b in barcodes]
     counts = [int(c) for c in counts]
     n = len(barcodes)
@@ -69,11 +71,14 @@ def merge_collisions(barcodes, counts, collide, min_count_fold, merge_ed, cells_
     for i in with_matches:
         cutoff = counts[i] // min_count_fold
         to_merge[barcodes[i]] = [index[int(collide[i]["bc"][e])] for e in range(2)
-                                 if collide[i]["valid"] >> e & 1 and e + 1 <= merge_ed and counts[index[int(collide[i]["bc"][e])]] < cutoff]
+                                 if collide[i]["valid"] >> e & 1 and e + 1 <= merge_ed and
+                                 (counts[index[int(collide[i]["bc"][e])]] < cutoff or (not strict and counts[index[int(collide[i]["bc"][e])]] == cutoff))]
     order, unpinned = hashmap_key_order(list(to_merge.keys()))
+    if visiting == "insertion":
+        order = list(to_merge.keys())
     alive = [True] * n
     for b in order:                                            # L186-L195: HashMap order; a barcode that was itself removed removes nobody
-        if alive[index[b]]:
+        if alive[index[b]] or not lazy:
             for c in to_merge[b]:
                 alive[c] = False
     live = [counts[i] for i in range(n) if alive[i]]

@@ -60,6 +60,20 @@ def test_merge_and_filter_match_reference_bytecode(pk):
     assert n_cases >= 36 and n_chain >= 3          # the vectors include lists where "everybody removes" differs from the reference's order-dependent result
 
 
+def test_vectors_pin_the_order_dependent_behaviour(pk):
+    """switching one behaviour of the reference off changes the kept list of at least one recorded case"""
+    def differing(**kw):
+        bad = 0
+        for c, z, a, b, col in cases(pk):
+            keep, _, _ = P.merge_collisions(z["barcodes"][a:b], z["counts"][a:b], col, int(z["min_count_fold"][c]), int(z["ed"][c]), int(z["cells_fold"][c]), **kw)
+            bad += not np.array_equal(keep, z["kept"][a:b].astype(bool))
+        return bad
+    assert differing() == 0
+    assert differing(lazy=False) > 0, "a removed barcode removes nobody"
+    assert differing(visiting="insertion") > 0, "the JDK HashMap's bin order, not the count order, decides chains"
+    assert differing(strict=False) > 0, "count(c) < count(B) / minCountFold is strict"
+
+
 def test_hashmap_order_model_agrees_with_interpreter_model(pk):
     """the bin layout used natively (and in pyref) against minijvm's JdkHashSet, the model the vectors were produced with"""
     from oracle import minijvm as J, make_ref_hier as H
