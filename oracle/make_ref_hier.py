@@ -277,7 +277,11 @@ class HVM(J.VM):
 
 
 def install_set_extras():
-    """java.util.HashSet.remove + the insertion-order iteration of identity-hashed elements"""
+    """java.util.HashSet.remove + the insertion-order iteration of identity-hashed elements (idempotent: a second call in one process would
+    wrap add() twice and list every identity-hashed element twice)"""
+    if getattr(J.JdkHashSet, "_extras_installed", False):
+        return
+
     def remove(self, e):
         if self.table is None:
             return 0
@@ -310,6 +314,7 @@ def install_set_extras():
             return list(self.order)
         return orig_items(self)
     J.JdkHashSet.remove, J.JdkHashSet.add, J.JdkHashSet.items = remove, add, items
+    J.JdkHashSet._extras_installed = True
 
 
 def bare(vm, name):

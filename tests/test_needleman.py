@@ -109,13 +109,6 @@ def test_mismatch_diff_matches_test_barcodes_bytecode(pk, orc):
     _bc_diff_check(pk, res_of)
 
 
-@pytest.mark.gpu
-def test_gpu_mismatch_diff_matches_test_barcodes_bytecode(pk, ctx):
-    def res_of(gene, allk, empk, sl, anchor, ed, pm, bail, slen):
-        sets = pk.GuidedSets(ctx, gene, np.array([0, len(gene)], dtype=np.int64), 16, bc_flavour=True, all_keys=allk, all_ed=3, empty_keys=empk, empty_ed=2)
-        return sets.match(sl, anchor, np.array([0], dtype=np.int32), ed, pm, 10, bailout=None if bail < 0 else bail, slice_len=slen)[0]
-    _bc_diff_check(pk, res_of)
-
 
 def test_mismatch_diff_refuses_foreign_records(pk):
     res = np.zeros(1, dtype=pk.GUIDED_RESULT)

@@ -18,6 +18,7 @@ TEST_BARCODES_FILES = ["ref_test_barcodes.npz", "ref_test_barcodes_wide.npz"]
 GUIDED_FILES = ["ref_guided.npz", "ref_guided_wide.npz"]
 DOJOB_FILES = ["ref_dojob.npz", "ref_dojob_wide.npz"]                  # wide: oracle/make_ref_wide2.py
 UMI_PAIR_FILES = ["ref_umi_pairs.npz", "ref_umi_pairs_wide.npz"]
+HIER_FILES = ["ref_hier.npz", "ref_hier_wide.npz"]                     # wide: oracle/make_ref_hier_wide.py
 M64 = (1 << 64) - 1
 
 
@@ -362,8 +363,11 @@ def test_calc_edit_distances_matches_reference_bytecode(orc, sim, fname):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fname", UMI_PAIR_FILES)
-def test_gpu_umi_distance_matches_reference_bytecode(pkg, ctx, fname):
+def test_gpu_umi_distance_matches_reference_bytecode(pkg, ctx):
+    gpu_umi_distance(pkg, ctx, UMI_PAIR_FILES[0])              # the wide set runs from tests/test_zz_late_gpu.py
+
+
+def gpu_umi_distance(pkg, ctx, fname):
     """the UMI kernel through the C ABI against calcEditDistances as run from the reference's class files: every pair is a job of two reads"""
     z = np.load(os.path.join(GOLDEN, fname))
     n = len(z["packed"])
@@ -713,11 +717,12 @@ def _check_hier(z, rec_of_job):
     return stats
 
 
-def test_cluster_one_hierarchical_matches_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", HIER_FILES)
+def test_cluster_one_hierarchical_matches_reference_bytecode(orc, fname):
     """ClusterOneHierarchical.call as a whole — LingPipe's CompleteLinkClusterer / SingleLinkClusterer / Dendrogram / BoundedPriorityQueue /
     ObjectToSet, DistanceMatrix, OneUmiCluster.setClusterCenter, ClusterOneBase.setSamflagsAndStatsForClustered — run from the reference's own
     class files (oracle/make_ref_hier.py) on jobs of 2 ... 100 reads: the C oracle reproduces every value the bytecode wrote"""
-    z = np.load(os.path.join(GOLDEN, "ref_hier.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     off, oo = z["job_offsets"], z["out_offsets"]
 
     def rec_of_job(j):
@@ -731,10 +736,15 @@ def test_cluster_one_hierarchical_matches_reference_bytecode(orc):
 
 @pytest.mark.gpu
 def test_gpu_cluster_one_hierarchical_matches_reference_bytecode(pkg, ctx):
+    stats = gpu_cluster_one_hierarchical(pkg, ctx, HIER_FILES[0])          # the wide set runs from tests/test_zz_late_gpu.py
+    assert stats[2] >= 200 and stats[0] > 1500, stats
+
+
+def gpu_cluster_one_hierarchical(pkg, ctx, fname):
     """the CUDA kernels through slr_umi_assign_dev against the same vectors (jobs grouped by parameter set)"""
     import ctypes as C
     import torch
-    z = np.load(os.path.join(GOLDEN, "ref_hier.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     off, oo = z["job_offsets"], z["out_offsets"]
     recs = {}
     for prm in sorted({tuple(int(x) for x in p) for p in z["params"]}):
@@ -754,8 +764,7 @@ def test_gpu_cluster_one_hierarchical_matches_reference_bytecode(pkg, ctx):
         got = d_rec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
         for k, j in enumerate(js):
             recs[j] = got[so[k]:so[k + 1]]
-    stats = _check_hier(z, lambda j: recs[j])
-    assert stats[2] >= 200 and stats[0] > 1500, stats
+    return _check_hier(z, lambda j: recs[j])
 
 
 # ------------------------------------------------------------------------------------------------------------- ClusterOne_MyClustering

@@ -136,15 +136,3 @@ def test_sim_collision_records_match_reference_dojob(pk, sim, orc):
         loads = C.c_longlong(0)
         sim.sim_bc_collide(bc.ctypes.data, len(bc), 0, int(z["ed"][c]), bc.ctypes.data, len(bc), got.ctypes.data, C.byref(loads))
         assert same_collisions(got, col), c
-
-
-@pytest.mark.gpu
-def test_gpu_pass1_to_pass2_list(pk, ctx):
-    """the whole hand-over with the collision records of the GPU kernel: identical to the list the reference's class files kept"""
-    for c, z, a, b, col in cases(pk):
-        bc, cnt = z["barcodes"][a:b], z["counts"][a:b]
-        table = pk.BarcodesMapForBCfinding.getMapFromCellRangerData(ctx, bc)
-        got = pk.BarcodeDatasetColissionTester(ctx, table, int(z["ed"][c])).colissionsFromScan(bc)
-        assert same_collisions(got, col), c                                                # slr_bc_collide == the reference's own doJob Matches
-        keep, rank, _ = pk.used_merge_collisions(bc, cnt, got, int(z["min_count_fold"][c]), int(z["ed"][c]), int(z["cells_fold"][c]))
-        assert np.array_equal(keep, z["kept"][a:b].astype(bool)), c
