@@ -19,6 +19,7 @@ GUIDED_FILES = ["ref_guided.npz", "ref_guided_wide.npz"]
 DOJOB_FILES = ["ref_dojob.npz", "ref_dojob_wide.npz"]                  # wide: oracle/make_ref_wide2.py
 UMI_PAIR_FILES = ["ref_umi_pairs.npz", "ref_umi_pairs_wide.npz"]
 HIER_FILES = ["ref_hier.npz", "ref_hier_wide.npz"]                     # wide: oracle/make_ref_hier_wide.py
+MYCLUST_FILES = ["ref_myclust.npz", "ref_myclust_wide.npz"]            # wide: oracle/make_ref_myclust_wide.py
 M64 = (1 << 64) - 1
 
 
@@ -768,12 +769,13 @@ def gpu_cluster_one_hierarchical(pkg, ctx, fname):
 
 
 # ------------------------------------------------------------------------------------------------------------- ClusterOne_MyClustering
-def test_cluster_one_myclustering_matches_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", MYCLUST_FILES)
+def test_cluster_one_myclustering_matches_reference_bytecode(orc, fname):
     """ClusterOne_MyClustering.call as a whole — clusterLocal on the full set, the depth rule, OneUmiCluster.setClusterCenter, the off-centre removal
     (removeEntries -> the fastutil iterator's backward-shift deletion -> re-centring), the second clusterLocal over the unclustered reads and
     setSamflagsAndStatsForClustered — run from the reference's own class files (oracle/make_ref_myclust.py, sequential streams) on 72 jobs of
     20 ... 330 reads: the C oracle reproduces every value the bytecode wrote"""
-    z = np.load(os.path.join(GOLDEN, "ref_myclust.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     off, oo = z["job_offsets"], z["out_offsets"]
 
     def rec_of_job(j):
@@ -789,10 +791,15 @@ def test_cluster_one_myclustering_matches_reference_bytecode(orc):
 
 @pytest.mark.gpu
 def test_gpu_cluster_one_myclustering_matches_reference_bytecode(pkg, ctx):
+    stats = gpu_cluster_one_myclustering(pkg, ctx, MYCLUST_FILES[0])       # the wide set runs from tests/test_zz_late_gpu.py
+    assert stats[2] >= 72 and stats[0] > 9000, stats
+
+
+def gpu_cluster_one_myclustering(pkg, ctx, fname):
     """the large-job kernels (umi_assign_deep.cu) through slr_umi_assign_dev2 against the same vectors (max_hier = 0 sends every job there)"""
     import ctypes as C
     import torch
-    z = np.load(os.path.join(GOLDEN, "ref_myclust.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     off, oo = z["job_offsets"], z["out_offsets"]
     L = pkg.gpu_lib()
     recs = {}
@@ -814,8 +821,7 @@ def test_gpu_cluster_one_myclustering_matches_reference_bytecode(pkg, ctx):
         got = d_rec.cpu().numpy().view(pkg.UMI_ASSIGN_REC).reshape(-1)
         for k, j in enumerate(js):
             recs[j] = got[so[k]:so[k + 1]]
-    stats = _check_hier(z, lambda j: recs[j])
-    assert stats[2] >= 72 and stats[0] > 9000, stats
+    return _check_hier(z, lambda j: recs[j])
 
 
 def test_oversized_group_split_matches_reference_bytecode(pkg):

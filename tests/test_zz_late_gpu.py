@@ -57,3 +57,9 @@ def test_gpu_umi_distance_wide_set(pkg, ctx):
 def test_gpu_cluster_one_hierarchical_wide_set(pkg, ctx):
     stats = RV.gpu_cluster_one_hierarchical(pkg, ctx, RV.HIER_FILES[1])
     assert stats[2] >= 400 and stats[0] > 3000, stats
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_one_myclustering_wide_set(pkg, ctx):
+    stats = RV.gpu_cluster_one_myclustering(pkg, ctx, RV.MYCLUST_FILES[1])
+    assert stats[2] >= 90 and stats[0] > 9000, stats
