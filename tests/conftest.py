@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: pytest-timeout's marker (registered here too, so that a box without the plugin only ignores it)")
 
 
 @pytest.fixture(scope="session")

@@ -11,6 +11,9 @@ from test_pipeline import GpuBackend, OracleBackend, check_sanity, run_pipeline
 from test_usedlist import cases, same_collisions
 
 
+pytestmark = pytest.mark.timeout(240, method="thread")      # never seen by a device: a wedged kernel must end the run, not sit in it
+
+
 @pytest.fixture(scope="module")
 def pk():
     p = g.load_package()
