@@ -20,6 +20,7 @@ DOJOB_FILES = ["ref_dojob.npz", "ref_dojob_wide.npz"]                  # wide: o
 UMI_PAIR_FILES = ["ref_umi_pairs.npz", "ref_umi_pairs_wide.npz"]
 HIER_FILES = ["ref_hier.npz", "ref_hier_wide.npz"]                     # wide: oracle/make_ref_hier_wide.py
 MYCLUST_FILES = ["ref_myclust.npz", "ref_myclust_wide.npz"]            # wide: oracle/make_ref_myclust_wide.py
+CLUSTER_LOCAL_FILES = ["ref_cluster_local.npz", "ref_cluster_local_wide.npz"]      # wide: oracle/make_ref_cluster_wide.py
 M64 = (1 << 64) - 1
 
 
@@ -642,8 +643,9 @@ def _check_cluster_records(z, rec):
     assert np.array_equal(has.astype(np.int32), z["present"])                      # Optional.empty <=> no key at all
 
 
-def test_cluster_local_matches_reference_bytecode(orc):
-    z = np.load(os.path.join(GOLDEN, "ref_cluster_local.npz"))
+@pytest.mark.parametrize("fname", CLUSTER_LOCAL_FILES)
+def test_cluster_local_matches_reference_bytecode(orc, fname):
+    z = np.load(os.path.join(GOLDEN, fname))
     assert len(z["ed"]) >= 50 and (z["label"] >= 0).sum() > 500
     rec = np.zeros(len(z["member"]), dtype=orc.CLUSTER_REC)
     for j in range(len(z["ed"])):                                                  # ed differs per job: one oracle call each
@@ -667,8 +669,12 @@ def test_cluster_local_matches_reference_bytecode(orc):
 
 @pytest.mark.gpu
 def test_gpu_cluster_local_matches_reference_bytecode(pkg, ctx):
+    gpu_cluster_local(pkg, ctx, CLUSTER_LOCAL_FILES[0])            # the wide set runs from tests/test_zz_late_gpu.py
+
+
+def gpu_cluster_local(pkg, ctx, fname):
     import torch
-    z = np.load(os.path.join(GOLDEN, "ref_cluster_local.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     m = len(z["member"])
     rec = np.zeros(m, dtype=pkg.UMI_CLUSTER_REC)
     d_m = torch.from_numpy(z["packed"]).cuda()

@@ -66,3 +66,8 @@ def test_gpu_cluster_one_hierarchical_wide_set(pkg, ctx):
 def test_gpu_cluster_one_myclustering_wide_set(pkg, ctx):
     stats = RV.gpu_cluster_one_myclustering(pkg, ctx, RV.MYCLUST_FILES[1])
     assert stats[2] >= 90 and stats[0] > 9000, stats
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_local_wide_set(pkg, ctx):
+    RV.gpu_cluster_local(pkg, ctx, RV.CLUSTER_LOCAL_FILES[1])
