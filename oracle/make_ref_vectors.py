@@ -632,9 +632,13 @@ def write_name_cases(vm, rng, n):
         vm.fastq_fields = {"getReadName": "read%d some description" % t, "getBaseQualityString": quals[::-1] if rev else quals, "getReadString": stranded,
                            "getBaseQualityHeader": "", "toString": "FastqRecord"}
         fq.f["reverseComplementQualities"] = J.JNative("pyfunc", lambda rec: quals)       # FastqRecordExt's own lambda reverses the qualities of a reversed read
-        rec = vm.call_virtual(fq, "getRecordForWriting", "(Lcom/rw/parameters/ReadScannerParameters;ZLjava/lang/Integer;)Lhtsjdk/samtools/fastq/FastqRecord;",
-                              rsp, int(five), rid)
-        out.append(dict(name=rec.v[0], stranded=stranded, quals=quals, rev=rev, five=five, rid=-1 if rid is None else rid, kw=repr(sorted(kw.items()))))
+        try:
+            rec = vm.call_virtual(fq, "getRecordForWriting", "(Lcom/rw/parameters/ReadScannerParameters;ZLjava/lang/Integer;)Lhtsjdk/samtools/fastq/FastqRecord;",
+                                  rsp, int(five), rid)
+            name = rec.v[0]
+        except J.JavaThrow as ex:                              # e.g. the X= slice starting at the first base: getMeanQV's skip(begin - 1) gets -1
+            name = "EXC:" + ex.cls
+        out.append(dict(name=name, stranded=stranded, quals=quals, rev=rev, five=five, rid=-1 if rid is None else rid, kw=repr(sorted(kw.items()))))
     return out
 
 

@@ -613,6 +613,8 @@ class VM:
                     items.sort(key=functools.cmp_to_key(lambda x, y: self.j_compare(x, y)))
                 return JNative("java/util/stream/Stream", JStream(items))
             if name == "skip":
+                if int(a[1]) < 0:                          # ReferencePipeline.skip: IllegalArgumentException(Long.toString(n))
+                    raise JavaThrow("java/lang/IllegalArgumentException", str(int(a[1])))
                 return JNative("java/util/stream/Stream", JStream(st_.run(self)[int(a[1]):]))
             if name == "mapToInt":
                 return JNative("java/util/stream/Stream", JStream(st_.src, st_.ops + [("map", a[1])]))

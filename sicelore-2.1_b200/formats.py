@@ -98,6 +98,10 @@ def read_name_extension(reversed_read, stranded_seq, stranded_quals, adapter_end
         end = adapter_end + tags.nbasesOfAdapterSeqInReadname - 1
     if begin < 0:
         return ""
+    if begin == 0:
+        # the range check lets begin == 0 through (L247: ifge), and getMeanQV then asks for IntStream.skip(begin - 1) = skip(-1) (L58): the
+        # reference dies here with an IllegalArgumentException — a 3' read whose adapter ends at base 41, a 5' read whose adapter ends at base 3
+        raise ValueError("IllegalArgumentException: -1 (IntStream.skip in getMeanQV, FastqRecordExt.java:L58)")
     if end > len(stranded_seq):
         raise IndexError("StringIndexOutOfBoundsException: substring(%d, %d)" % (begin, end))
     add += "%s%s_" % (tags.seqPrefix, stranded_seq[begin:end])                   # L261-L264

@@ -92,12 +92,13 @@ def test_assigned_tsv_round_trip(tmp_path):
     assert open(path).readline() == "Barcode\tn Reads with ED<=2 match\tED=0\tED=1\tED=2\n"
 
 
-def test_parser_matches_reference_bytecode():
+@pytest.mark.parametrize("fname", ["ref_read_names.npz", "ref_read_names_wide.npz"])      # wide: oracle/make_ref_names_wide.py
+def test_parser_matches_reference_bytecode(fname):
     """FastqRecordExt.getScanDatFromReadName run by the reference's own class files (oracle/minijvm.py, tests/golden/ref_read_names.npz): every
     parsed field, the absent / adapter-missing / read-id NumberFormatException outcomes, with and without the assignumis barcode-ED limit"""
     F = fmt()
     pkg = g.load_package()
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_read_names.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname))
     outcomes = set()
     for name, lim, parsed in zip(z["name"], z["limit"], z["parsed"]):
         name, parsed = str(name), str(parsed)
@@ -137,17 +138,24 @@ def test_parser_matches_reference_bytecode():
     assert outcomes == {"adapter", "nfe", "absent", "ok", "ok_nobc"}
 
 
-def test_writer_matches_reference_bytecode():
+@pytest.mark.parametrize("fname", ["ref_written_names.npz", "ref_written_names_wide.npz"])
+def test_writer_matches_reference_bytecode(fname):
     """FastqRecordExt.getRecordForWriting run by the reference's own class files (tests/golden/ref_written_names.npz): the whole read name for
     forward / reversed, 3' / 5' reads with and without polyA, TSO, barcode, second-best ED, rank, read id, and the adapter end too close to the
     read start for an X= slice"""
     F = fmt()
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_written_names.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname))
     shapes = set()
     for name, stranded, quals, rev, five, rid, kw in zip(z["name"], z["stranded"], z["quals"], z["rev"], z["five"], z["read_id"], z["kw"]):
         kw = dict(eval(str(kw)))
-        ext = F.read_name_extension(bool(rev), str(stranded), str(quals), is5p=bool(five), read_id=None if rid < 0 else int(rid), **kw)
         name = str(name)
+        if name.startswith("EXC:"):                      # the reference itself throws (adapter end exactly at the start of the X= slice)
+            assert name == "EXC:java/lang/IllegalArgumentException"
+            with pytest.raises(ValueError):
+                F.read_name_extension(bool(rev), str(stranded), str(quals), is5p=bool(five), read_id=None if rid < 0 else int(rid), **kw)
+            shapes.add("throws")
+            continue
+        ext = F.read_name_extension(bool(rev), str(stranded), str(quals), is5p=bool(five), read_id=None if rid < 0 else int(rid), **kw)
         assert name == name.split("_")[0] + ext, (name, ext)
         shapes.add(("X=" in ext, "bc=" in ext, "T=" in ext, "PS=" in ext, rid >= 0))
         if ext == "":
@@ -155,4 +163,4 @@ def test_writer_matches_reference_bytecode():
         if " cellBC=" in name:                           # the parser reads its own output back
             p = F.parse_read_name(name.split(" ")[0])
             assert p["bc"] == kw["bc"] and p["adapter_end"] == kw["adapter_end"] and p.get("read_id", 0) == max(int(rid), 0)
-    assert len(shapes) >= 5
+    assert len(shapes) >= 5 and ("throws" in shapes or "wide" not in fname)
