@@ -45,8 +45,9 @@ def test_primitives_match_reference_bytecode(orc):
     assert len(z["rows"]) == 1680
 
 
-def test_limited_compare_matches_reference_bytecode(orc):
-    z = np.load(os.path.join(GOLDEN, "ref_levenshtein.npz"))["rows"]
+@pytest.mark.parametrize("fname", ["ref_levenshtein.npz", "ref_levenshtein_wide.npz"])      # wide: oracle/make_ref_small_wide.py
+def test_limited_compare_matches_reference_bytecode(orc, fname):
+    z = np.load(os.path.join(GOLDEN, fname))["rows"]
     L = orc.lib()
     seen = set()
     for row in z:
@@ -108,10 +109,11 @@ def test_guided_engine_matches_reference_bytecode(orc, fname):
     assert {orc.W_GENE, orc.W_ALL, orc.W_EMPTY, orc.W_GENE | orc.W_ALL} <= flags_seen      # the inherited GENE bit occurs in the reference's own output
 
 
-def test_best_of_nine_and_packing_match_reference_bytecode(orc):
+@pytest.mark.parametrize("fname", ["ref_best9.npz", "ref_best9_wide.npz"])
+def test_best_of_nine_and_packing_match_reference_bytecode(orc, fname):
     """new ClusteringEditDistanceBase(eds) run by the reference's own class files (eds from its LevenshteinDistance.apply): the visiting
     order ZERO, PLUSONE, MINUSONE with strict '<', the BestEditDistance int and its transposed copy, the equality constant"""
-    z = np.load(os.path.join(GOLDEN, "ref_best9.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     L = orc.lib()
     assert L.orc_umi_equality() == int(z["equality"])
     shifted = 0
@@ -524,10 +526,14 @@ def _exact_inputs(z, g):
     return tp, sl, rel, lens, exp, int((z["found"][g] == -1).sum())
 
 
-def test_exact_lookup_matches_reference_bytecode(orc):
+EXACT_FILES = ["ref_exact_lookup.npz", "ref_exact_lookup_wide.npz"]
+
+
+@pytest.mark.parametrize("fname", EXACT_FILES)
+def test_exact_lookup_matches_reference_bytecode(orc, fname):
     """pass 1: UsedCellBCListGenerator$Worker's per-read lambda run by the reference's class files (window at the predicted position, whitelist
     test, unfilteredUsedBarcodeMap counts, reads whose window leaves the read) against the oracle's exact lookup"""
-    z = np.load(os.path.join(GOLDEN, "ref_exact_lookup.npz"))
+    z = np.load(os.path.join(GOLDEN, fname))
     for g in range(len(z["three_prime"])):
         tp, sl, anchor, lens, exp, n_throw = _exact_inputs(z, g)
         wl = z["whitelist"][g]
@@ -541,7 +547,11 @@ def test_exact_lookup_matches_reference_bytecode(orc):
 
 @pytest.mark.gpu
 def test_gpu_exact_lookup_matches_reference_bytecode(pkg, ctx):
-    z = np.load(os.path.join(GOLDEN, "ref_exact_lookup.npz"))
+    gpu_exact_lookup(pkg, ctx, EXACT_FILES[0])                     # the wide set runs from tests/test_zz_late_gpu.py
+
+
+def gpu_exact_lookup(pkg, ctx, fname):
+    z = np.load(os.path.join(GOLDEN, fname))
     for g in range(len(z["three_prime"])):
         tp, sl, anchor, lens, exp, n_throw = _exact_inputs(z, g)
         wl = z["whitelist"][g]

@@ -71,3 +71,8 @@ def test_gpu_cluster_one_myclustering_wide_set(pkg, ctx):
 @pytest.mark.gpu
 def test_gpu_cluster_local_wide_set(pkg, ctx):
     RV.gpu_cluster_local(pkg, ctx, RV.CLUSTER_LOCAL_FILES[1])
+
+
+@pytest.mark.gpu
+def test_gpu_exact_lookup_wide_set(pkg, ctx):
+    RV.gpu_exact_lookup(pkg, ctx, RV.EXACT_FILES[1])
